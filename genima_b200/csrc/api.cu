@@ -1,0 +1,147 @@
+// Handle lifecycle, error reporting and TMA descriptor construction for libgenima_b200.so.
+#include <stdarg.h>
+
+#include "common.h"
+
+namespace gn {
+
+int set_error(gn_handle* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_f16(gn_handle* h, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box) {
+  if (!h->encode_fn) return set_error(h, GN_ERR_NODRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
+  // cache key: raw bytes of every argument
+  std::string key;
+  key.reserve(8 + rank * 20);
+  key.append(reinterpret_cast<const char*>(&base), sizeof(base));
+  key.append(reinterpret_cast<const char*>(&rank), sizeof(rank));
+  key.append(reinterpret_cast<const char*>(dims), sizeof(uint64_t) * rank);
+  key.append(reinterpret_cast<const char*>(strides_bytes), sizeof(uint64_t) * (rank - 1));
+  key.append(reinterpret_cast<const char*>(box), sizeof(uint32_t) * rank);
+  auto it = h->tmap_cache.find(key);
+  if (it != h->tmap_cache.end()) {
+    *out = it->second;
+    return GN_OK;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0)
+    return set_error(h, GN_ERR_INVALID, "TMA base address %p is not 16-byte aligned", base);
+  cuuint64_t gdims[5];
+  cuuint64_t gstrides[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) return set_error(h, GN_ERR_INVALID, "TMA box[%d]=%u out of range", i, box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstrides[i] = strides_bytes[i];
+    if (strides_bytes[i] % 16 != 0)
+      return set_error(h, GN_ERR_INVALID, "TMA stride[%d]=%llu bytes is not a multiple of 16", i,
+                       (unsigned long long)strides_bytes[i]);
+  }
+  CUresult r = reinterpret_cast<EncodeTiledFn>(h->encode_fn)(
+      out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims, gstrides,
+      gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(h, GN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  if (h->tmap_cache.size() > 65536) h->tmap_cache.clear();
+  h->tmap_cache.emplace(std::move(key), *out);
+  return GN_OK;
+}
+
+}  // namespace gn
+
+extern "C" {
+
+const char* gn_version(void) { return "genima_b200 0.1 (sm_100a)"; }
+
+int gn_create(int device, gn_handle** out) {
+  if (!out) return GN_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return GN_ERR_NODRIVER;
+  }
+  if (device < 0 || device >= count) return GN_ERR_INVALID;
+  gn_handle* h = new (std::nothrow) gn_handle();
+  if (!h) return GN_ERR_NOMEM;
+  h->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete h;
+    return GN_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    delete h;
+    return GN_ERR_INVALID;  // sm_100a only: the kernels use tcgen05/TMEM
+  }
+  h->num_sms = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess) {
+    delete h;
+    return GN_ERR_CUDA;
+  }
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || !fn) {
+    cudaGetLastError();
+    delete h;
+    return GN_ERR_NODRIVER;
+  }
+  h->encode_fn = fn;
+  h->stats_scratch_bytes = 64 * 1024;
+  if (cudaMalloc(&h->stats_scratch, h->stats_scratch_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    delete h;
+    return GN_ERR_NOMEM;
+  }
+  *out = h;
+  return GN_OK;
+}
+
+int gn_destroy(gn_handle* h) {
+  if (h && h->stats_scratch) cudaFree(h->stats_scratch);
+  delete h;
+  return GN_OK;
+}
+
+const char* gn_last_error(const gn_handle* h) { return h ? h->err : "null handle"; }
+
+int gn_set_workspace(gn_handle* h, void* dptr, int64_t bytes) {
+  if (!h) return GN_ERR_INVALID;
+  h->workspace = dptr;
+  h->workspace_bytes = bytes;
+  return GN_OK;
+}
+
+int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits) {
+  if (!h) return GN_ERR_INVALID;
+  h->force_block_n = block_n;
+  h->force_splits = splits;
+  return GN_OK;
+}
+
+int gn_get_last_gemm_config(const gn_handle* h, int32_t* out4) {
+  if (!h || !out4) return GN_ERR_INVALID;
+  for (int i = 0; i < 4; ++i) out4[i] = h->last_cfg[i];
+  return GN_OK;
+}
+
+int64_t gn_launch_count(const gn_handle* h) { return h ? h->launches : -1; }
+
+}  // extern "C"

@@ -1,0 +1,653 @@
+// tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   out[M, N] = epilogue( sum_k A[m, k] * W[n, k] )        fp16 operands, fp32 accumulation in TMEM
+//
+// One CTA computes a 128 x block_n output tile (block_n chosen per problem, multiple of 16, <= 256):
+//   warp 0      TMA producer: A tile [128 rows][64 fp16] and W tile [block_n rows][64 fp16] per k-block,
+//               SWIZZLE_128B, multi-stage ring guarded by full/empty mbarriers
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 MMAs per k-block),
+//               tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5   epilogue: tcgen05.ld (one TMEM lane = one output row per thread) -> fused
+//               scale/bias/time-embedding/activation/residual/GEGLU -> fp16 stores
+//
+// The A operand is either a plain row-major matrix (2D tensor map) or an NHWC image addressed through 4D tensor
+// maps: k-blocks walk a table of "segments" (tap (dy, dx) x 64-channel blocks); TMA's zero OOB fill implements the
+// convolution padding, per-phase tensor maps implement stride 2, and extra 1x1 segments fuse ResnetBlock2D's
+// conv_shortcut into the same accumulation.  Split-K (gridDim.z) covers the weight-streaming-bound 8x8/16x16 levels.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace gn {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int MAX_SEGS = 52;
+constexpr int GEMM_THREADS = 192;
+
+struct KSeg {
+  int8_t map;  // index into tmA
+  int8_t dy;
+  int8_t dx;
+  int8_t _pad;
+  int32_t nblk;  // number of 64-channel k-blocks in this segment
+};
+
+struct EpiParams {
+  __half* out;
+  float* out32;
+  int64_t ldo;
+  const float* scale;
+  const float* bias;
+  const float* rowvec;
+  const __half* residual;
+  int64_t ldr;
+  int rows_per_batch;
+  int act_pre, act_post;
+  float alpha, beta;
+  int geglu;
+  int M, N;  // N = accumulator columns (before GEGLU halving)
+};
+
+struct GemmParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  EpiParams epi;
+  int num_kblocks;
+  int kb_per_split;
+  int splits;
+  int mode;  // 0: 2D A, 1: NHWC conv A
+  int num_segs;
+  int Ho, Wo, Bn;
+  int bw, bh, bb;
+  int tiles_w, tiles_h;
+  int block_n, stages, tmem_cols;
+  float* ws;  // split-K partials [splits][M][N] fp32
+  KSeg segs[MAX_SEGS];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case GN_ACT_SILU: return silu_f(v);
+    case GN_ACT_GELU: return gelu_erf_f(v);
+    case GN_ACT_RELU: return fmaxf(v, 0.0f);
+    case GN_ACT_QUICKGELU: return quick_gelu_f(v);
+    default: return v;
+  }
+}
+
+// v = act_pre(acc * scale[n] + bias[n] + rowvec[b, n])
+__device__ __forceinline__ float epi_pre(const EpiParams& e, float acc, int n, int b) {
+  float v = acc;
+  if (e.scale) v *= __ldg(e.scale + n);
+  if (e.bias) v += __ldg(e.bias + n);
+  if (e.rowvec) v += __ldg(e.rowvec + (int64_t)b * e.N + n);
+  return apply_act(v, e.act_pre);
+}
+
+// Finalise CH consecutive output columns [nout, nout + CH) of row m from pre-activation values v[].
+template <int CH>
+__device__ __forceinline__ void epi_store(const EpiParams& e, const float (&v)[CH], int m, int nout, int n_out_total) {
+  float o[CH];
+  const bool full = (nout + CH <= n_out_total);
+  if (e.residual) {
+    const __half* rp = e.residual + (int64_t)m * e.ldr + nout;
+    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 8) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
+        const __half2* hp = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 f = __half22float2(hp[t]);
+          o[j + 2 * t] = e.alpha * v[j + 2 * t] + e.beta * f.x;
+          o[j + 2 * t + 1] = e.alpha * v[j + 2 * t + 1] + e.beta * f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        float r = (nout + j < n_out_total) ? __half2float(rp[j]) : 0.0f;
+        o[j] = e.alpha * v[j] + e.beta * r;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) o[j] = e.alpha * v[j];
+  }
+  if (e.act_post != GN_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) o[j] = apply_act(o[j], e.act_post);
+  }
+  if (e.out32) {
+    float* op = e.out32 + (int64_t)m * e.ldo + nout;
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (nout + j < n_out_total) op[j] = o[j];
+    return;
+  }
+  __half* op = e.out + (int64_t)m * e.ldo + nout;
+  if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < CH; j += 8) {
+      uint4 q;
+      q.x = pack_half2(o[j], o[j + 1]);
+      q.y = pack_half2(o[j + 2], o[j + 3]);
+      q.z = pack_half2(o[j + 4], o[j + 5]);
+      q.w = pack_half2(o[j + 6], o[j + 7]);
+      *reinterpret_cast<uint4*>(op + j) = q;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CH; ++j)
+      if (nout + j < n_out_total) op[j] = __float2half_rn(o[j]);
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH]);
+template <>
+__device__ __forceinline__ void tmem_ld_chunk<32>(uint32_t taddr, uint32_t (&r)[32]) {
+  tmem_ld_x32(taddr, r);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_chunk<16>(uint32_t taddr, uint32_t (&r)[16]) {
+  tmem_ld_x16(taddr, r);
+}
+
+// Plain (non-GEGLU) epilogue of CH accumulator columns starting at tile column c.
+template <int CH>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, int c, int n0, int m, int b,
+                                               bool valid, int split) {
+  uint32_t r[CH];
+  tmem_ld_chunk<CH>(taddr + c, r);
+  tmem_ld_wait();
+  if (!valid) return;
+  const EpiParams& e = p.epi;
+  const int n = n0 + c;
+  if (n >= e.N) return;
+  if (p.splits > 1) {
+    float* wp = p.ws + ((int64_t)split * e.M + m) * e.N + n;
+    if (n + CH <= e.N && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 4)
+        *reinterpret_cast<uint4*>(wp + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (n + j < e.N) wp[j] = __uint_as_float(r[j]);
+    }
+    return;
+  }
+  float v[CH];
+#pragma unroll
+  for (int j = 0; j < CH; ++j) v[j] = (n + j < e.N) ? epi_pre(e, __uint_as_float(r[j]), n + j, b) : 0.0f;
+  epi_store<CH>(e, v, m, n, e.N);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.stages;
+  const int block_n = p.block_n;
+  const int b_stage_bytes = block_n * BLOCK_K * 2;
+
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + stages * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + stages * b_stage_bytes);
+  uint64_t* empty_bar = full_bar + stages;
+  uint64_t* tmem_full_bar = empty_bar + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n0 = blockIdx.x * block_n;
+  const int mt = blockIdx.y;
+  int m0 = 0, x0 = 0, y0 = 0, b0 = 0;
+  if (p.mode == 0) {
+    m0 = mt * BLOCK_M;
+  } else {
+    const int tw = mt % p.tiles_w;
+    const int th = (mt / p.tiles_w) % p.tiles_h;
+    const int tb = mt / (p.tiles_w * p.tiles_h);
+    x0 = tw * p.bw;
+    y0 = th * p.bh;
+    b0 = tb * p.bb;
+  }
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
+  const int num_it = kb_end - kb_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      int seg = 0, seg_start = 0;
+      if (p.mode == 1) {
+        while (kb_begin >= seg_start + p.segs[seg].nblk) {
+          seg_start += p.segs[seg].nblk;
+          ++seg;
+        }
+      }
+      int cb = kb_begin - seg_start;
+      const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
+      for (int it = 0; it < num_it; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (it / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        const int kb = kb_begin + it;
+        if (p.mode == 0) {
+          tma_load_2d(smem_a + s * A_STAGE_BYTES, &p.tmA[0], &full_bar[s], kb * BLOCK_K, m0);
+        } else {
+          const KSeg sg = p.segs[seg];
+          tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[sg.map], &full_bar[s], cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy,
+                      b0);
+          if (++cb == sg.nblk) {
+            cb = 0;
+            ++seg;
+          }
+        }
+        tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = umma_idesc_f16(block_n, 0, 0);
+      for (int it = 0; it < num_it; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (it / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES), 1024, 0);
+        const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * b_stage_bytes), 1024, 0);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+          umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue warps (2..5)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    int m;
+    bool valid;
+    if (p.mode == 0) {
+      m = m0 + row;
+      valid = m < p.epi.M;
+    } else {
+      const int x = row % p.bw;
+      const int y = (row / p.bw) % p.bh;
+      const int bb = row / (p.bw * p.bh);
+      const int gx = x0 + x, gy = y0 + y, gb = b0 + bb;
+      valid = (gx < p.Wo) && (gy < p.Ho) && (gb < p.Bn);
+      m = (gb * p.Ho + gy) * p.Wo + gx;
+    }
+    const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (p.epi.geglu) {
+      // columns come in 128-wide groups: [64 values | 64 gates]; out[m, j] = value * gelu(gate)
+      const EpiParams& e = p.epi;
+      const int n_out_total = e.N / 2;
+      for (int g = 0; g < block_n; g += 128) {
+#pragma unroll 1
+        for (int sub = 0; sub < 64; sub += 32) {
+          uint32_t rv[32], rg[32];
+          tmem_ld_x32(taddr + g + sub, rv);
+          tmem_ld_x32(taddr + g + 64 + sub, rg);
+          tmem_ld_wait();
+          const int n = n0 + g + sub;  // accumulator column of the value
+          if (!valid || n >= e.N) continue;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = epi_pre(e, __uint_as_float(rv[j]), n + j, b);
+            const float gt = epi_pre(e, __uint_as_float(rg[j]), n + 64 + j, b);
+            v[j] = a * gelu_erf_f(gt);
+          }
+          epi_store<32>(e, v, m, (n0 + g) / 2 + sub, n_out_total);
+        }
+      }
+    } else {
+      int c = 0;
+      for (; c + 32 <= block_n; c += 32) epilogue_chunk<32>(p, taddr, c, n0, m, b, valid, blockIdx.z);
+      if (c < block_n) epilogue_chunk<16>(p, taddr, c, n0, m, b, valid, blockIdx.z);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// Split-K second pass: sum the fp32 partials and run the same fused epilogue.  8 columns per thread.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(EpiParams e, const float* __restrict__ ws, int splits) {
+  const int cols8 = (e.N + 7) / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)e.M * cols8) return;
+  const int m = static_cast<int>(idx / cols8);
+  const int n = static_cast<int>(idx % cols8) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  const bool full = (n + 8 <= e.N) && ((e.N & 3) == 0);
+  for (int s = 0; s < splits; ++s) {
+    const float* wp = ws + ((int64_t)s * e.M + m) * e.N + n;
+    if (full) {
+      const float4 a = *reinterpret_cast<const float4*>(wp);
+      const float4 c = *reinterpret_cast<const float4*>(wp + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += c.z; acc[7] += c.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n + j < e.N) acc[j] += wp[j];
+    }
+  }
+  const int b = e.rowvec ? (m / e.rows_per_batch) : 0;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = (n + j < e.N) ? epi_pre(e, acc[j], n + j, b) : 0.0f;
+  epi_store<8>(e, v, m, n, e.N);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+struct TileChoice {
+  int block_n, splits, stages, tmem_cols;
+};
+
+static int smem_bytes_for(int block_n, int stages) {
+  return stages * (A_STAGE_BYTES + block_n * BLOCK_K * 2) + (2 * stages + 1) * 8 + 16 + 1024;
+}
+
+// Pick (block_n, splits) minimising a simple wave model of the kernel time.
+static TileChoice choose_tiles(const gn_handle* h, int tiles_m, int N, int num_kblocks, bool geglu, bool allow_split,
+                               int64_t ws_floats_per_split) {
+  static const int kCand[] = {256, 224, 192, 160, 128, 96, 80, 64, 48, 32, 16};
+  TileChoice best{128, 1, 4, 128};
+  double best_cost = 1e30;
+  const int sms = h->num_sms;
+  for (int bn : kCand) {
+    if (geglu && (bn % 128) != 0) continue;
+    if (h->force_block_n && bn != h->force_block_n) continue;
+    if (!h->force_block_n && bn > gn::round_up(N, 16)) continue;
+    const int tiles_n = gn::ceil_div(N, bn);
+    int max_splits = 1;
+    if (allow_split && !geglu) {
+      max_splits = num_kblocks / 4;  // keep >= 4 k-blocks per split
+      if (max_splits < 1) max_splits = 1;
+      if (max_splits > 32) max_splits = 32;
+      if (h->workspace_bytes <= 0) max_splits = 1;
+    }
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      if (h->force_splits && sp != h->force_splits && !(h->force_splits > max_splits && sp == max_splits)) continue;
+      if (sp > 1 && (int64_t)sp * ws_floats_per_split * 4 > h->workspace_bytes) break;
+      const int kb_per = gn::ceil_div(num_kblocks, sp);
+      if ((sp - 1) * kb_per >= num_kblocks) continue;  // an empty split
+      const int64_t ctas = (int64_t)tiles_m * tiles_n * sp;
+      const double waves = (double)((ctas + sms - 1) / sms);
+      // per k-block: tensor time 2*bn clk (128 x bn x 64 MACs @ 4096 MAC/clk) vs operand fetch at ~48 B/clk/SM
+      const double t_mma = 2.0 * bn;
+      const double t_ld = (A_STAGE_BYTES + bn * 128.0) / 48.0;
+      const double t_kb = t_mma > t_ld ? t_mma : t_ld;
+      double t_cta = kb_per * t_kb + 10.0 * bn + 3000.0;
+      double cost = waves * t_cta;
+      if (sp > 1) cost += 2500.0 + (double)ws_floats_per_split * sp * 8.0 / (sms * 40.0);
+      if (cost < best_cost) {
+        best_cost = cost;
+        best.block_n = bn;
+        best.splits = sp;
+      }
+    }
+  }
+  int tm = 32;
+  while (tm < best.block_n) tm <<= 1;
+  best.tmem_cols = tm;
+  int st = 8;
+  while (st > 2 && smem_bytes_for(best.block_n, st) > 200 * 1024) --st;
+  const int kb_per = gn::ceil_div(num_kblocks, best.splits);
+  if (st > kb_per) st = kb_per < 2 ? 2 : kb_per;
+  best.stages = st;
+  return best;
+}
+
+static int fill_epilogue(gn_handle* h, EpiParams& e, const gn_epilogue* epi, void* out, int64_t ldo, int M, int N,
+                         int default_rows_per_batch) {
+  memset(&e, 0, sizeof(e));
+  e.M = M;
+  e.N = N;
+  e.ldo = ldo;
+  e.alpha = 1.0f;
+  e.beta = 1.0f;
+  e.rows_per_batch = default_rows_per_batch > 0 ? default_rows_per_batch : M;
+  e.out = static_cast<__half*>(out);
+  if (epi) {
+    e.scale = epi->scale;
+    e.bias = epi->bias;
+    e.rowvec = epi->rowvec;
+    e.residual = static_cast<const __half*>(epi->residual);
+    e.ldr = epi->ldr;
+    if (epi->rows_per_batch > 0) e.rows_per_batch = epi->rows_per_batch;
+    e.act_pre = epi->act_pre;
+    e.act_post = epi->act_post;
+    e.alpha = epi->alpha;
+    e.beta = epi->beta;
+    e.geglu = epi->geglu;
+    if (epi->out_fp32) {
+      e.out32 = static_cast<float*>(out);
+      e.out = nullptr;
+    }
+    GN_CHECK_ARG(h, epi->gn_stats == nullptr, "gn_epilogue.gn_stats is not supported by this build");
+    GN_CHECK_ARG(h, !(epi->geglu && (N % 128) != 0), "GEGLU needs N %% 128 == 0 (got %d)", N);
+    GN_CHECK_ARG(h, !(epi->residual && epi->ldr <= 0), "residual given without ldr");
+  }
+  return GN_OK;
+}
+
+static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, int64_t ktot, bool allow_split,
+                       cudaStream_t stream) {
+  const int N = p.epi.N;
+  const int M = p.epi.M;
+  TileChoice tc = choose_tiles(h, tiles_m, N, p.num_kblocks, p.epi.geglu != 0, allow_split, (int64_t)M * N);
+  p.block_n = tc.block_n;
+  p.splits = tc.splits;
+  p.stages = tc.stages;
+  p.tmem_cols = tc.tmem_cols;
+  p.kb_per_split = gn::ceil_div(p.num_kblocks, tc.splits);
+  p.ws = static_cast<float*>(h->workspace);
+
+  // weight tensor map: [N rows][ktot] fp16, box {64, block_n}
+  {
+    uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)ktot * 2};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)tc.block_n};
+    int rc = make_tmap_f16(h, &p.tmB, W, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  const int smem = smem_bytes_for(tc.block_n, tc.stages);
+  if (!h->gemm_attr_set) {
+    GN_CHECK_CUDA(h, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    h->gemm_attr_set = true;
+  }
+  dim3 grid(gn::ceil_div(N, tc.block_n), tiles_m, tc.splits);
+  gemm_tc_kernel<<<grid, GEMM_THREADS, smem, stream>>>(p);
+  GN_CHECK_LAUNCH(h);
+  if (tc.splits > 1) {
+    const int cols8 = (N + 7) / 8;
+    const int64_t total = (int64_t)M * cols8;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(p.epi, p.ws, tc.splits);
+    GN_CHECK_LAUNCH(h);
+  }
+  h->last_cfg[0] = tc.block_n;
+  h->last_cfg[1] = tc.splits;
+  h->last_cfg[2] = tc.stages;
+  h->last_cfg[3] = (int)(grid.x * grid.y * grid.z);
+  return GN_OK;
+}
+
+}  // namespace gn
+
+using namespace gn;
+
+extern "C" int gn_linear(gn_handle* h, const void* A, int64_t lda, int M, int K, const void* W, int N, void* out,
+                         int64_t ldo, const gn_epilogue* epi, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  GN_CHECK_ARG(h, A && W && out, "gn_linear: null pointer");
+  GN_CHECK_ARG(h, M > 0 && N > 0 && K > 0, "gn_linear: bad shape M=%d N=%d K=%d", M, N, K);
+  GN_CHECK_ARG(h, (K % 8) == 0 && (lda % 8) == 0, "gn_linear: K (%d) and lda (%lld) must be multiples of 8", K,
+               (long long)lda);
+  static thread_local GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_epilogue(h, p.epi, epi, out, ldo, M, N, M);
+  if (rc) return rc;
+  p.mode = 0;
+  p.num_kblocks = ceil_div(K, BLOCK_K);
+  p.num_segs = 1;
+  p.segs[0].nblk = p.num_kblocks;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {BLOCK_K, BLOCK_M};
+    rc = make_tmap_f16(h, &p.tmA[0], A, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return launch_gemm(h, p, ceil_div(M, BLOCK_M), W, K, /*allow_split=*/true, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C, const void* w, int Cout, int KH,
+                         int KW, int stride, int pad, const void* ex0, int C_ex0, const void* ex1, int C_ex1,
+                         void* out, int64_t ldo, const gn_epilogue* epi, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  GN_CHECK_ARG(h, x && w && out, "gn_conv2d: null pointer");
+  GN_CHECK_ARG(h, B > 0 && H > 0 && W > 0 && C > 0 && Cout > 0, "gn_conv2d: bad shape");
+  GN_CHECK_ARG(h, (C % 8) == 0, "gn_conv2d: C (%d) must be a multiple of 8", C);
+  GN_CHECK_ARG(h, stride == 1 || stride == 2, "gn_conv2d: stride %d unsupported", stride);
+  GN_CHECK_ARG(h, KH * KW + 2 <= MAX_SEGS, "gn_conv2d: %dx%d kernel too large", KH, KW);
+  GN_CHECK_ARG(h, stride == 1 || ((H % 2) == 0 && (W % 2) == 0), "gn_conv2d: stride 2 needs even H, W");
+  const int Ho = (H + 2 * pad - KH) / stride + 1;
+  const int Wo = (W + 2 * pad - KW) / stride + 1;
+  GN_CHECK_ARG(h, Ho > 0 && Wo > 0, "gn_conv2d: empty output");
+  const int M = B * Ho * Wo;
+
+  static thread_local GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_epilogue(h, p.epi, epi, out, ldo, M, Cout, Ho * Wo);
+  if (rc) return rc;
+  p.mode = 1;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.Bn = B;
+  // 128 output pixels per tile as a (bw x bh x bb) box of powers of two; parts of the box beyond the image are
+  // zero-filled by TMA and masked in the epilogue.
+  auto pow2_ceil = [](int v) {
+    int r = 1;
+    while (r < v) r <<= 1;
+    return r;
+  };
+  int bw = pow2_ceil(Wo);
+  if (bw > 128) bw = 128;
+  int bh = pow2_ceil(Ho);
+  if (bh > 128 / bw) bh = 128 / bw;
+  const int bb = 128 / (bw * bh);
+  p.bw = bw;
+  p.bh = bh;
+  p.bb = bb;
+  p.tiles_w = ceil_div(Wo, bw);
+  p.tiles_h = ceil_div(Ho, bh);
+  const int tiles_b = ceil_div(B, bb);
+  const int tiles_m = p.tiles_w * p.tiles_h * tiles_b;
+
+  const int Cp = round_up(C, BLOCK_K);
+  const int cblk = Cp / BLOCK_K;
+  int nseg = 0;
+  int nmaps = 0;
+  if (stride == 1) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    rc = make_tmap_f16(h, &p.tmA[0], x, 4, dims, strides, box);
+    if (rc) return rc;
+    nmaps = 1;
+    for (int ky = 0; ky < KH; ++ky)
+      for (int kx = 0; kx < KW; ++kx) {
+        p.segs[nseg].map = 0;
+        p.segs[nseg].dy = (int8_t)(ky - pad);
+        p.segs[nseg].dx = (int8_t)(kx - pad);
+        p.segs[nseg].nblk = cblk;
+        ++nseg;
+      }
+  } else {
+    // stride 2: input pixel (2i + ky - pad, 2j + kx - pad) lives in phase plane (py, px) at (i + oy, j + ox)
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const __half* base = static_cast<const __half*>(x) + ((int64_t)py * W + px) * C;
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)(W / 2), (uint64_t)(H / 2), (uint64_t)B};
+        uint64_t strides[3] = {(uint64_t)2 * C * 2, (uint64_t)2 * W * C * 2, (uint64_t)H * W * C * 2};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+        rc = make_tmap_f16(h, &p.tmA[py * 2 + px], base, 4, dims, strides, box);
+        if (rc) return rc;
+      }
+    nmaps = 4;
+    for (int ky = 0; ky < KH; ++ky)
+      for (int kx = 0; kx < KW; ++kx) {
+        const int oy = ky - pad, ox = kx - pad;
+        const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
+        p.segs[nseg].map = (int8_t)(py * 2 + px);
+        p.segs[nseg].dy = (int8_t)((oy - py) / 2);
+        p.segs[nseg].dx = (int8_t)((ox - px) / 2);
+        p.segs[nseg].nblk = cblk;
+        ++nseg;
+      }
+  }
+  int64_t ktot = (int64_t)KH * KW * Cp;
+  const void* exs[2] = {ex0, ex1};
+  const int exc[2] = {C_ex0, C_ex1};
+  for (int i = 0; i < 2; ++i) {
+    if (!exs[i]) continue;
+    GN_CHECK_ARG(h, nmaps < 4, "gn_conv2d: extra 1x1 sources are not supported together with stride 2");
+    GN_CHECK_ARG(h, exc[i] > 0 && (exc[i] % 8) == 0, "gn_conv2d: extra source channels must be a multiple of 8");
+    uint64_t dims[4] = {(uint64_t)exc[i], (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)exc[i] * 2, (uint64_t)Wo * exc[i] * 2, (uint64_t)Ho * Wo * exc[i] * 2};
+    uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    rc = make_tmap_f16(h, &p.tmA[nmaps], exs[i], 4, dims, strides, box);
+    if (rc) return rc;
+    const int ecp = round_up(exc[i], BLOCK_K);
+    p.segs[nseg].map = (int8_t)nmaps;
+    p.segs[nseg].dy = 0;
+    p.segs[nseg].dx = 0;
+    p.segs[nseg].nblk = ecp / BLOCK_K;
+    ++nseg;
+    ++nmaps;
+    ktot += ecp;
+  }
+  p.num_segs = nseg;
+  p.num_kblocks = (int)(ktot / BLOCK_K);
+  return launch_gemm(h, p, tiles_m, w, ktot, /*allow_split=*/true, static_cast<cudaStream_t>(stream));
+}

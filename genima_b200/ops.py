@@ -1,0 +1,371 @@
+"""Thin tensor-level wrappers over the C ABI (genima_b200._cabi).
+
+torch is used for device memory and streams only; every arithmetic op below is one call into libgenima_b200.so on
+`torch.cuda.current_stream()`, so a chain of calls can be captured with `torch.cuda.graph`.
+
+Layout convention: activations are fp16, channels-last.  An image is a contiguous [B, H, W, C] tensor, which is also
+the row-major [B*H*W, C] matrix the GEMM kernels see.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import ACT_GELU, ACT_NONE, ACT_QUICKGELU, ACT_RELU, ACT_SILU, GnEpilogue  # noqa: F401
+
+_ACTS = {None: ACT_NONE, "none": ACT_NONE, "silu": ACT_SILU, "gelu": ACT_GELU, "relu": ACT_RELU,
+         "quick_gelu": ACT_QUICKGELU}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f16(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float16 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA float16 tensor, got {t.dtype} on {t.device}")
+    return t
+
+
+def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise TypeError(f"{name}: expected a contiguous CUDA float32 tensor")
+    return t
+
+
+class Ops:
+    """One instance per device; owns the gn_handle and the split-K workspace."""
+
+    def __init__(self, device: int = 0, workspace_mb: int = 64):
+        if not torch.cuda.is_available():
+            raise _cabi.GenimaB200Error("CUDA is not available: genima_b200 has no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.handle = _cabi.Handle(device)
+        self.lib = self.handle.lib
+        self.h = self.handle.ptr
+        self.workspace = torch.empty(workspace_mb * 1024 * 1024 // 4, dtype=torch.float32, device=self.device)
+        self.handle.check(self.lib.gn_set_workspace(self.h, self.workspace.data_ptr(), self.workspace.numel() * 4),
+                          "gn_set_workspace")
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def _epilogue(self, M: int, N: int, bias=None, scale=None, rowvec=None, rows_per_batch: int = 0, residual=None,
+                  act_pre=None, act_post=None, alpha: float = 1.0, beta: float = 1.0, geglu: bool = False,
+                  out_fp32: bool = False) -> GnEpilogue:
+        e = GnEpilogue()
+        e.scale = _ptr(_f32(scale, "scale"))
+        e.bias = _ptr(_f32(bias, "bias"))
+        e.rowvec = _ptr(_f32(rowvec, "rowvec"))
+        if bias is not None and bias.numel() != N:
+            raise ValueError(f"bias has {bias.numel()} elements, expected {N}")
+        if scale is not None and scale.numel() != N:
+            raise ValueError(f"scale has {scale.numel()} elements, expected {N}")
+        if rowvec is not None:
+            if rowvec.shape[-1] != N or rows_per_batch <= 0:
+                raise ValueError("rowvec needs shape [B, N] and rows_per_batch > 0")
+        n_out = N // 2 if geglu else N
+        if residual is not None:
+            _f16(residual, "residual")
+            r2 = residual.reshape(-1, residual.shape[-1])
+            if r2.shape[0] != M or r2.shape[1] < n_out or r2.stride(1) != 1:
+                raise ValueError(f"residual shape {tuple(residual.shape)} does not match output [{M}, {n_out}]")
+            e.residual = r2.data_ptr()
+            e.ldr = r2.stride(0)
+        e.rows_per_batch = rows_per_batch
+        e.act_pre = _ACTS[act_pre]
+        e.act_post = _ACTS[act_post]
+        e.alpha = alpha
+        e.beta = beta
+        e.geglu = 1 if geglu else 0
+        e.out_fp32 = 1 if out_fp32 else 0
+        return e
+
+    def set_gemm_tuning(self, block_n: int = 0, splits: int = 0) -> None:
+        self.handle.check(self.lib.gn_set_gemm_tuning(self.h, block_n, splits), "gn_set_gemm_tuning")
+
+    def last_gemm_config(self) -> Tuple[int, int, int, int]:
+        out = (C.c_int32 * 4)()
+        self.lib.gn_get_last_gemm_config(self.h, out)
+        return tuple(out)
+
+    def launch_count(self) -> int:
+        return self.handle.launch_count()
+
+    # ------------------------------------------------------------------------------------------------ contractions
+    def linear(self, a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, **epi) -> torch.Tensor:
+        """out[..., N'] = epilogue(a[..., K] @ w[N, K]^T); N' = N/2 with geglu=True."""
+        _f16(a, "a")
+        _f16(w, "w")
+        K = a.shape[-1]
+        a2 = a.reshape(-1, K)
+        if a2.stride(1) != 1:
+            a2 = a2.contiguous()
+        M = a2.shape[0]
+        N = w.shape[0]
+        if w.shape[1] != K or not w.is_contiguous():
+            raise ValueError(f"w must be contiguous [N, K={K}], got {tuple(w.shape)}")
+        n_out = N // 2 if epi.get("geglu") else N
+        out_dtype = torch.float32 if epi.get("out_fp32") else torch.float16
+        if out is None:
+            out = torch.empty(*a.shape[:-1], n_out, dtype=out_dtype, device=a.device)
+        o2 = out.reshape(-1, out.shape[-1])
+        if o2.shape[0] != M or o2.shape[1] < n_out or o2.stride(1) != 1 or out.dtype != out_dtype:
+            raise ValueError("bad `out` tensor for linear")
+        e = self._epilogue(M, N, **epi)
+        rc = self.lib.gn_linear(self.h, a2.data_ptr(), a2.stride(0), M, K, w.data_ptr(), N, o2.data_ptr(),
+                                o2.stride(0), C.byref(e), self._stream())
+        self.handle.check(rc, "gn_linear")
+        return out
+
+    def conv2d(self, x: torch.Tensor, w: torch.Tensor, cout: int, ksize: int = 3, stride: int = 1, pad: int = 1,
+               extras: Sequence[torch.Tensor] = (), out: Optional[torch.Tensor] = None, **epi) -> torch.Tensor:
+        """NHWC implicit-GEMM convolution.  `w` is packed by packing.pack_conv_weight ([Cout, K_total])."""
+        _f16(x, "x")
+        _f16(w, "w")
+        if x.dim() != 4 or not x.is_contiguous():
+            raise ValueError("x must be a contiguous [B, H, W, C] tensor")
+        B, H, W, Cin = x.shape
+        Ho = (H + 2 * pad - ksize) // stride + 1
+        Wo = (W + 2 * pad - ksize) // stride + 1
+        cp = (Cin + 63) // 64 * 64
+        ktot = ksize * ksize * cp
+        ex = [None, None]
+        exc = [0, 0]
+        for i, t in enumerate(extras):
+            _f16(t, "extra")
+            if t.dim() != 4 or not t.is_contiguous() or t.shape[:3] != (B, Ho, Wo):
+                raise ValueError("extra source must be contiguous [B, Ho, Wo, C]")
+            ex[i] = t.data_ptr()
+            exc[i] = t.shape[3]
+            ktot += (t.shape[3] + 63) // 64 * 64
+        if tuple(w.shape) != (cout, ktot) or not w.is_contiguous():
+            raise ValueError(f"packed conv weight must be [{cout}, {ktot}], got {tuple(w.shape)}")
+        out_dtype = torch.float32 if epi.get("out_fp32") else torch.float16
+        if out is None:
+            out = torch.empty(B, Ho, Wo, cout, dtype=out_dtype, device=x.device)
+        if out.shape[:3] != (B, Ho, Wo) or out.shape[3] < cout or out.stride(3) != 1 or out.dtype != out_dtype:
+            raise ValueError("bad `out` tensor for conv2d")
+        if out.stride(2) * Wo != out.stride(1) or out.stride(1) * Ho != out.stride(0):
+            raise ValueError("`out` must be pixel-contiguous")
+        M = B * Ho * Wo
+        epi.setdefault("rows_per_batch", Ho * Wo)
+        e = self._epilogue(M, cout, **epi)
+        rc = self.lib.gn_conv2d(self.h, x.data_ptr(), B, H, W, Cin, w.data_ptr(), cout, ksize, ksize, stride, pad,
+                                ex[0], exc[0], ex[1], exc[1], out.data_ptr(), out.stride(2), C.byref(e),
+                                self._stream())
+        self.handle.check(rc, "gn_conv2d")
+        return out
+
+    # ------------------------------------------------------------------------------------------------ attention
+    def attention(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, Tq: int, Tk: int,
+                  scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tcgen05 flash attention, head_dim 64.  q/k/v are 2D row views (last-dim stride 1) with heads*64 columns."""
+        for name, t in (("q", q), ("k", k), ("v", v)):
+            _f16(t, name)
+            if t.dim() != 2 or t.stride(1) != 1 or t.shape[1] != heads * 64:
+                raise ValueError(f"{name} must be a 2D view with {heads * 64} unit-stride columns")
+        if q.shape[0] != B * Tq or k.shape[0] != B * Tk or v.shape[0] != B * Tk:
+            raise ValueError("row counts do not match B*Tq / B*Tk")
+        if out is None:
+            out = torch.empty(B * Tq, heads * 64, dtype=torch.float16, device=q.device)
+        rc = self.lib.gn_attention(self.h, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                   v.stride(0), out.data_ptr(), out.stride(0), B, heads, Tq, Tk, float(scale),
+                                   self._stream())
+        self.handle.check(rc, "gn_attention")
+        return out
+
+    def attention_small(self, q, k, v, B: int, heads: int, head_dim: int, Tq: int, Tk: int, scale: float,
+                        causal: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        for name, t in (("q", q), ("k", k), ("v", v)):
+            _f16(t, name)
+            if t.dim() != 2 or t.stride(1) != 1 or t.shape[1] != heads * head_dim:
+                raise ValueError(f"{name} must be a 2D view with {heads * head_dim} unit-stride columns")
+        if out is None:
+            out = torch.empty(B * Tq, heads * head_dim, dtype=torch.float16, device=q.device)
+        rc = self.lib.gn_attention_small(self.h, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                         v.stride(0), out.data_ptr(), out.stride(0), B, heads, head_dim, Tq, Tk,
+                                         float(scale), 1 if causal else 0, self._stream())
+        self.handle.check(rc, "gn_attention_small")
+        return out
+
+    # ------------------------------------------------------------------------------------------------ normalisation
+    def group_norm(self, x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32,
+                   eps: float = 1e-5, silu: bool = False, x1: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """GroupNorm(+SiLU) over NHWC; with x1 the input is concat([x0, x1], channel) without materialising it."""
+        _f16(x0, "x0")
+        if not x0.is_contiguous():
+            raise ValueError("x0 must be contiguous NHWC")
+        B = x0.shape[0]
+        C0 = x0.shape[-1]
+        HW = x0.numel() // (B * C0)
+        C1 = 0
+        if x1 is not None:
+            _f16(x1, "x1")
+            if not x1.is_contiguous() or x1.shape[:-1] != x0.shape[:-1]:
+                raise ValueError("x1 must be contiguous and match x0's spatial shape")
+            C1 = x1.shape[-1]
+        _f32(gamma, "gamma")
+        _f32(beta, "beta")
+        if gamma.numel() != C0 + C1 or beta.numel() != C0 + C1:
+            raise ValueError("gamma/beta size mismatch")
+        if out is None:
+            out = torch.empty(*x0.shape[:-1], C0 + C1, dtype=torch.float16, device=x0.device)
+        rc = self.lib.gn_group_norm(self.h, x0.data_ptr(), C0, _ptr(x1), C1, B, HW, groups, float(eps),
+                                    gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, None, out.data_ptr(),
+                                    self._stream())
+        self.handle.check(rc, "gn_group_norm")
+        return out
+
+    def layer_norm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _f16(x, "x")
+        Cn = x.shape[-1]
+        x2 = x.reshape(-1, Cn)
+        if x2.stride(1) != 1:
+            raise ValueError("x must have unit stride in the last dim")
+        if out is None:
+            out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+        o2 = out.reshape(-1, Cn)
+        rc = self.lib.gn_layer_norm(self.h, x2.data_ptr(), x2.stride(0), x2.shape[0], Cn, float(eps),
+                                    _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(), o2.data_ptr(),
+                                    o2.stride(0), self._stream())
+        self.handle.check(rc, "gn_layer_norm")
+        return out
+
+    def softmax_rows_(self, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        _f16(x, "x")
+        if x.dim() != 2 or x.stride(1) != 1:
+            raise ValueError("x must be 2D with unit column stride")
+        rc = self.lib.gn_softmax_rows(self.h, x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], float(scale),
+                                      self._stream())
+        self.handle.check(rc, "gn_softmax_rows")
+        return x
+
+    # ------------------------------------------------------------------------------------------------ elementwise
+    def upsample_nearest2x(self, x: torch.Tensor) -> torch.Tensor:
+        _f16(x, "x")
+        B, H, W, Cn = x.shape
+        y = torch.empty(B, 2 * H, 2 * W, Cn, dtype=torch.float16, device=x.device)
+        self.handle.check(self.lib.gn_upsample_nearest2x(self.h, x.data_ptr(), B, H, W, Cn, y.data_ptr(),
+                                                         self._stream()), "gn_upsample_nearest2x")
+        return y
+
+    def maxpool3x3s2(self, x: torch.Tensor) -> torch.Tensor:
+        _f16(x, "x")
+        B, H, W, Cn = x.shape
+        y = torch.empty(B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cn, dtype=torch.float16, device=x.device)
+        self.handle.check(self.lib.gn_maxpool3x3s2(self.h, x.data_ptr(), B, H, W, Cn, y.data_ptr(), self._stream()),
+                          "gn_maxpool3x3s2")
+        return y
+
+    def add(self, a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _f16(a, "a")
+        _f16(b, "b")
+        if a.shape != b.shape or not a.is_contiguous() or not b.is_contiguous():
+            raise ValueError("add: shapes must match and be contiguous")
+        if out is None:
+            out = torch.empty_like(a)
+        self.handle.check(self.lib.gn_add(self.h, a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(),
+                                          self._stream()), "gn_add")
+        return out
+
+    def scale(self, x: torch.Tensor, s: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _f16(x, "x")
+        if out is None:
+            out = torch.empty_like(x)
+        self.handle.check(self.lib.gn_scale(self.h, x.data_ptr(), float(s), out.data_ptr(), x.numel(),
+                                            self._stream()), "gn_scale")
+        return out
+
+    def timestep_embedding(self, t: float, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(1, dim, dtype=torch.float16, device=self.device)
+        self.handle.check(self.lib.gn_timestep_embedding(self.h, float(t), dim, out.data_ptr(), self._stream()),
+                          "gn_timestep_embedding")
+        return out
+
+    def euler_step(self, x: torch.Tensor, eps: torch.Tensor, sigma: float, sigma_next: float,
+                   x_next: Optional[torch.Tensor] = None, x_scaled: Optional[torch.Tensor] = None):
+        _f16(x, "x")
+        _f16(eps, "eps")
+        if x_next is None:
+            x_next = torch.empty_like(x)
+        rc = self.lib.gn_euler_step(self.h, x.data_ptr(), eps.data_ptr(), float(sigma), float(sigma_next),
+                                    x_next.data_ptr(), _ptr(x_scaled), x.numel(), self._stream())
+        self.handle.check(rc, "gn_euler_step")
+        return x_next, x_scaled
+
+    def nchw_to_nhwc(self, src: torch.Tensor, cpad: Optional[int] = None) -> torch.Tensor:
+        if not src.is_cuda or not src.is_contiguous() or src.dtype not in (torch.float16, torch.float32):
+            raise TypeError("nchw_to_nhwc: contiguous CUDA fp16/fp32 tensor expected")
+        B, Cn, H, W = src.shape
+        cpad = cpad or Cn
+        dst = torch.empty(B, H, W, cpad, dtype=torch.float16, device=src.device)
+        rc = self.lib.gn_nchw_to_nhwc(self.h, src.data_ptr(), 1 if src.dtype == torch.float32 else 0, B, Cn, H, W,
+                                      cpad, dst.data_ptr(), self._stream())
+        self.handle.check(rc, "gn_nchw_to_nhwc")
+        return dst
+
+    def nhwc_to_nchw(self, src: torch.Tensor, channels: Optional[int] = None, fp32: bool = False) -> torch.Tensor:
+        _f16(src, "src")
+        B, H, W, cpad = src.shape
+        Cn = channels or cpad
+        dst = torch.empty(B, Cn, H, W, dtype=torch.float32 if fp32 else torch.float16, device=src.device)
+        rc = self.lib.gn_nhwc_to_nchw(self.h, src.data_ptr(), B, Cn, H, W, cpad, dst.data_ptr(), 1 if fp32 else 0,
+                                      self._stream())
+        self.handle.check(rc, "gn_nhwc_to_nchw")
+        return dst
+
+    def u8_to_nhwc(self, src: torch.Tensor, cpad: int = 64, mean=None, std=None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if src.dtype != torch.uint8 or not src.is_cuda or not src.is_contiguous() or src.shape[-1] != 3:
+            raise TypeError("u8_to_nhwc: contiguous CUDA uint8 [B, H, W, 3] expected")
+        B, H, W, _ = src.shape
+        if out is None:
+            out = torch.empty(B, H, W, cpad, dtype=torch.float16, device=src.device)
+        m = (C.c_float * 3)(*mean) if mean is not None else None
+        s = (C.c_float * 3)(*std) if std is not None else None
+        rc = self.lib.gn_u8_to_nhwc(self.h, src.data_ptr(), B, H, W, cpad, m, s, out.data_ptr(), self._stream())
+        self.handle.check(rc, "gn_u8_to_nhwc")
+        return out
+
+    def nhwc_to_u8(self, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        _f16(src, "src")
+        B, H, W, cpad = src.shape
+        if out is None:
+            out = torch.empty(B, H, W, 3, dtype=torch.uint8, device=src.device)
+        rc = self.lib.gn_nhwc_to_u8(self.h, src.data_ptr(), B, H, W, cpad, out.data_ptr(), self._stream())
+        self.handle.check(rc, "gn_nhwc_to_u8")
+        return out
+
+    def tile_views(self, views: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[B, 4, 256, 256, 3] u8 -> [B, 512, 512, 3] u8 (controller/utils/misc.py:6-19)."""
+        if views.dtype != torch.uint8 or not views.is_cuda or tuple(views.shape[1:]) != (4, 256, 256, 3):
+            raise TypeError("tile_views: CUDA uint8 [B, 4, 256, 256, 3] expected")
+        B = views.shape[0]
+        if out is None:
+            out = torch.empty(B, 512, 512, 3, dtype=torch.uint8, device=views.device)
+        self.handle.check(self.lib.gn_tile_views(self.h, views.contiguous().data_ptr(), B, out.data_ptr(),
+                                                 self._stream()), "gn_tile_views")
+        return out
+
+    def untile_views(self, tile: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """[B, 512, 512, 3] u8 -> [B, 4, 256, 256, 3] u8 (controller/utils/misc.py:22-47)."""
+        if tile.dtype != torch.uint8 or not tile.is_cuda or tuple(tile.shape[1:]) != (512, 512, 3):
+            raise TypeError("untile_views: CUDA uint8 [B, 512, 512, 3] expected")
+        B = tile.shape[0]
+        if out is None:
+            out = torch.empty(B, 4, 256, 256, 3, dtype=torch.uint8, device=tile.device)
+        self.handle.check(self.lib.gn_untile_views(self.h, tile.contiguous().data_ptr(), B, out.data_ptr(),
+                                                   self._stream()), "gn_untile_views")
+        return out

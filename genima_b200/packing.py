@@ -1,0 +1,73 @@
+"""One-time weight re-layouts from the upstream (diffusers / torchvision / RoboBase) state-dict layout to the layouts the
+sm_100a kernels consume.  Pure data movement, run once at bind time — never on the per-step path.
+
+  conv  [Cout, Cin, KH, KW]  ->  [Cout, KH*KW*Cp (+ Cp_extra...)]   tap-major, channels padded to 64 (zeros)
+  GEGLU [2*D, K] (value rows, then gate rows) -> 64-row interleaved (value, gate) blocks
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = (), cin_layout: Sequence[int] = ()) -> torch.Tensor:
+    """w: [Cout, Cin, KH, KW]; extras: 1x1 shortcut weights [Cout, Ce(,1,1)] appended along K.
+
+    cin_layout: when the activation tensor carries padded channels in several segments (e.g. a concat of two padded
+    tensors) give the (real, padded) pairs flattened: (r0, p0, r1, p1, ...); default = one segment padded to 64.
+    """
+    cout, cin, kh, kw = w.shape
+    w = w.to(torch.float16)
+    taps = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)  # [Cout, taps, Cin]
+    if cin_layout:
+        segs = []
+        off = 0
+        for i in range(0, len(cin_layout), 2):
+            real, padded = cin_layout[i], cin_layout[i + 1]
+            seg = taps[:, :, off:off + real]
+            if padded > real:
+                seg = torch.nn.functional.pad(seg, (0, padded - real))
+            segs.append(seg)
+            off += real
+        assert off == cin, (off, cin)
+        taps = torch.cat(segs, dim=2)
+    cp = round_up(taps.shape[2], 64)
+    if cp > taps.shape[2]:
+        taps = torch.nn.functional.pad(taps, (0, cp - taps.shape[2]))
+    parts = [taps.reshape(cout, kh * kw * cp)]
+    for e in extras:
+        e = e.to(torch.float16).reshape(cout, -1)
+        ep = round_up(e.shape[1], 64)
+        if ep > e.shape[1]:
+            e = torch.nn.functional.pad(e, (0, ep - e.shape[1]))
+        parts.append(e)
+    return torch.cat(parts, dim=1).contiguous()
+
+
+def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor):
+    """diffusers GEGLU: proj = Linear(K, 2D); hidden, gate = proj(x).chunk(2, -1); out = hidden * gelu(gate).
+    Re-order rows into 64-wide (value, gate) blocks so one 128-column accumulator group holds matching pairs."""
+    two_d, k = w.shape
+    d = two_d // 2
+    assert d % 64 == 0, d
+    wv = w[:d].reshape(d // 64, 64, k)
+    wg = w[d:].reshape(d // 64, 64, k)
+    wp = torch.stack([wv, wg], dim=1).reshape(two_d, k).contiguous()
+    bv = b[:d].reshape(d // 64, 64)
+    bg = b[d:].reshape(d // 64, 64)
+    bp = torch.stack([bv, bg], dim=1).reshape(two_d).contiguous()
+    return wp, bp
+
+
+def pad_cols(w: torch.Tensor, mult: int = 8) -> torch.Tensor:
+    """Pad the K (last) dim of a linear weight with zeros to a multiple of `mult`."""
+    k = w.shape[-1]
+    kp = round_up(k, mult)
+    if kp == k:
+        return w.contiguous()
+    return torch.nn.functional.pad(w, (0, kp - k)).contiguous()

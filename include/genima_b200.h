@@ -1,0 +1,152 @@
+/*
+ * genima_b200 — C ABI of the B200-native (sm_100a) kernels behind Genima's per-step inference hot path.
+ *
+ * The reference (MohitShridhar/genima) has no FFI of its own: its hot path is two Python calls,
+ *   controller/agent/sd_controlnet_agent.py:67-76   SDControlNetAgent.infer -> diffusers pipe(...)
+ *   controller/method/genima_act.py:165-214          GenimaACTPolicy.forward
+ * whose arithmetic runs inside diffusers 0.29.0 / RoboBase / torchvision library kernels (cuDNN, cuBLAS,
+ * xformers).  Each entry point below replaces one class of those library kernels; the Python
+ * shims in genima_b200/ (pipeline.py, act_policy.py) keep the reference call signatures and call ONLY these.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative gn_status otherwise; nothing throws across the ABI;
+ *    gn_last_error(h) returns a human-readable message for the last failure on that handle.
+ *  - all tensor arguments are DEVICE pointers owned by the caller (torch allocates them); activations are
+ *    fp16, channels-last: images are NHWC = a row-major [B*H*W, C] matrix, token sequences are [B*T, C].
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, no hidden sync, so a call
+ *    chain can be captured into a CUDA graph.
+ *  - one handle per (device, host thread); not re-entrant.
+ */
+#ifndef GENIMA_B200_H
+#define GENIMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gn_handle gn_handle;
+
+enum gn_status {
+  GN_OK = 0,
+  GN_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  GN_ERR_CUDA = -2,      /* CUDA runtime or driver error */
+  GN_ERR_NOMEM = -3,     /* workspace too small / allocation failed */
+  GN_ERR_NODRIVER = -4   /* no CUDA driver / device (CPU-only box) */
+};
+
+enum gn_act { GN_ACT_NONE = 0, GN_ACT_SILU = 1, GN_ACT_GELU = 2, GN_ACT_RELU = 3, GN_ACT_QUICKGELU = 4 };
+
+/* Fused GEMM epilogue, applied to the fp32 accumulator acc[m, n]:
+ *   v   = act_pre(acc * scale[n] + bias[n] + rowvec[m / rows_per_batch, n])
+ *   out = act_post(alpha * v + beta * residual[m, n])          (alpha = 1, beta = 1 when residual is given)
+ * geglu = 1: weight rows are packed in 64-wide (value, gate) blocks; out[m, j] = v_val * gelu(v_gate), N/2 columns.
+ * Replaces the bias-add / time-embedding add / residual add / activation torch kernels that follow every
+ * conv or linear in diffusers' ResnetBlock2D, BasicTransformerBlock, FeedForward(GEGLU) and torchvision BasicBlock. */
+typedef struct gn_epilogue {
+  const float* scale;
+  const float* bias;
+  const float* rowvec;
+  const void* residual; /* fp16 [M, ldr] */
+  int64_t ldr;
+  int32_t rows_per_batch;
+  int32_t act_pre;
+  int32_t act_post;
+  float alpha;
+  float beta;
+  int32_t geglu;
+  int32_t out_fp32; /* 0: fp16 output, 1: fp32 output */
+  float* gn_stats;  /* optional [B, groups, 2] fp32 (sum, sumsq) accumulated with atomics over the fp16-rounded output */
+  int32_t gn_groups;
+  int32_t reserved;
+} gn_epilogue;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------- */
+int gn_create(int device, gn_handle** out);
+int gn_destroy(gn_handle* h);
+const char* gn_last_error(const gn_handle* h);
+const char* gn_version(void);
+/* Scratch arena for split-K partial sums (caller-owned fp32 device buffer). */
+int gn_set_workspace(gn_handle* h, void* dptr, int64_t bytes);
+/* Force tile width / split count of the next GEMM-class calls (0 = heuristic); used by tests and tuning. */
+int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits);
+/* Last launch configuration chosen by gn_linear / gn_conv2d: out[0]=block_n, out[1]=splits, out[2]=stages, out[3]=ctas. */
+int gn_get_last_gemm_config(const gn_handle* h, int32_t* out4);
+/* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
+int64_t gn_launch_count(const gn_handle* h);
+
+/* ---- dense contractions (tcgen05.mma, TMA-staged operands, TMEM accumulators) --------------------------------
+ * out[M, N] = epilogue(A[M, K] @ W[N, K]^T).  A: fp16 row-major with row stride lda (elements, % 8 == 0), K % 8 == 0.
+ * W: fp16 [N, K] row-major (torch nn.Linear layout).  Replaces cuBLAS GEMMs behind nn.Linear / 1x1 conv. */
+int gn_linear(gn_handle* h, const void* A, int64_t lda, int M, int K, const void* W, int N, void* out, int64_t ldo,
+              const gn_epilogue* epi, void* stream);
+
+/* Implicit-GEMM convolution on NHWC fp16.  x: [B, H, W, C] (C % 8 == 0); w: packed [Cout][KH*KW][Cp] followed, per
+ * output channel, by [Cp_e0][Cp_e1] for up to two fused 1x1 "extra" sources (Cp = C rounded up to 64) — see
+ * genima_b200/packing.py.  The extra sources (ex0/ex1, NHWC at the OUTPUT resolution) implement ResnetBlock2D's
+ * conv_shortcut over the (possibly concatenated) block input inside the same accumulation.
+ * stride in {1, 2}.  out: [B, Ho, Wo, Cout] with row stride ldo.  Replaces cuDNN implicit-GEMM convolutions. */
+int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C, const void* w, int Cout, int KH, int KW,
+              int stride, int pad, const void* ex0, int C_ex0, const void* ex1, int C_ex1, void* out, int64_t ldo,
+              const gn_epilogue* epi, void* stream);
+
+/* ---- attention (tcgen05 flash attention, head_dim 64) -------------------------------------------------------
+ * q: rows [B*Tq] with row stride ldq, head h at columns [h*64, h*64+64); k, v likewise with Tk rows per batch.
+ * out[B*Tq, heads*64] = softmax(q k^T * scale) v.   Replaces xformers memory_efficient_attention / torch SDPA. */
+int gn_attention(gn_handle* h, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                 void* out, int64_t ldo, int B, int heads, int Tq, int Tk, float scale, void* stream);
+/* Generic SIMT attention for small problems (ACT transformer: head_dim 32; any Tk); fp16 in/out, fp32 math.
+ * Optional causal mask (CLIP text towers).  Replaces nn.MultiheadAttention's SDPA core. */
+int gn_attention_small(gn_handle* h, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                       int64_t ldv, void* out, int64_t ldo, int B, int heads, int head_dim, int Tq, int Tk,
+                       float scale, int causal, void* stream);
+
+/* ---- normalisation --------------------------------------------------------------------------------------- */
+/* GroupNorm over NHWC fp16, optional fused SiLU, optional channel-concat of two sources (x1 may be NULL).
+ * y[B, HW, C0+C1] = act(gn(concat(x0, x1)) * gamma + beta).  Statistics in fp32.  If stats_in != NULL the (sum, sumsq)
+ * pairs produced by a GEMM epilogue are used instead of a reduction pass.  Replaces torch group_norm + silu + cat. */
+int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x1, int C1, int B, int HW, int groups, float eps,
+                  const float* gamma, const float* beta, int silu, const float* stats_in, void* y, void* stream);
+/* LayerNorm over the last dim of a [rows, C] fp16 matrix (fp32 statistics). */
+int gn_layer_norm(gn_handle* h, const void* x, int64_t ldx, int rows, int C, float eps, const float* gamma,
+                  const float* beta, void* y, int64_t ldy, void* stream);
+/* Row softmax of a [rows, cols] fp16 matrix in place of torch.softmax (VAE mid-block attention, 1 head d=512). */
+int gn_softmax_rows(gn_handle* h, void* x, int64_t ldx, int rows, int cols, float scale, void* stream);
+
+/* ---- data movement / elementwise --------------------------------------------------------------------------- */
+/* y[B, 2H, 2W, C] = nearest-neighbour x2 upsample of x[B, H, W, C] (diffusers Upsample2D before its conv). */
+int gn_upsample_nearest2x(gn_handle* h, const void* x, int B, int H, int W, int C, void* y, void* stream);
+/* 3x3 stride-2 pad-1 max pool on NHWC fp16 (torchvision ResNet stem). */
+int gn_maxpool3x3s2(gn_handle* h, const void* x, int B, int H, int W, int C, void* y, void* stream);
+/* out = a + b (fp16, n elements). */
+int gn_add(gn_handle* h, const void* a, const void* b, void* out, int64_t n, void* stream);
+/* Sinusoidal timestep embedding (flip_sin_to_cos=True, freq_shift=0): out[dim] fp16 = [cos(t f), sin(t f)]. */
+int gn_timestep_embedding(gn_handle* h, float t, int dim, void* out, void* stream);
+/* Euler-discrete scheduler (diffusers EulerDiscreteScheduler.step, s_churn = 0), fp32 math on fp16 storage:
+ *   x_next = x + (sigma_next - sigma) * eps;   x_scaled = x_next / sqrt(sigma_next^2 + 1)  (input of the next step).
+ * x / eps / x_next / x_scaled: [n] fp16 element-wise; x_scaled may be NULL. */
+int gn_euler_step(gn_handle* h, const void* x, const void* eps, float sigma, float sigma_next, void* x_next,
+                  void* x_scaled, int64_t n, void* stream);
+/* y = x * s (fp16), used for scale_model_input at step 0 and latents / scaling_factor before the VAE. */
+int gn_scale(gn_handle* h, const void* x, float s, void* y, int64_t n, void* stream);
+/* NCHW fp16/fp32 <-> NHWC fp16 with channel padding (pad channels zero-filled). src_fp32: 1 if src is float. */
+int gn_nchw_to_nhwc(gn_handle* h, const void* src, int src_fp32, int B, int C, int H, int W, int Cpad, void* dst,
+                    void* stream);
+int gn_nhwc_to_nchw(gn_handle* h, const void* src, int B, int C, int H, int W, int Cpad, void* dst, int dst_fp32,
+                    void* stream);
+/* uint8 NHWC RGB [B, H, W, 3] -> fp16 NHWC [B, H, W, Cpad] = (u8 / 255 - mean[c]) / std[c]; (mean, std) = (0, 1) gives
+ * VaeImageProcessor.preprocess(do_normalize=False); ImageNet constants give GenimaACTPolicy's normalise. */
+int gn_u8_to_nhwc(gn_handle* h, const void* src_u8, int B, int H, int W, int Cpad, const float* mean3,
+                  const float* std3, void* dst, void* stream);
+/* VaeImageProcessor.postprocess: fp16 NHWC [B, H, W, Cpad] in [-1, 1] -> uint8 [B, H, W, 3] = round(clamp(x/2+.5)*255). */
+int gn_nhwc_to_u8(gn_handle* h, const void* src, int B, int H, int W, int Cpad, void* dst_u8, void* stream);
+/* tile_images / untile_images of controller/utils/misc.py:6-47 on device: 4 views u8 [4, 256, 256, 3] <-> one
+ * [512, 512, 3] tile (view k -> quadrant (k % 2, k / 2)). */
+int gn_tile_views(gn_handle* h, const void* views_u8, int B, void* tile_u8, void* stream);
+int gn_untile_views(gn_handle* h, const void* tile_u8, int B, void* views_u8, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENIMA_B200_H */

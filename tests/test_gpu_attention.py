@@ -1,0 +1,60 @@
+"""Parity of the tcgen05 flash-attention kernel and the SIMT small-attention kernel against fp32 softmax(QK^T)V.
+
+Tolerance: rtol 1e-3 / atol 1e-4 relative to the value scale.  P is rounded to fp16 before the PV MMA (as the
+reference's fp16 flash kernels do), so atol is scaled by max|V|.
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import report_close
+from oracle import ops_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.float16)
+
+
+@pytest.mark.parametrize("B,heads,Tq,Tk", [
+    (1, 1, 128, 128), (1, 2, 256, 256), (1, 5, 4096, 4096), (1, 10, 1024, 1024), (1, 20, 256, 256), (1, 20, 64, 64),
+    (1, 5, 4096, 77), (1, 20, 64, 77), (2, 3, 200, 300), (4, 2, 64, 77), (1, 1, 1, 1), (1, 2, 130, 129),
+])
+def test_attention_tc(ops, B, heads, Tq, Tk):
+    d = 64
+    q = _rand((B * Tq, heads * d), 1)
+    k = _rand((B * Tk, heads * d), 2)
+    v = _rand((B * Tk, heads * d), 3)
+    scale = 1.0 / math.sqrt(d)
+    out = ops.attention(q.cuda(), k.cuda(), v.cuda(), B, heads, Tq, Tk, scale)
+    ref = ops_ref.attention_ref(q, k, v, B, heads, d, Tq, Tk, scale)
+    report_close(f"attention B{B} h{heads} {Tq}x{Tk}", out, ref, rtol=1e-3, atol=1e-4 * float(v.abs().max()))
+
+
+def test_attention_tc_peaked_and_fused_qkv_layout(ops):
+    # q/k/v are column slices of one [M, 3C] buffer (the fused QKV projection output); large logits (peaked softmax)
+    B, heads, T, d = 1, 5, 512, 64
+    Cn = heads * d
+    qkv = _rand((B * T, 3 * Cn), 4, 3.0).cuda()
+    scale = 1.0 / math.sqrt(d)
+    out = ops.attention(qkv[:, :Cn], qkv[:, Cn:2 * Cn], qkv[:, 2 * Cn:], B, heads, T, T, scale)
+    c = qkv.cpu()
+    ref = ops_ref.attention_ref(c[:, :Cn], c[:, Cn:2 * Cn], c[:, 2 * Cn:], B, heads, d, T, T, scale)
+    report_close("attention peaked / strided", out, ref, rtol=1e-3, atol=1e-4 * float(c.abs().max()))
+
+
+@pytest.mark.parametrize("B,heads,d,Tq,Tk,causal", [
+    (1, 8, 32, 258, 258, False), (1, 8, 32, 20, 258, False), (1, 8, 32, 20, 20, False), (2, 8, 64, 77, 77, True),
+    (1, 16, 64, 77, 77, True), (3, 2, 32, 5, 70, False),
+])
+def test_attention_small(ops, B, heads, d, Tq, Tk, causal):
+    q = _rand((B * Tq, heads * d), 5)
+    k = _rand((B * Tk, heads * d), 6)
+    v = _rand((B * Tk, heads * d), 7)
+    scale = 1.0 / math.sqrt(d)
+    out = ops.attention_small(q.cuda(), k.cuda(), v.cuda(), B, heads, d, Tq, Tk, scale, causal=causal)
+    ref = ops_ref.attention_ref(q, k, v, B, heads, d, Tq, Tk, scale, causal=causal)
+    report_close(f"attention_small B{B} h{heads} d{d} {Tq}x{Tk} causal={causal}", out, ref)

@@ -1,0 +1,127 @@
+"""Parity of the tcgen05 GEMM (gn_linear) against the fp32 CPU oracle, through the C ABI.
+
+Tolerance (BASELINE.json north_star): rtol = 1e-3, atol = 1e-4 on fp16 outputs, operands identical (fp16-rounded).
+"""
+import pytest
+import torch
+
+from conftest import report_close
+from oracle import ops_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.float16)
+
+
+@pytest.mark.parametrize("M,N,K", [
+    (128, 128, 64), (256, 128, 128), (128, 256, 512), (4096, 320, 320), (1024, 640, 640), (256, 1280, 1280),
+    (64, 1280, 1280), (77, 320, 1024), (77, 1280, 1024), (4096, 960, 320), (100, 48, 72), (1, 1280, 320),
+    (20, 8, 256), (258, 2048, 256),
+])
+def test_linear_plain(ops, M, N, K):
+    a = _rand((M, K), 1)
+    w = _rand((N, K), 2, K ** -0.5)
+    out = ops.linear(a.cuda(), w.cuda())
+    report_close(f"linear {M}x{N}x{K}", out, ops_ref.linear_ref(a, w))
+
+
+@pytest.mark.parametrize("block_n", [16, 32, 48, 64, 96, 128, 160, 192, 256])
+def test_linear_block_n(ops, block_n):
+    M, N, K = 300, 320, 256
+    a = _rand((M, K), 3)
+    w = _rand((N, K), 4, K ** -0.5)
+    ops.set_gemm_tuning(block_n, 1)
+    try:
+        out = ops.linear(a.cuda(), w.cuda())
+        cfg = ops.last_gemm_config()
+    finally:
+        ops.set_gemm_tuning(0, 0)
+    assert cfg[0] == block_n
+    report_close(f"linear block_n={block_n}", out, ops_ref.linear_ref(a, w))
+
+
+@pytest.mark.parametrize("splits", [2, 3, 8])
+def test_linear_split_k(ops, splits):
+    M, N, K = 64, 1280, 2560
+    a = _rand((M, K), 5)
+    w = _rand((N, K), 6, K ** -0.5)
+    bias = torch.randn(N) * 0.1
+    res = _rand((M, N), 7)
+    ops.set_gemm_tuning(128, splits)
+    try:
+        out = ops.linear(a.cuda(), w.cuda(), bias=bias.cuda(), residual=res.cuda())
+        cfg = ops.last_gemm_config()
+    finally:
+        ops.set_gemm_tuning(0, 0)
+    assert cfg[1] == splits
+    report_close(f"linear split-K {splits}", out, ops_ref.linear_ref(a, w, bias=bias, residual=res))
+
+
+def test_linear_long_k_pipeline_wrap(ops):
+    # K = 8192 -> 128 k-blocks: the smem ring wraps many times (phase-bit handling)
+    M, N, K = 256, 256, 8192
+    a = _rand((M, K), 8)
+    w = _rand((N, K), 9, K ** -0.5)
+    ops.set_gemm_tuning(128, 1)
+    try:
+        out = ops.linear(a.cuda(), w.cuda())
+    finally:
+        ops.set_gemm_tuning(0, 0)
+    report_close("linear K=8192", out, ops_ref.linear_ref(a, w))
+
+
+@pytest.mark.parametrize("act_pre,act_post", [("silu", None), ("gelu", None), ("relu", None), ("quick_gelu", None),
+                                              (None, "relu")])
+def test_linear_epilogue(ops, act_pre, act_post):
+    M, N, K = 512, 320, 320
+    a = _rand((M, K), 10)
+    w = _rand((N, K), 11, K ** -0.5)
+    bias = torch.randn(N) * 0.1
+    scale = 1.0 + 0.1 * torch.randn(N)
+    rowvec = torch.randn(2, N) * 0.1
+    res = _rand((M, N), 12)
+    out = ops.linear(a.cuda(), w.cuda(), bias=bias.cuda(), scale=scale.cuda(), rowvec=rowvec.cuda(),
+                     rows_per_batch=256, residual=res.cuda(), act_pre=act_pre, act_post=act_post)
+    ref = ops_ref.linear_ref(a, w, bias=bias, scale=scale, rowvec=rowvec, rows_per_batch=256, residual=res,
+                             act_pre=act_pre, act_post=act_post)
+    report_close(f"linear epilogue {act_pre}/{act_post}", out, ref)
+
+
+def test_linear_alpha_beta_fp32_out(ops):
+    M, N, K = 20, 8, 256
+    a = _rand((M, K), 13)
+    w = _rand((N, K), 14, K ** -0.5)
+    bias = torch.randn(N) * 0.1
+    out = ops.linear(a.cuda(), w.cuda(), bias=bias.cuda(), out_fp32=True)
+    assert out.dtype == torch.float32
+    report_close("linear fp32 out", out, ops_ref.linear_ref(a, w, bias=bias), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("M,D,K", [(4096, 1280, 320), (64, 5120, 1280), (300, 128, 64)])
+def test_linear_geglu(ops, M, D, K):
+    from genima_b200.packing import pack_geglu_weight
+
+    a = _rand((M, K), 15)
+    w = _rand((2 * D, K), 16, K ** -0.5)
+    b = torch.randn(2 * D) * 0.1
+    wp, bp = pack_geglu_weight(w, b)
+    out = ops.linear(a.cuda(), wp.cuda(), bias=bp.cuda(), geglu=True)
+    assert out.shape == (M, D)
+    af = a.float()
+    proj = af @ w.float().t() + b
+    ref = proj[:, :D] * torch.nn.functional.gelu(proj[:, D:])
+    report_close(f"geglu {M}x{D}x{K}", out, ref)
+
+
+def test_linear_strided_views(ops):
+    # A is a column slice of a wider buffer (lda > K) and the output lands in a column slice (ldo > N)
+    M, N, K = 200, 64, 128
+    big = _rand((M, 3 * K), 17).cuda()
+    w = _rand((N, K), 18, K ** -0.5)
+    outbuf = torch.zeros(M, 2 * N, dtype=torch.float16, device="cuda")
+    ops.linear(big[:, K:2 * K], w.cuda(), out=outbuf[:, N:])
+    report_close("linear strided", outbuf[:, N:], ops_ref.linear_ref(big[:, K:2 * K].cpu(), w))
+    assert float(outbuf[:, :N].abs().max()) == 0.0
