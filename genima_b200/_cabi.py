@@ -61,19 +61,21 @@ SIGNATURES = {
     "gn_attention_small": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "gn_group_norm": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
     "gn_layer_norm": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i64, _vp]),
-    "gn_softmax_rows": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp]),
+    "gn_softmax_rows": (_i, [_vp, _vp, _i, _i64, _vp, _i64, _i, _i, _f, _vp]),
     "gn_upsample_nearest2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gn_maxpool3x3s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gn_add": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "gn_timestep_embedding": (_i, [_vp, _f, _i, _vp, _vp]),
     "gn_euler_step": (_i, [_vp, _vp, _vp, _f, _f, _vp, _vp, _i64, _vp]),
     "gn_scale": (_i, [_vp, _vp, _f, _vp, _i64, _vp]),
-    "gn_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "gn_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
     "gn_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "gn_u8_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
     "gn_nhwc_to_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gn_tile_views": (_i, [_vp, _vp, _i, _vp, _vp]),
     "gn_untile_views": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gn_embed_tokens": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "gn_film_fold": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -104,8 +104,14 @@ __global__ void euler_step_kernel(const __half* __restrict__ x, const __half* __
   }
 }
 
+struct Norm3 {
+  float mean[3];
+  float inv_std[3];
+  int enabled;
+};
+
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, int B, int C, int H, int W, int Cpad,
+__global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, int B, int C, int H, int W, int Cpad, Norm3 nm,
                                     __half* __restrict__ dst) {
   const int64_t total = (int64_t)B * H * W * Cpad;
   GRID_STRIDE(i, total) {
@@ -116,7 +122,10 @@ __global__ void nchw_to_nhwc_kernel(const T* __restrict__ src, int B, int C, int
     const int yh = (int)(r % H);
     const int b = (int)(r / H);
     float v = 0.f;
-    if (c < C) v = (float)src[(((int64_t)b * C + c) * H + yh) * W + xw];
+    if (c < C) {
+      v = (float)src[(((int64_t)b * C + c) * H + yh) * W + xw];
+      if (nm.enabled && c < 3) v = (v / 255.0f - nm.mean[c]) * nm.inv_std[c];
+    }
     dst[i] = __float2half_rn(v);
   }
 }
@@ -136,12 +145,7 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ src, int B, int C
   }
 }
 
-struct Norm3 {
-  float mean[3];
-  float inv_std[3];
-};
-
-// one thread per pixel: 3 bytes in, Cpad halves out (pad channels zero)
+// one thread per 8-channel vector: 3 bytes in, Cpad halves out (pad channels zero)
 __global__ void u8_to_nhwc_kernel(const uint8_t* __restrict__ src, int64_t npix, int Cpad, Norm3 nm,
                                   __half* __restrict__ dst) {
   const int CV = Cpad / 8;
@@ -195,9 +199,70 @@ __global__ void tile_views_kernel(const uint8_t* __restrict__ views, uint8_t* __
   }
 }
 
+// out[b, t, :] = tok_emb[ids[b, t], :] + pos_emb[t, :]   (CLIP text embeddings)
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const __half* __restrict__ tok,
+                                    const __half* __restrict__ pos, __half* __restrict__ out, int64_t rows, int T,
+                                    int D, int vocab) {
+  const int DV = D / 8;
+  GRID_STRIDE(i, rows * DV) {
+    const int64_t r = i / DV;
+    const int dv = (int)(i % DV);
+    int64_t id = ids[r];
+    if (id < 0) id = 0;
+    if (id >= vocab) id = vocab - 1;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(tok + id * D + dv * 8));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(pos + (r % T) * D + dv * 8));
+    const __half2* ha = reinterpret_cast<const __half2*>(&a);
+    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+    uint4 w;
+    uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 fa = __half22float2(ha[t]);
+      const float2 fb = __half22float2(hb[t]);
+      wp[t] = pack_half2(fa.x + fb.x, fa.y + fb.y);
+    }
+    *reinterpret_cast<uint4*>(out + r * D + dv * 8) = w;
+  }
+}
+
+// FiLM folded into a FrozenBatchNorm affine: film = [gamma | beta] (2C), (1 + gamma) * (s * x + t) + beta
+__global__ void film_fold_kernel(const float* __restrict__ film, const float* __restrict__ bn_scale,
+                                 const float* __restrict__ bn_shift, float* __restrict__ scale_out,
+                                 float* __restrict__ shift_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float g = 1.0f + film[c];
+  scale_out[c] = g * bn_scale[c];
+  shift_out[c] = g * bn_shift[c] + film[C + c];
+}
+
 }  // namespace gn
 
 using namespace gn;
+
+extern "C" int gn_embed_tokens(gn_handle* h, const void* ids_i64, const void* tok_emb, const void* pos_emb, int B,
+                               int T, int D, int vocab, void* out, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  GN_CHECK_ARG(h, ids_i64 && tok_emb && pos_emb && out && B > 0 && T > 0 && D > 0 && (D % 8) == 0 && vocab > 0,
+               "gn_embed_tokens: bad arguments");
+  const int64_t rows = (int64_t)B * T;
+  embed_tokens_kernel<<<grid_for(h, rows * (D / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const int64_t*>(ids_i64), static_cast<const __half*>(tok_emb), static_cast<const __half*>(pos_emb),
+      static_cast<__half*>(out), rows, T, D, vocab);
+  GN_CHECK_LAUNCH(h);
+  return GN_OK;
+}
+
+extern "C" int gn_film_fold(gn_handle* h, const float* film, const float* bn_scale, const float* bn_shift,
+                            float* scale_out, float* shift_out, int C, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  GN_CHECK_ARG(h, film && bn_scale && bn_shift && scale_out && shift_out && C > 0, "gn_film_fold: bad arguments");
+  film_fold_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(film, bn_scale, bn_shift, scale_out,
+                                                                                  shift_out, C);
+  GN_CHECK_LAUNCH(h);
+  return GN_OK;
+}
 
 extern "C" int gn_upsample_nearest2x(gn_handle* h, const void* x, int B, int H, int W, int C, void* y, void* stream) {
   if (!h) return GN_ERR_INVALID;
@@ -260,17 +325,23 @@ extern "C" int gn_euler_step(gn_handle* h, const void* x, const void* eps, float
 }
 
 extern "C" int gn_nchw_to_nhwc(gn_handle* h, const void* src, int src_fp32, int B, int C, int H, int W, int Cpad,
-                               void* dst, void* stream) {
+                               const float* mean3, const float* std3, void* dst, void* stream) {
   if (!h) return GN_ERR_INVALID;
   GN_CHECK_ARG(h, src && dst && B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "gn_nchw_to_nhwc: bad arguments");
   const int64_t total = (int64_t)B * H * W * Cpad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Norm3 nm;
+  nm.enabled = (mean3 && std3) ? 1 : 0;
+  for (int c = 0; c < 3; ++c) {
+    nm.mean[c] = nm.enabled ? mean3[c] : 0.f;
+    nm.inv_std[c] = nm.enabled ? 1.0f / std3[c] : 1.f;
+  }
   if (src_fp32)
     nchw_to_nhwc_kernel<float><<<grid_for(h, total), 256, 0, st>>>(static_cast<const float*>(src), B, C, H, W, Cpad,
-                                                                   static_cast<__half*>(dst));
+                                                                   nm, static_cast<__half*>(dst));
   else
     nchw_to_nhwc_kernel<__half><<<grid_for(h, total), 256, 0, st>>>(static_cast<const __half*>(src), B, C, H, W, Cpad,
-                                                                    static_cast<__half*>(dst));
+                                                                    nm, static_cast<__half*>(dst));
   GN_CHECK_LAUNCH(h);
   return GN_OK;
 }
@@ -297,6 +368,7 @@ extern "C" int gn_u8_to_nhwc(gn_handle* h, const void* src_u8, int B, int H, int
   GN_CHECK_ARG(h, src_u8 && dst && B > 0 && H > 0 && W > 0 && Cpad >= 8 && (Cpad % 8) == 0,
                "gn_u8_to_nhwc: bad arguments");
   Norm3 nm;
+  nm.enabled = 1;
   for (int c = 0; c < 3; ++c) {
     nm.mean[c] = mean3 ? mean3[c] : 0.f;   // host pointers: three floats each
     nm.inv_std[c] = std3 ? 1.0f / std3[c] : 1.f;

@@ -208,11 +208,16 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restric
   }
 }
 
-// In-place row softmax of exp(scale * x): one block per row, row in registers (cols <= 8192, cols % 8 == 0).
+// Row softmax of scale * x: one block per row, row in registers (cols <= 8192, cols % 8 == 0).  Input fp32 (scores
+// from a GEMM with fp32 output) or fp16; output fp16 (may alias an fp16 input).
 constexpr int SM_VPT = 4;
-__global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ x, int64_t ldx, int cols, float scale) {
+template <typename TIn>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const TIn* __restrict__ x, int64_t ldx,
+                                                           __half* __restrict__ y, int64_t ldy, int cols,
+                                                           float scale) {
   __shared__ float red[8];
-  __half* rp = x + (int64_t)blockIdx.x * ldx;
+  const TIn* rp = x + (int64_t)blockIdx.x * ldx;
+  __half* wp = y + (int64_t)blockIdx.x * ldy;
   const int NV = cols / 8;
   float v[SM_VPT][8];
   float mx = -INFINITY;
@@ -220,14 +225,25 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
   for (int i = 0; i < SM_VPT; ++i) {
     const int cv = threadIdx.x + i * 256;
     if (cv < NV) {
-      const uint4 q = *reinterpret_cast<const uint4*>(rp + cv * 8);
-      const __half2* hp = reinterpret_cast<const __half2*>(&q);
+      if constexpr (sizeof(TIn) == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(rp + cv * 8);
+        const float4 b = *reinterpret_cast<const float4*>(rp + cv * 8 + 4);
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+        v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+      } else {
+        const uint4 q = *reinterpret_cast<const uint4*>(rp + cv * 8);
+        const __half2* hp = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(hp[t]);
-        v[i][2 * t] = f.x * scale;
-        v[i][2 * t + 1] = f.y * scale;
-        mx = fmaxf(mx, fmaxf(v[i][2 * t], v[i][2 * t + 1]));
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __half22float2(hp[t]);
+          v[i][2 * t] = f.x;
+          v[i][2 * t + 1] = f.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[i][j] *= scale;
+        mx = fmaxf(mx, v[i][j]);
       }
     }
   }
@@ -268,7 +284,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(__half* __restrict__ 
       w.y = pack_half2(v[i][2] * inv, v[i][3] * inv);
       w.z = pack_half2(v[i][4] * inv, v[i][5] * inv);
       w.w = pack_half2(v[i][6] * inv, v[i][7] * inv);
-      *reinterpret_cast<uint4*>(rp + cv * 8) = w;
+      *reinterpret_cast<uint4*>(wp + cv * 8) = w;
     }
   }
 }
@@ -343,12 +359,20 @@ extern "C" int gn_layer_norm(gn_handle* h, const void* x, int64_t ldx, int rows,
   return GN_OK;
 }
 
-extern "C" int gn_softmax_rows(gn_handle* h, void* x, int64_t ldx, int rows, int cols, float scale, void* stream) {
+extern "C" int gn_softmax_rows(gn_handle* h, const void* x, int x_fp32, int64_t ldx, void* y, int64_t ldy, int rows,
+                               int cols, float scale, void* stream) {
   if (!h) return GN_ERR_INVALID;
-  GN_CHECK_ARG(h, x && rows > 0 && cols > 0, "gn_softmax_rows: bad arguments");
-  GN_CHECK_ARG(h, (cols % 8) == 0 && cols <= 8 * 256 * SM_VPT && (ldx % 8) == 0, "gn_softmax_rows: cols=%d unsupported",
-               cols);
-  softmax_rows_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__half*>(x), ldx, cols, scale);
+  GN_CHECK_ARG(h, x && y && rows > 0 && cols > 0, "gn_softmax_rows: bad arguments");
+  GN_CHECK_ARG(h, (cols % 8) == 0 && cols <= 8 * 256 * SM_VPT && (ldx % 8) == 0 && (ldy % 8) == 0,
+               "gn_softmax_rows: cols=%d unsupported", cols);
+  GN_CHECK_ARG(h, !(x_fp32 && x == y), "gn_softmax_rows: fp32 input cannot alias the fp16 output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_fp32)
+    softmax_rows_kernel<float><<<rows, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<__half*>(y), ldy,
+                                                     cols, scale);
+  else
+    softmax_rows_kernel<__half><<<rows, 256, 0, st>>>(static_cast<const __half*>(x), ldx, static_cast<__half*>(y),
+                                                      ldy, cols, scale);
   GN_CHECK_LAUNCH(h);
   return GN_OK;
 }

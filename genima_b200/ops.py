@@ -242,14 +242,17 @@ class Ops:
         self.handle.check(rc, "gn_layer_norm")
         return out
 
-    def softmax_rows_(self, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
-        _f16(x, "x")
-        if x.dim() != 2 or x.stride(1) != 1:
-            raise ValueError("x must be 2D with unit column stride")
-        rc = self.lib.gn_softmax_rows(self.h, x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], float(scale),
+    def softmax_rows(self, x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """softmax(scale * x) over the last dim of a 2D fp32/fp16 matrix -> fp16 (in place for fp16 input by default)."""
+        if x.dim() != 2 or x.stride(1) != 1 or not x.is_cuda or x.dtype not in (torch.float16, torch.float32):
+            raise ValueError("x must be a 2D CUDA fp16/fp32 matrix with unit column stride")
+        if out is None:
+            out = x if x.dtype == torch.float16 else torch.empty(x.shape, dtype=torch.float16, device=x.device)
+        rc = self.lib.gn_softmax_rows(self.h, x.data_ptr(), 1 if x.dtype == torch.float32 else 0, x.stride(0),
+                                      out.data_ptr(), out.stride(0), x.shape[0], x.shape[1], float(scale),
                                       self._stream())
         self.handle.check(rc, "gn_softmax_rows")
-        return x
+        return out
 
     # ------------------------------------------------------------------------------------------------ elementwise
     def upsample_nearest2x(self, x: torch.Tensor) -> torch.Tensor:
@@ -305,14 +308,16 @@ class Ops:
         self.handle.check(rc, "gn_euler_step")
         return x_next, x_scaled
 
-    def nchw_to_nhwc(self, src: torch.Tensor, cpad: Optional[int] = None) -> torch.Tensor:
+    def nchw_to_nhwc(self, src: torch.Tensor, cpad: Optional[int] = None, mean=None, std=None) -> torch.Tensor:
         if not src.is_cuda or not src.is_contiguous() or src.dtype not in (torch.float16, torch.float32):
             raise TypeError("nchw_to_nhwc: contiguous CUDA fp16/fp32 tensor expected")
         B, Cn, H, W = src.shape
         cpad = cpad or Cn
         dst = torch.empty(B, H, W, cpad, dtype=torch.float16, device=src.device)
+        m = (C.c_float * 3)(*mean) if mean is not None else None
+        s = (C.c_float * 3)(*std) if std is not None else None
         rc = self.lib.gn_nchw_to_nhwc(self.h, src.data_ptr(), 1 if src.dtype == torch.float32 else 0, B, Cn, H, W,
-                                      cpad, dst.data_ptr(), self._stream())
+                                      cpad, m, s, dst.data_ptr(), self._stream())
         self.handle.check(rc, "gn_nchw_to_nhwc")
         return dst
 
@@ -369,3 +374,29 @@ class Ops:
         self.handle.check(self.lib.gn_untile_views(self.h, tile.contiguous().data_ptr(), B, out.data_ptr(),
                                                    self._stream()), "gn_untile_views")
         return out
+
+    def embed_tokens(self, ids: torch.Tensor, tok_emb: torch.Tensor, pos_emb: torch.Tensor) -> torch.Tensor:
+        if ids.dtype != torch.int64 or not ids.is_cuda or ids.dim() != 2:
+            raise TypeError("embed_tokens: CUDA int64 [B, T] ids expected")
+        _f16(tok_emb, "tok_emb")
+        _f16(pos_emb, "pos_emb")
+        B, T = ids.shape
+        V, D = tok_emb.shape
+        out = torch.empty(B, T, D, dtype=torch.float16, device=ids.device)
+        rc = self.lib.gn_embed_tokens(self.h, ids.contiguous().data_ptr(), tok_emb.data_ptr(), pos_emb.data_ptr(), B,
+                                      T, D, V, out.data_ptr(), self._stream())
+        self.handle.check(rc, "gn_embed_tokens")
+        return out
+
+    def film_fold(self, film: torch.Tensor, bn_scale: torch.Tensor, bn_shift: torch.Tensor):
+        Cn = bn_scale.numel()
+        _f32(film, "film")
+        if film.numel() != 2 * Cn:
+            raise ValueError("film must hold [gamma | beta] = 2*C floats")
+        scale = torch.empty(Cn, dtype=torch.float32, device=film.device)
+        shift = torch.empty(Cn, dtype=torch.float32, device=film.device)
+        rc = self.lib.gn_film_fold(self.h, film.data_ptr(), _f32(bn_scale, "bn_scale").data_ptr(),
+                                   _f32(bn_shift, "bn_shift").data_ptr(), scale.data_ptr(), shift.data_ptr(), Cn,
+                                   self._stream())
+        self.handle.check(rc, "gn_film_fold")
+        return scale, shift

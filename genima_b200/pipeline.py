@@ -1,0 +1,358 @@
+"""B200ControlNetPipeline — drop-in for diffusers' StableDiffusionControlNetPipeline on Genima's eval path.
+
+The reference calls (controller/agent/sd_controlnet_agent.py:67-76)
+
+    self.pipe(prompt=..., image=..., negative_prompt=..., num_inference_steps=..., guidance_scale=..., generator=...)
+
+and reads `out[0]` as a list of 512x512 PIL images (controller/eval_genima.py:215,225).  `__call__` below keeps the
+diffusers 0.29.0 signature, implements the arguments the reference uses plus `latents`,
+`prompt_embeds`, `output_type` and RAISES for everything it does not implement (CFG, ip-adapter, guess mode, control
+guidance windows, multiple images per prompt) instead of silently ignoring it.
+
+Execution (restated for the device):
+  control image  u8 -> [B, 512, 512, 64] fp16 -> ControlNet conditioning embedding          (once per call)
+  prompt ids     -> text encoder -> cross-attention K/V of all 23 transformer layers        (cached per prompt)
+  timesteps      -> time-embedding MLP + per-ResBlock projections                           (cached per step count)
+  for each sigma: U-Net encoder -> ControlNet encoder (+zero-convs fused with the skip adds) -> U-Net decoder ->
+                  Euler update (+ next step's input scaling) — all on one stream, no host sync inside the loop
+  latents / 0.18215 -> VAE decoder -> (x / 2 + 0.5).clamp -> u8
+The whole post-upload chain can be captured once into a CUDA graph (`use_cuda_graph=True`) and replayed per call.
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Callable, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from .configs import CLIPTextConfig, SchedulerConfig, UNetConfig, VAEConfig
+from .ops import Ops
+from .scheduler import EulerDiscreteSchedule
+from .text_encoder import DeviceCLIPText
+from .unet import LATENT_CPAD, DeviceControlNet, DeviceUNet
+from .vae import DeviceVAEDecoder
+
+try:  # PIL is only needed for the "pil" input/output types the reference uses
+    from PIL import Image
+except Exception:  # pragma: no cover
+    Image = None
+
+
+class PipelineOutput:
+    """StableDiffusionPipelineOutput look-alike: `.images`, `.nsfw_content_detected`, tuple-style indexing."""
+
+    def __init__(self, images, nsfw_content_detected=None):
+        self.images = images
+        self.nsfw_content_detected = nsfw_content_detected
+
+    def __getitem__(self, i):
+        return (self.images, self.nsfw_content_detected)[i]
+
+    def __iter__(self):
+        return iter((self.images, self.nsfw_content_detected))
+
+    def __len__(self):
+        return 2
+
+
+class _ModuleShim:
+    """Accepts the attribute pokes DiffusionAgent.set_optimizations makes on pipe.vae / pipe.unet (no-ops here: the
+    kernels are already fused / sliced as needed)."""
+
+    def __init__(self, impl=None):
+        self.impl = impl
+
+    def enable_slicing(self):
+        return None
+
+    def to(self, *a, **k):
+        return self
+
+
+class B200ControlNetPipeline:
+    def __init__(self, ops: Ops, unet_sd, controlnet_sd, vae_sd, text_sd=None,
+                 unet_cfg: UNetConfig = UNetConfig(), vae_cfg: VAEConfig = VAEConfig(),
+                 text_cfg: CLIPTextConfig = CLIPTextConfig.sd_turbo(), scheduler_cfg: SchedulerConfig = SchedulerConfig(),
+                 tokenizer: Optional[Callable[[Sequence[str]], torch.Tensor]] = None, use_cuda_graph: bool = False):
+        self.ops = ops
+        self.unet_cfg, self.vae_cfg, self.text_cfg = unet_cfg, vae_cfg, text_cfg
+        self.unet_impl = DeviceUNet(ops, unet_sd, unet_cfg)
+        self.controlnet_impl = DeviceControlNet(ops, controlnet_sd, unet_cfg)
+        self.vae_impl = DeviceVAEDecoder(ops, vae_sd, vae_cfg)
+        self.text_impl = DeviceCLIPText(ops, text_sd, text_cfg) if text_sd is not None else None
+        self.schedule = EulerDiscreteSchedule(scheduler_cfg)
+        self.tokenizer = tokenizer
+        self.use_cuda_graph = use_cuda_graph
+        self.vae_scale_factor = 2 ** (len(vae_cfg.block_out_channels) - 1)
+        # attributes the reference pokes (controller/agent/diffusion_agent.py:21-42, sd_controlnet_agent.py:45-65)
+        self.vae = _ModuleShim(self.vae_impl)
+        self.unet = _ModuleShim(self.unet_impl)
+        self.controlnet = _ModuleShim(self.controlnet_impl)
+        self.text_encoder = _ModuleShim(self.text_impl)
+        self.scheduler = self.schedule
+        self._ctx_cache: Dict[str, torch.Tensor] = {}
+        self._kv_cache: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._temb_cache: Dict[tuple, list] = {}
+        self._graphs: Dict[tuple, dict] = {}
+        self.progress_bar_disabled = True
+
+    # ------------------------------------------------------------------ diffusers API surface used by the reference
+    def to(self, *args, **kwargs):
+        return self
+
+    def set_progress_bar_config(self, **kwargs):
+        self.progress_bar_disabled = bool(kwargs.get("disable", True))
+
+    def upcast_vae(self):
+        return None
+
+    def fuse_qkv_projections(self, unet: bool = True, vae: bool = True):
+        return None  # Q/K/V projections are always one GEMM here
+
+    def enable_xformers_memory_efficient_attention(self, *a, **k):
+        return None  # attention is always the tcgen05 flash kernel
+
+    # ------------------------------------------------------------------ prompt handling
+    def _prompt_ids(self, prompt) -> torch.Tensor:
+        if isinstance(prompt, torch.Tensor):
+            ids = prompt
+        elif isinstance(prompt, (list, tuple)) and len(prompt) and not isinstance(prompt[0], str):
+            ids = torch.as_tensor(np.asarray(prompt))
+        else:
+            if isinstance(prompt, str):
+                prompt = [prompt]
+            if self.tokenizer is None:
+                raise RuntimeError(
+                    "string prompts need a CLIP tokenizer, and no BPE vocabulary is available offline: pass "
+                    "`tokenizer=` to the pipeline, or token ids [B, 77] as `prompt`, or `prompt_embeds`")
+            ids = self.tokenizer(list(prompt))
+        ids = ids.to(torch.int64)
+        if ids.dim() == 1:
+            ids = ids[None]
+        return ids
+
+    def encode_prompt(self, prompt=None, prompt_embeds=None) -> torch.Tensor:
+        """-> [B, 77, D] fp16 on the device (diffusers encode_prompt without CFG, clip_skip=None)."""
+        if prompt_embeds is not None:
+            return prompt_embeds.to(self.ops.device, torch.float16).contiguous()
+        ids = self._prompt_ids(prompt)
+        key = hashlib.sha1(ids.cpu().numpy().tobytes()).hexdigest()
+        if key not in self._ctx_cache:
+            if self.text_impl is None:
+                raise RuntimeError("pipeline was built without a text encoder: pass prompt_embeds")
+            if len(self._ctx_cache) > 64:
+                self._ctx_cache.clear()
+            self._ctx_cache[key] = self.text_impl(ids.to(self.ops.device))[0]
+        return self._ctx_cache[key]
+
+    def _context_kv(self, ctx: torch.Tensor) -> Dict[str, torch.Tensor]:
+        key = f"{ctx.data_ptr()}:{tuple(ctx.shape)}:{ctx._version}"
+        if key not in self._kv_cache:
+            if len(self._kv_cache) > 8:
+                self._kv_cache.clear()
+            kv = {}
+            for net in (self.unet_impl, self.controlnet_impl):
+                for tr in net.transformers():
+                    kv[("u:" if net is self.unet_impl else "c:") + tr.prefix] = tr.project_context(self.ops, ctx)
+            self._kv_cache[key] = kv
+            self._kv_owner = ctx  # keep ctx alive so data_ptr cannot be recycled under the same key
+        return self._kv_cache[key]
+
+    def _time_rows(self, n_steps: int, batch: int):
+        key = (n_steps, batch)
+        if key not in self._temb_cache:
+            ts, _ = self.schedule.set_timesteps(n_steps)
+            per_step = []
+            for t in ts:
+                su = self.unet_impl.time_embedding(float(t))
+                sc = self.controlnet_impl.time_embedding(float(t))
+                per_step.append((self.unet_impl.temb_rows(self.unet_impl.resblocks(), su, batch),
+                                 self.controlnet_impl.temb_rows(self.controlnet_impl.resblocks(), sc, batch)))
+            self._temb_cache[key] = per_step
+        return self._temb_cache[key]
+
+    # ------------------------------------------------------------------ image handling
+    def _control_image_u8(self, image) -> torch.Tensor:
+        """-> uint8 [B, H, W, 3] on the device (VaeImageProcessor.preprocess without resize/normalise)."""
+        if isinstance(image, torch.Tensor):
+            t = image
+            if t.dtype != torch.uint8:
+                raise TypeError("tensor control images must be uint8 [B, H, W, 3]")
+            if t.dim() == 3:
+                t = t[None]
+        else:
+            if not isinstance(image, (list, tuple)):
+                image = [image]
+            arrs = []
+            for im in image:
+                if Image is not None and isinstance(im, Image.Image):
+                    im = np.asarray(im.convert("RGB"))
+                arrs.append(np.asarray(im, dtype=np.uint8))
+            t = torch.from_numpy(np.stack(arrs, axis=0))
+        if t.shape[-1] != 3:
+            raise ValueError(f"control image must be [B, H, W, 3], got {tuple(t.shape)}")
+        if not t.is_cuda:
+            t = t.pin_memory() if torch.cuda.is_available() else t
+        return t.to(self.ops.device, non_blocking=True).contiguous()
+
+    # ------------------------------------------------------------------ the device chain
+    def _denoise_and_decode(self, cond_u8: torch.Tensor, lat_in: torch.Tensor, kv, tk: int, n_steps: int,
+                            want_image: bool, cond_scale: float):
+        """cond_u8 [B, H, W, 3]; lat_in [B, h, w, 8] fp16 (unit-variance noise).  Returns (latents, image fp16|None)."""
+        ops = self.ops
+        B = lat_in.shape[0]
+        temb = self._time_rows(n_steps, B)
+        sig = self.schedule.sigmas
+        kv_u = {k[2:]: v for k, v in kv.items() if k.startswith("u:")}
+        kv_c = {k[2:]: v for k, v in kv.items() if k.startswith("c:")}
+        cond = ops.u8_to_nhwc(cond_u8, cpad=64)
+        cond_emb = self.controlnet_impl.cond_embedding(cond)
+        x = ops.scale(lat_in, self.schedule.init_noise_sigma)                       # latents * init_noise_sigma
+        xs = ops.scale(x, 1.0 / float(np.sqrt(float(sig[0]) ** 2 + 1.0)))           # scale_model_input, step 0
+        eps = torch.zeros_like(x)
+        for i in range(n_steps):
+            tu, tc = temb[i]
+            mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk)
+            skips, mid = self.controlnet_impl.residuals(xs, cond_emb, tc, kv_c, tk, skips, mid, cond_scale)
+            self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps)
+            x_next = torch.empty_like(x)
+            xs_next = torch.empty_like(x)
+            ops.euler_step(x, eps, float(sig[i]), float(sig[i + 1]), x_next=x_next, x_scaled=xs_next)
+            x, xs = x_next, xs_next
+        img = None
+        if want_image:
+            z = ops.scale(x, 1.0 / self.vae_cfg.scaling_factor)
+            img = self.vae_impl.decode(z)
+        return x, img
+
+    def _run(self, cond_u8, lat_in, kv, tk, n_steps, want_image, cond_scale):
+        if not self.use_cuda_graph:
+            return self._denoise_and_decode(cond_u8, lat_in, kv, tk, n_steps, want_image, cond_scale)
+        key = (tuple(cond_u8.shape), tuple(lat_in.shape), id(kv), tk, n_steps, want_image, cond_scale)
+        g = self._graphs.get(key)
+        if g is None:
+            static_cond = cond_u8.clone()
+            static_lat = lat_in.clone()
+            self._time_rows(n_steps, lat_in.shape[0])                 # hoisted work must exist before capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                             # warm-up: tensor maps, smem attributes, allocator
+                self._denoise_and_decode(static_cond, static_lat, kv, tk, n_steps, want_image, cond_scale)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            launches0 = ops_launches = self.ops.launch_count()
+            with torch.cuda.graph(graph):
+                out_lat, out_img = self._denoise_and_decode(static_cond, static_lat, kv, tk, n_steps, want_image,
+                                                            cond_scale)
+            ops_launches = self.ops.launch_count() - launches0
+            g = dict(graph=graph, cond=static_cond, lat=static_lat, out_lat=out_lat, out_img=out_img, kv=kv,
+                     launches=ops_launches)
+            if len(self._graphs) > 4:
+                self._graphs.clear()
+            self._graphs[key] = g
+        g["cond"].copy_(cond_u8, non_blocking=True)
+        g["lat"].copy_(lat_in, non_blocking=True)
+        g["graph"].replay()
+        self.last_graph_launches = g["launches"]
+        return g["out_lat"], g["out_img"]
+
+    # ------------------------------------------------------------------ public call
+    @torch.no_grad()
+    def __call__(self, prompt=None, image=None, height: Optional[int] = None, width: Optional[int] = None,
+                 num_inference_steps: int = 50, timesteps: Optional[List[int]] = None, guidance_scale: float = 7.5,
+                 negative_prompt=None, num_images_per_prompt: Optional[int] = 1, eta: float = 0.0, generator=None,
+                 latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_prompt_embeds: Optional[torch.Tensor] = None, ip_adapter_image=None,
+                 ip_adapter_image_embeds=None, output_type: Optional[str] = "pil", return_dict: bool = True,
+                 cross_attention_kwargs=None, controlnet_conditioning_scale: Union[float, List[float]] = 1.0,
+                 guess_mode: bool = False, control_guidance_start: Union[float, List[float]] = 0.0,
+                 control_guidance_end: Union[float, List[float]] = 1.0, clip_skip: Optional[int] = None,
+                 callback_on_step_end=None, callback_on_step_end_tensor_inputs: List[str] = ["latents"], **kwargs):
+        # ---- refuse what is not implemented (never silently ignore an argument that changes the result)
+        if guidance_scale is not None and guidance_scale > 1.0:
+            raise NotImplementedError("classifier-free guidance (guidance_scale > 1) is not implemented; Genima runs 0.0")
+        if num_images_per_prompt not in (None, 1):
+            raise NotImplementedError("num_images_per_prompt != 1 is not implemented")
+        if guess_mode:
+            raise NotImplementedError("guess_mode is not implemented")
+        if ip_adapter_image is not None or ip_adapter_image_embeds is not None:
+            raise NotImplementedError("ip-adapter inputs are not implemented")
+        if control_guidance_start != 0.0 or control_guidance_end != 1.0:
+            raise NotImplementedError("control_guidance_start/end windows are not implemented")
+        if isinstance(controlnet_conditioning_scale, (list, tuple)):
+            raise NotImplementedError("multi-ControlNet conditioning scales are not implemented")
+        if timesteps is not None:
+            raise NotImplementedError("custom `timesteps` are not implemented")
+        if clip_skip is not None:
+            raise NotImplementedError("clip_skip is not implemented")
+        if cross_attention_kwargs:
+            raise NotImplementedError("cross_attention_kwargs are not implemented")
+        if callback_on_step_end is not None:
+            raise NotImplementedError("per-step callbacks would force a host sync inside the loop; not implemented")
+        if kwargs:
+            raise TypeError(f"unexpected arguments: {sorted(kwargs)}")
+        if output_type not in ("pil", "np", "pt", "latent", "u8"):
+            raise ValueError(f"output_type {output_type!r} is not supported")
+        if image is None:
+            raise ValueError("`image` (the ControlNet conditioning image) is required")
+        # guidance_scale <= 1 -> no CFG: negative prompts are never encoded; eta is unused by Euler.
+
+        ops = self.ops
+        cond_u8 = self._control_image_u8(image)
+        B, H, W, _ = cond_u8.shape
+        f = self.vae_scale_factor
+        if (height not in (None, H)) or (width not in (None, W)):
+            raise NotImplementedError("resizing the control image is not implemented: pass it at the target size")
+        if H % (f * 8) or W % (f * 8):
+            raise ValueError(f"image size {H}x{W} must be a multiple of {f * 8}")
+        ctx = self.encode_prompt(prompt, prompt_embeds)
+        if ctx.shape[0] != B:
+            if ctx.shape[0] == 1:
+                ctx = ctx.expand(B, -1, -1).contiguous()
+            else:
+                raise ValueError(f"{ctx.shape[0]} prompts for {B} control images")
+        kv = self._context_kv(ctx)
+        tk = ctx.shape[1]
+
+        h, w = H // f, W // f
+        lc = self.unet_cfg.in_channels
+        if latents is None:
+            gens = generator if isinstance(generator, (list, tuple)) else [generator] * B
+            if len(gens) != B:
+                raise ValueError(f"{len(gens)} generators for batch {B}")
+            parts = []
+            for g in gens:  # diffusers randn_tensor: one draw per sample on the generator's device, model dtype
+                gdev = g.device if g is not None else ops.device
+                parts.append(torch.randn((1, lc, h, w), generator=g, device=gdev, dtype=torch.float16).to(ops.device))
+            latents = torch.cat(parts, dim=0)
+        else:
+            if tuple(latents.shape) != (B, lc, h, w):
+                raise ValueError(f"latents must be {(B, lc, h, w)}, got {tuple(latents.shape)}")
+            latents = latents.to(ops.device)
+            if latents.dtype not in (torch.float16, torch.float32):
+                latents = latents.float()
+        lat_in = ops.nchw_to_nhwc(latents.contiguous(), cpad=LATENT_CPAD)
+
+        self.schedule.set_timesteps(int(num_inference_steps))
+        x, img = self._run(cond_u8, lat_in, kv, tk, int(num_inference_steps), output_type != "latent",
+                           float(controlnet_conditioning_scale))
+
+        if output_type == "latent":
+            images = ops.nhwc_to_nchw(x, channels=lc)
+        elif output_type == "u8":
+            images = ops.nhwc_to_u8(img)                                    # device uint8 [B, H, W, 3]
+        elif output_type == "pt":
+            images = (ops.nhwc_to_nchw(img, channels=3, fp32=True) / 2 + 0.5).clamp(0, 1)
+        else:
+            u8 = ops.nhwc_to_u8(img).cpu().numpy()                          # the D->H copy is the step's sync point
+            if output_type == "np":
+                images = u8.astype(np.float32) / 255.0
+            else:
+                if Image is None:
+                    raise RuntimeError("PIL is not available for output_type='pil'")
+                images = [Image.fromarray(a) for a in u8]
+        if not return_dict:
+            return (images, None)
+        return PipelineOutput(images=images, nsfw_content_detected=None)

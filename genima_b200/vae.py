@@ -1,0 +1,92 @@
+"""Device-side KL-VAE decoder (diffusers AutoencoderKL.decode: post_quant_conv + Decoder) on the C-ABI kernels.
+
+Replaces `pipe.vae.decode(latents / scaling_factor)` at the end of diffusers' StableDiffusionControlNetPipeline.__call__
+(reached from controller/agent/sd_controlnet_agent.py:67-76).  Same NHWC / fused-epilogue execution as unet.py; the
+mid-block attention (1 head, d = 512, N = h*w) runs as two tcgen05 GEMMs around a row softmax:
+S = Q K^T (fp32), P = softmax(S / sqrt(C)) (fp16), O = P V with V^T produced directly by the value projection.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from .configs import VAEConfig
+from .ops import Ops
+from .unet import LATENT_CPAD, _Conv, _Params, _ResBlock
+
+RGB_CPAD = 8  # decoded image travels as [B, H, W, 8] fp16 (3 real channels)
+
+
+class DeviceVAEDecoder:
+    def __init__(self, ops: Ops, sd: Dict[str, torch.Tensor], cfg: VAEConfig):
+        self.ops, self.cfg = ops, cfg
+        P = self.P = _Params(sd, ops.device)
+        g, eps = cfg.norm_num_groups, cfg.norm_eps
+        ch = cfg.block_out_channels
+        top = ch[-1]
+        lc = cfg.latent_channels
+        # post_quant_conv (1x1, 4 -> 4) as a linear over 8-channel padded pixels
+        wq = torch.zeros(lc, LATENT_CPAD, dtype=torch.float16)
+        wq[:, :lc] = P.host16("post_quant_conv.weight").reshape(lc, lc)
+        self.pq_w, self.pq_b = wq.to(ops.device), P.f32("post_quant_conv.bias")
+        self.conv_in = _Conv(P, "decoder.conv_in", cin_layout=(lc, LATENT_CPAD))
+        self.mid0 = _ResBlock(P, "decoder.mid_block.resnets.0", (top,), g, eps)
+        self.mid1 = _ResBlock(P, "decoder.mid_block.resnets.1", (top,), g, eps)
+        a = "decoder.mid_block.attentions.0"
+        self.at_g, self.at_b = P.f32(f"{a}.group_norm.weight"), P.f32(f"{a}.group_norm.bias")
+        self.wq, self.bq = P.f16(f"{a}.to_q.weight"), P.f32(f"{a}.to_q.bias")
+        self.wk, self.bk = P.f16(f"{a}.to_k.weight"), P.f32(f"{a}.to_k.bias")
+        self.wv, self.bv = P.f16(f"{a}.to_v.weight"), P.f32(f"{a}.to_v.bias")
+        self.wo, self.bo = P.f16(f"{a}.to_out.0.weight"), P.f32(f"{a}.to_out.0.bias")
+        self.up: List = []
+        prev = top
+        for i, cout in enumerate(reversed(ch)):
+            res = []
+            for j in range(cfg.layers_per_block + 1):
+                res.append(_ResBlock(P, f"decoder.up_blocks.{i}.resnets.{j}", (prev,), g, eps))
+                prev = cout
+            us = _Conv(P, f"decoder.up_blocks.{i}.upsamplers.0.conv") if i < len(ch) - 1 else None
+            self.up.append((res, us))
+        self.out_g, self.out_b = P.f32("decoder.conv_norm_out.weight"), P.f32("decoder.conv_norm_out.bias")
+        self.conv_out = _Conv(P, "decoder.conv_out")
+
+    def _mid_attention(self, h: torch.Tensor) -> torch.Tensor:
+        ops = self.ops
+        B, H, W, C = h.shape
+        T = H * W
+        n = ops.group_norm(h, self.at_g, self.at_b, self.cfg.norm_num_groups, self.cfg.norm_eps, silu=False)
+        outs = []
+        for b in range(B):  # one [T, T] score matrix at a time
+            nb = n[b].reshape(T, C)
+            q = ops.linear(nb, self.wq, bias=self.bq)
+            k = ops.linear(nb, self.wk, bias=self.bk)
+            # V^T [C, T] = Wv @ n^T: the value projection with operands swapped, so P V needs no transpose kernel.
+            # Its bias is added after P V instead (softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T).
+            vt = ops.linear(self.wv, nb)
+            s = ops.linear(q, k, out_fp32=True)           # fp32 scores: |q.k| over 512 dims is too coarse in fp16
+            pr = ops.softmax_rows(s, scale=C ** -0.5)
+            o = ops.linear(pr, vt, bias=self.bv)
+            outs.append(ops.linear(o, self.wo, bias=self.bo, residual=h[b].reshape(T, C)))
+        out = outs[0] if B == 1 else torch.cat(outs, dim=0)
+        return out.reshape(B, H, W, C)
+
+    def decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """z: [B, h, w, 8] fp16 latents already divided by scaling_factor -> [B, 8h, 8w, 8] fp16 (RGB in 0..2)."""
+        ops = self.ops
+        B, hh, ww, _ = z.shape
+        zq = torch.zeros_like(z)
+        ops.linear(z.reshape(-1, LATENT_CPAD), self.pq_w, bias=self.pq_b, out=zq.reshape(-1, LATENT_CPAD))
+        h = self.conv_in(ops, zq)
+        h = self.mid0(ops, h, None, None)
+        h = self._mid_attention(h)
+        h = self.mid1(ops, h, None, None)
+        for res, us in self.up:
+            for rb in res:
+                h = rb(ops, h, None, None)
+            if us is not None:
+                h = us(ops, ops.upsample_nearest2x(h))
+        n = ops.group_norm(h, self.out_g, self.out_b, self.cfg.norm_num_groups, self.cfg.norm_eps, silu=True)
+        if out is None:
+            out = torch.zeros(B, hh * 8, ww * 8, RGB_CPAD, dtype=torch.float16, device=z.device)
+        return self.conv_out(ops, n, out=out)

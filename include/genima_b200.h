@@ -111,8 +111,11 @@ int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x1, int C1, 
 /* LayerNorm over the last dim of a [rows, C] fp16 matrix (fp32 statistics). */
 int gn_layer_norm(gn_handle* h, const void* x, int64_t ldx, int rows, int C, float eps, const float* gamma,
                   const float* beta, void* y, int64_t ldy, void* stream);
-/* Row softmax of a [rows, cols] fp16 matrix in place of torch.softmax (VAE mid-block attention, 1 head d=512). */
-int gn_softmax_rows(gn_handle* h, void* x, int64_t ldx, int rows, int cols, float scale, void* stream);
+/* y[rows, cols] (fp16) = softmax(scale * x[rows, cols]) row-wise; x is fp32 (x_fp32 = 1, e.g. attention scores from
+ * gn_linear with out_fp32) or fp16 (may then alias y).  Replaces torch.softmax inside the VAE mid-block attention
+ * (diffusers Attention with 1 head, d = 512). */
+int gn_softmax_rows(gn_handle* h, const void* x, int x_fp32, int64_t ldx, void* y, int64_t ldy, int rows, int cols,
+                    float scale, void* stream);
 
 /* ---- data movement / elementwise --------------------------------------------------------------------------- */
 /* y[B, 2H, 2W, C] = nearest-neighbour x2 upsample of x[B, H, W, C] (diffusers Upsample2D before its conv). */
@@ -130,9 +133,11 @@ int gn_euler_step(gn_handle* h, const void* x, const void* eps, float sigma, flo
                   void* x_scaled, int64_t n, void* stream);
 /* y = x * s (fp16), used for scale_model_input at step 0 and latents / scaling_factor before the VAE. */
 int gn_scale(gn_handle* h, const void* x, float s, void* y, int64_t n, void* stream);
-/* NCHW fp16/fp32 <-> NHWC fp16 with channel padding (pad channels zero-filled). src_fp32: 1 if src is float. */
-int gn_nchw_to_nhwc(gn_handle* h, const void* src, int src_fp32, int B, int C, int H, int W, int Cpad, void* dst,
-                    void* stream);
+/* NCHW fp16/fp32 <-> NHWC fp16 with channel padding (pad channels zero-filled). src_fp32: 1 if src is float.
+ * mean3/std3 (host pointers, may be NULL): channels 0..2 become (src / 255 - mean) / std — GenimaACTPolicy.forward's
+ * `self.normalize(image / 255.0)` (controller/method/genima_act.py:188) fused into the layout change. */
+int gn_nchw_to_nhwc(gn_handle* h, const void* src, int src_fp32, int B, int C, int H, int W, int Cpad,
+                    const float* mean3, const float* std3, void* dst, void* stream);
 int gn_nhwc_to_nchw(gn_handle* h, const void* src, int B, int C, int H, int W, int Cpad, void* dst, int dst_fp32,
                     void* stream);
 /* uint8 NHWC RGB [B, H, W, 3] -> fp16 NHWC [B, H, W, Cpad] = (u8 / 255 - mean[c]) / std[c]; (mean, std) = (0, 1) gives
@@ -145,6 +150,14 @@ int gn_nhwc_to_u8(gn_handle* h, const void* src, int B, int H, int W, int Cpad, 
  * [512, 512, 3] tile (view k -> quadrant (k % 2, k / 2)). */
 int gn_tile_views(gn_handle* h, const void* views_u8, int B, void* tile_u8, void* stream);
 int gn_untile_views(gn_handle* h, const void* tile_u8, int B, void* views_u8, void* stream);
+
+/* CLIP text embeddings: out[b, t, :] = tok_emb[ids[b, t], :] + pos_emb[t, :]; ids int64 [B, T] on device. */
+int gn_embed_tokens(gn_handle* h, const void* ids_i64, const void* tok_emb, const void* pos_emb, int B, int T, int D,
+                    int vocab, void* out, void* stream);
+/* Fold FiLM (film = [gamma | beta], fp32 [2C]) into a FrozenBatchNorm affine (scale, shift fp32 [C]):
+ * scale_out = (1 + gamma) * bn_scale, shift_out = (1 + gamma) * bn_shift + beta  (ACT ResNet-18 BasicBlock). */
+int gn_film_fold(gn_handle* h, const float* film, const float* bn_scale, const float* bn_shift, float* scale_out,
+                 float* shift_out, int C, void* stream);
 
 #ifdef __cplusplus
 }

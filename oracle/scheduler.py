@@ -1,0 +1,55 @@
+"""CPU restatement of diffusers 0.29.0 EulerDiscreteScheduler as shipped with stabilityai/sd-turbo
+(schedulers/scheduling_euler_discrete.py: __init__, set_timesteps, scale_model_input, step with s_churn = 0).
+TEST INFRASTRUCTURE — see oracle/__init__.  The reference never overrides pipe.scheduler on the eval path
+(controller/agent/sd_controlnet_agent.py:31-42), so this is the scheduler its `pipe(...)` call runs.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class EulerDiscreteOracle:
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, timestep_spacing="trailing"):
+        self.num_train_timesteps = num_train_timesteps
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.train_sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
+        self.timestep_spacing = timestep_spacing
+        self.timesteps = None
+        self.sigmas = None
+
+    def set_timesteps(self, n: int):
+        T = self.num_train_timesteps
+        if self.timestep_spacing == "trailing":
+            ts = np.round(np.arange(T, 0, -T / n)).astype(np.float64) - 1
+        elif self.timestep_spacing == "leading":
+            ts = (np.arange(0, n) * (T // n)).round()[::-1].astype(np.float64)
+        elif self.timestep_spacing == "linspace":
+            ts = np.linspace(0, T - 1, n, dtype=np.float64)[::-1].copy()
+        else:
+            raise ValueError(self.timestep_spacing)
+        sig = np.interp(ts, np.arange(0, T), self.train_sigmas)
+        self.sigmas = np.concatenate([sig, [0.0]]).astype(np.float32)
+        self.timesteps = ts.astype(np.float32)
+        return self.timesteps, self.sigmas
+
+    @property
+    def init_noise_sigma(self) -> float:
+        m = float(self.sigmas.max())
+        if self.timestep_spacing in ("linspace", "trailing"):
+            return m
+        return float((m ** 2 + 1) ** 0.5)
+
+    def scale_model_input(self, x: torch.Tensor, i: int) -> torch.Tensor:
+        s = float(self.sigmas[i])
+        return x / ((s ** 2 + 1) ** 0.5)
+
+    def step(self, eps: torch.Tensor, i: int, x: torch.Tensor) -> torch.Tensor:
+        """Upstream arithmetic order, in fp32: x0 = x - sigma*eps; d = (x - x0)/sigma; x + d*(sigma_next - sigma)."""
+        sigma = float(self.sigmas[i])
+        sigma_next = float(self.sigmas[i + 1])
+        x = x.to(torch.float32)
+        x0 = x - sigma * eps.to(torch.float32)
+        d = (x - x0) / sigma
+        return x + d * (sigma_next - sigma)

@@ -61,8 +61,12 @@ def test_layer_norm(ops, rows, C):
 def test_softmax_rows(ops):
     x = _rand((512, 4096), 6, 4.0)
     scale = 1.0 / math.sqrt(512)
-    out = ops.softmax_rows_(x.cuda().clone(), scale)
-    report_close("softmax_rows", out, torch.softmax(x.float() * scale, dim=-1), rtol=1e-3, atol=1e-6)
+    out = ops.softmax_rows(x.cuda().clone(), scale)
+    report_close("softmax_rows fp16", out, torch.softmax(x.float() * scale, dim=-1), rtol=1e-3, atol=1e-6)
+    x32 = x.float() * 37.0
+    out = ops.softmax_rows(x32.cuda(), scale)
+    assert out.dtype == torch.float16
+    report_close("softmax_rows fp32 in", out, torch.softmax(x32 * scale, dim=-1), rtol=1e-3, atol=1e-6)
 
 
 def test_upsample_maxpool_add_scale(ops):
@@ -92,8 +96,11 @@ def test_euler_step(ops):
     sigma, sigma_next = 14.6146, 4.0
     xs = torch.empty_like(x).cuda()
     xn, _ = ops.euler_step(x.cuda(), eps.cuda(), sigma, sigma_next, x_scaled=xs)
-    ref = (x.float() + (sigma_next - sigma) * eps.float()).to(torch.float16)
-    assert torch.equal(xn.cpu(), ref)  # fp32 update, one rounding to fp16: bit-exact
+    dsigma = float(np.float32(sigma_next) - np.float32(sigma))  # the kernel forms the step in fp32
+    ref = (x.float() + dsigma * eps.float()).to(torch.float16)
+    # fp32 update + one rounding to fp16; an FMA contraction may flip the last fp16 bit of a few elements
+    report_close("euler x_next", xn, ref.float(), rtol=1e-3, atol=1e-4)
+    assert float((xn.cpu() != ref).float().mean()) < 0.01
     report_close("euler x_scaled", xs, ref.float() / math.sqrt(sigma_next ** 2 + 1))
 
 
