@@ -54,6 +54,9 @@ SIGNATURES = {
     "gn_set_gemm_tuning": (_i, [_vp, _i, _i]),
     "gn_get_last_gemm_config": (_i, [_vp, C.POINTER(C.c_int32)]),
     "gn_launch_count": (_i64, [_vp]),
+    "gn_profile_begin": (_i, [_vp]),
+    "gn_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                            C.POINTER(C.c_double)]),
     "gn_linear": (_i, [_vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i64, C.POINTER(GnEpilogue), _vp]),
     "gn_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i64,
                        C.POINTER(GnEpilogue), _vp]),
@@ -72,8 +75,8 @@ SIGNATURES = {
     "gn_nhwc_to_nchw": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "gn_u8_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),
     "gn_nhwc_to_u8": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
-    "gn_tile_views": (_i, [_vp, _vp, _i, _vp, _vp]),
-    "gn_untile_views": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gn_tile_views": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "gn_untile_views": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "gn_embed_tokens": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "gn_film_fold": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
 }

@@ -1,0 +1,302 @@
+"""Device-side Genima ACT controller on the C-ABI kernels.
+
+Replaces, on the reference's eval path, `GenimaACTPolicy.forward` (controller/method/genima_act.py:165-214) and what it
+calls: RoboBase `ImageEncoderACT` (ResNet-18 trunk with FrozenBatchNorm2d + FiLM, 1x1 input projection, sine position
+embedding; cfg controller/cfgs/method/genima_act.yaml:29-39) and `GenimaMVTransformer.forward`
+(controller/method/genima_act.py:27-92: proprio MLP, zero latent, DETR post-norm transformer, action / is_pad heads).
+Same graph as oracle/act.py, different execution:
+
+  * the `image / 255 -> Normalize(ImageNet)` of genima_act.py:188 is fused into the NCHW->NHWC (or u8->NHWC) layout kernel;
+  * FrozenBatchNorm2d is folded into the per-channel (scale, bias) of the convolution epilogue, ReLU and the residual add
+    ride in the same epilogue; FiLM ((1 + gamma) * bn2(.) + beta) is folded into that affine by gn_film_fold, and the
+    eight FiLM projections of the task embedding are ONE GEMM, cached while the task embedding tensor is unchanged;
+  * every `x + pos` that feeds an attention projection is folded into a per-row fp32 bias of the projection GEMM
+    (W (x + pos) + b = W x + (W pos + b)); position embeddings, query embeddings and the zero-latent token are constants,
+    so these tables are built once at bind time with the same GEMM kernel.  Tokens stay in per-view order: attention is
+    permutation-equivariant and the position table is permuted to match, so no concat-along-width copy exists;
+  * the cross-attention K/V projections of all decoder layers are one GEMM over the encoder memory.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .configs import ACTConfig
+from .ops import Ops
+from .packing import pack_conv_weight
+from .unet import _Params, tensor_key
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+IMG_CPAD = 8  # normalised RGB travels as [N, H, W, 8] fp16
+
+
+def _sine_position_table(h: int, w: int, num_pos_feats: int, temperature: float = 10000.0) -> torch.Tensor:
+    """DETR PositionEmbeddingSine(normalize=True) of one unmasked [h, w] feature map -> [h*w, 2*npf] fp32 (host).
+    A data-independent constant table (like a weight), built once at bind time."""
+    eps, scale = 1e-6, 2 * math.pi
+    y = torch.arange(1, h + 1, dtype=torch.float32)[:, None].expand(h, w) / (h + eps) * scale
+    x = torch.arange(1, w + 1, dtype=torch.float32)[None, :].expand(h, w) / (w + eps) * scale
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / num_pos_feats)
+    px = x[:, :, None] / dim_t
+    py = y[:, :, None] / dim_t
+    px = torch.stack((px[:, :, 0::2].sin(), px[:, :, 1::2].cos()), dim=3).flatten(2)
+    py = torch.stack((py[:, :, 0::2].sin(), py[:, :, 1::2].cos()), dim=3).flatten(2)
+    return torch.cat((py, px), dim=2).reshape(h * w, 2 * num_pos_feats)
+
+
+class _BNConv:
+    """conv (no bias) + FrozenBatchNorm2d folded to (scale, shift) of the epilogue."""
+
+    def __init__(self, P: _Params, conv: str, bn: str, stride: int, eps: float, cin_layout=()):
+        w = P.host16(f"{conv}.weight")
+        self.cout, self.k, self.stride = w.shape[0], w.shape[2], stride
+        self.pad = self.k // 2
+        self.w = pack_conv_weight(w, cin_layout=cin_layout).to(P.device)
+        g, b = P.sd[f"{bn}.weight"].float(), P.sd[f"{bn}.bias"].float()
+        rm, rv = P.sd[f"{bn}.running_mean"].float(), P.sd[f"{bn}.running_var"].float()
+        scale = g * (rv + eps).rsqrt()
+        self.scale = scale.to(P.device).contiguous()
+        self.shift = (b - rm * scale).to(P.device).contiguous()
+
+    def __call__(self, ops: Ops, x, scale=None, shift=None, **epi):
+        return ops.conv2d(x, self.w, self.cout, ksize=self.k, stride=self.stride, pad=self.pad,
+                          scale=self.scale if scale is None else scale, bias=self.shift if shift is None else shift,
+                          **epi)
+
+
+class _MHA:
+    """torch.nn.MultiheadAttention parameters, split for the fused projections."""
+
+    def __init__(self, P: _Params, prefix: str, d: int):
+        wi = P.host16(f"{prefix}.in_proj_weight")
+        bi = P.sd[f"{prefix}.in_proj_bias"].float()
+        self.wq, self.wk, self.wv = wi[:d], wi[d:2 * d], wi[2 * d:]
+        self.bq, self.bk, self.bv = bi[:d], bi[d:2 * d], bi[2 * d:]
+        self.wo, self.bo = P.f16(f"{prefix}.out_proj.weight"), P.f32(f"{prefix}.out_proj.bias")
+
+
+class DeviceACT:
+    def __init__(self, ops: Ops, sd: Dict[str, torch.Tensor], cfg: ACTConfig = ACTConfig()):
+        self.ops, self.cfg = ops, cfg
+        dev = ops.device
+        P = self.P = _Params(sd, dev)
+        b = "encoder_model.backbone"
+        eps = cfg.bn_eps
+        self.stem = _BNConv(P, f"{b}.conv1", f"{b}.bn1", 2, eps, cin_layout=(3, IMG_CPAD))
+        self.blocks: List[dict] = []
+        film_w, film_b = [], []
+        cin = cfg.resnet_widths[0]
+        for li, cout in enumerate(cfg.resnet_widths):
+            for bi in range(2):
+                p = f"{b}.layer{li + 1}.{bi}"
+                stride = 2 if (li > 0 and bi == 0) else 1
+                blk = dict(c1=_BNConv(P, f"{p}.conv1", f"{p}.bn1", stride, eps),
+                           c2=_BNConv(P, f"{p}.conv2", f"{p}.bn2", 1, eps), cout=cout, ds=None)
+                if P.has(f"{p}.downsample.0.weight"):
+                    blk["ds"] = _BNConv(P, f"{p}.downsample.0", f"{p}.downsample.1", stride, eps)
+                    blk["ds"].pad = 0
+                film_w.append(P.host16(f"{p}.film.weight"))
+                film_b.append(P.sd[f"{p}.film.bias"].float())
+                self.blocks.append(blk)
+                cin = cout
+        self.film_w = torch.cat(film_w, 0).contiguous().to(dev)          # one GEMM for the eight FiLM projections
+        self.film_b = torch.cat(film_b, 0).contiguous().to(dev)
+        self._film_key = None
+        self._film: List[List[Tuple[torch.Tensor, torch.Tensor]]] = []
+        d = cfg.hidden_dim
+        self.proj_w = P.f16("encoder_model.input_proj.weight").reshape(d, -1).contiguous()
+        self.proj_b = P.f32("encoder_model.input_proj.bias")
+
+        a = "actor_model"
+        self.ps_w0 = P.f16(f"{a}.input_proj_robot_state.0.weight")
+        self.ps_b0 = P.f32(f"{a}.input_proj_robot_state.0.bias")
+        self.ps_w1 = P.f16(f"{a}.input_proj_robot_state.2.weight")
+        self.ps_b1 = P.f32(f"{a}.input_proj_robot_state.2.bias")
+        # latent_out_proj(zeros) == its bias (genima_act.py:71-75): a constant token
+        self.latent_tok = P.sd[f"{a}.latent_out_proj.bias"].to(dev, torch.float16).reshape(1, d).contiguous()
+
+        fh = cfg.image_size // 32
+        self.fh = fh
+        self.tokens_per_view = fh * fh
+        self.T = 2 + cfg.num_views * self.tokens_per_view
+        # position table in OUR token order: [latent, proprio, view0 (row-major h, w), view1, ...]
+        view_pos = _sine_position_table(fh, fh, d // 2)
+        add_pos = P.sd[f"{a}.additional_pos_embed.weight"].float()
+        pos = torch.cat([add_pos] + [view_pos] * cfg.num_views, 0)        # [T, d] fp32
+        self.pos16 = pos.to(dev, torch.float16).contiguous()
+        qpos_emb = P.sd[f"{a}.query_embed.weight"].float()
+        self.query16 = qpos_emb.to(dev, torch.float16).contiguous()
+        self.nq = cfg.num_queries
+
+        def posbias(w_rows: torch.Tensor, b_rows: torch.Tensor, table16: Optional[torch.Tensor]):
+            """fp32 [rows, n] = table @ w^T + b (or the plain bias broadcast when table is None)."""
+            if table16 is None:
+                return None
+            return ops.linear(table16, w_rows.contiguous().to(dev), bias=b_rows.to(dev).contiguous(), out_fp32=True)
+
+        self.enc: List[dict] = []
+        for i in range(cfg.enc_layers):
+            p = f"{a}.transformer.encoder.layers.{i}"
+            m = _MHA(P, f"{p}.self_attn", d)
+            w_qkv = torch.cat([m.wq, m.wk, m.wv], 0).contiguous().to(dev)
+            # row bias: [Wq pos + bq | Wk pos + bk | bv]
+            rq = posbias(m.wq, m.bq, self.pos16)
+            rk = posbias(m.wk, m.bk, self.pos16)
+            rv = m.bv.to(dev)[None, :].expand(self.T, -1)
+            self.enc.append(dict(w_qkv=w_qkv, rb=torch.cat([rq, rk, rv], 1).contiguous(), wo=m.wo, bo=m.bo,
+                                 w1=P.f16(f"{p}.linear1.weight"), b1=P.f32(f"{p}.linear1.bias"),
+                                 w2=P.f16(f"{p}.linear2.weight"), b2=P.f32(f"{p}.linear2.bias"),
+                                 n1=(P.f32(f"{p}.norm1.weight"), P.f32(f"{p}.norm1.bias")),
+                                 n2=(P.f32(f"{p}.norm2.weight"), P.f32(f"{p}.norm2.bias"))))
+        self.dec: List[dict] = []
+        w_mem, rb_mem = [], []
+        for i in range(cfg.dec_layers):
+            p = f"{a}.transformer.decoder.layers.{i}"
+            s = _MHA(P, f"{p}.self_attn", d)
+            c = _MHA(P, f"{p}.multihead_attn", d)
+            w_qkv = torch.cat([s.wq, s.wk, s.wv], 0).contiguous().to(dev)
+            rq = posbias(s.wq, s.bq, self.query16)
+            rk = posbias(s.wk, s.bk, self.query16)
+            rv = s.bv.to(dev)[None, :].expand(self.nq, -1)
+            # cross attention: q = Wq (tgt + query_pos); k = Wk (memory + pos); v = Wv memory
+            w_mem += [c.wk, c.wv]
+            rb_mem += [posbias(c.wk, c.bk, self.pos16), c.bv.to(dev)[None, :].expand(self.T, -1)]
+            self.dec.append(dict(w_qkv=w_qkv, rb=torch.cat([rq, rk, rv], 1).contiguous(), wo=s.wo, bo=s.bo,
+                                 wq_c=c.wq.contiguous().to(dev), rb_qc=posbias(c.wq, c.bq, self.query16),
+                                 wo_c=c.wo, bo_c=c.bo,
+                                 w1=P.f16(f"{p}.linear1.weight"), b1=P.f32(f"{p}.linear1.bias"),
+                                 w2=P.f16(f"{p}.linear2.weight"), b2=P.f32(f"{p}.linear2.bias"),
+                                 n=[(P.f32(f"{p}.norm{k}.weight"), P.f32(f"{p}.norm{k}.bias")) for k in (1, 2, 3)]))
+        self.w_mem = torch.cat(w_mem, 0).contiguous().to(dev)             # [dec_layers * 2d, d]
+        self.rb_mem = torch.cat(rb_mem, 1).contiguous()                   # [T, dec_layers * 2d] fp32
+        self.dec_norm = (P.f32(f"{a}.transformer.decoder.norm.weight"), P.f32(f"{a}.transformer.decoder.norm.bias"))
+        self.w_head = torch.cat([P.host16(f"{a}.action_head.weight"), P.host16(f"{a}.is_pad_head.weight")],
+                                0).contiguous().to(dev)
+        self.b_head = torch.cat([P.sd[f"{a}.action_head.bias"].float(), P.sd[f"{a}.is_pad_head.bias"].float()],
+                                0).to(dev)
+        self._rb_cache: Dict[int, dict] = {}
+        torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------------------------------------ hoisted work
+    def _row_biases(self, B: int) -> dict:
+        """Per-row bias tables repeated for a batch of B sequences (row m of the GEMM = token m % T of sample m // T)."""
+        if B not in self._rb_cache:
+            rep = lambda t: t if B == 1 else t.repeat(B, 1).contiguous()  # noqa: E731
+            self._rb_cache[B] = dict(enc=[rep(L["rb"]) for L in self.enc], dec=[rep(L["rb"]) for L in self.dec],
+                                     dec_qc=[rep(L["rb_qc"]) for L in self.dec], mem=rep(self.rb_mem))
+        return self._rb_cache[B]
+
+    def film_affines(self, task_emb: torch.Tensor) -> List[List[Tuple[torch.Tensor, torch.Tensor]]]:
+        """task_emb [B, E] fp32 -> per sample, per BasicBlock (scale, shift) of bn2 with FiLM folded in.
+        Constant per episode (the task text does not change): cached while the same tensor is passed."""
+        key = tensor_key(task_emb)
+        if key == self._film_key:
+            return self._film
+        ops = self.ops
+        te16 = ops.nchw_to_nhwc(task_emb.reshape(task_emb.shape[0], -1, 1, 1).contiguous())  # fp32 -> fp16 [B,1,1,E]
+        film = ops.linear(te16.reshape(task_emb.shape[0], -1), self.film_w, bias=self.film_b, out_fp32=True)
+        out = []
+        for bidx in range(task_emb.shape[0]):
+            per_block, off = [], 0
+            for blk in self.blocks:
+                c = blk["cout"]
+                per_block.append(ops.film_fold(film[bidx, off:off + 2 * c], blk["c2"].scale, blk["c2"].shift))
+                off += 2 * c
+            out.append(per_block)
+        self._film_key, self._film, self._film_owner = key, out, task_emb
+        return out
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def backbone(self, img: torch.Tensor, film: List[Tuple[torch.Tensor, torch.Tensor]],
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """img [N, H, W, 8] fp16 normalised -> [N * H/32 * W/32, hidden] fp16 (ResNet-18 trunk + 1x1 input_proj)."""
+        ops = self.ops
+        h = self.stem(ops, img, act_pre="relu")
+        h = ops.maxpool3x3s2(h)
+        for blk, (fs, fb) in zip(self.blocks, film):
+            idt = h if blk["ds"] is None else blk["ds"](ops, h)
+            o = blk["c1"](ops, h, act_pre="relu")
+            h = blk["c2"](ops, o, scale=fs, shift=fb, residual=idt, act_post="relu")
+        N, fh, fw, C = h.shape
+        return ops.linear(h.reshape(N * fh * fw, C), self.proj_w, bias=self.proj_b, out=out)
+
+    def _attn(self, q, k, v, B, Tq, Tk):
+        cfg = self.cfg
+        hd = cfg.hidden_dim // cfg.nheads
+        return self.ops.attention_small(q, k, v, B, cfg.nheads, hd, Tq, Tk, hd ** -0.5)
+
+    def _buffers(self, B: int) -> dict:
+        """Persistent input buffers: the encoder sequence (token 0 = the constant zero-latent token, pre-filled) and the
+        all-zero initial decoder target."""
+        rb = self._row_biases(B)
+        if "src" not in rb:
+            d = self.cfg.hidden_dim
+            src = torch.zeros(B, self.T, d, dtype=torch.float16, device=self.ops.device)
+            src[:, 0, :] = self.latent_tok
+            rb["src"] = src
+            rb["tgt0"] = torch.zeros(B * self.nq, d, dtype=torch.float16, device=self.ops.device)
+        return rb
+
+    def forward_tokens(self, qpos16: torch.Tensor, B: int):
+        """Runs the transformer on the sequence buffer whose image tokens `backbone(out=...)` has filled (per-view
+        order); qpos16 [B, state_dim] fp16 -> (a_hat [B, nq, A], is_pad [B, nq, 1]) fp32."""
+        ops, cfg = self.ops, self.cfg
+        d, T, nq = cfg.hidden_dim, self.T, self.nq
+        rb = self._buffers(B)
+        src = rb["src"]
+        pr = ops.linear(qpos16, self.ps_w0, bias=self.ps_b0)
+        ops.linear(pr, self.ps_w1, bias=self.ps_b1, out=src[:, 1, :])
+        src = src.reshape(B * T, d)
+        for L, rbe in zip(self.enc, rb["enc"]):
+            qkv = ops.linear(src, L["w_qkv"], rowvec=rbe, rows_per_batch=1)
+            a = self._attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, T, T)
+            src = ops.layer_norm(ops.linear(a, L["wo"], bias=L["bo"], residual=src), *L["n1"], eps=cfg.ln_eps)
+            f = ops.linear(src, L["w1"], bias=L["b1"], act_pre="relu")
+            src = ops.layer_norm(ops.linear(f, L["w2"], bias=L["b2"], residual=src), *L["n2"], eps=cfg.ln_eps)
+        mem_kv = ops.linear(src, self.w_mem, rowvec=rb["mem"], rows_per_batch=1)  # [B*T, dec_layers * 2d]
+        tgt = rb["tgt0"]
+        for i, L in enumerate(self.dec):
+            qkv = ops.linear(tgt, L["w_qkv"], rowvec=rb["dec"][i], rows_per_batch=1)
+            a = self._attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, nq, nq)
+            tgt = ops.layer_norm(ops.linear(a, L["wo"], bias=L["bo"], residual=tgt), *L["n"][0], eps=cfg.ln_eps)
+            q = ops.linear(tgt, L["wq_c"], rowvec=rb["dec_qc"][i], rows_per_batch=1)
+            kc = mem_kv[:, 2 * i * d:(2 * i + 1) * d]
+            vc = mem_kv[:, (2 * i + 1) * d:(2 * i + 2) * d]
+            a = self._attn(q, kc, vc, B, nq, T)
+            tgt = ops.layer_norm(ops.linear(a, L["wo_c"], bias=L["bo_c"], residual=tgt), *L["n"][1], eps=cfg.ln_eps)
+            f = ops.linear(tgt, L["w1"], bias=L["b1"], act_pre="relu")
+            tgt = ops.layer_norm(ops.linear(f, L["w2"], bias=L["b2"], residual=tgt), *L["n"][2], eps=cfg.ln_eps)
+        hs = ops.layer_norm(tgt, *self.dec_norm, eps=cfg.ln_eps)
+        out = ops.linear(hs, self.w_head, bias=self.b_head, out_fp32=True).reshape(B, nq, cfg.action_dim + 1)
+        return out[:, :, :cfg.action_dim], out[:, :, cfg.action_dim:]
+
+    @torch.no_grad()
+    def forward(self, qpos: torch.Tensor, image: torch.Tensor, task_emb: torch.Tensor):
+        """qpos [B, state_dim] fp32; image [B, V, 3, H, W] fp32/fp16 in 0..255 (the reference's layout) or uint8
+        [B, V, H, W, 3] (device-side untile output); task_emb [B, E] fp32.  -> (a_hat, is_pad_hat) fp32."""
+        ops, cfg = self.ops, self.cfg
+        B, V = image.shape[:2]
+        if V != cfg.num_views:
+            raise ValueError(f"expected {cfg.num_views} views, got {V}")
+        if image.dtype == torch.uint8:
+            if image.shape[-1] != 3:
+                raise ValueError("uint8 images must be [B, V, H, W, 3]")
+            img = ops.u8_to_nhwc(image.reshape(B * V, *image.shape[2:]).contiguous(), cpad=IMG_CPAD,
+                                 mean=IMAGENET_MEAN, std=IMAGENET_STD)
+        else:
+            if image.shape[2] != 3:
+                raise ValueError("float images must be [B, V, 3, H, W]")
+            img = ops.nchw_to_nhwc(image.reshape(B * V, *image.shape[2:]).contiguous(), cpad=IMG_CPAD,
+                                   mean=IMAGENET_MEAN, std=IMAGENET_STD)
+        if img.shape[1] != cfg.image_size or img.shape[2] != cfg.image_size:
+            raise ValueError(f"expected {cfg.image_size}x{cfg.image_size} views, got {img.shape[1]}x{img.shape[2]}")
+        film = self.film_affines(task_emb.to(ops.device, torch.float32))
+        src = self._buffers(B)["src"]
+        for b in range(B):  # FiLM makes the bn2 affine per-sample; the V views of one sample run as one batch
+            self.backbone(img[b * V:(b + 1) * V], film[b], out=src[b, 2:, :])
+        qpos16 = ops.nchw_to_nhwc(qpos.to(ops.device, torch.float32).reshape(B, -1, 1, 1).contiguous())
+        return self.forward_tokens(qpos16.reshape(B, -1), B)

@@ -1,0 +1,228 @@
+"""Reference-facing plugin classes: the drop-in boundary of SURVEY.md §8(b).
+
+  B200ControlNetAgent      hydra `_target_` replacement for `agent.SDControlNetAgent`
+                           (controller/cfgs/eval_genima.yaml:27-28; controller/agent/sd_controlnet_agent.py:11-76 over
+                           controller/agent/diffusion_agent.py:5-65): same constructor (eval_cfg), same
+                           load_checkpoint / set_optimizations / common_setup / infer methods, same `.pipe` attribute and
+                           `transform_to_half_resolution`; `.pipe` is a B200ControlNetPipeline.
+  B200GenimaACTPolicy      replacement for `GenimaACTPolicy` (controller/method/genima_act.py:142-214): forward(qpos, image,
+                           actions=None, is_pad=None, task_emb=None) -> a_hat [B, 20, 8]; inference only.
+  B200GenimaACT            the `act` / `encode_clip_text` surface of `GenimaACT` (genima_act.py:273-346) on the obs-dict
+                           conventions of the eval loop (controller/eval_genima.py:237-248).
+Everything arithmetic goes to libgenima_b200.so; these classes only translate arguments.
+"""
+from __future__ import annotations
+
+import os
+import re
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import checkpoint as ckpt
+from . import weights as W
+from .act_policy import DeviceACT
+from .configs import ACTConfig, CLIPTextConfig, SchedulerConfig, UNetConfig, VAEConfig
+from .ops import Ops
+from .pipeline import B200ControlNetPipeline
+from .text_encoder import DeviceCLIPText
+from .unet import tensor_key
+
+_OPS: Dict[int, Ops] = {}
+
+
+def get_ops(device="cuda") -> Ops:
+    """One Ops (gn_handle + workspace) per device, shared by the diffusion agent and the controller."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    if idx not in _OPS:
+        _OPS[idx] = Ops(idx)
+    return _OPS[idx]
+
+
+def _cfg_get(cfg, name, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(name, default)
+    try:
+        v = getattr(cfg, name)
+    except Exception:
+        return default
+    return default if v is None and default is not None else v
+
+
+def _preset(name: str):
+    if name == "tiny":
+        return UNetConfig.tiny(), VAEConfig.tiny(), CLIPTextConfig.tiny(), ACTConfig.tiny()
+    if name in ("sd-turbo", "full", True):
+        return UNetConfig(), VAEConfig(), CLIPTextConfig.sd_turbo(), ACTConfig()
+    raise ValueError(f"unknown synthetic_weights preset {name!r} (use 'sd-turbo' or 'tiny')")
+
+
+class _CenterResize:
+    """transforms.Compose([Resize(r, BILINEAR), CenterCrop(r)]) on PIL images (controller/agent/diffusion_agent.py:44-62)
+    without the torchvision dependency; an identity when the image is already r x r."""
+
+    def __init__(self, resolution: int):
+        self.r = int(resolution)
+
+    def __call__(self, im):
+        from PIL import Image
+
+        w, h = im.size
+        if (w, h) == (self.r, self.r):
+            return im
+        if w <= h:
+            nw, nh = self.r, int(self.r * h / w)
+        else:
+            nw, nh = int(self.r * w / h), self.r
+        im = im.resize((nw, nh), Image.BILINEAR)
+        left, top = int(round((nw - self.r) / 2.0)), int(round((nh - self.r) / 2.0))
+        return im.crop((left, top, left + self.r, top + self.r))
+
+
+class B200ControlNetAgent:
+    """Drop-in for agent.SDControlNetAgent.  Extra eval_cfg keys (all optional): `synthetic_weights` ('sd-turbo' | 'tiny';
+    seeded synthetic weights when no checkpoint exists offline), `use_cuda_graph` (default True), `tokenizer` (callable
+    list[str] -> ids [B, 77]; no CLIP BPE vocabulary is available offline)."""
+
+    def __init__(self, eval_cfg, ops: Optional[Ops] = None):
+        self.eval_cfg = eval_cfg
+        self.pipe = None
+        self._ops = ops
+        self.load_checkpoint()
+        self.set_optimizations()
+        self.common_setup()
+
+    # ---- controller/agent/sd_controlnet_agent.py:19-65
+    def load_checkpoint(self):
+        cfg = self.eval_cfg
+        ops = self._ops or get_ops(_cfg_get(cfg, "device", "cuda"))
+        autoenc = _cfg_get(cfg, "autoencoder", "") or ""
+        if "taesd" in autoenc:
+            raise NotImplementedError("autoencoder='taesd' (AutoencoderTiny) is not implemented; use the KL-VAE")
+        synth = _cfg_get(cfg, "synthetic_weights", None)
+        tok = _cfg_get(cfg, "tokenizer", None)
+        graph = bool(_cfg_get(cfg, "use_cuda_graph", True))
+        if synth:
+            ucfg, vcfg, tcfg, _ = _preset(synth)
+            with_text = bool(_cfg_get(cfg, "synthetic_text_encoder", True))
+            self.pipe = B200ControlNetPipeline(
+                ops, W.synth_state_dict(W.unet_shapes(ucfg)), W.synth_state_dict(W.controlnet_shapes(ucfg), salt=1),
+                W.synth_state_dict(W.vae_decoder_shapes(vcfg), salt=2),
+                W.synth_state_dict(W.clip_text_shapes(tcfg)) if with_text else None,
+                ucfg, vcfg, tcfg, SchedulerConfig(), tokenizer=tok, use_cuda_graph=graph)
+            return
+        loaded = ckpt.load_sd_turbo(_cfg_get(cfg, "sd_ckpt"), _cfg_get(cfg, "diffusion_ckpt"))
+        self.pipe = B200ControlNetPipeline(ops, loaded["unet"], loaded["controlnet"], loaded["vae"], loaded["text"],
+                                           loaded["unet_cfg"], loaded["vae_cfg"], loaded["text_cfg"],
+                                           loaded["scheduler_cfg"], tokenizer=tok, use_cuda_graph=graph)
+
+    # ---- controller/agent/diffusion_agent.py:21-42 (the toggles are accepted; the kernels are always fused)
+    def set_optimizations(self):
+        cfg = self.eval_cfg
+        if _cfg_get(cfg, "vae_slicing", False):
+            self.pipe.vae.enable_slicing()
+        if _cfg_get(cfg, "upcast_vae", False):
+            self.pipe.upcast_vae()
+        if _cfg_get(cfg, "fused_projections", False):
+            self.pipe.fuse_qkv_projections(vae=False)
+        if _cfg_get(cfg, "enable_xformers_memory_efficient_attention", False):
+            self.pipe.enable_xformers_memory_efficient_attention()
+        self.pipe.set_progress_bar_config(disable=(not _cfg_get(cfg, "show_diffusion_progress", False)))
+        self.pipe.to(_cfg_get(cfg, "device", "cuda"))
+
+    # ---- controller/agent/diffusion_agent.py:44-62
+    def common_setup(self):
+        resolution = int(_cfg_get(self.eval_cfg, "image_resolution", 512))
+        self.transform_to_resolution = _CenterResize(resolution)
+        self.transform_to_half_resolution = _CenterResize(resolution // 2)
+
+    # ---- controller/agent/sd_controlnet_agent.py:67-76
+    def infer(self, *args, **kwargs):
+        return self.pipe(
+            prompt=kwargs["prompts"],
+            image=kwargs["images"],
+            negative_prompt=kwargs["negative_prompts"],
+            num_inference_steps=kwargs["num_inference_steps"],
+            guidance_scale=kwargs["guidance_scale"],
+            generator=kwargs["generator"],
+            **{k: kwargs[k] for k in ("latents", "prompt_embeds", "output_type") if k in kwargs},
+        )
+
+
+class B200GenimaACTPolicy:
+    """GenimaACTPolicy.forward (controller/method/genima_act.py:165-214), inference branch."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ACTConfig = ACTConfig(), ops: Optional[Ops] = None,
+                 device="cuda"):
+        self.cfg = cfg
+        self.ops = ops or get_ops(device)
+        self._sd = dict(state_dict)
+        self.impl = DeviceACT(self.ops, self._sd, cfg)
+        self.training = False
+
+    def state_dict(self):
+        return dict(self._sd)
+
+    def load_state_dict(self, sd, strict: bool = True):
+        ckpt.check_schema(sd, W.act_shapes(self.cfg), "ACT policy")
+        self._sd = dict(sd)
+        self.impl = DeviceACT(self.ops, self._sd, self.cfg)
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def forward(self, qpos: torch.Tensor, image: torch.Tensor, actions: torch.Tensor = None,
+                is_pad: torch.Tensor = None, task_emb: torch.Tensor = None) -> torch.Tensor:
+        if actions is not None:
+            raise NotImplementedError("training (actions is not None) is out of scope: this is the inference path")
+        if task_emb is None:
+            raise ValueError("task_emb is required (genima_act.yaml: use_lang_cond=True)")
+        a_hat, _ = self.impl.forward(qpos, image, task_emb)
+        return a_hat
+
+    __call__ = forward
+
+
+class B200GenimaACT:
+    """`GenimaACT.act` / `.encode_clip_text` (controller/method/genima_act.py:273-346)."""
+
+    def __init__(self, policy: B200GenimaACTPolicy, clip_state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 clip_cfg: CLIPTextConfig = CLIPTextConfig.vit_b32()):
+        self.actor = policy
+        self.ops = policy.ops
+        self.clip = DeviceCLIPText(self.ops, clip_state_dict, clip_cfg) if clip_state_dict is not None else None
+        self._emb_cache: Dict[bytes, tuple] = {}
+
+    def encode_clip_text(self, tokens: torch.Tensor):
+        """tokens [B, T, 77] int -> (task_emb [B, proj] fp32, last hidden [B*T, 77, d]).  The text is constant for an
+        episode (controller/env/rlbench_utils.py:156), so results are cached by token content."""
+        if self.clip is None:
+            raise RuntimeError("no CLIP text tower bound: pass clip_state_dict or supply task_emb yourself")
+        shape = tokens.shape
+        tks = tokens.reshape(-1, shape[-1])
+        key = tks.cpu().numpy().tobytes()
+        hit = self._emb_cache.get(key)
+        if hit is None:
+            if len(self._emb_cache) > 64:
+                self._emb_cache.clear()
+            emb, pooled = self.clip(tks.to(self.ops.device, torch.int64))
+            x = pooled.reshape(shape[0], shape[1], -1)[:, 0].contiguous()   # text does not change across frames
+            hit = (x, emb)
+            self._emb_cache[key] = hit
+        return hit
+
+    @torch.no_grad()
+    def act(self, obs: Dict[str, torch.Tensor], step: int = 0, eval_mode: bool = True) -> torch.Tensor:
+        """obs: low_dim_state [B, T, S]; `*rgb*` [B, T, 3, H, W] (dict order = view order); lang_tokens [B, T, 77]."""
+        low = obs["low_dim_state"]
+        qpos = low.reshape(low.shape[0], -1).float()
+        rgbs = [v for k, v in obs.items() if re.match(r"rgb.*", k) or "_rgb" in k]
+        rgb = torch.stack(rgbs, 1)                                    # [B, V, T, 3, H, W]
+        image = rgb.reshape(rgb.shape[0], -1, 3, rgb.shape[-2], rgb.shape[-1]).float()
+        task_emb, _ = self.encode_clip_text(obs["lang_tokens"])
+        return self.actor(qpos, image, task_emb=task_emb)

@@ -1,0 +1,191 @@
+"""On-disk weight formats of the reference -> plain {name: tensor} state dicts for the device graphs.
+
+  * diffusers directories as read by controller/agent/sd_controlnet_agent.py:19-42:
+      <diffusion_ckpt>/checkpoint-<N>/controlnet/{config.json, diffusion_pytorch_model.safetensors}   (last N, natural sort)
+      <sd_ckpt>/{unet,vae,text_encoder}/...(.fp16).safetensors, <sd_ckpt>/scheduler/scheduler_config.json
+  * RoboBase controller snapshots written by controller/train_act.py:262-279 and read by
+    controller/eval_genima.py:91-103: torch.save({... "agent": state_dict minus clip_model.*}) as latest.pt / <N>.pt.
+No checkpoint is available offline, so everything else in this repo runs on `synthetic_weights`
+(genima_b200/weights.py); these loaders exist so that a real checkpoint binds through the same schema tables and are
+exercised on round-tripped synthetic checkpoints in tests/test_checkpoint.py.
+"""
+from __future__ import annotations
+
+import dataclasses
+import json
+import os
+import re
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import weights as W
+from .configs import ACTConfig, CLIPTextConfig, SchedulerConfig, UNetConfig, VAEConfig
+
+
+def _natural_key(s: str):
+    return [int(t) if t.isdigit() else t.lower() for t in re.split(r"(\d+)", s)]
+
+
+def find_controlnet_dir(diffusion_ckpt: str) -> str:
+    """controller/agent/sd_controlnet_agent.py:19-29: the last `*checkpoint*` sub-directory in natural order, else the
+    directory itself."""
+    dirs = sorted((d for d in os.listdir(diffusion_ckpt) if "checkpoint" in d), key=_natural_key)
+    if dirs:
+        return os.path.join(diffusion_ckpt, dirs[-1], "controlnet")
+    return diffusion_ckpt
+
+
+def load_safetensors_dir(path: str, prefer_fp16: bool = True) -> Dict[str, torch.Tensor]:
+    """Reads diffusion_pytorch_model[.fp16].safetensors / model[.fp16].safetensors from a diffusers component dir."""
+    from safetensors.torch import load_file
+
+    names = []
+    for stem in ("diffusion_pytorch_model", "model"):
+        if prefer_fp16:
+            names.append(f"{stem}.fp16.safetensors")
+        names.append(f"{stem}.safetensors")
+    for n in names:
+        f = os.path.join(path, n)
+        if os.path.exists(f):
+            return load_file(f)
+    raise FileNotFoundError(f"no safetensors weight file in {path} (looked for {names})")
+
+
+def _read_json(path: str) -> dict:
+    with open(path) as f:
+        return json.load(f)
+
+
+def unet_config_from_json(cfg: dict) -> UNetConfig:
+    """diffusers unet/config.json or controlnet/config.json -> UNetConfig; rejects topologies the graphs do not cover."""
+    boc = tuple(cfg.get("block_out_channels", (320, 640, 1280, 1280)))
+    down = cfg.get("down_block_types", ("CrossAttnDownBlock2D",) * 3 + ("DownBlock2D",))
+    heads = cfg.get("attention_head_dim", (5, 10, 20, 20))
+    if isinstance(heads, int):
+        heads = (heads,) * len(boc)
+    if not cfg.get("use_linear_projection", True):
+        raise NotImplementedError("use_linear_projection=False (conv proj_in/out, SD-1.x) is not implemented")
+    if cfg.get("upcast_attention", False):
+        raise NotImplementedError("upcast_attention=True (SD-2.1-768) is not implemented")
+    if cfg.get("class_embed_type") or cfg.get("addition_embed_type"):
+        raise NotImplementedError("class / additional embeddings (SDXL) are not implemented")
+    ce = tuple(cfg.get("conditioning_embedding_out_channels", (16, 32, 96, 256)))
+    return UNetConfig(in_channels=cfg.get("in_channels", 4), out_channels=cfg.get("out_channels", 4),
+                      block_out_channels=boc, layers_per_block=cfg.get("layers_per_block", 2),
+                      num_heads=tuple(heads), attn_levels=tuple("CrossAttn" in t for t in down),
+                      cross_attention_dim=cfg.get("cross_attention_dim", 1024),
+                      norm_num_groups=cfg.get("norm_num_groups", 32), norm_eps=cfg.get("norm_eps", 1e-5),
+                      cond_embed_channels=ce, sample_size=cfg.get("sample_size", 64))
+
+
+def scheduler_config_from_json(cfg: dict) -> SchedulerConfig:
+    return SchedulerConfig(class_name=cfg.get("_class_name", "EulerDiscreteScheduler"),
+                           num_train_timesteps=cfg.get("num_train_timesteps", 1000),
+                           beta_start=cfg.get("beta_start", 0.00085), beta_end=cfg.get("beta_end", 0.012),
+                           beta_schedule=cfg.get("beta_schedule", "scaled_linear"),
+                           timestep_spacing=cfg.get("timestep_spacing", "trailing"),
+                           prediction_type=cfg.get("prediction_type", "epsilon"))
+
+
+def check_schema(sd: Dict[str, torch.Tensor], shapes, what: str, allow_extra: Tuple[str, ...] = ()) -> None:
+    """Every key of the schema must be present with the expected shape — a wrong architecture fails at load time."""
+    missing = [k for k in shapes if k not in sd]
+    bad = [k for k, shp in shapes.items() if k in sd and tuple(sd[k].shape) != tuple(shp)]
+    if missing or bad:
+        raise ValueError(f"{what}: {len(missing)} missing keys (e.g. {missing[:3]}), "
+                         f"{len(bad)} shape mismatches (e.g. {[(k, tuple(sd[k].shape), shapes[k]) for k in bad[:3]]})")
+
+
+def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: str):
+    """-> dict(unet=, controlnet=, vae=, text=, unet_cfg=, vae_cfg=, text_cfg=, scheduler_cfg=) from local directories."""
+    if not os.path.isdir(sd_ckpt):
+        raise FileNotFoundError(
+            f"sd_ckpt {sd_ckpt!r} is not a local directory; hub ids cannot be resolved offline — point it at a local "
+            "snapshot of stabilityai/sd-turbo (unet/, vae/, text_encoder/, scheduler/)")
+    ucfg = unet_config_from_json(_read_json(os.path.join(sd_ckpt, "unet", "config.json")))
+    cn_dir = find_controlnet_dir(diffusion_ckpt)
+    ccfg = unet_config_from_json(_read_json(os.path.join(cn_dir, "config.json")))
+    if (ccfg.block_out_channels, ccfg.num_heads) != (ucfg.block_out_channels, ucfg.num_heads):
+        raise ValueError("ControlNet and U-Net configurations do not match")
+    ucfg = dataclasses.replace(ucfg, cond_embed_channels=ccfg.cond_embed_channels)
+    vj = _read_json(os.path.join(sd_ckpt, "vae", "config.json"))
+    vcfg = VAEConfig(latent_channels=vj.get("latent_channels", 4), out_channels=vj.get("out_channels", 3),
+                     block_out_channels=tuple(vj.get("block_out_channels", (128, 256, 512, 512))),
+                     layers_per_block=vj.get("layers_per_block", 2), norm_num_groups=vj.get("norm_num_groups", 32),
+                     scaling_factor=vj.get("scaling_factor", 0.18215))
+    tj = _read_json(os.path.join(sd_ckpt, "text_encoder", "config.json"))
+    tcfg = CLIPTextConfig(vocab_size=tj.get("vocab_size", 49408), hidden_size=tj.get("hidden_size", 1024),
+                          intermediate_size=tj.get("intermediate_size", 4096),
+                          num_layers=tj.get("num_hidden_layers", 23), num_heads=tj.get("num_attention_heads", 16),
+                          max_positions=tj.get("max_position_embeddings", 77),
+                          act="quick_gelu" if tj.get("hidden_act", "gelu") == "quick_gelu" else "gelu",
+                          eps=tj.get("layer_norm_eps", 1e-5))
+    scfg = scheduler_config_from_json(_read_json(os.path.join(sd_ckpt, "scheduler", "scheduler_config.json")))
+    out = dict(unet=load_safetensors_dir(os.path.join(sd_ckpt, "unet")), controlnet=load_safetensors_dir(cn_dir),
+               vae=load_safetensors_dir(os.path.join(sd_ckpt, "vae")),
+               text=load_safetensors_dir(os.path.join(sd_ckpt, "text_encoder")),
+               unet_cfg=ucfg, vae_cfg=vcfg, text_cfg=tcfg, scheduler_cfg=scfg)
+    check_schema(out["unet"], W.unet_shapes(ucfg), "U-Net")
+    check_schema(out["controlnet"], W.controlnet_shapes(ucfg), "ControlNet")
+    check_schema(out["vae"], W.vae_decoder_shapes(vcfg), "VAE decoder")
+    check_schema(out["text"], W.clip_text_shapes(tcfg), "text encoder")
+    return out
+
+
+def load_controller_snapshot(path: str, cfg: ACTConfig = ACTConfig(), prefix: str = "actor.") -> Dict[str, torch.Tensor]:
+    """RoboBase snapshot (controller/train_act.py:262-279) -> ACT state dict in the act_shapes schema.
+    `payload["agent"]` holds the agent's state dict without clip_model.* keys; the policy lives under `actor.`."""
+    payload = torch.load(path, map_location="cpu", weights_only=False)
+    agent = payload["agent"] if "agent" in payload else payload
+    sd = {k[len(prefix):]: v for k, v in agent.items() if k.startswith(prefix)}
+    check_schema(sd, W.act_shapes(cfg), f"controller snapshot {path}")
+    return sd
+
+
+def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcfg: CLIPTextConfig, acfg: ACTConfig):
+    """Writes seeded synthetic weights in the reference's on-disk layouts (for loader tests and offline demos)."""
+    from safetensors.torch import save_file
+
+    sd_ckpt = os.path.join(root, "sd-turbo")
+    dif = os.path.join(root, "diffusion_ckpt")
+    ctl = os.path.join(root, "controller_ckpt")
+    heads = list(ucfg.num_heads)
+    down = ["CrossAttnDownBlock2D" if a else "DownBlock2D" for a in ucfg.attn_levels]
+    ujson = dict(_class_name="UNet2DConditionModel", in_channels=ucfg.in_channels, out_channels=ucfg.out_channels,
+                 block_out_channels=list(ucfg.block_out_channels), layers_per_block=ucfg.layers_per_block,
+                 attention_head_dim=heads, down_block_types=down, cross_attention_dim=ucfg.cross_attention_dim,
+                 norm_num_groups=ucfg.norm_num_groups, norm_eps=ucfg.norm_eps, use_linear_projection=True,
+                 sample_size=ucfg.sample_size)
+    parts = [
+        (os.path.join(sd_ckpt, "unet"), "diffusion_pytorch_model.fp16.safetensors", W.unet_shapes(ucfg), 0, ujson),
+        (os.path.join(sd_ckpt, "vae"), "diffusion_pytorch_model.fp16.safetensors", W.vae_decoder_shapes(vcfg), 2,
+         dict(_class_name="AutoencoderKL", latent_channels=vcfg.latent_channels,
+              block_out_channels=list(vcfg.block_out_channels), layers_per_block=vcfg.layers_per_block,
+              norm_num_groups=vcfg.norm_num_groups, scaling_factor=vcfg.scaling_factor)),
+        (os.path.join(sd_ckpt, "text_encoder"), "model.fp16.safetensors", W.clip_text_shapes(tcfg), 0,
+         dict(vocab_size=tcfg.vocab_size, hidden_size=tcfg.hidden_size, intermediate_size=tcfg.intermediate_size,
+              num_hidden_layers=tcfg.num_layers, num_attention_heads=tcfg.num_heads,
+              max_position_embeddings=tcfg.max_positions, hidden_act=tcfg.act, layer_norm_eps=tcfg.eps)),
+        (os.path.join(dif, "checkpoint-500", "controlnet"), "diffusion_pytorch_model.safetensors",
+         W.controlnet_shapes(ucfg), 7, ujson),     # an older checkpoint with different weights: must NOT be picked
+        (os.path.join(dif, "checkpoint-1000", "controlnet"), "diffusion_pytorch_model.safetensors",
+         W.controlnet_shapes(ucfg), 1,
+         dict(ujson, _class_name="ControlNetModel",
+              conditioning_embedding_out_channels=list(ucfg.cond_embed_channels))),
+    ]
+    for d, fname, shapes, salt, cfg in parts:
+        os.makedirs(d, exist_ok=True)
+        save_file(W.synth_state_dict(shapes, salt=salt), os.path.join(d, fname))
+        with open(os.path.join(d, "config.json"), "w") as f:
+            json.dump(cfg, f)
+    os.makedirs(os.path.join(sd_ckpt, "scheduler"), exist_ok=True)
+    with open(os.path.join(sd_ckpt, "scheduler", "scheduler_config.json"), "w") as f:
+        json.dump(dict(_class_name="EulerDiscreteScheduler", num_train_timesteps=1000, beta_start=0.00085,
+                       beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="trailing",
+                       prediction_type="epsilon"), f)
+    os.makedirs(ctl, exist_ok=True)
+    act_sd = W.synth_state_dict(W.act_shapes(acfg), salt=3)
+    torch.save({"cfg": {}, "_epoch": 0, "_num_iters": 0, "agent": {f"actor.{k}": v for k, v in act_sd.items()}},
+               os.path.join(ctl, "latest.pt"))
+    return dict(sd_ckpt=sd_ckpt, diffusion_ckpt=dif, controller_ckpt=ctl)

@@ -115,6 +115,13 @@ int gn_create(int device, gn_handle** out) {
 }
 
 int gn_destroy(gn_handle* h) {
+  if (h) {
+    for (auto& r : h->prof) {
+      cudaEventDestroy(r.a);
+      cudaEventDestroy(r.b);
+    }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+  }
   if (h && h->stats_scratch) cudaFree(h->stats_scratch);
   delete h;
   return GN_OK;
@@ -143,5 +150,44 @@ int gn_get_last_gemm_config(const gn_handle* h, int32_t* out4) {
 }
 
 int64_t gn_launch_count(const gn_handle* h) { return h ? h->launches : -1; }
+
+int gn_profile_begin(gn_handle* h) {
+  if (!h) return GN_ERR_INVALID;
+  for (auto& r : h->prof) {
+    h->event_pool.push_back(r.a);
+    h->event_pool.push_back(r.b);
+  }
+  h->prof.clear();
+  h->profiling = true;
+  return GN_OK;
+}
+
+int gn_profile_end(gn_handle* h, double* ms, int64_t* calls, double* flops, double* bytes) {
+  if (!h || !ms || !calls || !flops || !bytes) return GN_ERR_INVALID;
+  h->profiling = false;
+  for (int c = 0; c < GN_PROF_NUM_CLASSES; ++c) {
+    ms[c] = 0.0;
+    calls[c] = 0;
+    flops[c] = 0.0;
+    bytes[c] = 0.0;
+  }
+  int rc = GN_OK;
+  for (auto& r : h->prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) {
+      cudaGetLastError();
+      rc = gn::set_error(h, GN_ERR_CUDA, "gn_profile_end: event timing failed (profiling inside graph capture?)");
+    } else if (r.cls >= 0 && r.cls < GN_PROF_NUM_CLASSES) {
+      ms[r.cls] += t;
+      calls[r.cls] += 1;
+      flops[r.cls] += r.flops;
+      bytes[r.cls] += r.bytes;
+    }
+    h->event_pool.push_back(r.a);
+    h->event_pool.push_back(r.b);
+  }
+  h->prof.clear();
+  return rc;
+}
 
 }  // extern "C"

@@ -317,6 +317,8 @@ extern "C" int gn_attention(gn_handle* h, const void* q, int64_t ldq, const void
   GN_CHECK_ARG(h, B > 0 && heads > 0 && Tq > 0 && Tk > 0, "gn_attention: bad shape");
   GN_CHECK_ARG(h, (ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0 && (ldo % 8) == 0,
                "gn_attention: row strides must be multiples of 8 elements");
+  ProfScope prof(h, stream, GN_PROF_ATTENTION, 4.0 * B * heads * (double)Tq * Tk * AT_D,
+                 2.0 * B * heads * AT_D * (2.0 * Tq + 2.0 * Tk));
   static thread_local AttnParams p;
   memset(&p, 0, sizeof(p));
   const void* ptrs[3] = {q, k, v};
@@ -353,6 +355,8 @@ extern "C" int gn_attention_small(gn_handle* h, const void* q, int64_t ldq, cons
   GN_CHECK_ARG(h, B > 0 && heads > 0 && Tq > 0 && Tk > 0, "gn_attention_small: bad shape");
   GN_CHECK_ARG(h, head_dim == 32 || head_dim == 64, "gn_attention_small: head_dim %d unsupported", head_dim);
   GN_CHECK_ARG(h, (ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 2) == 0, "gn_attention_small: bad row strides");
+  ProfScope prof(h, stream, GN_PROF_ATTN_SMALL, 4.0 * B * heads * (double)Tq * Tk * head_dim,
+                 2.0 * B * heads * head_dim * (2.0 * Tq + 2.0 * Tk));
   dim3 grid(ceil_div(Tq, 4), heads, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const __half* qh = static_cast<const __half*>(q);

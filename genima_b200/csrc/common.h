@@ -8,11 +8,22 @@
 
 #include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/genima_b200.h"
 
+struct gn_prof_rec {
+  cudaEvent_t a, b;
+  int cls;
+  double flops, bytes;
+};
+
 struct gn_handle {
   int device = 0;
+  // per-call CUDA-event profiling (gn_profile_begin / gn_profile_end); never active during graph capture
+  bool profiling = false;
+  std::vector<gn_prof_rec> prof;
+  std::vector<cudaEvent_t> event_pool;
   int num_sms = 148;
   char err[512] = {0};
   void* workspace = nullptr;
@@ -62,6 +73,35 @@ int set_error(gn_handle* h, int code, const char* fmt, ...);
 // of dim i+1.  Returns 0 or a negative gn_status.
 int make_tmap_f16(gn_handle* h, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box);
+
+// RAII scope recording a CUDA event pair around one C-ABI call when profiling is on (cls: enum gn_prof_class).
+struct ProfScope {
+  gn_handle* h;
+  cudaStream_t st;
+  int idx = -1;
+  ProfScope(gn_handle* h_, void* stream, int cls, double flops, double bytes) : h(h_), st((cudaStream_t)stream) {
+    if (!h || !h->profiling) return;
+    gn_prof_rec r;
+    r.cls = cls;
+    r.flops = flops;
+    r.bytes = bytes;
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+      if (!h->event_pool.empty()) {
+        *e = h->event_pool.back();
+        h->event_pool.pop_back();
+      } else if (cudaEventCreate(e) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+      }
+    }
+    cudaEventRecord(r.a, st);
+    h->prof.push_back(r);
+    idx = (int)h->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(h->prof[idx].b, st);
+  }
+};
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

@@ -177,15 +177,17 @@ __global__ void nhwc_to_u8_kernel(const __half* __restrict__ src, int64_t npix, 
   }
 }
 
-// views [B, 4, 256, 256, 3] <-> tile [B, 512, 512, 3]; view k sits at (x, y) = ((k % 2) * 256, (k / 2) * 256)
-__global__ void tile_views_kernel(const uint8_t* __restrict__ views, uint8_t* __restrict__ tile, int B, int to_tile) {
-  const int64_t total = (int64_t)B * 512 * 512;
+// views [B, 4, S, S, 3] <-> tile [B, 2S, 2S, 3]; view k sits at (x, y) = ((k % 2) * S, (k / 2) * S)   (S = 256 upstream)
+__global__ void tile_views_kernel(const uint8_t* __restrict__ views, uint8_t* __restrict__ tile, int B, int S,
+                                  int to_tile) {
+  const int S2 = 2 * S;
+  const int64_t total = (int64_t)B * S2 * S2;
   GRID_STRIDE(i, total) {
-    const int x = (int)(i % 512);
-    const int y = (int)((i / 512) % 512);
-    const int b = (int)(i / (512 * 512));
-    const int k = (y / 256) * 2 + (x / 256);
-    const int64_t vi = ((((int64_t)b * 4 + k) * 256 + (y % 256)) * 256 + (x % 256)) * 3;
+    const int x = (int)(i % S2);
+    const int y = (int)((i / S2) % S2);
+    const int b = (int)(i / ((int64_t)S2 * S2));
+    const int k = (y / S) * 2 + (x / S);
+    const int64_t vi = ((((int64_t)b * 4 + k) * S + (y % S)) * S + (x % S)) * 3;
     const int64_t ti = i * 3;
     if (to_tile) {
       tile[ti] = views[vi];
@@ -244,6 +246,7 @@ using namespace gn;
 extern "C" int gn_embed_tokens(gn_handle* h, const void* ids_i64, const void* tok_emb, const void* pos_emb, int B,
                                int T, int D, int vocab, void* out, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, ids_i64 && tok_emb && pos_emb && out && B > 0 && T > 0 && D > 0 && (D % 8) == 0 && vocab > 0,
                "gn_embed_tokens: bad arguments");
   const int64_t rows = (int64_t)B * T;
@@ -257,6 +260,7 @@ extern "C" int gn_embed_tokens(gn_handle* h, const void* ids_i64, const void* to
 extern "C" int gn_film_fold(gn_handle* h, const float* film, const float* bn_scale, const float* bn_shift,
                             float* scale_out, float* shift_out, int C, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, film && bn_scale && bn_shift && scale_out && shift_out && C > 0, "gn_film_fold: bad arguments");
   film_fold_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(film, bn_scale, bn_shift, scale_out,
                                                                                   shift_out, C);
@@ -266,6 +270,7 @@ extern "C" int gn_film_fold(gn_handle* h, const float* film, const float* bn_sca
 
 extern "C" int gn_upsample_nearest2x(gn_handle* h, const void* x, int B, int H, int W, int C, void* y, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, x && y && B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0, "gn_upsample_nearest2x: bad arguments");
   const int64_t total = (int64_t)B * 4 * H * W * (C / 8);
   upsample2x_kernel<<<grid_for(h, total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -276,6 +281,7 @@ extern "C" int gn_upsample_nearest2x(gn_handle* h, const void* x, int B, int H, 
 
 extern "C" int gn_maxpool3x3s2(gn_handle* h, const void* x, int B, int H, int W, int C, void* y, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, x && y && B > 0 && H > 0 && W > 0 && C > 0 && (C % 8) == 0, "gn_maxpool3x3s2: bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
@@ -287,6 +293,7 @@ extern "C" int gn_maxpool3x3s2(gn_handle* h, const void* x, int B, int H, int W,
 
 extern "C" int gn_add(gn_handle* h, const void* a, const void* b, void* out, int64_t n, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, a && b && out && n > 0 && (n % 2) == 0, "gn_add: bad arguments");
   add_kernel<<<grid_for(h, n / 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half2*>(a), static_cast<const __half2*>(b), static_cast<__half2*>(out), n / 2);
@@ -296,6 +303,7 @@ extern "C" int gn_add(gn_handle* h, const void* a, const void* b, void* out, int
 
 extern "C" int gn_scale(gn_handle* h, const void* x, float s, void* y, int64_t n, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, x && y && n > 0, "gn_scale: bad arguments");
   scale_kernel<<<grid_for(h, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(x), s,
                                                                               static_cast<__half*>(y), n);
@@ -305,6 +313,7 @@ extern "C" int gn_scale(gn_handle* h, const void* x, float s, void* y, int64_t n
 
 extern "C" int gn_timestep_embedding(gn_handle* h, float t, int dim, void* out, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, out && dim > 0 && (dim % 2) == 0, "gn_timestep_embedding: bad arguments");
   timestep_embedding_kernel<<<(dim / 2 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       t, dim, static_cast<__half*>(out));
@@ -315,6 +324,7 @@ extern "C" int gn_timestep_embedding(gn_handle* h, float t, int dim, void* out, 
 extern "C" int gn_euler_step(gn_handle* h, const void* x, const void* eps, float sigma, float sigma_next, void* x_next,
                              void* x_scaled, int64_t n, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, x && eps && x_next && n > 0, "gn_euler_step: bad arguments");
   const float inv = 1.0f / sqrtf(sigma_next * sigma_next + 1.0f);
   euler_step_kernel<<<grid_for(h, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -327,6 +337,7 @@ extern "C" int gn_euler_step(gn_handle* h, const void* x, const void* eps, float
 extern "C" int gn_nchw_to_nhwc(gn_handle* h, const void* src, int src_fp32, int B, int C, int H, int W, int Cpad,
                                const float* mean3, const float* std3, void* dst, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, src && dst && B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "gn_nchw_to_nhwc: bad arguments");
   const int64_t total = (int64_t)B * H * W * Cpad;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -349,6 +360,7 @@ extern "C" int gn_nchw_to_nhwc(gn_handle* h, const void* src, int src_fp32, int 
 extern "C" int gn_nhwc_to_nchw(gn_handle* h, const void* src, int B, int C, int H, int W, int Cpad, void* dst,
                                int dst_fp32, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, src && dst && B > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C, "gn_nhwc_to_nchw: bad arguments");
   const int64_t total = (int64_t)B * C * H * W;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -365,6 +377,7 @@ extern "C" int gn_nhwc_to_nchw(gn_handle* h, const void* src, int B, int C, int 
 extern "C" int gn_u8_to_nhwc(gn_handle* h, const void* src_u8, int B, int H, int W, int Cpad, const float* mean3,
                              const float* std3, void* dst, void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, src_u8 && dst && B > 0 && H > 0 && W > 0 && Cpad >= 8 && (Cpad % 8) == 0,
                "gn_u8_to_nhwc: bad arguments");
   Norm3 nm;
@@ -383,6 +396,7 @@ extern "C" int gn_u8_to_nhwc(gn_handle* h, const void* src_u8, int B, int H, int
 extern "C" int gn_nhwc_to_u8(gn_handle* h, const void* src, int B, int H, int W, int Cpad, void* dst_u8,
                              void* stream) {
   if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
   GN_CHECK_ARG(h, src && dst_u8 && B > 0 && H > 0 && W > 0 && Cpad >= 3, "gn_nhwc_to_u8: bad arguments");
   const int64_t npix = (int64_t)B * H * W;
   nhwc_to_u8_kernel<<<grid_for(h, npix), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -391,20 +405,22 @@ extern "C" int gn_nhwc_to_u8(gn_handle* h, const void* src, int B, int H, int W,
   return GN_OK;
 }
 
-extern "C" int gn_tile_views(gn_handle* h, const void* views_u8, int B, void* tile_u8, void* stream) {
+extern "C" int gn_tile_views(gn_handle* h, const void* views_u8, int B, int S, void* tile_u8, void* stream) {
   if (!h) return GN_ERR_INVALID;
-  GN_CHECK_ARG(h, views_u8 && tile_u8 && B > 0, "gn_tile_views: bad arguments");
-  tile_views_kernel<<<grid_for(h, (int64_t)B * 512 * 512), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint8_t*>(views_u8), static_cast<uint8_t*>(tile_u8), B, 1);
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
+  GN_CHECK_ARG(h, views_u8 && tile_u8 && B > 0 && S > 0, "gn_tile_views: bad arguments");
+  tile_views_kernel<<<grid_for(h, (int64_t)B * 4 * S * S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(views_u8), static_cast<uint8_t*>(tile_u8), B, S, 1);
   GN_CHECK_LAUNCH(h);
   return GN_OK;
 }
 
-extern "C" int gn_untile_views(gn_handle* h, const void* tile_u8, int B, void* views_u8, void* stream) {
+extern "C" int gn_untile_views(gn_handle* h, const void* tile_u8, int B, int S, void* views_u8, void* stream) {
   if (!h) return GN_ERR_INVALID;
-  GN_CHECK_ARG(h, views_u8 && tile_u8 && B > 0, "gn_untile_views: bad arguments");
-  tile_views_kernel<<<grid_for(h, (int64_t)B * 512 * 512), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint8_t*>(views_u8), static_cast<uint8_t*>(const_cast<void*>(tile_u8)), B, 0);
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
+  GN_CHECK_ARG(h, views_u8 && tile_u8 && B > 0 && S > 0, "gn_untile_views: bad arguments");
+  tile_views_kernel<<<grid_for(h, (int64_t)B * 4 * S * S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(views_u8), static_cast<uint8_t*>(const_cast<void*>(tile_u8)), B, S, 0);
   GN_CHECK_LAUNCH(h);
   return GN_OK;
 }

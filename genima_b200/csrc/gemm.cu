@@ -523,6 +523,8 @@ extern "C" int gn_linear(gn_handle* h, const void* A, int64_t lda, int M, int K,
   GN_CHECK_ARG(h, M > 0 && N > 0 && K > 0, "gn_linear: bad shape M=%d N=%d K=%d", M, N, K);
   GN_CHECK_ARG(h, (K % 8) == 0 && (lda % 8) == 0, "gn_linear: K (%d) and lda (%lld) must be multiples of 8", K,
                (long long)lda);
+  ProfScope prof(h, stream, GN_PROF_LINEAR, 2.0 * M * N * K,
+                 2.0 * ((double)M * K + (double)N * K) + (double)M * N * ((epi && epi->out_fp32) ? 4 : 2));
   static thread_local GemmParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_epilogue(h, p.epi, epi, out, ldo, M, N, M);
@@ -555,6 +557,10 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
   const int Wo = (W + 2 * pad - KW) / stride + 1;
   GN_CHECK_ARG(h, Ho > 0 && Wo > 0, "gn_conv2d: empty output");
   const int M = B * Ho * Wo;
+  const double kreal = (double)KH * KW * C + (ex0 ? C_ex0 : 0) + (ex1 ? C_ex1 : 0);
+  ProfScope prof(h, stream, GN_PROF_CONV, 2.0 * M * Cout * kreal,
+                 2.0 * ((double)B * H * W * C + (double)M * ((ex0 ? C_ex0 : 0) + (ex1 ? C_ex1 : 0)) + Cout * kreal +
+                        (double)M * Cout));
 
   static thread_local GemmParams p;
   memset(&p, 0, sizeof(p));

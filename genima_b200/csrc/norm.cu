@@ -307,6 +307,7 @@ extern "C" int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x
   GN_CHECK_ARG(h, h->stats_scratch && (int64_t)B * groups * 2 * 4 <= h->stats_scratch_bytes,
                "gn_group_norm: B*groups too large for the statistics scratch");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(h, stream, GN_PROF_NORM, 0.0, 4.0 * B * HW * C);
   GNParams p;
   p.x0 = static_cast<const __half*>(x0);
   p.x1 = static_cast<const __half*>(x1);
@@ -352,6 +353,7 @@ extern "C" int gn_layer_norm(gn_handle* h, const void* x, int64_t ldx, int rows,
   GN_CHECK_ARG(h, x && y && gamma && beta, "gn_layer_norm: null pointer");
   GN_CHECK_ARG(h, rows > 0 && C > 0 && (C % 8) == 0 && C <= 8 * 32 * LN_MAX_VPL, "gn_layer_norm: C=%d unsupported", C);
   GN_CHECK_ARG(h, (ldx % 8) == 0 && (ldy % 8) == 0, "gn_layer_norm: row strides must be multiples of 8");
+  ProfScope prof(h, stream, GN_PROF_NORM, 0.0, 4.0 * rows * C);
   const int rows_per_block = 8;
   layer_norm_kernel<<<(rows + rows_per_block - 1) / rows_per_block, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), ldx, rows, C, eps, gamma, beta, static_cast<__half*>(y), ldy);
@@ -367,6 +369,7 @@ extern "C" int gn_softmax_rows(gn_handle* h, const void* x, int x_fp32, int64_t 
                "gn_softmax_rows: cols=%d unsupported", cols);
   GN_CHECK_ARG(h, !(x_fp32 && x == y), "gn_softmax_rows: fp32 input cannot alias the fp16 output");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfScope prof(h, stream, GN_PROF_NORM, 0.0, (double)rows * cols * (x_fp32 ? 6.0 : 4.0));
   if (x_fp32)
     softmax_rows_kernel<float><<<rows, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<__half*>(y), ldy,
                                                      cols, scale);

@@ -100,6 +100,20 @@ class Ops:
     def launch_count(self) -> int:
         return self.handle.launch_count()
 
+    PROF_CLASSES = ("linear", "conv", "attention", "attention_small", "norm", "elementwise")
+
+    def profile_begin(self) -> None:
+        """Start per-call CUDA-event timing inside the library (eager launches only, not under graph capture)."""
+        self.handle.check(self.lib.gn_profile_begin(self.h), "gn_profile_begin")
+
+    def profile_end(self) -> dict:
+        """-> {class: dict(ms=, calls=, flops=, bytes=)} summed over the calls since profile_begin (synchronises)."""
+        n = len(self.PROF_CLASSES)
+        ms, calls, flops, byts = (C.c_double * n)(), (C.c_int64 * n)(), (C.c_double * n)(), (C.c_double * n)()
+        self.handle.check(self.lib.gn_profile_end(self.h, ms, calls, flops, byts), "gn_profile_end")
+        return {name: dict(ms=ms[i], calls=int(calls[i]), flops=flops[i], bytes=byts[i])
+                for i, name in enumerate(self.PROF_CLASSES)}
+
     # ------------------------------------------------------------------------------------------------ contractions
     def linear(self, a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, **epi) -> torch.Tensor:
         """out[..., N'] = epilogue(a[..., K] @ w[N, K]^T); N' = N/2 with geglu=True."""
@@ -354,24 +368,26 @@ class Ops:
         return out
 
     def tile_views(self, views: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """[B, 4, 256, 256, 3] u8 -> [B, 512, 512, 3] u8 (controller/utils/misc.py:6-19)."""
-        if views.dtype != torch.uint8 or not views.is_cuda or tuple(views.shape[1:]) != (4, 256, 256, 3):
-            raise TypeError("tile_views: CUDA uint8 [B, 4, 256, 256, 3] expected")
-        B = views.shape[0]
+        """[B, 4, S, S, 3] u8 -> [B, 2S, 2S, 3] u8 (controller/utils/misc.py:6-19; S = 256 there)."""
+        if (views.dtype != torch.uint8 or not views.is_cuda or views.dim() != 5 or views.shape[1] != 4
+                or views.shape[2] != views.shape[3] or views.shape[4] != 3):
+            raise TypeError("tile_views: CUDA uint8 [B, 4, S, S, 3] expected")
+        B, S = views.shape[0], views.shape[2]
         if out is None:
-            out = torch.empty(B, 512, 512, 3, dtype=torch.uint8, device=views.device)
-        self.handle.check(self.lib.gn_tile_views(self.h, views.contiguous().data_ptr(), B, out.data_ptr(),
+            out = torch.empty(B, 2 * S, 2 * S, 3, dtype=torch.uint8, device=views.device)
+        self.handle.check(self.lib.gn_tile_views(self.h, views.contiguous().data_ptr(), B, S, out.data_ptr(),
                                                  self._stream()), "gn_tile_views")
         return out
 
     def untile_views(self, tile: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """[B, 512, 512, 3] u8 -> [B, 4, 256, 256, 3] u8 (controller/utils/misc.py:22-47)."""
-        if tile.dtype != torch.uint8 or not tile.is_cuda or tuple(tile.shape[1:]) != (512, 512, 3):
-            raise TypeError("untile_views: CUDA uint8 [B, 512, 512, 3] expected")
-        B = tile.shape[0]
+        """[B, 2S, 2S, 3] u8 -> [B, 4, S, S, 3] u8 (controller/utils/misc.py:22-47; S = 256 there)."""
+        if (tile.dtype != torch.uint8 or not tile.is_cuda or tile.dim() != 4 or tile.shape[1] != tile.shape[2]
+                or tile.shape[1] % 2 or tile.shape[3] != 3):
+            raise TypeError("untile_views: CUDA uint8 [B, 2S, 2S, 3] expected")
+        B, S = tile.shape[0], tile.shape[1] // 2
         if out is None:
-            out = torch.empty(B, 4, 256, 256, 3, dtype=torch.uint8, device=tile.device)
-        self.handle.check(self.lib.gn_untile_views(self.h, tile.contiguous().data_ptr(), B, out.data_ptr(),
+            out = torch.empty(B, 4, S, S, 3, dtype=torch.uint8, device=tile.device)
+        self.handle.check(self.lib.gn_untile_views(self.h, tile.contiguous().data_ptr(), B, S, out.data_ptr(),
                                                    self._stream()), "gn_untile_views")
         return out
 

@@ -15,6 +15,11 @@ def round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
+def _pad_last(t: torch.Tensor, n: int) -> torch.Tensor:
+    """Append n zeros along the last dim."""
+    return torch.cat([t, t.new_zeros(*t.shape[:-1], n)], dim=-1)
+
+
 def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = (), cin_layout: Sequence[int] = ()) -> torch.Tensor:
     """w: [Cout, Cin, KH, KW]; extras: 1x1 shortcut weights [Cout, Ce(,1,1)] appended along K.
 
@@ -31,20 +36,20 @@ def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = (), cin_l
             real, padded = cin_layout[i], cin_layout[i + 1]
             seg = taps[:, :, off:off + real]
             if padded > real:
-                seg = torch.nn.functional.pad(seg, (0, padded - real))
+                seg = _pad_last(seg, padded - real)
             segs.append(seg)
             off += real
         assert off == cin, (off, cin)
         taps = torch.cat(segs, dim=2)
     cp = round_up(taps.shape[2], 64)
     if cp > taps.shape[2]:
-        taps = torch.nn.functional.pad(taps, (0, cp - taps.shape[2]))
+        taps = _pad_last(taps, cp - taps.shape[2])
     parts = [taps.reshape(cout, kh * kw * cp)]
     for e in extras:
         e = e.to(torch.float16).reshape(cout, -1)
         ep = round_up(e.shape[1], 64)
         if ep > e.shape[1]:
-            e = torch.nn.functional.pad(e, (0, ep - e.shape[1]))
+            e = _pad_last(e, ep - e.shape[1])
         parts.append(e)
     return torch.cat(parts, dim=1).contiguous()
 
@@ -70,4 +75,4 @@ def pad_cols(w: torch.Tensor, mult: int = 8) -> torch.Tensor:
     kp = round_up(k, mult)
     if kp == k:
         return w.contiguous()
-    return torch.nn.functional.pad(w, (0, kp - k)).contiguous()
+    return _pad_last(w, kp - k).contiguous()

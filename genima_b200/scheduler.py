@@ -22,11 +22,13 @@ class EulerDiscreteSchedule:
             raise NotImplementedError("only epsilon prediction with the scaled_linear beta schedule is implemented")
         self.cfg = cfg
         T = cfg.num_train_timesteps
-        # float32 throughout, like the torch.linspace(...)**2 / cumprod chain upstream
-        betas = np.linspace(np.float32(cfg.beta_start) ** np.float32(0.5), np.float32(cfg.beta_end) ** np.float32(0.5),
-                            T, dtype=np.float32) ** 2
-        alphas_cumprod = np.cumprod((1.0 - betas).astype(np.float32), dtype=np.float32)
-        self.train_sigmas = np.sqrt((1 - alphas_cumprod) / alphas_cumprod).astype(np.float32)
+        # float32 torch ops in the same order as diffusers' __init__ (torch.linspace(...)**2, cumprod), so the tables
+        # are bit-identical to the upstream scheduler's; host scalars only, computed once
+        import torch
+
+        betas = torch.linspace(cfg.beta_start ** 0.5, cfg.beta_end ** 0.5, T, dtype=torch.float32) ** 2
+        alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.train_sigmas = (((1 - alphas_cumprod) / alphas_cumprod) ** 0.5).numpy()
         self.timesteps = None
         self.sigmas = None
 

@@ -30,6 +30,16 @@ from .weights import unet_skip_channels
 LATENT_CPAD = 8  # latents travel as [B, h, w, 8] fp16 (4 real channels): 16-byte pixels for TMA
 
 
+def tensor_key(t: torch.Tensor) -> tuple:
+    """Identity of a tensor's current contents for the per-prompt / per-task caches (inference-mode tensors carry no
+    version counter; they are immutable in practice)."""
+    try:
+        ver = t._version
+    except RuntimeError:
+        ver = -1
+    return (t.data_ptr(), ver, tuple(t.shape), t.dtype)
+
+
 class _Params:
     """Moves a state dict to the device once, in the layouts the kernels want."""
 

@@ -277,9 +277,10 @@ def synth_tensor(name: str, shape: Tuple[int, ...], salt: int = 0) -> torch.Tens
         t = 0.02 * torch.randn(shape, generator=g)
     elif leaf == "weight" and len(shape) == 1:
         t = 1.0 + 0.02 * torch.randn(shape, generator=g)  # norm scales
-    elif "embedding" in parent or "embed" in parent:
-        t = 0.02 * torch.randn(shape, generator=g) if "token" in parent or "position" in parent \
-            else torch.randn(shape, generator=g)
+    elif parent.rsplit(".", 1)[-1] in ("token_embedding", "position_embedding"):
+        t = 0.02 * torch.randn(shape, generator=g)        # CLIP embedding tables
+    elif parent.rsplit(".", 1)[-1] in ("query_embed", "additional_pos_embed"):
+        t = torch.randn(shape, generator=g)               # nn.Embedding default init (DETR / ACT learned positions)
     else:
         fan_in = 1
         for v in shape[1:]:

@@ -76,6 +76,23 @@ int gn_get_last_gemm_config(const gn_handle* h, int32_t* out4);
 /* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t gn_launch_count(const gn_handle* h);
 
+/* Per-call timing with CUDA events on the caller's stream (bench.py's roofline figures).  Between gn_profile_begin and
+ * gn_profile_end every compute entry point records an event pair around its launches; gn_profile_end synchronises and
+ * returns, per class, the summed milliseconds, call count, algorithmic FLOPs (2 x MACs on real channels) and
+ * algorithmic bytes (external inputs + outputs + weights, each once).  Arrays hold GN_PROF_NUM_CLASSES entries.
+ * Not usable while the stream is being captured into a CUDA graph. */
+enum gn_prof_class {
+  GN_PROF_LINEAR = 0,     /* gn_linear (gemm_tc_kernel [+ splitk_reduce_kernel]) */
+  GN_PROF_CONV = 1,       /* gn_conv2d (gemm_tc_kernel, implicit GEMM [+ splitk_reduce_kernel]) */
+  GN_PROF_ATTENTION = 2,  /* gn_attention (attn_tc_kernel) */
+  GN_PROF_ATTN_SMALL = 3, /* gn_attention_small */
+  GN_PROF_NORM = 4,       /* gn_group_norm, gn_layer_norm, gn_softmax_rows */
+  GN_PROF_ELEMENTWISE = 5,
+  GN_PROF_NUM_CLASSES = 6
+};
+int gn_profile_begin(gn_handle* h);
+int gn_profile_end(gn_handle* h, double* ms, int64_t* calls, double* flops, double* bytes);
+
 /* ---- dense contractions (tcgen05.mma, TMA-staged operands, TMEM accumulators) --------------------------------
  * out[M, N] = epilogue(A[M, K] @ W[N, K]^T).  A: fp16 row-major with row stride lda (elements, % 8 == 0), K % 8 == 0.
  * W: fp16 [N, K] row-major (torch nn.Linear layout).  Replaces cuBLAS GEMMs behind nn.Linear / 1x1 conv. */
@@ -146,10 +163,10 @@ int gn_u8_to_nhwc(gn_handle* h, const void* src_u8, int B, int H, int W, int Cpa
                   const float* std3, void* dst, void* stream);
 /* VaeImageProcessor.postprocess: fp16 NHWC [B, H, W, Cpad] in [-1, 1] -> uint8 [B, H, W, 3] = round(clamp(x/2+.5)*255). */
 int gn_nhwc_to_u8(gn_handle* h, const void* src, int B, int H, int W, int Cpad, void* dst_u8, void* stream);
-/* tile_images / untile_images of controller/utils/misc.py:6-47 on device: 4 views u8 [4, 256, 256, 3] <-> one
- * [512, 512, 3] tile (view k -> quadrant (k % 2, k / 2)). */
-int gn_tile_views(gn_handle* h, const void* views_u8, int B, void* tile_u8, void* stream);
-int gn_untile_views(gn_handle* h, const void* tile_u8, int B, void* views_u8, void* stream);
+/* tile_images / untile_images of controller/utils/misc.py:6-47 on device: 4 views u8 [B, 4, S, S, 3] <-> one
+ * [B, 2S, 2S, 3] tile (view k -> quadrant (k % 2, k / 2)); S = 256 in the reference. */
+int gn_tile_views(gn_handle* h, const void* views_u8, int B, int S, void* tile_u8, void* stream);
+int gn_untile_views(gn_handle* h, const void* tile_u8, int B, int S, void* views_u8, void* stream);
 
 /* CLIP text embeddings: out[b, t, :] = tok_emb[ids[b, t], :] + pos_emb[t, :]; ids int64 [B, T] on device. */
 int gn_embed_tokens(gn_handle* h, const void* ids_i64, const void* tok_emb, const void* pos_emb, int B, int T, int D,

@@ -1,0 +1,64 @@
+"""fp32 CPU restatement of one Genima agent step (TEST INFRASTRUCTURE — see oracle/__init__).
+
+  controlnet_pipeline()  diffusers 0.29.0 StableDiffusionControlNetPipeline.__call__ exactly as the reference exercises it
+                         (controller/agent/sd_controlnet_agent.py:67-76): no CFG (guidance 0.0,
+                         controller/cfgs/eval_genima.yaml:31), control image in [0, 1] without normalisation, explicit
+                         `latents` multiplied by init_noise_sigma, Euler-trailing loop with ControlNet residuals added to
+                         the U-Net skips, VAE decode of latents / scaling_factor, postprocess to uint8.
+  agent_step()           controller/eval_genima.py:163-249 between `obs` and `actions`: tile_images -> pipeline ->
+                         untile_images -> GenimaACT.act (policy forward on the four generated views).
+PARITY UNPINNED (no upstream package, weights or golden vectors offline); pinned sub-pieces are listed in oracle/__init__.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from genima_b200.configs import ACTConfig, UNetConfig, VAEConfig
+
+from . import act as act_oracle
+from . import sd_models, tiling
+from .scheduler import EulerDiscreteOracle
+
+
+def controlnet_pipeline(unet_sd, cn_sd, vae_sd, ucfg: UNetConfig, vcfg: VAEConfig, cond_u8: np.ndarray,
+                        ctx: torch.Tensor, latents: torch.Tensor, n_steps: int, conditioning_scale: float = 1.0,
+                        return_intermediates: bool = False):
+    """cond_u8 [B, H, W, 3] uint8; ctx [B, 77, D] fp32 prompt embeddings; latents [B, 4, H/8, W/8] unit-variance noise.
+    Returns dict(latents=final latents fp32, image=decoded image in [-1, 1] NCHW fp32, u8=[B, H, W, 3] uint8)."""
+    sched = EulerDiscreteOracle()
+    ts, sig = sched.set_timesteps(n_steps)
+    cond = torch.from_numpy(cond_u8.astype(np.float32) / 255.0).permute(0, 3, 1, 2)      # VaeImageProcessor.preprocess
+    x = latents.to(torch.float32) * sched.init_noise_sigma
+    inter = []
+    for i, t in enumerate(ts):
+        xs = sched.scale_model_input(x, i)
+        tt = torch.tensor([float(t)])
+        down, mid = sd_models.controlnet_forward(cn_sd, ucfg, xs, tt, ctx, cond, conditioning_scale)
+        eps = sd_models.unet_forward(unet_sd, ucfg, xs, tt, ctx, down, mid)
+        x = sched.step(eps, i, x)
+        if return_intermediates:
+            inter.append(dict(eps=eps, x=x))
+    img = sd_models.vae_decode(vae_sd, vcfg, x / vcfg.scaling_factor)
+    den = (img / 2 + 0.5).clamp(0, 1)                                                      # postprocess, denormalize
+    u8 = (den.permute(0, 2, 3, 1).numpy() * 255).round().astype(np.uint8)
+    out = dict(latents=x, image=img, u8=u8)
+    if return_intermediates:
+        out["steps"] = inter
+    return out
+
+
+def agent_step(weights: Dict[str, dict], ucfg: UNetConfig, vcfg: VAEConfig, acfg: ACTConfig, views_u8: np.ndarray,
+               ctx: torch.Tensor, latents: torch.Tensor, qpos: torch.Tensor, task_emb: torch.Tensor, n_steps: int):
+    """views_u8 [4, 256, 256, 3] (camera order) -> dict(a_hat [1, nq, A], tile_u8, gen_views_u8 [4, 256, 256, 3]).
+    `weights`: dict(unet=, controlnet=, vae=, act=) state dicts."""
+    tile = tiling.tile_views(views_u8)[None]
+    out = controlnet_pipeline(weights["unet"], weights["controlnet"], weights["vae"], ucfg, vcfg, tile, ctx, latents,
+                              n_steps)
+    gen = tiling.untile_views(out["u8"][0])                                               # [4, 256, 256, 3]
+    image = torch.from_numpy(gen).permute(0, 3, 1, 2)[None].float()                       # [1, V, 3, H, W] 0..255
+    a_hat, is_pad = act_oracle.act_forward(weights["act"], acfg, qpos, image, task_emb)
+    return dict(a_hat=a_hat, is_pad=is_pad, tile_u8=out["u8"], gen_views_u8=gen, latents=out["latents"],
+                image=out["image"])

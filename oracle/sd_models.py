@@ -34,14 +34,15 @@ def _w(sd: SD, key: str) -> torch.Tensor:
 def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     """get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0, max_period=10000)."""
     half = dim // 2
-    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half
     emb = t.to(torch.float32)[:, None] * torch.exp(exponent)[None, :]
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
 
 def time_embed(sd: SD, cfg: UNetConfig, t: torch.Tensor) -> torch.Tensor:
     emb = timestep_embedding(t, cfg.block_out_channels[0])
-    emb = F.linear(emb, _w(sd, "time_embedding.linear_1.weight"), _w(sd, "time_embedding.linear_1.bias"))
+    w1 = _w(sd, "time_embedding.linear_1.weight")
+    emb = F.linear(emb.to(w1.dtype), w1, _w(sd, "time_embedding.linear_1.bias"))  # sinusoid in fp32, then model dtype
     emb = F.silu(emb)
     return F.linear(emb, _w(sd, "time_embedding.linear_2.weight"), _w(sd, "time_embedding.linear_2.bias"))
 

@@ -1,0 +1,59 @@
+"""Weight-format loaders on round-tripped synthetic checkpoints in the reference's on-disk layouts."""
+import os
+
+import pytest
+import torch
+
+from genima_b200 import checkpoint as ckpt
+from genima_b200 import weights as W
+from genima_b200.configs import ACTConfig, CLIPTextConfig, UNetConfig, VAEConfig
+
+
+@pytest.fixture(scope="module")
+def dirs(tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("ckpt"))
+    return ckpt.save_synthetic_checkpoints(root, UNetConfig.tiny(), VAEConfig.tiny(), CLIPTextConfig.tiny(),
+                                           ACTConfig.tiny())
+
+
+def test_last_checkpoint_is_chosen_in_natural_order(dirs, tmp_path):
+    assert ckpt.find_controlnet_dir(dirs["diffusion_ckpt"]).endswith(os.path.join("checkpoint-1000", "controlnet"))
+    for n in ("checkpoint-9", "checkpoint-10", "checkpoint-100"):
+        os.makedirs(tmp_path / n / "controlnet")
+    assert ckpt.find_controlnet_dir(str(tmp_path)).endswith(os.path.join("checkpoint-100", "controlnet"))
+    empty = tmp_path / "flat"
+    os.makedirs(empty)
+    assert ckpt.find_controlnet_dir(str(empty)) == str(empty)      # no checkpoint-* sub-directory: the dir itself
+
+
+def test_load_sd_turbo_round_trip(dirs):
+    out = ckpt.load_sd_turbo(dirs["sd_ckpt"], dirs["diffusion_ckpt"])
+    assert out["unet_cfg"] == UNetConfig.tiny()
+    assert out["vae_cfg"].block_out_channels == VAEConfig.tiny().block_out_channels
+    assert out["scheduler_cfg"].timestep_spacing == "trailing"
+    want = W.synth_state_dict(W.controlnet_shapes(UNetConfig.tiny()), salt=1)    # checkpoint-1000, not -500
+    for k, v in want.items():
+        assert torch.equal(out["controlnet"][k], v), k
+    want = W.synth_state_dict(W.unet_shapes(UNetConfig.tiny()))
+    assert all(torch.equal(out["unet"][k], v) for k, v in want.items())
+
+
+def test_schema_mismatch_fails_loudly(dirs):
+    sd = W.synth_state_dict(W.unet_shapes(UNetConfig.tiny()))
+    sd.pop("conv_in.weight")
+    with pytest.raises(ValueError):
+        ckpt.check_schema(sd, W.unet_shapes(UNetConfig.tiny()), "U-Net")
+    with pytest.raises(FileNotFoundError):
+        ckpt.load_sd_turbo("stabilityai/sd-turbo", dirs["diffusion_ckpt"])   # hub ids cannot resolve offline
+    with pytest.raises(NotImplementedError):
+        ckpt.unet_config_from_json({"use_linear_projection": False})
+    with pytest.raises(NotImplementedError):
+        ckpt.scheduler_config_from_json({"_class_name": "EulerAncestralDiscreteScheduler"}) and None or \
+            __import__("genima_b200.scheduler", fromlist=["x"]).EulerDiscreteSchedule(
+                ckpt.scheduler_config_from_json({"_class_name": "EulerAncestralDiscreteScheduler"}))
+
+
+def test_controller_snapshot_round_trip(dirs):
+    sd = ckpt.load_controller_snapshot(os.path.join(dirs["controller_ckpt"], "latest.pt"), ACTConfig.tiny())
+    want = W.synth_state_dict(W.act_shapes(ACTConfig.tiny()), salt=3)
+    assert set(sd) == set(want) and all(torch.equal(sd[k], want[k]) for k in want)

@@ -1,0 +1,54 @@
+"""Euler-discrete schedule tables (genima_b200/scheduler.py, host scalars only) against the oracle restatement of
+diffusers' EulerDiscreteScheduler and against closed-form facts."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from genima_b200.configs import SchedulerConfig
+from genima_b200.scheduler import EulerDiscreteSchedule
+from oracle.scheduler import EulerDiscreteOracle
+
+
+@pytest.mark.parametrize("n,expect", [(1, [999]), (4, [999, 749, 499, 249]), (5, [999, 799, 599, 399, 199]),
+                                       (10, [999, 899, 799, 699, 599, 499, 399, 299, 199, 99])])
+def test_trailing_timesteps(n, expect):
+    ts, sig = EulerDiscreteSchedule().set_timesteps(n)
+    assert ts.tolist() == expect
+    ots, osig = EulerDiscreteOracle().set_timesteps(n)
+    assert np.array_equal(ts, ots) and np.array_equal(sig, osig)
+    assert sig[-1] == 0.0 and np.all(np.diff(sig) < 0)
+
+
+def test_sigma_max_and_init_noise_sigma():
+    s = EulerDiscreteSchedule()
+    s.set_timesteps(5)
+    assert abs(s.init_noise_sigma - 14.6146) < 1e-3          # sigma_999 of the SD scaled-linear schedule
+    lead = EulerDiscreteSchedule(SchedulerConfig(timestep_spacing="leading"))
+    lead.set_timesteps(5)
+    assert abs(lead.init_noise_sigma - math.sqrt(float(lead.sigmas.max()) ** 2 + 1)) < 1e-6
+
+
+def test_unknown_scheduler_classes_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        EulerDiscreteSchedule(SchedulerConfig(class_name="EulerAncestralDiscreteScheduler"))
+    with pytest.raises(NotImplementedError):
+        EulerDiscreteSchedule(SchedulerConfig(prediction_type="v_prediction"))
+
+
+def test_euler_step_equals_ddim_eta0_update():
+    """with y = x / sqrt(sigma^2 + 1), DDIM(eta=0) on y is the Euler step on x."""
+    o = EulerDiscreteOracle()
+    _, sig = o.set_timesteps(5)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64) * float(sig[0])
+    eps = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64)
+    for i in range(5):
+        s, s2 = float(sig[i]), float(sig[i + 1])
+        x_next = o.step(eps.float(), i, x.float()).double()
+        ab, ab2 = 1 / (s * s + 1), 1 / (s2 * s2 + 1)                      # alpha_bar from sigma
+        y = x * math.sqrt(ab)
+        y2 = math.sqrt(ab2) * (y - math.sqrt(1 - ab) * eps) / math.sqrt(ab) + math.sqrt(1 - ab2) * eps
+        assert torch.allclose(x_next * math.sqrt(ab2), y2, rtol=1e-5, atol=1e-5)
+        x = x_next

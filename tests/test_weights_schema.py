@@ -1,0 +1,59 @@
+"""State-dict schemas reproduce the published parameter counts of the upstream models, which pins
+the restated architectures structurally: a missing / mis-shaped layer changes the total."""
+import torch
+
+from genima_b200 import weights as W
+from genima_b200.configs import ACTConfig, CLIPTextConfig, UNetConfig, VAEConfig
+
+
+def test_parameter_counts_match_published_models():
+    assert round(W.count_params(W.unet_shapes(UNetConfig())) / 1e6, 1) == 865.9       # SD-2.1 U-Net
+    assert round(W.count_params(W.controlnet_shapes(UNetConfig())) / 1e6, 1) == 364.2  # ControlNetModel.from_unet
+    assert round(W.count_params(W.vae_decoder_shapes(VAEConfig())) / 1e6, 1) == 49.5   # KL-VAE decoder + post_quant
+    assert round(W.count_params(W.clip_text_shapes(CLIPTextConfig.sd_turbo())) / 1e6, 1) == 340.4  # OpenCLIP-H text
+
+
+def test_clip_text_schema_matches_transformers_module():
+    from transformers import CLIPTextConfig as HFConfig
+    from transformers import CLIPTextModel
+
+    cfg = CLIPTextConfig.tiny()
+    hf = CLIPTextModel(HFConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
+                                intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_layers,
+                                num_attention_heads=cfg.num_heads, max_position_embeddings=cfg.max_positions))
+    ours = W.clip_text_shapes(cfg)
+    theirs = {k: tuple(v.shape) for k, v in hf.state_dict().items() if "position_ids" not in k}
+    assert dict(ours) == theirs
+
+
+def test_resnet18_trunk_schema_matches_torchvision():
+    import torchvision
+
+    tv = torchvision.models.resnet18(weights=None, norm_layer=torchvision.ops.FrozenBatchNorm2d)
+    theirs = {f"encoder_model.backbone.{k}": tuple(v.shape) for k, v in tv.state_dict().items()
+              if not k.startswith("fc.")}
+    ours = {k: v for k, v in W.act_shapes(ACTConfig()).items()
+            if k.startswith("encoder_model.backbone.") and ".film." not in k}
+    assert ours == theirs
+
+
+def test_unet_skip_channels_and_decoder_inputs():
+    cfg = UNetConfig()
+    assert W.unet_skip_channels(cfg) == [320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280]
+    s = W.unet_shapes(cfg)
+    # decoder ResBlock input widths after the skip concat
+    cins = [s[f"up_blocks.{i}.resnets.{j}.conv1.weight"][1] for i in range(4) for j in range(3)]
+    assert cins == [2560, 2560, 2560, 2560, 2560, 1920, 1920, 1280, 960, 960, 640, 640]
+
+
+def test_synthetic_weights_are_deterministic_fp16_and_well_scaled():
+    shapes = W.controlnet_shapes(UNetConfig.tiny())
+    a, b = W.synth_state_dict(shapes, salt=1), W.synth_state_dict(shapes, salt=1)
+    c = W.synth_state_dict(shapes, salt=2)
+    for k in shapes:
+        assert a[k].dtype == torch.float16 and torch.equal(a[k], b[k])
+    assert not torch.equal(a["conv_in.weight"], c["conv_in.weight"])
+    for k, v in a.items():
+        if v.dim() > 1:      # conv / linear weights ~ N(0, 1/fan_in): activations stay O(1) through the stack
+            fan_in = v[0].numel()
+            assert 0.5 < float(v.float().std()) * fan_in ** 0.5 < 1.5, k
