@@ -124,8 +124,8 @@ class DeviceACT:
         self.tokens_per_view = fh * fh
         self.T = 2 + cfg.num_views * self.tokens_per_view
         # position table in OUR token order: [latent, proprio, view0 (row-major h, w), view1, ...]
-        view_pos = _sine_position_table(fh, fh, d // 2)
-        add_pos = P.sd[f"{a}.additional_pos_embed.weight"].float()
+        view_pos = _sine_position_table(fh, fh, d // 2).to(dev)
+        add_pos = P.sd[f"{a}.additional_pos_embed.weight"].to(dev, torch.float32)
         pos = torch.cat([add_pos] + [view_pos] * cfg.num_views, 0)        # [T, d] fp32
         self.pos16 = pos.to(dev, torch.float16).contiguous()
         qpos_emb = P.sd[f"{a}.query_embed.weight"].float()

@@ -201,13 +201,13 @@ class B200GenimaACT:
     def encode_clip_text(self, tokens: torch.Tensor):
         """tokens [B, T, 77] int -> (task_emb [B, proj] fp32, last hidden [B*T, 77, d]).  The text is constant for an
         episode (controller/env/rlbench_utils.py:156), so results are cached by token content."""
-        if self.clip is None:
-            raise RuntimeError("no CLIP text tower bound: pass clip_state_dict or supply task_emb yourself")
         shape = tokens.shape
         tks = tokens.reshape(-1, shape[-1])
         key = tks.cpu().numpy().tobytes()
         hit = self._emb_cache.get(key)
         if hit is None:
+            if self.clip is None:
+                raise RuntimeError("no CLIP text tower bound: pass clip_state_dict or supply task_emb yourself")
             if len(self._emb_cache) > 64:
                 self._emb_cache.clear()
             emb, pooled = self.clip(tks.to(self.ops.device, torch.int64))

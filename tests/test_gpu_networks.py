@@ -309,14 +309,18 @@ def test_pipeline_cuda_graph_matches_eager(ops):
     x, ctx, cond = _unet_inputs(ucfg, 1, seed=12)
     lat = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(2))
     kw = dict(prompt_embeds=ctx.cuda().half(), num_inference_steps=3, guidance_scale=0.0, latents=lat, output_type="u8")
+    def same(x, y):
+        d = (x.int() - y.int()).abs()
+        return int(d.max()) <= 1 and float((d == 0).float().mean()) > 0.999
+
     a = pipe(image=cond, **kw).images.cpu()
     b = gpipe(image=cond, **kw).images.cpu()
-    assert torch.equal(a, b)
+    assert same(a, b)
     cond2 = torch.flip(cond, dims=[1])
     a2 = pipe(image=cond2, **kw).images.cpu()
     b2 = gpipe(image=cond2, **kw).images.cpu()       # replay of the captured graph on new inputs
-    assert torch.equal(a2, b2)
-    assert not torch.equal(a, a2)
+    assert same(a2, b2)
+    assert not same(a, a2)
 
 
 def test_pipeline_rejects_unimplemented(ops):
