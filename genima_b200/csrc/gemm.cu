@@ -23,7 +23,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int MAX_SEGS = 52;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_COLSPLIT = 2;                        // epilogue warps per TMEM lane quadrant
+constexpr int GEMM_THREADS = 64 + 128 * EPI_COLSPLIT;  // producer warp + MMA warp + epilogue warps
 
 struct KSeg {
   int8_t map;  // index into tmA
@@ -75,8 +76,16 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     default: return v;
   }
 }
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v) {
+  if constexpr (ACT == GN_ACT_SILU) return silu_f(v);
+  else if constexpr (ACT == GN_ACT_GELU) return gelu_erf_f(v);
+  else if constexpr (ACT == GN_ACT_RELU) return fmaxf(v, 0.0f);
+  else if constexpr (ACT == GN_ACT_QUICKGELU) return quick_gelu_f(v);
+  else return v;
+}
 
-// v = act_pre(acc * scale[n] + bias[n] + rowvec[b, n])
+// v = act_pre(acc * scale[n] + bias[n] + rowvec[b, n])   (runtime-dispatched form, used by the split-K reduce pass)
 __device__ __forceinline__ float epi_pre(const EpiParams& e, float acc, int n, int b) {
   float v = acc;
   if (e.scale) v *= __ldg(e.scale + n);
@@ -85,10 +94,10 @@ __device__ __forceinline__ float epi_pre(const EpiParams& e, float acc, int n, i
   return apply_act(v, e.act_pre);
 }
 
-// Finalise CH consecutive output columns [nout, nout + CH) of row m from pre-activation values v[].
+// Finalise CH consecutive output columns [nout, nout + CH) of row m from pre-activation values v[]:
+// out = act_post(alpha * v + beta * residual).  16-byte vector path when the chunk is full and aligned.
 template <int CH>
-__device__ __forceinline__ void epi_store(const EpiParams& e, const float (&v)[CH], int m, int nout, int n_out_total) {
-  float o[CH];
+__device__ __forceinline__ void epi_store(const EpiParams& e, float (&v)[CH], int m, int nout, int n_out_total) {
   const bool full = (nout + CH <= n_out_total);
   if (e.residual) {
     const __half* rp = e.residual + (int64_t)m * e.ldr + nout;
@@ -100,30 +109,38 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, const float (&v)[C
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           float2 f = __half22float2(hp[t]);
-          o[j + 2 * t] = e.alpha * v[j + 2 * t] + e.beta * f.x;
-          o[j + 2 * t + 1] = e.alpha * v[j + 2 * t + 1] + e.beta * f.y;
+          v[j + 2 * t] = fmaf(e.alpha, v[j + 2 * t], e.beta * f.x);
+          v[j + 2 * t + 1] = fmaf(e.alpha, v[j + 2 * t + 1], e.beta * f.y);
         }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         float r = (nout + j < n_out_total) ? __half2float(rp[j]) : 0.0f;
-        o[j] = e.alpha * v[j] + e.beta * r;
+        v[j] = e.alpha * v[j] + e.beta * r;
       }
     }
-  } else {
+  } else if (e.alpha != 1.0f) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) o[j] = e.alpha * v[j];
+    for (int j = 0; j < CH; ++j) v[j] *= e.alpha;
   }
-  if (e.act_post != GN_ACT_NONE) {
+  if (e.act_post == GN_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) o[j] = apply_act(o[j], e.act_post);
+    for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (e.act_post != GN_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], e.act_post);
   }
   if (e.out32) {
     float* op = e.out32 + (int64_t)m * e.ldo + nout;
+    if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (nout + j < n_out_total) op[j] = o[j];
+      for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (nout + j < n_out_total) op[j] = v[j];
+    }
     return;
   }
   __half* op = e.out + (int64_t)m * e.ldo + nout;
@@ -131,58 +148,118 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, const float (&v)[C
 #pragma unroll
     for (int j = 0; j < CH; j += 8) {
       uint4 q;
-      q.x = pack_half2(o[j], o[j + 1]);
-      q.y = pack_half2(o[j + 2], o[j + 3]);
-      q.z = pack_half2(o[j + 4], o[j + 5]);
-      q.w = pack_half2(o[j + 6], o[j + 7]);
+      q.x = pack_half2(v[j], v[j + 1]);
+      q.y = pack_half2(v[j + 2], v[j + 3]);
+      q.z = pack_half2(v[j + 4], v[j + 5]);
+      q.w = pack_half2(v[j + 6], v[j + 7]);
       *reinterpret_cast<uint4*>(op + j) = q;
     }
   } else {
 #pragma unroll
     for (int j = 0; j < CH; ++j)
-      if (nout + j < n_out_total) op[j] = __float2half_rn(o[j]);
+      if (nout + j < n_out_total) op[j] = __float2half_rn(v[j]);
   }
 }
 
-template <int CH>
-__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH]);
-template <>
-__device__ __forceinline__ void tmem_ld_chunk<32>(uint32_t taddr, uint32_t (&r)[32]) {
-  tmem_ld_x32(taddr, r);
-}
-template <>
-__device__ __forceinline__ void tmem_ld_chunk<16>(uint32_t taddr, uint32_t (&r)[16]) {
-  tmem_ld_x16(taddr, r);
+// Epilogue of one output row over this warp's share of the tile's 16-column chunks (chunk index cw, cw + EPI_COLSPLIT, ...).
+// s_scale / s_bias: per-column fp32 vectors of the tile staged in shared memory (scale = 1 / bias = 0 when absent).
+// Rolled loop over chunks with a compile-time activation: the body stays small enough for the instruction cache
+// (a fully unrolled, runtime-dispatched epilogue measured ~60 instructions per element and was fetch-bound).
+template <int ACT>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int n0, int m, int b, bool valid,
+                                              int cw, const float* s_scale, const float* s_bias) {
+  const EpiParams& e = p.epi;
+  const int nchunks = p.block_n >> 4;
+#pragma unroll 1
+  for (int ch = cw; ch < nchunks; ch += EPI_COLSPLIT) {
+    const int c = ch << 4;
+    uint32_t r[16];
+    tmem_ld_x16(taddr + c, r);
+    tmem_ld_wait();
+    const int n = n0 + c;
+    if (!valid || n >= e.N) continue;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + j);
+      const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + j);
+      v[j] = fmaf(__uint_as_float(r[j]), sc.x, bi.x);
+      v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, bi.y);
+      v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, bi.z);
+      v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, bi.w);
+    }
+    if (e.rowvec) {
+      const float* rv = e.rowvec + (int64_t)b * e.N + n;
+      if (n + 16 <= e.N && ((reinterpret_cast<uintptr_t>(rv) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(rv + j));
+          v[j] += t.x;
+          v[j + 1] += t.y;
+          v[j + 2] += t.z;
+          v[j + 3] += t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n + j < e.N) v[j] += __ldg(rv + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = act_ct<ACT>(v[j]);
+    epi_store<16>(e, v, m, n, e.N);
+  }
 }
 
-// Plain (non-GEGLU) epilogue of CH accumulator columns starting at tile column c.
-template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, int c, int n0, int m, int b,
-                                               bool valid, int split) {
-  uint32_t r[CH];
-  tmem_ld_chunk<CH>(taddr + c, r);
-  tmem_ld_wait();
-  if (!valid) return;
+// GEGLU epilogue: accumulator columns come in 128-wide groups [64 values | 64 gates]; out[m, j] = value * gelu(gate).
+__device__ __forceinline__ void epilogue_rows_geglu(const GemmParams& p, uint32_t taddr, int n0, int m, bool valid,
+                                                    int cw, const float* s_bias) {
   const EpiParams& e = p.epi;
-  const int n = n0 + c;
-  if (n >= e.N) return;
-  if (p.splits > 1) {
-    float* wp = p.ws + ((int64_t)split * e.M + m) * e.N + n;
-    if (n + CH <= e.N && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
+  const int n_out_total = e.N >> 1;
+  const int nchunks = p.block_n >> 5;  // 16-wide value chunks: 4 per 128-column group
+#pragma unroll 1
+  for (int ch = cw; ch < nchunks; ch += EPI_COLSPLIT) {
+    const int c = ((ch >> 2) << 7) + ((ch & 3) << 4);  // tile column of the value chunk
+    uint32_t rv[16], rg[16];
+    tmem_ld_x16(taddr + c, rv);
+    tmem_ld_x16(taddr + c + 64, rg);
+    tmem_ld_wait();
+    const int n = n0 + c;
+    if (!valid || n >= e.N) continue;
+    float v[16];
 #pragma unroll
-      for (int j = 0; j < CH; j += 4)
-        *reinterpret_cast<uint4*>(wp + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    for (int j = 0; j < 16; ++j) {
+      const float a = __uint_as_float(rv[j]) + s_bias[c + j];
+      const float g = __uint_as_float(rg[j]) + s_bias[c + 64 + j];
+      v[j] = a * gelu_erf_f(g);
+    }
+    epi_store<16>(e, v, m, ((n0 + ((ch >> 2) << 7)) >> 1) + ((ch & 3) << 4), n_out_total);
+  }
+}
+
+// Split-K partial: raw fp32 accumulators to the workspace [split][M][N].
+__device__ __forceinline__ void epilogue_rows_partial(const GemmParams& p, uint32_t taddr, int n0, int m, bool valid,
+                                                      int cw, int split) {
+  const EpiParams& e = p.epi;
+  const int nchunks = p.block_n >> 4;
+#pragma unroll 1
+  for (int ch = cw; ch < nchunks; ch += EPI_COLSPLIT) {
+    const int c = ch << 4;
+    uint32_t r[16];
+    tmem_ld_x16(taddr + c, r);
+    tmem_ld_wait();
+    const int n = n0 + c;
+    if (!valid || n >= e.N) continue;
+    float* wp = p.ws + ((int64_t)split * e.M + m) * e.N + n;
+    if (n + 16 <= e.N && ((reinterpret_cast<uintptr_t>(wp) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(wp + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < CH; ++j)
+      for (int j = 0; j < 16; ++j)
         if (n + j < e.N) wp[j] = __uint_as_float(r[j]);
     }
-    return;
   }
-  float v[CH];
-#pragma unroll
-  for (int j = 0; j < CH; ++j) v[j] = (n + j < e.N) ? epi_pre(e, __uint_as_float(r[j]), n + j, b) : 0.0f;
-  epi_store<CH>(e, v, m, n, e.N);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -198,11 +275,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + stages * b_stage_bytes);
+  float* s_scale = reinterpret_cast<float*>(smem_b + stages * b_stage_bytes);
+  float* s_bias = s_scale + 256;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  const int n0 = blockIdx.x * block_n;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
@@ -214,12 +294,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp >= 2) {
+    // stage the tile's per-column scale / bias once (identity when absent) — read back as broadcast float4s
+    for (int i = threadIdx.x - 64; i < block_n; i += GEMM_THREADS - 64) {
+      const int n = n0 + i;
+      s_scale[i] = (p.epi.scale && n < p.epi.N) ? __ldg(p.epi.scale + n) : 1.0f;
+      s_bias[i] = (p.epi.bias && n < p.epi.N) ? __ldg(p.epi.bias + n) : 0.0f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n0 = blockIdx.x * block_n;
   const int mt = blockIdx.y;
   int m0 = 0, x0 = 0, y0 = 0, b0 = 0;
   if (p.mode == 0) {
@@ -289,8 +376,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       umma_commit(tmem_full_bar);
     }
   } else {
-    // -------------------------------------------------------------------- epilogue warps (2..5)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // -------------------------------------------------------------------- epilogue warps (2 .. 2 + 4 * EPI_COLSPLIT)
+    const int q = warp & 3;                // TMEM lane quadrant this warp may access
+    const int cw = (warp - 2) >> 2;        // which share of the column chunks
     const int row = q * 32 + lane;
     int m;
     bool valid;
@@ -309,33 +397,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    if (p.epi.geglu) {
-      // columns come in 128-wide groups: [64 values | 64 gates]; out[m, j] = value * gelu(gate)
-      const EpiParams& e = p.epi;
-      const int n_out_total = e.N / 2;
-      for (int g = 0; g < block_n; g += 128) {
-#pragma unroll 1
-        for (int sub = 0; sub < 64; sub += 32) {
-          uint32_t rv[32], rg[32];
-          tmem_ld_x32(taddr + g + sub, rv);
-          tmem_ld_x32(taddr + g + 64 + sub, rg);
-          tmem_ld_wait();
-          const int n = n0 + g + sub;  // accumulator column of the value
-          if (!valid || n >= e.N) continue;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = epi_pre(e, __uint_as_float(rv[j]), n + j, b);
-            const float gt = epi_pre(e, __uint_as_float(rg[j]), n + 64 + j, b);
-            v[j] = a * gelu_erf_f(gt);
-          }
-          epi_store<32>(e, v, m, (n0 + g) / 2 + sub, n_out_total);
-        }
-      }
+    if (p.splits > 1) {
+      epilogue_rows_partial(p, taddr, n0, m, valid, cw, blockIdx.z);
+    } else if (p.epi.geglu) {
+      epilogue_rows_geglu(p, taddr, n0, m, valid, cw, s_bias);
     } else {
-      int c = 0;
-      for (; c + 32 <= block_n; c += 32) epilogue_chunk<32>(p, taddr, c, n0, m, b, valid, blockIdx.z);
-      if (c < block_n) epilogue_chunk<16>(p, taddr, c, n0, m, b, valid, blockIdx.z);
+      switch (p.epi.act_pre) {
+        case GN_ACT_SILU: epilogue_rows<GN_ACT_SILU>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias); break;
+        case GN_ACT_GELU: epilogue_rows<GN_ACT_GELU>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias); break;
+        case GN_ACT_RELU: epilogue_rows<GN_ACT_RELU>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias); break;
+        case GN_ACT_QUICKGELU: epilogue_rows<GN_ACT_QUICKGELU>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias); break;
+        default: epilogue_rows<GN_ACT_NONE>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias); break;
+      }
     }
     tc_fence_before();
   }
@@ -384,7 +457,7 @@ struct TileChoice {
 };
 
 static int smem_bytes_for(int block_n, int stages) {
-  return stages * (A_STAGE_BYTES + block_n * BLOCK_K * 2) + (2 * stages + 1) * 8 + 16 + 1024;
+  return stages * (A_STAGE_BYTES + block_n * BLOCK_K * 2) + 2 * 256 * 4 + (2 * stages + 1) * 8 + 16 + 1024;
 }
 
 // Pick (block_n, splits) minimising a simple wave model of the kernel time.

@@ -1,0 +1,39 @@
+"""Runs one gn_linear / gn_conv2d problem a few times (for `ncu --set full -k regex:gemm_tc`).
+Usage: python tools/one_gemm.py linear M N K [geglu|fp32out|bias_res|plain]   |   conv B H Cin Cout [stride]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from genima_b200.ops import Ops  # noqa: E402
+from genima_b200.packing import pack_conv_weight, pack_geglu_weight  # noqa: E402
+
+ops = Ops(0, workspace_mb=256)
+kind = sys.argv[1]
+if kind == "linear":
+    M, N, K = (int(v) for v in sys.argv[2:5])
+    mode = sys.argv[5] if len(sys.argv) > 5 else "plain"
+    a = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).half()
+    b = torch.randn(N, device="cuda")
+    kw = {}
+    if mode == "geglu":
+        w, b = pack_geglu_weight(w, b)
+        kw = dict(bias=b, geglu=True)
+    elif mode == "fp32out":
+        kw = dict(out_fp32=True)
+    elif mode == "bias_res":
+        kw = dict(bias=b, residual=torch.randn(M, N, device="cuda").half())
+    for _ in range(5):
+        out = ops.linear(a, w, **kw)
+else:
+    B, H, Cin, Cout = (int(v) for v in sys.argv[2:6])
+    s = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+    x = torch.randn(B, H, H, Cin, device="cuda").half()
+    wp = pack_conv_weight((torch.randn(Cout, Cin, 3, 3) * (Cin * 9) ** -0.5).half()).cuda()
+    bias = torch.randn(Cout, device="cuda")
+    for _ in range(5):
+        out = ops.conv2d(x, wp, Cout, stride=s, bias=bias)
+torch.cuda.synchronize()
+print(ops.last_gemm_config(), float(out.float().abs().mean()))
