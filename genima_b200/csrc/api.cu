@@ -143,6 +143,12 @@ int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits) {
   return GN_OK;
 }
 
+int gn_set_gemm_trace(gn_handle* h, void* dptr_u64x8) {
+  if (!h) return GN_ERR_INVALID;
+  h->gemm_trace = dptr_u64x8;
+  return GN_OK;
+}
+
 int gn_get_last_gemm_config(const gn_handle* h, int32_t* out4) {
   if (!h || !out4) return GN_ERR_INVALID;
   for (int i = 0; i < 4; ++i) out4[i] = h->last_cfg[i];

@@ -28,6 +28,7 @@ struct gn_handle {
   char err[512] = {0};
   void* workspace = nullptr;
   int64_t workspace_bytes = 0;
+  void* gemm_trace = nullptr;  // device uint64[8]: phase timestamps of CTA (0,0,0) of the next GEMM launches
   int force_block_n = 0;
   int force_splits = 0;
   int32_t last_cfg[4] = {0, 0, 0, 0};

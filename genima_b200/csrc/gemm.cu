@@ -64,8 +64,17 @@ struct GemmParams {
   int tiles_w, tiles_h;
   int block_n, stages, tmem_cols;
   float* ws;  // split-K partials [splits][M][N] fp32
+  unsigned long long* trace;  // optional: %globaltimer stamps of CTA (0,0,0)'s phases (gn_set_gemm_trace)
   KSeg segs[MAX_SEGS];
 };
+
+__device__ __forceinline__ void trace_stamp(const GemmParams& p, int slot) {
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[slot] = t;
+  }
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -283,6 +292,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int n0 = blockIdx.x * block_n;
+  if (threadIdx.x == 0) trace_stamp(p, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
@@ -306,6 +316,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(p, 1);
 
   const int mt = blockIdx.y;
   int m0 = 0, x0 = 0, y0 = 0, b0 = 0;
@@ -353,6 +364,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
         }
         tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+        if (it == 0) trace_stamp(p, 2);
       }
     }
   } else if (warp == 1) {
@@ -364,6 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const uint32_t ph = (it / stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (it == 0) trace_stamp(p, 3);
         const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES), 1024, 0);
         const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * b_stage_bytes), 1024, 0);
 #pragma unroll
@@ -374,6 +387,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         umma_commit(&empty_bar[s]);
       }
       umma_commit(tmem_full_bar);
+      trace_stamp(p, 4);
     }
   } else {
     // -------------------------------------------------------------------- epilogue warps (2 .. 2 + 4 * EPI_COLSPLIT)
@@ -396,6 +410,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) trace_stamp(p, 5);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     if (p.splits > 1) {
       epilogue_rows_partial(p, taddr, n0, m, valid, cw, blockIdx.z);
@@ -411,12 +426,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
     }
     tc_fence_before();
+    if (threadIdx.x == 64) trace_stamp(p, 6);
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (threadIdx.x == 0) trace_stamp(p, 7);
 }
 
 // Split-K second pass: sum the fp32 partials and run the same fused epilogue.  8 columns per thread.
@@ -555,6 +572,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
   p.tmem_cols = tc.tmem_cols;
   p.kb_per_split = gn::ceil_div(p.num_kblocks, tc.splits);
   p.ws = static_cast<float*>(h->workspace);
+  p.trace = static_cast<unsigned long long*>(h->gemm_trace);
 
   // weight tensor map: [N rows][ktot] fp16, box {64, block_n}
   {

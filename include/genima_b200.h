@@ -71,6 +71,10 @@ const char* gn_version(void);
 int gn_set_workspace(gn_handle* h, void* dptr, int64_t bytes);
 /* Force tile width / split count of the next GEMM-class calls (0 = heuristic); used by tests and tuning. */
 int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits);
+/* Debug aid: when dptr (device uint64[8]) is non-NULL, CTA (0,0,0) of every following GEMM-class launch writes
+ * %globaltimer stamps of its phases: 0 start, 1 set-up done, 2 first TMA issued, 3 first operands landed, 4 all MMAs
+ * issued, 5 accumulator complete, 6 epilogue done, 7 exit.  NULL switches it off. */
+int gn_set_gemm_trace(gn_handle* h, void* dptr_u64x8);
 /* Last launch configuration chosen by gn_linear / gn_conv2d: out[0]=block_n, out[1]=splits, out[2]=stages, out[3]=ctas. */
 int gn_get_last_gemm_config(const gn_handle* h, int32_t* out4);
 /* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
