@@ -104,8 +104,9 @@ int gn_create(int device, gn_handle** out) {
     return GN_ERR_NODRIVER;
   }
   h->encode_fn = fn;
-  h->stats_scratch_bytes = 64 * 1024;
-  if (cudaMalloc(&h->stats_scratch, h->stats_scratch_bytes) != cudaSuccess) {
+  h->stats_scratch_bytes = 256 * 1024;
+  if (cudaMalloc(&h->stats_scratch, h->stats_scratch_bytes) != cudaSuccess ||
+      cudaMemset(h->stats_scratch, 0, h->stats_scratch_bytes) != cudaSuccess) {
     cudaGetLastError();
     delete h;
     return GN_ERR_NOMEM;
@@ -121,6 +122,8 @@ int gn_destroy(gn_handle* h) {
       cudaEventDestroy(r.b);
     }
     for (auto e : h->event_pool) cudaEventDestroy(e);
+    for (auto e : h->tune_ev)
+      if (e) cudaEventDestroy(e);
   }
   if (h && h->stats_scratch) cudaFree(h->stats_scratch);
   delete h;
@@ -140,6 +143,19 @@ int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits) {
   if (!h) return GN_ERR_INVALID;
   h->force_block_n = block_n;
   h->force_splits = splits;
+  return GN_OK;
+}
+
+int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm) {
+  if (!h || ctas_per_sm < 0 || ctas_per_sm > 2) return GN_ERR_INVALID;
+  h->force_occupancy = ctas_per_sm;
+  return GN_OK;
+}
+
+int gn_set_autotune(gn_handle* h, int enable) {
+  if (!h) return GN_ERR_INVALID;
+  h->autotune = enable != 0;
+  if (enable < 0) h->tune_cache.clear();
   return GN_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <array>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -31,12 +32,18 @@ struct gn_handle {
   void* gemm_trace = nullptr;  // device uint64[8]: phase timestamps of CTA (0,0,0) of the next GEMM launches
   int force_block_n = 0;
   int force_splits = 0;
+  int force_occupancy = 0;
+  // measured tile configurations per problem shape (gn_set_autotune): key -> {block_n, splits, stages, tmem_cols}
+  bool autotune = false;
+  std::unordered_map<std::string, std::array<int, 4>> tune_cache;
+  cudaEvent_t tune_ev[2] = {nullptr, nullptr};
   int32_t last_cfg[4] = {0, 0, 0, 0};
   int64_t launches = 0;
   bool gemm_attr_set = false;
-  void* stats_scratch = nullptr;  // GroupNorm (sum, sumsq) accumulators, owned by the handle
+  void* stats_scratch = nullptr;  // GroupNorm: grid-barrier words (first 256 B, zero-initialised) + per-CTA partials
   int64_t stats_scratch_bytes = 0;
   bool attn_attr_set = false;
+  bool gn_attr_set = false;
   // cuTensorMapEncodeTiled resolved at runtime through cudaGetDriverEntryPoint (the library must load on a
   // CPU-only box, so libcuda is never linked directly).
   void* encode_fn = nullptr;

@@ -1,6 +1,6 @@
 // GroupNorm (NHWC, optional channel-concat of two sources, optional fused SiLU), LayerNorm and row softmax.
-// All HBM/L2-bound: 16-byte vector loads, fp32 statistics, one read for the statistics and one read+write for the
-// normalisation.  Grids are sized to ~2 waves of the SM count.
+// All HBM/L2-bound: 16-byte vector loads, fp32 statistics; GroupNorm is a single launch with a grid barrier between
+// the statistics and the normalisation phase (one read + one write when the per-CTA slice fits in shared memory).
 #include "common.h"
 #include "ptx.cuh"
 
@@ -9,15 +9,27 @@ namespace gn {
 struct GNParams {
   const __half* x0;
   const __half* x1;
-  int C0, C1, C, B, HW, G, cg;
-  int pix_per_block;
+  int C0, C1, C, B, HW, G, cg, NV;
+  int ctas_per_b, pix_per_cta;
+  int k;      // pixel lanes per CTA: thread t owns channel vector t % NV and pixels pix0 + t / NV + i * k
+  int cache;  // 1: the CTA's slice of x is kept in shared memory between the two phases
   float eps;
   const float* gamma;
   const float* beta;
   int silu;
-  float* stats;  // [B, G, 2] shifted sums
+  float* partial;     // [B][ctas_per_b][G][2] shifted (sum, sumsq) of each CTA's slice
+  unsigned int* bar;  // grid barrier: [0] arrival count, [1] generation
+  unsigned long long* trace;  // optional phase timestamps of CTA 0 (gn_set_gemm_trace)
   __half* y;
 };
+
+__device__ __forceinline__ void gn_stamp(const GNParams& p, int slot) {
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[slot] = t;
+  }
+}
 
 __device__ __forceinline__ const __half* gn_src(const GNParams& p, int b, int pix, int c) {
   // pointer to channel c (multiple of 8; C0 % 8 == 0) of pixel pix in the virtual concat tensor
@@ -31,108 +43,197 @@ __device__ __forceinline__ float gn_shift(const GNParams& p, int b, int g) {
   return __half2float(__ldg(s));
 }
 
-// grid: (blocks_per_image, B); block: (bdx, bdy) — x walks 8-channel vectors, y walks pixels
-__global__ void __launch_bounds__(256) gn_stats_kernel(GNParams p) {
-  __shared__ float s_sum[64];
-  __shared__ float s_sq[64];
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int i = tid; i < p.G; i += blockDim.x * blockDim.y) {
-    s_sum[i] = 0.f;
-    s_sq[i] = 0.f;
-  }
-  __syncthreads();
-  const int b = blockIdx.y;
-  const int pix0 = blockIdx.x * p.pix_per_block;
-  const int pix1 = min(p.HW, pix0 + p.pix_per_block);
-  const int NV = p.C / 8;
-  for (int cv = threadIdx.x; cv < NV; cv += blockDim.x) {
-    const int c0 = cv * 8;
-    const int gA = c0 / p.cg;
-    const int gB = (c0 + 7) / p.cg;  // a vector spans at most two groups when cg >= 8 ... general case handled below
-    float kj[8];
-    int gj[8];
+// Group index of each of the 8 consecutive channels c0 .. c0 + 7 (one integer division when cg >= 8).
+__device__ __forceinline__ void gn_groups8(int c0, int cg, int (&g)[8]) {
+  const int g0 = c0 / cg;
+  if (cg >= 8) {
+    const int rem = c0 - g0 * cg;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      gj[j] = (c0 + j) / p.cg;
-      kj[j] = gn_shift(p, b, gj[j]);
-    }
-    float a1[8], a2[8];
+    for (int j = 0; j < 8; ++j) g[j] = g0 + ((rem + j >= cg) ? 1 : 0);
+  } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
-    for (int pix = pix0 + threadIdx.y; pix < pix1; pix += blockDim.y) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(gn_src(p, b, pix, c0)));
-      const __half2* hp = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(hp[t]);
-        const float d0 = f.x - kj[2 * t], d1 = f.y - kj[2 * t + 1];
-        a1[2 * t] += d0;
-        a2[2 * t] += d0 * d0;
-        a1[2 * t + 1] += d1;
-        a2[2 * t + 1] += d1 * d1;
-      }
-    }
-    if (gA == gB) {
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1 += a1[j];
-        s2 += a2[j];
-      }
-      atomicAdd(&s_sum[gA], s1);
-      atomicAdd(&s_sq[gA], s2);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&s_sum[gj[j]], a1[j]);
-        atomicAdd(&s_sq[gj[j]], a2[j]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < p.G; i += blockDim.x * blockDim.y) {
-    atomicAdd(&p.stats[((int64_t)b * p.G + i) * 2 + 0], s_sum[i]);
-    atomicAdd(&p.stats[((int64_t)b * p.G + i) * 2 + 1], s_sq[i]);
+    for (int j = 0; j < 8; ++j) g[j] = (c0 + j) / cg;
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(GNParams p) {
-  const int NV = p.C / 8;
-  const int64_t total = (int64_t)p.B * p.HW * NV;
-  const float inv_n = 1.0f / ((float)p.cg * (float)p.HW);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % NV);
-    const int64_t bp = idx / NV;
-    const int pix = (int)(bp % p.HW);
-    const int b = (int)(bp / p.HW);
-    const int c0 = cv * 8;
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(gn_src(p, b, pix, c0)));
-    const __half2* hp = reinterpret_cast<const __half2*>(&q);
-    float xv[8];
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// GroupNorm in ONE launch, one HBM read + one write, bit-reproducible:
+//   phase 1  every CTA reads its pixel slice once (kept in shared memory when it fits), accumulates shifted sums per
+//            thread, reduces them per channel then per group in a FIXED order and publishes [G][2] partials;
+//   barrier  grid-wide (all CTAs are co-resident: grid <= #SMs, one CTA per SM), sense-reversing, self-resetting so a
+//            captured CUDA graph can replay it;
+//   phase 2  every CTA sums the partials of its image in CTA order, normalises its slice and writes y (+ SiLU).
+// Dynamic smem: [red: T*16 floats][chan: C*2 floats][gstat: G*2 floats][slice cache: uint4 x pix_per_cta*NV].
+__global__ void __launch_bounds__(1024, 1) gn_fused_kernel(const GNParams p) {
+  extern __shared__ __align__(16) uint8_t gn_smem[];
+  const int T = p.NV * p.k;  // active threads
+  float* red = reinterpret_cast<float*>(gn_smem);
+  float* chan = red + (size_t)T * 16;
+  float* gstat = chan + (size_t)p.C * 2;
+  uint4* slice = reinterpret_cast<uint4*>(gstat + ((p.G * 2 + 3) & ~3));
+  __shared__ unsigned int s_gen;
+
+  const int t = threadIdx.x;
+  const int b = blockIdx.x / p.ctas_per_b;
+  const int ci = blockIdx.x % p.ctas_per_b;
+  const int pix0 = ci * p.pix_per_cta;
+  const int pix1 = min(p.HW, pix0 + p.pix_per_cta);
+  const bool active = t < T;
+  const int cv = active ? t % p.NV : 0;
+  const int pl = active ? t / p.NV : 0;
+  const int c0 = cv * 8;
+  gn_stamp(p, 0);
+  if (t == 0) s_gen = *reinterpret_cast<volatile unsigned int*>(p.bar + 1);
+
+  // ---- phase 1: shifted sums of this thread's channel vector over its pixels
+  int gj[8];
+  gn_groups8(c0, p.cg, gj);
+  float kj[8];
+  {
+    const float k_first = gn_shift(p, b, gj[0]);
+    const float k_last = (gj[7] != gj[0] && p.cg >= 8) ? gn_shift(p, b, gj[7]) : k_first;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 f = __half22float2(hp[t]);
-      xv[2 * t] = f.x;
-      xv[2 * t + 1] = f.y;
+    for (int j = 0; j < 8; ++j)
+      kj[j] = (p.cg >= 8) ? (gj[j] == gj[0] ? k_first : k_last) : ((j == 0) ? k_first : gn_shift(p, b, gj[j]));
+  }
+  if (active) {
+    float a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+    for (int pix = pix0 + pl; pix < pix1; pix += p.k) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(gn_src(p, b, pix, c0)));
+      if (p.cache) slice[(size_t)(pix - pix0) * p.NV + cv] = q;
+      const __half2* hp = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f = __half22float2(hp[u]);
+        const float d0 = f.x - kj[2 * u], d1 = f.y - kj[2 * u + 1];
+        a1[2 * u] += d0;
+        a2[2 * u] = fmaf(d0, d0, a2[2 * u]);
+        a1[2 * u + 1] += d1;
+        a2[2 * u + 1] = fmaf(d1, d1, a2[2 * u + 1]);
+      }
     }
-    float o[8];
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
+    float4* r4 = reinterpret_cast<float4*>(red + (size_t)t * 16);
+    r4[0] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+    r4[1] = make_float4(a1[4], a1[5], a1[6], a1[7]);
+    r4[2] = make_float4(a2[0], a2[1], a2[2], a2[3]);
+    r4[3] = make_float4(a2[4], a2[5], a2[6], a2[7]);
+  }
+  __syncthreads();
+  gn_stamp(p, 1);
+  // per channel: fixed-order sum over the k pixel lanes
+  for (int c = t; c < p.C; c += blockDim.x) {
+    const int v = c >> 3, j = c & 7;
+    float s1 = 0.f, s2 = 0.f;
+    for (int l = 0; l < p.k; ++l) {
+      const float* r = red + ((size_t)l * p.NV + v) * 16;
+      s1 += r[j];
+      s2 += r[8 + j];
+    }
+    chan[2 * c] = s1;
+    chan[2 * c + 1] = s2;
+  }
+  __syncthreads();
+  // per group: one warp per group, lane-strided sums then a fixed shuffle tree; publish this CTA's partial
+  {
+    const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < p.G; g += nwarps) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = g * p.cg + lane; c < (g + 1) * p.cg; c += 32) {
+        s1 += chan[2 * c];
+        s2 += chan[2 * c + 1];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) {
+        float* dst = p.partial + (((size_t)b * p.ctas_per_b + ci) * p.G + g) * 2;
+        dst[0] = s1;
+        dst[1] = s2;
+      }
+    }
+  }
+  // ---- grid barrier
+  __syncthreads();
+  gn_stamp(p, 2);
+  if (t == 0) {
+    __threadfence();
+    const unsigned int old = atomicAdd(p.bar, 1u);
+    if (old == gridDim.x - 1) {
+      atomicExch(p.bar, 0u);
+      __threadfence();
+      atomicAdd(p.bar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*reinterpret_cast<volatile unsigned int*>(p.bar + 1) == s_gen) {
+        if (clock64() - t0 > 4000000000LL) __trap();  // a scheduling bug must surface as an error, never a hang
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  gn_stamp(p, 3);
+  // ---- phase 2: final statistics and normalisation.  One warp per group: lane i sums partials i, i + 32, ... in
+  // order, then a fixed xor-shuffle tree — the same summation order on every CTA and every run.
+  {
+    const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < p.G; g += nwarps) {
+      float s1 = 0.f, s2 = 0.f;
+      const float* src = p.partial + ((size_t)b * p.ctas_per_b * p.G + g) * 2;
+      for (int i = lane; i < p.ctas_per_b; i += 32) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(src + (size_t)i * p.G * 2));
+        s1 += v.x;
+        s2 += v.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0) {
+        const float inv_n = 1.0f / ((float)p.cg * (float)p.HW);
+        const float m1 = s1 * inv_n, m2 = s2 * inv_n;
+        gstat[2 * g] = gn_shift(p, b, g) + m1;
+        gstat[2 * g + 1] = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + p.eps);
+      }
+    }
+  }
+  __syncthreads();
+  gn_stamp(p, 4);
+  if (!active) return;
+  float sc[8], sh[8];
+  {
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + c0));
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(p.beta + c0));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4));
+    const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / p.cg;
-      if (g != g_prev) {
-        const float k = gn_shift(p, b, g);
-        const float s1 = __ldg(&p.stats[((int64_t)b * p.G + g) * 2 + 0]) * inv_n;
-        const float s2 = __ldg(&p.stats[((int64_t)b * p.G + g) * 2 + 1]) * inv_n;
-        mean = k + s1;
-        rstd = rsqrtf(fmaxf(s2 - s1 * s1, 0.f) + p.eps);
-        g_prev = g;
-      }
-      float v = (xv[j] - mean) * rstd * __ldg(p.gamma + c0 + j) + __ldg(p.beta + c0 + j);
-      if (p.silu) v = silu_f(v);
-      o[j] = v;
+      const float mean = gstat[2 * gj[j]], rstd = gstat[2 * gj[j] + 1];
+      sc[j] = rstd * gam[j];
+      sh[j] = bet[j] - mean * sc[j];
+    }
+  }
+  for (int pix = pix0 + pl; pix < pix1; pix += p.k) {
+    const uint4 q = p.cache ? slice[(size_t)(pix - pix0) * p.NV + cv]
+                            : __ldg(reinterpret_cast<const uint4*>(gn_src(p, b, pix, c0)));
+    const __half2* hp = reinterpret_cast<const __half2*>(&q);
+    float o[8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float2 f = __half22float2(hp[u]);
+      o[2 * u] = fmaf(f.x, sc[2 * u], sh[2 * u]);
+      o[2 * u + 1] = fmaf(f.y, sc[2 * u + 1], sh[2 * u + 1]);
+    }
+    if (p.silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = silu_fast(o[j]);
     }
     uint4 w;
     w.x = pack_half2(o[0], o[1]);
@@ -141,6 +242,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GNParams p) {
     w.w = pack_half2(o[6], o[7]);
     *reinterpret_cast<uint4*>(p.y + ((int64_t)b * p.HW + pix) * p.C + c0) = w;
   }
+  gn_stamp(p, 5);
 }
 
 // One warp per row; the row lives in registers (C <= 2048).
@@ -304,8 +406,8 @@ extern "C" int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x
   GN_CHECK_ARG(h, (C0 % 8) == 0 && (C1 % 8) == 0 && (C % groups) == 0, "gn_group_norm: C0=%d C1=%d groups=%d", C0, C1,
                groups);
   GN_CHECK_ARG(h, stats_in == nullptr, "gn_group_norm: stats_in is not supported by this build");
-  GN_CHECK_ARG(h, h->stats_scratch && (int64_t)B * groups * 2 * 4 <= h->stats_scratch_bytes,
-               "gn_group_norm: B*groups too large for the statistics scratch");
+  GN_CHECK_ARG(h, C / 8 <= 1024, "gn_group_norm: C=%d too large", C);
+  GN_CHECK_ARG(h, B <= h->num_sms, "gn_group_norm: B=%d exceeds the SM count (grid barrier needs co-resident CTAs)", B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfScope prof(h, stream, GN_PROF_NORM, 0.0, 4.0 * B * HW * C);
   GNParams p;
@@ -318,31 +420,40 @@ extern "C" int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x
   p.HW = HW;
   p.G = groups;
   p.cg = C / groups;
+  p.NV = C / 8;
   p.eps = eps;
   p.gamma = gamma;
   p.beta = beta;
   p.silu = silu;
-  p.stats = static_cast<float*>(h->stats_scratch);
   p.y = static_cast<__half*>(y);
-  GN_CHECK_CUDA(h, cudaMemsetAsync(p.stats, 0, (size_t)B * groups * 2 * sizeof(float), st));
-  const int NV = C / 8;
-  int bdx = NV < 256 ? NV : 256;
-  if (bdx > 32) bdx = (bdx / 32) * 32;  // whole warps along x when possible
-  int bdy = 256 / bdx;
-  if (bdy < 1) bdy = 1;
-  int target_blocks = (2 * h->num_sms + B - 1) / B;
-  int pix = (HW + target_blocks - 1) / target_blocks;
-  if (pix < bdy) pix = bdy;
-  p.pix_per_block = pix;
-  dim3 grid((HW + pix - 1) / pix, B);
-  dim3 block(bdx, bdy);
-  gn_stats_kernel<<<grid, block, 0, st>>>(p);
-  GN_CHECK_LAUNCH(h);
-  const int64_t total = (int64_t)B * HW * NV;
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)h->num_sms * 8;
-  if (blocks > cap) blocks = cap;
-  gn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+  p.bar = static_cast<unsigned int*>(h->stats_scratch);
+  p.trace = static_cast<unsigned long long*>(h->gemm_trace);
+  p.partial = reinterpret_cast<float*>(static_cast<uint8_t*>(h->stats_scratch) + 256);
+  // CTAs per image: enough bytes per CTA to amortise the barrier, never more than one CTA per SM in total
+  const int64_t vectors = (int64_t)HW * (C / 8);
+  int ctas = (int)((vectors + 1535) / 1536);  // ~1.5 sixteen-byte vectors per thread before the grid is capped
+  const int max_ctas = h->num_sms / B;
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas > HW) ctas = HW;
+  if (ctas < 1) ctas = 1;
+  p.pix_per_cta = (HW + ctas - 1) / ctas;
+  p.ctas_per_b = (HW + p.pix_per_cta - 1) / p.pix_per_cta;
+  p.k = 1024 / p.NV;
+  if (p.k > p.pix_per_cta) p.k = p.pix_per_cta;
+  if (p.k < 1) p.k = 1;
+  const int T = p.NV * p.k;
+  const int threads = (T + 31) / 32 * 32;
+  GN_CHECK_ARG(h, (int64_t)B * p.ctas_per_b * groups * 8 + 256 <= h->stats_scratch_bytes,
+               "gn_group_norm: statistics scratch too small");
+  const size_t fixed = (size_t)T * 16 * 4 + (size_t)C * 2 * 4 + (size_t)((groups * 2 + 3) & ~3) * 4;
+  const size_t slice = (size_t)p.pix_per_cta * p.NV * 16;
+  p.cache = (fixed + slice <= 200 * 1024) ? 1 : 0;
+  const size_t smem = fixed + (p.cache ? slice : 0);
+  if (!h->gn_attr_set) {
+    GN_CHECK_CUDA(h, cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    h->gn_attr_set = true;
+  }
+  gn_fused_kernel<<<B * p.ctas_per_b, threads, smem, st>>>(p);
   GN_CHECK_LAUNCH(h);
   return GN_OK;
 }

@@ -39,9 +39,9 @@ def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
 
 
 class Ops:
-    """One instance per device; owns the gn_handle and the split-K workspace."""
+    """One instance per device; owns the gn_handle and the scratch workspace (L2-flush buffer of the autotuner)."""
 
-    def __init__(self, device: int = 0, workspace_mb: int = 64):
+    def __init__(self, device: int = 0, workspace_mb: int = 160, autotune: bool = True):
         if not torch.cuda.is_available():
             raise _cabi.GenimaB200Error("CUDA is not available: genima_b200 has no CPU fallback")
         self.device = torch.device("cuda", device)
@@ -52,6 +52,8 @@ class Ops:
         self.workspace = torch.empty(workspace_mb * 1024 * 1024 // 4, dtype=torch.float32, device=self.device)
         self.handle.check(self.lib.gn_set_workspace(self.h, self.workspace.data_ptr(), self.workspace.numel() * 4),
                           "gn_set_workspace")
+        # tile configurations are measured once per problem shape (first eager call) and cached in the handle
+        self.handle.check(self.lib.gn_set_autotune(self.h, 1 if autotune else 0), "gn_set_autotune")
 
     # ------------------------------------------------------------------------------------------------ helpers
     @staticmethod

@@ -67,10 +67,19 @@ int gn_create(int device, gn_handle** out);
 int gn_destroy(gn_handle* h);
 const char* gn_last_error(const gn_handle* h);
 const char* gn_version(void);
-/* Scratch arena for split-K partial sums (caller-owned fp32 device buffer). */
+/* Caller-owned device scratch (>= 140 MiB to enable L2-cold timing in the autotuner: it is overwritten to evict the
+ * L2 before weight-heavy candidates are timed).  Split-K needs no workspace: partial sums are reduced through
+ * distributed shared memory inside a thread-block cluster. */
 int gn_set_workspace(gn_handle* h, void* dptr, int64_t bytes);
 /* Force tile width / split count of the next GEMM-class calls (0 = heuristic); used by tests and tuning. */
 int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits);
+/* enable = 1: the first call of gn_linear / gn_conv2d for a new problem shape times the tile-configuration candidates of
+ * the cost model (CUDA events on the caller's stream, a few extra launches writing the same output) and caches the
+ * fastest; later calls, and calls made while the stream is being captured into a CUDA graph, use the cache.
+ * enable = 0 keeps the pure model; enable = -1 also clears the cache. */
+int gn_set_autotune(gn_handle* h, int enable);
+/* Force the operand-ring sizing of the next GEMM-class calls for 1 or 2 resident CTAs per SM (0 = heuristic). */
+int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm);
 /* Debug aid: when dptr (device uint64[8]) is non-NULL, CTA (0,0,0) of every following GEMM-class launch writes
  * %globaltimer stamps of its phases: 0 start, 1 set-up done, 2 first TMA issued, 3 first operands landed, 4 all MMAs
  * issued, 5 accumulator complete, 6 epilogue done, 7 exit.  NULL switches it off. */

@@ -1,0 +1,60 @@
+"""In-situ (warm, CUDA-graph replay) per-kernel durations of the agent step through torch.profiler (CUPTI).
+Usage: python tools/profile_step.py [--eager] [--reps 5]  -> prints a table and writes gpurun_out/kineto_step.txt"""
+import argparse
+import collections
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from genima_b200 import distributed as gd  # noqa: E402
+from genima_b200.act_policy import DeviceACT  # noqa: E402
+from genima_b200.ops import Ops  # noqa: E402
+from genima_b200.pipeline import B200ControlNetPipeline  # noqa: E402
+from genima_b200.step import GenimaStep  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--eager", action="store_true")
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--out", default="gpurun_out/kineto_step.txt")
+args = ap.parse_args()
+ucfg, vcfg, acfg = bench.presets("sd-turbo")
+shapes = bench.model_shapes(ucfg, vcfg, acfg)
+dev = torch.device("cuda", 0)
+sds, arena = gd.broadcast_weights(shapes, bench.synth_all(shapes), device=dev)
+ops = Ops(0)
+pipe = B200ControlNetPipeline(ops, sds["unet"], sds["controlnet"], sds["vae"], None, ucfg, vcfg)
+act = DeviceACT(ops, sds["act"], acfg)
+step = GenimaStep(pipe, act, num_inference_steps=5, use_cuda_graph=not args.eager)
+views, qpos, task, ctx, lat = bench.make_inputs(ucfg, acfg)
+d = dict(views=views.permute(0, 2, 3, 1).contiguous()[None].to(dev), lat=lat.to(dev), qpos=qpos.to(dev),
+         task=task.to(dev), ctx=ctx.to(dev))
+for _ in range(3):
+    step(d["views"], d["lat"], d["qpos"], d["task"], prompt_embeds=d["ctx"])
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(args.reps):
+        step(d["views"], d["lat"], d["qpos"], d["task"], prompt_embeds=d["ctx"])
+    torch.cuda.synchronize()
+agg = collections.defaultdict(lambda: [0, 0.0])
+t_min, t_max = None, None
+for ev in prof.events():
+    if ev.device_type is not None and "cuda" in str(ev.device_type).lower():
+        name = ev.name.split("(")[0].replace("void ", "")
+        agg[name][0] += 1
+        agg[name][1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        tr = ev.time_range
+        t_min = tr.start if t_min is None else min(t_min, tr.start)
+        t_max = tr.end if t_max is None else max(t_max, tr.end)
+tot = sum(v[1] for v in agg.values())
+lines = [f"per step: kernel time {tot / args.reps / 1e3:.2f} ms over {sum(v[0] for v in agg.values()) // args.reps} kernels; "
+         f"span {(t_max - t_min) / args.reps / 1e3:.2f} ms ({'eager' if args.eager else 'CUDA graph replay'}, warm)"]
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    lines.append(f"{k[:60]:60s} n/step={v[0] // args.reps:5d} us/step={v[1] / args.reps:10.1f} share={v[1] / tot:.3f} avg={v[1] / v[0]:.2f}")
+print("\n".join(lines))
+os.makedirs(os.path.dirname(args.out), exist_ok=True)
+with open(args.out, "w") as f:
+    f.write("\n".join(lines) + "\n")
