@@ -332,9 +332,18 @@ def run_ours(args):
         eager = GenimaStep(pipe, act, num_inference_steps=args.denoise_steps, use_cuda_graph=False)
         eager(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx)
         torch.cuda.synchronize()
-        ops.profile_begin()
+        for o in pipe.all_ops():
+            o.profile_begin()
         eager(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx)
-        classes = ops.profile_end()
+        classes = None
+        for o in pipe.all_ops():           # the ControlNet encoder runs through its own handle / stream
+            part = o.profile_end()
+            if classes is None:
+                classes = part
+            else:
+                for k, v in part.items():
+                    for f in v:
+                        classes[k][f] += v[f]
         roofline = make_roofline(classes, ms / args.steps)
 
     cpu_baseline = None

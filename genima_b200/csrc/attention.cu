@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         }
       }
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);  // m_run = -inf -> 0
+      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);  // m_run = -inf -> 0
       const float moff = m_new * p.scale_log2;
       float lsum = 0.f;
       // pass 2: probabilities -> fp16 -> swizzled smem
@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float p0 = (c + j < nvalid) ? exp2f(fmaf(__uint_as_float(r[j]), p.scale_log2, -moff)) : 0.f;
-          float p1 = (c + j + 1 < nvalid) ? exp2f(fmaf(__uint_as_float(r[j + 1]), p.scale_log2, -moff)) : 0.f;
+          float p0 = (c + j < nvalid) ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -moff)) : 0.f;
+          float p1 = (c + j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2, -moff)) : 0.f;
           lsum += p0 + p1;
           pk[j >> 1] = pack_half2(p0, p1);
         }

@@ -44,6 +44,7 @@ struct gn_handle {
   int64_t stats_scratch_bytes = 0;
   bool attn_attr_set = false;
   bool gn_attr_set = false;
+  int gn_max_ctas = 0;  // 0: one CTA per SM
   // cuTensorMapEncodeTiled resolved at runtime through cudaGetDriverEntryPoint (the library must load on a
   // CPU-only box, so libcuda is never linked directly).
   void* encode_fn = nullptr;

@@ -321,7 +321,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + stages * A_STAGE_BYTES;
-  float* s_scale = reinterpret_cast<float*>(smem_b + stages * b_stage_bytes);
+  // the fp32 staging tile of the split-K cluster reduction aliases the operand ring and may be larger than it
+  int ring_bytes = stages * (A_STAGE_BYTES + b_stage_bytes);
+  if (p.splits > 1 && block_n * BLOCK_M * 4 > ring_bytes) ring_bytes = block_n * BLOCK_M * 4;
+  float* s_scale = reinterpret_cast<float*>(smem + ring_bytes);
   float* s_bias = s_scale + 256;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
   uint64_t* empty_bar = full_bar + stages;

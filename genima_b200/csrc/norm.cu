@@ -432,7 +432,9 @@ extern "C" int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x
   // CTAs per image: enough bytes per CTA to amortise the barrier, never more than one CTA per SM in total
   const int64_t vectors = (int64_t)HW * (C / 8);
   int ctas = (int)((vectors + 1535) / 1536);  // ~1.5 sixteen-byte vectors per thread before the grid is capped
-  const int max_ctas = h->num_sms / B;
+  const int sm_cap = (h->gn_max_ctas > 0 && h->gn_max_ctas < h->num_sms) ? h->gn_max_ctas : h->num_sms;
+  GN_CHECK_ARG(h, B <= sm_cap, "gn_group_norm: B=%d exceeds the CTA cap %d", B, sm_cap);
+  const int max_ctas = sm_cap / B;
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas > HW) ctas = HW;
   if (ctas < 1) ctas = 1;

@@ -102,6 +102,13 @@ class Ops:
     def launch_count(self) -> int:
         return self.handle.launch_count()
 
+    def num_sms(self) -> int:
+        return torch.cuda.get_device_properties(self.device).multi_processor_count
+
+    def set_gn_max_ctas(self, n: int) -> None:
+        """Cap the grid of the following gn_group_norm launches (0 = one CTA per SM)."""
+        self.handle.check(self.lib.gn_set_gn_max_ctas(self.h, int(n)), "gn_set_gn_max_ctas")
+
     PROF_CLASSES = ("linear", "conv", "attention", "attention_small", "norm", "elementwise")
 
     def profile_begin(self) -> None:

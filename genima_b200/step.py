@@ -61,9 +61,9 @@ class GenimaStep:
         if latents.dtype not in (torch.float16, torch.float32):
             raise TypeError("latents must be fp16 or fp32")
         if not self.use_cuda_graph:
-            l0 = ops.launch_count()
+            l0 = pipe.launch_count()
             a_hat, is_pad, gen_tile = self._chain(views_u8.contiguous(), latents.contiguous(), qpos, task_emb, kv, tk)
-            self.launches_per_step = ops.launch_count() - l0
+            self.launches_per_step = pipe.launch_count() - l0
             return dict(a_hat=a_hat, is_pad_hat=is_pad, tile_u8=gen_tile)
 
         key = (tuple(views_u8.shape), tuple(latents.shape), latents.dtype, id(kv), tensor_key(task_emb), self.n_steps)
@@ -79,11 +79,11 @@ class GenimaStep:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
-            l0 = ops.launch_count()
+            l0 = pipe.launch_count()
             with torch.cuda.graph(graph):
                 a_hat, is_pad, gen_tile = self._chain(st["views"], st["lat"], st["qpos"], st["task"], kv, tk)
             g = dict(graph=graph, st=st, a_hat=a_hat, is_pad=is_pad, tile=gen_tile, kv=kv,
-                     launches=ops.launch_count() - l0)
+                     launches=pipe.launch_count() - l0)
             if len(self._graphs) > 4:
                 self._graphs.clear()
             self._graphs[key] = g

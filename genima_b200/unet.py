@@ -329,13 +329,17 @@ class DeviceControlNet(_Encoder):
             e = conv(ops, e, act_pre="silu")
         return self.ce_out(ops, e)
 
-    def residuals(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk, unet_skips: List[torch.Tensor],
-                  unet_mid: torch.Tensor, conditioning_scale: float = 1.0):
-        """Returns (skips + down residuals, mid + mid residual): the zero-conv epilogues add the U-Net tensors, so the
-        `sample + residual` adds of UNet2DConditionModel.forward cost no extra pass."""
+    def encode(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk):
+        """conv_in(x) + cond_emb -> encoder copy -> (mid, [S0..S11]) BEFORE the zero-convs.  Independent of the U-Net's own
+        encoder, so the pipeline runs it on a second stream concurrently with DeviceUNet.encode."""
+        h = self.conv_in(self.ops, x, residual=cond_emb)
+        return self.run(h, temb, kv, tk)
+
+    def zero_convs(self, mid: torch.Tensor, skips: List[torch.Tensor], unet_skips: List[torch.Tensor],
+                   unet_mid: torch.Tensor, conditioning_scale: float = 1.0):
+        """Returns (U-Net skips + down residuals, U-Net mid + mid residual): the zero-conv epilogues add the U-Net tensors,
+        so the `sample + residual` adds of UNet2DConditionModel.forward cost no extra pass."""
         ops = self.ops
-        h = self.conv_in(ops, x, residual=cond_emb)
-        mid, skips = self.run(h, temb, kv, tk)
         out = []
         for s, w, b, us in zip(skips, self.zero_w, self.zero_b, unet_skips):
             B, H, W, C = s.shape
@@ -346,3 +350,9 @@ class DeviceControlNet(_Encoder):
         m = ops.linear(mid.reshape(B * H * W, C), self.mid_w, bias=self.mid_b,
                        residual=unet_mid.reshape(B * H * W, C), alpha=conditioning_scale)
         return out, m.reshape(B, H, W, C)
+
+    def residuals(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk, unet_skips: List[torch.Tensor],
+                  unet_mid: torch.Tensor, conditioning_scale: float = 1.0):
+        """encode + zero_convs on the current stream."""
+        mid, skips = self.encode(x, cond_emb, temb, kv, tk)
+        return self.zero_convs(mid, skips, unet_skips, unet_mid, conditioning_scale)

@@ -73,6 +73,10 @@ const char* gn_version(void);
 int gn_set_workspace(gn_handle* h, void* dptr, int64_t bytes);
 /* Force tile width / split count of the next GEMM-class calls (0 = heuristic); used by tests and tuning. */
 int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits);
+/* gn_group_norm synchronises its CTAs with a grid barrier, so all of them must be co-resident: the grid never exceeds
+ * the SM count.  When two streams may each run a gn_group_norm at the same time (each through its OWN handle), cap both
+ * at half the SMs with this call; 0 restores the default. */
+int gn_set_gn_max_ctas(gn_handle* h, int max_ctas);
 /* enable = 1: the first call of gn_linear / gn_conv2d for a new problem shape times the tile-configuration candidates of
  * the cost model (CUDA events on the caller's stream, a few extra launches writing the same output) and caches the
  * fastest; later calls, and calls made while the stream is being captured into a CUDA graph, use the cache.

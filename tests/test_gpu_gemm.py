@@ -125,3 +125,28 @@ def test_linear_strided_views(ops):
     ops.linear(big[:, K:2 * K], w.cuda(), out=outbuf[:, N:])
     report_close("linear strided", outbuf[:, N:], ops_ref.linear_ref(big[:, K:2 * K].cpu(), w))
     assert float(outbuf[:, :N].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 1280, 1280), (256, 1280, 5120), (300, 400, 2048)])
+def test_forced_tile_configurations_sweep(ops, M, N, K):
+    """Every (block_n, cluster split-K, CTAs/SM) combination the autotuner may pick must give the same result: covers the
+    operand-ring / fp32 staging-tile aliasing of the cluster reduction (block_n = 192 with a 2-stage ring)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = (torch.randn(M, K, generator=g)).to(torch.float16)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(torch.float16)
+    bias = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g).to(torch.float16)
+    ref = ops_ref.linear_ref(a, w, bias=bias, residual=res)
+    ad, wd, bd, rd = a.cuda(), w.cuda(), bias.cuda(), res.cuda()
+    try:
+        for bn in (256, 192, 160, 96, 48):
+            for sp in (1, 2, 5, 8):
+                for occ in (1, 2):
+                    ops.set_gemm_tuning(bn, sp)
+                    ops.lib.gn_set_gemm_occupancy(ops.h, occ)
+                    out = ops.linear(ad, wd, bias=bd, residual=rd)
+                    err = float((out.float().cpu() - ref).abs().max())
+                    assert err < 2e-2, f"bn={bn} splits={sp} occ={occ} cfg={ops.last_gemm_config()}: max abs err {err}"
+    finally:
+        ops.set_gemm_tuning(0, 0)
+        ops.lib.gn_set_gemm_occupancy(ops.h, 0)

@@ -304,23 +304,24 @@ def test_pipeline_tiny_vs_oracle(ops, n_steps):
 
 
 def test_pipeline_cuda_graph_matches_eager(ops):
+    """Same pipeline object (same handles, hence the same measured tile configurations): eager launches, CUDA-graph
+    capture and graph replay on new inputs must agree bit for bit — every kernel is deterministic, including GroupNorm
+    (fixed-order reductions) and split-K (cluster reduction in rank order)."""
     pipe, (_, _, _, ucfg, _) = _tiny_pipeline(ops)
-    gpipe, _ = _tiny_pipeline(ops, use_cuda_graph=True)
     x, ctx, cond = _unet_inputs(ucfg, 1, seed=12)
     lat = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(2))
     kw = dict(prompt_embeds=ctx.cuda().half(), num_inference_steps=3, guidance_scale=0.0, latents=lat, output_type="u8")
-    def same(x, y):
-        d = (x.int() - y.int()).abs()
-        return int(d.max()) <= 1 and float((d == 0).float().mean()) > 0.999
-
-    a = pipe(image=cond, **kw).images.cpu()
-    b = gpipe(image=cond, **kw).images.cpu()
-    assert same(a, b)
     cond2 = torch.flip(cond, dims=[1])
+    pipe.use_cuda_graph = False
+    a0 = pipe(image=cond, **kw).images.cpu()          # first eager call: sequential encoders (autotuning pass)
+    a = pipe(image=cond, **kw).images.cpu()           # second eager call: ControlNet || U-Net encoder on two streams
     a2 = pipe(image=cond2, **kw).images.cpu()
-    b2 = gpipe(image=cond2, **kw).images.cpu()       # replay of the captured graph on new inputs
-    assert same(a2, b2)
-    assert not same(a, a2)
+    pipe.use_cuda_graph = True
+    b = pipe(image=cond, **kw).images.cpu().clone()   # capture + first replay
+    b2 = pipe(image=cond2, **kw).images.cpu().clone()  # replay of the captured graph on new inputs
+    assert torch.equal(a0, a) and torch.equal(a, b)
+    assert torch.equal(a2, b2)
+    assert not torch.equal(a, a2)
 
 
 def test_pipeline_rejects_unimplemented(ops):

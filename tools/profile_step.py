@@ -54,6 +54,23 @@ lines = [f"per step: kernel time {tot / args.reps / 1e3:.2f} ms over {sum(v[0] f
          f"span {(t_max - t_min) / args.reps / 1e3:.2f} ms ({'eager' if args.eager else 'CUDA graph replay'}, warm)"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append(f"{k[:60]:60s} n/step={v[0] // args.reps:5d} us/step={v[1] / args.reps:10.1f} share={v[1] / tot:.3f} avg={v[1] / v[0]:.2f}")
+# per-grid breakdown of the GEMM kernel from the chrome trace (kineto records grid / block per kernel)
+import json, tempfile
+tmp = tempfile.mktemp(suffix=".json")
+prof.export_chrome_trace(tmp)
+with open(tmp) as f:
+    tr = json.load(f)
+g = collections.defaultdict(lambda: [0, 0.0])
+for ev in tr.get("traceEvents", []):
+    if ev.get("cat") == "kernel" and "gemm_tc" in ev.get("name", ""):
+        a = ev.get("args", {})
+        key = (tuple(a.get("grid", [])), a.get("shared memory", 0))
+        g[key][0] += 1
+        g[key][1] += ev.get("dur", 0.0)
+lines.append("--- gemm_tc_kernel by (grid, dynamic smem): n/step, us/step, avg us")
+for k, v in sorted(g.items(), key=lambda kv: -kv[1][1])[:45]:
+    lines.append(f"{str(k):40s} n={v[0] // args.reps:4d} us={v[1] / args.reps:9.1f} avg={v[1] / v[0]:7.2f}")
+os.remove(tmp)
 print("\n".join(lines))
 os.makedirs(os.path.dirname(args.out), exist_ok=True)
 with open(args.out, "w") as f:
