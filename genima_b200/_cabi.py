@@ -52,6 +52,7 @@ SIGNATURES = {
     "gn_version": (C.c_char_p, []),
     "gn_set_workspace": (_i, [_vp, _vp, _i64]),
     "gn_set_gemm_tuning": (_i, [_vp, _i, _i]),
+    "gn_set_pdl": (_i, [_vp, _i]),
     "gn_set_gn_max_ctas": (_i, [_vp, _i]),
     "gn_set_autotune": (_i, [_vp, _i]),
     "gn_set_gemm_occupancy": (_i, [_vp, _i]),

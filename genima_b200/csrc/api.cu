@@ -152,6 +152,12 @@ int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm) {
   return GN_OK;
 }
 
+int gn_set_pdl(gn_handle* h, int enable) {
+  if (!h) return GN_ERR_INVALID;
+  h->pdl = enable != 0;
+  return GN_OK;
+}
+
 int gn_set_gn_max_ctas(gn_handle* h, int max_ctas) {
   if (!h || max_ctas < 0) return GN_ERR_INVALID;
   h->gn_max_ctas = max_ctas;

@@ -80,6 +80,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // q / k / v come from the previous kernel in the stream
   const uint32_t tmem_s = tmem_base;        // 128 fp32 columns
   const uint32_t tmem_o = tmem_base + 128;  // 64 fp32 columns
 
@@ -240,6 +242,8 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const __half* __restric
                                                          const __half* __restrict__ v, int64_t ldv,
                                                          __half* __restrict__ out, int64_t ldo, int heads, int Tq,
                                                          int Tk, float scale, int causal) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int qi = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (qi >= Tq) return;
@@ -342,8 +346,9 @@ extern "C" int gn_attention(gn_handle* h, const void* q, int64_t ldq, const void
     h->attn_attr_set = true;
   }
   dim3 grid(ceil_div(Tq, AT_BQ), heads, B);
-  attn_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
-  GN_CHECK_LAUNCH(h);
+  GN_CHECK_CUDA(h, launch_ex(h, attn_tc_kernel, grid, dim3(AT_THREADS, 1, 1), AT_SMEM_BYTES,
+                              static_cast<cudaStream_t>(stream), 1, p));
+  h->launches++;
   return GN_OK;
 }
 
@@ -364,9 +369,11 @@ extern "C" int gn_attention_small(gn_handle* h, const void* q, int64_t ldq, cons
   const __half* vh = static_cast<const __half*>(v);
   __half* oh = static_cast<__half*>(out);
   if (head_dim == 32)
-    attn_small_kernel<32><<<grid, 128, 0, st>>>(qh, ldq, kh, ldk, vh, ldv, oh, ldo, heads, Tq, Tk, scale, causal);
+    GN_CHECK_CUDA(h, launch_ex(h, attn_small_kernel<32>, grid, dim3(128, 1, 1), 0, st, 1, qh, ldq, kh, ldk, vh, ldv, oh,
+                                ldo, heads, Tq, Tk, scale, causal));
   else
-    attn_small_kernel<64><<<grid, 128, 0, st>>>(qh, ldq, kh, ldk, vh, ldv, oh, ldo, heads, Tq, Tk, scale, causal);
-  GN_CHECK_LAUNCH(h);
+    GN_CHECK_CUDA(h, launch_ex(h, attn_small_kernel<64>, grid, dim3(128, 1, 1), 0, st, 1, qh, ldq, kh, ldk, vh, ldv, oh,
+                                ldo, heads, Tq, Tk, scale, causal));
+  h->launches++;
   return GN_OK;
 }

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <array>
+#include <utility>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -45,6 +46,7 @@ struct gn_handle {
   bool attn_attr_set = false;
   bool gn_attr_set = false;
   int gn_max_ctas = 0;  // 0: one CTA per SM
+  bool pdl = true;      // launch the main kernels with programmatic stream serialization (gn_set_pdl)
   // cuTensorMapEncodeTiled resolved at runtime through cudaGetDriverEntryPoint (the library must load on a
   // CPU-only box, so libcuda is never linked directly).
   void* encode_fn = nullptr;
@@ -111,6 +113,37 @@ struct ProfScope {
     if (idx >= 0) cudaEventRecord(h->prof[idx].b, st);
   }
 };
+
+// Launch through cudaLaunchKernelEx with the programmatic-dependent-launch attribute (when enabled on the handle) and an
+// optional thread-block cluster along grid.z.  Every kernel launched through this helper calls pdl_wait() before its
+// first global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(const gn_handle* h, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                             cudaStream_t stream, int cluster_z, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_z > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = cluster_z;
+    ++na;
+  }
+  if (h->pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }

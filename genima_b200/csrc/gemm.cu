@@ -344,17 +344,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
-  if (warp >= 2) {
-    // stage the tile's per-column scale / bias once (identity when absent) — read back as broadcast float4s
-    for (int i = threadIdx.x - 64; i < block_n; i += GEMM_THREADS - 64) {
-      const int n = n0 + i;
-      s_scale[i] = (p.epi.scale && n < p.epi.N) ? __ldg(p.epi.scale + n) : 1.0f;
-      s_bias[i] = (p.epi.bias && n < p.epi.N) ? __ldg(p.epi.bias + n) : 0.0f;
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // Everything above touched only this CTA's shared / tensor memory.  Let the next kernel's CTAs be scheduled, then wait
+  // for the previous kernel in the stream before the first global-memory access (programmatic dependent launch).
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace_stamp(p, 1);
 
@@ -448,6 +444,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       m = (gb * p.Ho + gy) * p.Wo + gx;
     }
     const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
+    // stage the tile's per-column scale / bias once (identity when absent) — read back as broadcast float4s
+    for (int i = threadIdx.x - 64; i < block_n; i += GEMM_THREADS - 64) {
+      const int n = n0 + i;
+      s_scale[i] = (p.epi.scale && n < p.epi.N) ? __ldg(p.epi.scale + n) : 1.0f;
+      s_bias[i] = (p.epi.bias && n < p.epi.N) ? __ldg(p.epi.bias + n) : 0.0f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // epilogue warps only
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) trace_stamp(p, 5);
@@ -660,20 +663,8 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
     h->gemm_attr_set = true;
   }
   dim3 grid(gn::ceil_div(N, tc.block_n), tiles_m, tc.splits);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;  // the K-splits of one output tile form a thread-block cluster
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = tc.splits;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  GN_CHECK_CUDA(h, cudaLaunchKernelEx(&cfg, gemm_tc_kernel, p));
+  // the K-splits of one output tile form a thread-block cluster (grid.z == cluster size)
+  GN_CHECK_CUDA(h, launch_ex(h, gemm_tc_kernel, grid, dim3(GEMM_THREADS, 1, 1), smem, stream, tc.splits, p));
   h->last_cfg[0] = tc.block_n;
   h->last_cfg[1] = tc.splits;
   h->last_cfg[2] = tc.stages;

@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(1024, 1) gn_fused_kernel(const GNParams p) {
   const int cv = active ? t % p.NV : 0;
   const int pl = active ? t / p.NV : 0;
   const int c0 = cv * 8;
+  pdl_trigger();
+  pdl_wait();  // x comes from the previous kernel; the barrier generation word may still be moving until it is done
   gn_stamp(p, 0);
   if (t == 0) s_gen = *reinterpret_cast<volatile unsigned int*>(p.bar + 1);
 
@@ -251,6 +253,8 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restric
                                                          float eps, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, __half* __restrict__ y,
                                                          int64_t ldy) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -455,8 +459,8 @@ extern "C" int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x
     GN_CHECK_CUDA(h, cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     h->gn_attr_set = true;
   }
-  gn_fused_kernel<<<B * p.ctas_per_b, threads, smem, st>>>(p);
-  GN_CHECK_LAUNCH(h);
+  GN_CHECK_CUDA(h, launch_ex(h, gn_fused_kernel, dim3(B * p.ctas_per_b, 1, 1), dim3(threads, 1, 1), smem, st, 1, p));
+  h->launches++;
   return GN_OK;
 }
 
@@ -468,9 +472,10 @@ extern "C" int gn_layer_norm(gn_handle* h, const void* x, int64_t ldx, int rows,
   GN_CHECK_ARG(h, (ldx % 8) == 0 && (ldy % 8) == 0, "gn_layer_norm: row strides must be multiples of 8");
   ProfScope prof(h, stream, GN_PROF_NORM, 0.0, 4.0 * rows * C);
   const int rows_per_block = 8;
-  layer_norm_kernel<<<(rows + rows_per_block - 1) / rows_per_block, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(x), ldx, rows, C, eps, gamma, beta, static_cast<__half*>(y), ldy);
-  GN_CHECK_LAUNCH(h);
+  GN_CHECK_CUDA(h, launch_ex(h, layer_norm_kernel, dim3((rows + rows_per_block - 1) / rows_per_block, 1, 1),
+                              dim3(256, 1, 1), 0, static_cast<cudaStream_t>(stream), 1, static_cast<const __half*>(x), ldx,
+                              rows, C, eps, gamma, beta, static_cast<__half*>(y), ldy));
+  h->launches++;
   return GN_OK;
 }
 

@@ -9,6 +9,7 @@ the row-major [B*H*W, C] matrix the GEMM kernels see.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -54,6 +55,8 @@ class Ops:
                           "gn_set_workspace")
         # tile configurations are measured once per problem shape (first eager call) and cached in the handle
         self.handle.check(self.lib.gn_set_autotune(self.h, 1 if autotune else 0), "gn_set_autotune")
+        if os.environ.get("GENIMA_B200_PDL", "1") == "0":   # A/B switch for programmatic dependent launch
+            self.handle.check(self.lib.gn_set_pdl(self.h, 0), "gn_set_pdl")
 
     # ------------------------------------------------------------------------------------------------ helpers
     @staticmethod

@@ -73,6 +73,11 @@ const char* gn_version(void);
 int gn_set_workspace(gn_handle* h, void* dptr, int64_t bytes);
 /* Force tile width / split count of the next GEMM-class calls (0 = heuristic); used by tests and tuning. */
 int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits);
+/* Programmatic dependent launch (default on): gn_linear / gn_conv2d / gn_attention* / gn_group_norm / gn_layer_norm are
+ * launched with cudaLaunchAttributeProgrammaticStreamSerialization and execute griddepcontrol.wait before their first
+ * global-memory access, so their set-up (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
+ * previous kernel in the stream, also inside a captured CUDA graph.  enable = 0 restores ordinary launches. */
+int gn_set_pdl(gn_handle* h, int enable);
 /* gn_group_norm synchronises its CTAs with a grid barrier, so all of them must be co-resident: the grid never exceeds
  * the SM count.  When two streams may each run a gn_group_norm at the same time (each through its OWN handle), cap both
  * at half the SMs with this call; 0 restores the default. */
