@@ -1,0 +1,40 @@
+"""Host logic of the episode-parallel replay harness (genima_b200/eval_replay.py) with a fake agent: episode structure
+follows controller/eval_genima.py (per-episode re-seed, advance by len(actions), stop past episode_length), and the
+union of all ranks' shards covers every (task, episode) exactly once."""
+import numpy as np
+
+from genima_b200 import distributed as gd
+from genima_b200.eval_replay import RLBENCH_25, StubEnv, run_units, summarize
+
+
+def test_episode_loop_structure():
+    seeds, calls = [], []
+
+    def fake_agent(views, qpos, k):
+        assert views.shape == (4, 256, 256, 3) and views.dtype == np.uint8 and qpos.shape == (1, 8)
+        calls.append(k)
+        return np.zeros((20, 8), dtype=np.float32)
+
+    recs = run_units([("open_box", 0), ("open_box", 1)], fake_agent, episode_length=200, reseed=seeds.append)
+    assert seeds == [2, 2]                                # diffusion_seed re-applied per episode (eval_genima.py:129-135)
+    # 20 sim steps per agent step, terminate once t > 200 -> 11 agent steps (eval_genima.py:261-275)
+    assert [r["agent_steps"] for r in recs] == [11, 11] and recs[0]["sim_steps"] == 220
+    assert calls == list(range(11)) * 2
+
+
+def test_stub_env_is_deterministic_per_unit():
+    a, b = StubEnv("t", 3, size=64).observe(), StubEnv("t", 3, size=64).observe()
+    c = StubEnv("t", 4, size=64).observe()
+    assert np.array_equal(a[0], b[0]) and not np.array_equal(a[0], c[0])
+
+
+def test_shards_cover_config5_exactly_once():
+    world = 8
+    seen = []
+    for r in range(world):
+        seen += gd.shard_units(RLBENCH_25, 25, r, world)
+    assert len(seen) == 625 and len(set(seen)) == 625      # 25 tasks x 25 episodes (BASELINE configs[4])
+    sizes = [len(gd.shard_units(RLBENCH_25, 25, r, world)) for r in range(world)]
+    assert max(sizes) - min(sizes) <= 1
+    s = summarize([{"agent_steps": 11, "mean_step_time": 0.03}] * 4, wall_s=2.0, world=2)
+    assert s["agent_steps"] == 44 and s["agent_steps_per_sec"] == 22.0

@@ -1,4 +1,5 @@
-"""Runs one gn_linear / gn_conv2d problem a few times (for `ncu --set full -k regex:gemm_tc`).
+"""Runs one op a few times; the LAST call sits between cudaProfilerStart/Stop so that
+`ncu --profile-from-start off --set full ...` captures the tuned configuration, not an autotuning candidate.
 Usage: python tools/one_gemm.py linear M N K [geglu|fp32out|bias_res|plain]   |   conv B H Cin Cout [stride]"""
 import os
 import sys
@@ -25,15 +26,31 @@ if kind == "linear":
         kw = dict(out_fp32=True)
     elif mode == "bias_res":
         kw = dict(bias=b, residual=torch.randn(M, N, device="cuda").half())
-    for _ in range(5):
-        out = ops.linear(a, w, **kw)
+    fn = lambda: ops.linear(a, w, **kw)
+elif kind == "attn":
+    tq, tk, heads = (int(v) for v in sys.argv[2:5])
+    c = heads * 64
+    q = torch.randn(tq, c, device="cuda").half()
+    k = torch.randn(tk, c, device="cuda").half()
+    v = torch.randn(tk, c, device="cuda").half()
+    fn = lambda: ops.attention(q, k, v, 1, heads, tq, tk, 0.125)
+elif kind == "gn":
+    hw, c = int(sys.argv[2]), int(sys.argv[3])
+    x = torch.randn(1, hw, hw, c, device="cuda").half()
+    g, b = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    fn = lambda: ops.group_norm(x, g, b, 32, 1e-5, silu=True)
 else:
     B, H, Cin, Cout = (int(v) for v in sys.argv[2:6])
     s = int(sys.argv[6]) if len(sys.argv) > 6 else 1
     x = torch.randn(B, H, H, Cin, device="cuda").half()
     wp = pack_conv_weight((torch.randn(Cout, Cin, 3, 3) * (Cin * 9) ** -0.5).half()).cuda()
     bias = torch.randn(Cout, device="cuda")
-    for _ in range(5):
-        out = ops.conv2d(x, wp, Cout, stride=s, bias=bias)
+    fn = lambda: ops.conv2d(x, wp, Cout, stride=s, bias=bias)
+for _ in range(4):
+    out = fn()
 torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStart()
+out = fn()
+torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 print(ops.last_gemm_config(), float(out.float().abs().mean()))
