@@ -37,8 +37,12 @@ class GnEpilogue(C.Structure):
         ("beta", C.c_float),
         ("geglu", C.c_int32),
         ("out_fp32", C.c_int32),
-        ("gn_stats", C.c_void_p),
-        ("gn_groups", C.c_int32),
+        ("ln_stats", C.c_void_p),
+        ("ln_colsum", C.c_void_p),
+        ("ln_parts", C.c_int32),
+        ("ln_eps", C.c_float),
+        ("rowstats_out", C.c_void_p),
+        ("rowstats_capacity", C.c_int32),
         ("reserved", C.c_int32),
     ]
 
@@ -58,6 +62,7 @@ SIGNATURES = {
     "gn_set_gemm_occupancy": (_i, [_vp, _i]),
     "gn_set_gemm_trace": (_i, [_vp, _vp]),
     "gn_get_last_gemm_config": (_i, [_vp, C.POINTER(C.c_int32)]),
+    "gn_get_last_rowstats_parts": (_i, [_vp]),
     "gn_launch_count": (_i64, [_vp]),
     "gn_profile_begin": (_i, [_vp]),
     "gn_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),

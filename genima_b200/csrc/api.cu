@@ -183,6 +183,8 @@ int gn_get_last_gemm_config(const gn_handle* h, int32_t* out4) {
   return GN_OK;
 }
 
+int gn_get_last_rowstats_parts(const gn_handle* h) { return h ? h->last_rowstats_parts : -1; }
+
 int64_t gn_launch_count(const gn_handle* h) { return h ? h->launches : -1; }
 
 int gn_profile_begin(gn_handle* h) {

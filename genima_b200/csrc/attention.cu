@@ -1,13 +1,18 @@
 // Attention kernels.
 //
 // attn_tc_kernel — tcgen05 flash attention, head_dim 64, fp16, one CTA per (128 queries, head, batch):
-//   warp 0      TMA producer: Q tile once, K tiles (2-stage ring) and V tile (1 stage) per 128-key block
-//   warp 1      single-thread MMA issuer:  S = Q K^T  (M128 N128 K64, K-major A/B)  -> TMEM cols [0,128)
-//                                          O_blk = P V (M128 N64 K128, A = P from smem, B = V MN-major) -> TMEM [128,192)
-//   warps 2-5   online softmax: thread r owns query row r (TMEM lane r): tcgen05.ld S, running max / sum in fp32,
-//               exp2 with the softmax scale folded into one FFMA, P written to shared memory as fp16 in the
-//               SWIZZLE_128B K-major layout the MMA expects, O accumulated in registers with the usual rescale.
-// Two CTAs fit per SM (96 KiB smem, 256 TMEM columns each) so one CTA's MMAs overlap the other's softmax.
+//   warp 0      TMA producer: Q tile once, K and V tiles through 2-stage rings, one 128-key block per stage
+//   warp 1      single-thread MMA issuer:  S_b = Q K^T  (M128 N128 K64, K-major A/B)  -> TMEM S buffers b = 0, 1
+//                                          O += P V     (M128 N64 K128, A = P from smem, B = V MN-major) -> TMEM O
+//               QK^T of block i+1 is issued BEFORE P V of block i, so the tensor core computes the next scores while
+//               the softmax warps are still working on the current ones (S is double-buffered in TMEM)
+//   warps 2-9   online softmax, two warps per TMEM lane quadrant: thread (row r, half h) owns 64 of the 128 scores of
+//               query row r; the halves exchange their row maxima through shared memory.  O stays in TMEM and is
+//               rescaled only when the running maximum grew by more than 2^8 since the last rescale (the stale
+//               maximum is used consistently for P and the row sum, so the result is exact); exponentials are single
+//               ex2.approx instructions with the softmax scale folded into one FFMA; P goes to shared memory as fp16 in
+//               the SWIZZLE_128B K-major layout the MMA expects.
+// Shared memory 112 KiB + TMEM 512 columns: one CTA per SM.
 //
 // attn_small_kernel — SIMT attention for tiny problems (ACT transformer, CLIP text towers): one warp per query.
 #include "common.h"
@@ -20,10 +25,13 @@ constexpr int AT_BKV = 128;
 constexpr int AT_D = 64;
 constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KiB: Q, K and V tiles
 constexpr int AT_P_BYTES = 128 * 128 * 2;    // 32 KiB
-constexpr int AT_KSTAGES = 2;
-constexpr int AT_THREADS = 192;
-constexpr int AT_TMEM_COLS = 256;
-constexpr int AT_SMEM_BYTES = AT_TILE_BYTES /*Q*/ + AT_P_BYTES + AT_KSTAGES * AT_TILE_BYTES + AT_TILE_BYTES /*V*/ + 256 + 1024;
+constexpr int AT_STAGES = 2;
+constexpr int AT_SM_WARPS = 8;
+constexpr int AT_THREADS = 64 + 32 * AT_SM_WARPS;
+constexpr int AT_TMEM_COLS = 512;
+constexpr int AT_SMEM_BYTES =
+    AT_TILE_BYTES /*Q*/ + AT_P_BYTES + 2 * AT_STAGES * AT_TILE_BYTES /*K, V*/ + 4 * 128 * 4 /*row exchange*/ + 256 + 1024;
+constexpr float AT_RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
@@ -33,24 +41,30 @@ struct AttnParams {
   float scale_log2;  // softmax scale * log2(e)
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+__device__ __forceinline__ void at_bar_sync_softmax() {
+  asm volatile("bar.sync 2, %0;" ::"n"(32 * AT_SM_WARPS) : "memory");
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sP = sQ + AT_TILE_BYTES;
   uint8_t* sK = sP + AT_P_BYTES;
-  uint8_t* sV = sK + AT_KSTAGES * AT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_TILE_BYTES);
+  uint8_t* sV = sK + AT_STAGES * AT_TILE_BYTES;
+  float* s_xchg = reinterpret_cast<float*>(sV + AT_STAGES * AT_TILE_BYTES);  // [2 parities][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_xchg + 4 * 128);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 6;
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* o_full = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* s_free = bars + 11;   // [2]
+  uint64_t* p_full = bars + 13;
+  uint64_t* pv_done = bars + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -64,15 +78,16 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < AT_KSTAGES; ++s) {
+    for (int s = 0; s < AT_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_free[s], 32 * AT_SM_WARPS);
     }
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(p_full, 32 * AT_SM_WARPS);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, AT_TMEM_COLS);
@@ -82,8 +97,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
   pdl_wait();  // q / k / v come from the previous kernel in the stream
-  const uint32_t tmem_s = tmem_base;        // 128 fp32 columns
-  const uint32_t tmem_o = tmem_base + 128;  // 64 fp32 columns
+  const uint32_t tmem_o = tmem_base + 256;  // 64 fp32 columns; S buffers: tmem_base + 0 and + 128
 
   if (warp == 0) {
     if (lane == 0) {
@@ -91,13 +105,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
       mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
       tma_load_2d(sQ, &p.tmQ, q_full, head * AT_D, batch * p.Tq + q0);
       for (int i = 0; i < nblk; ++i) {
-        const int ks = i % AT_KSTAGES;
-        mbar_wait(&k_empty[ks], ((i / AT_KSTAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[ks], AT_TILE_BYTES);
-        tma_load_2d(sK + ks * AT_TILE_BYTES, &p.tmK, &k_full[ks], head * AT_D, batch * p.Tk + i * AT_BKV);
-        mbar_wait(v_empty, (i & 1) ^ 1);
-        mbar_arrive_expect_tx(v_full, AT_TILE_BYTES);
-        tma_load_2d(sV, &p.tmV, v_full, head * AT_D, batch * p.Tk + i * AT_BKV);
+        const int st = i & 1;
+        const uint32_t ph = ((i >> 1) & 1) ^ 1;
+        mbar_wait(&k_empty[st], ph);
+        mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
+        tma_load_2d(sK + st * AT_TILE_BYTES, &p.tmK, &k_full[st], head * AT_D, batch * p.Tk + i * AT_BKV);
+        mbar_wait(&v_empty[st], ph);
+        mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
+        tma_load_2d(sV + st * AT_TILE_BYTES, &p.tmV, &v_full[st], head * AT_D, batch * p.Tk + i * AT_BKV);
       }
     }
   } else if (warp == 1) {
@@ -106,123 +121,142 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_kernel(const __grid_con
       const uint32_t idesc_qk = umma_idesc_f16(AT_BKV, 0, 0);  // N = 128 keys, both operands K-major
       const uint32_t idesc_pv = umma_idesc_f16(AT_D, 0, 1);    // N = 64 dims, B (= V) MN-major
       const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ), 1024, 0);
-      auto issue_qk = [&](int i) {
-        const int ks = i % AT_KSTAGES;
-        mbar_wait(&k_full[ks], (i / AT_KSTAGES) & 1);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        if (j >= 2) mbar_wait(&s_free[st], ((j >> 1) - 1) & 1);  // softmax of block j-2 has read this S buffer
         tc_fence_after();
-        const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + ks * AT_TILE_BYTES), 1024, 0);
+        const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + st * AT_TILE_BYTES), 1024, 0);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k) umma_f16_ss(tmem_s, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0);
-        umma_commit(s_full);
-        umma_commit(&k_empty[ks]);
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_f16_ss(tmem_base + st * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0);
+        umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);
       };
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int i = 0; i < nblk; ++i) {
+        if (i + 1 < nblk) issue_qk(i + 1);  // next scores while the softmax warps work on block i
+        const int st = i & 1;
         mbar_wait(p_full, i & 1);
-        mbar_wait(v_full, i & 1);
+        mbar_wait(&v_full[st], (i >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < AT_BKV / 16; ++j) {
           // A: P[128 rows][16 k] slice j: 64-column sub-tile j/4, 32-byte step j%4 inside the swizzle row
           const uint64_t a_desc = umma_desc_sw128(smem_u32(sP + (j >> 2) * AT_TILE_BYTES), 1024, 0) + 2 * (j & 3);
           // B: V rows [16 j, 16 j + 16) x 64 dims, MN-major: two 8-row swizzle atoms 1024 B apart
-          const uint64_t b_desc = umma_desc_sw128(smem_u32(sV + j * 2048), 1024, 1024);
-          umma_f16_ss(tmem_o, a_desc, b_desc, idesc_pv, j > 0);
+          const uint64_t b_desc = umma_desc_sw128(smem_u32(sV + st * AT_TILE_BYTES + j * 2048), 1024, 1024);
+          umma_f16_ss(tmem_o, a_desc, b_desc, idesc_pv, (i > 0 || j > 0) ? 1u : 0u);
         }
-        umma_commit(o_full);
-        umma_commit(v_empty);
-        if (i + 1 < nblk) issue_qk(i + 1);
+        umma_commit(pv_done);
+        umma_commit(&v_empty[st]);
       }
     }
   } else {
-    // ------------------------------------------------------------------ softmax / output warps (2..5)
-    const int qd = warp & 3;
+    // ------------------------------------------------------------------ softmax / output warps (2..9)
+    const int qd = warp & 3;          // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;  // which 64 of the 128 scores of the row
     const int row = qd * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
-    float m_run = -INFINITY;  // running max of raw scores
-    float l_run = 0.f;
-    float o_acc[AT_D];
-#pragma unroll
-    for (int j = 0; j < AT_D; ++j) o_acc[j] = 0.f;
-    const uint32_t p_row = smem_u32(sP) + row * 128;
+    float m_used = -INFINITY;  // maximum the stored P / l / O are currently scaled with (raw score units)
+    float l_run = 0.f;         // this half's share of the row sum
+    const uint32_t p_row = smem_u32(sP) + half * AT_TILE_BYTES + row * 128;
     const uint32_t swz = static_cast<uint32_t>(row & 7);
+    const float c = p.scale_log2;
 
     for (int i = 0; i < nblk; ++i) {
-      mbar_wait(s_full, i & 1);
+      const int st = i & 1;
+      mbar_wait(&s_full[st], (i >> 1) & 1);
       tc_fence_after();
-      const int kv0 = i * AT_BKV;
-      const int nvalid = p.Tk - kv0;  // >= 1
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < AT_BKV; c += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(tmem_s + lane_sel + c, r);
+      uint32_t r[64];
+      {
+        uint32_t lo[32], hi[32];
+        const uint32_t ta = tmem_base + st * 128 + lane_sel + half * 64;
+        tmem_ld_x32(ta, lo);
+        tmem_ld_x32(ta + 32, hi);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float s = (c + j < nvalid) ? __uint_as_float(r[j]) : -INFINITY;
-          mx = fmaxf(mx, s);
+          r[j] = lo[j];
+          r[32 + j] = hi[j];
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2_approx((m_run - m_new) * p.scale_log2);  // m_run = -inf -> 0
-      const float moff = m_new * p.scale_log2;
+      tc_fence_before();
+      mbar_arrive(&s_free[st]);  // the scores are in registers: QK^T of block i+2 may overwrite this buffer
+      const int nvalid = p.Tk - i * AT_BKV - half * 64;  // valid columns of this half (may be <= 0)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const float sv = (j < nvalid) ? __uint_as_float(r[j]) : -INFINITY;
+        r[j] = __float_as_uint(sv);
+        mx = fmaxf(mx, sv);
+      }
+      float* xc = s_xchg + (i & 1) * 256;  // double-buffered: the barrier of block i+1 separates reuse from this read
+      xc[half * 128 + row] = mx;
+      at_bar_sync_softmax();
+      const float m_blk = fmaxf(mx, xc[(half ^ 1) * 128 + row]);
+      const float m_new = fmaxf(m_used, m_blk);
+      if (i > 0) mbar_wait(pv_done, (i - 1) & 1);  // P V of block i-1 finished: P may be rewritten, O may be rescaled
+      // lazy rescale, warp-uniform (tcgen05.ld/st are warp-collective); both halves of a row see the same values
+      if (__any_sync(0xffffffffu, (m_new - m_used) * c > AT_RESCALE_LOG2)) {
+        const float alpha = ex2_approx((m_used - m_new) * c);  // m_used = -inf -> 0
+        if (i > 0) {
+          tc_fence_after();
+          uint32_t o[32];
+          tmem_ld_x32(tmem_o + lane_sel + half * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+          tmem_st_x32(tmem_o + lane_sel + half * 32, o);
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        l_run *= alpha;
+        m_used = m_new;
+      }
+      const float moff = m_used * c;
       float lsum = 0.f;
-      // pass 2: probabilities -> fp16 -> swizzled smem
-#pragma unroll 1
-      for (int c = 0; c < AT_BKV; c += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(tmem_s + lane_sel + c, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float p0 = (c + j < nvalid) ? ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -moff)) : 0.f;
-          float p1 = (c + j + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2, -moff)) : 0.f;
+      for (int t = 0; t < 8; ++t) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[8 * t + 2 * u]), c, -moff));      // -inf -> 0
+          const float p1 = ex2_approx(fmaf(__uint_as_float(r[8 * t + 2 * u + 1]), c, -moff));
           lsum += p0 + p1;
-          pk[j >> 1] = pack_half2(p0, p1);
+          pk[u] = pack_half2(p0, p1);
         }
-        // 32 columns = 4 chunks of 16 bytes inside sub-tile (c / 64), chunk index ((c % 64) / 8 + t) ^ (row & 7)
-        const uint32_t sub = p_row + (c >> 6) * AT_TILE_BYTES;
-        const uint32_t chunk0 = (c & 63) >> 3;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint32_t addr = sub + (((chunk0 + t) ^ swz) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * t]), "r"(pk[4 * t + 1]),
-                       "r"(pk[4 * t + 2]), "r"(pk[4 * t + 3])
-                       : "memory");
-        }
+        const uint32_t addr = p_row + ((static_cast<uint32_t>(t) ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                     "r"(pk[3])
+                     : "memory");
       }
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
+      l_run += lsum;
       fence_proxy_async_smem();  // P (generic-proxy writes) must be visible to the tensor core (async proxy)
-      tc_fence_before();         // our tcgen05.ld of S precede the MMA that overwrites S
       mbar_arrive(p_full);
-
-      mbar_wait(o_full, i & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < AT_D; c += 32) {
-        uint32_t r[32];
-        tmem_ld_x32(tmem_o + lane_sel + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o_acc[c + j] = fmaf(o_acc[c + j], alpha, __uint_as_float(r[j]));
-      }
     }
+    // ---- output: O / l
+    float* xl = s_xchg + (nblk & 1) * 256;
+    xl[half * 128 + row] = l_run;
+    at_bar_sync_softmax();
+    const float l_tot = l_run + xl[(half ^ 1) * 128 + row];
+    mbar_wait(pv_done, (nblk - 1) & 1);
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld_x32(tmem_o + lane_sel + half * 32, o);
+    tmem_ld_wait();
     tc_fence_before();
     if (q0 + row < p.Tq) {
-      const float inv = 1.0f / l_run;
-      __half* op = p.out + ((int64_t)batch * p.Tq + q0 + row) * p.ldo + head * AT_D;
+      const float inv = 1.0f / l_tot;
+      __half* op = p.out + ((int64_t)batch * p.Tq + q0 + row) * p.ldo + head * AT_D + half * 32;
 #pragma unroll
-      for (int j = 0; j < AT_D; j += 8) {
+      for (int j = 0; j < 32; j += 8) {
         uint4 w;
-        w.x = pack_half2(o_acc[j] * inv, o_acc[j + 1] * inv);
-        w.y = pack_half2(o_acc[j + 2] * inv, o_acc[j + 3] * inv);
-        w.z = pack_half2(o_acc[j + 4] * inv, o_acc[j + 5] * inv);
-        w.w = pack_half2(o_acc[j + 6] * inv, o_acc[j + 7] * inv);
+        w.x = pack_half2(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+        w.y = pack_half2(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+        w.z = pack_half2(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+        w.w = pack_half2(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
         *reinterpret_cast<uint4*>(op + j) = w;
       }
     }

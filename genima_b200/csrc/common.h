@@ -39,6 +39,7 @@ struct gn_handle {
   std::unordered_map<std::string, std::array<int, 4>> tune_cache;
   cudaEvent_t tune_ev[2] = {nullptr, nullptr};
   int32_t last_cfg[4] = {0, 0, 0, 0};
+  int last_rowstats_parts = 0;
   int64_t launches = 0;
   bool gemm_attr_set = false;
   void* stats_scratch = nullptr;  // GroupNorm: grid-barrier words (first 256 B, zero-initialised) + per-CTA partials

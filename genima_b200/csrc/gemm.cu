@@ -54,6 +54,15 @@ struct EpiParams {
   float alpha, beta;
   int geglu;
   int M, N;  // N = accumulator columns (before GEGLU halving)
+  // LayerNorm folded into this GEMM (A = un-normalised x, W pre-multiplied by gamma):
+  //   out = rstd[m] * (acc - mean[m] * colsum[n]) + bias[n],  (mean, rstd) from the row partials the producer of x wrote
+  const float2* ln_stats;  // [M][ln_parts] (sum, sumsq) partials of each row of x; NULL = no folded LayerNorm
+  int ln_parts;
+  int ln_dim;              // row length of x (= K)
+  float ln_eps;
+  // row statistics of THIS GEMM's fp16 output for a LayerNorm folded into its consumer: [M][rs_parts] partials
+  float2* rs_out;
+  int rs_parts;
 };
 
 struct GemmParams {
@@ -70,6 +79,7 @@ struct GemmParams {
   int tiles_w, tiles_h;
   int block_n, stages, tmem_cols;
   float* ws;  // split-K partials [splits][M][N] fp32
+  int rs_capacity;            // host-side: capacity (partials per row) of epi.rs_out
   unsigned long long* trace;  // optional: %globaltimer stamps of CTA (0,0,0)'s phases (gn_set_gemm_trace)
   KSeg segs[MAX_SEGS];
 };
@@ -112,7 +122,8 @@ __device__ __forceinline__ float epi_pre(const EpiParams& e, float acc, int n, i
 // Finalise CH consecutive output columns [nout, nout + CH) of row m from pre-activation values v[]:
 // out = act_post(alpha * v + beta * residual).  16-byte vector path when the chunk is full and aligned.
 template <int CH>
-__device__ __forceinline__ void epi_store(const EpiParams& e, float (&v)[CH], int m, int nout, int n_out_total) {
+__device__ __forceinline__ void epi_store(const EpiParams& e, float (&v)[CH], int m, int nout, int n_out_total,
+                                          float* rs = nullptr) {
   const bool full = (nout + CH <= n_out_total);
   if (e.residual) {
     const __half* rp = e.residual + (int64_t)m * e.ldr + nout;
@@ -159,6 +170,15 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, float (&v)[CH], in
     return;
   }
   __half* op = e.out + (int64_t)m * e.ldo + nout;
+  if (rs) {
+    // statistics of the values the consumer will read back: the fp16-rounded outputs
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const float h = (nout + j < n_out_total) ? __half2float(__float2half_rn(v[j])) : 0.f;
+      rs[0] += h;
+      rs[1] = fmaf(h, h, rs[1]);
+    }
+  }
   if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
     for (int j = 0; j < CH; j += 8) {
@@ -176,6 +196,33 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, float (&v)[CH], in
   }
 }
 
+// (rstd, -mean * rstd) of row m of the GEMM's A operand from the row partials its producer wrote (fixed summation order).
+__device__ __forceinline__ void ln_row(const EpiParams& e, int m, float& rstd, float& nmr) {
+  const float2* sp = e.ln_stats + (int64_t)m * e.ln_parts;
+  float s1 = 0.f, s2 = 0.f;
+  int i = 0;
+  for (; i + 8 <= e.ln_parts; i += 8) {  // eight independent loads in flight, summed in index order
+    float2 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = __ldg(sp + i + u);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      s1 += t[u].x;
+      s2 += t[u].y;
+    }
+  }
+  for (; i < e.ln_parts; ++i) {
+    const float2 t = __ldg(sp + i);
+    s1 += t.x;
+    s2 += t.y;
+  }
+  const float inv = 1.0f / (float)e.ln_dim;
+  const float mean = s1 * inv;
+  const float var = fmaxf(s2 * inv - mean * mean, 0.f);
+  rstd = rsqrtf(var + e.ln_eps);
+  nmr = -mean * rstd;
+}
+
 // Epilogue of one output row over this warp's share of the tile's 16-column chunks (chunk index cw, cw + EPI_COLSPLIT, ...).
 // s_scale / s_bias: per-column fp32 vectors of the tile staged in shared memory (scale = 1 / bias = 0 when absent).
 // Rolled loop over chunks with a compile-time activation: the body stays small enough for the instruction cache
@@ -183,13 +230,14 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, float (&v)[CH], in
 template <int ACT, bool CLUSTER>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int n0, int m, int b, bool valid,
                                               int cw, const float* s_scale, const float* s_bias, const float* stage,
-                                              int row) {
+                                              int row, float ln_rstd, float ln_nmr) {
   const EpiParams& e = p.epi;
   const int nchunks = p.block_n >> 4;
   // CLUSTER (split-K): this CTA finishes the chunks rank, rank + S, ... of the tile, summing the fp32 partials that all
   // S CTAs of the cluster staged in their shared memory (read through DSMEM in rank order: deterministic).
   const int first = CLUSTER ? (int)cg::this_cluster().block_rank() + p.splits * cw : cw;
   const int step = CLUSTER ? p.splits * EPI_COLSPLIT : EPI_COLSPLIT;
+  float rs[2] = {0.f, 0.f};
 #pragma unroll 1
   for (int ch = first; ch < nchunks; ch += step) {
     const int c = ch << 4;
@@ -211,14 +259,27 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
     }
     const int n = n0 + c;
     if (!valid || n >= e.N) continue;
+    if (e.ln_stats) {
+      // s_scale holds colsum[n] = sum_k gamma[k] W[n, k], s_bias holds bias[n] + sum_k beta[k] W[n, k]
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + j);
-      const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + j);
-      v[j] = fmaf(v[j], sc.x, bi.x);
-      v[j + 1] = fmaf(v[j + 1], sc.y, bi.y);
-      v[j + 2] = fmaf(v[j + 2], sc.z, bi.z);
-      v[j + 3] = fmaf(v[j + 3], sc.w, bi.w);
+      for (int j = 0; j < 16; j += 4) {
+        const float4 cs = *reinterpret_cast<const float4*>(s_scale + c + j);
+        const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + j);
+        v[j] = fmaf(v[j], ln_rstd, fmaf(ln_nmr, cs.x, bi.x));
+        v[j + 1] = fmaf(v[j + 1], ln_rstd, fmaf(ln_nmr, cs.y, bi.y));
+        v[j + 2] = fmaf(v[j + 2], ln_rstd, fmaf(ln_nmr, cs.z, bi.z));
+        v[j + 3] = fmaf(v[j + 3], ln_rstd, fmaf(ln_nmr, cs.w, bi.w));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + j);
+        const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + j);
+        v[j] = fmaf(v[j], sc.x, bi.x);
+        v[j + 1] = fmaf(v[j + 1], sc.y, bi.y);
+        v[j + 2] = fmaf(v[j + 2], sc.z, bi.z);
+        v[j + 3] = fmaf(v[j + 3], sc.w, bi.w);
+      }
     }
     if (e.rowvec) {
       const float* rv = e.rowvec + (int64_t)b * e.N + n;
@@ -239,36 +300,48 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = act_ct<ACT>(v[j]);
-    epi_store<16>(e, v, m, n, e.N);
+    epi_store<16>(e, v, m, n, e.N, e.rs_out ? rs : nullptr);
+  }
+  if (e.rs_out && valid) {
+    // one partial per (n-tile, K-split rank, column share); the consumer sums them in index order
+    const int rank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
+    const int part = ((int)blockIdx.x * p.splits + rank) * EPI_COLSPLIT + cw;
+    e.rs_out[(int64_t)m * e.rs_parts + part] = make_float2(rs[0], rs[1]);
   }
 }
 
 template <bool CLUSTER>
 __device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, uint32_t taddr, int n0, int m, int b, bool valid,
                                                   int cw, const float* s_scale, const float* s_bias,
-                                                  const float* stage, int row) {
+                                                  const float* stage, int row, float ln_rstd, float ln_nmr) {
   switch (p.epi.act_pre) {
     case GN_ACT_SILU:
-      epilogue_rows<GN_ACT_SILU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row);
+      epilogue_rows<GN_ACT_SILU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
+                                          ln_nmr);
       break;
     case GN_ACT_GELU:
-      epilogue_rows<GN_ACT_GELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row);
+      epilogue_rows<GN_ACT_GELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
+                                          ln_nmr);
       break;
     case GN_ACT_RELU:
-      epilogue_rows<GN_ACT_RELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row);
+      epilogue_rows<GN_ACT_RELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
+                                          ln_nmr);
       break;
     case GN_ACT_QUICKGELU:
-      epilogue_rows<GN_ACT_QUICKGELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row);
+      epilogue_rows<GN_ACT_QUICKGELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
+                                          ln_nmr);
       break;
     default:
-      epilogue_rows<GN_ACT_NONE, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row);
+      epilogue_rows<GN_ACT_NONE, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
+                                          ln_nmr);
       break;
   }
 }
 
 // GEGLU epilogue: accumulator columns come in 128-wide groups [64 values | 64 gates]; out[m, j] = value * gelu(gate).
 __device__ __forceinline__ void epilogue_rows_geglu(const GemmParams& p, uint32_t taddr, int n0, int m, bool valid,
-                                                    int cw, const float* s_bias) {
+                                                    int cw, const float* s_scale, const float* s_bias, float ln_rstd,
+                                                    float ln_nmr) {
   const EpiParams& e = p.epi;
   const int n_out_total = e.N >> 1;
   const int nchunks = p.block_n >> 5;  // 16-wide value chunks: 4 per 128-column group
@@ -284,8 +357,9 @@ __device__ __forceinline__ void epilogue_rows_geglu(const GemmParams& p, uint32_
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float a = __uint_as_float(rv[j]) + s_bias[c + j];
-      const float g = __uint_as_float(rg[j]) + s_bias[c + 64 + j];
+      // folded LayerNorm: acc * rstd - mean * rstd * colsum[n] + bias'[n]  (identity when rstd = 1, nmr = 0)
+      const float a = fmaf(__uint_as_float(rv[j]), ln_rstd, fmaf(ln_nmr, s_scale[c + j], s_bias[c + j]));
+      const float g = fmaf(__uint_as_float(rg[j]), ln_rstd, fmaf(ln_nmr, s_scale[c + 64 + j], s_bias[c + 64 + j]));
       v[j] = a * gelu_erf_f(g);
     }
     epi_store<16>(e, v, m, ((n0 + ((ch >> 2) << 7)) >> 1) + ((ch & 3) << 4), n_out_total);
@@ -369,6 +443,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
   const int num_it = kb_end - kb_begin;
+  float ln_rstd = 1.f, ln_nmr = 0.f;  // folded LayerNorm of this thread's row (epilogue warps)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -451,6 +526,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       s_bias[i] = (p.epi.bias && n < p.epi.N) ? __ldg(p.epi.bias + n) : 0.0f;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // epilogue warps only
+    // folded LayerNorm: (rstd, -mean * rstd) of this row from the producer's partials, fetched while the MMAs run
+    if (p.epi.ln_stats && valid) ln_row(p.epi, m, ln_rstd, ln_nmr);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) trace_stamp(p, 5);
@@ -459,9 +536,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       // all MMAs have completed (tmem_full), so the operand ring is free: reuse it as the fp32 staging tile
       epilogue_rows_stage(p, taddr, cw, reinterpret_cast<float*>(smem), row);
     } else if (p.epi.geglu) {
-      epilogue_rows_geglu(p, taddr, n0, m, valid, cw, s_bias);
+      epilogue_rows_geglu(p, taddr, n0, m, valid, cw, s_scale, s_bias, ln_rstd, ln_nmr);
     } else {
-      epilogue_dispatch<false>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, nullptr, row);
+      epilogue_dispatch<false>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, nullptr, row, ln_rstd, ln_nmr);
     }
     tc_fence_before();
     if (threadIdx.x == 64) trace_stamp(p, 6);
@@ -488,7 +565,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         m = (gb * p.Ho + gy) * p.Wo + gx;
       }
       const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
-      epilogue_dispatch<true>(p, 0, n0, m, b, valid, cw, s_scale, s_bias, reinterpret_cast<const float*>(smem), row);
+      epilogue_dispatch<true>(p, 0, n0, m, b, valid, cw, s_scale, s_bias, reinterpret_cast<const float*>(smem), row,
+                              ln_rstd, ln_nmr);
     }
     cluster.sync();  // peers may still be reading this CTA's staging tile
   }
@@ -531,7 +609,7 @@ struct Candidate {
 };
 
 static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblocks, bool geglu, bool allow_split,
-                          Candidate* out, int max_out) {
+                          Candidate* out, int max_out, int rs_capacity = 0) {
   static const int kCand[] = {256, 224, 192, 160, 128, 96, 80, 64, 48, 32, 16};
   const int sms = h->num_sms;
   std::vector<Candidate> all;
@@ -550,6 +628,7 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
       if (h->force_splits && sp != h->force_splits && !(h->force_splits > max_splits && sp == max_splits)) continue;
       const int kb_per = gn::ceil_div(num_kblocks, sp);
       if ((sp - 1) * kb_per >= num_kblocks) continue;  // an empty split
+      if (rs_capacity > 0 && tiles_n * sp * EPI_COLSPLIT > rs_capacity) continue;  // row-statistics partials must fit
       const int64_t ctas = (int64_t)tiles_m * tiles_n * sp;
       for (int occ = 1; occ <= 2; ++occ) {
         if (h->force_occupancy && occ != h->force_occupancy) continue;
@@ -600,9 +679,11 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
 //     (128 + bn) * 128 / 46 [operand feed]) cycles of that SM, whichever CTA it belongs to;
 //   * every CTA pays ~3000 clk of latency (set-up, first TMA round trip, exit) plus ~25 clk per accumulator column of
 //     epilogue; with two co-resident CTAs that latency overlaps the neighbour's main loop.
-static TileChoice choose_tiles(const gn_handle* h, int tiles_m, int N, int num_kblocks, bool geglu, bool allow_split) {
+static TileChoice choose_tiles(const gn_handle* h, int tiles_m, int N, int num_kblocks, bool geglu, bool allow_split,
+                               int rs_capacity) {
   Candidate c[1];
-  if (candidate_list(h, tiles_m, N, num_kblocks, geglu, allow_split, c, 1) < 1) return TileChoice{128, 1, 4, 128};
+  if (candidate_list(h, tiles_m, N, num_kblocks, geglu, allow_split, c, 1, rs_capacity) < 1)
+    return TileChoice{128, 1, 4, 128};
   return c[0].tc;
 }
 
@@ -632,7 +713,20 @@ static int fill_epilogue(gn_handle* h, EpiParams& e, const gn_epilogue* epi, voi
       e.out32 = static_cast<float*>(out);
       e.out = nullptr;
     }
-    GN_CHECK_ARG(h, epi->gn_stats == nullptr, "gn_epilogue.gn_stats is not supported by this build");
+    if (epi->ln_stats) {
+      GN_CHECK_ARG(h, epi->ln_colsum && epi->ln_parts > 0 && !epi->scale,
+                   "folded LayerNorm needs ln_colsum, ln_parts > 0 and no scale vector");
+      e.ln_stats = static_cast<const float2*>(epi->ln_stats);
+      e.ln_parts = epi->ln_parts;
+      e.ln_eps = epi->ln_eps;
+      e.scale = epi->ln_colsum;  // staged in the per-column "scale" slot of the epilogue
+    }
+    if (epi->rowstats_out) {
+      GN_CHECK_ARG(h, !epi->geglu && !epi->out_fp32 && epi->rowstats_capacity > 0,
+                   "rowstats_out needs a plain fp16 output and a capacity");
+      e.rs_out = static_cast<float2*>(epi->rowstats_out);
+      e.rs_parts = epi->rowstats_capacity;  // replaced by the real partial count once the tile config is known
+    }
     GN_CHECK_ARG(h, !(epi->geglu && (N % 128) != 0), "GEGLU needs N %% 128 == 0 (got %d)", N);
     GN_CHECK_ARG(h, !(epi->residual && epi->ldr <= 0), "residual given without ldr");
   }
@@ -649,6 +743,13 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
   p.kb_per_split = gn::ceil_div(p.num_kblocks, tc.splits);
   p.ws = nullptr;
   p.trace = static_cast<unsigned long long*>(h->gemm_trace);
+  if (p.epi.rs_out) {
+    const int parts = gn::ceil_div(N, tc.block_n) * tc.splits * EPI_COLSPLIT;
+    GN_CHECK_ARG(h, parts <= p.rs_capacity, "row-statistics buffer too small: %d partials, capacity %d", parts,
+                 p.rs_capacity);
+    p.epi.rs_parts = parts;
+    h->last_rowstats_parts = parts;
+  }
   // weight tensor map: [N rows][ktot] fp16, box {64, block_n}
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)N};
@@ -682,8 +783,10 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
   const bool geglu = p.epi.geglu != 0;
   const bool forced = h->force_block_n || h->force_splits || h->force_occupancy;
   char keybuf[96];
-  snprintf(keybuf, sizeof(keybuf), "%d:%d:%d:%d:%d:%d:%d", p.mode, tiles_m, N, p.num_kblocks, geglu ? 1 : 0,
-           p.epi.out32 ? 1 : 0, p.epi.residual ? 1 : 0);
+  const int rs_capacity = p.epi.rs_out ? p.epi.rs_parts : 0;
+  p.rs_capacity = rs_capacity;
+  snprintf(keybuf, sizeof(keybuf), "%d:%d:%d:%d:%d:%d:%d:%d:%d", p.mode, tiles_m, N, p.num_kblocks, geglu ? 1 : 0,
+           p.epi.out32 ? 1 : 0, p.epi.residual ? 1 : 0, p.epi.ln_stats ? 1 : 0, rs_capacity);
   const std::string key(keybuf);
   if (!forced) {
     auto it = h->tune_cache.find(key);
@@ -698,7 +801,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
   cudaStreamIsCapturing(stream, &cap);
   if (h->autotune && !forced && !h->profiling && cap == cudaStreamCaptureStatusNone) {
     Candidate cand[10];
-    const int nc = candidate_list(h, tiles_m, N, p.num_kblocks, geglu, allow_split, cand, 10);
+    const int nc = candidate_list(h, tiles_m, N, p.num_kblocks, geglu, allow_split, cand, 10, rs_capacity);
     if (nc > 1) {
       if (!h->tune_ev[0]) {
         GN_CHECK_CUDA(h, cudaEventCreate(&h->tune_ev[0]));
@@ -740,7 +843,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
       return rc;
     }
   }
-  TileChoice tc = choose_tiles(h, tiles_m, N, p.num_kblocks, geglu, allow_split);
+  TileChoice tc = choose_tiles(h, tiles_m, N, p.num_kblocks, geglu, allow_split, rs_capacity);
   int rc = launch_config(h, p, tc, tiles_m, W, ktot, stream);
   if (rc == GN_OK) h->launches++;
   return rc;
@@ -763,6 +866,7 @@ extern "C" int gn_linear(gn_handle* h, const void* A, int64_t lda, int M, int K,
   memset(&p, 0, sizeof(p));
   int rc = fill_epilogue(h, p.epi, epi, out, ldo, M, N, M);
   if (rc) return rc;
+  p.epi.ln_dim = K;
   p.mode = 0;
   p.num_kblocks = ceil_div(K, BLOCK_K);
   p.num_segs = 1;

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(1024, 1) gn_fused_kernel(const GNParams p) {
   float* red = reinterpret_cast<float*>(gn_smem);
   float* chan = red + (size_t)T * 16;
   float* gstat = chan + (size_t)p.C * 2;
-  uint4* slice = reinterpret_cast<uint4*>(gstat + ((p.G * 2 + 3) & ~3));
+  float* kshift = gstat + ((p.G * 2 + 3) & ~3);  // (spare)
+  uint4* slice = reinterpret_cast<uint4*>(kshift + ((p.G + 3) & ~3));
   __shared__ unsigned int s_gen;
 
   const int t = threadIdx.x;
@@ -159,37 +160,37 @@ __global__ void __launch_bounds__(1024, 1) gn_fused_kernel(const GNParams p) {
       }
     }
   }
-  // ---- grid barrier
+  // ---- grid barrier; the LAST CTA to arrive reduces the partials of every image to final (mean, rstd) per group in
+  // a fixed order and publishes them before it releases the others (one reader instead of #CTA readers hammering the
+  // same few L2 lines).
+  __shared__ unsigned int s_last;
   __syncthreads();
   gn_stamp(p, 2);
   if (t == 0) {
-    __threadfence();
-    const unsigned int old = atomicAdd(p.bar, 1u);
-    if (old == gridDim.x - 1) {
-      atomicExch(p.bar, 0u);
-      __threadfence();
-      atomicAdd(p.bar + 1, 1u);
-    } else {
-      const long long t0 = clock64();
-      while (*reinterpret_cast<volatile unsigned int*>(p.bar + 1) == s_gen) {
-        if (clock64() - t0 > 4000000000LL) __trap();  // a scheduling bug must surface as an error, never a hang
-      }
-    }
-    __threadfence();
+    // release: this CTA's partials (ordered before by the __syncthreads above) become visible with the arrival
+    unsigned int old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.bar) : "memory");
+    s_last = (old == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
-  gn_stamp(p, 3);
-  // ---- phase 2: final statistics and normalisation.  One warp per group: lane i sums partials i, i + 32, ... in
-  // order, then a fixed xor-shuffle tree — the same summation order on every CTA and every run.
-  {
+  float* final_stats = p.partial + (size_t)p.B * p.ctas_per_b * p.G * 2;  // [B][G][2] = (mean, rstd)
+  if (s_last) {
     const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
-    for (int g = warp; g < p.G; g += nwarps) {
+    for (int bg = warp; bg < p.B * p.G; bg += nwarps) {
+      const int bb = bg / p.G, g = bg - bb * p.G;
+      const float* src = p.partial + ((size_t)bb * p.ctas_per_b * p.G + g) * 2;
+      float2 v[5];  // up to 160 partials: five independent loads per lane in flight, summed in index order
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int i = lane + 32 * u;
+        v[u] = (i < p.ctas_per_b) ? __ldcg(reinterpret_cast<const float2*>(src + (size_t)i * p.G * 2))
+                                  : make_float2(0.f, 0.f);
+      }
       float s1 = 0.f, s2 = 0.f;
-      const float* src = p.partial + ((size_t)b * p.ctas_per_b * p.G + g) * 2;
-      for (int i = lane; i < p.ctas_per_b; i += 32) {
-        const float2 v = __ldcg(reinterpret_cast<const float2*>(src + (size_t)i * p.G * 2));
-        s1 += v.x;
-        s2 += v.y;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        s1 += v[u].x;
+        s2 += v[u].y;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -199,11 +200,27 @@ __global__ void __launch_bounds__(1024, 1) gn_fused_kernel(const GNParams p) {
       if (lane == 0) {
         const float inv_n = 1.0f / ((float)p.cg * (float)p.HW);
         const float m1 = s1 * inv_n, m2 = s2 * inv_n;
-        gstat[2 * g] = gn_shift(p, b, g) + m1;
-        gstat[2 * g + 1] = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + p.eps);
+        final_stats[2 * bg] = gn_shift(p, bb, g) + m1;
+        final_stats[2 * bg + 1] = rsqrtf(fmaxf(m2 - m1 * m1, 0.f) + p.eps);
       }
     }
+    __syncthreads();
+    if (t == 0) {
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.bar), "r"(0u) : "memory");
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.bar + 1) : "memory");
+    }
+  } else if (t == 0) {
+    const long long t0 = clock64();
+    unsigned int g;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(p.bar + 1) : "memory");
+      if (g == s_gen && clock64() - t0 > 4000000000LL) __trap();  // a scheduling bug must never hang the GPU
+    } while (g == s_gen);
   }
+  __syncthreads();
+  gn_stamp(p, 3);
+  // ---- phase 2: normalisation with the published statistics
+  if (t < 2 * p.G) gstat[t] = __ldcg(final_stats + (size_t)b * p.G * 2 + t);
   __syncthreads();
   gn_stamp(p, 4);
   if (!active) return;
@@ -449,9 +466,11 @@ extern "C" int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x
   if (p.k < 1) p.k = 1;
   const int T = p.NV * p.k;
   const int threads = (T + 31) / 32 * 32;
-  GN_CHECK_ARG(h, (int64_t)B * p.ctas_per_b * groups * 8 + 256 <= h->stats_scratch_bytes,
+  GN_CHECK_ARG(h, (int64_t)B * (p.ctas_per_b + 1) * groups * 8 + 256 <= h->stats_scratch_bytes,
                "gn_group_norm: statistics scratch too small");
-  const size_t fixed = (size_t)T * 16 * 4 + (size_t)C * 2 * 4 + (size_t)((groups * 2 + 3) & ~3) * 4;
+  const size_t fixed = (size_t)T * 16 * 4 + (size_t)C * 2 * 4 + (size_t)((groups * 2 + 3) & ~3) * 4 +
+                       (size_t)((groups + 3) & ~3) * 4;
+  GN_CHECK_ARG(h, p.ctas_per_b <= 160, "gn_group_norm: more than 160 CTAs per image");
   const size_t slice = (size_t)p.pix_per_cta * p.NV * 16;
   p.cache = (fixed + slice <= 200 * 1024) ? 1 : 0;
   const size_t smem = fixed + (p.cache ? slice : 0);

@@ -39,6 +39,15 @@ def _f32(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     return t
 
 
+class RowStats:
+    """Per-row (sum, sumsq) partials of a GEMM output: float2 [M][parts] (parts is set by the producing call)."""
+
+    def __init__(self, M: int, N: int, device):
+        self.capacity = max(4, (N + 15) // 16 + 2)
+        self.buf = torch.empty(M, self.capacity, 2, dtype=torch.float32, device=device)
+        self.parts = 0
+
+
 class Ops:
     """One instance per device; owns the gn_handle and the scratch workspace (L2-flush buffer of the autotuner)."""
 
@@ -65,7 +74,7 @@ class Ops:
 
     def _epilogue(self, M: int, N: int, bias=None, scale=None, rowvec=None, rows_per_batch: int = 0, residual=None,
                   act_pre=None, act_post=None, alpha: float = 1.0, beta: float = 1.0, geglu: bool = False,
-                  out_fp32: bool = False) -> GnEpilogue:
+                  out_fp32: bool = False, ln=None, row_stats=None) -> GnEpilogue:
         e = GnEpilogue()
         e.scale = _ptr(_f32(scale, "scale"))
         e.bias = _ptr(_f32(bias, "bias"))
@@ -92,6 +101,18 @@ class Ops:
         e.beta = beta
         e.geglu = 1 if geglu else 0
         e.out_fp32 = 1 if out_fp32 else 0
+        if ln is not None:
+            # ln = (RowStats of the A operand, colsum [N] fp32, eps): LayerNorm folded into this GEMM
+            stats, colsum, eps = ln
+            if stats.buf.shape[0] != M or colsum.numel() != N:
+                raise ValueError("folded LayerNorm: row statistics / colsum do not match the GEMM")
+            e.ln_stats = stats.buf.data_ptr()
+            e.ln_colsum = _f32(colsum, "ln colsum").data_ptr()
+            e.ln_parts = stats.parts
+            e.ln_eps = float(eps)
+        if row_stats is not None:
+            e.rowstats_out = row_stats.buf.data_ptr()
+            e.rowstats_capacity = row_stats.capacity
         return e
 
     def set_gemm_tuning(self, block_n: int = 0, splits: int = 0) -> None:
@@ -127,8 +148,14 @@ class Ops:
                 for i, name in enumerate(self.PROF_CLASSES)}
 
     # ------------------------------------------------------------------------------------------------ contractions
+    def new_row_stats(self, M: int, N: int) -> "RowStats":
+        """Buffer for the per-row (sum, sumsq) partials a GEMM with N output columns writes (row_stats=...)."""
+        return RowStats(M, N, self.device)
+
     def linear(self, a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, **epi) -> torch.Tensor:
-        """out[..., N'] = epilogue(a[..., K] @ w[N, K]^T); N' = N/2 with geglu=True."""
+        """out[..., N'] = epilogue(a[..., K] @ w[N, K]^T); N' = N/2 with geglu=True.
+        row_stats=RowStats: also write the row statistics of the fp16 output (for a LayerNorm folded into the consumer);
+        ln=(RowStats, colsum, eps): `a` is un-normalised, `w` is pre-multiplied by gamma (packing.fold_layer_norm)."""
         _f16(a, "a")
         _f16(w, "w")
         K = a.shape[-1]
@@ -150,6 +177,8 @@ class Ops:
         rc = self.lib.gn_linear(self.h, a2.data_ptr(), a2.stride(0), M, K, w.data_ptr(), N, o2.data_ptr(),
                                 o2.stride(0), C.byref(e), self._stream())
         self.handle.check(rc, "gn_linear")
+        if epi.get("row_stats") is not None:
+            epi["row_stats"].parts = int(self.lib.gn_get_last_rowstats_parts(self.h))
         return out
 
     def conv2d(self, x: torch.Tensor, w: torch.Tensor, cout: int, ksize: int = 3, stride: int = 1, pad: int = 1,

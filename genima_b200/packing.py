@@ -76,3 +76,18 @@ def pad_cols(w: torch.Tensor, mult: int = 8) -> torch.Tensor:
     if kp == k:
         return w.contiguous()
     return _pad_last(w, kp - k).contiguous()
+
+
+def fold_layer_norm(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: torch.Tensor = None):
+    """LayerNorm(x) @ w^T + bias  ==  rstd * (x @ w_g^T - mean * colsum) + bias_f   with
+         w_g    = fp16(w * gamma)          (what the tensor core multiplies)
+         colsum = sum_k w_g[n, k]          (fp32, from the fp16-rounded w_g so that it matches the accumulation)
+         bias_f = bias + w @ beta          (fp32)
+    w: [N, K] (any row order, e.g. GEGLU-interleaved: the fold acts on the K axis only).  Returns (w_g, colsum, bias_f)."""
+    wf = w.float()
+    w_g = (wf * gamma.float()[None, :]).to(torch.float16).contiguous()
+    colsum = w_g.float().sum(dim=1).contiguous()
+    bias_f = wf @ beta.float()
+    if bias is not None:
+        bias_f = bias_f + bias.float()
+    return w_g, colsum, bias_f.contiguous()

@@ -24,7 +24,7 @@ import torch
 
 from .configs import UNetConfig
 from .ops import Ops
-from .packing import pack_conv_weight, pack_geglu_weight
+from .packing import fold_layer_norm, pack_conv_weight, pack_geglu_weight
 from .weights import unet_skip_channels
 
 LATENT_CPAD = 8  # latents travel as [B, h, w, 8] fp16 (4 real channels): 16-byte pixels for TMA
@@ -121,16 +121,20 @@ class _Transformer2D:
         self.gn_g, self.gn_b = P.f32(f"{prefix}.norm.weight"), P.f32(f"{prefix}.norm.bias")
         self.w_in, self.b_in = P.f16(f"{prefix}.proj_in.weight"), P.f32(f"{prefix}.proj_in.bias")
         self.w_out, self.b_out = P.f16(f"{prefix}.proj_out.weight"), P.f32(f"{prefix}.proj_out.bias")
-        self.ln = [(P.f32(f"{t}.norm{i}.weight"), P.f32(f"{t}.norm{i}.bias")) for i in (1, 2, 3)]
-        self.w_qkv = torch.cat([P.host16(f"{t}.attn1.to_{n}.weight") for n in "qkv"], dim=0).contiguous().to(dev)
+        # The three LayerNorms are folded into the GEMMs that consume them (gn_epilogue.ln_*): gamma goes into the
+        # weights, beta into the bias, and (mean, rstd) come from row statistics written by the producing GEMM's epilogue.
+        ln = [(P.sd[f"{t}.norm{i}.weight"].to(dev).float(), P.sd[f"{t}.norm{i}.bias"].to(dev).float()) for i in (1, 2, 3)]
+        w_qkv = torch.cat([P.host16(f"{t}.attn1.to_{n}.weight") for n in "qkv"], dim=0).to(dev)
+        self.w_qkv, self.cs_qkv, self.b_qkv = fold_layer_norm(w_qkv, *ln[0])
         self.w_o1, self.b_o1 = P.f16(f"{t}.attn1.to_out.0.weight"), P.f32(f"{t}.attn1.to_out.0.bias")
-        self.w_q2 = P.f16(f"{t}.attn2.to_q.weight")
+        self.w_q2, self.cs_q2, self.b_q2 = fold_layer_norm(P.f16(f"{t}.attn2.to_q.weight"), *ln[1])
         self.w_kv2 = torch.cat([P.host16(f"{t}.attn2.to_k.weight"), P.host16(f"{t}.attn2.to_v.weight")],
                                dim=0).contiguous().to(dev)
         self.w_o2, self.b_o2 = P.f16(f"{t}.attn2.to_out.0.weight"), P.f32(f"{t}.attn2.to_out.0.bias")
         wg, bg = pack_geglu_weight(P.host16(f"{t}.ff.net.0.proj.weight"), P.sd[f"{t}.ff.net.0.proj.bias"].float())
-        self.w_ff1, self.b_ff1 = wg.to(dev), bg.to(dev)
+        self.w_ff1, self.cs_ff1, self.b_ff1 = fold_layer_norm(wg.to(dev), *ln[2], bias=bg.to(dev))
         self.w_ff2, self.b_ff2 = P.f16(f"{t}.ff.net.2.weight"), P.f32(f"{t}.ff.net.2.bias")
+        self.ln_eps = 1e-5
         self.scale = 64 ** -0.5
         assert c // heads == 64, "the tcgen05 attention kernel is specialised for head_dim 64"
 
@@ -142,20 +146,20 @@ class _Transformer2D:
         B, H, W, C = x.shape
         T = H * W
         n = ops.group_norm(x, self.gn_g, self.gn_b, self.groups, 1e-6, silu=False)
-        h = ops.linear(n.reshape(B * T, C), self.w_in, bias=self.b_in)
-        # self attention
-        n1 = ops.layer_norm(h, *self.ln[0])
-        qkv = ops.linear(n1, self.w_qkv)
+        st = ops.new_row_stats(B * T, C)
+        h = ops.linear(n.reshape(B * T, C), self.w_in, bias=self.b_in, row_stats=st)
+        # self attention (norm1 folded into the QKV projection)
+        qkv = ops.linear(h, self.w_qkv, bias=self.b_qkv, ln=(st, self.cs_qkv, self.ln_eps))
         a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, self.heads, T, T, self.scale)
-        h = ops.linear(a, self.w_o1, bias=self.b_o1, residual=h)
-        # cross attention against the cached text K/V
-        n2 = ops.layer_norm(h, *self.ln[1])
-        q = ops.linear(n2, self.w_q2)
+        st = ops.new_row_stats(B * T, C)
+        h = ops.linear(a, self.w_o1, bias=self.b_o1, residual=h, row_stats=st)
+        # cross attention against the cached text K/V (norm2 folded into the Q projection)
+        q = ops.linear(h, self.w_q2, bias=self.b_q2, ln=(st, self.cs_q2, self.ln_eps))
         a = ops.attention(q, kv[:, :C], kv[:, C:], B, self.heads, T, tk, self.scale)
-        h = ops.linear(a, self.w_o2, bias=self.b_o2, residual=h)
-        # GEGLU feed-forward
-        n3 = ops.layer_norm(h, *self.ln[2])
-        g = ops.linear(n3, self.w_ff1, bias=self.b_ff1, geglu=True)
+        st = ops.new_row_stats(B * T, C)
+        h = ops.linear(a, self.w_o2, bias=self.b_o2, residual=h, row_stats=st)
+        # GEGLU feed-forward (norm3 folded into the first projection)
+        g = ops.linear(h, self.w_ff1, bias=self.b_ff1, ln=(st, self.cs_ff1, self.ln_eps), geglu=True)
         h = ops.linear(g, self.w_ff2, bias=self.b_ff2, residual=h)
         out = ops.linear(h, self.w_out, bias=self.b_out, residual=x.reshape(B * T, C))
         return out.reshape(B, H, W, C)

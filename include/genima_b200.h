@@ -57,8 +57,21 @@ typedef struct gn_epilogue {
   float beta;
   int32_t geglu;
   int32_t out_fp32; /* 0: fp16 output, 1: fp32 output */
-  float* gn_stats;  /* optional [B, groups, 2] fp32 (sum, sumsq) accumulated with atomics over the fp16-rounded output */
-  int32_t gn_groups;
+  /* LayerNorm folded into this GEMM (gn_linear only; BasicTransformerBlock's norm1/2/3 -> to_q/k/v, to_q, ff.net.0):
+   * A holds the UN-normalised rows x, W is pre-multiplied by the LayerNorm gamma, and the epilogue applies
+   *   acc' = rstd[m] * (acc - mean[m] * ln_colsum[n]) + bias[n],  ln_colsum[n] = sum_k W[n, k],
+   *   bias[n] = original bias + sum_k beta[k] * W_unscaled[n, k]
+   * with (mean, rstd) of row m computed from `ln_parts` (sum, sumsq) partials per row written by the GEMM that
+   * produced x (its rowstats_out).  `scale` must be NULL.  The LayerNorm kernel launch disappears. */
+  const void* ln_stats;   /* float2 [M][ln_parts] */
+  const float* ln_colsum; /* [N] */
+  int32_t ln_parts;
+  float ln_eps;
+  /* Row statistics of this GEMM's fp16 output: (sum, sumsq) partials, one per (n-tile, K-split, column share), written
+   * as float2 [M][parts] with parts = gn_get_last_rowstats_parts() <= rowstats_capacity (tile configurations that
+   * would need more partials are not considered). */
+  void* rowstats_out;
+  int32_t rowstats_capacity;
   int32_t reserved;
 } gn_epilogue;
 
@@ -95,6 +108,8 @@ int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm);
 int gn_set_gemm_trace(gn_handle* h, void* dptr_u64x8);
 /* Last launch configuration chosen by gn_linear / gn_conv2d: out[0]=block_n, out[1]=splits, out[2]=stages, out[3]=ctas. */
 int gn_get_last_gemm_config(const gn_handle* h, int32_t* out4);
+/* Partials per row the last gn_linear call with rowstats_out wrote (the consumer's ln_parts). */
+int gn_get_last_rowstats_parts(const gn_handle* h);
 /* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t gn_launch_count(const gn_handle* h);
 

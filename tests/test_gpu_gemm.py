@@ -150,3 +150,42 @@ def test_forced_tile_configurations_sweep(ops, M, N, K):
     finally:
         ops.set_gemm_tuning(0, 0)
         ops.lib.gn_set_gemm_occupancy(ops.h, 0)
+
+
+@pytest.mark.parametrize("M,C,N,geglu", [(4096, 320, 960, False), (256, 1280, 1280, False), (300, 128, 256, True),
+                                         (1024, 640, 5120, True), (64, 1280, 3840, False)])
+def test_layer_norm_folded_into_gemm(ops, M, C, N, geglu):
+    """BasicTransformerBlock: h = Linear(a) + res; y = Linear2(LayerNorm(h)).  The device path never materialises the
+    LayerNorm: the first GEMM's epilogue writes per-row (sum, sumsq) partials of h, the second GEMM runs on the
+    un-normalised h with gamma folded into its weight and applies rstd * (acc - mean * colsum) + bias' in its epilogue."""
+    import torch.nn.functional as F
+
+    from genima_b200.packing import fold_layer_norm, pack_geglu_weight
+
+    g = torch.Generator().manual_seed(M + N)
+    a = torch.randn(M, C, generator=g).to(torch.float16)
+    w0 = (torch.randn(C, C, generator=g) * C ** -0.5).to(torch.float16)
+    b0 = torch.randn(C, generator=g) * 0.1
+    res = (torch.randn(M, C, generator=g) + 0.5).to(torch.float16)          # non-zero row means
+    gamma = 1.0 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    w1 = (torch.randn(N, C, generator=g) * C ** -0.5).to(torch.float16)
+    b1 = torch.randn(N, generator=g) * 0.1
+    # reference: fp32 LayerNorm of the fp16-rounded h, then the second linear (GEGLU: value * gelu(gate))
+    h_ref = (a.float() @ w0.float().t() + b0 + res.float()).to(torch.float16)
+    y = F.linear(F.layer_norm(h_ref.float(), (C,), gamma, beta, 1e-5), w1.float(), b1)
+    ref = y[:, :N // 2] * F.gelu(y[:, N // 2:]) if geglu else y
+    # device
+    st = ops.new_row_stats(M, C)
+    h = ops.linear(a.cuda(), w0.cuda(), bias=b0.cuda(), residual=res.cuda(), row_stats=st)
+    assert torch.equal(h.cpu(), h_ref) or float((h.cpu().float() - h_ref.float()).abs().max()) < 2e-2
+    assert 0 < st.parts <= st.capacity
+    if geglu:
+        w1p, b1p = pack_geglu_weight(w1, b1)
+    else:
+        w1p, b1p = w1, b1
+    wg, colsum, bias_f = fold_layer_norm(w1p.cuda(), gamma.cuda(), beta.cuda(), bias=b1p.cuda())
+    out = ops.linear(h, wg, bias=bias_f, ln=(st, colsum, 1e-5), geglu=geglu)
+    err = float((out.float().cpu() - ref).abs().max() / ref.abs().max())
+    print(f"LN folded into GEMM M={M} C={C} N={N} geglu={geglu}: normalised max err {err:.3e}, {st.parts} row partials")
+    assert err < 3e-3
