@@ -179,6 +179,7 @@ class DeviceACT:
         self.b_head = torch.cat([P.sd[f"{a}.action_head.bias"].float(), P.sd[f"{a}.is_pad_head.bias"].float()],
                                 0).to(dev)
         self._rb_cache: Dict[int, dict] = {}
+        self._graphs: Dict[tuple, dict] = {}
         torch.cuda.current_stream().synchronize()
 
     # ------------------------------------------------------------------------------------------------ hoisted work
@@ -275,6 +276,37 @@ class DeviceACT:
         return out[:, :, :cfg.action_dim], out[:, :, cfg.action_dim:]
 
     @torch.no_grad()
+    def forward_graphed(self, qpos: torch.Tensor, image: torch.Tensor, task_emb: torch.Tensor):
+        """forward() replayed from a CUDA graph (captured once per input shape / task embedding): the ~150 kernel
+        launches of the controller cost one graph launch.  Inputs are copied into static buffers; the returned tensors
+        are overwritten by the next call."""
+        ops = self.ops
+        qpos = qpos.to(ops.device, torch.float32)
+        image = image.to(ops.device)
+        task_emb = task_emb.to(ops.device, torch.float32)
+        key = (tuple(qpos.shape), tuple(image.shape), image.dtype, tensor_key(task_emb))
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(qpos=qpos.clone(), image=image.clone(), task=task_emb)
+            self.film_affines(task_emb)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):           # warm-up outside capture (autotuning, smem attributes, allocator)
+                self.forward(st["qpos"], st["image"], st["task"])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                a_hat, is_pad = self.forward(st["qpos"], st["image"], st["task"])
+            if len(self._graphs) > 4:
+                self._graphs.clear()
+            g = self._graphs[key] = dict(graph=graph, st=st, a_hat=a_hat, is_pad=is_pad)
+        g["st"]["qpos"].copy_(qpos, non_blocking=True)
+        g["st"]["image"].copy_(image, non_blocking=True)
+        g["graph"].replay()
+        return g["a_hat"], g["is_pad"]
+
+    @torch.no_grad()
     def forward(self, qpos: torch.Tensor, image: torch.Tensor, task_emb: torch.Tensor):
         """qpos [B, state_dim] fp32; image [B, V, 3, H, W] fp32/fp16 in 0..255 (the reference's layout) or uint8
         [B, V, H, W, 3] (device-side untile output); task_emb [B, E] fp32.  -> (a_hat, is_pad_hat) fp32."""
@@ -282,14 +314,14 @@ class DeviceACT:
         B, V = image.shape[:2]
         if V != cfg.num_views:
             raise ValueError(f"expected {cfg.num_views} views, got {V}")
-        if image.dtype == torch.uint8:
-            if image.shape[-1] != 3:
-                raise ValueError("uint8 images must be [B, V, H, W, 3]")
+        if image.dtype == torch.uint8 and image.shape[-1] == 3 and image.shape[2] != 3:
+            # device-side untile output: [B, V, H, W, 3]
             img = ops.u8_to_nhwc(image.reshape(B * V, *image.shape[2:]).contiguous(), cpad=IMG_CPAD,
                                  mean=IMAGENET_MEAN, std=IMAGENET_STD)
         else:
+            # the reference's layout [B, V, 3, H, W]: uint8 camera frames, or their float() cast (genima_act.py:296)
             if image.shape[2] != 3:
-                raise ValueError("float images must be [B, V, 3, H, W]")
+                raise ValueError("images must be [B, V, 3, H, W] (or uint8 [B, V, H, W, 3])")
             img = ops.nchw_to_nhwc(image.reshape(B * V, *image.shape[2:]).contiguous(), cpad=IMG_CPAD,
                                    mean=IMAGENET_MEAN, std=IMAGENET_STD)
         if img.shape[1] != cfg.image_size or img.shape[2] != cfg.image_size:

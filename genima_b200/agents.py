@@ -155,7 +155,8 @@ class B200GenimaACTPolicy:
     """GenimaACTPolicy.forward (controller/method/genima_act.py:165-214), inference branch."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: ACTConfig = ACTConfig(), ops: Optional[Ops] = None,
-                 device="cuda"):
+                 device="cuda", use_cuda_graph: bool = True):
+        self.use_cuda_graph = use_cuda_graph
         self.cfg = cfg
         self.ops = ops or get_ops(device)
         self._sd = dict(state_dict)
@@ -182,7 +183,10 @@ class B200GenimaACTPolicy:
             raise NotImplementedError("training (actions is not None) is out of scope: this is the inference path")
         if task_emb is None:
             raise ValueError("task_emb is required (genima_act.yaml: use_lang_cond=True)")
-        a_hat, _ = self.impl.forward(qpos, image, task_emb)
+        if getattr(self, "use_cuda_graph", True):
+            a_hat, _ = self.impl.forward_graphed(qpos, image, task_emb)
+        else:
+            a_hat, _ = self.impl.forward(qpos, image, task_emb)
         return a_hat
 
     __call__ = forward
@@ -223,6 +227,8 @@ class B200GenimaACT:
         qpos = low.reshape(low.shape[0], -1).float()
         rgbs = [v for k, v in obs.items() if re.match(r"rgb.*", k) or "_rgb" in k]
         rgb = torch.stack(rgbs, 1)                                    # [B, V, T, 3, H, W]
-        image = rgb.reshape(rgb.shape[0], -1, 3, rgb.shape[-2], rgb.shape[-1]).float()
+        image = rgb.reshape(rgb.shape[0], -1, 3, rgb.shape[-2], rgb.shape[-1])
+        if image.dtype != torch.uint8:
+            image = image.float()                                     # genima_act.py:296 (`rgb.float()`)
         task_emb, _ = self.encode_clip_text(obs["lang_tokens"])
         return self.actor(qpos, image, task_emb=task_emb)

@@ -347,9 +347,12 @@ extern "C" int gn_nchw_to_nhwc(gn_handle* h, const void* src, int src_fp32, int 
     nm.mean[c] = nm.enabled ? mean3[c] : 0.f;
     nm.inv_std[c] = nm.enabled ? 1.0f / std3[c] : 1.f;
   }
-  if (src_fp32)
+  if (src_fp32 == 1)
     nchw_to_nhwc_kernel<float><<<grid_for(h, total), 256, 0, st>>>(static_cast<const float*>(src), B, C, H, W, Cpad,
                                                                    nm, static_cast<__half*>(dst));
+  else if (src_fp32 == 2)
+    nchw_to_nhwc_kernel<uint8_t><<<grid_for(h, total), 256, 0, st>>>(static_cast<const uint8_t*>(src), B, C, H, W,
+                                                                     Cpad, nm, static_cast<__half*>(dst));
   else
     nchw_to_nhwc_kernel<__half><<<grid_for(h, total), 256, 0, st>>>(static_cast<const __half*>(src), B, C, H, W, Cpad,
                                                                     nm, static_cast<__half*>(dst));

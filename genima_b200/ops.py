@@ -364,14 +364,15 @@ class Ops:
         return x_next, x_scaled
 
     def nchw_to_nhwc(self, src: torch.Tensor, cpad: Optional[int] = None, mean=None, std=None) -> torch.Tensor:
-        if not src.is_cuda or not src.is_contiguous() or src.dtype not in (torch.float16, torch.float32):
-            raise TypeError("nchw_to_nhwc: contiguous CUDA fp16/fp32 tensor expected")
+        if not src.is_cuda or not src.is_contiguous() or src.dtype not in (torch.float16, torch.float32, torch.uint8):
+            raise TypeError("nchw_to_nhwc: contiguous CUDA fp16/fp32/uint8 tensor expected")
         B, Cn, H, W = src.shape
         cpad = cpad or Cn
         dst = torch.empty(B, H, W, cpad, dtype=torch.float16, device=src.device)
         m = (C.c_float * 3)(*mean) if mean is not None else None
         s = (C.c_float * 3)(*std) if std is not None else None
-        rc = self.lib.gn_nchw_to_nhwc(self.h, src.data_ptr(), 1 if src.dtype == torch.float32 else 0, B, Cn, H, W,
+        code = {torch.float16: 0, torch.float32: 1, torch.uint8: 2}[src.dtype]
+        rc = self.lib.gn_nchw_to_nhwc(self.h, src.data_ptr(), code, B, Cn, H, W,
                                       cpad, m, s, dst.data_ptr(), self._stream())
         self.handle.check(rc, "gn_nchw_to_nhwc")
         return dst

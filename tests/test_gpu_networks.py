@@ -268,6 +268,12 @@ def test_act_forward(ops, name, B):
     check(f"ACT {name} is_pad_hat", p, ref_p, NET_TOL)
     a2, _ = act.forward(qpos.cuda(), views.permute(0, 1, 3, 4, 2).contiguous().cuda(), task.cuda())
     assert torch.equal(a2, a), "uint8 NHWC input path must give the same result as the float NCHW path"
+    a3, _ = act.forward(qpos.cuda(), views.cuda(), task.cuda())
+    assert torch.equal(a3, a), "uint8 NCHW (the reference's obs layout) must give the same result too"
+    task_dev = task.cuda()
+    a4, _ = act.forward_graphed(qpos.cuda(), views.cuda(), task_dev)
+    a5, _ = act.forward_graphed(qpos.cuda(), views.cuda(), task_dev)          # replay
+    assert torch.equal(a4, a) and torch.equal(a5, a), "CUDA-graph replay of the controller must be bit-identical"
 
 
 # --------------------------------------------------------------------------------------------------- pipeline
