@@ -43,7 +43,8 @@ class GnEpilogue(C.Structure):
         ("ln_eps", C.c_float),
         ("rowstats_out", C.c_void_p),
         ("rowstats_capacity", C.c_int32),
-        ("reserved", C.c_int32),
+        ("gn_bucket", C.c_int32),
+        ("gnstats_out", C.c_void_p),
     ]
 
 
@@ -58,8 +59,11 @@ SIGNATURES = {
     "gn_set_gemm_tuning": (_i, [_vp, _i, _i]),
     "gn_set_pdl": (_i, [_vp, _i]),
     "gn_set_gn_max_ctas": (_i, [_vp, _i]),
+    "gn_set_staged_epilogue": (_i, [_vp, _i]),
     "gn_set_autotune": (_i, [_vp, _i]),
     "gn_set_gemm_occupancy": (_i, [_vp, _i]),
+    "gn_set_gemm_multicast": (_i, [_vp, _i, _i]),
+    "gn_set_conv_halo": (_i, [_vp, _i, _i]),
     "gn_set_gemm_trace": (_i, [_vp, _vp]),
     "gn_get_last_gemm_config": (_i, [_vp, C.POINTER(C.c_int32)]),
     "gn_get_last_rowstats_parts": (_i, [_vp]),
@@ -73,6 +77,7 @@ SIGNATURES = {
     "gn_attention": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _vp]),
     "gn_attention_small": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "gn_group_norm": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
+    "gn_group_norm_apply": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp]),
     "gn_layer_norm": (_i, [_vp, _vp, _i64, _i, _i, _f, _vp, _vp, _vp, _i64, _vp]),
     "gn_softmax_rows": (_i, [_vp, _vp, _i, _i64, _vp, _i64, _i, _i, _f, _vp]),
     "gn_upsample_nearest2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -20,7 +20,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_tmap_f16(gn_handle* h, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box) {
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   if (!h->encode_fn) return set_error(h, GN_ERR_NODRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver)");
   // cache key: raw bytes of every argument
   std::string key;
@@ -30,6 +30,7 @@ int make_tmap_f16(gn_handle* h, CUtensorMap* out, const void* base, int rank, co
   key.append(reinterpret_cast<const char*>(dims), sizeof(uint64_t) * rank);
   key.append(reinterpret_cast<const char*>(strides_bytes), sizeof(uint64_t) * (rank - 1));
   key.append(reinterpret_cast<const char*>(box), sizeof(uint32_t) * rank);
+  key.append(reinterpret_cast<const char*>(&swizzle_bytes), sizeof(swizzle_bytes));
   auto it = h->tmap_cache.find(key);
   if (it != h->tmap_cache.end()) {
     *out = it->second;
@@ -53,9 +54,16 @@ int make_tmap_f16(gn_handle* h, CUtensorMap* out, const void* base, int rank, co
       return set_error(h, GN_ERR_INVALID, "TMA stride[%d]=%llu bytes is not a multiple of 16", i,
                        (unsigned long long)strides_bytes[i]);
   }
+  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (swizzle_bytes == 64) swz = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 32) swz = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle_bytes != 128) return set_error(h, GN_ERR_INVALID, "TMA swizzle %d unsupported", swizzle_bytes);
+  if ((uint64_t)box[0] * 2 > (uint64_t)swizzle_bytes)
+    return set_error(h, GN_ERR_INVALID, "TMA inner box (%u elements) exceeds the %d-byte swizzle span", box[0],
+                     swizzle_bytes);
   CUresult r = reinterpret_cast<EncodeTiledFn>(h->encode_fn)(
       out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims, gstrides,
-      gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(h, GN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   if (h->tmap_cache.size() > 65536) h->tmap_cache.clear();
@@ -146,6 +154,22 @@ int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits) {
   return GN_OK;
 }
 
+int gn_set_gemm_multicast(gn_handle* h, int max_cluster, int force_cluster) {
+  if (!h || max_cluster < 1 || max_cluster > 4 || force_cluster < 0 || force_cluster > 4) return GN_ERR_INVALID;
+  h->mcast_max = max_cluster;
+  h->force_mcast = force_cluster;
+  h->tune_cache.clear();
+  return GN_OK;
+}
+
+int gn_set_conv_halo(gn_handle* h, int enable, int base_offset_field) {
+  if (!h) return GN_ERR_INVALID;
+  h->halo_conv = enable != 0;
+  h->halo_base_offset = base_offset_field != 0;
+  h->tune_cache.clear();
+  return GN_OK;
+}
+
 int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm) {
   if (!h || ctas_per_sm < 0 || ctas_per_sm > 2) return GN_ERR_INVALID;
   h->force_occupancy = ctas_per_sm;
@@ -155,6 +179,14 @@ int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm) {
 int gn_set_pdl(gn_handle* h, int enable) {
   if (!h) return GN_ERR_INVALID;
   h->pdl = enable != 0;
+  return GN_OK;
+}
+
+int gn_set_staged_epilogue(gn_handle* h, int enable) {
+  if (!h) return GN_ERR_INVALID;
+  h->staged_epilogue = enable != 0;
+  h->fast_epilogue = enable == 1;  // 2: staged output through the generic kernel flavour (A/B)
+  h->tune_cache.clear();
   return GN_OK;
 }
 

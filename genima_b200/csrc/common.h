@@ -34,6 +34,10 @@ struct gn_handle {
   int force_block_n = 0;
   int force_splits = 0;
   int force_occupancy = 0;
+  bool halo_conv = false;        // 3x3 stride-1 convolutions fetch column-strip halo tiles (gn_set_conv_halo); measured slower
+  bool halo_base_offset = false;  // UMMA descriptor variant: B200 swizzles on absolute address bits, the field stays 0
+  int force_mcast = 0;  // 0: autotuned; 2 / 4: W-tile multicast cluster size wherever applicable
+  int mcast_max = 1;    // largest multicast cluster the tile search may try (1 = off: measured slower on B200)
   // measured tile configurations per problem shape (gn_set_autotune): key -> {block_n, splits, stages, tmem_cols}
   bool autotune = false;
   std::unordered_map<std::string, std::array<int, 4>> tune_cache;
@@ -46,8 +50,11 @@ struct gn_handle {
   int64_t stats_scratch_bytes = 0;
   bool attn_attr_set = false;
   bool gn_attr_set = false;
+  bool gna_attr_set = false;
   int gn_max_ctas = 0;  // 0: one CTA per SM
   bool pdl = true;      // launch the main kernels with programmatic stream serialization (gn_set_pdl)
+  bool staged_epilogue = true;  // GEMM outputs staged in shared memory and TMA-stored (gn_set_staged_epilogue)
+  bool fast_epilogue = true;    // compact per-activation kernel flavours (gn_set_staged_epilogue(h, 2) = staged, generic)
   // cuTensorMapEncodeTiled resolved at runtime through cudaGetDriverEntryPoint (the library must load on a
   // CPU-only box, so libcuda is never linked directly).
   void* encode_fn = nullptr;
@@ -81,10 +88,10 @@ int set_error(gn_handle* h, int code, const char* fmt, ...);
     (h)->launches++;                                                                                         \
   } while (0)
 
-// fp16 tiled tensor map, SWIZZLE_128B, zero OOB fill.  dims/strides innermost first; strides[i] (bytes) is the stride
-// of dim i+1.  Returns 0 or a negative gn_status.
+// fp16 tiled tensor map, SWIZZLE_128B by default (64 / 32 for narrower inner boxes), zero OOB fill.  dims/strides
+// innermost first; strides[i] (bytes) is the stride of dim i+1.  Returns 0 or a negative gn_status.
 int make_tmap_f16(gn_handle* h, CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box);
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 // RAII scope recording a CUDA event pair around one C-ABI call when profiling is on (cls: enum gn_prof_class).
 struct ProfScope {
@@ -129,11 +136,14 @@ inline cudaError_t launch_ex(const gn_handle* h, void (*kernel)(KArgs...), dim3 
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (cluster_z > 1) {
+  // cluster_z: low byte = cluster size along grid.z, next byte = cluster size along grid.y (0 / 1 = none)
+  const int cz = (cluster_z & 0xff) > 1 ? (cluster_z & 0xff) : 1;
+  const int cy = ((cluster_z >> 8) & 0xff) > 1 ? ((cluster_z >> 8) & 0xff) : 1;
+  if (cz > 1 || cy > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 1;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = cluster_z;
+    attr[na].val.clusterDim.y = cy;
+    attr[na].val.clusterDim.z = cz;
     ++na;
   }
   if (h->pdl) {

@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -68,6 +69,8 @@ struct EpiParams {
 struct GemmParams {
   CUtensorMap tmA[4];
   CUtensorMap tmB;
+  CUtensorMap tmOut;  // staged output: fp16 [M][N_out] (2-D) or NHWC (4-D), box {io_w, 128 rows}
+  CUtensorMap tmRes;  // residual prefetch, same box
   EpiParams epi;
   int num_kblocks;
   int kb_per_split;
@@ -78,11 +81,47 @@ struct GemmParams {
   int bw, bh, bb;
   int tiles_w, tiles_h;
   int block_n, stages, tmem_cols;
-  float* ws;  // split-K partials [splits][M][N] fp32
+  // ---- halo mode (3x3, stride 1, pad 1 convolutions): the A ring holds 8 x (16 + 2) pixel column strips of one
+  // 64-channel block, one per horizontal tap offset kx; the three vertical taps are the windows of the strip that start
+  // 0 / 8 / 16 rows (whole 1 KiB swizzle atoms) into it, so the input is fetched 3 times per channel block instead of 9.
+  // (A single (8 + 2) x (16 + 2) halo tile with nine windows at arbitrary row offsets also gives correct results -- the
+  // tensor core swizzles on absolute address bits -- but its MMAs measured ~3x slower: windows must stay atom-aligned.)
+  int halo;      // 1: halo mode (mode == 1 only)
+  int halo_ncb;  // 64-channel blocks of the main input; k-blocks [0, 9 * halo_ncb) are ((cb, kx), ky), ky fastest
+  int halo_bo;   // (unused) descriptor variant switch
+  int mcast;  // compact flavours: cluster size along grid.y whose CTAs share the W tile through TMA multicast (1 = off)
+  // ---- output staging (see epilogue_tail): the epilogue warps write the finished fp16 tile into shared memory in the
+  // layout of a TMA box {io_w columns, 128 rows} per sub-tile (swizzle span = 2 * io_w bytes) and ONE thread stores it with
+  // cp.async.bulk.tensor; the residual tile is prefetched into the same buffer by the producer warp while the MMAs run.
+  int staged;    // 1: TMA-stored output
+  int res_tma;   // 1: residual tile prefetched by TMA into the staging buffer (staged only)
+  int res_late;  // 1: the staging buffer aliases the operand ring, so the prefetch is issued once the stages under it
+                 //    are free (end of the main loop) instead of at kernel start -- keeps the ring as deep as possible
+  int io_lw;     // log2(io_w): 6 / 5 / 4  (sub-tile width 64 / 32 / 16 columns)
+  int io_off;    // byte offset of the staging buffer from the 1024-aligned shared-memory base
+  int tail_off;  // byte offset of the fixed tail region (scale / bias / column partials / barriers)
+  // ---- GroupNorm statistics of this GEMM's fp16 output, for the gn_group_norm_apply that consumes it
+  unsigned long long* gn_out;  // [B][gn_nb][2] fixed-point (sum, sumsq) accumulators, zeroed by the caller
+  int gn_bucket;               // channels per statistics bucket (even; divides the consumer's channels-per-group)
+  int gn_nb;                   // buckets per image = N_out / gn_bucket
+  int gn_rows;                 // rows per column-pass row group (16 / 32 / 64 / 128)
+  int gn_img_rows;             // rows of one image inside a 128-row tile (<= 128, multiple of gn_rows)
+  int gn_stat_images;          // host-side: images covered by gn_out
+  int dbg;    // experiment switches (GENIMA_B200_DBG): 1 skip scale/bias smem reads, 2 skip staging stores, 4 skip tmem_ld
+  float* ws;  // (unused) split-K workspace
   int rs_capacity;            // host-side: capacity (partials per row) of epi.rs_out
   unsigned long long* trace;  // optional: %globaltimer stamps of CTA (0,0,0)'s phases (gn_set_gemm_trace)
   KSeg segs[MAX_SEGS];
 };
+
+constexpr int HALO_W = 8, HALO_H = 16;                 // output pixels per tile in halo mode
+constexpr int HALO_ROWS = HALO_W * (HALO_H + 2);        // one column strip: 8 x 18 pixel rows of 128 bytes
+constexpr int HALO_BYTES = HALO_ROWS * 128;             // 18 KiB per strip (a multiple of the 1 KiB swizzle repeat)
+constexpr int HALO_STAGE = HALO_BYTES;
+constexpr int HALO_STAGES = 4;
+constexpr float GN_FIXED_SCALE = 1048576.0f;  // 2^20: fixed-point scale of the GroupNorm (sum, sumsq) accumulators
+constexpr int TAIL_SCALE_FLOATS = 256;
+constexpr int TAIL_COL_FLOATS = 1024;  // column partials of the GroupNorm pass: row groups x out columns x 2 <= 1024
 
 __device__ __forceinline__ void trace_stamp(const GemmParams& p, int slot) {
   if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
@@ -110,89 +149,150 @@ __device__ __forceinline__ float act_ct(float v) {
   else return v;
 }
 
-// v = act_pre(acc * scale[n] + bias[n] + rowvec[b, n])   (runtime-dispatched form, used by the split-K reduce pass)
-__device__ __forceinline__ float epi_pre(const EpiParams& e, float acc, int n, int b) {
-  float v = acc;
-  if (e.scale) v *= __ldg(e.scale + n);
-  if (e.bias) v += __ldg(e.bias + n);
-  if (e.rowvec) v += __ldg(e.rowvec + (int64_t)b * e.N + n);
-  return apply_act(v, e.act_pre);
+// Byte offset (swizzled) inside the staging buffer of the 16-byte unit holding out-tile columns [ct, ct + 8) of `row`.
+// Sub-tile s = ct >> lw holds columns [s * w, (s + 1) * w) as 128 rows of 2 * w bytes, exactly what a TMA box {w, 128}
+// with swizzle span 2 * w reads / writes: byte-address bits [4, 4 + lw - 3) are XOR-ed with bits [7, ...).
+__device__ __forceinline__ uint32_t io_offset(int lw, int row, int ct) {
+  const uint32_t off = (static_cast<uint32_t>(ct >> lw) << (8 + lw)) + (static_cast<uint32_t>(row) << (1 + lw)) +
+                       (static_cast<uint32_t>(ct & ((1 << lw) - 1)) << 1);
+  const uint32_t smask = (1u << (lw - 3)) - 1u;  // 7 / 3 / 1
+  return off ^ (((off >> 7) & smask) << 4);
 }
 
-// Finalise CH consecutive output columns [nout, nout + CH) of row m from pre-activation values v[]:
-// out = act_post(alpha * v + beta * residual).  16-byte vector path when the chunk is full and aligned.
-template <int CH>
-__device__ __forceinline__ void epi_store(const EpiParams& e, float (&v)[CH], int m, int nout, int n_out_total,
-                                          float* rs = nullptr) {
-  const bool full = (nout + CH <= n_out_total);
-  if (e.residual) {
-    const __half* rp = e.residual + (int64_t)m * e.ldr + nout;
-    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 q;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+  return q;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& q) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+}
+
+// Finalise the 16 consecutive output columns [nout, nout + 16) of row m (tile row `row`, out-tile column ct) from the
+// pre-activation values v[]:  out = act_post(alpha * v + beta * residual), rounded to fp16 and
+//   * staged:   written into the shared-memory staging buffer (the TMA store clips rows / columns outside the tensor),
+//   * otherwise written straight to global memory (fp32 outputs, split-K, unaligned tensors).
+// Rows outside the tensor and columns >= n_out_total are staged as zeros so that the GroupNorm column pass is exact.
+__device__ __forceinline__ void epi_finish16(const GemmParams& p, float (&v)[16], int m, bool valid, int nout, int ct,
+                                             int row, uint32_t io_base, float* rs) {
+  const EpiParams& e = p.epi;
+  const int n_out_total = e.geglu ? (e.N >> 1) : e.N;
+  const bool full = (nout + 16 <= n_out_total);
+  const bool to_smem = p.staged || p.gn_out != nullptr;
+  uint32_t a0 = 0, a1 = 0;
+  if (to_smem || p.res_tma) {
+    a0 = io_base + io_offset(p.io_lw, row, ct);
+    a1 = io_base + io_offset(p.io_lw, row, ct + 8);
+  }
+  if (p.res_tma) {
+    const uint4 q0 = lds128(a0), q1 = lds128(a1);
+    const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
 #pragma unroll
-      for (int j = 0; j < CH; j += 8) {
-        uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
-        const __half2* hp = reinterpret_cast<const __half2*>(&q);
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(h0[t]);
+      const float2 g = __half22float2(h1[t]);
+      v[2 * t] = fmaf(e.alpha, v[2 * t], e.beta * f.x);
+      v[2 * t + 1] = fmaf(e.alpha, v[2 * t + 1], e.beta * f.y);
+      v[8 + 2 * t] = fmaf(e.alpha, v[8 + 2 * t], e.beta * g.x);
+      v[8 + 2 * t + 1] = fmaf(e.alpha, v[8 + 2 * t + 1], e.beta * g.y);
+    }
+  } else if (e.residual) {
+    if (valid) {
+      const __half* rp = e.residual + (int64_t)m * e.ldr + nout;
+      if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float2 f = __half22float2(hp[t]);
-          v[j + 2 * t] = fmaf(e.alpha, v[j + 2 * t], e.beta * f.x);
-          v[j + 2 * t + 1] = fmaf(e.alpha, v[j + 2 * t + 1], e.beta * f.y);
+        for (int j = 0; j < 16; j += 8) {
+          uint4 q = __ldg(reinterpret_cast<const uint4*>(rp + j));
+          const __half2* hp = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float2 f = __half22float2(hp[t]);
+            v[j + 2 * t] = fmaf(e.alpha, v[j + 2 * t], e.beta * f.x);
+            v[j + 2 * t + 1] = fmaf(e.alpha, v[j + 2 * t + 1], e.beta * f.y);
+          }
         }
-      }
-    } else {
+      } else {
 #pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        float r = (nout + j < n_out_total) ? __half2float(rp[j]) : 0.0f;
-        v[j] = e.alpha * v[j] + e.beta * r;
+        for (int j = 0; j < 16; ++j) {
+          float r = (nout + j < n_out_total) ? __half2float(rp[j]) : 0.0f;
+          v[j] = e.alpha * v[j] + e.beta * r;
+        }
       }
     }
   } else if (e.alpha != 1.0f) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] *= e.alpha;
+    for (int j = 0; j < 16; ++j) v[j] *= e.alpha;
   }
   if (e.act_post == GN_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.0f);
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (e.act_post != GN_ACT_NONE) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) v[j] = apply_act(v[j], e.act_post);
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], e.act_post);
   }
   if (e.out32) {
+    if (!valid) return;
     float* op = e.out32 + (int64_t)m * e.ldo + nout;
     if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
 #pragma unroll
-      for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < CH; ++j)
+      for (int j = 0; j < 16; ++j)
         if (nout + j < n_out_total) op[j] = v[j];
     }
     return;
   }
-  __half* op = e.out + (int64_t)m * e.ldo + nout;
-  if (rs) {
-    // statistics of the values the consumer will read back: the fp16-rounded outputs
+  if (!valid || !full) {
 #pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const float h = (nout + j < n_out_total) ? __half2float(__float2half_rn(v[j])) : 0.f;
-      rs[0] += h;
-      rs[1] = fmaf(h, h, rs[1]);
+    for (int j = 0; j < 16; ++j)
+      if (!valid || nout + j >= n_out_total) v[j] = 0.f;
+  }
+  uint4 q0, q1;
+  q0.x = pack_half2(v[0], v[1]);
+  q0.y = pack_half2(v[2], v[3]);
+  q0.z = pack_half2(v[4], v[5]);
+  q0.w = pack_half2(v[6], v[7]);
+  q1.x = pack_half2(v[8], v[9]);
+  q1.y = pack_half2(v[10], v[11]);
+  q1.z = pack_half2(v[12], v[13]);
+  q1.w = pack_half2(v[14], v[15]);
+  if (rs) {
+    // statistics of the values the consumer will read back: the fp16-rounded outputs (zeros outside the tensor)
+    const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+    const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(h0[t]);
+      rs[0] += f.x + f.y;
+      rs[1] = fmaf(f.x, f.x, fmaf(f.y, f.y, rs[1]));
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __half22float2(h1[t]);
+      rs[0] += f.x + f.y;
+      rs[1] = fmaf(f.x, f.x, fmaf(f.y, f.y, rs[1]));
     }
   }
-  if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+  if (to_smem && !(p.dbg & 2)) {
+    sts128(a0, q0);
+    sts128(a1, q1);
+  }
+  if (!p.staged && valid) {
+    __half* op = e.out + (int64_t)m * e.ldo + nout;
+    if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+      *reinterpret_cast<uint4*>(op) = q0;
+      *reinterpret_cast<uint4*>(op + 8) = q1;
+    } else {
+      const __half* hv0 = reinterpret_cast<const __half*>(&q0);
+      const __half* hv1 = reinterpret_cast<const __half*>(&q1);
 #pragma unroll
-    for (int j = 0; j < CH; j += 8) {
-      uint4 q;
-      q.x = pack_half2(v[j], v[j + 1]);
-      q.y = pack_half2(v[j + 2], v[j + 3]);
-      q.z = pack_half2(v[j + 4], v[j + 5]);
-      q.w = pack_half2(v[j + 6], v[j + 7]);
-      *reinterpret_cast<uint4*>(op + j) = q;
+      for (int j = 0; j < 8; ++j) {
+        if (nout + j < n_out_total) op[j] = hv0[j];
+        if (nout + 8 + j < n_out_total) op[8 + j] = hv1[j];
+      }
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < CH; ++j)
-      if (nout + j < n_out_total) op[j] = __float2half_rn(v[j]);
   }
 }
 
@@ -230,13 +330,14 @@ __device__ __forceinline__ void ln_row(const EpiParams& e, int m, float& rstd, f
 template <int ACT, bool CLUSTER>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int n0, int m, int b, bool valid,
                                               int cw, const float* s_scale, const float* s_bias, const float* stage,
-                                              int row, float ln_rstd, float ln_nmr) {
+                                              int row, float ln_rstd, float ln_nmr, uint32_t io_base) {
   const EpiParams& e = p.epi;
   const int nchunks = p.block_n >> 4;
   // CLUSTER (split-K): this CTA finishes the chunks rank, rank + S, ... of the tile, summing the fp32 partials that all
   // S CTAs of the cluster staged in their shared memory (read through DSMEM in rank order: deterministic).
   const int first = CLUSTER ? (int)cg::this_cluster().block_rank() + p.splits * cw : cw;
   const int step = CLUSTER ? p.splits * EPI_COLSPLIT : EPI_COLSPLIT;
+  const bool rows_needed = valid || p.staged || p.gn_out != nullptr;  // staged tiles hold every row (zeros when invalid)
   float rs[2] = {0.f, 0.f};
 #pragma unroll 1
   for (int ch = first; ch < nchunks; ch += step) {
@@ -252,14 +353,20 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
       }
     } else {
       uint32_t r[16];
-      tmem_ld_x16(taddr + c, r);
-      tmem_ld_wait();
+      if (!(p.dbg & 4)) {
+        tmem_ld_x16(taddr + c, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0;
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
     }
     const int n = n0 + c;
-    if (!valid || n >= e.N) continue;
-    if (e.ln_stats) {
+    if (!rows_needed || n >= e.N) continue;
+    if (p.dbg & 1) {
+    } else if (e.ln_stats) {
       // s_scale holds colsum[n] = sum_k gamma[k] W[n, k], s_bias holds bias[n] + sum_k beta[k] W[n, k]
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
@@ -300,7 +407,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = act_ct<ACT>(v[j]);
-    epi_store<16>(e, v, m, n, e.N, e.rs_out ? rs : nullptr);
+    epi_finish16(p, v, m, valid, n, c, row, io_base, e.rs_out ? rs : nullptr);
   }
   if (e.rs_out && valid) {
     // one partial per (n-tile, K-split rank, column share); the consumer sums them in index order
@@ -313,27 +420,28 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
 template <bool CLUSTER>
 __device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, uint32_t taddr, int n0, int m, int b, bool valid,
                                                   int cw, const float* s_scale, const float* s_bias,
-                                                  const float* stage, int row, float ln_rstd, float ln_nmr) {
+                                                  const float* stage, int row, float ln_rstd, float ln_nmr,
+                                                  uint32_t io_base) {
   switch (p.epi.act_pre) {
     case GN_ACT_SILU:
       epilogue_rows<GN_ACT_SILU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
-                                          ln_nmr);
+                                          ln_nmr, io_base);
       break;
     case GN_ACT_GELU:
       epilogue_rows<GN_ACT_GELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
-                                          ln_nmr);
+                                          ln_nmr, io_base);
       break;
     case GN_ACT_RELU:
       epilogue_rows<GN_ACT_RELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
-                                          ln_nmr);
+                                          ln_nmr, io_base);
       break;
     case GN_ACT_QUICKGELU:
       epilogue_rows<GN_ACT_QUICKGELU, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
-                                          ln_nmr);
+                                          ln_nmr, io_base);
       break;
     default:
       epilogue_rows<GN_ACT_NONE, CLUSTER>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, stage, row, ln_rstd,
-                                          ln_nmr);
+                                          ln_nmr, io_base);
       break;
   }
 }
@@ -341,10 +449,10 @@ __device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, uint32_t 
 // GEGLU epilogue: accumulator columns come in 128-wide groups [64 values | 64 gates]; out[m, j] = value * gelu(gate).
 __device__ __forceinline__ void epilogue_rows_geglu(const GemmParams& p, uint32_t taddr, int n0, int m, bool valid,
                                                     int cw, const float* s_scale, const float* s_bias, float ln_rstd,
-                                                    float ln_nmr) {
+                                                    float ln_nmr, int row, uint32_t io_base) {
   const EpiParams& e = p.epi;
-  const int n_out_total = e.N >> 1;
   const int nchunks = p.block_n >> 5;  // 16-wide value chunks: 4 per 128-column group
+  const bool rows_needed = valid || p.staged || p.gn_out != nullptr;
 #pragma unroll 1
   for (int ch = cw; ch < nchunks; ch += EPI_COLSPLIT) {
     const int c = ((ch >> 2) << 7) + ((ch & 3) << 4);  // tile column of the value chunk
@@ -353,7 +461,7 @@ __device__ __forceinline__ void epilogue_rows_geglu(const GemmParams& p, uint32_
     tmem_ld_x16(taddr + c + 64, rg);
     tmem_ld_wait();
     const int n = n0 + c;
-    if (!valid || n >= e.N) continue;
+    if (!rows_needed || n >= e.N) continue;
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -362,7 +470,8 @@ __device__ __forceinline__ void epilogue_rows_geglu(const GemmParams& p, uint32_
       const float g = fmaf(__uint_as_float(rg[j]), ln_rstd, fmaf(ln_nmr, s_scale[c + 64 + j], s_bias[c + 64 + j]));
       v[j] = a * gelu_erf_f(g);
     }
-    epi_store<16>(e, v, m, ((n0 + ((ch >> 2) << 7)) >> 1) + ((ch & 3) << 4), n_out_total);
+    const int ct = ((ch >> 2) << 6) + ((ch & 3) << 4);  // column inside the (block_n / 2)-wide output tile
+    epi_finish16(p, v, m, valid, (n0 >> 1) + ct, ct, row, io_base, nullptr);
   }
 }
 
@@ -382,6 +491,470 @@ __device__ __forceinline__ void epilogue_rows_stage(const GemmParams& p, uint32_
   }
 }
 
+// Kernel flavours: one compact epilogue per compile-time activation for the common case (fp16 output staged in shared
+// memory and TMA-stored, residual prefetched by TMA, no split-K), plus one generic kernel with every other feature.
+// The per-chunk loop of the compact flavours is ~200 instructions: it stays resident in the 6 KB L0 instruction cache,
+// whereas the generic loop body (all fallbacks inlined) is fetch-bound at ~1000 cycles per 16-column chunk.
+constexpr int K_GEGLU = 5;    // kinds 0 .. 4 = enum gn_act of the fused activation
+constexpr int K_GENERIC = 6;
+
+template <int KIND>
+__device__ __forceinline__ void fast_epilogue_rows(const GemmParams& p, uint32_t taddr, int n0, int n0_out, int m, int b,
+                                                   bool valid, int cw, const float* s_scale, const float* s_bias,
+                                                   const float* s_cs, int row, float ln_rstd, float ln_nmr,
+                                                   uint32_t io_base) {
+  const EpiParams& e = p.epi;
+  constexpr bool GEGLU = KIND == K_GEGLU;
+  const int n_out_total = GEGLU ? (e.N >> 1) : e.N;
+  const int nchunks = GEGLU ? (p.block_n >> 5) : (p.block_n >> 4);
+  const int lw = p.io_lw;
+  float rs[2] = {0.f, 0.f};
+#pragma unroll 1
+  for (int ch = cw; ch < nchunks; ch += EPI_COLSPLIT) {
+    const int c = GEGLU ? (((ch >> 2) << 7) + ((ch & 3) << 4)) : (ch << 4);   // accumulator column of the chunk
+    const int ct = GEGLU ? (((ch >> 2) << 6) + ((ch & 3) << 4)) : (ch << 4);  // column inside the output tile
+    if (n0 + c >= e.N) break;  // the remaining chunks lie beyond the last column too
+    float v[16];
+    {
+      uint32_t r[16];
+      tmem_ld_x16(taddr + c, r);
+      if constexpr (GEGLU) {
+        uint32_t g[16];
+        tmem_ld_x16(taddr + c + 64, g);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaf(__uint_as_float(r[j]), ln_rstd, fmaf(ln_nmr, s_cs[c + j], s_bias[c + j]));
+          const float gt = fmaf(__uint_as_float(g[j]), ln_rstd, fmaf(ln_nmr, s_cs[c + 64 + j], s_bias[c + 64 + j]));
+          v[j] = a * gelu_erf_f(gt);
+        }
+      } else {
+        tmem_ld_wait();
+        // v = acc * (rstd[m] * scale[n]) + (-mean[m] rstd[m] * colsum[n] + bias[n]); rstd = 1, mean = 0 without a folded LN
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + j);
+          const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + j);
+          const float4 cs = *reinterpret_cast<const float4*>(s_cs + c + j);
+          v[j] = fmaf(__uint_as_float(r[j]), ln_rstd * sc.x, fmaf(ln_nmr, cs.x, bi.x));
+          v[j + 1] = fmaf(__uint_as_float(r[j + 1]), ln_rstd * sc.y, fmaf(ln_nmr, cs.y, bi.y));
+          v[j + 2] = fmaf(__uint_as_float(r[j + 2]), ln_rstd * sc.z, fmaf(ln_nmr, cs.z, bi.z));
+          v[j + 3] = fmaf(__uint_as_float(r[j + 3]), ln_rstd * sc.w, fmaf(ln_nmr, cs.w, bi.w));
+        }
+      }
+    }
+    if constexpr (!GEGLU) {
+      if (e.rowvec) {  // 16-byte aligned by construction (host check)
+        const float4* rv = reinterpret_cast<const float4*>(e.rowvec + (int64_t)b * e.N + n0 + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = __ldg(rv + j);
+          v[4 * j] += t.x;
+          v[4 * j + 1] += t.y;
+          v[4 * j + 2] += t.z;
+          v[4 * j + 3] += t.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = act_ct<KIND>(v[j]);
+    }
+    const uint32_t a0 = io_base + io_offset(lw, row, ct);
+    const uint32_t a1 = io_base + io_offset(lw, row, ct + 8);
+    if (p.res_tma) {
+      const uint4 q0 = lds128(a0), q1 = lds128(a1);
+      const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h0[t]);
+        const float2 g = __half22float2(h1[t]);
+        v[2 * t] = fmaf(e.alpha, v[2 * t], e.beta * f.x);
+        v[2 * t + 1] = fmaf(e.alpha, v[2 * t + 1], e.beta * f.y);
+        v[8 + 2 * t] = fmaf(e.alpha, v[8 + 2 * t], e.beta * g.x);
+        v[8 + 2 * t + 1] = fmaf(e.alpha, v[8 + 2 * t + 1], e.beta * g.y);
+      }
+    } else if (e.alpha != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= e.alpha;
+    }
+    const int nout = n0_out + ct;
+    if (!valid || nout + 16 > n_out_total) {  // zeros outside the tensor (TMA clips them; the GroupNorm pass sums them)
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (!valid || nout + j >= n_out_total) v[j] = 0.f;
+    }
+    uint4 q0, q1;
+    q0.x = pack_half2(v[0], v[1]);
+    q0.y = pack_half2(v[2], v[3]);
+    q0.z = pack_half2(v[4], v[5]);
+    q0.w = pack_half2(v[6], v[7]);
+    q1.x = pack_half2(v[8], v[9]);
+    q1.y = pack_half2(v[10], v[11]);
+    q1.z = pack_half2(v[12], v[13]);
+    q1.w = pack_half2(v[14], v[15]);
+    if (e.rs_out) {
+      const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h0[t]);
+        const float2 g = __half22float2(h1[t]);
+        rs[0] += (f.x + f.y) + (g.x + g.y);
+        rs[1] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(g.x, g.x, fmaf(g.y, g.y, rs[1]))));
+      }
+    }
+    sts128(a0, q0);
+    sts128(a1, q1);
+  }
+  if (e.rs_out && valid) {
+    const int part = (int)blockIdx.x * EPI_COLSPLIT + cw;  // one partial per (n-tile, column share)
+    e.rs_out[(int64_t)m * e.rs_parts + part] = make_float2(rs[0], rs[1]);
+  }
+}
+
+__device__ __forceinline__ void epi_bar_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // epilogue warps only
+}
+
+// After every epilogue warp has staged its part of the tile (et = epilogue thread index 0 .. 255):
+//   * one thread TMA-stores the tile (rows / columns outside the tensor are clipped by the TMA unit);
+//   * GroupNorm statistics of the tile for the consumer's normalisation: every thread sums a column pair over a row
+//     group straight from the staged fp16 values (fixed order), the per-bucket totals go to the global fixed-point
+//     accumulators with 64-bit integer atomics -- integer addition is associative, so the result does not depend on the
+//     order in which the CTAs arrive (bit-reproducible statistics without a grid barrier or a second pass over HBM).
+__device__ __forceinline__ void epilogue_tail(const GemmParams& p, uint32_t io_base, float* s_col, int et, int n0_out,
+                                              int m0, int x0, int y0, int b0) {
+  const EpiParams& e = p.epi;
+  const int n_out_total = e.geglu ? (e.N >> 1) : e.N;
+  const int bn_out = e.geglu ? (p.block_n >> 1) : p.block_n;
+  if (et == 0) trace_stamp(p, 8);
+  fence_proxy_async_smem();  // staged tile (generic-proxy writes) -> visible to the TMA unit (async proxy)
+  epi_bar_sync();
+  if (et == 0) trace_stamp(p, 9);
+  if (p.staged && et == 0) {
+    const int w = 1 << p.io_lw;
+    for (int s = 0; s * w < bn_out && n0_out + s * w < n_out_total; ++s) {
+      const uint32_t src = io_base + (static_cast<uint32_t>(s) << (8 + p.io_lw));
+      if (p.mode == 0) tma_store_2d(&p.tmOut, src, n0_out + s * w, m0);
+      else tma_store_4d(&p.tmOut, src, n0_out + s * w, x0, y0, b0);
+    }
+    tma_store_commit();
+    trace_stamp(p, 10);
+  }
+  if (p.gn_out) {
+    const int ncv = min(bn_out, n_out_total - n0_out);  // valid out columns of this tile (even)
+    const int P = bn_out >> 1;                           // column pairs the tile can hold
+    const int R = p.gn_rows;
+    const int rgs = BLOCK_M / R;
+    const int pair = et % P;
+    const int rg = et / P;
+    const int col = pair << 1;
+    if (rg < rgs && col < ncv) {
+      float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+      for (int r = rg * R; r < rg * R + R; ++r) {
+        uint32_t w32;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w32) : "r"(io_base + io_offset(p.io_lw, r, col)));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w32));
+        s1a += f.x;
+        s2a = fmaf(f.x, f.x, s2a);
+        s1b += f.y;
+        s2b = fmaf(f.y, f.y, s2b);
+      }
+      float4* dst = reinterpret_cast<float4*>(s_col + ((size_t)rg * bn_out + col) * 2);
+      *dst = make_float4(s1a, s2a, s1b, s2b);
+    }
+    epi_bar_sync();
+    if (ncv > 0) {
+      const int bs = p.gn_bucket;
+      const int kb0 = n0_out / bs;
+      const int nbt = (n0_out + ncv - 1) / bs - kb0 + 1;
+      const int n_img = BLOCK_M / p.gn_img_rows;
+      const int rg_per_img = p.gn_img_rows / R;
+      for (int idx = et; idx < nbt * n_img; idx += GEMM_THREADS - 64) {
+        const int k = kb0 + idx % nbt;
+        const int i = idx / nbt;
+        int bimg;
+        if (p.mode == 0) {
+          const int mrow = m0 + i * p.gn_img_rows;
+          if (mrow >= e.M) continue;
+          bimg = mrow / e.rows_per_batch;
+        } else {
+          bimg = b0 + i;
+          if (bimg >= p.Bn) continue;
+        }
+        const int c_lo = max(k * bs, n0_out) - n0_out;
+        const int c_hi = min((k + 1) * bs, n0_out + ncv) - n0_out;
+        float s1 = 0.f, s2 = 0.f;
+        for (int g = i * rg_per_img; g < (i + 1) * rg_per_img; ++g) {
+          const float2* src = reinterpret_cast<const float2*>(s_col + (size_t)g * bn_out * 2);
+          for (int c = c_lo; c < c_hi; ++c) {
+            const float2 t = src[c];
+            s1 += t.x;
+            s2 += t.y;
+          }
+        }
+        const long long f1 = __float2ll_rn(s1 * GN_FIXED_SCALE);
+        const long long f2 = __float2ll_rn(s2 * GN_FIXED_SCALE);
+        unsigned long long* dst = p.gn_out + ((size_t)bimg * p.gn_nb + k) * 2;
+        if (f1 != 0) atomicAdd(dst, static_cast<unsigned long long>(f1));
+        if (f2 != 0) atomicAdd(dst + 1, static_cast<unsigned long long>(f2));
+      }
+    }
+  }
+  if (et == 0) trace_stamp(p, 11);
+  if (p.staged && et == 0) tma_store_wait_read();  // the TMA unit has read the tile: shared memory may be released
+  if (et == 0) trace_stamp(p, 12);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Split-K flavour (K_SPLIT): the S CTAs of a cluster each accumulate one K-slice of the same 128 x block_n tile.
+//   phase 1  every CTA writes its fp32 accumulator (rows inside the tensor only) to the handle's L2-resident workspace,
+//            [rank][tile][chunk][row][16 floats]: 64 contiguous bytes per thread.  (Exchanging the partials through
+//            distributed shared memory measured ~21 B/clk per SM; the L2 path sustains more than twice that.)
+//   sync     ONE cluster barrier (release / acquire at cluster scope orders the global writes);
+//   phase 2  rank r finishes the 16-column chunks r, r + S, ...: sums the S partials in rank order (deterministic) with
+//            L2 loads, applies the compact epilogue, stages fp16 and TMA-stores each chunk as a {16 column, 128 row} box;
+//            GroupNorm statistics over the owned chunks only.  Nobody reads a peer's shared memory, so CTAs exit freely.
+constexpr int K_SPLIT = 7;
+
+__device__ __forceinline__ float* split_ws_ptr(const GemmParams& p, int rank, int ch, int row) {
+  const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+  const size_t ntiles = (size_t)gridDim.x * gridDim.y;
+  return p.ws + ((((size_t)rank * ntiles + tile) * (p.block_n >> 4) + ch) * BLOCK_M + row) * 16;
+}
+
+__device__ __forceinline__ void split_dump(const GemmParams& p, uint32_t taddr, int cw, int rank, int row, bool valid) {
+  const int nchunks = p.block_n >> 4;
+#pragma unroll 1
+  for (int ch = cw; ch < nchunks; ch += EPI_COLSPLIT) {
+    uint32_t r[16];
+    tmem_ld_x16(taddr + (ch << 4), r);
+    tmem_ld_wait();
+    if (valid) {
+      float4* dst = reinterpret_cast<float4*>(split_ws_ptr(p, rank, ch, row));
+#pragma unroll
+      for (int f = 0; f < 4; ++f)
+        __stcg(dst + f, make_float4(__uint_as_float(r[4 * f]), __uint_as_float(r[4 * f + 1]),
+                                    __uint_as_float(r[4 * f + 2]), __uint_as_float(r[4 * f + 3])));
+    }
+  }
+}
+
+__device__ __forceinline__ void split_finish(const GemmParams& p, int rank, int n0, int m, int b,
+                                             bool valid, int cw, const float* s_scale, const float* s_bias,
+                                             const float* s_cs, int row, float ln_rstd, float ln_nmr, uint32_t io_base,
+                                             float* s_col, int et, int m0, int x0, int y0, int b0) {
+  const EpiParams& e = p.epi;
+  const int S = p.splits;
+  const int nchunks = p.block_n >> 4;
+  float rs[2] = {0.f, 0.f};
+#pragma unroll 1
+  for (int ch = rank + S * cw; ch < nchunks; ch += S * EPI_COLSPLIT) {
+    const int c = ch << 4;
+    if (n0 + c >= e.N) break;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    if (valid) {
+      // two partials (eight 16-byte L2 loads) in flight per thread; summed in rank order
+      int sr = 0;
+      for (; sr + 2 <= S; sr += 2) {
+        const float4* s0 = reinterpret_cast<const float4*>(split_ws_ptr(p, sr, ch, row));
+        const float4* s1 = reinterpret_cast<const float4*>(split_ws_ptr(p, sr + 1, ch, row));
+        float4 t[8];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          t[f] = __ldcg(s0 + f);
+          t[4 + f] = __ldcg(s1 + f);
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          v[4 * f] += t[f].x;
+          v[4 * f + 1] += t[f].y;
+          v[4 * f + 2] += t[f].z;
+          v[4 * f + 3] += t[f].w;
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          v[4 * f] += t[4 + f].x;
+          v[4 * f + 1] += t[4 + f].y;
+          v[4 * f + 2] += t[4 + f].z;
+          v[4 * f + 3] += t[4 + f].w;
+        }
+      }
+      if (sr < S) {
+        const float4* s0 = reinterpret_cast<const float4*>(split_ws_ptr(p, sr, ch, row));
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          const float4 t = __ldcg(s0 + f);
+          v[4 * f] += t.x;
+          v[4 * f + 1] += t.y;
+          v[4 * f + 2] += t.z;
+          v[4 * f + 3] += t.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + j);
+      const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + j);
+      const float4 cs = *reinterpret_cast<const float4*>(s_cs + c + j);
+      v[j] = fmaf(v[j], ln_rstd * sc.x, fmaf(ln_nmr, cs.x, bi.x));
+      v[j + 1] = fmaf(v[j + 1], ln_rstd * sc.y, fmaf(ln_nmr, cs.y, bi.y));
+      v[j + 2] = fmaf(v[j + 2], ln_rstd * sc.z, fmaf(ln_nmr, cs.z, bi.z));
+      v[j + 3] = fmaf(v[j + 3], ln_rstd * sc.w, fmaf(ln_nmr, cs.w, bi.w));
+    }
+    if (e.rowvec) {
+      const float4* rv = reinterpret_cast<const float4*>(e.rowvec + (int64_t)b * e.N + n0 + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldg(rv + j);
+        v[4 * j] += t.x;
+        v[4 * j + 1] += t.y;
+        v[4 * j + 2] += t.z;
+        v[4 * j + 3] += t.w;
+      }
+    }
+    if (e.act_pre == GN_ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+    } else if (e.act_pre == GN_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    const uint32_t a0 = io_base + io_offset(4, row, c);
+    const uint32_t a1 = io_base + io_offset(4, row, c + 8);
+    if (p.res_tma) {
+      const uint4 q0 = lds128(a0), q1 = lds128(a1);
+      const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h0[t]);
+        const float2 g = __half22float2(h1[t]);
+        v[2 * t] = fmaf(e.alpha, v[2 * t], e.beta * f.x);
+        v[2 * t + 1] = fmaf(e.alpha, v[2 * t + 1], e.beta * f.y);
+        v[8 + 2 * t] = fmaf(e.alpha, v[8 + 2 * t], e.beta * g.x);
+        v[8 + 2 * t + 1] = fmaf(e.alpha, v[8 + 2 * t + 1], e.beta * g.y);
+      }
+    } else if (e.alpha != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= e.alpha;
+    }
+    const int nout = n0 + c;
+    if (!valid || nout + 16 > e.N) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (!valid || nout + j >= e.N) v[j] = 0.f;
+    }
+    uint4 q0, q1;
+    q0.x = pack_half2(v[0], v[1]);
+    q0.y = pack_half2(v[2], v[3]);
+    q0.z = pack_half2(v[4], v[5]);
+    q0.w = pack_half2(v[6], v[7]);
+    q1.x = pack_half2(v[8], v[9]);
+    q1.y = pack_half2(v[10], v[11]);
+    q1.z = pack_half2(v[12], v[13]);
+    q1.w = pack_half2(v[14], v[15]);
+    if (e.rs_out) {
+      const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h0[t]);
+        const float2 g = __half22float2(h1[t]);
+        rs[0] += (f.x + f.y) + (g.x + g.y);
+        rs[1] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(g.x, g.x, fmaf(g.y, g.y, rs[1]))));
+      }
+    }
+    sts128(a0, q0);
+    sts128(a1, q1);
+  }
+  if (e.rs_out && valid) {
+    const int part = ((int)blockIdx.x * S + rank) * EPI_COLSPLIT + cw;
+    e.rs_out[(int64_t)m * e.rs_parts + part] = make_float2(rs[0], rs[1]);
+  }
+  // ---- store the owned chunks, GroupNorm statistics of the owned chunks
+  if (et == 0) trace_stamp(p, 9);
+  int owned = 0;
+  for (int ch = rank; ch < nchunks && n0 + (ch << 4) < e.N; ch += S) ++owned;
+  fence_proxy_async_smem();
+  epi_bar_sync();
+  if (et == 0) {
+    for (int k = 0; k < owned; ++k) {
+      const int ch = rank + S * k;
+      const uint32_t src = io_base + (static_cast<uint32_t>(ch) << 12);
+      if (p.mode == 0) tma_store_2d(&p.tmOut, src, n0 + (ch << 4), m0);
+      else tma_store_4d(&p.tmOut, src, n0 + (ch << 4), x0, y0, b0);
+    }
+    tma_store_commit();
+    trace_stamp(p, 10);
+  }
+  if (p.gn_out && owned > 0) {
+    const int P = owned << 3;  // column pairs of the owned chunks
+    int R = 16;
+    while ((BLOCK_M / R) * P > GEMM_THREADS - 64) R <<= 1;
+    const int rgs = BLOCK_M / R;
+    const int pair = et % P;
+    const int rg = et / P;
+    const int lcol = pair << 1;                                   // column among the owned chunks
+    const int col = ((rank + S * (lcol >> 4)) << 4) + (lcol & 15);  // column inside the tile
+    if (rg < rgs && n0 + col < e.N) {
+      float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+      for (int r = rg * R; r < rg * R + R; ++r) {
+        uint32_t w32;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w32) : "r"(io_base + io_offset(4, r, col)));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w32));
+        s1a += f.x;
+        s2a = fmaf(f.x, f.x, s2a);
+        s1b += f.y;
+        s2b = fmaf(f.y, f.y, s2b);
+      }
+      *reinterpret_cast<float4*>(s_col + ((size_t)rg * (owned << 4) + lcol) * 2) = make_float4(s1a, s2a, s1b, s2b);
+    }
+    epi_bar_sync();
+    const int bs = p.gn_bucket;
+    const int n_img = BLOCK_M / p.gn_img_rows;
+    const int rg_per_img = p.gn_img_rows / R;
+    // items: (owned chunk k, image i, t-th bucket touching the chunk); a chunk touches at most 9 buckets (bs >= 2)
+    for (int idx = et; idx < owned * n_img * 9; idx += GEMM_THREADS - 64) {
+      const int t = idx % 9;
+      const int i = (idx / 9) % n_img;
+      const int k = idx / (9 * n_img);
+      const int cbeg = n0 + ((rank + S * k) << 4);        // first global column of the chunk
+      const int cend = min(cbeg + 16, e.N);
+      const int bk = cbeg / bs + t;
+      const int lo = max(bk * bs, cbeg), hi = min((bk + 1) * bs, cend);
+      if (lo >= hi) continue;
+      int bimg;
+      if (p.mode == 0) {
+        const int mrow = m0 + i * p.gn_img_rows;
+        if (mrow >= e.M) continue;
+        bimg = mrow / e.rows_per_batch;
+      } else {
+        bimg = b0 + i;
+        if (bimg >= p.Bn) continue;
+      }
+      float s1 = 0.f, s2 = 0.f;
+      for (int g = i * rg_per_img; g < (i + 1) * rg_per_img; ++g) {
+        const float2* src = reinterpret_cast<const float2*>(s_col + (size_t)g * (owned << 4) * 2) + (k << 4);
+        for (int cc = lo - cbeg; cc < hi - cbeg; ++cc) {
+          const float2 tt = src[cc];
+          s1 += tt.x;
+          s2 += tt.y;
+        }
+      }
+      const long long f1 = __float2ll_rn(s1 * GN_FIXED_SCALE);
+      const long long f2 = __float2ll_rn(s2 * GN_FIXED_SCALE);
+      unsigned long long* dst = p.gn_out + ((size_t)bimg * p.gn_nb + bk) * 2;
+      if (f1 != 0) atomicAdd(dst, static_cast<unsigned long long>(f1));
+      if (f2 != 0) atomicAdd(dst + 1, static_cast<unsigned long long>(f2));
+    }
+  }
+  if (et == 0) tma_store_wait_read();
+}
+
+template <int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -394,37 +967,56 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   const int b_stage_bytes = block_n * BLOCK_K * 2;
 
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + stages * A_STAGE_BYTES;
-  // the fp32 staging tile of the split-K cluster reduction aliases the operand ring and may be larger than it
-  int ring_bytes = stages * (A_STAGE_BYTES + b_stage_bytes);
-  if (p.splits > 1 && block_n * BLOCK_M * 4 > ring_bytes) ring_bytes = block_n * BLOCK_M * 4;
-  float* s_scale = reinterpret_cast<float*>(smem + ring_bytes);
-  float* s_bias = s_scale + 256;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + 256);
+  uint8_t* smem_b = smem + (p.halo ? HALO_STAGES * HALO_STAGE : stages * A_STAGE_BYTES);
+  // tail region (offsets computed by the host, see smem_layout): per-column scale / bias, GroupNorm column partials,
+  // mbarriers.  The fp32 staging tile of the split-K cluster reduction aliases the operand ring; the fp16 output staging
+  // buffer aliases it too unless it must coexist with the main loop (residual prefetch) or with the split-K partials.
+  float* s_scale = reinterpret_cast<float*>(smem + p.tail_off);
+  float* s_bias = s_scale + TAIL_SCALE_FLOATS;
+  float* s_cs = s_bias + TAIL_SCALE_FLOATS;
+  float* s_col = s_cs + TAIL_SCALE_FLOATS;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_col + TAIL_COL_FLOATS);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* res_full_bar = tmem_full_bar + 1;
+  uint64_t* afull_bar = res_full_bar + 1;   // halo mode: A ring (HALO_STAGES) full / empty
+  uint64_t* aempty_bar = afull_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
+  const uint32_t io_base = smem_u32(smem) + p.io_off;
 
   const int n0 = blockIdx.x * block_n;
+  const int n0_out = p.epi.geglu ? (n0 >> 1) : n0;
+  const bool mcast_on = (KIND < K_GENERIC) && p.mcast > 1;
   if (threadIdx.x == 0) trace_stamp(p, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     tma_prefetch_desc(&p.tmB);
+    if (p.staged) tma_prefetch_desc(&p.tmOut);
+    if (p.res_tma) tma_prefetch_desc(&p.tmRes);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      // with W multicast a stage is free only when the MMA warps of ALL CTAs of the cluster have consumed it
+      mbar_init(&empty_bar[s], mcast_on ? p.mcast : 1);
     }
     mbar_init(tmem_full_bar, 1);
+    mbar_init(res_full_bar, 1);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&afull_bar[s], 1);
+      mbar_init(&aempty_bar[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // peers multicast into this CTA's shared memory and arrive on its barriers: they must see them initialised
+  if (mcast_on) cluster_arrive();
   // Everything above touched only this CTA's shared / tensor memory.  Let the next kernel's CTAs be scheduled, then wait
   // for the previous kernel in the stream before the first global-memory access (programmatic dependent launch).
   pdl_trigger();
   pdl_wait();
+  if (mcast_on) cluster_wait();  // (arrived above: complete long before the previous kernel has drained)
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace_stamp(p, 1);
 
@@ -448,6 +1040,70 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
+      if (KIND == K_SPLIT && p.res_tma) {
+        // residual boxes ({16 columns, 128 rows}) of the chunks this rank will finish -> staging buffer
+        const int rank = (int)cg::this_cluster().block_rank();
+        const int nchunks = block_n >> 4;
+        int owned = 0;
+        for (int ch = rank; ch < nchunks && n0 + (ch << 4) < p.epi.N; ch += p.splits) ++owned;
+        if (owned > 0) {
+          mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(owned) << 12);
+          for (int k = 0; k < owned; ++k) {
+            const int ch = rank + p.splits * k;
+            uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(ch) << 12);
+            if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0 + (ch << 4), m0);
+            else tma_load_4d(dst, &p.tmRes, res_full_bar, n0 + (ch << 4), x0, y0, b0);
+          }
+        }
+      } else if (p.res_tma && !p.res_late) {
+        // residual tile -> staging buffer, in flight while the main loop runs
+        const int w = 1 << p.io_lw;
+        const int bn_out = p.epi.geglu ? (block_n >> 1) : block_n;
+        const int n_out_total = p.epi.geglu ? (p.epi.N >> 1) : p.epi.N;
+        int nsub = 0;
+        for (int s = 0; s * w < bn_out && n0_out + s * w < n_out_total; ++s) ++nsub;
+        mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(nsub) << (8 + p.io_lw));
+        for (int s = 0; s < nsub; ++s) {
+          uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(s) << (8 + p.io_lw));
+          if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0_out + s * w, m0);
+          else tma_load_4d(dst, &p.tmRes, res_full_bar, n0_out + s * w, x0, y0, b0);
+        }
+      }
+      if (p.halo) {
+        // ---- halo mode: one A load per group of k-blocks (the 9 taps of a channel block / one extra 1x1 block)
+        const int nk_halo = 9 * p.halo_ncb;
+        const int cp = p.halo_ncb * BLOCK_K;
+        int ia = 0;
+        for (int it = 0; it < num_it; ++it) {
+          const int kb = kb_begin + it;
+          const bool is_halo = kb < nk_halo;
+          const int grp = kb / 3, ky = kb - grp * 3;  // group = (cb, kx)
+          const int cbh = grp / 3, kx = grp - cbh * 3;
+          if (it == 0 || !is_halo || ky == 0) {
+            const int sa = ia % HALO_STAGES;
+            mbar_wait(&aempty_bar[sa], ((ia / HALO_STAGES) & 1) ^ 1);
+            if (is_halo) {
+              mbar_arrive_expect_tx(&afull_bar[sa], HALO_BYTES);
+              tma_load_4d(smem_a + sa * HALO_STAGE, &p.tmA[0], &afull_bar[sa], cbh * BLOCK_K, x0 - 1 + kx, y0 - 1, b0);
+            } else {
+              int e = kb - nk_halo, sg = 0;
+              while (e >= p.segs[sg].nblk) {
+                e -= p.segs[sg].nblk;
+                ++sg;
+              }
+              mbar_arrive_expect_tx(&afull_bar[sa], A_STAGE_BYTES);
+              tma_load_4d(smem_a + sa * HALO_STAGE, &p.tmA[p.segs[sg].map], &afull_bar[sa], e * BLOCK_K, x0, y0, b0);
+            }
+            ++ia;
+          }
+          const int s = it % stages;
+          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], b_stage_bytes);
+          const int wcol = is_halo ? ((ky * 3 + kx) * cp + cbh * BLOCK_K) : (9 * cp + (kb - nk_halo) * BLOCK_K);
+          tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], wcol, n0);
+          if (it == 0) trace_stamp(p, 2);
+        }
+      } else {
       int seg = 0, seg_start = 0;
       if (p.mode == 1) {
         while (kb_begin >= seg_start + p.segs[seg].nblk) {
@@ -474,14 +1130,74 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             ++seg;
           }
         }
-        tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+        if (mcast_on) {
+          // this CTA fetches its 1 / mcast slice of the W tile for every CTA of the cluster
+          const int slice_rows = block_n / p.mcast;
+          const int r = (int)cluster_ctarank();
+          tma_load_2d_mcast(smem_b + s * b_stage_bytes + r * slice_rows * (BLOCK_K * 2), &p.tmB, &full_bar[s],
+                            kb * BLOCK_K, n0 + r * slice_rows, static_cast<uint16_t>((1u << p.mcast) - 1u));
+        } else {
+          tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+        }
         if (it == 0) trace_stamp(p, 2);
+      }
+      }  // !halo
+      if (KIND != K_SPLIT && p.res_tma && p.res_late) {
+        // late residual prefetch: the staging buffer lies over the first operand stages; wait until the MMAs that read
+        // them last have completed (same wait the producer would do before refilling them), then fetch the residual tile
+        const int w = 1 << p.io_lw;
+        const int bn_out = p.epi.geglu ? (block_n >> 1) : block_n;
+        const int n_out_total = p.epi.geglu ? (p.epi.N >> 1) : p.epi.N;
+        const int io_bytes = bn_out * BLOCK_M * 2;
+        const int a_bytes = p.halo ? HALO_STAGES * HALO_STAGE : stages * A_STAGE_BYTES;
+        int need = (io_bytes <= a_bytes && !p.halo) ? (io_bytes + A_STAGE_BYTES - 1) / A_STAGE_BYTES : stages;
+        if (need > stages) need = stages;
+        for (int s = 0; s < need; ++s) {
+          int itv = num_it - (num_it % stages) + s;  // first virtual iteration >= num_it that would reuse stage s
+          if (itv < num_it) itv += stages;
+          mbar_wait(&empty_bar[s], ((itv / stages) & 1) ^ 1);
+        }
+        int nsub = 0;
+        for (int sidx = 0; sidx * w < bn_out && n0_out + sidx * w < n_out_total; ++sidx) ++nsub;
+        mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(nsub) << (8 + p.io_lw));
+        for (int sidx = 0; sidx < nsub; ++sidx) {
+          uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(sidx) << (8 + p.io_lw));
+          if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0_out + sidx * w, m0);
+          else tma_load_4d(dst, &p.tmRes, res_full_bar, n0_out + sidx * w, x0, y0, b0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer
       const uint32_t idesc = umma_idesc_f16(block_n, 0, 0);
+      if (p.halo) {
+        const int nk_halo = 9 * p.halo_ncb;
+        int ia = 0;
+        for (int it = 0; it < num_it; ++it) {
+          const int kb = kb_begin + it;
+          const bool is_halo = kb < nk_halo;
+          const int ky = kb % 3;
+          const int sa = ia % HALO_STAGES;
+          if (it == 0 || !is_halo || ky == 0) mbar_wait(&afull_bar[sa], (ia / HALO_STAGES) & 1);
+          const int s = it % stages;
+          mbar_wait(&full_bar[s], (it / stages) & 1);
+          tc_fence_after();
+          if (it == 0) trace_stamp(p, 3);
+          // vertical tap ky = the window that starts ky image rows (ky whole swizzle atoms) into the strip
+          const uint64_t a_desc =
+              umma_desc_sw128(smem_u32(smem_a + sa * HALO_STAGE) + (is_halo ? ky * (HALO_W * 128) : 0), 1024, 0);
+          const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * b_stage_bytes), 1024, 0);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (it == num_it - 1 || !is_halo || ky == 2) {
+            umma_commit(&aempty_bar[sa]);
+            ++ia;
+          }
+        }
+      } else
       for (int it = 0; it < num_it; ++it) {
         const int s = it % stages;
         const uint32_t ph = (it / stages) & 1;
@@ -495,7 +1211,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
           // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
           umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[s]);
+        if (mcast_on) umma_commit_mcast(&empty_bar[s], static_cast<uint16_t>((1u << p.mcast) - 1u));
+        else umma_commit(&empty_bar[s]);
       }
       umma_commit(tmem_full_bar);
       trace_stamp(p, 4);
@@ -505,6 +1222,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     const int q = warp & 3;                // TMEM lane quadrant this warp may access
     const int cw = (warp - 2) >> 2;        // which share of the column chunks
     const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
     int m;
     bool valid;
     if (p.mode == 0) {
@@ -519,15 +1237,63 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       m = (gb * p.Ho + gy) * p.Wo + gx;
     }
     const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
+    if constexpr (KIND == K_SPLIT) {
+      for (int i = et; i < block_n; i += GEMM_THREADS - 64) {
+        const int n = n0 + i;
+        const bool in = n < p.epi.N;
+        const bool ln = p.epi.ln_stats != nullptr;
+        s_scale[i] = (p.epi.scale && !ln && in) ? __ldg(p.epi.scale + n) : 1.0f;
+        s_bias[i] = (p.epi.bias && in) ? __ldg(p.epi.bias + n) : 0.0f;
+        s_cs[i] = (ln && in) ? __ldg(p.epi.scale + n) : 0.0f;
+      }
+      epi_bar_sync();
+      if (p.epi.ln_stats && valid) ln_row(p.epi, m, ln_rstd, ln_nmr);
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      if (threadIdx.x == 64) trace_stamp(p, 5);
+      split_dump(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16), cw, (int)cg::this_cluster().block_rank(), row,
+                 valid);
+      tc_fence_before();
+      if (threadIdx.x == 64) trace_stamp(p, 6);
+    } else if constexpr (KIND != K_GENERIC) {
+      // ---- compact flavour: staged fp16 output, compile-time activation, no split-K
+      for (int i = et; i < block_n; i += GEMM_THREADS - 64) {
+        const int n = n0 + i;
+        const bool in = n < p.epi.N;
+        const bool ln = p.epi.ln_stats != nullptr;  // the "scale" slot then carries the folded LayerNorm's column sums
+        s_scale[i] = (p.epi.scale && !ln && in) ? __ldg(p.epi.scale + n) : 1.0f;
+        s_bias[i] = (p.epi.bias && in) ? __ldg(p.epi.bias + n) : 0.0f;
+        s_cs[i] = (ln && in) ? __ldg(p.epi.scale + n) : 0.0f;
+      }
+      epi_bar_sync();
+      if (p.epi.ln_stats && valid) ln_row(p.epi, m, ln_rstd, ln_nmr);
+      if (p.res_tma) mbar_wait(res_full_bar, 0);
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      if (threadIdx.x == 64) trace_stamp(p, 5);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      fast_epilogue_rows<KIND>(p, taddr, n0, n0_out, m, b, valid, cw, s_scale, s_bias, s_cs, row, ln_rstd, ln_nmr,
+                               io_base);
+      epilogue_tail(p, io_base, s_col, et, n0_out, m0, x0, y0, b0);
+      tc_fence_before();
+      if (threadIdx.x == 64) trace_stamp(p, 6);
+    } else {
     // stage the tile's per-column scale / bias once (identity when absent) — read back as broadcast float4s
-    for (int i = threadIdx.x - 64; i < block_n; i += GEMM_THREADS - 64) {
+    for (int i = et; i < block_n; i += GEMM_THREADS - 64) {
       const int n = n0 + i;
       s_scale[i] = (p.epi.scale && n < p.epi.N) ? __ldg(p.epi.scale + n) : 1.0f;
       s_bias[i] = (p.epi.bias && n < p.epi.N) ? __ldg(p.epi.bias + n) : 0.0f;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // epilogue warps only
+    if (p.gn_out && p.splits > 1) {
+      // split-K + GroupNorm statistics: every CTA of the cluster finishes only some chunks of the tile; the others must
+      // read as zeros in its (dedicated) staging buffer
+      const int io_bytes = block_n * BLOCK_M * 2;
+      for (int i = et * 16; i < io_bytes; i += (GEMM_THREADS - 64) * 16) sts128(io_base + i, make_uint4(0, 0, 0, 0));
+    }
+    epi_bar_sync();
     // folded LayerNorm: (rstd, -mean * rstd) of this row from the producer's partials, fetched while the MMAs run
     if (p.epi.ln_stats && valid) ln_row(p.epi, m, ln_rstd, ln_nmr);
+    if (p.res_tma) mbar_wait(res_full_bar, 0);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     if (threadIdx.x == 64) trace_stamp(p, 5);
@@ -535,15 +1301,53 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     if (p.splits > 1) {
       // all MMAs have completed (tmem_full), so the operand ring is free: reuse it as the fp32 staging tile
       epilogue_rows_stage(p, taddr, cw, reinterpret_cast<float*>(smem), row);
-    } else if (p.epi.geglu) {
-      epilogue_rows_geglu(p, taddr, n0, m, valid, cw, s_scale, s_bias, ln_rstd, ln_nmr);
     } else {
-      epilogue_dispatch<false>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, nullptr, row, ln_rstd, ln_nmr);
+      if (p.epi.geglu) {
+        epilogue_rows_geglu(p, taddr, n0, m, valid, cw, s_scale, s_bias, ln_rstd, ln_nmr, row, io_base);
+      } else {
+        epilogue_dispatch<false>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, nullptr, row, ln_rstd, ln_nmr,
+                                 io_base);
+      }
+      if (p.staged || p.gn_out) epilogue_tail(p, io_base, s_col, et, n0_out, m0, x0, y0, b0);
     }
     tc_fence_before();
     if (threadIdx.x == 64) trace_stamp(p, 6);
+    }  // generic flavour
   }
-  if (p.splits > 1) {
+  if constexpr (KIND == K_SPLIT) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();  // every CTA's partial is in the workspace (barrier.cluster: release / acquire over global memory)
+    if (threadIdx.x == 64) trace_stamp(p, 8);
+    if (warp >= 2) {
+      const int q = warp & 3;
+      const int cw = (warp - 2) >> 2;
+      const int row = q * 32 + lane;
+      int m;
+      bool valid;
+      if (p.mode == 0) {
+        m = m0 + row;
+        valid = m < p.epi.M;
+      } else {
+        const int x = row % p.bw;
+        const int y = (row / p.bw) % p.bh;
+        const int bb = row / (p.bw * p.bh);
+        const int gx = x0 + x, gy = y0 + y, gb = b0 + bb;
+        valid = (gx < p.Wo) && (gy < p.Ho) && (gb < p.Bn);
+        m = (gb * p.Ho + gy) * p.Wo + gx;
+      }
+      const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
+      const int rank = (int)cluster.block_rank();
+      if (p.res_tma) {
+        int owned = 0;
+        for (int ch = rank; ch < (block_n >> 4) && n0 + (ch << 4) < p.epi.N; ch += p.splits) ++owned;
+        if (owned > 0) mbar_wait(res_full_bar, 0);
+      }
+      split_finish(p, rank, n0, m, b, valid, cw, s_scale, s_bias, s_cs, row, ln_rstd, ln_nmr, io_base, s_col,
+                   threadIdx.x - 64, m0, x0, y0, b0);
+    }
+    if (threadIdx.x == 64) trace_stamp(p, 11);
+  }
+  if (KIND == K_GENERIC && p.splits > 1) {
     // ---- split-K reduction across the cluster (gridDim.z == cluster size): no workspace, no second kernel
     cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();
@@ -566,7 +1370,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       }
       const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
       epilogue_dispatch<true>(p, 0, n0, m, b, valid, cw, s_scale, s_bias, reinterpret_cast<const float*>(smem), row,
-                              ln_rstd, ln_nmr);
+                              ln_rstd, ln_nmr, io_base);
+      if (p.gn_out) epilogue_tail(p, io_base, s_col, threadIdx.x - 64, n0_out, m0, x0, y0, b0);
     }
     cluster.sync();  // peers may still be reading this CTA's staging tile
   }
@@ -575,6 +1380,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (mcast_on) {
+    // no CTA may exit while a peer's tcgen05.commit can still arrive on its barriers
+    cluster_arrive();
+    cluster_wait();
+  }
   if (threadIdx.x == 0) trace_stamp(p, 7);
 }
 
@@ -582,13 +1392,65 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
 
 struct TileChoice {
   int block_n, splits, stages, tmem_cols;
+  int mcast = 1;  // W-tile multicast cluster size along the M tiles (compact non-split flavours)
 };
 
-static int smem_bytes_for(int block_n, int stages, int splits) {
-  int ring = stages * (A_STAGE_BYTES + block_n * BLOCK_K * 2);
+// What the epilogue of this launch may do (decided per call from the tensors' alignment and the gn_epilogue request).
+struct OutGeom {
+  int rank = 2;          // 2: out[M][N_out];  4: out[B][Ho][Wo][N_out]
+  uint64_t dims[4];      // innermost first; dims[0] = N_out
+  uint64_t ostr[3];      // byte strides of the output (dims 1 ..)
+  uint64_t rstr[3];      // byte strides of the residual
+  uint32_t box_rows[3];  // box extents of dims 1 .. (their product is BLOCK_M)
+  const void* out = nullptr;
+  const void* res = nullptr;
+  bool stage_ok = false;  // the fp16 output can be written by a TMA store
+  bool res_ok = false;    // the residual can be prefetched by TMA
+  bool gn = false;        // GroupNorm statistics requested
+  bool geglu = false;
+  bool split_fast = false;  // a split-K launch of this problem can use the compact K_SPLIT flavour
+  bool mcast_ok = false;    // a non-split launch can use a compact flavour (and therefore W-tile multicast)
+  bool halo = false;        // halo-mode convolution: the A ring holds HALO_STAGES halo tiles
+  bool res_late = false;    // (set per candidate) alias the residual staging buffer with the operand ring
+  int img_rows = 0;       // rows of one image inside a 128-row tile (GroupNorm statistics); 0: layout unsupported
+};
+
+struct SmemLayout {
+  int io_off, tail_off, total;
+  bool staged, res_tma, res_late, io_needed;
+};
+
+// rows per row group of the GroupNorm column pass for a bn_out-wide output tile, 0 if the tile cannot be handled
+static int gn_rows_for(int bn_out, int img_rows) {
+  for (int R = 16; R <= BLOCK_M; R <<= 1)
+    if ((BLOCK_M / R) * (bn_out / 2) <= GEMM_THREADS - 64 && R <= img_rows) return R;
+  return 0;
+}
+
+static SmemLayout smem_layout(int block_n, int stages, int splits, const OutGeom& og) {
+  SmemLayout L;
+  const int bn_out = og.geglu ? block_n / 2 : block_n;
+  int ring = og.halo ? HALO_STAGES * HALO_STAGE + stages * block_n * BLOCK_K * 2
+                     : stages * (A_STAGE_BYTES + block_n * BLOCK_K * 2);
   const int stage_tile = block_n * BLOCK_M * 4;  // fp32 staging tile of the cluster split-K reduction (aliases the ring)
-  if (splits > 1 && stage_tile > ring) ring = stage_tile;
-  return ring + 2 * 256 * 4 + (2 * stages + 1) * 8 + 16 + 1024;
+  const bool split_fast = splits > 1 && og.split_fast;
+  if (splits > 1 && !split_fast && stage_tile > ring) ring = stage_tile;
+  L.staged = og.stage_ok && (splits == 1 || split_fast);
+  L.res_tma = L.staged && og.res_ok;
+  L.io_needed = L.staged || og.gn;
+  // residual prefetch: a dedicated staging buffer lets it run during the whole main loop, but costs operand stages; the
+  // caller asks for the aliased ("late") variant when the ring would otherwise get shallower than the K loop can use
+  L.res_late = L.res_tma && og.res_late && splits == 1 && !og.halo;
+  const bool dedicated = (L.res_tma && !L.res_late) || (og.gn && splits > 1 && !split_fast);
+  const int io_bytes = L.io_needed ? bn_out * BLOCK_M * 2 : 0;
+  L.io_off = dedicated ? ring : 0;
+  L.tail_off = dedicated ? ring + io_bytes : (ring > io_bytes ? ring : io_bytes);
+  L.total = L.tail_off + (3 * TAIL_SCALE_FLOATS + TAIL_COL_FLOATS) * 4 + (2 * stages + 2 + 8) * 8 + 16 + 1024;
+  return L;
+}
+
+static int smem_bytes_for(int block_n, int stages, int splits, const OutGeom& og) {
+  return smem_layout(block_n, stages, splits, og).total;
 }
 
 constexpr int MAX_CLUSTER_SPLITS = 8;  // portable cluster size limit
@@ -596,9 +1458,9 @@ constexpr int MAX_CLUSTER_SPLITS = 8;  // portable cluster size limit
 constexpr int SMEM_OCC1 = 200 * 1024;  // one CTA per SM: deep operand ring
 constexpr int SMEM_OCC2 = 112 * 1024;  // two CTAs per SM: one CTA's epilogue / set-up overlaps the other's main loop
 
-static int stages_for(int block_n, int splits, int kb_per, int budget) {
-  int st = 8;
-  while (st > 2 && smem_bytes_for(block_n, st, splits) > budget) --st;
+static int stages_for(int block_n, int splits, int kb_per, int budget, const OutGeom& og) {
+  int st = og.halo ? 12 : 8;
+  while (st > 2 && smem_bytes_for(block_n, st, splits, og) > budget) --st;
   if (st > kb_per) st = kb_per < 2 ? 2 : kb_per;
   return st;
 }
@@ -609,7 +1471,7 @@ struct Candidate {
 };
 
 static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblocks, bool geglu, bool allow_split,
-                          Candidate* out, int max_out, int rs_capacity = 0) {
+                          Candidate* out, int max_out, int rs_capacity, const OutGeom& og) {
   static const int kCand[] = {256, 224, 192, 160, 128, 96, 80, 64, 48, 32, 16};
   const int sms = h->num_sms;
   std::vector<Candidate> all;
@@ -618,6 +1480,7 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
     if (h->force_block_n && bn != h->force_block_n) continue;
     if (!h->force_block_n && bn > gn::round_up(N, 16)) continue;
     const int tiles_n = gn::ceil_div(N, bn);
+    if (og.gn && gn_rows_for(geglu ? bn / 2 : bn, og.img_rows) == 0) continue;  // GroupNorm column pass cannot cover it
     int max_splits = 1;
     if (allow_split && !geglu) {
       max_splits = num_kblocks / 4;  // keep >= 4 k-blocks per split
@@ -629,10 +1492,14 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
       const int kb_per = gn::ceil_div(num_kblocks, sp);
       if ((sp - 1) * kb_per >= num_kblocks) continue;  // an empty split
       if (rs_capacity > 0 && tiles_n * sp * EPI_COLSPLIT > rs_capacity) continue;  // row-statistics partials must fit
+      if (sp > 1 && og.split_fast &&
+          (int64_t)sp * tiles_n * tiles_m * bn * BLOCK_M * 4 > h->workspace_bytes) continue;  // partials would not fit
       const int64_t ctas = (int64_t)tiles_m * tiles_n * sp;
       for (int occ = 1; occ <= 2; ++occ) {
-        if (h->force_occupancy && occ != h->force_occupancy) continue;
-        if (occ == 2 && smem_bytes_for(bn, 2, sp) > SMEM_OCC2) continue;
+        const bool occ2_fits = smem_bytes_for(bn, 2, sp, og) <= SMEM_OCC2;
+        if (h->force_occupancy == 1 && occ != 1) continue;
+        if (h->force_occupancy == 2 && occ == 1 && occ2_fits) continue;  // forced 2 CTAs/SM, unless that cannot fit
+        if (occ == 2 && !occ2_fits) continue;
         const double t_mma = 2.0 * bn;
         const double t_ld = (128.0 + bn) * 128.0 / 46.0;
         const double t_kb = t_mma > t_ld ? t_mma : t_ld;
@@ -641,7 +1508,8 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
         double lat = 25.0 * bn + 3000.0;
         if (sp > 1) lat += 2500.0 + 8.0 * bn;   // two cluster barriers + DSMEM reduction
         if (sp == 5 || sp == 7) lat += 2000.0;  // cluster sizes that pack the 18-SM GPCs badly
-        const int st = stages_for(bn, sp, kb_per, occ == 2 ? SMEM_OCC2 : SMEM_OCC1);
+        const int st = stages_for(bn, sp, kb_per, occ == 2 ? SMEM_OCC2 : SMEM_OCC1, og);
+        if (smem_bytes_for(bn, st, sp, og) > 227 * 1024) continue;
         double mainloop = per_sm * kb_per * t_kb;
         if (occ * st < 4) mainloop *= 1.3;  // too few loads in flight to cover the TMA round trip
         Candidate c;
@@ -656,6 +1524,24 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
         for (const Candidate& o : all)
           if (o.tc.block_n == bn && o.tc.splits == sp && o.tc.stages == st) dup = true;
         if (!dup) all.push_back(c);
+        // W-tile multicast variants: the m-tiles of one n-tile form clusters of 2 / 4 CTAs (compact flavours only)
+        if (!dup && sp == 1 && og.mcast_ok && h->mcast_max > 1) {
+          bool forced_applied = false;
+          for (int mc = 2; mc <= h->mcast_max && mc <= 4; mc <<= 1) {
+            if (h->force_mcast && mc != h->force_mcast) continue;
+            if ((tiles_m % mc) != 0 || (bn % (8 * mc)) != 0) continue;
+            Candidate m = c;
+            m.tc.mcast = mc;
+            m.cost = c.cost * (mc == 2 ? 0.97 : 0.95);
+            if (h->force_mcast) {
+              all.back() = m;  // forced: replaces the plain variant
+              forced_applied = true;
+            } else {
+              all.push_back(m);
+            }
+          }
+          (void)forced_applied;
+        }
       }
     }
   }
@@ -667,7 +1553,7 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
     if (n_out >= max_out) break;
     int same_bn = 0;
     for (int i = 0; i < n_out; ++i) same_bn += out[i].tc.block_n == c.tc.block_n;
-    if (same_bn >= 3) continue;
+    if (same_bn >= 4) continue;
     out[n_out++] = c;
   }
   return n_out;
@@ -679,12 +1565,12 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
 //     (128 + bn) * 128 / 46 [operand feed]) cycles of that SM, whichever CTA it belongs to;
 //   * every CTA pays ~3000 clk of latency (set-up, first TMA round trip, exit) plus ~25 clk per accumulator column of
 //     epilogue; with two co-resident CTAs that latency overlaps the neighbour's main loop.
-static TileChoice choose_tiles(const gn_handle* h, int tiles_m, int N, int num_kblocks, bool geglu, bool allow_split,
-                               int rs_capacity) {
+static bool choose_tiles(const gn_handle* h, int tiles_m, int N, int num_kblocks, bool geglu, bool allow_split,
+                         int rs_capacity, const OutGeom& og, TileChoice* tc) {
   Candidate c[1];
-  if (candidate_list(h, tiles_m, N, num_kblocks, geglu, allow_split, c, 1, rs_capacity) < 1)
-    return TileChoice{128, 1, 4, 128};
-  return c[0].tc;
+  if (candidate_list(h, tiles_m, N, num_kblocks, geglu, allow_split, c, 1, rs_capacity, og) < 1) return false;
+  *tc = c[0].tc;
+  return true;
 }
 
 static int fill_epilogue(gn_handle* h, EpiParams& e, const gn_epilogue* epi, void* out, int64_t ldo, int M, int N,
@@ -733,15 +1619,66 @@ static int fill_epilogue(gn_handle* h, EpiParams& e, const gn_epilogue* epi, voi
   return GN_OK;
 }
 
+// Output geometry shared by gn_linear (rank 2) and gn_conv2d (rank 4): what may be staged / prefetched by TMA, and the
+// GroupNorm-statistics request of the epilogue.  `p.gn_*` device fields that do not depend on the tile are set here.
+static int fill_out_geom(gn_handle* h, GemmParams& p, OutGeom& og, const gn_epilogue* epi, const void* out) {
+  const EpiParams& e = p.epi;
+  const int n_out = e.geglu ? e.N / 2 : e.N;
+  og.geglu = e.geglu != 0;
+  og.out = out;
+  og.res = e.residual;
+  og.dims[0] = (uint64_t)n_out;
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  og.stage_ok = h->staged_epilogue && !e.out32 && (e.ldo % 8) == 0 && aligned16(out);
+  og.res_ok = og.stage_ok && e.residual && (e.ldr % 8) == 0 && aligned16(e.residual);
+  og.split_fast = h->fast_epilogue && h->workspace && h->workspace_bytes >= (64 << 20) && og.stage_ok && (!e.residual || og.res_ok) && e.act_post == GN_ACT_NONE && !e.geglu &&
+                  (e.act_pre == GN_ACT_NONE || e.act_pre == GN_ACT_SILU || e.act_pre == GN_ACT_RELU) &&
+                  (!e.rowvec || ((e.N % 4) == 0 && (reinterpret_cast<uintptr_t>(e.rowvec) & 15) == 0));
+  og.mcast_ok = h->fast_epilogue && og.stage_ok && (!e.residual || og.res_ok) && e.act_post == GN_ACT_NONE &&
+                (!e.rowvec || ((e.N % 4) == 0 && (reinterpret_cast<uintptr_t>(e.rowvec) & 15) == 0)) &&
+                e.act_pre >= GN_ACT_NONE && e.act_pre <= GN_ACT_QUICKGELU && !(e.geglu && e.act_pre != GN_ACT_NONE);
+  og.gn = false;
+  p.gn_out = nullptr;
+  if (epi && epi->gnstats_out) {
+    const int bs = epi->gn_bucket;
+    GN_CHECK_ARG(h, !e.out32, "gnstats_out needs an fp16 output");
+    GN_CHECK_ARG(h, bs >= 2 && (bs % 2) == 0 && (n_out % bs) == 0 && (n_out % 2) == 0,
+                 "gnstats_out: bucket %d must be even and divide the %d output columns", bs, n_out);
+    int img_rows = 0;
+    if (p.mode == 0) {
+      const int rpb = e.rows_per_batch;
+      if (rpb >= BLOCK_M && (rpb % BLOCK_M) == 0) img_rows = BLOCK_M;
+      else if (rpb >= 16 && rpb < BLOCK_M && (BLOCK_M % rpb) == 0) img_rows = rpb;
+    } else {
+      img_rows = p.bw * p.bh;
+      if (img_rows < 16) img_rows = 0;
+    }
+    GN_CHECK_ARG(h, img_rows > 0, "gnstats_out: %d rows per image cannot be tiled for the statistics pass",
+                 p.mode == 0 ? e.rows_per_batch : p.bw * p.bh);
+    og.gn = true;
+    og.img_rows = img_rows;
+    p.gn_out = static_cast<unsigned long long*>(epi->gnstats_out);
+    p.gn_bucket = bs;
+    p.gn_nb = n_out / bs;
+    p.gn_img_rows = img_rows;
+    p.gn_stat_images = p.mode == 0 ? gn::ceil_div(e.M, e.rows_per_batch) : p.Bn;
+  }
+  return GN_OK;
+}
+
 static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int tiles_m, const void* W, int64_t ktot,
-                         cudaStream_t stream) {
+                         const OutGeom& og, cudaStream_t stream) {
   const int N = p.epi.N;
   p.block_n = tc.block_n;
   p.splits = tc.splits;
   p.stages = tc.stages;
   p.tmem_cols = tc.tmem_cols;
   p.kb_per_split = gn::ceil_div(p.num_kblocks, tc.splits);
-  p.ws = nullptr;
+  p.ws = static_cast<float*>(h->workspace);
+  {
+    static const char* dbg_env = getenv("GENIMA_B200_DBG");
+    p.dbg = dbg_env ? atoi(dbg_env) : 0;
+  }
   p.trace = static_cast<unsigned long long*>(h->gemm_trace);
   if (p.epi.rs_out) {
     const int parts = gn::ceil_div(N, tc.block_n) * tc.splits * EPI_COLSPLIT;
@@ -754,22 +1691,75 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ktot * 2};
-    uint32_t box[2] = {BLOCK_K, (uint32_t)tc.block_n};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)(tc.block_n / tc.mcast)};  // with multicast every CTA fetches one slice
     int rc = make_tmap_f16(h, &p.tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  const int smem = smem_bytes_for(tc.block_n, tc.stages, tc.splits);
+  p.mcast = tc.mcast;
+  // epilogue staging: layout, sub-tile width and the output / residual tensor maps
+  const SmemLayout L = smem_layout(tc.block_n, tc.stages, tc.splits, og);
+  const int bn_out = og.geglu ? tc.block_n / 2 : tc.block_n;
+  p.staged = L.staged ? 1 : 0;
+  p.res_tma = L.res_tma ? 1 : 0;
+  p.res_late = L.res_late ? 1 : 0;
+  p.io_off = L.io_off;
+  p.tail_off = L.tail_off;
+  p.io_lw = (bn_out % 64) == 0 ? 6 : ((bn_out % 32) == 0 ? 5 : 4);
+  const bool split_fast = tc.splits > 1 && og.split_fast;
+  if (split_fast) {
+    const int64_t need = (int64_t)tc.splits * gn::ceil_div(N, tc.block_n) * tiles_m * tc.block_n * BLOCK_M * 4;
+    GN_CHECK_ARG(h, h->workspace && need <= h->workspace_bytes,
+                 "split-K needs %lld bytes of workspace (gn_set_workspace)", (long long)need);
+  }
+  if (split_fast) p.io_lw = 4;  // every 16-column chunk is its own TMA box: each rank stores the chunks it finished
+  if (og.gn && split_fast) {
+    const int owned_cols = gn::ceil_div(tc.block_n >> 4, tc.splits) << 4;
+    GN_CHECK_ARG(h, gn_rows_for(owned_cols, og.img_rows) > 0, "GroupNorm statistics: split tile unsupported");
+    p.gn_rows = 0;  // chosen on the device from the number of owned chunks
+  } else if (og.gn) {
+    p.gn_rows = gn_rows_for(bn_out, og.img_rows);
+    GN_CHECK_ARG(h, p.gn_rows > 0, "GroupNorm statistics: tile width %d unsupported with %d rows per image", bn_out,
+                 og.img_rows);
+  }
+  if (L.staged) {
+    const int w = 1 << p.io_lw;
+    uint32_t box[4] = {(uint32_t)w, 1, 1, 1};
+    for (int i = 1; i < og.rank; ++i) box[i] = og.box_rows[i - 1];
+    int rc = make_tmap_f16(h, &p.tmOut, og.out, og.rank, og.dims, og.ostr, box, 2 * w);
+    if (rc) return rc;
+    if (L.res_tma) {
+      rc = make_tmap_f16(h, &p.tmRes, og.res, og.rank, og.dims, og.rstr, box, 2 * w);
+      if (rc) return rc;
+    }
+  }
+  const int smem = L.total;
+  GN_CHECK_ARG(h, smem <= 227 * 1024, "GEMM tile configuration needs %d bytes of shared memory", smem);
+  typedef void (*GemmKernel)(const GemmParams);
+  static const GemmKernel kKernels[K_SPLIT + 1] = {
+      gemm_tc_kernel<GN_ACT_NONE>,      gemm_tc_kernel<GN_ACT_SILU>, gemm_tc_kernel<GN_ACT_GELU>,
+      gemm_tc_kernel<GN_ACT_RELU>,      gemm_tc_kernel<GN_ACT_QUICKGELU>, gemm_tc_kernel<K_GEGLU>,
+      gemm_tc_kernel<K_GENERIC>,        gemm_tc_kernel<K_SPLIT>};
   if (!h->gemm_attr_set) {
-    GN_CHECK_CUDA(h, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (GemmKernel k : kKernels)
+      GN_CHECK_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     h->gemm_attr_set = true;
   }
+  // compact flavour when the whole epilogue can run from shared memory (see fast_epilogue_rows)
+  const EpiParams& e = p.epi;
+  const bool rowvec_ok = !e.rowvec || ((N % 4) == 0 && (reinterpret_cast<uintptr_t>(e.rowvec) & 15) == 0);
+  const bool fast = h->fast_epilogue && L.staged && (!e.residual || L.res_tma) && e.act_post == GN_ACT_NONE && rowvec_ok &&
+                    e.act_pre >= GN_ACT_NONE && e.act_pre <= GN_ACT_QUICKGELU && !(e.geglu && e.act_pre != GN_ACT_NONE);
+  const int kind = split_fast ? K_SPLIT : (!fast || tc.splits > 1) ? K_GENERIC : (e.geglu ? K_GEGLU : e.act_pre);
   dim3 grid(gn::ceil_div(N, tc.block_n), tiles_m, tc.splits);
   // the K-splits of one output tile form a thread-block cluster (grid.z == cluster size)
-  GN_CHECK_CUDA(h, launch_ex(h, gemm_tc_kernel, grid, dim3(GEMM_THREADS, 1, 1), smem, stream, tc.splits, p));
+  GN_CHECK_ARG(h, tc.mcast == 1 || (kind < K_GENERIC && tc.splits == 1 && (tiles_m % tc.mcast) == 0),
+               "W multicast needs a compact non-split flavour and m-tiles divisible by the cluster size");
+  GN_CHECK_CUDA(h, launch_ex(h, kKernels[kind], grid, dim3(GEMM_THREADS, 1, 1), smem, stream,
+                              tc.splits | (tc.mcast << 8), p));
   h->last_cfg[0] = tc.block_n;
   h->last_cfg[1] = tc.splits;
   h->last_cfg[2] = tc.stages;
-  h->last_cfg[3] = (int)(grid.x * grid.y * grid.z);
+  h->last_cfg[3] = (int)(grid.x * grid.y * grid.z) * (tc.mcast > 1 ? -tc.mcast : 1);  // negative: x multicast size
   return GN_OK;
 }
 
@@ -778,21 +1768,26 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
 // the stream is being captured into a graph (the cached or modelled choice is used there), and re-running a launch is
 // safe because GEMM outputs never alias their inputs.
 static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, int64_t ktot, bool allow_split,
-                       cudaStream_t stream) {
+                       OutGeom& og, cudaStream_t stream) {
+  // long K loops keep the operand ring as deep as possible (throughput = bytes in flight / ~2 us of load latency): the
+  // residual tile is then fetched into the ring once the main loop has drained instead of into a dedicated buffer
+  og.res_late = p.num_kblocks > 6;
   const int N = p.epi.N;
   const bool geglu = p.epi.geglu != 0;
   const bool forced = h->force_block_n || h->force_splits || h->force_occupancy;
   char keybuf[96];
   const int rs_capacity = p.epi.rs_out ? p.epi.rs_parts : 0;
   p.rs_capacity = rs_capacity;
-  snprintf(keybuf, sizeof(keybuf), "%d:%d:%d:%d:%d:%d:%d:%d:%d", p.mode, tiles_m, N, p.num_kblocks, geglu ? 1 : 0,
-           p.epi.out32 ? 1 : 0, p.epi.residual ? 1 : 0, p.epi.ln_stats ? 1 : 0, rs_capacity);
+  snprintf(keybuf, sizeof(keybuf), "%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d", p.mode, tiles_m, N, p.num_kblocks,
+           geglu ? 1 : 0, p.epi.out32 ? 1 : 0, p.epi.residual ? 1 : 0, p.epi.ln_stats ? 1 : 0, rs_capacity,
+           og.stage_ok ? 1 : 0, og.res_ok ? 1 : 0, (og.gn ? og.img_rows : 0) + (og.halo ? 1000 : 0));
   const std::string key(keybuf);
   if (!forced) {
     auto it = h->tune_cache.find(key);
     if (it != h->tune_cache.end()) {
-      TileChoice tc{it->second[0], it->second[1], it->second[2], it->second[3]};
-      int rc = launch_config(h, p, tc, tiles_m, W, ktot, stream);
+      TileChoice tc{it->second[0], it->second[1], it->second[2], it->second[3] & 0xffff, it->second[3] >> 16};
+      if (tc.mcast < 1) tc.mcast = 1;
+      int rc = launch_config(h, p, tc, tiles_m, W, ktot, og, stream);
       if (rc == GN_OK) h->launches++;
       return rc;
     }
@@ -801,7 +1796,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
   cudaStreamIsCapturing(stream, &cap);
   if (h->autotune && !forced && !h->profiling && cap == cudaStreamCaptureStatusNone) {
     Candidate cand[10];
-    const int nc = candidate_list(h, tiles_m, N, p.num_kblocks, geglu, allow_split, cand, 10, rs_capacity);
+    const int nc = candidate_list(h, tiles_m, N, p.num_kblocks, geglu, allow_split, cand, 10, rs_capacity, og);
     if (nc > 1) {
       if (!h->tune_ev[0]) {
         GN_CHECK_CUDA(h, cudaEventCreate(&h->tune_ev[0]));
@@ -814,7 +1809,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
       int best = 0;
       float best_ms = 1e30f;
       for (int i = 0; i < nc; ++i) {
-        int rc = launch_config(h, p, cand[i].tc, tiles_m, W, ktot, stream);  // warm-up (tensor maps, smem carve-out)
+        int rc = launch_config(h, p, cand[i].tc, tiles_m, W, ktot, og, stream);  // warm-up (tensor maps, smem carve-out)
         if (rc) return rc;
         float total = 0.f;
         const int reps = cold ? 2 : 1;
@@ -822,7 +1817,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
           if (cold) GN_CHECK_CUDA(h, cudaMemsetAsync(h->workspace, r, (size_t)h->workspace_bytes, stream));
           GN_CHECK_CUDA(h, cudaEventRecord(h->tune_ev[0], stream));
           for (int q = 0; q < (cold ? 1 : 3); ++q) {
-            rc = launch_config(h, p, cand[i].tc, tiles_m, W, ktot, stream);
+            rc = launch_config(h, p, cand[i].tc, tiles_m, W, ktot, og, stream);
             if (rc) return rc;
           }
           GN_CHECK_CUDA(h, cudaEventRecord(h->tune_ev[1], stream));
@@ -837,14 +1832,19 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
         }
       }
       const TileChoice& tc = cand[best].tc;
-      h->tune_cache[key] = {tc.block_n, tc.splits, tc.stages, tc.tmem_cols};
-      int rc = launch_config(h, p, tc, tiles_m, W, ktot, stream);
+      h->tune_cache[key] = {tc.block_n, tc.splits, tc.stages, tc.tmem_cols | (tc.mcast << 16)};
+      // the timed launches accumulated into the caller's GroupNorm statistics as well: start them again from zero
+      if (p.gn_out)
+        GN_CHECK_CUDA(h, cudaMemsetAsync(p.gn_out, 0, (size_t)p.gn_stat_images * p.gn_nb * 16, stream));
+      int rc = launch_config(h, p, tc, tiles_m, W, ktot, og, stream);
       if (rc == GN_OK) h->launches++;
       return rc;
     }
   }
-  TileChoice tc = choose_tiles(h, tiles_m, N, p.num_kblocks, geglu, allow_split, rs_capacity);
-  int rc = launch_config(h, p, tc, tiles_m, W, ktot, stream);
+  TileChoice tc;
+  GN_CHECK_ARG(h, choose_tiles(h, tiles_m, N, p.num_kblocks, geglu, allow_split, rs_capacity, og, &tc),
+               "no GEMM tile configuration fits this problem (M tiles %d, N %d)", tiles_m, N);
+  int rc = launch_config(h, p, tc, tiles_m, W, ktot, og, stream);
   if (rc == GN_OK) h->launches++;
   return rc;
 }
@@ -878,7 +1878,15 @@ extern "C" int gn_linear(gn_handle* h, const void* A, int64_t lda, int M, int K,
     rc = make_tmap_f16(h, &p.tmA[0], A, 2, dims, strides, box);
     if (rc) return rc;
   }
-  return launch_gemm(h, p, ceil_div(M, BLOCK_M), W, K, /*allow_split=*/true, static_cast<cudaStream_t>(stream));
+  OutGeom og;
+  rc = fill_out_geom(h, p, og, epi, out);
+  if (rc) return rc;
+  og.rank = 2;
+  og.dims[1] = (uint64_t)M;
+  og.ostr[0] = (uint64_t)ldo * 2;
+  og.rstr[0] = (uint64_t)p.epi.ldr * 2;
+  og.box_rows[0] = BLOCK_M;
+  return launch_gemm(h, p, ceil_div(M, BLOCK_M), W, K, /*allow_split=*/true, og, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C, const void* w, int Cout, int KH,
@@ -919,7 +1927,15 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
   if (bw > 128) bw = 128;
   int bh = pow2_ceil(Ho);
   if (bh > 128 / bw) bh = 128 / bw;
-  const int bb = 128 / (bw * bh);
+  int bb = 128 / (bw * bh);
+  // halo mode: 3x3 / stride 1 / pad 1 over whole 64-channel blocks and image widths that tile by 8
+  const bool halo = h->halo_conv && KH == 3 && KW == 3 && stride == 1 && pad == 1 && (C % BLOCK_K) == 0 &&
+                    (Wo % HALO_W) == 0 && Ho >= 8;
+  if (halo) {
+    bw = HALO_W;
+    bh = HALO_H;
+    bb = 1;
+  }
   p.bw = bw;
   p.bh = bh;
   p.bb = bb;
@@ -932,7 +1948,18 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
   const int cblk = Cp / BLOCK_K;
   int nseg = 0;
   int nmaps = 0;
-  if (stride == 1) {
+  if (halo) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {BLOCK_K, HALO_W, HALO_H + 2, 1};
+    rc = make_tmap_f16(h, &p.tmA[0], x, 4, dims, strides, box);
+    if (rc) return rc;
+    nmaps = 1;
+    p.halo = 1;
+    p.halo_ncb = cblk;
+    p.halo_bo = h->halo_base_offset ? 1 : 0;
+    nseg = 0;  // the segment table lists the extra 1x1 sources only
+  } else if (stride == 1) {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
     uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
@@ -993,5 +2020,22 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
   }
   p.num_segs = nseg;
   p.num_kblocks = (int)(ktot / BLOCK_K);
-  return launch_gemm(h, p, tiles_m, w, ktot, /*allow_split=*/true, static_cast<cudaStream_t>(stream));
+  OutGeom og;
+  rc = fill_out_geom(h, p, og, epi, out);
+  if (rc) return rc;
+  og.halo = halo;
+  og.rank = 4;
+  og.dims[1] = (uint64_t)Wo;
+  og.dims[2] = (uint64_t)Ho;
+  og.dims[3] = (uint64_t)B;
+  og.ostr[0] = (uint64_t)ldo * 2;
+  og.ostr[1] = (uint64_t)Wo * ldo * 2;
+  og.ostr[2] = (uint64_t)Ho * Wo * ldo * 2;
+  og.rstr[0] = (uint64_t)p.epi.ldr * 2;
+  og.rstr[1] = (uint64_t)Wo * p.epi.ldr * 2;
+  og.rstr[2] = (uint64_t)Ho * Wo * p.epi.ldr * 2;
+  og.box_rows[0] = (uint32_t)bw;
+  og.box_rows[1] = (uint32_t)bh;
+  og.box_rows[2] = (uint32_t)bb;
+  return launch_gemm(h, p, tiles_m, w, ktot, /*allow_split=*/true, og, static_cast<cudaStream_t>(stream));
 }

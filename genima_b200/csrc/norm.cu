@@ -264,6 +264,143 @@ __global__ void __launch_bounds__(1024, 1) gn_fused_kernel(const GNParams p) {
   gn_stamp(p, 5);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm from statistics accumulated by the producing GEMM epilogues (gemm.cu: epilogue_tail): ONE elementwise pass.
+// stats: uint64 [B][C / bucket][2], 2^20-scaled fixed-point (sum, sumsq) of every (image, bucket of channels).
+struct GNApplyParams {
+  const __half* x0;
+  const __half* x1;
+  const unsigned long long* st0;
+  const unsigned long long* st1;
+  int C0, C1, C, B, HW, G, cg, NV, bucket;
+  int ctas_per_b;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  int silu;
+  __half* y;
+};
+
+constexpr int GNA_THREADS = 256;
+
+__global__ void __launch_bounds__(GNA_THREADS) gn_apply_kernel(const GNApplyParams p) {
+  extern __shared__ __align__(16) uint8_t gna_smem[];
+  float* sc = reinterpret_cast<float*>(gna_smem);  // [C] gamma -> scale, then [C] beta -> shift
+  float* sh = sc + p.C;
+  __shared__ float s_mean[64], s_rstd[64];
+  const int t = threadIdx.x;
+  const int b = blockIdx.x / p.ctas_per_b;
+  const int ci = blockIdx.x % p.ctas_per_b;
+  // gamma / beta are weights: fetch them while the producer of x is still running (programmatic dependent launch)
+  for (int c = t; c < p.C; c += GNA_THREADS) {
+    sc[c] = __ldg(p.gamma + c);
+    sh[c] = __ldg(p.beta + c);
+  }
+  pdl_trigger();
+  pdl_wait();  // x and the statistics come from the previous kernels in the stream
+  // this CTA's share of the image's 16-byte vectors; the first vectors are requested before the statistics are reduced
+  const int64_t nvec = (int64_t)p.HW * p.NV;
+  const int64_t per = (nvec + p.ctas_per_b - 1) / p.ctas_per_b;
+  const int64_t v_begin = (int64_t)ci * per;
+  const int64_t v_end = min(nvec, v_begin + per);
+  constexpr int PF = 4;
+  uint4 pre[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {
+    const int64_t v = v_begin + t + (int64_t)i * GNA_THREADS;
+    if (v < v_end) {
+      const int pix = (int)(v / p.NV);
+      const int c0 = (int)(v - (int64_t)pix * p.NV) * 8;
+      const __half* src = (c0 < p.C0) ? p.x0 + ((int64_t)b * p.HW + pix) * p.C0 + c0
+                                      : p.x1 + ((int64_t)b * p.HW + pix) * p.C1 + (c0 - p.C0);
+      pre[i] = __ldg(reinterpret_cast<const uint4*>(src));
+    }
+  }
+  if (t < p.G) {
+    // exact integer totals of the group's buckets (each bucket lies entirely in x0 or in x1)
+    long long s1 = 0, s2 = 0;
+    const int nb0 = p.C0 / p.bucket, nb1 = p.C1 / p.bucket;
+    const int per_g = p.cg / p.bucket;
+    const int kb = t * per_g;
+    for (int k0 = 0; k0 < per_g; k0 += 4) {  // four buckets (eight 8-byte loads) in flight
+      ulonglong2 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = kb + k0 + u;
+        if (k0 + u < per_g) {
+          const unsigned long long* src =
+              (k < nb0) ? p.st0 + ((size_t)b * nb0 + k) * 2 : p.st1 + ((size_t)b * nb1 + (k - nb0)) * 2;
+          q[u] = __ldcg(reinterpret_cast<const ulonglong2*>(src));
+        } else {
+          q[u] = make_ulonglong2(0, 0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s1 += static_cast<long long>(q[u].x);
+        s2 += static_cast<long long>(q[u].y);
+      }
+    }
+    const double inv = 1.0 / (1048576.0 * (double)p.cg * (double)p.HW);
+    const double mean = (double)s1 * inv;
+    double var = (double)s2 * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[t] = (float)mean;
+    s_rstd[t] = rsqrtf((float)var + p.eps);
+  }
+  __syncthreads();
+  for (int c = t; c < p.C; c += GNA_THREADS) {
+    const int g = c / p.cg;
+    const float a = s_rstd[g] * sc[c];
+    sh[c] = sh[c] - s_mean[g] * a;
+    sc[c] = a;
+  }
+  __syncthreads();
+  for (int64_t v = v_begin + t, i = 0; v < v_end; v += GNA_THREADS, ++i) {
+    const int pix = (int)(v / p.NV);
+    const int c0 = (int)(v - (int64_t)pix * p.NV) * 8;
+    uint4 q;
+    if (i < PF) {
+      q = pre[0];
+#pragma unroll
+      for (int j = 1; j < PF; ++j)
+        if (i == j) q = pre[j];
+    } else {
+      const __half* src = (c0 < p.C0) ? p.x0 + ((int64_t)b * p.HW + pix) * p.C0 + c0
+                                      : p.x1 + ((int64_t)b * p.HW + pix) * p.C1 + (c0 - p.C0);
+      q = __ldg(reinterpret_cast<const uint4*>(src));
+    }
+    const __half2* hp = reinterpret_cast<const __half2*>(&q);
+    const float4 a0 = *reinterpret_cast<const float4*>(sc + c0);
+    const float4 a1 = *reinterpret_cast<const float4*>(sc + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sh + c0);
+    const float4 b1 = *reinterpret_cast<const float4*>(sh + c0 + 4);
+    float o[8];
+    float2 f = __half22float2(hp[0]);
+    o[0] = fmaf(f.x, a0.x, b0.x);
+    o[1] = fmaf(f.y, a0.y, b0.y);
+    f = __half22float2(hp[1]);
+    o[2] = fmaf(f.x, a0.z, b0.z);
+    o[3] = fmaf(f.y, a0.w, b0.w);
+    f = __half22float2(hp[2]);
+    o[4] = fmaf(f.x, a1.x, b1.x);
+    o[5] = fmaf(f.y, a1.y, b1.y);
+    f = __half22float2(hp[3]);
+    o[6] = fmaf(f.x, a1.z, b1.z);
+    o[7] = fmaf(f.y, a1.w, b1.w);
+    if (p.silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = silu_fast(o[j]);
+    }
+    uint4 w;
+    w.x = pack_half2(o[0], o[1]);
+    w.y = pack_half2(o[2], o[3]);
+    w.z = pack_half2(o[4], o[5]);
+    w.w = pack_half2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(p.y + ((int64_t)b * p.HW + pix) * p.C + c0) = w;
+  }
+}
+
 // One warp per row; the row lives in registers (C <= 2048).
 constexpr int LN_MAX_VPL = 8;
 __global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restrict__ x, int64_t ldx, int rows, int C,
@@ -479,6 +616,59 @@ extern "C" int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x
     h->gn_attr_set = true;
   }
   GN_CHECK_CUDA(h, launch_ex(h, gn_fused_kernel, dim3(B * p.ctas_per_b, 1, 1), dim3(threads, 1, 1), smem, st, 1, p));
+  h->launches++;
+  return GN_OK;
+}
+
+extern "C" int gn_group_norm_apply(gn_handle* h, const void* x0, int C0, const void* stats0, const void* x1, int C1,
+                                   const void* stats1, int bucket, int B, int HW, int groups, float eps,
+                                   const float* gamma, const float* beta, int silu, void* y, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  GN_CHECK_ARG(h, x0 && stats0 && y && gamma && beta, "gn_group_norm_apply: null pointer");
+  if (!x1) C1 = 0;
+  GN_CHECK_ARG(h, x1 == nullptr || stats1 != nullptr, "gn_group_norm_apply: x1 given without its statistics");
+  const int C = C0 + C1;
+  GN_CHECK_ARG(h, B > 0 && HW > 0 && groups > 0 && groups <= 64, "gn_group_norm_apply: bad shape");
+  GN_CHECK_ARG(h, (C0 % 8) == 0 && (C1 % 8) == 0 && (C % groups) == 0, "gn_group_norm_apply: C0=%d C1=%d groups=%d", C0,
+               C1, groups);
+  const int cg = C / groups;
+  GN_CHECK_ARG(h, bucket > 0 && (cg % bucket) == 0 && (C0 % bucket) == 0 && (C1 % bucket) == 0,
+               "gn_group_norm_apply: bucket %d must divide C0=%d, C1=%d and the %d channels per group", bucket, C0, C1, cg);
+  GN_CHECK_ARG(h, (size_t)C * 8 <= 96 * 1024, "gn_group_norm_apply: C=%d too large", C);
+  ProfScope prof(h, stream, GN_PROF_NORM, 0.0, 4.0 * B * HW * C);
+  GNApplyParams p;
+  p.x0 = static_cast<const __half*>(x0);
+  p.x1 = static_cast<const __half*>(x1);
+  p.st0 = static_cast<const unsigned long long*>(stats0);
+  p.st1 = static_cast<const unsigned long long*>(stats1);
+  p.C0 = C0;
+  p.C1 = C1;
+  p.C = C;
+  p.B = B;
+  p.HW = HW;
+  p.G = groups;
+  p.cg = cg;
+  p.NV = C / 8;
+  p.bucket = bucket;
+  p.eps = eps;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.silu = silu;
+  p.y = static_cast<__half*>(y);
+  // ~8 sixteen-byte vectors per thread, at most 4 CTAs per SM in total
+  const int64_t nvec = (int64_t)HW * p.NV;
+  int64_t ctas = (nvec + GNA_THREADS * 8 - 1) / (GNA_THREADS * 8);
+  const int64_t cap = (int64_t)h->num_sms * 4 / B > 0 ? (int64_t)h->num_sms * 4 / B : 1;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  p.ctas_per_b = (int)ctas;
+  const size_t smem = (size_t)C * 8;
+  if (smem > 48 * 1024 && !h->gna_attr_set) {
+    GN_CHECK_CUDA(h, cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    h->gna_attr_set = true;
+  }
+  GN_CHECK_CUDA(h, launch_ex(h, gn_apply_kernel, dim3(B * p.ctas_per_b, 1, 1), dim3(GNA_THREADS, 1, 1), smem,
+                              static_cast<cudaStream_t>(stream), 1, p));
   h->launches++;
   return GN_OK;
 }

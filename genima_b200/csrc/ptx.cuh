@@ -91,6 +91,48 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, 
       : "memory");
 }
 
+// ----------------------------------------------------------------------------- TMA stores (smem -> global, bulk async group)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_addr), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t smem_addr, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the smem source of every committed bulk store of this thread has been read (the CTA may exit / reuse it)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------- cluster helpers (TMA multicast pipelines)
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                  uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// arrive (count 1) on the mbarrier at the same shared-memory offset in every CTA of cta_mask once the MMAs issued so far
+// by this thread have completed
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 // ncols: power of two in [32, 512]. Executed by one full warp.
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -114,6 +156,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;        // stride byte offset  [32,46)
   d |= static_cast<uint64_t>(1) << 46;                                // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;                                // layout type: SWIZZLE_128B
+  return d;
+}
+
+// Same, for an operand window that starts at an arbitrary 128-byte row of a swizzled buffer (not on a 1024-byte
+// repeat of the swizzle pattern): the "matrix base offset" field (bits [49, 52)) carries (addr >> 7) & 7 so that the
+// tensor core applies the same address-based XOR pattern the TMA unit used when it wrote the buffer.
+__device__ __forceinline__ uint64_t umma_desc_sw128_window(uint32_t smem_addr, uint32_t sbo_bytes, int base_offset_on) {
+  uint64_t d = umma_desc_sw128(smem_addr, sbo_bytes, 0);
+  if (base_offset_on) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;
   return d;
 }
 

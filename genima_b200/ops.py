@@ -48,8 +48,34 @@ class RowStats:
         self.parts = 0
 
 
+class GNStats:
+    """GroupNorm statistics of one fp16 tensor, accumulated by the GEMM epilogue that produced it: uint64
+    [B][C / bucket][2] fixed-point (sum, sumsq) per (image, bucket of channels) in the owning Ops' statistics arena."""
+
+    __slots__ = ("buf", "bucket", "generation", "owner")
+
+    def __init__(self, buf: torch.Tensor, bucket: int, generation: int, owner=None):
+        self.buf, self.bucket, self.generation, self.owner = buf, bucket, generation, owner
+
+
+def gn_bucket_for(channels: Sequence[int], groups: int) -> int:
+    """Channels per statistics bucket such that every GroupNorm over any of `channels` (or a concat of two of them) with
+    `groups` groups covers whole buckets: gcd(channels) / groups; 0 (fusion off) when that is not an even integer."""
+    import math
+
+    g = 0
+    for c in channels:
+        g = math.gcd(g, int(c))
+    if g == 0 or g % groups:
+        return 0
+    b = g // groups
+    return b if b >= 2 and b % 2 == 0 else 0
+
+
 class Ops:
     """One instance per device; owns the gn_handle and the scratch workspace (L2-flush buffer of the autotuner)."""
+
+    GN_ARENA_WORDS = 1 << 19  # 4 MiB of uint64 statistics accumulators: far more than one agent step needs
 
     def __init__(self, device: int = 0, workspace_mb: int = 160, autotune: bool = True):
         if not torch.cuda.is_available():
@@ -66,6 +92,24 @@ class Ops:
         self.handle.check(self.lib.gn_set_autotune(self.h, 1 if autotune else 0), "gn_set_autotune")
         if os.environ.get("GENIMA_B200_PDL", "1") == "0":   # A/B switch for programmatic dependent launch
             self.handle.check(self.lib.gn_set_pdl(self.h, 0), "gn_set_pdl")
+        if os.environ.get("GENIMA_B200_STAGED", "1") == "0":   # A/B switch for the TMA-stored GEMM epilogue
+            self.handle.check(self.lib.gn_set_staged_epilogue(self.h, 0), "gn_set_staged_epilogue")
+        halo = os.environ.get("GENIMA_B200_HALO")   # "enable[,base_offset_field]": halo-mode convolutions (A/B)
+        if halo:
+            parts = [int(v) for v in halo.split(",")]
+            self.handle.check(self.lib.gn_set_conv_halo(self.h, parts[0], parts[1] if len(parts) > 1 else 1),
+                              "gn_set_conv_halo")
+        mc = os.environ.get("GENIMA_B200_MCAST")   # "max[,force]": W-tile multicast cluster sizes (A/B)
+        if mc:
+            parts = [int(v) for v in mc.split(",")]
+            self.handle.check(self.lib.gn_set_gemm_multicast(self.h, parts[0], parts[1] if len(parts) > 1 else 0),
+                              "gn_set_gemm_multicast")
+        # GroupNorm statistics fused into the producing GEMM epilogues (A/B switch: GENIMA_B200_GNFUSE=0)
+        self.gn_fuse = os.environ.get("GENIMA_B200_GNFUSE", "1") != "0"
+        self._gn_arena = torch.zeros(self.GN_ARENA_WORDS, dtype=torch.int64, device=self.device)
+        self._gn_used = 0
+        self._gn_generation = 0
+        self.gn_apply_calls = 0   # group_norm calls served by gn_group_norm_apply (fused statistics)
 
     # ------------------------------------------------------------------------------------------------ helpers
     @staticmethod
@@ -74,7 +118,7 @@ class Ops:
 
     def _epilogue(self, M: int, N: int, bias=None, scale=None, rowvec=None, rows_per_batch: int = 0, residual=None,
                   act_pre=None, act_post=None, alpha: float = 1.0, beta: float = 1.0, geglu: bool = False,
-                  out_fp32: bool = False, ln=None, row_stats=None) -> GnEpilogue:
+                  out_fp32: bool = False, ln=None, row_stats=None, gn_stats: Optional[GNStats] = None) -> GnEpilogue:
         e = GnEpilogue()
         e.scale = _ptr(_f32(scale, "scale"))
         e.bias = _ptr(_f32(bias, "bias"))
@@ -113,7 +157,39 @@ class Ops:
         if row_stats is not None:
             e.rowstats_out = row_stats.buf.data_ptr()
             e.rowstats_capacity = row_stats.capacity
+        if gn_stats is not None:
+            e.gnstats_out = gn_stats.buf.data_ptr()
+            e.gn_bucket = gn_stats.bucket
         return e
+
+    # ------------------------------------------------------------------------------------------------ GroupNorm statistics
+    def gn_stats_reset(self) -> None:
+        """Zero the statistics arena on the current stream and start allocating from its beginning again.  Call once at
+        the top of every forward pass (it is one memset node in a captured graph); statistics handed out before the
+        reset are no longer used (group_norm falls back to its own reduction for them)."""
+        self._gn_arena.zero_()
+        self._gn_used = 0
+        self._gn_generation += 1
+
+    def _gn_stats_alloc(self, images: int, n_out: int, bucket: int) -> GNStats:
+        words = images * (n_out // bucket) * 2
+        if self._gn_used + words > self.GN_ARENA_WORDS:
+            # arena exhausted (nobody called gn_stats_reset): slow path, a private zeroed buffer that never expires
+            return GNStats(torch.zeros(words, dtype=torch.int64, device=self.device), bucket, 0, None)
+        buf = self._gn_arena[self._gn_used:self._gn_used + words]
+        self._gn_used += (words + 1) // 2 * 2
+        return GNStats(buf, bucket, self._gn_generation, self)
+
+    @staticmethod
+    def _gn_rows_ok(rows_per_image: int) -> bool:
+        return (rows_per_image >= 128 and rows_per_image % 128 == 0) or rows_per_image in (16, 32, 64)
+
+    def carry_stats(self, view: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+        """`view` is a reshape of `src`: keep the GroupNorm statistics attached."""
+        st = getattr(src, "gn_stats", None)
+        if st is not None:
+            view.gn_stats = st
+        return view
 
     def set_gemm_tuning(self, block_n: int = 0, splits: int = 0) -> None:
         self.handle.check(self.lib.gn_set_gemm_tuning(self.h, block_n, splits), "gn_set_gemm_tuning")
@@ -173,13 +249,29 @@ class Ops:
         o2 = out.reshape(-1, out.shape[-1])
         if o2.shape[0] != M or o2.shape[1] < n_out or o2.stride(1) != 1 or out.dtype != out_dtype:
             raise ValueError("bad `out` tensor for linear")
+        st = self._gn_request(epi, M, n_out, epi.get("rows_per_batch") or M, out_dtype)
         e = self._epilogue(M, N, **epi)
         rc = self.lib.gn_linear(self.h, a2.data_ptr(), a2.stride(0), M, K, w.data_ptr(), N, o2.data_ptr(),
                                 o2.stride(0), C.byref(e), self._stream())
         self.handle.check(rc, "gn_linear")
         if epi.get("row_stats") is not None:
             epi["row_stats"].parts = int(self.lib.gn_get_last_rowstats_parts(self.h))
+        if st is not None:
+            out.gn_stats = st
         return out
+
+    def _gn_request(self, epi: dict, M: int, n_out: int, rows_per_image: int, out_dtype) -> Optional[GNStats]:
+        """Turn the `gn_stats=<bucket>` keyword of linear / conv2d into an allocated GNStats (or drop it when the layout
+        is not supported by the fused statistics pass: the consumer then reduces on its own)."""
+        bucket = epi.pop("gn_stats", 0)
+        if not bucket or not self.gn_fuse:
+            return None
+        if (out_dtype != torch.float16 or bucket % 2 or n_out % bucket or n_out % 2 or M % rows_per_image
+                or not self._gn_rows_ok(rows_per_image)):
+            return None
+        st = self._gn_stats_alloc(M // rows_per_image, n_out, bucket)
+        epi["gn_stats"] = st
+        return st
 
     def conv2d(self, x: torch.Tensor, w: torch.Tensor, cout: int, ksize: int = 3, stride: int = 1, pad: int = 1,
                extras: Sequence[torch.Tensor] = (), out: Optional[torch.Tensor] = None, **epi) -> torch.Tensor:
@@ -213,11 +305,19 @@ class Ops:
             raise ValueError("`out` must be pixel-contiguous")
         M = B * Ho * Wo
         epi.setdefault("rows_per_batch", Ho * Wo)
+        # rows of one image inside a 128-pixel tile (bw x bh box of powers of two, see gn_conv2d)
+        bw = min(128, 1 << max(0, (Wo - 1).bit_length()))
+        bh = min(128 // bw, 1 << max(0, (Ho - 1).bit_length()))
+        st = self._gn_request(epi, B * 128, cout, 128, out_dtype) if bw * bh >= 16 and epi.get("gn_stats") else None
+        if st is None:
+            epi.pop("gn_stats", None)
         e = self._epilogue(M, cout, **epi)
         rc = self.lib.gn_conv2d(self.h, x.data_ptr(), B, H, W, Cin, w.data_ptr(), cout, ksize, ksize, stride, pad,
                                 ex[0], exc[0], ex[1], exc[1], out.data_ptr(), out.stride(2), C.byref(e),
                                 self._stream())
         self.handle.check(rc, "gn_conv2d")
+        if st is not None:
+            out.gn_stats = st
         return out
 
     # ------------------------------------------------------------------------------------------------ attention
@@ -275,11 +375,28 @@ class Ops:
             raise ValueError("gamma/beta size mismatch")
         if out is None:
             out = torch.empty(*x0.shape[:-1], C0 + C1, dtype=torch.float16, device=x0.device)
+        st0 = getattr(x0, "gn_stats", None)
+        st1 = getattr(x1, "gn_stats", None) if x1 is not None else None
+        if (st0 is not None and (x1 is None or st1 is not None) and self._gn_stats_live(st0) and
+                (st1 is None or (self._gn_stats_live(st1) and st1.bucket == st0.bucket)) and
+                (C0 + C1) % groups == 0 and ((C0 + C1) // groups) % st0.bucket == 0 and C0 % st0.bucket == 0):
+            rc = self.lib.gn_group_norm_apply(self.h, x0.data_ptr(), C0, st0.buf.data_ptr(), _ptr(x1), C1,
+                                              None if st1 is None else st1.buf.data_ptr(), st0.bucket, B, HW, groups,
+                                              float(eps), gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0,
+                                              out.data_ptr(), self._stream())
+            self.handle.check(rc, "gn_group_norm_apply")
+            self.gn_apply_calls += 1
+            return out
         rc = self.lib.gn_group_norm(self.h, x0.data_ptr(), C0, _ptr(x1), C1, B, HW, groups, float(eps),
                                     gamma.data_ptr(), beta.data_ptr(), 1 if silu else 0, None, out.data_ptr(),
                                     self._stream())
         self.handle.check(rc, "gn_group_norm")
         return out
+
+    @staticmethod
+    def _gn_stats_live(st: GNStats) -> bool:
+        """Statistics from an arena are valid until that arena's next reset (any Ops: the producer may be another handle)."""
+        return st.owner is None or st.owner._gn_generation == st.generation
 
     def layer_norm(self, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
                    out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -254,6 +254,10 @@ class B200ControlNetPipeline:
         ops = self.ops
         B = lat_in.shape[0]
         temb = self._time_rows(n_steps, B)
+        # GroupNorm statistics are accumulated by the GEMM epilogues into per-handle arenas: one memset per forward pass
+        # (issued here, before the two encoder streams fork)
+        for o in self.all_ops():
+            o.gn_stats_reset()
         sig = self.schedule.sigmas
         kv_u = {k[2:]: v for k, v in kv.items() if k.startswith("u:")}
         kv_c = {k[2:]: v for k, v in kv.items() if k.startswith("c:")}

@@ -23,7 +23,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from .configs import UNetConfig
-from .ops import Ops
+from .ops import Ops, gn_bucket_for
 from .packing import fold_layer_norm, pack_conv_weight, pack_geglu_weight
 from .weights import unet_skip_channels
 
@@ -46,6 +46,8 @@ class _Params:
     def __init__(self, sd: Dict[str, torch.Tensor], device: torch.device):
         self.sd = sd
         self.device = device
+        # channels per GroupNorm-statistics bucket of this network (ops.gn_bucket_for); 0 = statistics are not fused
+        self.gn_bucket = 0
         self._f16: Dict[str, torch.Tensor] = {}
         self._f32: Dict[str, torch.Tensor] = {}
 
@@ -70,6 +72,7 @@ class _ResBlock:
     def __init__(self, P: _Params, prefix: str, cin_parts: Sequence[int], groups: int, eps: float):
         self.groups, self.eps = groups, eps
         self.prefix = prefix
+        self.bucket = P.gn_bucket
         w1 = P.host16(f"{prefix}.conv1.weight")
         self.cout = w1.shape[0]
         self.cin_parts = tuple(cin_parts)
@@ -101,21 +104,24 @@ class _ResBlock:
     def __call__(self, ops: Ops, x0: torch.Tensor, x1: Optional[torch.Tensor], temb_row: Optional[torch.Tensor]):
         n1 = ops.group_norm(x0, self.g1, self.b1, self.groups, self.eps, silu=True, x1=x1)
         hw = x0.shape[1] * x0.shape[2]
+        # both convolutions also accumulate the GroupNorm statistics of their output (for norm2 / the next block's norm)
         if temb_row is not None:
-            h = ops.conv2d(n1, self.w1, self.cout, bias=self.cb1, rowvec=temb_row, rows_per_batch=hw)
+            h = ops.conv2d(n1, self.w1, self.cout, bias=self.cb1, rowvec=temb_row, rows_per_batch=hw,
+                           gn_stats=self.bucket)
         else:
-            h = ops.conv2d(n1, self.w1, self.cout, bias=self.cb1)
+            h = ops.conv2d(n1, self.w1, self.cout, bias=self.cb1, gn_stats=self.bucket)
         n2 = ops.group_norm(h, self.g2, self.b2, self.groups, self.eps, silu=True)
         if self.has_shortcut:
             extras = [x0] if x1 is None else [x0, x1]
-            return ops.conv2d(n2, self.w2, self.cout, extras=extras, bias=self.cb2)
-        return ops.conv2d(n2, self.w2, self.cout, bias=self.cb2, residual=x0)
+            return ops.conv2d(n2, self.w2, self.cout, extras=extras, bias=self.cb2, gn_stats=self.bucket)
+        return ops.conv2d(n2, self.w2, self.cout, bias=self.cb2, residual=x0, gn_stats=self.bucket)
 
 
 class _Transformer2D:
     def __init__(self, P: _Params, prefix: str, c: int, heads: int, groups: int):
         self.c, self.heads, self.groups = c, heads, groups
         self.prefix = prefix
+        self.bucket = P.gn_bucket
         t = f"{prefix}.transformer_blocks.0"
         dev = P.device
         self.gn_g, self.gn_b = P.f32(f"{prefix}.norm.weight"), P.f32(f"{prefix}.norm.bias")
@@ -161,12 +167,14 @@ class _Transformer2D:
         # GEGLU feed-forward (norm3 folded into the first projection)
         g = ops.linear(h, self.w_ff1, bias=self.b_ff1, ln=(st, self.cs_ff1, self.ln_eps), geglu=True)
         h = ops.linear(g, self.w_ff2, bias=self.b_ff2, residual=h)
-        out = ops.linear(h, self.w_out, bias=self.b_out, residual=x.reshape(B * T, C))
-        return out.reshape(B, H, W, C)
+        out = ops.linear(h, self.w_out, bias=self.b_out, residual=x.reshape(B * T, C), rows_per_batch=T,
+                         gn_stats=self.bucket)
+        return ops.carry_stats(out.reshape(B, H, W, C), out)
 
 
 class _Conv:
-    def __init__(self, P: _Params, prefix: str, stride: int = 1, cin_layout: Sequence[int] = ()):
+    def __init__(self, P: _Params, prefix: str, stride: int = 1, cin_layout: Sequence[int] = (), gn: bool = False):
+        self.bucket = P.gn_bucket if gn else 0   # gn: the output feeds a GroupNorm -> accumulate its statistics
         w = P.host16(f"{prefix}.weight")
         self.cout, self.k, self.stride = w.shape[0], w.shape[2], stride
         self.pad = self.k // 2
@@ -174,7 +182,8 @@ class _Conv:
         self.b = P.f32(f"{prefix}.bias")
 
     def __call__(self, ops: Ops, x: torch.Tensor, **epi) -> torch.Tensor:
-        return ops.conv2d(x, self.w, self.cout, ksize=self.k, stride=self.stride, pad=self.pad, bias=self.b, **epi)
+        return ops.conv2d(x, self.w, self.cout, ksize=self.k, stride=self.stride, pad=self.pad, bias=self.b,
+                          gn_stats=self.bucket, **epi)
 
 
 class _Encoder:
@@ -185,7 +194,8 @@ class _Encoder:
         P = self.P = _Params(sd, ops.device)
         g, eps = cfg.norm_num_groups, cfg.norm_eps
         ch = cfg.block_out_channels
-        self.conv_in = _Conv(P, "conv_in", cin_layout=(cfg.in_channels, LATENT_CPAD))
+        P.gn_bucket = gn_bucket_for(ch, g)
+        self.conv_in = _Conv(P, "conv_in", cin_layout=(cfg.in_channels, LATENT_CPAD), gn=True)
         self.te_w1, self.te_b1 = P.f16("time_embedding.linear_1.weight"), P.f32("time_embedding.linear_1.bias")
         self.te_w2, self.te_b2 = P.f16("time_embedding.linear_2.weight"), P.f32("time_embedding.linear_2.bias")
         self.down: List[Tuple[List[_ResBlock], List[Optional[_Transformer2D]], Optional[_Conv]]] = []
@@ -197,7 +207,7 @@ class _Encoder:
                 att.append(_Transformer2D(P, f"down_blocks.{i}.attentions.{j}", cout, cfg.num_heads[i], g)
                            if cfg.attn_levels[i] else None)
                 cin = cout
-            ds = _Conv(P, f"down_blocks.{i}.downsamplers.0.conv", stride=2) if i < len(ch) - 1 else None
+            ds = _Conv(P, f"down_blocks.{i}.downsamplers.0.conv", stride=2, gn=True) if i < len(ch) - 1 else None
             self.down.append((res, att, ds))
         self.mid_res0 = _ResBlock(P, "mid_block.resnets.0", (ch[-1],), g, eps)
         self.mid_attn = _Transformer2D(P, "mid_block.attentions.0", ch[-1], cfg.num_heads[-1], g)
@@ -270,7 +280,7 @@ class DeviceUNet(_Encoder):
                 att.append(_Transformer2D(P, f"up_blocks.{i}.attentions.{j}", cout, cfg.num_heads[level], g)
                            if cfg.attn_levels[level] else None)
                 prev = cout
-            us = _Conv(P, f"up_blocks.{i}.upsamplers.0.conv") if i < len(ch) - 1 else None
+            us = _Conv(P, f"up_blocks.{i}.upsamplers.0.conv", gn=True) if i < len(ch) - 1 else None
             self.up.append((res, att, us))
         self.out_g, self.out_b = P.f32("conv_norm_out.weight"), P.f32("conv_norm_out.bias")
         self.conv_out = _Conv(P, "conv_out")
@@ -348,12 +358,13 @@ class DeviceControlNet(_Encoder):
         for s, w, b, us in zip(skips, self.zero_w, self.zero_b, unet_skips):
             B, H, W, C = s.shape
             o = ops.linear(s.reshape(B * H * W, C), w, bias=b, residual=us.reshape(B * H * W, C),
-                           alpha=conditioning_scale)
-            out.append(o.reshape(B, H, W, C))
+                           alpha=conditioning_scale, rows_per_batch=H * W, gn_stats=self.P.gn_bucket)
+            out.append(ops.carry_stats(o.reshape(B, H, W, C), o))
         B, H, W, C = mid.shape
         m = ops.linear(mid.reshape(B * H * W, C), self.mid_w, bias=self.mid_b,
-                       residual=unet_mid.reshape(B * H * W, C), alpha=conditioning_scale)
-        return out, m.reshape(B, H, W, C)
+                       residual=unet_mid.reshape(B * H * W, C), alpha=conditioning_scale, rows_per_batch=H * W,
+                       gn_stats=self.P.gn_bucket)
+        return out, ops.carry_stats(m.reshape(B, H, W, C), m)
 
     def residuals(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk, unet_skips: List[torch.Tensor],
                   unet_mid: torch.Tensor, conditioning_scale: float = 1.0):

@@ -12,7 +12,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .configs import VAEConfig
-from .ops import Ops
+from .ops import Ops, gn_bucket_for
 from .unet import LATENT_CPAD, _Conv, _Params, _ResBlock
 
 RGB_CPAD = 8  # decoded image travels as [B, H, W, 8] fp16 (3 real channels)
@@ -26,11 +26,12 @@ class DeviceVAEDecoder:
         ch = cfg.block_out_channels
         top = ch[-1]
         lc = cfg.latent_channels
+        P.gn_bucket = gn_bucket_for(ch, g)
         # post_quant_conv (1x1, 4 -> 4) as a linear over 8-channel padded pixels
         wq = torch.zeros(lc, LATENT_CPAD, dtype=torch.float16)
         wq[:, :lc] = P.host16("post_quant_conv.weight").reshape(lc, lc)
         self.pq_w, self.pq_b = wq.to(ops.device), P.f32("post_quant_conv.bias")
-        self.conv_in = _Conv(P, "decoder.conv_in", cin_layout=(lc, LATENT_CPAD))
+        self.conv_in = _Conv(P, "decoder.conv_in", cin_layout=(lc, LATENT_CPAD), gn=True)
         self.mid0 = _ResBlock(P, "decoder.mid_block.resnets.0", (top,), g, eps)
         self.mid1 = _ResBlock(P, "decoder.mid_block.resnets.1", (top,), g, eps)
         a = "decoder.mid_block.attentions.0"
@@ -46,7 +47,7 @@ class DeviceVAEDecoder:
             for j in range(cfg.layers_per_block + 1):
                 res.append(_ResBlock(P, f"decoder.up_blocks.{i}.resnets.{j}", (prev,), g, eps))
                 prev = cout
-            us = _Conv(P, f"decoder.up_blocks.{i}.upsamplers.0.conv") if i < len(ch) - 1 else None
+            us = _Conv(P, f"decoder.up_blocks.{i}.upsamplers.0.conv", gn=True) if i < len(ch) - 1 else None
             self.up.append((res, us))
         self.out_g, self.out_b = P.f32("decoder.conv_norm_out.weight"), P.f32("decoder.conv_norm_out.bias")
         self.conv_out = _Conv(P, "decoder.conv_out")
@@ -67,9 +68,10 @@ class DeviceVAEDecoder:
             s = ops.linear(q, k, out_fp32=True)           # fp32 scores: |q.k| over 512 dims is too coarse in fp16
             pr = ops.softmax_rows(s, scale=C ** -0.5)
             o = ops.linear(pr, vt, bias=self.bv)
-            outs.append(ops.linear(o, self.wo, bias=self.bo, residual=h[b].reshape(T, C)))
+            outs.append(ops.linear(o, self.wo, bias=self.bo, residual=h[b].reshape(T, C),
+                                   gn_stats=self.P.gn_bucket if B == 1 else 0))
         out = outs[0] if B == 1 else torch.cat(outs, dim=0)
-        return out.reshape(B, H, W, C)
+        return ops.carry_stats(out.reshape(B, H, W, C), out)
 
     def decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """z: [B, h, w, 8] fp16 latents already divided by scaling_factor -> [B, 8h, 8w, 8] fp16 (RGB in 0..2)."""

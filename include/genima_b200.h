@@ -72,7 +72,15 @@ typedef struct gn_epilogue {
    * would need more partials are not considered). */
   void* rowstats_out;
   int32_t rowstats_capacity;
-  int32_t reserved;
+  /* GroupNorm statistics of this GEMM's fp16 output for the gn_group_norm_apply that normalises it (ResnetBlock2D
+   * norm1/norm2, Transformer2DModel.norm, conv_norm_out): channels are grouped in buckets of `gn_bucket` (even, divides
+   * the output columns and the consumer's channels-per-group) and the (sum, sumsq) of every (image, bucket) is ADDED,
+   * as 2^20-scaled 64-bit fixed point, to gnstats_out = uint64 [images][N_out / gn_bucket][2], which the caller zeroes
+   * beforehand.  Integer accumulation makes the result independent of CTA arrival order (bit-reproducible).  Image of
+   * row m = m / rows_per_batch; rows_per_batch must be a multiple of 128, or a power of two in [16, 64].  The separate
+   * statistics pass over HBM (and its grid barrier) disappears. */
+  int32_t gn_bucket;
+  void* gnstats_out;
 } gn_epilogue;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------- */
@@ -91,6 +99,9 @@ int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits);
  * global-memory access, so their set-up (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
  * previous kernel in the stream, also inside a captured CUDA graph.  enable = 0 restores ordinary launches. */
 int gn_set_pdl(gn_handle* h, int enable);
+/* GEMM epilogues stage the finished fp16 tile in shared memory and write it with one TMA store per sub-tile (the
+ * residual tile is prefetched the same way while the MMAs run); enable = 0 restores per-thread global stores (A/B). */
+int gn_set_staged_epilogue(gn_handle* h, int enable);
 /* gn_group_norm synchronises its CTAs with a grid barrier, so all of them must be co-resident: the grid never exceeds
  * the SM count.  When two streams may each run a gn_group_norm at the same time (each through its OWN handle), cap both
  * at half the SMs with this call; 0 restores the default. */
@@ -100,6 +111,15 @@ int gn_set_gn_max_ctas(gn_handle* h, int max_ctas);
  * fastest; later calls, and calls made while the stream is being captured into a CUDA graph, use the cache.
  * enable = 0 keeps the pure model; enable = -1 also clears the cache. */
 int gn_set_autotune(gn_handle* h, int enable);
+/* W-tile TMA multicast: the CTAs computing the m-tiles of one n-tile form clusters of up to max_cluster (1, 2 or 4) CTAs
+ * that fetch one slice of the weight tile each and multicast it to the others (less L2 traffic on shapes where many
+ * m-tiles re-read the same weights).  force_cluster = 2 / 4 uses that size wherever it applies (tests, A/B); 0 = autotuned. */
+int gn_set_gemm_multicast(gn_handle* h, int max_cluster, int force_cluster);
+/* Halo mode of gn_conv2d (3x3, stride 1, pad 1, C % 64 == 0, output width % 8 == 0): every CTA fetches, per
+ * 64-channel block, three 8 x (16 + 2) pixel column strips (one per horizontal tap offset) and feeds the three vertical
+ * taps of each to the tensor core as atom-aligned shared-memory windows of the strip, instead of fetching a 128-pixel
+ * tile for each of the nine taps (3x less activation traffic into the SM).  enable = 0 restores per-tap loads (A/B). */
+int gn_set_conv_halo(gn_handle* h, int enable, int base_offset_field);
 /* Force the operand-ring sizing of the next GEMM-class calls for 1 or 2 resident CTAs per SM (0 = heuristic). */
 int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm);
 /* Debug aid: when dptr (device uint64[8]) is non-NULL, CTA (0,0,0) of every following GEMM-class launch writes
@@ -162,6 +182,12 @@ int gn_attention_small(gn_handle* h, const void* q, int64_t ldq, const void* k, 
  * pairs produced by a GEMM epilogue are used instead of a reduction pass.  Replaces torch group_norm + silu + cat. */
 int gn_group_norm(gn_handle* h, const void* x0, int C0, const void* x1, int C1, int B, int HW, int groups, float eps,
                   const float* gamma, const float* beta, int silu, const float* stats_in, void* y, void* stream);
+/* GroupNorm from statistics accumulated by the producing GEMM epilogues (gn_epilogue.gnstats_out): one elementwise pass,
+ * no reduction, no grid barrier.  stats0 / stats1: uint64 [B][C0 / bucket][2] / [B][C1 / bucket][2] of x0 / x1 (x1, stats1
+ * NULL without a concat); bucket must divide C0 and (C0 + C1) / groups.  Same result contract as gn_group_norm. */
+int gn_group_norm_apply(gn_handle* h, const void* x0, int C0, const void* stats0, const void* x1, int C1,
+                        const void* stats1, int bucket, int B, int HW, int groups, float eps, const float* gamma,
+                        const float* beta, int silu, void* y, void* stream);
 /* LayerNorm over the last dim of a [rows, C] fp16 matrix (fp32 statistics). */
 int gn_layer_norm(gn_handle* h, const void* x, int64_t ldx, int rows, int C, float eps, const float* gamma,
                   const float* beta, void* y, int64_t ldy, void* stream);

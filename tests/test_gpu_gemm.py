@@ -189,3 +189,61 @@ def test_layer_norm_folded_into_gemm(ops, M, C, N, geglu):
     err = float((out.float().cpu() - ref).abs().max() / ref.abs().max())
     print(f"LN folded into GEMM M={M} C={C} N={N} geglu={geglu}: normalised max err {err:.3e}, {st.parts} row partials")
     assert err < 3e-3
+
+
+@pytest.mark.parametrize("M,N,K,residual", [(4096, 320, 320, True), (1024, 1920, 640, False), (300, 80, 256, True),
+                                            (77, 1280, 1024, False), (130, 48, 72, True)])
+def test_linear_direct_epilogue_matches_staged(ops, M, N, K, residual):
+    """A/B: per-thread global stores (gn_set_staged_epilogue 0) and the TMA-stored staged tile give the same bits."""
+    a = _rand((M, K), 30)
+    w = _rand((N, K), 31, K ** -0.5)
+    bias = torch.randn(N) * 0.1
+    kw = dict(bias=bias.cuda())
+    if residual:
+        kw["residual"] = _rand((M, N), 32).cuda()
+    ops.set_gemm_tuning(64 if N >= 64 else 48, 1)   # same tile configuration on both sides: same summation order
+    try:
+        staged = ops.linear(a.cuda(), w.cuda(), **kw)
+        ops.handle.check(ops.lib.gn_set_staged_epilogue(ops.h, 0), "gn_set_staged_epilogue")
+        direct = ops.linear(a.cuda(), w.cuda(), **kw)
+    finally:
+        ops.handle.check(ops.lib.gn_set_staged_epilogue(ops.h, 1), "gn_set_staged_epilogue")
+        ops.set_gemm_tuning(0, 0)
+    report_close(f"linear staged {M}x{N}x{K}", staged,
+                 ops_ref.linear_ref(a, w, bias=bias, residual=kw.get("residual")))
+    assert torch.equal(staged, direct)
+
+
+def test_linear_strided_output_and_residual(ops):
+    # out / residual are column slices of wider matrices (row stride > N): staged TMA stores must respect ldo / ldr
+    M, N, K = 512, 320, 256
+    a = _rand((M, K), 33)
+    w = _rand((N, K), 34, K ** -0.5)
+    big_res = _rand((M, 2 * N), 35).cuda()
+    big_out = torch.zeros(M, 3 * N, dtype=torch.float16, device="cuda")
+    ops.linear(a.cuda(), w.cuda(), residual=big_res[:, N:], out=big_out[:, N:2 * N])
+    report_close("linear strided", big_out[:, N:2 * N], ops_ref.linear_ref(a, w, residual=big_res[:, N:].cpu()))
+    assert float(big_out[:, :N].abs().max()) == 0.0 and float(big_out[:, 2 * N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mc", [2, 4])
+@pytest.mark.parametrize("M,N,K,residual", [(4096, 320, 320, True), (1024, 1920, 640, False), (512, 256, 1024, True)])
+def test_linear_w_multicast(ops, mc, M, N, K, residual):
+    """W-tile TMA multicast across clusters of m-tiles (gn_set_gemm_multicast) must not change the result."""
+    a = _rand((M, K), 40)
+    w = _rand((N, K), 41, K ** -0.5)
+    bias = torch.randn(N) * 0.1
+    kw = dict(bias=bias.cuda())
+    if residual:
+        kw["residual"] = _rand((M, N), 42).cuda()
+    ops.handle.check(ops.lib.gn_set_gemm_multicast(ops.h, 4, mc), "gn_set_gemm_multicast")
+    ops.set_gemm_tuning(64, 1)
+    try:
+        out = ops.linear(a.cuda(), w.cuda(), **kw)
+        cfg = ops.last_gemm_config()
+    finally:
+        ops.handle.check(ops.lib.gn_set_gemm_multicast(ops.h, 4, 0), "gn_set_gemm_multicast")
+        ops.set_gemm_tuning(0, 0)
+    assert cfg[3] < 0 and -cfg[3] % mc == 0, f"multicast not applied: cfg={cfg}"
+    report_close(f"linear multicast x{mc} {M}x{N}x{K}", out,
+                 ops_ref.linear_ref(a, w, bias=bias, residual=kw.get("residual")))

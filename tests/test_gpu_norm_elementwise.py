@@ -139,3 +139,88 @@ def test_tile_untile_views(ops):
     ref[:, 256:, 256:] = views[:, 3]
     assert torch.equal(tile.cpu(), ref)
     assert torch.equal(ops.untile_views(tile).cpu(), views)
+
+
+# ---- GroupNorm statistics accumulated by the producing GEMM epilogue (gn_epilogue.gnstats_out) + gn_group_norm_apply
+def _fused_gn_check(ops, name, y, gamma, beta, groups, silu, x1=None):
+    """y (and x1) carry gn_stats: the apply kernel must agree with the oracle GroupNorm of the SAME fp16 tensors."""
+    assert getattr(y, "gn_stats", None) is not None, f"{name}: the producer did not attach statistics"
+    calls0 = ops.gn_apply_calls
+    out = ops.group_norm(y, gamma.cuda(), beta.cuda(), groups=groups, eps=1e-5, silu=silu, x1=x1)
+    assert ops.gn_apply_calls == calls0 + 1, f"{name}: the statistics were not used"
+    ref = ops_ref.group_norm_ref(y.cpu(), gamma, beta, groups, 1e-5, silu, x1=None if x1 is None else x1.cpu())
+    report_close(name, out, ref)
+
+
+@pytest.mark.parametrize("B,HW,K,N,bucket,splits", [
+    (1, 4096, 320, 320, 10, 0), (1, 1024, 640, 640, 10, 0), (1, 256, 1280, 1280, 10, 0), (2, 64, 1280, 1280, 10, 0),
+    (1, 64, 2560, 1280, 10, 4), (1, 256, 1280, 640, 10, 2), (1, 4096, 512, 512, 4, 0), (3, 16, 64, 96, 2, 0),
+    (1, 4096, 1280, 320, 10, 2),
+])
+def test_fused_gn_stats_linear(ops, B, HW, K, N, bucket, splits):
+    a = _rand((B * HW, K), 20)
+    w = _rand((N, K), 21, K ** -0.5)
+    bias = torch.randn(N) * 0.5
+    res = _rand((B * HW, N), 22)
+    ops.gn_stats_reset()
+    if splits:
+        ops.set_gemm_tuning(0, splits)
+    try:
+        y = ops.linear(a.cuda(), w.cuda(), bias=bias.cuda(), residual=res.cuda(), rows_per_batch=HW, gn_stats=bucket)
+        cfg = ops.last_gemm_config()
+    finally:
+        ops.set_gemm_tuning(0, 0)
+    if splits:
+        assert cfg[1] == splits
+    report_close("producer", y, ops_ref.linear_ref(a, w, bias=bias, residual=res))
+    groups = 32 if N % 32 == 0 and (N // 32) % bucket == 0 else N // bucket // 2
+    gamma = 1.0 + 0.1 * torch.randn(N)
+    beta = 0.1 * torch.randn(N)
+    _fused_gn_check(ops, f"fused GN linear B{B} HW{HW} N{N} splits{splits}", ops.carry_stats(y.reshape(B, HW, N), y),
+                    gamma, beta, groups, True)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,stride,bucket", [
+    (1, 64, 320, 320, 1, 10), (1, 32, 640, 640, 1, 10), (2, 8, 1280, 1280, 1, 10), (1, 16, 640, 1280, 1, 10),
+    (1, 64, 320, 320, 2, 10), (1, 128, 128, 128, 1, 4), (1, 12, 64, 64, 1, 2), (2, 4, 64, 128, 1, 2),
+])
+def test_fused_gn_stats_conv(ops, B, H, Cin, Cout, stride, bucket):
+    from genima_b200.packing import pack_conv_weight
+
+    x = _rand((B, H, H, Cin), 23)
+    w = _rand((Cout, Cin, 3, 3), 24, (9 * Cin) ** -0.5)
+    bias = torch.randn(Cout) * 0.5
+    ops.gn_stats_reset()
+    y = ops.conv2d(x.cuda(), pack_conv_weight(w).cuda(), Cout, stride=stride, bias=bias.cuda(), gn_stats=bucket)
+    gamma = 1.0 + 0.1 * torch.randn(Cout)
+    beta = 0.1 * torch.randn(Cout)
+    groups = 32 if (Cout // 32) % bucket == 0 else Cout // bucket
+    _fused_gn_check(ops, f"fused GN conv B{B} {H}^2 {Cin}->{Cout} s{stride}", y, gamma, beta, groups, True)
+
+
+def test_fused_gn_stats_concat(ops):
+    # up-block norm1 over concat(hidden 1280, skip 640): 60 channels per group, buckets of 10 from two producers
+    B, HW = 1, 1024
+    ops.gn_stats_reset()
+    ys = []
+    for i, n in enumerate((1280, 640)):
+        a = _rand((B * HW, 320), 30 + i)
+        w = _rand((n, 320), 40 + i, 320 ** -0.5)
+        y = ops.linear(a.cuda(), w.cuda(), rows_per_batch=HW, gn_stats=10)
+        ys.append(ops.carry_stats(y.reshape(B, 32, 32, n), y))
+    gamma = 1.0 + 0.1 * torch.randn(1920)
+    beta = 0.1 * torch.randn(1920)
+    _fused_gn_check(ops, "fused GN concat 1280+640", ys[0], gamma, beta, 32, True, x1=ys[1])
+
+
+def test_fused_gn_stats_expire_on_reset(ops):
+    a = _rand((256, 320), 50)
+    w = _rand((320, 320), 51, 320 ** -0.5)
+    ops.gn_stats_reset()
+    y = ops.linear(a.cuda(), w.cuda(), gn_stats=10)
+    ops.gn_stats_reset()   # the arena is recycled: y's statistics must not be used any more
+    gamma, beta = torch.ones(320), torch.zeros(320)
+    calls0 = ops.gn_apply_calls
+    out = ops.group_norm(ops.carry_stats(y.reshape(1, 256, 320), y), gamma.cuda(), beta.cuda())
+    assert ops.gn_apply_calls == calls0
+    report_close("GN after reset", out, ops_ref.group_norm_ref(y.cpu().reshape(1, 256, 320), gamma, beta, 32, 1e-5))

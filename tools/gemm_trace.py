@@ -8,8 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from genima_b200.ops import Ops  # noqa: E402
 
 ops = Ops(0, workspace_mb=256)
-tr = torch.zeros(8, dtype=torch.int64, device="cuda")
-names = ["start", "setup", "tma0", "ops0", "mma_issued", "acc_done", "epi_done", "exit"]
+tr = torch.zeros(16, dtype=torch.int64, device="cuda")
+names = ["start", "setup", "tma0", "ops0", "mma_issued", "acc_done", "epi_done", "exit", "chunks", "bar", "st_issued", "gn", "st_read"]
 for (M, N, K, res) in [(4096, 320, 320, True), (4096, 320, 1280, True), (4096, 960, 320, False), (1024, 640, 640, True),
                        (256, 1280, 1280, True), (64, 1280, 1280, True), (4096, 512, 512, False)]:
     a = torch.randn(M, K, device="cuda").half()
@@ -31,7 +31,8 @@ for (M, N, K, res) in [(4096, 320, 320, True), (4096, 320, 1280, True), (4096, 9
         e1.record()
         torch.cuda.synchronize()
         ops.lib.gn_set_gemm_trace(ops.h, None)
-        t = tr.cpu().tolist()
-        rel = [(x - t[0]) / 1e3 for x in t]
+        t = tr.cpu().tolist()[:len(names)]
+        rel = [(x - t[0]) / 1e3 if x else float("nan") for x in t]
+        tr.zero_()
         print(f"M{M} N{N} K{K} cfg{ops.last_gemm_config()} {'cold' if cold else 'warm'} events {e0.elapsed_time(e1) * 1e3:.1f} us | "
               + " ".join(f"{n}={r:.2f}" for n, r in zip(names, rel)))

@@ -49,6 +49,22 @@ def main():
             t = graph_time(lambda: ops.group_norm(x0, g, b, 32, 1e-5, silu=True, x1=x1, out=out))
             mb = hw * hw * (c0 + c1) * 4 / 1e6
             print(f"gn {hw:3d}^2 C={c0}+{c1}: {t:7.2f} us  ({mb:6.1f} MB moved -> {mb / t * 1e3:7.1f} GB/s)", flush=True)
+    if which == "gnapply":
+        # GroupNorm from statistics accumulated by the producing GEMM epilogue (gn_group_norm_apply)
+        for (hw, c, bucket) in [(64, 320, 10), (32, 640, 10), (16, 1280, 10), (8, 1280, 10), (64, 512, 4), (128, 512, 4),
+                                (256, 256, 4), (512, 128, 4)]:
+            a = torch.randn(hw * hw, 64, device="cuda").half()
+            w = torch.randn(c, 64, device="cuda").half() * 0.125
+            ops.gn_stats_reset()
+            y = ops.linear(a, w, gn_stats=bucket)
+            x = ops.carry_stats(y.reshape(1, hw, hw, c), y)
+            g, b = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+            out = torch.empty(1, hw, hw, c, device="cuda", dtype=torch.float16)
+            n0 = ops.gn_apply_calls
+            t = graph_time(lambda: ops.group_norm(x, g, b, 32, 1e-5, silu=True, out=out))
+            assert ops.gn_apply_calls > n0
+            mb = hw * hw * c * 4 / 1e6
+            print(f"gn_apply {hw:3d}^2 C={c}: {t:7.2f} us  ({mb:6.1f} MB moved -> {mb / t * 1e3:7.1f} GB/s)", flush=True)
     if which == "ln":
         for (rows, c) in [(4096, 320), (1024, 640), (256, 1280), (64, 1280), (258, 256), (77, 1024)]:
             x = torch.randn(rows, c, device="cuda").half()
