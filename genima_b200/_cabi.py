@@ -45,6 +45,8 @@ class GnEpilogue(C.Structure):
         ("rowstats_capacity", C.c_int32),
         ("gn_bucket", C.c_int32),
         ("gnstats_out", C.c_void_p),
+        ("w_dynamic", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

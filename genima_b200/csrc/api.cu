@@ -179,6 +179,7 @@ int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm) {
 int gn_set_pdl(gn_handle* h, int enable) {
   if (!h) return GN_ERR_INVALID;
   h->pdl = enable != 0;
+  h->w_prefetch = enable == 1;
   return GN_OK;
 }
 

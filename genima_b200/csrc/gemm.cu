@@ -89,6 +89,8 @@ struct GemmParams {
   int halo;      // 1: halo mode (mode == 1 only)
   int halo_ncb;  // 64-channel blocks of the main input; k-blocks [0, 9 * halo_ncb) are ((cb, kx), ky), ky fastest
   int halo_bo;   // (unused) descriptor variant switch
+  int w_prefetch;  // 1: W is a constant weight matrix -- the producer requests the first W tiles BEFORE griddepcontrol.wait,
+                   // so weight streaming (cold in HBM at batch 1) overlaps the tail of the previous kernel
   int mcast;  // compact flavours: cluster size along grid.y whose CTAs share the W tile through TMA multicast (1 = off)
   // ---- output staging (see epilogue_tail): the epilogue warps write the finished fp16 tile into shared memory in the
   // layout of a TMA box {io_w columns, 128 rows} per sub-tile (swizzle span = 2 * io_w bytes) and ONE thread stores it with
@@ -107,6 +109,7 @@ struct GemmParams {
   int gn_rows;                 // rows per column-pass row group (16 / 32 / 64 / 128)
   int gn_img_rows;             // rows of one image inside a 128-row tile (<= 128, multiple of gn_rows)
   int gn_stat_images;          // host-side: images covered by gn_out
+  int w_dynamic;  // host-side: W is produced by an earlier kernel of the stream (no early prefetch)
   int dbg;    // experiment switches (GENIMA_B200_DBG): 1 skip scale/bias smem reads, 2 skip staging stores, 4 skip tmem_ld
   float* ws;  // (unused) split-K workspace
   int rs_capacity;            // host-side: capacity (partials per row) of epi.rs_out
@@ -723,24 +726,36 @@ __device__ __forceinline__ float* split_ws_ptr(const GemmParams& p, int rank, in
   return p.ws + ((((size_t)rank * ntiles + tile) * (p.block_n >> 4) + ch) * BLOCK_M + row) * 16;
 }
 
+__device__ __forceinline__ void st_cg_v8(float* dst, const uint32_t* r) {
+  asm volatile("st.global.cg.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_cg_v8(const float* src, float* t) {
+  asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
+               : "l"(src)
+               : "memory");
+}
+
 __device__ __forceinline__ void split_dump(const GemmParams& p, uint32_t taddr, int cw, int rank, int row, bool valid) {
   const int nchunks = p.block_n >> 4;
 #pragma unroll 1
   for (int ch = cw; ch < nchunks; ch += EPI_COLSPLIT) {
+    if (ch % p.splits == rank) continue;  // this rank finishes the chunk itself: its partial stays in tensor memory
     uint32_t r[16];
     tmem_ld_x16(taddr + (ch << 4), r);
     tmem_ld_wait();
     if (valid) {
-      float4* dst = reinterpret_cast<float4*>(split_ws_ptr(p, rank, ch, row));
-#pragma unroll
-      for (int f = 0; f < 4; ++f)
-        __stcg(dst + f, make_float4(__uint_as_float(r[4 * f]), __uint_as_float(r[4 * f + 1]),
-                                    __uint_as_float(r[4 * f + 2]), __uint_as_float(r[4 * f + 3])));
+      // two 32-byte stores per thread: whole L2 sectors (16-byte stores to 64-byte-strided rows write half sectors)
+      float* dst = split_ws_ptr(p, rank, ch, row);
+      st_cg_v8(dst, r);
+      st_cg_v8(dst + 8, r + 8);
     }
   }
 }
 
-__device__ __forceinline__ void split_finish(const GemmParams& p, int rank, int n0, int m, int b,
+__device__ __forceinline__ void split_finish(const GemmParams& p, uint32_t taddr, int rank, int n0, int m, int b,
                                              bool valid, int cw, const float* s_scale, const float* s_bias,
                                              const float* s_cs, int row, float ln_rstd, float ln_nmr, uint32_t io_base,
                                              float* s_col, int et, int m0, int x0, int y0, int b0) {
@@ -753,44 +768,44 @@ __device__ __forceinline__ void split_finish(const GemmParams& p, int rank, int 
     const int c = ch << 4;
     if (n0 + c >= e.N) break;
     float v[16];
+    uint32_t own[16];
+    tmem_ld_x16(taddr + c, own);  // this rank's own partial never left tensor memory
+    tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = 0.f;
     if (valid) {
-      // two partials (eight 16-byte L2 loads) in flight per thread; summed in rank order
+      // the S - 1 peer partials come from the L2 workspace, two (four 32-byte loads) in flight per thread; everything
+      // is summed in rank order, the own partial at its rank's position: deterministic
       int sr = 0;
-      for (; sr + 2 <= S; sr += 2) {
-        const float4* s0 = reinterpret_cast<const float4*>(split_ws_ptr(p, sr, ch, row));
-        const float4* s1 = reinterpret_cast<const float4*>(split_ws_ptr(p, sr + 1, ch, row));
-        float4 t[8];
+      while (sr < S) {
+        if (sr == rank) {
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          t[f] = __ldcg(s0 + f);
-          t[4 + f] = __ldcg(s1 + f);
+          for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(own[j]);
+          ++sr;
+          continue;
         }
+        const int sr1 = (sr + 1 == rank) ? sr + 2 : sr + 1;  // next peer after sr (skipping this rank)
+        if (sr1 < S && sr + 1 != rank) {
+          const float* s0 = split_ws_ptr(p, sr, ch, row);
+          const float* s1 = split_ws_ptr(p, sr1, ch, row);
+          float t0[16], t1[16];
+          ld_cg_v8(s0, t0);
+          ld_cg_v8(s0 + 8, t0 + 8);
+          ld_cg_v8(s1, t1);
+          ld_cg_v8(s1 + 8, t1 + 8);
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          v[4 * f] += t[f].x;
-          v[4 * f + 1] += t[f].y;
-          v[4 * f + 2] += t[f].z;
-          v[4 * f + 3] += t[f].w;
-        }
+          for (int j = 0; j < 16; ++j) v[j] += t0[j];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          v[4 * f] += t[4 + f].x;
-          v[4 * f + 1] += t[4 + f].y;
-          v[4 * f + 2] += t[4 + f].z;
-          v[4 * f + 3] += t[4 + f].w;
-        }
-      }
-      if (sr < S) {
-        const float4* s0 = reinterpret_cast<const float4*>(split_ws_ptr(p, sr, ch, row));
+          for (int j = 0; j < 16; ++j) v[j] += t1[j];
+          sr += 2;
+        } else {
+          const float* s0 = split_ws_ptr(p, sr, ch, row);
+          float t0[16];
+          ld_cg_v8(s0, t0);
+          ld_cg_v8(s0 + 8, t0 + 8);
 #pragma unroll
-        for (int f = 0; f < 4; ++f) {
-          const float4 t = __ldcg(s0 + f);
-          v[4 * f] += t.x;
-          v[4 * f + 1] += t.y;
-          v[4 * f + 2] += t.z;
-          v[4 * f + 3] += t.w;
+          for (int j = 0; j < 16; ++j) v[j] += t0[j];
+          ++sr;
         }
       }
     }
@@ -1015,6 +1030,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   // Everything above touched only this CTA's shared / tensor memory.  Let the next kernel's CTAs be scheduled, then wait
   // for the previous kernel in the stream before the first global-memory access (programmatic dependent launch).
   pdl_trigger();
+  int w_pre = 0;  // k-blocks whose W tile was requested ahead of the dependency wait (producer thread only)
+  if (p.w_prefetch && !mcast_on && !p.halo && warp == 0 && lane == 0) {
+    const int kb0 = blockIdx.z * p.kb_per_split;
+    const int nit = min(p.num_kblocks, kb0 + p.kb_per_split) - kb0;
+    w_pre = min(nit, stages);
+    for (int it = 0; it < w_pre; ++it) {
+      mbar_expect_tx(&full_bar[it], b_stage_bytes);
+      tma_load_2d(smem_b + it * b_stage_bytes, &p.tmB, &full_bar[it], (kb0 + it) * BLOCK_K, n0);
+    }
+  }
   pdl_wait();
   if (mcast_on) cluster_wait();  // (arrived above: complete long before the previous kernel has drained)
   const uint32_t tmem_base = *tmem_slot;
@@ -1117,7 +1142,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         const int s = it % stages;
         const uint32_t ph = (it / stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        mbar_arrive_expect_tx(&full_bar[s], it < w_pre ? (uint32_t)A_STAGE_BYTES : tx_bytes);
         const int kb = kb_begin + it;
         if (p.mode == 0) {
           tma_load_2d(smem_a + s * A_STAGE_BYTES, &p.tmA[0], &full_bar[s], kb * BLOCK_K, m0);
@@ -1136,7 +1161,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
           const int r = (int)cluster_ctarank();
           tma_load_2d_mcast(smem_b + s * b_stage_bytes + r * slice_rows * (BLOCK_K * 2), &p.tmB, &full_bar[s],
                             kb * BLOCK_K, n0 + r * slice_rows, static_cast<uint16_t>((1u << p.mcast) - 1u));
-        } else {
+        } else if (it >= w_pre) {
           tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
         }
         if (it == 0) trace_stamp(p, 2);
@@ -1342,8 +1367,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         for (int ch = rank; ch < (block_n >> 4) && n0 + (ch << 4) < p.epi.N; ch += p.splits) ++owned;
         if (owned > 0) mbar_wait(res_full_bar, 0);
       }
-      split_finish(p, rank, n0, m, b, valid, cw, s_scale, s_bias, s_cs, row, ln_rstd, ln_nmr, io_base, s_col,
-                   threadIdx.x - 64, m0, x0, y0, b0);
+      tc_fence_after();
+      split_finish(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16), rank, n0, m, b, valid, cw, s_scale, s_bias,
+                   s_cs, row, ln_rstd, ln_nmr, io_base, s_col, threadIdx.x - 64, m0, x0, y0, b0);
+      tc_fence_before();
     }
     if (threadIdx.x == 64) trace_stamp(p, 11);
   }
@@ -1696,6 +1723,7 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
     if (rc) return rc;
   }
   p.mcast = tc.mcast;
+  p.w_prefetch = (h->w_prefetch && !p.w_dynamic) ? 1 : 0;
   // epilogue staging: layout, sub-tile width and the output / residual tensor maps
   const SmemLayout L = smem_layout(tc.block_n, tc.stages, tc.splits, og);
   const int bn_out = og.geglu ? tc.block_n / 2 : tc.block_n;
@@ -1711,7 +1739,7 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
     GN_CHECK_ARG(h, h->workspace && need <= h->workspace_bytes,
                  "split-K needs %lld bytes of workspace (gn_set_workspace)", (long long)need);
   }
-  if (split_fast) p.io_lw = 4;  // every 16-column chunk is its own TMA box: each rank stores the chunks it finished
+  if (split_fast) p.io_lw = 4;
   if (og.gn && split_fast) {
     const int owned_cols = gn::ceil_div(tc.block_n >> 4, tc.splits) << 4;
     GN_CHECK_ARG(h, gn_rows_for(owned_cols, og.img_rows) > 0, "GroupNorm statistics: split tile unsupported");
@@ -1868,6 +1896,7 @@ extern "C" int gn_linear(gn_handle* h, const void* A, int64_t lda, int M, int K,
   if (rc) return rc;
   p.epi.ln_dim = K;
   p.mode = 0;
+  p.w_dynamic = (epi && epi->w_dynamic) ? 1 : 0;
   p.num_kblocks = ceil_div(K, BLOCK_K);
   p.num_segs = 1;
   p.segs[0].nblk = p.num_kblocks;

@@ -90,8 +90,8 @@ class Ops:
                           "gn_set_workspace")
         # tile configurations are measured once per problem shape (first eager call) and cached in the handle
         self.handle.check(self.lib.gn_set_autotune(self.h, 1 if autotune else 0), "gn_set_autotune")
-        if os.environ.get("GENIMA_B200_PDL", "1") == "0":   # A/B switch for programmatic dependent launch
-            self.handle.check(self.lib.gn_set_pdl(self.h, 0), "gn_set_pdl")
+        if os.environ.get("GENIMA_B200_PDL", "1") != "1":   # A/B: 0 = ordinary launches, 2 = PDL without weight prefetch
+            self.handle.check(self.lib.gn_set_pdl(self.h, int(os.environ["GENIMA_B200_PDL"])), "gn_set_pdl")
         if os.environ.get("GENIMA_B200_STAGED", "1") == "0":   # A/B switch for the TMA-stored GEMM epilogue
             self.handle.check(self.lib.gn_set_staged_epilogue(self.h, 0), "gn_set_staged_epilogue")
         halo = os.environ.get("GENIMA_B200_HALO")   # "enable[,base_offset_field]": halo-mode convolutions (A/B)
@@ -118,7 +118,8 @@ class Ops:
 
     def _epilogue(self, M: int, N: int, bias=None, scale=None, rowvec=None, rows_per_batch: int = 0, residual=None,
                   act_pre=None, act_post=None, alpha: float = 1.0, beta: float = 1.0, geglu: bool = False,
-                  out_fp32: bool = False, ln=None, row_stats=None, gn_stats: Optional[GNStats] = None) -> GnEpilogue:
+                  out_fp32: bool = False, ln=None, row_stats=None, gn_stats: Optional[GNStats] = None,
+                  w_dynamic: bool = False) -> GnEpilogue:
         e = GnEpilogue()
         e.scale = _ptr(_f32(scale, "scale"))
         e.bias = _ptr(_f32(bias, "bias"))
@@ -160,6 +161,7 @@ class Ops:
         if gn_stats is not None:
             e.gnstats_out = gn_stats.buf.data_ptr()
             e.gn_bucket = gn_stats.bucket
+        e.w_dynamic = 1 if w_dynamic else 0   # `w` is an activation of this stream, not a constant weight matrix
         return e
 
     # ------------------------------------------------------------------------------------------------ GroupNorm statistics

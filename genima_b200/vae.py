@@ -64,10 +64,11 @@ class DeviceVAEDecoder:
             k = ops.linear(nb, self.wk, bias=self.bk)
             # V^T [C, T] = Wv @ n^T: the value projection with operands swapped, so P V needs no transpose kernel.
             # Its bias is added after P V instead (softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T).
-            vt = ops.linear(self.wv, nb)
-            s = ops.linear(q, k, out_fp32=True)           # fp32 scores: |q.k| over 512 dims is too coarse in fp16
+            # (w_dynamic: the "weight" operand of these three GEMMs is an activation produced just before)
+            vt = ops.linear(self.wv, nb, w_dynamic=True)
+            s = ops.linear(q, k, out_fp32=True, w_dynamic=True)   # fp32 scores: |q.k| over 512 dims is too coarse in fp16
             pr = ops.softmax_rows(s, scale=C ** -0.5)
-            o = ops.linear(pr, vt, bias=self.bv)
+            o = ops.linear(pr, vt, bias=self.bv, w_dynamic=True)
             outs.append(ops.linear(o, self.wo, bias=self.bo, residual=h[b].reshape(T, C),
                                    gn_stats=self.P.gn_bucket if B == 1 else 0))
         out = outs[0] if B == 1 else torch.cat(outs, dim=0)

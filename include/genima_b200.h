@@ -81,6 +81,11 @@ typedef struct gn_epilogue {
    * statistics pass over HBM (and its grid barrier) disappears. */
   int32_t gn_bucket;
   void* gnstats_out;
+  /* gn_linear only: W is not a constant weight matrix but the output of an earlier kernel in the stream (attention
+   * scores Q K^T, P V).  Constant weights are requested by the TMA producer BEFORE the programmatic-dependent-launch
+   * wait, so that (cold, HBM-resident) weight tiles stream in while the previous kernel drains. */
+  int32_t w_dynamic;
+  int32_t reserved;
 } gn_epilogue;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------------- */
@@ -97,7 +102,8 @@ int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits);
 /* Programmatic dependent launch (default on): gn_linear / gn_conv2d / gn_attention* / gn_group_norm / gn_layer_norm are
  * launched with cudaLaunchAttributeProgrammaticStreamSerialization and execute griddepcontrol.wait before their first
  * global-memory access, so their set-up (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail of the
- * previous kernel in the stream, also inside a captured CUDA graph.  enable = 0 restores ordinary launches. */
+ * previous kernel in the stream, also inside a captured CUDA graph.  enable = 0 restores ordinary launches; enable = 2
+ * keeps the dependent launch but switches the early weight prefetch of the GEMM producer off (A/B). */
 int gn_set_pdl(gn_handle* h, int enable);
 /* GEMM epilogues stage the finished fp16 tile in shared memory and write it with one TMA store per sub-tile (the
  * residual tile is prefetched the same way while the MMAs run); enable = 0 restores per-thread global stores (A/B). */

@@ -51,8 +51,9 @@ def test_version_and_no_driver_error_code(lib_path):
 def test_epilogue_struct_layout_matches_header():
     from genima_b200._cabi import GnEpilogue
 
-    # 4 pointers, int64, 3 x int32, 2 x float, 2 x int32, pad, 2 pointers, int32, float, pointer, 2 x int32, pointer
-    assert ctypes.sizeof(GnEpilogue) == 4 * 8 + 8 + 3 * 4 + 2 * 4 + 2 * 4 + 4 + 2 * 8 + 4 + 4 + 8 + 2 * 4 + 8
+    # 4 pointers, int64, 3 x int32, 2 x float, 2 x int32, pad, 2 pointers, int32, float, pointer, 2 x int32, pointer,
+    # 2 x int32
+    assert ctypes.sizeof(GnEpilogue) == 4 * 8 + 8 + 3 * 4 + 2 * 4 + 2 * 4 + 4 + 2 * 8 + 4 + 4 + 8 + 2 * 4 + 8 + 2 * 4
     assert GnEpilogue.ldr.offset == 32 and GnEpilogue.ln_stats.offset == 72 and GnEpilogue.rowstats_out.offset == 96
     assert GnEpilogue.gn_bucket.offset == 108 and GnEpilogue.gnstats_out.offset == 112
 
