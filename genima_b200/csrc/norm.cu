@@ -283,7 +283,7 @@ struct GNApplyParams {
 
 constexpr int GNA_THREADS = 256;
 
-__global__ void __launch_bounds__(GNA_THREADS) gn_apply_kernel(const GNApplyParams p) {
+__global__ void __launch_bounds__(GNA_THREADS, 4) gn_apply_kernel(const GNApplyParams p) {
   extern __shared__ __align__(16) uint8_t gna_smem[];
   float* sc = reinterpret_cast<float*>(gna_smem);  // [C] gamma -> scale, then [C] beta -> shift
   float* sh = sc + p.C;
@@ -298,24 +298,28 @@ __global__ void __launch_bounds__(GNA_THREADS) gn_apply_kernel(const GNApplyPara
   }
   pdl_trigger();
   pdl_wait();  // x and the statistics come from the previous kernels in the stream
-  // this CTA's share of the image's 16-byte vectors; the first vectors are requested before the statistics are reduced
+  // this CTA's share of the image's 16-byte vectors, processed in batches of PF vectors per thread (all loads of a
+  // batch in flight together); the first batch is requested before the statistics are reduced
   const int64_t nvec = (int64_t)p.HW * p.NV;
   const int64_t per = (nvec + p.ctas_per_b - 1) / p.ctas_per_b;
   const int64_t v_begin = (int64_t)ci * per;
   const int64_t v_end = min(nvec, v_begin + per);
   constexpr int PF = 4;
   uint4 pre[PF];
+  auto load_batch = [&](int64_t base) {
 #pragma unroll
-  for (int i = 0; i < PF; ++i) {
-    const int64_t v = v_begin + t + (int64_t)i * GNA_THREADS;
-    if (v < v_end) {
-      const int pix = (int)(v / p.NV);
-      const int c0 = (int)(v - (int64_t)pix * p.NV) * 8;
-      const __half* src = (c0 < p.C0) ? p.x0 + ((int64_t)b * p.HW + pix) * p.C0 + c0
-                                      : p.x1 + ((int64_t)b * p.HW + pix) * p.C1 + (c0 - p.C0);
-      pre[i] = __ldg(reinterpret_cast<const uint4*>(src));
+    for (int i = 0; i < PF; ++i) {
+      const int64_t v = base + t + (int64_t)i * GNA_THREADS;
+      if (v < v_end) {
+        const int pix = (int)(v / p.NV);
+        const int c0 = (int)(v - (int64_t)pix * p.NV) * 8;
+        const __half* src = (c0 < p.C0) ? p.x0 + ((int64_t)b * p.HW + pix) * p.C0 + c0
+                                        : p.x1 + ((int64_t)b * p.HW + pix) * p.C1 + (c0 - p.C0);
+        pre[i] = __ldg(reinterpret_cast<const uint4*>(src));
+      }
     }
-  }
+  };
+  load_batch(v_begin);
   if (t < p.G) {
     // exact integer totals of the group's buckets (each bucket lies entirely in x0 or in x1)
     long long s1 = 0, s2 = 0;
@@ -356,48 +360,48 @@ __global__ void __launch_bounds__(GNA_THREADS) gn_apply_kernel(const GNApplyPara
     sc[c] = a;
   }
   __syncthreads();
-  for (int64_t v = v_begin + t, i = 0; v < v_end; v += GNA_THREADS, ++i) {
-    const int pix = (int)(v / p.NV);
-    const int c0 = (int)(v - (int64_t)pix * p.NV) * 8;
-    uint4 q;
-    if (i < PF) {
-      q = pre[0];
+  for (int64_t base = v_begin; base < v_end; base += (int64_t)PF * GNA_THREADS) {
+    uint4 cur[PF];
 #pragma unroll
-      for (int j = 1; j < PF; ++j)
-        if (i == j) q = pre[j];
-    } else {
-      const __half* src = (c0 < p.C0) ? p.x0 + ((int64_t)b * p.HW + pix) * p.C0 + c0
-                                      : p.x1 + ((int64_t)b * p.HW + pix) * p.C1 + (c0 - p.C0);
-      q = __ldg(reinterpret_cast<const uint4*>(src));
-    }
-    const __half2* hp = reinterpret_cast<const __half2*>(&q);
-    const float4 a0 = *reinterpret_cast<const float4*>(sc + c0);
-    const float4 a1 = *reinterpret_cast<const float4*>(sc + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(sh + c0);
-    const float4 b1 = *reinterpret_cast<const float4*>(sh + c0 + 4);
-    float o[8];
-    float2 f = __half22float2(hp[0]);
-    o[0] = fmaf(f.x, a0.x, b0.x);
-    o[1] = fmaf(f.y, a0.y, b0.y);
-    f = __half22float2(hp[1]);
-    o[2] = fmaf(f.x, a0.z, b0.z);
-    o[3] = fmaf(f.y, a0.w, b0.w);
-    f = __half22float2(hp[2]);
-    o[4] = fmaf(f.x, a1.x, b1.x);
-    o[5] = fmaf(f.y, a1.y, b1.y);
-    f = __half22float2(hp[3]);
-    o[6] = fmaf(f.x, a1.z, b1.z);
-    o[7] = fmaf(f.y, a1.w, b1.w);
-    if (p.silu) {
+    for (int i = 0; i < PF; ++i) cur[i] = pre[i];
+    // next batch in flight while this one is normalised
+    if (base + (int64_t)PF * GNA_THREADS < v_end) load_batch(base + (int64_t)PF * GNA_THREADS);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = silu_fast(o[j]);
+    for (int i = 0; i < PF; ++i) {
+      const int64_t v = base + t + (int64_t)i * GNA_THREADS;
+      if (v >= v_end) continue;
+      const int pix = (int)(v / p.NV);
+      const int c0 = (int)(v - (int64_t)pix * p.NV) * 8;
+      const uint4 q = cur[i];
+      const __half2* hp = reinterpret_cast<const __half2*>(&q);
+      const float4 a0 = *reinterpret_cast<const float4*>(sc + c0);
+      const float4 a1 = *reinterpret_cast<const float4*>(sc + c0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sh + c0);
+      const float4 b1 = *reinterpret_cast<const float4*>(sh + c0 + 4);
+      float o[8];
+      float2 f = __half22float2(hp[0]);
+      o[0] = fmaf(f.x, a0.x, b0.x);
+      o[1] = fmaf(f.y, a0.y, b0.y);
+      f = __half22float2(hp[1]);
+      o[2] = fmaf(f.x, a0.z, b0.z);
+      o[3] = fmaf(f.y, a0.w, b0.w);
+      f = __half22float2(hp[2]);
+      o[4] = fmaf(f.x, a1.x, b1.x);
+      o[5] = fmaf(f.y, a1.y, b1.y);
+      f = __half22float2(hp[3]);
+      o[6] = fmaf(f.x, a1.z, b1.z);
+      o[7] = fmaf(f.y, a1.w, b1.w);
+      if (p.silu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = silu_fast(o[j]);
+      }
+      uint4 w;
+      w.x = pack_half2(o[0], o[1]);
+      w.y = pack_half2(o[2], o[3]);
+      w.z = pack_half2(o[4], o[5]);
+      w.w = pack_half2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(p.y + ((int64_t)b * p.HW + pix) * p.C + c0) = w;
     }
-    uint4 w;
-    w.x = pack_half2(o[0], o[1]);
-    w.y = pack_half2(o[2], o[3]);
-    w.z = pack_half2(o[4], o[5]);
-    w.w = pack_half2(o[6], o[7]);
-    *reinterpret_cast<uint4*>(p.y + ((int64_t)b * p.HW + pix) * p.C + c0) = w;
   }
 }
 
@@ -655,9 +659,9 @@ extern "C" int gn_group_norm_apply(gn_handle* h, const void* x0, int C0, const v
   p.beta = beta;
   p.silu = silu;
   p.y = static_cast<__half*>(y);
-  // ~8 sixteen-byte vectors per thread, at most 4 CTAs per SM in total
+  // one batch of 4 sixteen-byte vectors per thread on small tensors, at most 4 CTAs per SM in total
   const int64_t nvec = (int64_t)HW * p.NV;
-  int64_t ctas = (nvec + GNA_THREADS * 8 - 1) / (GNA_THREADS * 8);
+  int64_t ctas = (nvec + GNA_THREADS * 4 - 1) / (GNA_THREADS * 4);
   const int64_t cap = (int64_t)h->num_sms * 4 / B > 0 ? (int64_t)h->num_sms * 4 / B : 1;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
