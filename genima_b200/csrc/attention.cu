@@ -11,8 +11,9 @@
 //               rescaled only when the running maximum grew by more than 2^8 since the last rescale (the stale
 //               maximum is used consistently for P and the row sum, so the result is exact); exponentials are single
 //               ex2.approx instructions with the softmax scale folded into one FFMA; P goes to shared memory as fp16 in
-//               the SWIZZLE_128B K-major layout the MMA expects.
-// Shared memory 112 KiB + TMEM 512 columns: one CTA per SM.
+//               the SWIZZLE_128B K-major layout the MMA expects.  P is double-buffered as well, so the softmax of block i+1
+//               never waits for P V of block i (only a rescale of O does).
+// Shared memory 146 KiB + TMEM 512 columns: one CTA per SM.
 //
 // attn_small_kernel — SIMT attention for tiny problems (ACT transformer, CLIP text towers): one warp per query.
 #include "common.h"
@@ -29,8 +30,8 @@ constexpr int AT_STAGES = 2;
 constexpr int AT_SM_WARPS = 8;
 constexpr int AT_THREADS = 64 + 32 * AT_SM_WARPS;
 constexpr int AT_TMEM_COLS = 512;
-constexpr int AT_SMEM_BYTES =
-    AT_TILE_BYTES /*Q*/ + AT_P_BYTES + 2 * AT_STAGES * AT_TILE_BYTES /*K, V*/ + 4 * 128 * 4 /*row exchange*/ + 256 + 1024;
+constexpr int AT_SMEM_BYTES = AT_TILE_BYTES /*Q*/ + 2 * AT_P_BYTES /*P, double-buffered*/ +
+                             2 * AT_STAGES * AT_TILE_BYTES /*K, V*/ + 4 * 128 * 4 /*row exchange*/ + 256 + 1024;
 constexpr float AT_RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
@@ -40,6 +41,19 @@ struct AttnParams {
   int Tq, Tk;
   float scale_log2;  // softmax scale * log2(e)
 };
+
+// 2^x for x <= ~8 without the SFU: n = round(x) through the 1.5 * 2^23 magic constant (its low mantissa bits then hold n),
+// 2^(x - n) by a degree-4 polynomial on [-0.5, 0.5], n added to the exponent field with an integer shift / add.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float r = x + 12582912.0f;
+  const float f = x - (r - 12582912.0f);
+  float q = fmaf(f, 0.00961812910762848f, 0.0555041086648216f);
+  q = fmaf(q, f, 0.240226506959101f);
+  q = fmaf(q, f, 0.693147180559945f);
+  q = fmaf(q, f, 1.0f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
+}
 
 __device__ __forceinline__ void at_bar_sync_softmax() {
   asm volatile("bar.sync 2, %0;" ::"n"(32 * AT_SM_WARPS) : "memory");
@@ -51,7 +65,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sP = sQ + AT_TILE_BYTES;
-  uint8_t* sK = sP + AT_P_BYTES;
+  uint8_t* sK = sP + 2 * AT_P_BYTES;
   uint8_t* sV = sK + AT_STAGES * AT_TILE_BYTES;
   float* s_xchg = reinterpret_cast<float*>(sV + AT_STAGES * AT_TILE_BYTES);  // [2 parities][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_xchg + 4 * 128);
@@ -62,9 +76,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
   uint64_t* v_empty = bars + 7;   // [2]
   uint64_t* s_full = bars + 9;    // [2]
   uint64_t* s_free = bars + 11;   // [2]
-  uint64_t* p_full = bars + 13;
-  uint64_t* pv_done = bars + 14;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_full = bars + 13;   // [2]
+  uint64_t* pv_done = bars + 15;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,9 +99,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&s_free[s], 32 * AT_SM_WARPS);
+      mbar_init(&p_full[s], 32 * AT_SM_WARPS);
+      mbar_init(&pv_done[s], 1);
     }
-    mbar_init(p_full, 32 * AT_SM_WARPS);
-    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, AT_TMEM_COLS);
@@ -138,18 +152,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
       for (int i = 0; i < nblk; ++i) {
         if (i + 1 < nblk) issue_qk(i + 1);  // next scores while the softmax warps work on block i
         const int st = i & 1;
-        mbar_wait(p_full, i & 1);
+        mbar_wait(&p_full[st], (i >> 1) & 1);
         mbar_wait(&v_full[st], (i >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < AT_BKV / 16; ++j) {
-          // A: P[128 rows][16 k] slice j: 64-column sub-tile j/4, 32-byte step j%4 inside the swizzle row
-          const uint64_t a_desc = umma_desc_sw128(smem_u32(sP + (j >> 2) * AT_TILE_BYTES), 1024, 0) + 2 * (j & 3);
+          // A: P buffer i & 1, [128 rows][16 k] slice j: 64-column sub-tile j/4, 32-byte step j%4 inside the swizzle row
+          const uint64_t a_desc =
+              umma_desc_sw128(smem_u32(sP + st * AT_P_BYTES + (j >> 2) * AT_TILE_BYTES), 1024, 0) + 2 * (j & 3);
           // B: V rows [16 j, 16 j + 16) x 64 dims, MN-major: two 8-row swizzle atoms 1024 B apart
           const uint64_t b_desc = umma_desc_sw128(smem_u32(sV + st * AT_TILE_BYTES + j * 2048), 1024, 1024);
           umma_f16_ss(tmem_o, a_desc, b_desc, idesc_pv, (i > 0 || j > 0) ? 1u : 0u);
         }
-        umma_commit(pv_done);
+        umma_commit(&pv_done[st]);
         umma_commit(&v_empty[st]);
       }
     }
@@ -161,7 +176,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
     const uint32_t lane_sel = static_cast<uint32_t>(qd * 32) << 16;
     float m_used = -INFINITY;  // maximum the stored P / l / O are currently scaled with (raw score units)
     float l_run = 0.f;         // this half's share of the row sum
-    const uint32_t p_row = smem_u32(sP) + half * AT_TILE_BYTES + row * 128;
+    const uint32_t p_row0 = smem_u32(sP) + half * AT_TILE_BYTES + row * 128;
     const uint32_t swz = static_cast<uint32_t>(row & 7);
     const float c = p.scale_log2;
 
@@ -186,22 +201,31 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
       mbar_arrive(&s_free[st]);  // the scores are in registers: QK^T of block i+2 may overwrite this buffer
       const int nvalid = p.Tk - i * AT_BKV - half * 64;  // valid columns of this half (may be <= 0)
       float mx = -INFINITY;
+      if (nvalid >= 64) {  // (warp-uniform) every column is a real key: no masking
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const float sv = (j < nvalid) ? __uint_as_float(r[j]) : -INFINITY;
-        r[j] = __float_as_uint(sv);
-        mx = fmaxf(mx, sv);
+        for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const float sv = (j < nvalid) ? __uint_as_float(r[j]) : -INFINITY;
+          r[j] = __float_as_uint(sv);
+          mx = fmaxf(mx, sv);
+        }
       }
       float* xc = s_xchg + (i & 1) * 256;  // double-buffered: the barrier of block i+1 separates reuse from this read
       xc[half * 128 + row] = mx;
       at_bar_sync_softmax();
       const float m_blk = fmaxf(mx, xc[(half ^ 1) * 128 + row]);
       const float m_new = fmaxf(m_used, m_blk);
-      if (i > 0) mbar_wait(pv_done, (i - 1) & 1);  // P V of block i-1 finished: P may be rewritten, O may be rescaled
+      // P is double-buffered: this block's probabilities go to buffer i & 1, which P V of block i-2 has finished reading
+      // (the tensor core may still be working on P V of block i-1 out of the other buffer)
+      if (i >= 2) mbar_wait(&pv_done[st], ((i >> 1) - 1) & 1);
+      const uint32_t p_row = p_row0 + st * AT_P_BYTES;
       // lazy rescale, warp-uniform (tcgen05.ld/st are warp-collective); both halves of a row see the same values
       if (__any_sync(0xffffffffu, (m_new - m_used) * c > AT_RESCALE_LOG2)) {
         const float alpha = ex2_approx((m_used - m_new) * c);  // m_used = -inf -> 0
         if (i > 0) {
+          mbar_wait(&pv_done[(i - 1) & 1], ((i - 1) >> 1) & 1);  // O is stable only once P V of block i-1 is complete
           tc_fence_after();
           uint32_t o[32];
           tmem_ld_x32(tmem_o + lane_sel + half * 32, o);
@@ -222,8 +246,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
         uint32_t pk[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(r[8 * t + 2 * u]), c, -moff));      // -inf -> 0
-          const float p1 = ex2_approx(fmaf(__uint_as_float(r[8 * t + 2 * u + 1]), c, -moff));
+          // The SFU of B200 delivers ~8 ex2 per clock per SM: with 16K exponentials per 128 x 128 score block it, not
+          // the tensor core, bounds the kernel.  Every fourth exponential is therefore computed on the FMA pipes
+          // (Cody-Waite range reduction + degree-4 polynomial, relative error 4e-5, far below the fp16 rounding of P).
+          const float p0 = ex2_approx(fmaf(__uint_as_float(r[8 * t + 2 * u]), c, -moff));     // -inf -> 0
+          const float x1 = fmaf(__uint_as_float(r[8 * t + 2 * u + 1]), c, -moff);
+          const float p1 = (u & 1) ? ex2_poly(x1) : ex2_approx(x1);  // -inf -> 2^-126 / 0
           lsum += p0 + p1;
           pk[u] = pack_half2(p0, p1);
         }
@@ -234,14 +262,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
       }
       l_run += lsum;
       fence_proxy_async_smem();  // P (generic-proxy writes) must be visible to the tensor core (async proxy)
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[st]);
     }
     // ---- output: O / l
     float* xl = s_xchg + (nblk & 1) * 256;
     xl[half * 128 + row] = l_run;
     at_bar_sync_softmax();
     const float l_tot = l_run + xl[(half ^ 1) * 128 + row];
-    mbar_wait(pv_done, (nblk - 1) & 1);
+    mbar_wait(&pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
     tc_fence_after();
     uint32_t o[32];
     tmem_ld_x32(tmem_o + lane_sel + half * 32, o);
