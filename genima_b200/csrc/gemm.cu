@@ -526,10 +526,19 @@ __device__ __forceinline__ void fast_epilogue_rows(const GemmParams& p, uint32_t
         tmem_ld_x16(taddr + c + 64, g);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = fmaf(__uint_as_float(r[j]), ln_rstd, fmaf(ln_nmr, s_cs[c + j], s_bias[c + j]));
-          const float gt = fmaf(__uint_as_float(g[j]), ln_rstd, fmaf(ln_nmr, s_cs[c + 64 + j], s_bias[c + 64 + j]));
-          v[j] = a * gelu_erf_f(gt);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 ca = *reinterpret_cast<const float4*>(s_cs + c + j);
+          const float4 ba = *reinterpret_cast<const float4*>(s_bias + c + j);
+          const float4 cg4 = *reinterpret_cast<const float4*>(s_cs + c + 64 + j);
+          const float4 bg4 = *reinterpret_cast<const float4*>(s_bias + c + 64 + j);
+          const float csa[4] = {ca.x, ca.y, ca.z, ca.w}, bia[4] = {ba.x, ba.y, ba.z, ba.w};
+          const float csg[4] = {cg4.x, cg4.y, cg4.z, cg4.w}, big[4] = {bg4.x, bg4.y, bg4.z, bg4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float a = fmaf(__uint_as_float(r[j + u]), ln_rstd, fmaf(ln_nmr, csa[u], bia[u]));
+            const float gt = fmaf(__uint_as_float(g[j + u]), ln_rstd, fmaf(ln_nmr, csg[u], big[u]));
+            v[j + u] = a * gelu_erf_f(gt);
+          }
         }
       } else {
         tmem_ld_wait();
