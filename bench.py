@@ -273,6 +273,32 @@ def run_ours(args):
     torch.cuda.synchronize()
     unet_ms = u0.elapsed_time(u1) / nrep / args.denoise_steps
 
+    # ---- throughput variant: B independent episodes batched into one denoise call.
+    # Informational only: `value` above is the batch-1 step.  Results are bit-identical across the batch entries.
+    batched = None
+    if rank == 0 and not args.no_batched:
+        batched = []
+        for Bt in (2, 4):
+            bv = d_views.repeat(Bt, 1, 1, 1, 1)
+            bargs = (bv, d_lat.repeat(Bt, 1, 1, 1), d_qpos.repeat(Bt, 1), d_task.repeat(Bt, 1))
+            bctx = d_ctx.repeat(Bt, 1, 1)
+            for _ in range(3):
+                bout = step(*bargs, prompt_embeds=bctx)
+            torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nb = max(5, min(args.steps, 10))
+            b0.record()
+            for _ in range(nb):
+                bout = step(*bargs, prompt_embeds=bctx)
+            b1.record()
+            torch.cuda.synchronize()
+            bms = b0.elapsed_time(b1) / nb
+            ba = bout["a_hat"].float()
+            batched.append({"tile_batch": Bt, "ms_per_call": bms, "value": Bt * 1e3 / bms, "unit": UNIT,
+                            "max_abs_diff_between_batch_entries": float((ba - ba[0:1]).abs().max()),
+                            "max_abs_diff_vs_batch_1": float((ba[0].cpu() - a_hat[0]).abs().max())})
+        out = step(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx)   # back to the batch-1 graph / buffers
+
     # ---- e2e through the reference-facing API with host buffers
     from PIL import Image
 
@@ -373,7 +399,7 @@ def run_ours(args):
                     "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
                     "api": "B200ControlNetAgent.infer + untile_images + B200GenimaACT.act (PIL / numpy host buffers)"},
             "gpu_launches": int(launches), "launches_per_step": int(step.launches_per_step),
-            "roofline": roofline, "kernel_classes": classes, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "kernel_classes": classes, "cpu_baseline": cpu_baseline, "batched": batched,
             "weights_broadcast_s": weight_s, "weights_gb": arena.numel() * 2 / 1e9,
             "agent_step_tflop": (args.denoise_steps * FLOPS_DENOISE_ITER + FLOPS_VAE + FLOPS_ACT) / 1e12
             if args.preset != "tiny" else None,
@@ -423,6 +449,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the tile_batch 2 / 4 throughput variant")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

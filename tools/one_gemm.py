@@ -1,6 +1,7 @@
 """Runs one op a few times; the LAST call sits between cudaProfilerStart/Stop so that
 `ncu --profile-from-start off --set full ...` captures the tuned configuration, not an autotuning candidate.
-Usage: python tools/one_gemm.py linear M N K [geglu|fp32out|bias_res|plain]   |   conv B H Cin Cout [stride]"""
+Usage: python tools/one_gemm.py linear M N K [geglu|fp32out|bias_res|plain]   |   conv B H Cin Cout [stride]
+       |   attn Tq Tk heads   |   gnapply hw C bucket   |   gn hw C"""
 import os
 import sys
 
@@ -34,6 +35,16 @@ elif kind == "attn":
     k = torch.randn(tk, c, device="cuda").half()
     v = torch.randn(tk, c, device="cuda").half()
     fn = lambda: ops.attention(q, k, v, 1, heads, tq, tk, 0.125)
+elif kind == "gnapply":
+    # GroupNorm from statistics accumulated by the producing GEMM epilogue: `gnapply hw C bucket`
+    hw, c, bucket = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    a = torch.randn(hw * hw, 64, device="cuda").half()
+    w = torch.randn(c, 64, device="cuda").half() * 0.125
+    ops.gn_stats_reset()
+    y = ops.linear(a, w, gn_stats=bucket)
+    x = ops.carry_stats(y.reshape(1, hw, hw, c), y)
+    g, b = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    fn = lambda: ops.group_norm(x, g, b, 32, 1e-5, silu=True)
 elif kind == "gn":
     hw, c = int(sys.argv[2]), int(sys.argv[3])
     x = torch.randn(1, hw, hw, c, device="cuda").half()
