@@ -21,6 +21,7 @@ The whole post-upload chain can be captured once into a CUDA graph (`use_cuda_gr
 from __future__ import annotations
 
 import hashlib
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Union
 
 import numpy as np
@@ -83,7 +84,13 @@ class B200ControlNetPipeline:
         # gn_handle so that the per-handle GroupNorm scratch / grid-barrier words are never shared between streams.
         self.concurrent_controlnet = bool(concurrent_controlnet)
         self.ops_side = Ops(ops.device.index) if self.concurrent_controlnet else ops
-        self.side_stream = torch.cuda.Stream(device=ops.device) if self.concurrent_controlnet else None
+        # third handle / stream: the 13 zero-convs start as soon as both encoders have produced their skip tensor,
+        # instead of running one after the other once the two encoders have joined
+        self.ops_zero = Ops(ops.device.index) if self.concurrent_controlnet else ops
+        self.zero_stream = torch.cuda.Stream(device=ops.device) if self.concurrent_controlnet else None
+        self.overlap_zero_convs = os.environ.get("GENIMA_B200_ZERO_OVERLAP", "1") != "0"
+        self.side_stream = (torch.cuda.Stream(device=ops.device, priority=int(os.environ.get("GENIMA_B200_SIDE_PRIO", "0")))
+                            if self.concurrent_controlnet else None)
         self.unet_impl = DeviceUNet(ops, unet_sd, unet_cfg)
         self.controlnet_impl = DeviceControlNet(self.ops_side, controlnet_sd, unet_cfg)
         self.vae_impl = DeviceVAEDecoder(ops, vae_sd, vae_cfg)
@@ -108,13 +115,10 @@ class B200ControlNetPipeline:
 
     def launch_count(self) -> int:
         """Kernels launched through this pipeline's handle(s) since creation."""
-        n = self.ops.launch_count()
-        if self.ops_side is not self.ops:
-            n += self.ops_side.launch_count()
-        return n
+        return sum(o.launch_count() for o in self.all_ops())
 
     def all_ops(self):
-        return [self.ops] if self.ops_side is self.ops else [self.ops, self.ops_side]
+        return [self.ops] if self.ops_side is self.ops else [self.ops, self.ops_side, self.ops_zero]
 
     # ------------------------------------------------------------------ diffusers API surface used by the reference
     def to(self, *args, **kwargs):
@@ -280,6 +284,34 @@ class B200ControlNetPipeline:
             o.set_gn_max_ctas(half_sms)
         for i in range(n_steps):
             tu, tc = temb[i]
+            if concurrent and self.overlap_zero_convs:
+                main = torch.cuda.current_stream()
+                n_ev = len(self.controlnet_impl.zero_w) + 1
+                ev_u = [torch.cuda.Event() for _ in range(n_ev)]
+                ev_c = [torch.cuda.Event() for _ in range(n_ev)]
+                self.side_stream.wait_stream(main)
+                self.zero_stream.wait_stream(main)
+                with torch.cuda.stream(self.side_stream):
+                    cn_mid, cn_skips = self.controlnet_impl.encode(
+                        xs, cond_emb, tc, kv_c, tk, on_skip=lambda j: ev_c[j].record(self.side_stream))
+                mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk, on_skip=lambda j: ev_u[j].record(main))
+                with torch.cuda.stream(self.zero_stream):
+                    outs = []
+                    for j in range(n_ev):
+                        self.zero_stream.wait_event(ev_u[j])
+                        self.zero_stream.wait_event(ev_c[j])
+                        src_c, src_u = (cn_skips[j], skips[j]) if j < n_ev - 1 else (cn_mid, mid)
+                        outs.append(self.controlnet_impl.zero_conv(j, src_c, src_u, cond_scale, ops=self.ops_zero))
+                main.wait_stream(self.side_stream)
+                main.wait_stream(self.zero_stream)
+                skips, mid = outs[:-1], outs[-1]
+                del cn_mid, cn_skips, outs
+                self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps)
+                x_next = torch.empty_like(x)
+                xs_next = torch.empty_like(x)
+                ops.euler_step(x, eps, float(sig[i]), float(sig[i + 1]), x_next=x_next, x_scaled=xs_next)
+                x, xs = x_next, xs_next
+                continue
             if concurrent:
                 main = torch.cuda.current_stream()
                 self.side_stream.wait_stream(main)
@@ -290,7 +322,9 @@ class B200ControlNetPipeline:
             else:
                 mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk)
                 cn_mid, cn_skips = self.controlnet_impl.encode(xs, cond_emb, tc, kv_c, tk)
-            skips, mid = self.controlnet_impl.zero_convs(cn_mid, cn_skips, skips, mid, cond_scale)
+            # (same handle as the overlapped path, so that its tile configurations are the ones measured here)
+            skips, mid = self.controlnet_impl.zero_convs(cn_mid, cn_skips, skips, mid, cond_scale,
+                                                         ops=self.ops_zero if self.overlap_zero_convs else None)
             del cn_mid, cn_skips
             self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps)
             x_next = torch.empty_like(x)

@@ -242,22 +242,29 @@ class _Encoder:
                 rows[rb.prefix] = r.expand(batch, -1).contiguous()
         return rows
 
-    def run(self, h: torch.Tensor, temb: Dict[str, torch.Tensor], kv: Dict[str, torch.Tensor], tk: int):
-        """h: conv_in output [B, H, W, C0] -> (mid output, [S0..S11])."""
+    def run(self, h: torch.Tensor, temb: Dict[str, torch.Tensor], kv: Dict[str, torch.Tensor], tk: int, on_skip=None):
+        """h: conv_in output [B, H, W, C0] -> (mid output, [S0..S11]).  on_skip(i) is called right after skip i (and
+        finally i = len(skips) for the mid-block output) has been enqueued, so that a caller can record a stream event
+        per tensor and start consuming them while the rest of the encoder is still running."""
         ops = self.ops
         skips = [h]
+        note = on_skip if on_skip is not None else (lambda i: None)
+        note(0)
         for res, att, ds in self.down:
             for rb, tr in zip(res, att):
                 h = rb(ops, h, None, temb[rb.prefix])
                 if tr is not None:
                     h = tr(ops, h, kv[tr.prefix], tk)
                 skips.append(h)
+                note(len(skips) - 1)
             if ds is not None:
                 h = ds(ops, h)
                 skips.append(h)
+                note(len(skips) - 1)
         h = self.mid_res0(ops, h, None, temb[self.mid_res0.prefix])
         h = self.mid_attn(ops, h, kv[self.mid_attn.prefix], tk)
         h = self.mid_res1(ops, h, None, temb[self.mid_res1.prefix])
+        note(len(skips))
         return h, skips
 
 
@@ -297,9 +304,9 @@ class DeviceUNet(_Encoder):
             out += [a for a in att if a is not None]
         return out
 
-    def encode(self, x: torch.Tensor, temb, kv, tk):
+    def encode(self, x: torch.Tensor, temb, kv, tk, on_skip=None):
         h = self.conv_in(self.ops, x)
-        return self.run(h, temb, kv, tk)
+        return self.run(h, temb, kv, tk, on_skip)
 
     def decode(self, h: torch.Tensor, skips: List[torch.Tensor], temb, kv, tk, eps_out: torch.Tensor) -> torch.Tensor:
         """`skips` / `h` already include the ControlNet residuals.  Writes eps into eps_out [B, H, W, 8] (4 valid)."""
@@ -343,28 +350,28 @@ class DeviceControlNet(_Encoder):
             e = conv(ops, e, act_pre="silu")
         return self.ce_out(ops, e)
 
-    def encode(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk):
+    def encode(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk, on_skip=None):
         """conv_in(x) + cond_emb -> encoder copy -> (mid, [S0..S11]) BEFORE the zero-convs.  Independent of the U-Net's own
         encoder, so the pipeline runs it on a second stream concurrently with DeviceUNet.encode."""
         h = self.conv_in(self.ops, x, residual=cond_emb)
-        return self.run(h, temb, kv, tk)
+        return self.run(h, temb, kv, tk, on_skip)
+
+    def zero_conv(self, i: int, s: torch.Tensor, us: torch.Tensor, conditioning_scale: float = 1.0,
+                  ops: Optional[Ops] = None) -> torch.Tensor:
+        """Zero-conv of ControlNet skip i (i == len(zero_w): the mid-block one) added to the U-Net tensor `us`."""
+        ops = ops or self.ops
+        w, b = (self.zero_w[i], self.zero_b[i]) if i < len(self.zero_w) else (self.mid_w, self.mid_b)
+        B, H, W, C = s.shape
+        o = ops.linear(s.reshape(B * H * W, C), w, bias=b, residual=us.reshape(B * H * W, C), alpha=conditioning_scale,
+                       rows_per_batch=H * W, gn_stats=self.P.gn_bucket)
+        return ops.carry_stats(o.reshape(B, H, W, C), o)
 
     def zero_convs(self, mid: torch.Tensor, skips: List[torch.Tensor], unet_skips: List[torch.Tensor],
-                   unet_mid: torch.Tensor, conditioning_scale: float = 1.0):
+                   unet_mid: torch.Tensor, conditioning_scale: float = 1.0, ops: Optional[Ops] = None):
         """Returns (U-Net skips + down residuals, U-Net mid + mid residual): the zero-conv epilogues add the U-Net tensors,
         so the `sample + residual` adds of UNet2DConditionModel.forward cost no extra pass."""
-        ops = self.ops
-        out = []
-        for s, w, b, us in zip(skips, self.zero_w, self.zero_b, unet_skips):
-            B, H, W, C = s.shape
-            o = ops.linear(s.reshape(B * H * W, C), w, bias=b, residual=us.reshape(B * H * W, C),
-                           alpha=conditioning_scale, rows_per_batch=H * W, gn_stats=self.P.gn_bucket)
-            out.append(ops.carry_stats(o.reshape(B, H, W, C), o))
-        B, H, W, C = mid.shape
-        m = ops.linear(mid.reshape(B * H * W, C), self.mid_w, bias=self.mid_b,
-                       residual=unet_mid.reshape(B * H * W, C), alpha=conditioning_scale, rows_per_batch=H * W,
-                       gn_stats=self.P.gn_bucket)
-        return out, ops.carry_stats(m.reshape(B, H, W, C), m)
+        out = [self.zero_conv(i, s, us, conditioning_scale, ops) for i, (s, us) in enumerate(zip(skips, unet_skips))]
+        return out, self.zero_conv(len(self.zero_w), mid, unet_mid, conditioning_scale, ops)
 
     def residuals(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk, unet_skips: List[torch.Tensor],
                   unet_mid: torch.Tensor, conditioning_scale: float = 1.0):
