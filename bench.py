@@ -46,15 +46,20 @@ FLOPS_VAE = 2.515e12
 FLOPS_ACT = 0.0228e12
 
 
-def presets(name: str):
+def presets(name: str, autoencoder: str = ""):
+    """autoencoder containing 'taesd' selects AutoencoderTiny, like eval_cfg.autoencoder in the reference
+    (controller/agent/sd_controlnet_agent.py:45-49); the default ('') is the KL-VAE of BASELINE configs[2]."""
+    from genima_b200.configs import TAESDConfig
+
+    taesd = "taesd" in (autoencoder or "")
     if name == "tiny":
-        return UNetConfig.tiny(), VAEConfig.tiny(), ACTConfig.tiny()
-    return UNetConfig(), VAEConfig(), ACTConfig()
+        return UNetConfig.tiny(), (TAESDConfig.tiny() if taesd else VAEConfig.tiny()), ACTConfig.tiny()
+    return UNetConfig(), (TAESDConfig() if taesd else VAEConfig()), ACTConfig()
 
 
 def model_shapes(ucfg, vcfg, acfg):
-    return OrderedDict(unet=W.unet_shapes(ucfg), controlnet=W.controlnet_shapes(ucfg),
-                       vae=W.vae_decoder_shapes(vcfg), act=W.act_shapes(acfg))
+    vae = W.taesd_decoder_shapes(vcfg) if hasattr(vcfg, "num_blocks") else W.vae_decoder_shapes(vcfg)
+    return OrderedDict(unet=W.unet_shapes(ucfg), controlnet=W.controlnet_shapes(ucfg), vae=vae, act=W.act_shapes(acfg))
 
 
 def synth_all(shapes):
@@ -140,7 +145,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ucfg, vcfg, acfg = presets(args.preset)
+    ucfg, vcfg, acfg = presets(args.preset, args.autoencoder)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sds = synth_all(model_shapes(ucfg, vcfg, acfg))
@@ -181,6 +186,7 @@ def workload_config(args, ucfg):
                         f"ControlNet+SD-Turbo U-Net x{args.denoise_steps} Euler-trailing steps -> KL-VAE decode -> "
                         "untile -> ACT (ResNet18-FiLM x4 + 4enc/6dec transformer) -> a_hat[1,20,8]",
             "preset": args.preset, "denoise_steps": args.denoise_steps, "tile_batch": 1, "guidance_scale": 0.0,
+            "autoencoder": ("taesd (AutoencoderTiny)" if "taesd" in (args.autoencoder or "") else "AutoencoderKL"),
             "weights": "synthetic seeded (real SD-2.1/SD-Turbo + ACT topologies)", "parallelism": f"episode-dp{args.gpus}",
             "l2": "inputs larger than L2: ~2.7 GB of fp16 weights streamed per step vs 126 MB L2"}
 
@@ -211,7 +217,7 @@ def run_ours(args):
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
 
-    ucfg, vcfg, acfg = presets(args.preset)
+    ucfg, vcfg, acfg = presets(args.preset, args.autoencoder)
     shapes = model_shapes(ucfg, vcfg, acfg)
     # ---- weights: rank 0 synthesises, ONE broadcast of the packed arena, every rank binds views into its copy
     t_w = time.perf_counter()
@@ -401,7 +407,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "launches_per_step": int(step.launches_per_step),
             "roofline": roofline, "kernel_classes": classes, "cpu_baseline": cpu_baseline, "batched": batched,
             "weights_broadcast_s": weight_s, "weights_gb": arena.numel() * 2 / 1e9,
-            "agent_step_tflop": (args.denoise_steps * FLOPS_DENOISE_ITER + FLOPS_VAE + FLOPS_ACT) / 1e12
+            "agent_step_tflop": (args.denoise_steps * FLOPS_DENOISE_ITER
+                                 + (0.14e12 if "taesd" in (args.autoencoder or "") else FLOPS_VAE) + FLOPS_ACT) / 1e12
             if args.preset != "tiny" else None,
         }
         print(json.dumps(line), flush=True)
@@ -454,6 +461,8 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the tile_batch 2 / 4 throughput variant")
+    ap.add_argument("--autoencoder", default="", help="'taesd': decode with AutoencoderTiny (reference option "
+                                                      "eval_cfg.autoencoder); default: the KL-VAE of the headline config")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

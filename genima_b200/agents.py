@@ -23,7 +23,7 @@ import torch
 from . import checkpoint as ckpt
 from . import weights as W
 from .act_policy import DeviceACT
-from .configs import ACTConfig, CLIPTextConfig, SchedulerConfig, UNetConfig, VAEConfig
+from .configs import ACTConfig, CLIPTextConfig, SchedulerConfig, TAESDConfig, UNetConfig, VAEConfig
 from .ops import Ops
 from .pipeline import B200ControlNetPipeline
 from .text_encoder import DeviceCLIPText
@@ -99,21 +99,25 @@ class B200ControlNetAgent:
         cfg = self.eval_cfg
         ops = self._ops or get_ops(_cfg_get(cfg, "device", "cuda"))
         autoenc = _cfg_get(cfg, "autoencoder", "") or ""
-        if "taesd" in autoenc:
-            raise NotImplementedError("autoencoder='taesd' (AutoencoderTiny) is not implemented; use the KL-VAE")
+        taesd = "taesd" in autoenc          # same test as the reference (sd_controlnet_agent.py:45): AutoencoderTiny
         synth = _cfg_get(cfg, "synthetic_weights", None)
         tok = _cfg_get(cfg, "tokenizer", None)
         graph = bool(_cfg_get(cfg, "use_cuda_graph", True))
         if synth:
             ucfg, vcfg, tcfg, _ = _preset(synth)
             with_text = bool(_cfg_get(cfg, "synthetic_text_encoder", True))
+            if taesd:
+                vcfg = TAESDConfig.tiny() if synth == "tiny" else TAESDConfig()
+            vae_sd = W.synth_state_dict(W.taesd_decoder_shapes(vcfg) if taesd else W.vae_decoder_shapes(vcfg), salt=2)
             self.pipe = B200ControlNetPipeline(
                 ops, W.synth_state_dict(W.unet_shapes(ucfg)), W.synth_state_dict(W.controlnet_shapes(ucfg), salt=1),
-                W.synth_state_dict(W.vae_decoder_shapes(vcfg), salt=2),
+                vae_sd,
                 W.synth_state_dict(W.clip_text_shapes(tcfg)) if with_text else None,
                 ucfg, vcfg, tcfg, SchedulerConfig(), tokenizer=tok, use_cuda_graph=graph)
             return
         loaded = ckpt.load_sd_turbo(_cfg_get(cfg, "sd_ckpt"), _cfg_get(cfg, "diffusion_ckpt"))
+        if taesd:
+            loaded["vae"], loaded["vae_cfg"] = ckpt.load_taesd(autoenc)
         self.pipe = B200ControlNetPipeline(ops, loaded["unet"], loaded["controlnet"], loaded["vae"], loaded["text"],
                                            loaded["unet_cfg"], loaded["vae_cfg"], loaded["text_cfg"],
                                            loaded["scheduler_cfg"], tokenizer=tok, use_cuda_graph=graph)

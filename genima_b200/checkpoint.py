@@ -20,7 +20,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 from . import weights as W
-from .configs import ACTConfig, CLIPTextConfig, SchedulerConfig, UNetConfig, VAEConfig
+from .configs import ACTConfig, CLIPTextConfig, SchedulerConfig, TAESDConfig, UNetConfig, VAEConfig
 
 
 def _natural_key(s: str):
@@ -131,6 +131,23 @@ def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: str):
     check_schema(out["vae"], W.vae_decoder_shapes(vcfg), "VAE decoder")
     check_schema(out["text"], W.clip_text_shapes(tcfg), "text encoder")
     return out
+
+
+def load_taesd(path: str):
+    """Local snapshot of an AutoencoderTiny checkpoint (madebyollin/taesd: config.json + diffusion_pytorch_model.safetensors)
+    -> (decoder state dict, TAESDConfig).  The reference passes a hub id (sd_controlnet_agent.py:45-49); offline it must be
+    a directory."""
+    if not os.path.isdir(path):
+        raise FileNotFoundError(f"autoencoder {path!r} is not a local directory; hub ids cannot be resolved offline — "
+                                "point it at a local snapshot of madebyollin/taesd")
+    j = _read_json(os.path.join(path, "config.json"))
+    chans = j.get("decoder_block_out_channels", (64, 64, 64, 64))
+    cfg = TAESDConfig(latent_channels=j.get("latent_channels", 4), out_channels=j.get("out_channels", 3),
+                      channels=int(chans[0]), num_blocks=tuple(j.get("num_decoder_blocks", (3, 3, 3, 1))),
+                      latent_magnitude=float(j.get("latent_magnitude", 3)), scaling_factor=float(j.get("scaling_factor", 1.0)))
+    sd = {k: v for k, v in load_safetensors_dir(path).items() if k.startswith("decoder.")}
+    check_schema(sd, W.taesd_decoder_shapes(cfg), "TAESD decoder")
+    return sd, cfg
 
 
 def load_controller_snapshot(path: str, cfg: ACTConfig = ACTConfig(), prefix: str = "actor.") -> Dict[str, torch.Tensor]:

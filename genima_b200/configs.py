@@ -56,6 +56,26 @@ class VAEConfig:
 
 
 @dataclass(frozen=True)
+class TAESDConfig:
+    """diffusers AutoencoderTiny (madebyollin/taesd) decoder, selected by `autoencoder: <...taesd...>` in the reference's
+    eval config (controller/agent/sd_controlnet_agent.py:45-49): conv / ReLU only, 1.22 M parameters."""
+    latent_channels: int = 4
+    out_channels: int = 3
+    channels: int = 64
+    num_blocks: Tuple[int, ...] = (3, 3, 3, 1)   # decoder_block_out_channels = (64, 64, 64, 64)
+    latent_magnitude: float = 3.0                # DecoderTiny.forward: tanh(x / 3) * 3
+    scaling_factor: float = 1.0
+
+    @staticmethod
+    def tiny() -> "TAESDConfig":
+        return TAESDConfig(num_blocks=(1, 1, 1, 1))
+
+    @property
+    def block_out_channels(self) -> Tuple[int, ...]:   # one entry per resolution level (pipeline's vae_scale_factor)
+        return (self.channels,) * len(self.num_blocks)
+
+
+@dataclass(frozen=True)
 class CLIPTextConfig:
     vocab_size: int = 49408
     hidden_size: int = 1024

@@ -311,6 +311,21 @@ extern "C" int gn_scale(gn_handle* h, const void* x, float s, void* y, int64_t n
   return GN_OK;
 }
 
+__global__ void tanh_clamp_kernel(const __half* __restrict__ x, float mag, __half* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2half_rn(tanhf(__half2float(x[i]) / mag) * mag);
+}
+
+extern "C" int gn_tanh_clamp(gn_handle* h, const void* x, float mag, void* y, int64_t n, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
+  GN_CHECK_ARG(h, x && y && n > 0 && mag > 0.f, "gn_tanh_clamp: bad arguments");
+  tanh_clamp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), mag, static_cast<__half*>(y), n);
+  GN_CHECK_LAUNCH(h);
+  return GN_OK;
+}
+
 extern "C" int gn_timestep_embedding(gn_handle* h, float t, int dim, void* out, void* stream) {
   if (!h) return GN_ERR_INVALID;
   ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);

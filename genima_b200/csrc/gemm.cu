@@ -589,6 +589,10 @@ __device__ __forceinline__ void fast_epilogue_rows(const GemmParams& p, uint32_t
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] *= e.alpha;
     }
+    if (e.act_post == GN_ACT_RELU) {  // ReLU after the residual add (torchvision BasicBlock, AutoencoderTinyBlock.fuse)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
     const int nout = n0_out + ct;
     if (!valid || nout + 16 > n_out_total) {  // zeros outside the tensor (TMA clips them; the GroupNorm pass sums them)
 #pragma unroll
@@ -1670,7 +1674,8 @@ static int fill_out_geom(gn_handle* h, GemmParams& p, OutGeom& og, const gn_epil
   og.split_fast = h->fast_epilogue && h->workspace && h->workspace_bytes >= (64 << 20) && og.stage_ok && (!e.residual || og.res_ok) && e.act_post == GN_ACT_NONE && !e.geglu &&
                   (e.act_pre == GN_ACT_NONE || e.act_pre == GN_ACT_SILU || e.act_pre == GN_ACT_RELU) &&
                   (!e.rowvec || ((e.N % 4) == 0 && (reinterpret_cast<uintptr_t>(e.rowvec) & 15) == 0));
-  og.mcast_ok = h->fast_epilogue && og.stage_ok && (!e.residual || og.res_ok) && e.act_post == GN_ACT_NONE &&
+  og.mcast_ok = h->fast_epilogue && og.stage_ok && (!e.residual || og.res_ok) &&
+                (e.act_post == GN_ACT_NONE || (e.act_post == GN_ACT_RELU && !e.geglu)) &&
                 (!e.rowvec || ((e.N % 4) == 0 && (reinterpret_cast<uintptr_t>(e.rowvec) & 15) == 0)) &&
                 e.act_pre >= GN_ACT_NONE && e.act_pre <= GN_ACT_QUICKGELU && !(e.geglu && e.act_pre != GN_ACT_NONE);
   og.gn = false;
@@ -1784,7 +1789,8 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
   // compact flavour when the whole epilogue can run from shared memory (see fast_epilogue_rows)
   const EpiParams& e = p.epi;
   const bool rowvec_ok = !e.rowvec || ((N % 4) == 0 && (reinterpret_cast<uintptr_t>(e.rowvec) & 15) == 0);
-  const bool fast = h->fast_epilogue && L.staged && (!e.residual || L.res_tma) && e.act_post == GN_ACT_NONE && rowvec_ok &&
+  const bool fast = h->fast_epilogue && L.staged && (!e.residual || L.res_tma) &&
+                    (e.act_post == GN_ACT_NONE || (e.act_post == GN_ACT_RELU && !e.geglu)) && rowvec_ok &&
                     e.act_pre >= GN_ACT_NONE && e.act_pre <= GN_ACT_QUICKGELU && !(e.geglu && e.act_pre != GN_ACT_NONE);
   const int kind = split_fast ? K_SPLIT : (!fast || tc.splits > 1) ? K_GENERIC : (e.geglu ? K_GEGLU : e.act_pre);
   dim3 grid(gn::ceil_div(N, tc.block_n), tiles_m, tc.splits);

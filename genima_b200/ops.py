@@ -464,6 +464,15 @@ class Ops:
                                             self._stream()), "gn_scale")
         return out
 
+    def tanh_clamp(self, x: torch.Tensor, mag: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tanh(x / mag) * mag (AutoencoderTiny's latent clamp)."""
+        _f16(x, "x")
+        if out is None:
+            out = torch.empty_like(x)
+        self.handle.check(self.lib.gn_tanh_clamp(self.h, x.data_ptr(), float(mag), out.data_ptr(), x.numel(),
+                                                 self._stream()), "gn_tanh_clamp")
+        return out
+
     def timestep_embedding(self, t: float, dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if out is None:
             out = torch.empty(1, dim, dtype=torch.float16, device=self.device)

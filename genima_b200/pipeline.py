@@ -27,12 +27,12 @@ from typing import Callable, Dict, List, Optional, Sequence, Union
 import numpy as np
 import torch
 
-from .configs import CLIPTextConfig, SchedulerConfig, UNetConfig, VAEConfig
+from .configs import CLIPTextConfig, SchedulerConfig, TAESDConfig, UNetConfig, VAEConfig
 from .ops import Ops
 from .scheduler import EulerDiscreteSchedule
 from .text_encoder import DeviceCLIPText
 from .unet import LATENT_CPAD, DeviceControlNet, DeviceUNet, tensor_key
-from .vae import DeviceVAEDecoder
+from .vae import DeviceTAESDDecoder, DeviceVAEDecoder
 
 try:  # PIL is only needed for the "pil" input/output types the reference uses
     from PIL import Image
@@ -93,7 +93,9 @@ class B200ControlNetPipeline:
                             if self.concurrent_controlnet else None)
         self.unet_impl = DeviceUNet(ops, unet_sd, unet_cfg)
         self.controlnet_impl = DeviceControlNet(self.ops_side, controlnet_sd, unet_cfg)
-        self.vae_impl = DeviceVAEDecoder(ops, vae_sd, vae_cfg)
+        # AutoencoderKL decoder, or AutoencoderTiny when the caller selected TAESD (vae_cfg is a TAESDConfig)
+        self.vae_impl = (DeviceTAESDDecoder(ops, vae_sd, vae_cfg) if isinstance(vae_cfg, TAESDConfig)
+                         else DeviceVAEDecoder(ops, vae_sd, vae_cfg))
         self.text_impl = DeviceCLIPText(ops, text_sd, text_cfg) if text_sd is not None else None
         self.schedule = EulerDiscreteSchedule(scheduler_cfg)
         self.tokenizer = tokenizer

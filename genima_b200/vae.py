@@ -11,9 +11,11 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .configs import VAEConfig
+from .configs import TAESDConfig, VAEConfig
 from .ops import Ops, gn_bucket_for
+from .packing import pack_conv_weight
 from .unet import LATENT_CPAD, _Conv, _Params, _ResBlock
+from .weights import taesd_layer_plan
 
 RGB_CPAD = 8  # decoded image travels as [B, H, W, 8] fp16 (3 real channels)
 
@@ -93,3 +95,61 @@ class DeviceVAEDecoder:
         if out is None:
             out = torch.zeros(B, hh * 8, ww * 8, RGB_CPAD, dtype=torch.float16, device=z.device)
         return self.conv_out(ops, n, out=out)
+
+
+class DeviceTAESDDecoder:
+    """diffusers AutoencoderTiny.decode (DecoderTiny) on the same implicit-GEMM convolution kernel: every ReLU, the block
+    residual add + ReLU and the final `x * 2 - 1` live in GEMM epilogues (the last one folded into conv_out's weights and
+    bias), so the decoder is 35 convolutions, 3 nearest-upsample copies and one tanh clamp.  Same interface as
+    DeviceVAEDecoder.decode; selected when eval_cfg.autoencoder names a TAESD checkpoint
+    (controller/agent/sd_controlnet_agent.py:45-49)."""
+
+    def __init__(self, ops: Ops, sd: Dict[str, torch.Tensor], cfg: TAESDConfig):
+        self.ops, self.cfg = ops, cfg
+        P = self.P = _Params(sd, ops.device)
+        self.plan = []
+        for kind, i in taesd_layer_plan(cfg):
+            p = f"decoder.layers.{i}"
+            if kind == "conv_in":
+                self.plan.append(("conv", _Conv(P, p, cin_layout=(cfg.latent_channels, LATENT_CPAD)), "relu"))
+            elif kind == "relu":
+                continue                                            # fused into conv_in's epilogue
+            elif kind == "block":
+                self.plan.append(("block", [_Conv(P, f"{p}.conv.{j}") for j in (0, 2, 4)], None))
+            elif kind == "up":
+                self.plan.append(("up", None, None))
+            elif kind == "conv":                                    # bias-free 64 -> 64 convolution after an upsample
+                c = _Conv.__new__(_Conv)
+                w = P.host16(f"{p}.weight")
+                c.cout, c.k, c.stride, c.pad, c.bucket = w.shape[0], 3, 1, 1, 0
+                c.w = pack_conv_weight(w).to(ops.device)
+                c.b = torch.zeros(w.shape[0], dtype=torch.float32, device=ops.device)
+                self.plan.append(("conv", c, None))
+            elif kind == "conv_out":                                # (x * 2 - 1) folded: W' = 2 W, b' = 2 b - 1
+                c = _Conv.__new__(_Conv)
+                w = P.host16(f"{p}.weight")
+                c.cout, c.k, c.stride, c.pad, c.bucket = w.shape[0], 3, 1, 1, 0
+                c.w = pack_conv_weight((w.float() * 2.0).to(torch.float16)).to(ops.device)
+                c.b = (P.sd[f"{p}.bias"].float() * 2.0 - 1.0).to(ops.device)
+                self.plan.append(("conv_out", c, None))
+
+    def decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """z: [B, h, w, 8] fp16 latents (already divided by scaling_factor = 1) -> [B, 8h, 8w, 8] fp16 (RGB in 0..2)."""
+        ops = self.ops
+        B, hh, ww, _ = z.shape
+        up = 2 ** (len(self.cfg.num_blocks) - 1)
+        h = ops.tanh_clamp(z, self.cfg.latent_magnitude)
+        for kind, mod, act in self.plan:
+            if kind == "conv":
+                h = mod(ops, h, act_pre=act) if act else mod(ops, h)
+            elif kind == "block":
+                y = mod[0](ops, h, act_pre="relu")
+                y = mod[1](ops, y, act_pre="relu")
+                h = mod[2](ops, y, residual=h, act_post="relu")
+            elif kind == "up":
+                h = ops.upsample_nearest2x(h)
+            else:
+                if out is None:
+                    out = torch.zeros(B, hh * up, ww * up, RGB_CPAD, dtype=torch.float16, device=z.device)
+                return mod(ops, h, out=out)
+        raise RuntimeError("TAESD layer plan has no conv_out")

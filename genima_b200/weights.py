@@ -164,6 +164,45 @@ def vae_decoder_shapes(cfg: VAEConfig) -> Shapes:
     return s
 
 
+def taesd_layer_plan(cfg):
+    """DecoderTiny's nn.Sequential as [(kind, index)]: kind in conv_in / relu / block / up / conv / conv_out; index = the
+    position in `decoder.layers` (the state-dict key prefix)."""
+    plan = [("conv_in", 0), ("relu", 1)]
+    idx = 2
+    n = len(cfg.num_blocks)
+    for i, nb in enumerate(cfg.num_blocks):
+        for _ in range(nb):
+            plan.append(("block", idx))
+            idx += 1
+        if i < n - 1:
+            plan.append(("up", idx))
+            idx += 1
+            plan.append(("conv", idx))
+        else:
+            plan.append(("conv_out", idx))
+        idx += 1
+    return plan
+
+
+def taesd_decoder_shapes(cfg) -> Shapes:
+    """diffusers AutoencoderTiny: decoder.layers.{i}[.conv.{0,2,4}].{weight,bias} (the 64 -> 64 convolutions that follow an
+    Upsample have no bias; AutoencoderTinyBlock.skip is an Identity because in == out channels)."""
+    s: Shapes = OrderedDict()
+    c = cfg.channels
+    for kind, i in taesd_layer_plan(cfg):
+        p = f"decoder.layers.{i}"
+        if kind == "conv_in":
+            _conv(s, p, c, cfg.latent_channels, 3)
+        elif kind == "block":
+            for j in (0, 2, 4):
+                _conv(s, f"{p}.conv.{j}", c, c, 3)
+        elif kind == "conv":
+            s[f"{p}.weight"] = (c, c, 3, 3)
+        elif kind == "conv_out":
+            _conv(s, p, cfg.out_channels, c, 3)
+    return s
+
+
 def clip_text_shapes(cfg: CLIPTextConfig) -> Shapes:
     """transformers CLIPTextModel schema (OpenAI clip weights map 1:1 onto it; text_projection is [proj, hidden])."""
     s: Shapes = OrderedDict()

@@ -219,6 +219,9 @@ int gn_euler_step(gn_handle* h, const void* x, const void* eps, float sigma, flo
                   void* x_scaled, int64_t n, void* stream);
 /* y = x * s (fp16), used for scale_model_input at step 0 and latents / scaling_factor before the VAE. */
 int gn_scale(gn_handle* h, const void* x, float s, void* y, int64_t n, void* stream);
+/* y = tanh(x / mag) * mag (fp16, n elements): AutoencoderTiny's soft clamp of the latents before its decoder
+ * (diffusers DecoderTiny.forward, reached when eval_cfg.autoencoder selects TAESD: sd_controlnet_agent.py:45-49). */
+int gn_tanh_clamp(gn_handle* h, const void* x, float mag, void* y, int64_t n, void* stream);
 /* NCHW fp16/fp32/uint8 <-> NHWC fp16 with channel padding (pad channels zero-filled). src_fp32: source element type,
  * 0 = fp16, 1 = fp32, 2 = uint8 (the camera frames of the reference's obs dict, [T, 3, 256, 256] u8).
  * mean3/std3 (host pointers, may be NULL): channels 0..2 become (src / 255 - mean) / std — GenimaACTPolicy.forward's

@@ -41,7 +41,9 @@ def controlnet_pipeline(unet_sd, cn_sd, vae_sd, ucfg: UNetConfig, vcfg: VAEConfi
         x = sched.step(eps, i, x)
         if return_intermediates:
             inter.append(dict(eps=eps, x=x))
-    img = sd_models.vae_decode(vae_sd, vcfg, x / vcfg.scaling_factor)
+    # AutoencoderKL, or AutoencoderTiny when the caller selected TAESD (sd_controlnet_agent.py:45-49)
+    decode = sd_models.taesd_decode if hasattr(vcfg, "num_blocks") else sd_models.vae_decode
+    img = decode(vae_sd, vcfg, x / vcfg.scaling_factor)
     den = (img / 2 + 0.5).clamp(0, 1)                                                      # postprocess, denormalize
     u8 = (den.permute(0, 2, 3, 1).numpy() * 255).round().astype(np.uint8)
     out = dict(latents=x, image=img, u8=u8)

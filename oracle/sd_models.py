@@ -204,3 +204,29 @@ def vae_decode(sd: SD, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
     h = F.group_norm(h, g, _w(sd, "decoder.conv_norm_out.weight"), _w(sd, "decoder.conv_norm_out.bias"), eps)
     h = F.silu(h)
     return F.conv2d(h, _w(sd, "decoder.conv_out.weight"), _w(sd, "decoder.conv_out.bias"), padding=1)
+
+
+def taesd_decode(sd: SD, cfg, z: torch.Tensor) -> torch.Tensor:
+    """diffusers AutoencoderTiny.decode(z) = DecoderTiny.forward: tanh(z / 3) * 3 -> conv / ReLU stack with nearest x2
+    upsampling -> x * 2 - 1 (images in [-1, 1], like AutoencoderKL.decode).  Reached from
+    controller/agent/sd_controlnet_agent.py:45-49 when eval_cfg.autoencoder names a TAESD checkpoint; the pipeline divides
+    the latents by scaling_factor (1.0) first.  [upstream, from memory: diffusers 0.29.0 models/autoencoders/vae.py]"""
+    from genima_b200.weights import taesd_layer_plan
+
+    h = torch.tanh(z / cfg.latent_magnitude) * cfg.latent_magnitude
+    for kind, i in taesd_layer_plan(cfg):
+        p = f"decoder.layers.{i}"
+        if kind in ("conv_in", "conv_out"):
+            h = F.conv2d(h, _w(sd, f"{p}.weight"), _w(sd, f"{p}.bias"), padding=1)
+        elif kind == "relu":
+            h = F.relu(h)
+        elif kind == "block":
+            y = F.relu(F.conv2d(h, _w(sd, f"{p}.conv.0.weight"), _w(sd, f"{p}.conv.0.bias"), padding=1))
+            y = F.relu(F.conv2d(y, _w(sd, f"{p}.conv.2.weight"), _w(sd, f"{p}.conv.2.bias"), padding=1))
+            y = F.conv2d(y, _w(sd, f"{p}.conv.4.weight"), _w(sd, f"{p}.conv.4.bias"), padding=1)
+            h = F.relu(y + h)
+        elif kind == "up":
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+        elif kind == "conv":
+            h = F.conv2d(h, _w(sd, f"{p}.weight"), None, padding=1)
+    return h * 2.0 - 1.0

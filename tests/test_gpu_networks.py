@@ -244,6 +244,52 @@ def test_vae_decode_full_size(ops):
     check("full-size VAE decode", out[..., :3], nhwc(ref), NET_TOL, nhwc(stock))
 
 
+# --------------------------------------------------------------------------------------------------- TAESD decoder
+@pytest.mark.parametrize("name,B,hw", [("tiny", 2, 16), ("full", 1, 64)])
+def test_taesd_decode(ops, name, B, hw):
+    """diffusers AutoencoderTiny.decode (eval_cfg.autoencoder = '...taesd...', sd_controlnet_agent.py:45-49): tanh clamp,
+    ReLU / residual / (x * 2 - 1) epilogues.  Latents are scaled up so that the tanh clamp is exercised."""
+    from genima_b200.configs import TAESDConfig
+    from genima_b200.vae import DeviceTAESDDecoder
+    from oracle import sd_models
+
+    cfg = TAESDConfig.tiny() if name == "tiny" else TAESDConfig()
+    sd = W.synth_state_dict(W.taesd_decoder_shapes(cfg), salt=2)
+    z = torch.randn(B, 4, hw, hw, generator=torch.Generator().manual_seed(9)).to(torch.float16).float() * 2.5
+    ref = sd_models.taesd_decode(sd, cfg, z)
+    stock = sd_models.taesd_decode(_HalfSD(sd), cfg, z.to("cuda", torch.float16))
+    out = DeviceTAESDDecoder(ops, sd, cfg).decode(_latent_pad(z))
+    assert out.shape[:3] == (B, hw * 8, hw * 8)
+    check(f"{name} TAESD decode (B={B})", out[..., :3], nhwc(ref), NET_TOL, nhwc(stock))
+
+
+def test_agent_with_taesd_autoencoder(ops):
+    """B200ControlNetAgent with autoencoder='madebyollin/taesd' (synthetic tiny weights) against the oracle pipeline."""
+    import numpy as np
+    from PIL import Image
+
+    from genima_b200.agents import B200ControlNetAgent
+    from genima_b200.configs import TAESDConfig
+    from oracle.pipeline import controlnet_pipeline
+
+    agent = B200ControlNetAgent(dict(synthetic_weights="tiny", autoencoder="madebyollin/taesd", image_resolution=128,
+                                     device="cuda:0", use_cuda_graph=False, synthetic_text_encoder=False), ops=ops)
+    ucfg, tcfg = UNetConfig.tiny(), TAESDConfig.tiny()
+    g = torch.Generator().manual_seed(0)
+    tile = torch.randint(0, 256, (128, 128, 3), generator=g, dtype=torch.uint8).numpy()
+    ctx = torch.randn(1, 77, ucfg.cross_attention_dim, generator=g).half()
+    lat = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(2)).half()
+    out = agent.infer(images=[Image.fromarray(tile)], prompts=None, negative_prompts=None, prompt_embeds=ctx.cuda(),
+                      num_inference_steps=2, guidance_scale=0.0, generator=None, latents=lat.cuda())
+    got = np.asarray(out[0][0]).astype(np.int32)
+    ref = controlnet_pipeline(W.synth_state_dict(W.unet_shapes(ucfg)), W.synth_state_dict(W.controlnet_shapes(ucfg), 1),
+                              W.synth_state_dict(W.taesd_decoder_shapes(tcfg), 2), ucfg, tcfg, tile[None], ctx.float(),
+                              lat.float(), n_steps=2)
+    d = np.abs(got - ref["u8"][0].astype(np.int32))
+    print(f"agent + TAESD: uint8 image max |diff| {d.max()}, exact {100.0 * (d == 0).mean():.2f}%")
+    assert d.max() <= 2
+
+
 # --------------------------------------------------------------------------------------------------- ACT controller
 def _act_inputs(cfg, B=1):
     g = torch.Generator().manual_seed(0)

@@ -57,3 +57,32 @@ def test_synthetic_weights_are_deterministic_fp16_and_well_scaled():
         if v.dim() > 1:      # conv / linear weights ~ N(0, 1/fan_in): activations stay O(1) through the stack
             fan_in = v[0].numel()
             assert 0.5 < float(v.float().std()) * fan_in ** 0.5 < 1.5, k
+
+
+def test_taesd_decoder_schema_matches_published_size():
+    """AutoencoderTiny (madebyollin/taesd) decoder: 1.22 M parameters, 35 convolutions, bias-free 64->64 convs after
+    each of the three upsamples."""
+    from genima_b200 import weights as W
+    from genima_b200.configs import TAESDConfig
+
+    cfg = TAESDConfig()
+    shapes = W.taesd_decoder_shapes(cfg)
+    n = sum(int(torch.tensor(s).prod()) for s in shapes.values())
+    assert n == 1_222_531
+    convs = [k for k in shapes if k.endswith(".weight")]
+    assert len(convs) == 1 + 10 * 3 + 3 + 1
+    no_bias = [k for k in convs if k.replace(".weight", ".bias") not in shapes]
+    assert sorted(no_bias) == ["decoder.layers.11.weight", "decoder.layers.16.weight", "decoder.layers.6.weight"]
+    assert shapes["decoder.layers.18.weight"] == (3, 64, 3, 3) and shapes["decoder.layers.0.weight"] == (64, 4, 3, 3)
+
+
+def test_taesd_oracle_runs_and_is_bounded():
+    from genima_b200 import weights as W
+    from genima_b200.configs import TAESDConfig
+    from oracle import sd_models
+
+    cfg = TAESDConfig.tiny()
+    sd = W.synth_state_dict(W.taesd_decoder_shapes(cfg), salt=2)
+    z = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(0)) * 5.0
+    img = sd_models.taesd_decode(sd, cfg, z)
+    assert img.shape == (1, 3, 64, 64) and torch.isfinite(img).all()
