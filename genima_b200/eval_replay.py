@@ -66,6 +66,47 @@ def run_units(units: Sequence[Tuple[str, int]], agent_step: Callable[[np.ndarray
     return records
 
 
+def run_units_batched(units: Sequence[Tuple[str, int]],
+                      agent_step: Callable[[np.ndarray, np.ndarray, int, Sequence[bool]], np.ndarray], in_flight: int,
+                      size: int = 256, episode_length: int = 200, diffusion_seed: int = 2,
+                      reseed: Callable[[int, int], None] = lambda slot, seed: None) -> List[dict]:
+    """Like run_units, with up to `in_flight` independent episodes advanced in lock-step and batched into ONE agent-step
+    call (the reference loop is serial, README.md:299; episodes are independent, eval_genima.py:129-142, so batching them
+    changes no episode's results).  `agent_step(views [E, 4, S, S, 3], qpos [E, 1, 8], step, active [E]) -> actions
+    [E, 20, 8]`; `reseed(slot, seed)` re-seeds the generator of batch slot `slot` when a new episode starts there."""
+    records = []
+    for g0 in range(0, len(units), in_flight):
+        group = list(units[g0:g0 + in_flight])
+        envs = [StubEnv(t, e, size=size, episode_length=episode_length) for t, e in group]
+        for slot in range(len(group)):
+            reseed(slot, diffusion_seed)
+        steps = [0] * len(group)
+        done = [False] * len(group)
+        last = [None] * len(group)
+        t_total, k = 0.0, 0
+        obs = [env.observe() for env in envs]
+        while not all(done):
+            for i, env in enumerate(envs):
+                if not done[i] and k > 0:
+                    obs[i] = env.observe()
+            pad = in_flight - len(group)
+            views = np.stack([o[0] for o in obs] + [obs[0][0]] * pad)
+            qpos = np.stack([o[1] for o in obs] + [obs[0][1]] * pad)
+            t0 = time.perf_counter()
+            actions = agent_step(views, qpos, k, [not d for d in done] + [False] * pad)
+            t_total += time.perf_counter() - t0
+            for i, env in enumerate(envs):
+                if not done[i]:
+                    last[i] = actions[i]
+                    done[i] = env.step(actions[i])
+                    steps[i] += 1
+            k += 1
+        for i, (task, ep) in enumerate(group):
+            records.append({"task": task, "episode": ep, "agent_steps": steps[i], "sim_steps": envs[i].t,
+                            "mean_step_time": t_total / max(k, 1), "checksum": float(np.abs(last[i]).sum())})
+    return records
+
+
 def summarize(records: List[dict], wall_s: float, world: int) -> dict:
     steps = sum(r["agent_steps"] for r in records)
     return {"episodes": len(records), "agent_steps": steps, "wall_s": wall_s, "n_gpus": world,
@@ -90,6 +131,8 @@ def main(argv=None):
     ap.add_argument("--denoise-steps", type=int, default=5)
     ap.add_argument("--preset", default="sd-turbo", choices=["sd-turbo", "tiny"])
     ap.add_argument("--out", default="")
+    ap.add_argument("--episodes-in-flight", type=int, default=1,
+                    help="independent episodes batched into one agent-step call per GPU (1 = the reference's serial loop)")
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -114,28 +157,41 @@ def main(argv=None):
     S = acfg.image_size
     ctx = torch.randn(1, 77, ucfg.cross_attention_dim, generator=torch.Generator().manual_seed(3)).half().to(dev)
     task_emb = torch.randn(1, acfg.task_emb_dim, generator=torch.Generator().manual_seed(4)).to(dev)
-    gen = torch.Generator(device=dev)
-    pin_v = torch.empty(1, 4, S, S, 3, dtype=torch.uint8).pin_memory()
-    pin_q = torch.empty(1, acfg.state_dim, dtype=torch.float32).pin_memory()
+    E = max(1, args.episodes_in_flight)
+    gens = [torch.Generator(device=dev) for _ in range(E)]            # one noise stream per in-flight episode
+    pin_v = torch.empty(E, 4, S, S, 3, dtype=torch.uint8).pin_memory()
+    pin_q = torch.empty(E, acfg.state_dim, dtype=torch.float32).pin_memory()
+    ctx_e, task_e = ctx.repeat(E, 1, 1), task_emb.repeat(E, 1)
 
-    def agent_step(views, qpos, _k):
-        pin_v.copy_(torch.from_numpy(views)[None])
-        pin_q.copy_(torch.from_numpy(qpos))
-        lat = torch.randn((1, 4, S // 4, S // 4), generator=gen, device=dev, dtype=torch.float16)   # diffusers prepare_latents
-        out = step(pin_v.to(dev, non_blocking=True), lat, pin_q.to(dev, non_blocking=True), task_emb, prompt_embeds=ctx)
-        return out["a_hat"][0].float().cpu().numpy()                                                 # the step's sync point
+    def agent_step_batched(views, qpos, _k, _active):
+        pin_v.copy_(torch.from_numpy(views))
+        pin_q.copy_(torch.from_numpy(qpos).reshape(E, -1))
+        # diffusers prepare_latents, one generator per episode: every episode sees the noise it would see on its own
+        lat = torch.cat([torch.randn((1, 4, S // 4, S // 4), generator=g, device=dev, dtype=torch.float16) for g in gens])
+        out = step(pin_v.to(dev, non_blocking=True), lat, pin_q.to(dev, non_blocking=True), task_e, prompt_embeds=ctx_e)
+        return out["a_hat"].float().cpu().numpy()                                                    # the step's sync point
+
+    def agent_step(views, qpos, k):
+        return agent_step_batched(views[None], qpos[None], k, [True])[0]
 
     units = gd.shard_units(RLBENCH_25[:args.tasks], args.episodes, rank, world)
-    agent_step(*StubEnv("warm", 0, S).observe(), 0)                     # graph capture outside the timed region
+    w_views, w_qpos = StubEnv("warm", 0, S).observe()
+    agent_step_batched(np.stack([w_views] * E), np.stack([w_qpos] * E), 0, [True] * E)   # graph capture, untimed
     if world > 1:
         dist.barrier(device_ids=[local])
     t0 = time.perf_counter()
-    recs = run_units(units, agent_step, size=S, episode_length=args.episode_length, reseed=lambda s: gen.manual_seed(s))
+    if E == 1:
+        recs = run_units(units, agent_step, size=S, episode_length=args.episode_length,
+                         reseed=lambda s: gens[0].manual_seed(s))
+    else:
+        recs = run_units_batched(units, agent_step_batched, E, size=S, episode_length=args.episode_length,
+                                 reseed=lambda slot, s: gens[slot].manual_seed(s))
     torch.cuda.synchronize()
     wall = gd.reduce_max(time.perf_counter() - t0, device=dev)
     allrecs = gd.gather_records(recs)
     if rank == 0:
         out = summarize(allrecs, wall, world)
+        out["episodes_in_flight_per_gpu"] = E
         print(json.dumps(out), flush=True)
         if args.out:
             with open(args.out, "w") as f:

@@ -38,3 +38,30 @@ def test_shards_cover_config5_exactly_once():
     assert max(sizes) - min(sizes) <= 1
     s = summarize([{"agent_steps": 11, "mean_step_time": 0.03}] * 4, wall_s=2.0, world=2)
     assert s["agent_steps"] == 44 and s["agent_steps_per_sec"] == 22.0
+
+
+def test_batched_episode_loop_matches_the_serial_one():
+    """Episodes advanced in lock-step (episodes in flight) see the same observations, step counts and per-slot re-seeding
+    as the serial loop; a ragged last group is padded, never stepped."""
+    from genima_b200.eval_replay import run_units_batched
+
+    units = [("open_box", 0), ("open_box", 1), ("push_button", 0)]
+    seen_serial, seen_batched, seeds = {}, {}, []
+
+    def fake_serial(views, qpos, k):
+        seen_serial.setdefault(len(seen_serial) // 11, []).append(int(views.sum()))
+        return np.full((20, 8), float(views[0, 0, 0, 0]), dtype=np.float32)
+
+    def fake_batched(views, qpos, k, active):
+        assert views.shape == (2, 4, 64, 64, 3) and qpos.shape == (2, 1, 8) and len(active) == 2
+        for i, a in enumerate(active):
+            if a:
+                seen_batched.setdefault((len(seeds), i), []).append(int(views[i].sum()))
+        return np.stack([np.full((20, 8), float(v[0, 0, 0, 0]), dtype=np.float32) for v in views])
+
+    serial = run_units(units, fake_serial, size=64, episode_length=200)
+    batched = run_units_batched(units, fake_batched, 2, size=64, episode_length=200,
+                                reseed=lambda slot, s: seeds.append((slot, s)))
+    assert seeds == [(0, 2), (1, 2), (0, 2)]
+    assert [(r["task"], r["episode"], r["agent_steps"], r["sim_steps"], r["checksum"]) for r in serial] == \
+           [(r["task"], r["episode"], r["agent_steps"], r["sim_steps"], r["checksum"]) for r in batched]
