@@ -53,6 +53,7 @@ struct gn_handle {
   bool gna_attr_set = false;
   int gn_max_ctas = 0;  // 0: one CTA per SM
   bool pdl = true;      // launch the main kernels with programmatic stream serialization (gn_set_pdl)
+  bool half_a_box = true;       // 64-row A boxes / 8 KiB A stages when an m-tile has at most 64 real rows
   bool w_prefetch = true;       // GEMM producers request the first W tiles before griddepcontrol.wait (gn_set_pdl(h, 2) = off)
   bool staged_epilogue = true;  // GEMM outputs staged in shared memory and TMA-stored (gn_set_staged_epilogue)
   bool fast_epilogue = true;    // compact per-activation kernel flavours (gn_set_staged_epilogue(h, 2) = staged, generic)

@@ -89,6 +89,9 @@ struct GemmParams {
   int halo;      // 1: halo mode (mode == 1 only)
   int halo_ncb;  // 64-channel blocks of the main input; k-blocks [0, 9 * halo_ncb) are ((cb, kx), ky), ky fastest
   int halo_bo;   // (unused) descriptor variant switch
+  int a_stage_bytes;  // bytes of one A stage: 16 KiB, or 8 KiB when every m-tile has at most 64 real rows (8 x 8 images,
+                      // M <= 64): the A box then carries 64 rows, the MMA still spans 128 (rows 64.. read whatever follows in
+                      // shared memory; those accumulator rows are never stored), and the ring gets ~1.5x deeper
   int w_prefetch;  // 1: W is a constant weight matrix -- the producer requests the first W tiles BEFORE griddepcontrol.wait,
                    // so weight streaming (cold in HBM at batch 1) overlaps the tail of the previous kernel
   int mcast;  // compact flavours: cluster size along grid.y whose CTAs share the W tile through TMA multicast (1 = off)
@@ -995,7 +998,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   const int b_stage_bytes = block_n * BLOCK_K * 2;
 
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + (p.halo ? HALO_STAGES * HALO_STAGE : stages * A_STAGE_BYTES);
+  uint8_t* smem_b = smem + (p.halo ? HALO_STAGES * HALO_STAGE : stages * p.a_stage_bytes);
   // tail region (offsets computed by the host, see smem_layout): per-column scale / bias, GroupNorm column partials,
   // mbarriers.  The fp32 staging tile of the split-K cluster reduction aliases the operand ring; the fp16 output staging
   // buffer aliases it too unless it must coexist with the main loop (residual prefetch) or with the split-K partials.
@@ -1150,18 +1153,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         }
       }
       int cb = kb_begin - seg_start;
-      const uint32_t tx_bytes = A_STAGE_BYTES + b_stage_bytes;
+      const uint32_t tx_bytes = p.a_stage_bytes + b_stage_bytes;
       for (int it = 0; it < num_it; ++it) {
         const int s = it % stages;
         const uint32_t ph = (it / stages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], it < w_pre ? (uint32_t)A_STAGE_BYTES : tx_bytes);
+        mbar_arrive_expect_tx(&full_bar[s], it < w_pre ? (uint32_t)p.a_stage_bytes : tx_bytes);
         const int kb = kb_begin + it;
         if (p.mode == 0) {
-          tma_load_2d(smem_a + s * A_STAGE_BYTES, &p.tmA[0], &full_bar[s], kb * BLOCK_K, m0);
+          tma_load_2d(smem_a + s * p.a_stage_bytes, &p.tmA[0], &full_bar[s], kb * BLOCK_K, m0);
         } else {
           const KSeg sg = p.segs[seg];
-          tma_load_4d(smem_a + s * A_STAGE_BYTES, &p.tmA[sg.map], &full_bar[s], cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy,
+          tma_load_4d(smem_a + s * p.a_stage_bytes, &p.tmA[sg.map], &full_bar[s], cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy,
                       b0);
           if (++cb == sg.nblk) {
             cb = 0;
@@ -1187,8 +1190,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         const int bn_out = p.epi.geglu ? (block_n >> 1) : block_n;
         const int n_out_total = p.epi.geglu ? (p.epi.N >> 1) : p.epi.N;
         const int io_bytes = bn_out * BLOCK_M * 2;
-        const int a_bytes = p.halo ? HALO_STAGES * HALO_STAGE : stages * A_STAGE_BYTES;
-        int need = (io_bytes <= a_bytes && !p.halo) ? (io_bytes + A_STAGE_BYTES - 1) / A_STAGE_BYTES : stages;
+        const int a_bytes = p.halo ? HALO_STAGES * HALO_STAGE : stages * p.a_stage_bytes;
+        int need = (io_bytes <= a_bytes && !p.halo) ? (io_bytes + p.a_stage_bytes - 1) / p.a_stage_bytes : stages;
         if (need > stages) need = stages;
         for (int s = 0; s < need; ++s) {
           int itv = num_it - (num_it % stages) + s;  // first virtual iteration >= num_it that would reuse stage s
@@ -1242,7 +1245,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (it == 0) trace_stamp(p, 3);
-        const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES), 1024, 0);
+        const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * p.a_stage_bytes), 1024, 0);
         const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * b_stage_bytes), 1024, 0);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 16; ++k) {
@@ -1452,6 +1455,7 @@ struct OutGeom {
   bool mcast_ok = false;    // a non-split launch can use a compact flavour (and therefore W-tile multicast)
   bool halo = false;        // halo-mode convolution: the A ring holds HALO_STAGES halo tiles
   bool res_late = false;    // (set per candidate) alias the residual staging buffer with the operand ring
+  int a_stage = A_STAGE_BYTES;  // bytes of one A stage (8 KiB when the A box carries 64 rows)
   int img_rows = 0;       // rows of one image inside a 128-row tile (GroupNorm statistics); 0: layout unsupported
 };
 
@@ -1471,7 +1475,7 @@ static SmemLayout smem_layout(int block_n, int stages, int splits, const OutGeom
   SmemLayout L;
   const int bn_out = og.geglu ? block_n / 2 : block_n;
   int ring = og.halo ? HALO_STAGES * HALO_STAGE + stages * block_n * BLOCK_K * 2
-                     : stages * (A_STAGE_BYTES + block_n * BLOCK_K * 2);
+                     : stages * (og.a_stage + block_n * BLOCK_K * 2);
   const int stage_tile = block_n * BLOCK_M * 4;  // fp32 staging tile of the cluster split-K reduction (aliases the ring)
   const bool split_fast = splits > 1 && og.split_fast;
   if (splits > 1 && !split_fast && stage_tile > ring) ring = stage_tile;
@@ -1499,7 +1503,7 @@ constexpr int SMEM_OCC1 = 200 * 1024;  // one CTA per SM: deep operand ring
 constexpr int SMEM_OCC2 = 112 * 1024;  // two CTAs per SM: one CTA's epilogue / set-up overlaps the other's main loop
 
 static int stages_for(int block_n, int splits, int kb_per, int budget, const OutGeom& og) {
-  int st = og.halo ? 12 : 8;
+  int st = (og.halo || og.a_stage < A_STAGE_BYTES) ? 12 : 8;
   while (st > 2 && smem_bytes_for(block_n, st, splits, og) > budget) --st;
   if (st > kb_per) st = kb_per < 2 ? 2 : kb_per;
   return st;
@@ -1737,6 +1741,7 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
     if (rc) return rc;
   }
   p.mcast = tc.mcast;
+  p.a_stage_bytes = og.a_stage;
   p.w_prefetch = (h->w_prefetch && !p.w_dynamic) ? 1 : 0;
   // epilogue staging: layout, sub-tile width and the output / residual tensor maps
   const SmemLayout L = smem_layout(tc.block_n, tc.stages, tc.splits, og);
@@ -1823,7 +1828,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
   p.rs_capacity = rs_capacity;
   snprintf(keybuf, sizeof(keybuf), "%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d", p.mode, tiles_m, N, p.num_kblocks,
            geglu ? 1 : 0, p.epi.out32 ? 1 : 0, p.epi.residual ? 1 : 0, p.epi.ln_stats ? 1 : 0, rs_capacity,
-           og.stage_ok ? 1 : 0, og.res_ok ? 1 : 0, (og.gn ? og.img_rows : 0) + (og.halo ? 1000 : 0));
+           og.stage_ok ? 1 : 0, og.res_ok ? 1 : 0, (og.gn ? og.img_rows : 0) + (og.halo ? 1000 : 0) + (og.a_stage != A_STAGE_BYTES ? 2000 : 0));
   const std::string key(keybuf);
   if (!forced) {
     auto it = h->tune_cache.find(key);
@@ -1918,11 +1923,12 @@ extern "C" int gn_linear(gn_handle* h, const void* A, int64_t lda, int M, int K,
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t strides[1] = {(uint64_t)lda * 2};
-    uint32_t box[2] = {BLOCK_K, BLOCK_M};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)(M <= 64 && h->half_a_box ? 64 : BLOCK_M)};
     rc = make_tmap_f16(h, &p.tmA[0], A, 2, dims, strides, box);
     if (rc) return rc;
   }
   OutGeom og;
+  og.a_stage = (M <= 64 && h->half_a_box) ? A_STAGE_BYTES / 2 : A_STAGE_BYTES;
   rc = fill_out_geom(h, p, og, epi, out);
   if (rc) return rc;
   og.rank = 2;
@@ -1980,6 +1986,10 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
     bh = HALO_H;
     bb = 1;
   }
+  // images per A box: when the whole batch fills exactly 64 of the tile's 128 rows (one 8 x 8 image), the A box carries
+  // just those rows (8 KiB stages, see GemmParams::a_stage_bytes)
+  int bb_box = bb;
+  if (!halo && h->half_a_box && B < bb && bw * bh * B == 64) bb_box = B;
   p.bw = bw;
   p.bh = bh;
   p.bb = bb;
@@ -2006,7 +2016,7 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
   } else if (stride == 1) {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb_box};
     rc = make_tmap_f16(h, &p.tmA[0], x, 4, dims, strides, box);
     if (rc) return rc;
     nmaps = 1;
@@ -2025,7 +2035,7 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
         const __half* base = static_cast<const __half*>(x) + ((int64_t)py * W + px) * C;
         uint64_t dims[4] = {(uint64_t)C, (uint64_t)(W / 2), (uint64_t)(H / 2), (uint64_t)B};
         uint64_t strides[3] = {(uint64_t)2 * C * 2, (uint64_t)2 * W * C * 2, (uint64_t)H * W * C * 2};
-        uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb_box};
         rc = make_tmap_f16(h, &p.tmA[py * 2 + px], base, 4, dims, strides, box);
         if (rc) return rc;
       }
@@ -2050,7 +2060,7 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
     GN_CHECK_ARG(h, exc[i] > 0 && (exc[i] % 8) == 0, "gn_conv2d: extra source channels must be a multiple of 8");
     uint64_t dims[4] = {(uint64_t)exc[i], (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)exc[i] * 2, (uint64_t)Wo * exc[i] * 2, (uint64_t)Ho * Wo * exc[i] * 2};
-    uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb_box};
     rc = make_tmap_f16(h, &p.tmA[nmaps], exs[i], 4, dims, strides, box);
     if (rc) return rc;
     const int ecp = round_up(exc[i], BLOCK_K);
@@ -2068,6 +2078,7 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
   rc = fill_out_geom(h, p, og, epi, out);
   if (rc) return rc;
   og.halo = halo;
+  og.a_stage = bb_box != bb ? A_STAGE_BYTES / 2 : A_STAGE_BYTES;
   og.rank = 4;
   og.dims[1] = (uint64_t)Wo;
   og.dims[2] = (uint64_t)Ho;
