@@ -203,7 +203,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
       float mx = -INFINITY;
       if (nvalid >= 64) {  // (warp-uniform) every column is a real key: no masking
 #pragma unroll
-        for (int j = 0; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        {
+          // four independent chains instead of one 64-deep dependent FMNMX chain (two warps per scheduler cannot hide it)
+          float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]), m2 = __uint_as_float(r[2]), m3 = __uint_as_float(r[3]);
+#pragma unroll
+          for (int j = 4; j < 64; j += 4) {
+            m0 = fmaxf(m0, __uint_as_float(r[j]));
+            m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
+            m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 64; ++j) {
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
         m_used = m_new;
       }
       const float moff = m_used * c;
-      float lsum = 0.f;
+      float lsum4[4] = {0.f, 0.f, 0.f, 0.f};  // independent partial sums (fixed combination order: deterministic)
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         uint32_t pk[4];
@@ -252,7 +263,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
           const float p0 = ex2_approx(fmaf(__uint_as_float(r[8 * t + 2 * u]), c, -moff));     // -inf -> 0
           const float x1 = fmaf(__uint_as_float(r[8 * t + 2 * u + 1]), c, -moff);
           const float p1 = (u & 1) ? ex2_poly(x1) : ex2_approx(x1);  // -inf -> 2^-126 / 0
-          lsum += p0 + p1;
+          lsum4[u] += p0 + p1;
           pk[u] = pack_half2(p0, p1);
         }
         const uint32_t addr = p_row + ((static_cast<uint32_t>(t) ^ swz) << 4);
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
                      "r"(pk[3])
                      : "memory");
       }
-      l_run += lsum;
+      l_run += (lsum4[0] + lsum4[1]) + (lsum4[2] + lsum4[3]);
       fence_proxy_async_smem();  // P (generic-proxy writes) must be visible to the tensor core (async proxy)
       mbar_arrive(&p_full[st]);
     }
