@@ -106,6 +106,8 @@ class Ops:
                               "gn_set_gemm_multicast")
         # GroupNorm statistics fused into the producing GEMM epilogues (A/B switch: GENIMA_B200_GNFUSE=0)
         self.gn_fuse = os.environ.get("GENIMA_B200_GNFUSE", "1") != "0"
+        # nearest-upsample folded into the following convolution (four 2x2 phase kernels; A/B: GENIMA_B200_UPFOLD=0)
+        self.fold_upsample = os.environ.get("GENIMA_B200_UPFOLD", "1") != "0"
         self._gn_arena = torch.zeros(self.GN_ARENA_WORDS, dtype=torch.int64, device=self.device)
         self._gn_used = 0
         self._gn_generation = 0
@@ -318,6 +320,36 @@ class Ops:
                                 ex[0], exc[0], ex[1], exc[1], out.data_ptr(), out.stride(2), C.byref(e),
                                 self._stream())
         self.handle.check(rc, "gn_conv2d")
+        if st is not None:
+            out.gn_stats = st
+        return out
+
+    def conv2d_up2x(self, x: torch.Tensor, w4: torch.Tensor, cout: int, out: Optional[torch.Tensor] = None,
+                    **epi) -> torch.Tensor:
+        """conv3x3(pad 1)(nearest x2 upsample(x)) as four 2x2 phase convolutions over x (gn_conv2d_up2x); `w4` from
+        packing.pack_upsample_conv_weight.  Returns [B, 2H, 2W, cout]."""
+        _f16(x, "x")
+        _f16(w4, "w4")
+        if x.dim() != 4 or not x.is_contiguous():
+            raise ValueError("x must be a contiguous [B, H, W, C] tensor")
+        B, H, W, Cin = x.shape
+        cp = (Cin + 63) // 64 * 64
+        if tuple(w4.shape) != (4, cout, 4 * cp) or not w4.is_contiguous():
+            raise ValueError(f"packed phase weights must be [4, {cout}, {4 * cp}], got {tuple(w4.shape)}")
+        if out is None:
+            out = torch.empty(B, 2 * H, 2 * W, cout, dtype=torch.float16, device=x.device)
+        if tuple(out.shape) != (B, 2 * H, 2 * W, cout) or not out.is_contiguous() or out.dtype != torch.float16:
+            raise ValueError("bad `out` tensor for conv2d_up2x")
+        epi.setdefault("rows_per_batch", H * W)
+        bw = min(128, 1 << max(0, (W - 1).bit_length()))
+        bh = min(128 // bw, 1 << max(0, (H - 1).bit_length()))
+        st = self._gn_request(epi, B * 128, cout, 128, torch.float16) if bw * bh >= 16 and epi.get("gn_stats") else None
+        if st is None:
+            epi.pop("gn_stats", None)
+        e = self._epilogue(B * H * W, cout, **epi)
+        rc = self.lib.gn_conv2d_up2x(self.h, x.data_ptr(), B, H, W, Cin, w4.data_ptr(), cout, out.data_ptr(), cout,
+                                     C.byref(e), self._stream())
+        self.handle.check(rc, "gn_conv2d_up2x")
         if st is not None:
             out.gn_stats = st
         return out

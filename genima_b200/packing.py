@@ -54,6 +54,29 @@ def pack_conv_weight(w: torch.Tensor, extras: Sequence[torch.Tensor] = (), cin_l
     return torch.cat(parts, dim=1).contiguous()
 
 
+def pack_upsample_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """3x3 convolution that follows a nearest-neighbour x2 upsample (diffusers Upsample2D, TAESD) -> the four 2x2 phase
+    kernels of gn_conv2d_up2x, packed [4, Cout, 4 * Cp].
+
+    Output pixel (2y + py, 2x + px) of conv3x3(upsample(x)) reads upsampled rows 2y + py - 1 .. 2y + py + 1, i.e. input rows
+    {y - 1, y, y} for py = 0 and {y, y, y + 1} for py = 1: the taps that fall on the same input pixel are summed (in fp32,
+    rounded to fp16 once)."""
+    assert w.shape[2:] == (3, 3), w.shape
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}   # parity -> kernel taps per effective tap
+    wf = w.float()
+    phases = []
+    for py in (0, 1):
+        for px in (0, 1):
+            eff = torch.zeros(w.shape[0], w.shape[1], 2, 2, device=w.device)
+            for ty, kys in enumerate(groups[py]):
+                for tx, kxs in enumerate(groups[px]):
+                    for ky in kys:
+                        for kx in kxs:
+                            eff[:, :, ty, tx] += wf[:, :, ky, kx]
+            phases.append(pack_conv_weight(eff.to(torch.float16)))
+    return torch.stack(phases, 0).contiguous()
+
+
 def pack_geglu_weight(w: torch.Tensor, b: torch.Tensor):
     """diffusers GEGLU: proj = Linear(K, 2D); hidden, gate = proj(x).chunk(2, -1); out = hidden * gelu(gate).
     Re-order rows into 64-wide (value, gate) blocks so one 128-column accumulator group holds matching pairs."""

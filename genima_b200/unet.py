@@ -24,7 +24,7 @@ import torch
 
 from .configs import UNetConfig
 from .ops import Ops, gn_bucket_for
-from .packing import fold_layer_norm, pack_conv_weight, pack_geglu_weight
+from .packing import fold_layer_norm, pack_conv_weight, pack_geglu_weight, pack_upsample_conv_weight
 from .weights import unet_skip_channels
 
 LATENT_CPAD = 8  # latents travel as [B, h, w, 8] fp16 (4 real channels): 16-byte pixels for TMA
@@ -173,17 +173,27 @@ class _Transformer2D:
 
 
 class _Conv:
-    def __init__(self, P: _Params, prefix: str, stride: int = 1, cin_layout: Sequence[int] = (), gn: bool = False):
+    def __init__(self, P: _Params, prefix: str, stride: int = 1, cin_layout: Sequence[int] = (), gn: bool = False,
+                 upsample: bool = False):
         self.bucket = P.gn_bucket if gn else 0   # gn: the output feeds a GroupNorm -> accumulate its statistics
         w = P.host16(f"{prefix}.weight")
         self.cout, self.k, self.stride = w.shape[0], w.shape[2], stride
         self.pad = self.k // 2
         self.w = pack_conv_weight(w, cin_layout=cin_layout).to(P.device)
-        self.b = P.f32(f"{prefix}.bias")
+        self.b = P.f32(f"{prefix}.bias") if P.has(f"{prefix}.bias") else torch.zeros(self.cout, device=P.device)
+        # upsample: this convolution follows a nearest x2 upsample (Upsample2D): keep the four 2x2 phase kernels too
+        self.w4 = pack_upsample_conv_weight(w).to(P.device) if upsample and self.k == 3 and w.shape[1] % 8 == 0 else None
 
     def __call__(self, ops: Ops, x: torch.Tensor, **epi) -> torch.Tensor:
         return ops.conv2d(x, self.w, self.cout, ksize=self.k, stride=self.stride, pad=self.pad, bias=self.b,
                           gn_stats=self.bucket, **epi)
+
+    def upsampled(self, ops: Ops, x: torch.Tensor, **epi) -> torch.Tensor:
+        """conv(nearest_upsample_x2(x)): folded into four 2x2 phase convolutions over x (4/9 of the multiply-adds, no
+        upsampled tensor) when the phase kernels exist, else upsample kernel + convolution."""
+        if self.w4 is not None and ops.fold_upsample and x.shape[2] % 8 == 0:
+            return ops.conv2d_up2x(x, self.w4, self.cout, bias=self.b, gn_stats=self.bucket, **epi)
+        return self(ops, ops.upsample_nearest2x(x), **epi)
 
 
 class _Encoder:
@@ -287,7 +297,7 @@ class DeviceUNet(_Encoder):
                 att.append(_Transformer2D(P, f"up_blocks.{i}.attentions.{j}", cout, cfg.num_heads[level], g)
                            if cfg.attn_levels[level] else None)
                 prev = cout
-            us = _Conv(P, f"up_blocks.{i}.upsamplers.0.conv", gn=True) if i < len(ch) - 1 else None
+            us = _Conv(P, f"up_blocks.{i}.upsamplers.0.conv", gn=True, upsample=True) if i < len(ch) - 1 else None
             self.up.append((res, att, us))
         self.out_g, self.out_b = P.f32("conv_norm_out.weight"), P.f32("conv_norm_out.bias")
         self.conv_out = _Conv(P, "conv_out")
@@ -318,7 +328,7 @@ class DeviceUNet(_Encoder):
                 if tr is not None:
                     h = tr(ops, h, kv[tr.prefix], tk)
             if us is not None:
-                h = us(ops, ops.upsample_nearest2x(h))
+                h = us.upsampled(ops, h)
         n = ops.group_norm(h, self.out_g, self.out_b, self.cfg.norm_num_groups, self.cfg.norm_eps, silu=True)
         return self.conv_out(ops, n, out=eps_out)
 

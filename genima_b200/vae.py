@@ -49,7 +49,7 @@ class DeviceVAEDecoder:
             for j in range(cfg.layers_per_block + 1):
                 res.append(_ResBlock(P, f"decoder.up_blocks.{i}.resnets.{j}", (prev,), g, eps))
                 prev = cout
-            us = _Conv(P, f"decoder.up_blocks.{i}.upsamplers.0.conv", gn=True) if i < len(ch) - 1 else None
+            us = _Conv(P, f"decoder.up_blocks.{i}.upsamplers.0.conv", gn=True, upsample=True) if i < len(ch) - 1 else None
             self.up.append((res, us))
         self.out_g, self.out_b = P.f32("decoder.conv_norm_out.weight"), P.f32("decoder.conv_norm_out.bias")
         self.conv_out = _Conv(P, "decoder.conv_out")
@@ -90,7 +90,7 @@ class DeviceVAEDecoder:
             for rb in res:
                 h = rb(ops, h, None, None)
             if us is not None:
-                h = us(ops, ops.upsample_nearest2x(h))
+                h = us.upsampled(ops, h)
         n = ops.group_norm(h, self.out_g, self.out_b, self.cfg.norm_num_groups, self.cfg.norm_eps, silu=True)
         if out is None:
             out = torch.zeros(B, hh * 8, ww * 8, RGB_CPAD, dtype=torch.float16, device=z.device)
@@ -119,12 +119,8 @@ class DeviceTAESDDecoder:
             elif kind == "up":
                 self.plan.append(("up", None, None))
             elif kind == "conv":                                    # bias-free 64 -> 64 convolution after an upsample
-                c = _Conv.__new__(_Conv)
-                w = P.host16(f"{p}.weight")
-                c.cout, c.k, c.stride, c.pad, c.bucket = w.shape[0], 3, 1, 1, 0
-                c.w = pack_conv_weight(w).to(ops.device)
-                c.b = torch.zeros(w.shape[0], dtype=torch.float32, device=ops.device)
-                self.plan.append(("conv", c, None))
+                assert self.plan[-1][0] == "up"
+                self.plan[-1] = ("upconv", _Conv(P, p, upsample=True), None)   # folded: four 2x2 phase convolutions
             elif kind == "conv_out":                                # (x * 2 - 1) folded: W' = 2 W, b' = 2 b - 1
                 c = _Conv.__new__(_Conv)
                 w = P.host16(f"{p}.weight")
@@ -146,6 +142,8 @@ class DeviceTAESDDecoder:
                 y = mod[0](ops, h, act_pre="relu")
                 y = mod[1](ops, y, act_pre="relu")
                 h = mod[2](ops, y, residual=h, act_post="relu")
+            elif kind == "upconv":
+                h = mod.upsampled(ops, h)
             elif kind == "up":
                 h = ops.upsample_nearest2x(h)
             else:

@@ -171,6 +171,15 @@ int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C, const voi
               int stride, int pad, const void* ex0, int C_ex0, const void* ex1, int C_ex1, void* out, int64_t ldo,
               const gn_epilogue* epi, void* stream);
 
+/* out[B, 2H, 2W, Cout] = conv3x3(pad 1)(nearest-neighbour x2 upsample of x[B, H, W, C]) WITHOUT materialising the
+ * upsampled tensor (diffusers Upsample2D = F.interpolate(scale 2, "nearest") + conv): every output parity (py, px) is a
+ * 2x2 convolution over x whose taps are sums of the 3x3 taps that fall on the same input pixel, so the op is four
+ * implicit GEMMs with 4/9 of the multiply-adds, each TMA-storing its pixels with stride 2.  w4: four packed
+ * [Cout][2*2][Cp] matrices, phase (py * 2 + px) major (packing.pack_upsample_conv_weight).  GroupNorm statistics
+ * (gnstats_out) accumulate across the four launches.  Replaces upsample2x + cuDNN convolution. */
+int gn_conv2d_up2x(gn_handle* h, const void* x, int B, int H, int W, int C, const void* w4, int Cout, void* out,
+                   int64_t ldo, const gn_epilogue* epi, void* stream);
+
 /* ---- attention (tcgen05 flash attention, head_dim 64) -------------------------------------------------------
  * q: rows [B*Tq] with row stride ldq, head h at columns [h*64, h*64+64); k, v likewise with Tk rows per batch.
  * out[B*Tq, heads*64] = softmax(q k^T * scale) v.   Replaces xformers memory_efficient_attention / torch SDPA. */

@@ -108,3 +108,30 @@ def test_conv_heuristic_uses_split_k_for_weight_bound_levels(ops):
     bias = torch.randn(1280) * 0.1
     _conv_case(ops, 1, 8, 8, 2560, 1280, seed=31, bias=bias)
     assert ops.last_gemm_config()[1] > 1
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,bucket", [(1, 32, 640, 640, 10), (1, 8, 1280, 1280, 10), (2, 16, 128, 64, 0),
+                                                 (1, 64, 256, 256, 4)])
+def test_conv_up2x_matches_upsample_then_conv(ops, B, H, Cin, Cout, bucket):
+    """gn_conv2d_up2x (four 2x2 phase convolutions, strided TMA stores) against conv3x3(nearest x2 upsample) of the oracle;
+    with a bucket the GroupNorm statistics accumulated over the four launches are checked through gn_group_norm_apply."""
+    import torch.nn.functional as F
+
+    from genima_b200.packing import pack_upsample_conv_weight
+
+    g = torch.Generator().manual_seed(H + Cin)
+    x = torch.randn(B, H, H, Cin, generator=g).to(torch.float16)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5).to(torch.float16)
+    bias = torch.randn(Cout, generator=g) * 0.3
+    ops.gn_stats_reset()
+    out = ops.conv2d_up2x(x.cuda(), pack_upsample_conv_weight(w).cuda(), Cout, bias=bias.cuda(), gn_stats=bucket)
+    ref = F.conv2d(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest"), w.float(), bias,
+                   padding=1).permute(0, 2, 3, 1)
+    # the summed taps are rounded to fp16 once: slightly looser than the plain convolution tolerance
+    report_close(f"conv_up2x B{B} {H}^2 {Cin}->{Cout}", out, ref, rtol=2e-3, atol=2e-3)
+    if bucket:
+        gamma, beta = 1.0 + 0.1 * torch.randn(Cout, generator=g), 0.1 * torch.randn(Cout, generator=g)
+        calls0 = ops.gn_apply_calls
+        n = ops.group_norm(out, gamma.cuda(), beta.cuda(), groups=32, eps=1e-5, silu=True)
+        assert ops.gn_apply_calls == calls0 + 1
+        report_close("GN after conv_up2x", n, ops_ref.group_norm_ref(out.cpu(), gamma, beta, 32, 1e-5, True))

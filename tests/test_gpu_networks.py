@@ -287,7 +287,7 @@ def test_agent_with_taesd_autoencoder(ops):
                               lat.float(), n_steps=2)
     d = np.abs(got - ref["u8"][0].astype(np.int32))
     print(f"agent + TAESD: uint8 image max |diff| {d.max()}, exact {100.0 * (d == 0).mean():.2f}%")
-    assert d.max() <= 2
+    assert d.max() <= 3 and (d <= 1).mean() > 0.99   # (three folded upsample convolutions: summed taps rounded to fp16)
 
 
 # --------------------------------------------------------------------------------------------------- ACT controller

@@ -43,3 +43,36 @@ def test_pad_cols():
     w = torch.randn(3, 13).half()
     p = pad_cols(w, 8)
     assert p.shape == (3, 16) and torch.equal(p[:, :13], w) and not p[:, 13:].any()
+
+
+def test_upsample_conv_phase_kernels_reproduce_the_3x3_convolution():
+    """conv3x3(pad 1)(nearest x2 upsample(x)) == four 2x2 phase convolutions over x with summed taps (the identity behind
+    gn_conv2d_up2x), checked in fp64 on the unpacked effective kernels."""
+    import torch
+    import torch.nn.functional as F
+
+    from genima_b200.packing import pack_upsample_conv_weight
+
+    g = torch.Generator().manual_seed(0)
+    cin, cout, H, W = 64, 8, 6, 8
+    w = torch.randn(cout, cin, 3, 3, generator=g).half()
+    x = torch.randn(2, cin, H, W, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w.double(), padding=1)
+    w4 = pack_upsample_conv_weight(w)
+    assert tuple(w4.shape) == (4, cout, 4 * 64)
+    out = torch.zeros_like(ref)
+    for py in (0, 1):
+        for px in (0, 1):
+            eff = w4[py * 2 + px].double().reshape(cout, 2, 2, 64).permute(0, 3, 1, 2)   # [Cout, Cin, ty, tx]
+            # taps read input rows {y - 1, y} (parity 0) or {y, y + 1} (parity 1): pad one row / column on that side
+            xp = F.pad(x, (1 - px, px, 1 - py, py))
+            out[:, :, py::2, px::2] = F.conv2d(xp, eff)
+    # the only difference is the fp16 rounding of the summed taps
+    assert float((out - ref).abs().max()) < 2e-2 * float(ref.abs().max())
+    eff_exact = torch.zeros(cout, cin, 2, 2, dtype=torch.float64)
+    eff_exact[:, :, 0, 0] = w[:, :, 0, 0].double()
+    eff_exact[:, :, 0, 1] = (w[:, :, 0, 1].double() + w[:, :, 0, 2].double())
+    eff_exact[:, :, 1, 0] = (w[:, :, 1, 0].double() + w[:, :, 2, 0].double())
+    eff_exact[:, :, 1, 1] = w[:, :, 1:, 1:].double().sum(dim=(2, 3))
+    got00 = w4[0].double().reshape(cout, 2, 2, 64).permute(0, 3, 1, 2)
+    assert float((got00 - eff_exact).abs().max()) < 4e-3
