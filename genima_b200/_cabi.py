@@ -76,6 +76,8 @@ SIGNATURES = {
     "gn_linear": (_i, [_vp, _vp, _i64, _i, _i, _vp, _i, _vp, _i64, C.POINTER(GnEpilogue), _vp]),
     "gn_conv2d": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _i64,
                        C.POINTER(GnEpilogue), _vp]),
+    "gn_conv2d_asym": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i64,
+                            C.POINTER(GnEpilogue), _vp]),
     "gn_conv2d_up2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i64, C.POINTER(GnEpilogue), _vp]),
     "gn_attention": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _vp]),
     "gn_attention_small": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _vp]),

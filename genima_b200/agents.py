@@ -5,6 +5,8 @@
                            controller/agent/diffusion_agent.py:5-65): same constructor (eval_cfg), same
                            load_checkpoint / set_optimizations / common_setup / infer methods, same `.pipe` attribute and
                            `transform_to_half_resolution`; `.pipe` is a B200ControlNetPipeline.
+  B200Pix2PixAgent         the same for `agent.SDPix2PixAgent` (controller/agent/sd_pix2pix_agent.py:11-60); `.pipe` is a
+                           B200Pix2PixPipeline (InstructPix2Pix: VAE-encoded image latents, no ControlNet).
   B200GenimaACTPolicy      replacement for `GenimaACTPolicy` (controller/method/genima_act.py:142-214): forward(qpos, image,
                            actions=None, is_pad=None, task_emb=None) -> a_hat [B, 20, 8]; inference only.
   B200GenimaACT            the `act` / `encode_clip_text` surface of `GenimaACT` (genima_act.py:273-346) on the obs-dict
@@ -13,6 +15,7 @@ Everything arithmetic goes to libgenima_b200.so; these classes only translate ar
 """
 from __future__ import annotations
 
+import dataclasses
 import os
 import re
 from typing import Dict, List, Optional
@@ -25,7 +28,7 @@ from . import weights as W
 from .act_policy import DeviceACT
 from .configs import ACTConfig, CLIPTextConfig, SchedulerConfig, TAESDConfig, UNetConfig, VAEConfig
 from .ops import Ops
-from .pipeline import B200ControlNetPipeline
+from .pipeline import B200ControlNetPipeline, B200Pix2PixPipeline
 from .text_encoder import DeviceCLIPText
 from .unet import tensor_key
 
@@ -153,6 +156,37 @@ class B200ControlNetAgent:
             generator=kwargs["generator"],
             **{k: kwargs[k] for k in ("latents", "prompt_embeds", "output_type") if k in kwargs},
         )
+
+
+class B200Pix2PixAgent(B200ControlNetAgent):
+    """Drop-in for agent.SDPix2PixAgent (controller/agent/sd_pix2pix_agent.py:11-60): same constructor, optimisation
+    toggles, transforms and `infer` keywords as the ControlNet agent; `.pipe` is a B200Pix2PixPipeline (fine-tuned
+    8-channel U-Net from `<diffusion_ckpt>/checkpoint-*/unet`, VAE encoder + decoder, text encoder, scheduler from
+    sd_ckpt)."""
+
+    def load_checkpoint(self):
+        cfg = self.eval_cfg
+        ops = self._ops or get_ops(_cfg_get(cfg, "device", "cuda"))
+        if "taesd" in (_cfg_get(cfg, "autoencoder", "") or ""):
+            raise NotImplementedError("the InstructPix2Pix agent needs the AutoencoderKL encoder; TAESD is decode-only")
+        synth = _cfg_get(cfg, "synthetic_weights", None)
+        tok = _cfg_get(cfg, "tokenizer", None)
+        graph = bool(_cfg_get(cfg, "use_cuda_graph", True))
+        if synth:
+            ucfg, vcfg, tcfg, _ = _preset(synth)
+            ucfg = dataclasses.replace(ucfg, in_channels=2 * vcfg.latent_channels)
+            with_text = bool(_cfg_get(cfg, "synthetic_text_encoder", True))
+            vae_sd = W.synth_state_dict(W.vae_decoder_shapes(vcfg), salt=2)
+            vae_sd.update(W.synth_state_dict(W.vae_encoder_shapes(vcfg), salt=2))
+            self.pipe = B200Pix2PixPipeline(
+                ops, W.synth_state_dict(W.unet_shapes(ucfg), salt=5), vae_sd,
+                W.synth_state_dict(W.clip_text_shapes(tcfg)) if with_text else None,
+                ucfg, vcfg, tcfg, SchedulerConfig(), tokenizer=tok, use_cuda_graph=graph)
+            return
+        loaded = ckpt.load_sd_pix2pix(_cfg_get(cfg, "sd_ckpt"), _cfg_get(cfg, "diffusion_ckpt"))
+        self.pipe = B200Pix2PixPipeline(ops, loaded["unet"], loaded["vae"], loaded["text"], loaded["unet_cfg"],
+                                        loaded["vae_cfg"], loaded["text_cfg"], loaded["scheduler_cfg"], tokenizer=tok,
+                                        use_cuda_graph=graph)
 
 
 class B200GenimaACTPolicy:

@@ -15,6 +15,7 @@ import dataclasses
 import json
 import os
 import re
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -97,18 +98,44 @@ def check_schema(sd: Dict[str, torch.Tensor], shapes, what: str, allow_extra: Tu
                          f"{len(bad)} shape mismatches (e.g. {[(k, tuple(sd[k].shape), shapes[k]) for k in bad[:3]]})")
 
 
-def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: str):
-    """-> dict(unet=, controlnet=, vae=, text=, unet_cfg=, vae_cfg=, text_cfg=, scheduler_cfg=) from local directories."""
+def find_pix2pix_unet_dir(diffusion_ckpt: str) -> str:
+    """controller/agent/sd_pix2pix_agent.py:19-33: the last `*checkpoint*` sub-directory in natural order (else the
+    directory itself), sub-folder `unet`."""
+    dirs = sorted((d for d in os.listdir(diffusion_ckpt) if "checkpoint" in d), key=_natural_key)
+    return os.path.join(os.path.join(diffusion_ckpt, dirs[-1]) if dirs else diffusion_ckpt, "unet")
+
+
+def load_sd_pix2pix(sd_ckpt: str, diffusion_ckpt: str):
+    """-> dict(unet=, vae=, text=, unet_cfg=, vae_cfg=, text_cfg=, scheduler_cfg=): the fine-tuned 8-channel U-Net from
+    `<diffusion_ckpt>/checkpoint-*/unet`, everything else (full VAE with its encoder, text encoder, scheduler) from
+    sd_ckpt — what StableDiffusionInstructPix2PixPipeline.from_pretrained(sd_ckpt, unet=unet) assembles
+    (controller/agent/sd_pix2pix_agent.py:29-41)."""
+    out = load_sd_turbo(sd_ckpt, None)
+    udir = find_pix2pix_unet_dir(diffusion_ckpt)
+    ucfg = unet_config_from_json(_read_json(os.path.join(udir, "config.json")))
+    if ucfg.in_channels != 2 * out["vae_cfg"].latent_channels:
+        raise ValueError(f"InstructPix2Pix U-Net must take {2 * out['vae_cfg'].latent_channels} input channels, "
+                         f"{udir} has {ucfg.in_channels}")
+    out["unet"], out["unet_cfg"] = load_safetensors_dir(udir), ucfg
+    check_schema(out["unet"], W.unet_shapes(ucfg), "InstructPix2Pix U-Net")
+    check_schema(out["vae"], W.vae_encoder_shapes(out["vae_cfg"]), "VAE encoder")
+    return out
+
+
+def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: Optional[str]):
+    """-> dict(unet=, controlnet=, vae=, text=, unet_cfg=, vae_cfg=, text_cfg=, scheduler_cfg=) from local directories
+    (diffusion_ckpt None: the base components only, no ControlNet)."""
     if not os.path.isdir(sd_ckpt):
         raise FileNotFoundError(
             f"sd_ckpt {sd_ckpt!r} is not a local directory; hub ids cannot be resolved offline — point it at a local "
             "snapshot of stabilityai/sd-turbo (unet/, vae/, text_encoder/, scheduler/)")
     ucfg = unet_config_from_json(_read_json(os.path.join(sd_ckpt, "unet", "config.json")))
-    cn_dir = find_controlnet_dir(diffusion_ckpt)
-    ccfg = unet_config_from_json(_read_json(os.path.join(cn_dir, "config.json")))
-    if (ccfg.block_out_channels, ccfg.num_heads) != (ucfg.block_out_channels, ucfg.num_heads):
-        raise ValueError("ControlNet and U-Net configurations do not match")
-    ucfg = dataclasses.replace(ucfg, cond_embed_channels=ccfg.cond_embed_channels)
+    cn_dir = find_controlnet_dir(diffusion_ckpt) if diffusion_ckpt is not None else None
+    if cn_dir is not None:
+        ccfg = unet_config_from_json(_read_json(os.path.join(cn_dir, "config.json")))
+        if (ccfg.block_out_channels, ccfg.num_heads) != (ucfg.block_out_channels, ucfg.num_heads):
+            raise ValueError("ControlNet and U-Net configurations do not match")
+        ucfg = dataclasses.replace(ucfg, cond_embed_channels=ccfg.cond_embed_channels)
     vj = _read_json(os.path.join(sd_ckpt, "vae", "config.json"))
     vcfg = VAEConfig(latent_channels=vj.get("latent_channels", 4), out_channels=vj.get("out_channels", 3),
                      block_out_channels=tuple(vj.get("block_out_channels", (128, 256, 512, 512))),
@@ -122,12 +149,14 @@ def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: str):
                           act="quick_gelu" if tj.get("hidden_act", "gelu") == "quick_gelu" else "gelu",
                           eps=tj.get("layer_norm_eps", 1e-5))
     scfg = scheduler_config_from_json(_read_json(os.path.join(sd_ckpt, "scheduler", "scheduler_config.json")))
-    out = dict(unet=load_safetensors_dir(os.path.join(sd_ckpt, "unet")), controlnet=load_safetensors_dir(cn_dir),
+    out = dict(unet=load_safetensors_dir(os.path.join(sd_ckpt, "unet")),
+               controlnet=load_safetensors_dir(cn_dir) if cn_dir is not None else None,
                vae=load_safetensors_dir(os.path.join(sd_ckpt, "vae")),
                text=load_safetensors_dir(os.path.join(sd_ckpt, "text_encoder")),
                unet_cfg=ucfg, vae_cfg=vcfg, text_cfg=tcfg, scheduler_cfg=scfg)
     check_schema(out["unet"], W.unet_shapes(ucfg), "U-Net")
-    check_schema(out["controlnet"], W.controlnet_shapes(ucfg), "ControlNet")
+    if cn_dir is not None:
+        check_schema(out["controlnet"], W.controlnet_shapes(ucfg), "ControlNet")
     check_schema(out["vae"], W.vae_decoder_shapes(vcfg), "VAE decoder")
     check_schema(out["text"], W.clip_text_shapes(tcfg), "text encoder")
     return out
@@ -176,7 +205,8 @@ def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcf
                  sample_size=ucfg.sample_size)
     parts = [
         (os.path.join(sd_ckpt, "unet"), "diffusion_pytorch_model.fp16.safetensors", W.unet_shapes(ucfg), 0, ujson),
-        (os.path.join(sd_ckpt, "vae"), "diffusion_pytorch_model.fp16.safetensors", W.vae_decoder_shapes(vcfg), 2,
+        (os.path.join(sd_ckpt, "vae"), "diffusion_pytorch_model.fp16.safetensors",
+         OrderedDict(list(W.vae_decoder_shapes(vcfg).items()) + list(W.vae_encoder_shapes(vcfg).items())), 2,
          dict(_class_name="AutoencoderKL", latent_channels=vcfg.latent_channels,
               block_out_channels=list(vcfg.block_out_channels), layers_per_block=vcfg.layers_per_block,
               norm_num_groups=vcfg.norm_num_groups, scaling_factor=vcfg.scaling_factor)),
@@ -190,6 +220,10 @@ def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcf
          W.controlnet_shapes(ucfg), 1,
          dict(ujson, _class_name="ControlNetModel",
               conditioning_embedding_out_channels=list(ucfg.cond_embed_channels))),
+        # InstructPix2Pix fine-tune (diffusion/train_instruct_pix2pix_genima.py output): 8-channel conv_in
+        (os.path.join(root, "pix2pix_ckpt", "checkpoint-200", "unet"), "diffusion_pytorch_model.safetensors",
+         W.unet_shapes(dataclasses.replace(ucfg, in_channels=2 * vcfg.latent_channels)), 5,
+         dict(ujson, in_channels=2 * vcfg.latent_channels)),
     ]
     for d, fname, shapes, salt, cfg in parts:
         os.makedirs(d, exist_ok=True)
@@ -205,4 +239,4 @@ def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcf
     act_sd = W.synth_state_dict(W.act_shapes(acfg), salt=3)
     torch.save({"cfg": {}, "_epoch": 0, "_num_iters": 0, "agent": {f"actor.{k}": v for k, v in act_sd.items()}},
                os.path.join(ctl, "latest.pt"))
-    return dict(sd_ckpt=sd_ckpt, diffusion_ckpt=dif, controller_ckpt=ctl)
+    return dict(sd_ckpt=sd_ckpt, diffusion_ckpt=dif, controller_ckpt=ctl, pix2pix_ckpt=os.path.join(root, "pix2pix_ckpt"))

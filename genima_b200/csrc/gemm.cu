@@ -1953,7 +1953,7 @@ extern "C" int gn_linear(gn_handle* h, const void* A, int64_t lda, int M, int K,
 // Output placement of a convolution whose pixels do not land contiguously (gn_conv2d_up2x: one output parity per launch).
 struct ConvOutView {
   int Ho, Wo;              // output grid of THIS launch
-  int off_y, off_x;        // tap (ky, kx) reads input pixel (y + ky + off_y, x + kx + off_x)   (stride 1)
+  int off_y, off_x;        // tap (ky, kx) reads input pixel (s*y + ky + off_y, s*x + kx + off_x), s = stride
   int64_t sx, sy, sb;      // element strides of the output (and nothing else) per x / y / image step; 0 = contiguous
 };
 
@@ -1967,7 +1967,8 @@ static int conv_impl(gn_handle* h, const void* x, int B, int H, int W, int C, co
   GN_CHECK_ARG(h, stride == 1 || stride == 2, "gn_conv2d: stride %d unsupported", stride);
   GN_CHECK_ARG(h, KH * KW + 2 <= MAX_SEGS, "gn_conv2d: %dx%d kernel too large", KH, KW);
   GN_CHECK_ARG(h, stride == 1 || ((H % 2) == 0 && (W % 2) == 0), "gn_conv2d: stride 2 needs even H, W");
-  GN_CHECK_ARG(h, !view || (stride == 1 && !ex0 && !ex1), "strided output views need stride 1 and no extra sources");
+  GN_CHECK_ARG(h, !view || (!ex0 && !ex1), "output views take no extra sources");
+  GN_CHECK_ARG(h, !view || !view->sx || stride == 1, "strided output views need stride 1");
   const int Ho = view ? view->Ho : (H + 2 * pad - KH) / stride + 1;
   const int Wo = view ? view->Wo : (W + 2 * pad - KW) / stride + 1;
   const int off_y = view ? view->off_y : -pad, off_x = view ? view->off_x : -pad;
@@ -2049,7 +2050,7 @@ static int conv_impl(gn_handle* h, const void* x, int B, int H, int W, int C, co
         ++nseg;
       }
   } else {
-    // stride 2: input pixel (2i + ky - pad, 2j + kx - pad) lives in phase plane (py, px) at (i + oy, j + ox)
+    // stride 2: input pixel (2i + ky + off_y, 2j + kx + off_x) lives in phase plane (py, px) at (i + dy, j + dx)
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         const __half* base = static_cast<const __half*>(x) + ((int64_t)py * W + px) * C;
@@ -2062,7 +2063,7 @@ static int conv_impl(gn_handle* h, const void* x, int B, int H, int W, int C, co
     nmaps = 4;
     for (int ky = 0; ky < KH; ++ky)
       for (int kx = 0; kx < KW; ++kx) {
-        const int oy = ky - pad, ox = kx - pad;
+        const int oy = ky + off_y, ox = kx + off_x;
         const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
         p.segs[nseg].map = (int8_t)(py * 2 + px);
         p.segs[nseg].dy = (int8_t)((oy - py) / 2);
@@ -2127,6 +2128,23 @@ extern "C" int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C
                          int KW, int stride, int pad, const void* ex0, int C_ex0, const void* ex1, int C_ex1,
                          void* out, int64_t ldo, const gn_epilogue* epi, void* stream) {
   return conv_impl(h, x, B, H, W, C, w, Cout, KH, KW, stride, pad, ex0, C_ex0, ex1, C_ex1, out, ldo, epi, stream, nullptr);
+}
+
+extern "C" int gn_conv2d_asym(gn_handle* h, const void* x, int B, int H, int W, int C, const void* w, int Cout, int KH,
+                              int KW, int stride, int pad_top, int pad_left, int pad_bottom, int pad_right, void* out,
+                              int64_t ldo, const gn_epilogue* epi, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  GN_CHECK_ARG(h, pad_top >= 0 && pad_left >= 0 && pad_bottom >= 0 && pad_right >= 0, "gn_conv2d_asym: negative padding");
+  GN_CHECK_ARG(h, stride == 1 || stride == 2, "gn_conv2d_asym: stride %d unsupported", stride);
+  GN_CHECK_ARG(h, KH > 0 && KW > 0 && H + pad_top + pad_bottom >= KH && W + pad_left + pad_right >= KW,
+               "gn_conv2d_asym: kernel larger than the padded image");
+  ConvOutView v;
+  v.Ho = (H + pad_top + pad_bottom - KH) / stride + 1;
+  v.Wo = (W + pad_left + pad_right - KW) / stride + 1;
+  v.off_y = -pad_top;
+  v.off_x = -pad_left;
+  v.sx = v.sy = v.sb = 0;
+  return conv_impl(h, x, B, H, W, C, w, Cout, KH, KW, stride, 0, nullptr, 0, nullptr, 0, out, ldo, epi, stream, &v);
 }
 
 extern "C" int gn_conv2d_up2x(gn_handle* h, const void* x, int B, int H, int W, int C, const void* w4, int Cout,

@@ -324,6 +324,39 @@ class Ops:
             out.gn_stats = st
         return out
 
+    def conv2d_asym(self, x: torch.Tensor, w: torch.Tensor, cout: int, ksize: int = 3, stride: int = 2,
+                    pads: Sequence[int] = (0, 0, 1, 1), out: Optional[torch.Tensor] = None, **epi) -> torch.Tensor:
+        """Convolution with (top, left, bottom, right) zero padding (gn_conv2d_asym); the default is the VAE encoder's
+        Downsample2D: F.pad(x, (0, 1, 0, 1)) + 3x3 stride-2 convolution."""
+        _f16(x, "x")
+        _f16(w, "w")
+        if x.dim() != 4 or not x.is_contiguous():
+            raise ValueError("x must be a contiguous [B, H, W, C] tensor")
+        B, H, W, Cin = x.shape
+        pt, pl, pb, pr = (int(v) for v in pads)
+        Ho = (H + pt + pb - ksize) // stride + 1
+        Wo = (W + pl + pr - ksize) // stride + 1
+        cp = (Cin + 63) // 64 * 64
+        if tuple(w.shape) != (cout, ksize * ksize * cp) or not w.is_contiguous():
+            raise ValueError(f"packed conv weight must be [{cout}, {ksize * ksize * cp}], got {tuple(w.shape)}")
+        if out is None:
+            out = torch.empty(B, Ho, Wo, cout, dtype=torch.float16, device=x.device)
+        if tuple(out.shape) != (B, Ho, Wo, cout) or not out.is_contiguous() or out.dtype != torch.float16:
+            raise ValueError("bad `out` tensor for conv2d_asym")
+        epi.setdefault("rows_per_batch", Ho * Wo)
+        bw = min(128, 1 << max(0, (Wo - 1).bit_length()))
+        bh = min(128 // bw, 1 << max(0, (Ho - 1).bit_length()))
+        st = self._gn_request(epi, B * 128, cout, 128, torch.float16) if bw * bh >= 16 and epi.get("gn_stats") else None
+        if st is None:
+            epi.pop("gn_stats", None)
+        e = self._epilogue(B * Ho * Wo, cout, **epi)
+        rc = self.lib.gn_conv2d_asym(self.h, x.data_ptr(), B, H, W, Cin, w.data_ptr(), cout, ksize, ksize, stride,
+                                     pt, pl, pb, pr, out.data_ptr(), cout, C.byref(e), self._stream())
+        self.handle.check(rc, "gn_conv2d_asym")
+        if st is not None:
+            out.gn_stats = st
+        return out
+
     def conv2d_up2x(self, x: torch.Tensor, w4: torch.Tensor, cout: int, out: Optional[torch.Tensor] = None,
                     **epi) -> torch.Tensor:
         """conv3x3(pad 1)(nearest x2 upsample(x)) as four 2x2 phase convolutions over x (gn_conv2d_up2x); `w4` from

@@ -32,7 +32,7 @@ from .ops import Ops
 from .scheduler import EulerDiscreteSchedule
 from .text_encoder import DeviceCLIPText
 from .unet import LATENT_CPAD, DeviceControlNet, DeviceUNet, tensor_key
-from .vae import DeviceTAESDDecoder, DeviceVAEDecoder
+from .vae import DeviceTAESDDecoder, DeviceVAEDecoder, DeviceVAEEncoder
 
 try:  # PIL is only needed for the "pil" input/output types the reference uses
     from PIL import Image
@@ -413,7 +413,12 @@ class B200ControlNetPipeline:
         if image is None:
             raise ValueError("`image` (the ControlNet conditioning image) is required")
         # guidance_scale <= 1 -> no CFG: negative prompts are never encoded; eta is unused by Euler.
+        return self._generate(prompt, image, height, width, num_inference_steps, generator, latents, prompt_embeds,
+                              output_type, return_dict, float(controlnet_conditioning_scale))
 
+    def _generate(self, prompt, image, height, width, num_inference_steps, generator, latents, prompt_embeds,
+                  output_type, return_dict, cond_scale: float):
+        """Shared body of the public calls: image / prompt / latents preparation -> device chain -> output conversion."""
         ops = self.ops
         cond_u8 = self._control_image_u8(image)
         B, H, W, _ = cond_u8.shape
@@ -429,7 +434,7 @@ class B200ControlNetPipeline:
         tk = ctx.shape[1]
 
         h, w = H // f, W // f
-        lc = self.unet_cfg.in_channels
+        lc = self.vae_cfg.latent_channels
         if latents is None:
             gens = generator if isinstance(generator, (list, tuple)) else [generator] * B
             if len(gens) != B:
@@ -448,8 +453,7 @@ class B200ControlNetPipeline:
         lat_in = ops.nchw_to_nhwc(latents.contiguous(), cpad=LATENT_CPAD)
 
         self.schedule.set_timesteps(int(num_inference_steps))
-        x, img = self._run(cond_u8, lat_in, kv, tk, int(num_inference_steps), output_type != "latent",
-                           float(controlnet_conditioning_scale))
+        x, img = self._run(cond_u8, lat_in, kv, tk, int(num_inference_steps), output_type != "latent", cond_scale)
 
         if output_type == "latent":
             images = ops.nhwc_to_nchw(x, channels=lc)
@@ -468,3 +472,116 @@ class B200ControlNetPipeline:
         if not return_dict:
             return (images, None)
         return PipelineOutput(images=images, nsfw_content_detected=None)
+
+
+class B200Pix2PixPipeline(B200ControlNetPipeline):
+    """Drop-in for diffusers' StableDiffusionInstructPix2PixPipeline as controller/agent/sd_pix2pix_agent.py:52-60 calls
+    it (same six keyword arguments as the ControlNet agent).  No ControlNet: the input image is VAE-encoded once per
+    call (posterior mode, not scaled) and its 4 latent channels ride in channels 4..7 of the U-Net's 8-channel conv_in
+    input at every step (`torch.cat([scaled_latents, image_latents], dim=1)` upstream).  With the reference's
+    guidance_scale 0.0 `do_classifier_free_guidance` is False upstream, so there is one U-Net evaluation per step;
+    guidance (guidance_scale > 1 and image_guidance_scale >= 1: the three-way batch) raises NotImplementedError."""
+
+    def __init__(self, ops: Ops, unet_sd, vae_sd, text_sd=None, unet_cfg: UNetConfig = UNetConfig(in_channels=8),
+                 vae_cfg: VAEConfig = VAEConfig(), text_cfg: CLIPTextConfig = CLIPTextConfig.sd_turbo(),
+                 scheduler_cfg: SchedulerConfig = SchedulerConfig(),
+                 tokenizer: Optional[Callable[[Sequence[str]], torch.Tensor]] = None, use_cuda_graph: bool = False):
+        if isinstance(vae_cfg, TAESDConfig):
+            raise NotImplementedError("the InstructPix2Pix pipeline needs the AutoencoderKL encoder; TAESD is decode-only here")
+        if unet_cfg.in_channels != 2 * vae_cfg.latent_channels or 2 * vae_cfg.latent_channels != LATENT_CPAD:
+            raise ValueError(f"InstructPix2Pix U-Net must take {2 * vae_cfg.latent_channels} input channels "
+                             f"(latents + image latents), config says {unet_cfg.in_channels}")
+        self.ops = ops
+        self.unet_cfg, self.vae_cfg, self.text_cfg = unet_cfg, vae_cfg, text_cfg
+        self.concurrent_controlnet = False
+        self.ops_side = self.ops_zero = ops
+        self.side_stream = self.zero_stream = None
+        self.overlap_zero_convs = False
+        self.unet_impl = DeviceUNet(ops, unet_sd, unet_cfg)
+        self.controlnet_impl = None
+        self.vae_impl = DeviceVAEDecoder(ops, vae_sd, vae_cfg)
+        self.vae_enc_impl = DeviceVAEEncoder(ops, vae_sd, vae_cfg)
+        self.text_impl = DeviceCLIPText(ops, text_sd, text_cfg) if text_sd is not None else None
+        self.schedule = EulerDiscreteSchedule(scheduler_cfg)
+        self.tokenizer = tokenizer
+        self.use_cuda_graph = use_cuda_graph
+        self.vae_scale_factor = 2 ** (len(vae_cfg.block_out_channels) - 1)
+        self.vae = _ModuleShim(self.vae_impl)
+        self.unet = _ModuleShim(self.unet_impl)
+        self.text_encoder = _ModuleShim(self.text_impl)
+        self.scheduler = self.schedule
+        self._ctx_cache, self._kv_cache, self._temb_cache, self._graphs, self._pinned = {}, {}, {}, {}, {}
+        self._tuned_shapes = set()
+        self.progress_bar_disabled = True
+
+    def _context_kv(self, ctx: torch.Tensor) -> Dict[str, torch.Tensor]:
+        key = tensor_key(ctx)
+        if key not in self._kv_cache:
+            if len(self._kv_cache) > 8:
+                self._kv_cache.clear()
+            self._kv_cache[key] = {"u:" + tr.prefix: tr.project_context(self.ops, ctx)
+                                   for tr in self.unet_impl.transformers()}
+            self._kv_owner = ctx
+        return self._kv_cache[key]
+
+    def _time_rows(self, n_steps: int, batch: int):
+        key = (n_steps, batch)
+        if key not in self._temb_cache:
+            ts, _ = self.schedule.set_timesteps(n_steps)
+            self._temb_cache[key] = [self.unet_impl.temb_rows(self.unet_impl.resblocks(),
+                                                              self.unet_impl.time_embedding(float(t)), batch) for t in ts]
+        return self._temb_cache[key]
+
+    def _denoise_and_decode(self, cond_u8: torch.Tensor, lat_in: torch.Tensor, kv, tk: int, n_steps: int,
+                            want_image: bool, cond_scale: float):
+        """cond_u8 [B, H, W, 3] (the image to edit); lat_in [B, h, w, 8] fp16 (unit-variance noise in channels 0..3)."""
+        ops = self.ops
+        temb = self._time_rows(n_steps, lat_in.shape[0])
+        ops.gn_stats_reset()
+        sig = self.schedule.sigmas
+        kv_u = {k[2:]: v for k, v in kv.items() if k.startswith("u:")}
+        lc = self.vae_cfg.latent_channels
+        img_lat = self.vae_enc_impl.encode(cond_u8)                                  # [B, h, w, 8], mean in 0..3
+        x = ops.scale(lat_in, self.schedule.init_noise_sigma)
+        xs = ops.scale(x, 1.0 / float(np.sqrt(float(sig[0]) ** 2 + 1.0)))
+        eps = torch.zeros_like(x)
+        for i in range(n_steps):
+            xs[..., lc:] = img_lat[..., :lc]                                         # cat([scaled latents, image latents])
+            mid, skips = self.unet_impl.encode(xs, temb[i], kv_u, tk)
+            self.unet_impl.decode(mid, skips, temb[i], kv_u, tk, eps)
+            x_next, xs_next = torch.empty_like(x), torch.empty_like(x)
+            ops.euler_step(x, eps, float(sig[i]), float(sig[i + 1]), x_next=x_next, x_scaled=xs_next)
+            x, xs = x_next, xs_next
+        img = None
+        if want_image:
+            img = self.vae_impl.decode(ops.scale(x, 1.0 / self.vae_cfg.scaling_factor))
+        return x, img
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, image=None, num_inference_steps: int = 100, guidance_scale: float = 7.5,
+                 image_guidance_scale: float = 1.5, negative_prompt=None, num_images_per_prompt: Optional[int] = 1,
+                 eta: float = 0.0, generator=None, latents: Optional[torch.Tensor] = None,
+                 prompt_embeds: Optional[torch.Tensor] = None, negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 ip_adapter_image=None, ip_adapter_image_embeds=None, output_type: Optional[str] = "pil",
+                 return_dict: bool = True, callback_on_step_end=None,
+                 callback_on_step_end_tensor_inputs: List[str] = ["latents"], cross_attention_kwargs=None, **kwargs):
+        # upstream: do_classifier_free_guidance = guidance_scale > 1.0 and image_guidance_scale >= 1.0
+        if guidance_scale is not None and guidance_scale > 1.0 and image_guidance_scale >= 1.0:
+            raise NotImplementedError("text / image classifier-free guidance (three-way batch) is not implemented; "
+                                      "Genima runs guidance_scale 0.0")
+        if num_images_per_prompt not in (None, 1):
+            raise NotImplementedError("num_images_per_prompt != 1 is not implemented")
+        if ip_adapter_image is not None or ip_adapter_image_embeds is not None:
+            raise NotImplementedError("ip-adapter inputs are not implemented")
+        if cross_attention_kwargs:
+            raise NotImplementedError("cross_attention_kwargs are not implemented")
+        if callback_on_step_end is not None:
+            raise NotImplementedError("per-step callbacks would force a host sync inside the loop; not implemented")
+        if kwargs:
+            raise TypeError(f"unexpected arguments: {sorted(kwargs)}")
+        if output_type not in ("pil", "np", "pt", "latent", "u8"):
+            raise ValueError(f"output_type {output_type!r} is not supported")
+        if image is None:
+            raise ValueError("`image` cannot be undefined.")
+        return self._generate(prompt, image, None, None, num_inference_steps, generator, latents, prompt_embeds,
+                              output_type, return_dict, 1.0)

@@ -1,4 +1,5 @@
-"""Device-side KL-VAE decoder (diffusers AutoencoderKL.decode: post_quant_conv + Decoder) on the C-ABI kernels.
+"""Device-side KL-VAE decoder (diffusers AutoencoderKL.decode: post_quant_conv + Decoder), the encoder
+(AutoencoderKL.encode, for the InstructPix2Pix sibling) and the TAESD decoder on the C-ABI kernels.
 
 Replaces `pipe.vae.decode(latents / scaling_factor)` at the end of diffusers' StableDiffusionControlNetPipeline.__call__
 (reached from controller/agent/sd_controlnet_agent.py:67-76).  Same NHWC / fused-epilogue execution as unet.py; the
@@ -20,42 +21,20 @@ from .weights import taesd_layer_plan
 RGB_CPAD = 8  # decoded image travels as [B, H, W, 8] fp16 (3 real channels)
 
 
-class DeviceVAEDecoder:
-    def __init__(self, ops: Ops, sd: Dict[str, torch.Tensor], cfg: VAEConfig):
-        self.ops, self.cfg = ops, cfg
-        P = self.P = _Params(sd, ops.device)
-        g, eps = cfg.norm_num_groups, cfg.norm_eps
-        ch = cfg.block_out_channels
-        top = ch[-1]
-        lc = cfg.latent_channels
-        P.gn_bucket = gn_bucket_for(ch, g)
-        # post_quant_conv (1x1, 4 -> 4) as a linear over 8-channel padded pixels
-        wq = torch.zeros(lc, LATENT_CPAD, dtype=torch.float16)
-        wq[:, :lc] = P.host16("post_quant_conv.weight").reshape(lc, lc)
-        self.pq_w, self.pq_b = wq.to(ops.device), P.f32("post_quant_conv.bias")
-        self.conv_in = _Conv(P, "decoder.conv_in", cin_layout=(lc, LATENT_CPAD), gn=True)
-        self.mid0 = _ResBlock(P, "decoder.mid_block.resnets.0", (top,), g, eps)
-        self.mid1 = _ResBlock(P, "decoder.mid_block.resnets.1", (top,), g, eps)
-        a = "decoder.mid_block.attentions.0"
+class _MidAttention:
+    """The VAE mid-block attention (1 head over all channels, projections with bias, residual) as tcgen05 GEMMs around a
+    row softmax; shared by the decoder and the encoder."""
+
+    def __init__(self, P: _Params, prefix: str, cfg: VAEConfig):
+        self.P, self.cfg = P, cfg
+        a = prefix
         self.at_g, self.at_b = P.f32(f"{a}.group_norm.weight"), P.f32(f"{a}.group_norm.bias")
         self.wq, self.bq = P.f16(f"{a}.to_q.weight"), P.f32(f"{a}.to_q.bias")
         self.wk, self.bk = P.f16(f"{a}.to_k.weight"), P.f32(f"{a}.to_k.bias")
         self.wv, self.bv = P.f16(f"{a}.to_v.weight"), P.f32(f"{a}.to_v.bias")
         self.wo, self.bo = P.f16(f"{a}.to_out.0.weight"), P.f32(f"{a}.to_out.0.bias")
-        self.up: List = []
-        prev = top
-        for i, cout in enumerate(reversed(ch)):
-            res = []
-            for j in range(cfg.layers_per_block + 1):
-                res.append(_ResBlock(P, f"decoder.up_blocks.{i}.resnets.{j}", (prev,), g, eps))
-                prev = cout
-            us = _Conv(P, f"decoder.up_blocks.{i}.upsamplers.0.conv", gn=True, upsample=True) if i < len(ch) - 1 else None
-            self.up.append((res, us))
-        self.out_g, self.out_b = P.f32("decoder.conv_norm_out.weight"), P.f32("decoder.conv_norm_out.bias")
-        self.conv_out = _Conv(P, "decoder.conv_out")
 
-    def _mid_attention(self, h: torch.Tensor) -> torch.Tensor:
-        ops = self.ops
+    def __call__(self, ops: Ops, h: torch.Tensor) -> torch.Tensor:
         B, H, W, C = h.shape
         T = H * W
         n = ops.group_norm(h, self.at_g, self.at_b, self.cfg.norm_num_groups, self.cfg.norm_eps, silu=False)
@@ -76,6 +55,39 @@ class DeviceVAEDecoder:
         out = outs[0] if B == 1 else torch.cat(outs, dim=0)
         return ops.carry_stats(out.reshape(B, H, W, C), out)
 
+
+class DeviceVAEDecoder:
+    def __init__(self, ops: Ops, sd: Dict[str, torch.Tensor], cfg: VAEConfig):
+        self.ops, self.cfg = ops, cfg
+        P = self.P = _Params(sd, ops.device)
+        g, eps = cfg.norm_num_groups, cfg.norm_eps
+        ch = cfg.block_out_channels
+        top = ch[-1]
+        lc = cfg.latent_channels
+        P.gn_bucket = gn_bucket_for(ch, g)
+        # post_quant_conv (1x1, 4 -> 4) as a linear over 8-channel padded pixels
+        wq = torch.zeros(lc, LATENT_CPAD, dtype=torch.float16)
+        wq[:, :lc] = P.host16("post_quant_conv.weight").reshape(lc, lc)
+        self.pq_w, self.pq_b = wq.to(ops.device), P.f32("post_quant_conv.bias")
+        self.conv_in = _Conv(P, "decoder.conv_in", cin_layout=(lc, LATENT_CPAD), gn=True)
+        self.mid0 = _ResBlock(P, "decoder.mid_block.resnets.0", (top,), g, eps)
+        self.mid1 = _ResBlock(P, "decoder.mid_block.resnets.1", (top,), g, eps)
+        self.mid_attn = _MidAttention(P, "decoder.mid_block.attentions.0", cfg)
+        self.up: List = []
+        prev = top
+        for i, cout in enumerate(reversed(ch)):
+            res = []
+            for j in range(cfg.layers_per_block + 1):
+                res.append(_ResBlock(P, f"decoder.up_blocks.{i}.resnets.{j}", (prev,), g, eps))
+                prev = cout
+            us = _Conv(P, f"decoder.up_blocks.{i}.upsamplers.0.conv", gn=True, upsample=True) if i < len(ch) - 1 else None
+            self.up.append((res, us))
+        self.out_g, self.out_b = P.f32("decoder.conv_norm_out.weight"), P.f32("decoder.conv_norm_out.bias")
+        self.conv_out = _Conv(P, "decoder.conv_out")
+
+    def _mid_attention(self, h: torch.Tensor) -> torch.Tensor:
+        return self.mid_attn(self.ops, h)
+
     def decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """z: [B, h, w, 8] fp16 latents already divided by scaling_factor -> [B, 8h, 8w, 8] fp16 (RGB in 0..2)."""
         ops = self.ops
@@ -95,6 +107,64 @@ class DeviceVAEDecoder:
         if out is None:
             out = torch.zeros(B, hh * 8, ww * 8, RGB_CPAD, dtype=torch.float16, device=z.device)
         return self.conv_out(ops, n, out=out)
+
+
+class DeviceVAEEncoder:
+    """diffusers AutoencoderKL.encode(x).latent_dist.mode() (Encoder + quant_conv, mean half of the moments) on the same
+    kernels: what StableDiffusionInstructPix2PixPipeline.prepare_image_latents computes once per call
+    (controller/agent/sd_pix2pix_agent.py:52-60).  Downsample2D's F.pad(0, 1, 0, 1) + stride-2 convolution is one
+    gn_conv2d_asym launch (the padding is TMA zero fill); only the 4 mean rows of conv_out∘quant_conv are evaluated."""
+
+    def __init__(self, ops: Ops, sd: Dict[str, torch.Tensor], cfg: VAEConfig):
+        self.ops, self.cfg = ops, cfg
+        P = self.P = _Params(sd, ops.device)
+        g, eps = cfg.norm_num_groups, cfg.norm_eps
+        ch = cfg.block_out_channels
+        top = ch[-1]
+        lc = cfg.latent_channels
+        P.gn_bucket = gn_bucket_for(ch, g)
+        self.conv_in = _Conv(P, "encoder.conv_in", cin_layout=(cfg.out_channels, RGB_CPAD), gn=True)
+        self.down: List = []
+        prev = ch[0]
+        for i, cout in enumerate(ch):
+            res = []
+            for j in range(cfg.layers_per_block):
+                res.append(_ResBlock(P, f"encoder.down_blocks.{i}.resnets.{j}", (prev,), g, eps))
+                prev = cout
+            ds = _Conv(P, f"encoder.down_blocks.{i}.downsamplers.0.conv", stride=2, gn=True) if i < len(ch) - 1 else None
+            self.down.append((res, ds))
+        self.mid0 = _ResBlock(P, "encoder.mid_block.resnets.0", (top,), g, eps)
+        self.mid_attn = _MidAttention(P, "encoder.mid_block.attentions.0", cfg)
+        self.mid1 = _ResBlock(P, "encoder.mid_block.resnets.1", (top,), g, eps)
+        self.out_g, self.out_b = P.f32("encoder.conv_norm_out.weight"), P.f32("encoder.conv_norm_out.bias")
+        self.conv_out = _Conv(P, "encoder.conv_out")
+        # quant_conv (1x1, 8 -> 8): only the mean rows, written into an 8-channel padded latent pixel
+        wq = torch.zeros(lc, 2 * lc, dtype=torch.float16)
+        wq[:, :] = P.host16("quant_conv.weight").reshape(2 * lc, 2 * lc)[:lc]
+        self.q_w, self.q_b = wq.to(ops.device), P.f32("quant_conv.bias")[:lc].contiguous()
+
+    def encode(self, image_u8: torch.Tensor) -> torch.Tensor:
+        """image_u8: [B, H, W, 3] uint8 on the device -> [B, H/8, W/8, 8] fp16, channels 0..3 = posterior mean (not
+        multiplied by scaling_factor), channels 4..7 zero.  The [-1, 1] normalisation of VaeImageProcessor.preprocess
+        happens inside the layout kernel."""
+        ops = self.ops
+        x = ops.u8_to_nhwc(image_u8, cpad=RGB_CPAD, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))
+        h = self.conv_in(ops, x)
+        for res, ds in self.down:
+            for rb in res:
+                h = rb(ops, h, None, None)
+            if ds is not None:
+                h = ops.conv2d_asym(h, ds.w, ds.cout, ksize=3, stride=2, pads=(0, 0, 1, 1), bias=ds.b,
+                                    gn_stats=ds.bucket)
+        h = self.mid0(ops, h, None, None)
+        h = self.mid_attn(ops, h)
+        h = self.mid1(ops, h, None, None)
+        n = ops.group_norm(h, self.out_g, self.out_b, self.cfg.norm_num_groups, self.cfg.norm_eps, silu=True)
+        m = self.conv_out(ops, n)                                              # [B, h, w, 8] moments before quant_conv
+        B, hh, ww, c2 = m.shape
+        z = torch.zeros(B, hh, ww, LATENT_CPAD, dtype=torch.float16, device=m.device)
+        ops.linear(m.reshape(-1, c2), self.q_w, bias=self.q_b, out=z.reshape(-1, LATENT_CPAD))
+        return z
 
 
 class DeviceTAESDDecoder:

@@ -164,6 +164,32 @@ def vae_decoder_shapes(cfg: VAEConfig) -> Shapes:
     return s
 
 
+def vae_encoder_shapes(cfg: VAEConfig) -> Shapes:
+    """diffusers AutoencoderKL: encoder.* + quant_conv keys (used by StableDiffusionInstructPix2PixPipeline's
+    prepare_image_latents; controller/agent/sd_pix2pix_agent.py:36-41 loads the full VAE from sd_ckpt)."""
+    s: Shapes = OrderedDict()
+    ch = cfg.block_out_channels
+    top = ch[-1]
+    _conv(s, "encoder.conv_in", ch[0], cfg.out_channels, 3)
+    prev = ch[0]
+    for i, cout in enumerate(ch):
+        for j in range(cfg.layers_per_block):
+            _resnet(s, f"encoder.down_blocks.{i}.resnets.{j}", prev, cout, 0)
+            prev = cout
+        if i < len(ch) - 1:
+            _conv(s, f"encoder.down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
+    _resnet(s, "encoder.mid_block.resnets.0", top, top, 0)
+    a = "encoder.mid_block.attentions.0"
+    _norm(s, f"{a}.group_norm", top)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        _lin(s, f"{a}.{n}", top, top)
+    _resnet(s, "encoder.mid_block.resnets.1", top, top, 0)
+    _norm(s, "encoder.conv_norm_out", top)
+    _conv(s, "encoder.conv_out", 2 * cfg.latent_channels, top, 3)
+    _conv(s, "quant_conv", 2 * cfg.latent_channels, 2 * cfg.latent_channels, 1)
+    return s
+
+
 def taesd_layer_plan(cfg):
     """DecoderTiny's nn.Sequential as [(kind, index)]: kind in conv_in / relu / block / up / conv / conv_out; index = the
     position in `decoder.layers` (the state-dict key prefix)."""

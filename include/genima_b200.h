@@ -171,6 +171,15 @@ int gn_conv2d(gn_handle* h, const void* x, int B, int H, int W, int C, const voi
               int stride, int pad, const void* ex0, int C_ex0, const void* ex1, int C_ex1, void* out, int64_t ldo,
               const gn_epilogue* epi, void* stream);
 
+/* gn_conv2d with separate top / left / bottom / right zero padding and no extra sources.  diffusers' VAE-encoder
+ * Downsample2D is F.pad(x, (0, 1, 0, 1)) followed by a 3x3 stride-2 convolution with padding 0 (reached through
+ * StableDiffusionInstructPix2PixPipeline.prepare_image_latents, controller/agent/sd_pix2pix_agent.py:52-60): here the
+ * padding is TMA out-of-bounds zero fill, no padded copy of x exists.
+ * out: [B, (H + pt + pb - KH) / stride + 1, (W + pl + pr - KW) / stride + 1, Cout]. */
+int gn_conv2d_asym(gn_handle* h, const void* x, int B, int H, int W, int C, const void* w, int Cout, int KH, int KW,
+                   int stride, int pad_top, int pad_left, int pad_bottom, int pad_right, void* out, int64_t ldo,
+                   const gn_epilogue* epi, void* stream);
+
 /* out[B, 2H, 2W, Cout] = conv3x3(pad 1)(nearest-neighbour x2 upsample of x[B, H, W, C]) WITHOUT materialising the
  * upsampled tensor (diffusers Upsample2D = F.interpolate(scale 2, "nearest") + conv): every output parity (py, px) is a
  * 2x2 convolution over x whose taps are sums of the 3x3 taps that fall on the same input pixel, so the op is four

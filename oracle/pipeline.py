@@ -5,6 +5,8 @@
                          controller/cfgs/eval_genima.yaml:31), control image in [0, 1] without normalisation, explicit
                          `latents` multiplied by init_noise_sigma, Euler-trailing loop with ControlNet residuals added to
                          the U-Net skips, VAE decode of latents / scaling_factor, postprocess to uint8.
+  pix2pix_pipeline()     the InstructPix2Pix sibling (controller/agent/sd_pix2pix_agent.py): VAE-encoded image latents
+                         concatenated to the U-Net input, no ControlNet.
   agent_step()           controller/eval_genima.py:163-249 between `obs` and `actions`: tile_images -> pipeline ->
                          untile_images -> GenimaACT.act (policy forward on the four generated views).
 PARITY UNPINNED (no upstream package, weights or golden vectors offline); pinned sub-pieces are listed in oracle/__init__.
@@ -50,6 +52,30 @@ def controlnet_pipeline(unet_sd, cn_sd, vae_sd, ucfg: UNetConfig, vcfg: VAEConfi
     if return_intermediates:
         out["steps"] = inter
     return out
+
+
+def pix2pix_pipeline(unet_sd, vae_sd, ucfg: UNetConfig, vcfg: VAEConfig, image_u8: np.ndarray, ctx: torch.Tensor,
+                     latents: torch.Tensor, n_steps: int):
+    """diffusers 0.29.0 StableDiffusionInstructPix2PixPipeline.__call__ as controller/agent/sd_pix2pix_agent.py:52-60
+    exercises it: guidance_scale 0.0 (controller/cfgs/eval_genima.yaml:31) -> do_classifier_free_guidance is False, so
+    one U-Net evaluation per step on cat([scale_model_input(latents), image_latents], dim=1) with the 8-channel conv_in;
+    image_latents = vae.encode(preprocess(image)).latent_dist.mode() (image normalised to [-1, 1], latents NOT scaled).
+    [upstream, from memory.  Older diffusers releases converted eps to x0 and back around the guidance step for
+    sigma-space schedulers; without guidance that round trip is the identity, so either variant computes this.]
+    image_u8 [B, H, W, 3]; ctx [B, 77, D]; latents [B, 4, H/8, W/8] unit-variance noise."""
+    sched = EulerDiscreteOracle()
+    ts, sig = sched.set_timesteps(n_steps)
+    img = torch.from_numpy(image_u8.astype(np.float32) / 255.0).permute(0, 3, 1, 2) * 2.0 - 1.0
+    image_latents = sd_models.vae_encode_mean(vae_sd, vcfg, img)
+    x = latents.to(torch.float32) * sched.init_noise_sigma
+    for i, t in enumerate(ts):
+        xs = torch.cat([sched.scale_model_input(x, i), image_latents], dim=1)
+        eps = sd_models.unet_forward(unet_sd, ucfg, xs, torch.tensor([float(t)]), ctx)
+        x = sched.step(eps, i, x)
+    out = sd_models.vae_decode(vae_sd, vcfg, x / vcfg.scaling_factor)
+    den = (out / 2 + 0.5).clamp(0, 1)
+    u8 = (den.permute(0, 2, 3, 1).numpy() * 255).round().astype(np.uint8)
+    return dict(latents=x, image=out, u8=u8, image_latents=image_latents)
 
 
 def agent_step(weights: Dict[str, dict], ucfg: UNetConfig, vcfg: VAEConfig, acfg: ACTConfig, views_u8: np.ndarray,

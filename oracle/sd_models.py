@@ -11,8 +11,9 @@ Upstream modules restated (file paths inside diffusers 0.29.0):
   models/transformers/transformer_2d.py   Transformer2DModel (use_linear_projection=True)
   models/unets/unet_2d_condition.py       UNet2DConditionModel.forward
   models/controlnet.py            ControlNetModel.forward, ControlNetConditioningEmbedding
-  models/autoencoders/vae.py      Decoder; autoencoder_kl.py AutoencoderKL.decode
-Reference call sites: controller/agent/sd_controlnet_agent.py:31-42 (model construction), :67-76 (pipe call).
+  models/autoencoders/vae.py      Decoder, Encoder; autoencoder_kl.py AutoencoderKL.decode / .encode
+Reference call sites: controller/agent/sd_controlnet_agent.py:31-42 (model construction), :67-76 (pipe call);
+controller/agent/sd_pix2pix_agent.py:29-41, :52-60 (InstructPix2Pix sibling).
 """
 from __future__ import annotations
 
@@ -175,14 +176,8 @@ def unet_forward(sd: SD, cfg: UNetConfig, x: torch.Tensor, t: torch.Tensor, ctx:
     return F.conv2d(h, _w(sd, "conv_out.weight"), _w(sd, "conv_out.bias"), padding=1)
 
 
-def vae_decode(sd: SD, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
-    """AutoencoderKL.decode(z): post_quant_conv -> Decoder.  The caller divides latents by scaling_factor first."""
-    g, eps = cfg.norm_num_groups, cfg.norm_eps
-    h = F.conv2d(z, _w(sd, "post_quant_conv.weight"), _w(sd, "post_quant_conv.bias"))
-    h = F.conv2d(h, _w(sd, "decoder.conv_in.weight"), _w(sd, "decoder.conv_in.bias"), padding=1)
-    h = resnet_block(sd, "decoder.mid_block.resnets.0", h, None, g, eps)
-    # mid attention: one head over all channels, linear projections WITH bias, residual connection
-    a = "decoder.mid_block.attentions.0"
+def _vae_mid_attention(sd: SD, a: str, h: torch.Tensor, g: int, eps: float) -> torch.Tensor:
+    """UNetMidBlock2D's Attention in the VAE: one head over all channels, linear projections WITH bias, residual."""
     b, c, hh, ww = h.shape
     n = F.group_norm(h, g, _w(sd, f"{a}.group_norm.weight"), _w(sd, f"{a}.group_norm.bias"), eps)
     n = n.reshape(b, c, hh * ww).transpose(1, 2)
@@ -191,7 +186,41 @@ def vae_decode(sd: SD, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
     v = F.linear(n, _w(sd, f"{a}.to_v.weight"), _w(sd, f"{a}.to_v.bias"))
     o = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(c), dim=-1) @ v
     o = F.linear(o, _w(sd, f"{a}.to_out.0.weight"), _w(sd, f"{a}.to_out.0.bias"))
-    h = h + o.transpose(1, 2).reshape(b, c, hh, ww)
+    return h + o.transpose(1, 2).reshape(b, c, hh, ww)
+
+
+def vae_encode_mean(sd: SD, cfg: VAEConfig, image: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKL.encode(image).latent_dist.mode(): Encoder -> quant_conv -> first half of the moments (the mean of
+    the diagonal Gaussian; its mode).  image: [B, 3, H, W] in [-1, 1] -> [B, latent_channels, H/8, W/8], NOT multiplied
+    by scaling_factor (StableDiffusionInstructPix2PixPipeline.prepare_image_latents uses the raw mode; reached from
+    controller/agent/sd_pix2pix_agent.py:52-60).  [upstream, from memory: diffusers 0.29.0 models/autoencoders/vae.py
+    Encoder, DownEncoderBlock2D; Downsample2D(padding=0) pads (0, 1, 0, 1) before its stride-2 convolution]"""
+    g, eps = cfg.norm_num_groups, cfg.norm_eps
+    ch = cfg.block_out_channels
+    h = F.conv2d(image, _w(sd, "encoder.conv_in.weight"), _w(sd, "encoder.conv_in.bias"), padding=1)
+    for i in range(len(ch)):
+        for j in range(cfg.layers_per_block):
+            h = resnet_block(sd, f"encoder.down_blocks.{i}.resnets.{j}", h, None, g, eps)
+        if i < len(ch) - 1:
+            p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0.0)
+            h = F.conv2d(h, _w(sd, f"{p}.weight"), _w(sd, f"{p}.bias"), stride=2)
+    h = resnet_block(sd, "encoder.mid_block.resnets.0", h, None, g, eps)
+    h = _vae_mid_attention(sd, "encoder.mid_block.attentions.0", h, g, eps)
+    h = resnet_block(sd, "encoder.mid_block.resnets.1", h, None, g, eps)
+    h = F.group_norm(h, g, _w(sd, "encoder.conv_norm_out.weight"), _w(sd, "encoder.conv_norm_out.bias"), eps)
+    h = F.conv2d(F.silu(h), _w(sd, "encoder.conv_out.weight"), _w(sd, "encoder.conv_out.bias"), padding=1)
+    moments = F.conv2d(h, _w(sd, "quant_conv.weight"), _w(sd, "quant_conv.bias"))
+    return moments[:, :cfg.latent_channels]
+
+
+def vae_decode(sd: SD, cfg: VAEConfig, z: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKL.decode(z): post_quant_conv -> Decoder.  The caller divides latents by scaling_factor first."""
+    g, eps = cfg.norm_num_groups, cfg.norm_eps
+    h = F.conv2d(z, _w(sd, "post_quant_conv.weight"), _w(sd, "post_quant_conv.bias"))
+    h = F.conv2d(h, _w(sd, "decoder.conv_in.weight"), _w(sd, "decoder.conv_in.bias"), padding=1)
+    h = resnet_block(sd, "decoder.mid_block.resnets.0", h, None, g, eps)
+    h = _vae_mid_attention(sd, "decoder.mid_block.attentions.0", h, g, eps)
     h = resnet_block(sd, "decoder.mid_block.resnets.1", h, None, g, eps)
     n_levels = len(cfg.block_out_channels)
     for i in range(n_levels):

@@ -57,3 +57,22 @@ def test_controller_snapshot_round_trip(dirs):
     sd = ckpt.load_controller_snapshot(os.path.join(dirs["controller_ckpt"], "latest.pt"), ACTConfig.tiny())
     want = W.synth_state_dict(W.act_shapes(ACTConfig.tiny()), salt=3)
     assert set(sd) == set(want) and all(torch.equal(sd[k], want[k]) for k in want)
+
+
+def test_pix2pix_checkpoint_round_trip(dirs):
+    """controller/agent/sd_pix2pix_agent.py:19-41: U-Net from <diffusion_ckpt>/checkpoint-*/unet, the rest from sd_ckpt."""
+    import dataclasses
+
+    assert ckpt.find_pix2pix_unet_dir(dirs["pix2pix_ckpt"]).endswith(os.path.join("checkpoint-200", "unet"))
+    out = ckpt.load_sd_pix2pix(dirs["sd_ckpt"], dirs["pix2pix_ckpt"])
+    ucfg = dataclasses.replace(UNetConfig.tiny(), in_channels=8)
+    # (cond_embed_channels is a ControlNet property: a plain U-Net's config.json does not carry it)
+    assert dataclasses.replace(out["unet_cfg"], cond_embed_channels=ucfg.cond_embed_channels) == ucfg
+    assert out["controlnet"] is None
+    want = W.synth_state_dict(W.unet_shapes(ucfg), salt=5)
+    assert all(torch.equal(out["unet"][k], v) for k, v in want.items())
+    assert out["unet"]["conv_in.weight"].shape[1] == 8
+    enc = W.synth_state_dict(W.vae_encoder_shapes(VAEConfig.tiny()), salt=2)
+    assert all(torch.equal(out["vae"][k], v) for k, v in enc.items())
+    with pytest.raises(ValueError):               # a 4-channel U-Net is not an InstructPix2Pix U-Net
+        ckpt.load_sd_pix2pix(dirs["sd_ckpt"], os.path.join(dirs["sd_ckpt"]))

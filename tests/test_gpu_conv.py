@@ -55,6 +55,29 @@ def test_conv3x3_stride2(ops, B, H, W, Cin, Cout):
     _conv_case(ops, B, H, W, Cin, Cout, stride=2, seed=9)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,pads", [
+    (1, 64, 64, 128, 128, 2, (0, 0, 1, 1)),     # VAE-encoder Downsample2D: F.pad(x, (0, 1, 0, 1)) + stride-2 conv
+    (2, 32, 32, 64, 128, 2, (0, 0, 1, 1)),
+    (1, 16, 16, 512, 512, 2, (0, 0, 1, 1)),
+    (1, 32, 32, 64, 64, 1, (1, 0, 1, 2)),       # stride 1 with four different pads
+    (1, 16, 16, 64, 64, 2, (1, 1, 0, 0)),
+])
+def test_conv3x3_asymmetric_padding(ops, B, H, W, Cin, Cout, stride, pads):
+    """gn_conv2d_asym (padding = TMA zero fill at shifted coordinates) against F.pad + F.conv2d."""
+    import torch.nn.functional as F
+
+    from genima_b200.packing import pack_conv_weight
+
+    x = _rand((B, H, W, Cin), 31)
+    w = _rand((Cout, Cin, 3, 3), 32, (Cin * 9) ** -0.5)
+    bias = _rand((Cout,), 33).float()
+    pt, pl, pb, pr = pads
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (pl, pr, pt, pb)), w.float(), bias, stride=stride)
+    out = ops.conv2d_asym(x.cuda(), pack_conv_weight(w).cuda(), Cout, ksize=3, stride=stride, pads=pads,
+                          bias=bias.cuda())
+    report_close(f"asym conv B{B} {H}x{W} {Cin}->{Cout} s{stride} pads{pads}", out, ref.permute(0, 2, 3, 1))
+
+
 def test_conv7x7_stride2_stem(ops):
     _conv_case(ops, 2, 64, 64, 3, 64, k=7, stride=2, pad=3, cpad=64, seed=10)
 

@@ -244,6 +244,25 @@ def test_vae_decode_full_size(ops):
     check("full-size VAE decode", out[..., :3], nhwc(ref), NET_TOL, nhwc(stock))
 
 
+# --------------------------------------------------------------------------------------------------- VAE encoder
+@pytest.mark.parametrize("name,B,hw", [("tiny", 1, 128), ("tiny", 2, 64), ("full", 1, 256)])
+def test_vae_encode_mean(ops, name, B, hw):
+    """AutoencoderKL.encode(x).latent_dist.mode() (InstructPix2Pix image latents, sd_pix2pix_agent.py:52-60): uint8 image
+    -> [-1, 1] -> Encoder (asymmetric-pad stride-2 downsamples, mid attention) -> quant_conv -> mean."""
+    from genima_b200.vae import DeviceVAEEncoder
+    from oracle import sd_models
+
+    cfg = VAEConfig.tiny() if name == "tiny" else VAEConfig()
+    sd = W.synth_state_dict(W.vae_encoder_shapes(cfg), salt=2)
+    img = torch.randint(0, 256, (B, hw, hw, 3), generator=torch.Generator().manual_seed(13), dtype=torch.uint8)
+    x = img.float().permute(0, 3, 1, 2) / 255.0 * 2.0 - 1.0
+    ref = sd_models.vae_encode_mean(sd, cfg, x)
+    stock = sd_models.vae_encode_mean(_HalfSD(sd), cfg, x.to("cuda", torch.float16))
+    out = DeviceVAEEncoder(ops, sd, cfg).encode(img.cuda())
+    assert out.shape == (B, hw // 8, hw // 8, 8) and float(out[..., 4:].abs().max()) == 0.0
+    check(f"{name} VAE encode mean (B={B}, {hw}x{hw})", out[..., :4], nhwc(ref), NET_TOL, nhwc(stock))
+
+
 # --------------------------------------------------------------------------------------------------- TAESD decoder
 @pytest.mark.parametrize("name,B,hw", [("tiny", 2, 16), ("full", 1, 64)])
 def test_taesd_decode(ops, name, B, hw):
@@ -387,3 +406,72 @@ def test_pipeline_rejects_unimplemented(ops):
         pipe(prompt_embeds=ctx, image=cond, num_inference_steps=1, guidance_scale=0.0, num_images_per_prompt=2)
     with pytest.raises(RuntimeError):
         pipe(prompt="open the box", image=cond, num_inference_steps=1, guidance_scale=0.0)   # no tokenizer offline
+
+
+# --------------------------------------------------------------------------------------------------- InstructPix2Pix sibling
+def _tiny_pix2pix(ops, use_cuda_graph=False):
+    import dataclasses
+
+    from genima_b200.pipeline import B200Pix2PixPipeline
+
+    ucfg, vcfg = dataclasses.replace(UNetConfig.tiny(), in_channels=8), VAEConfig.tiny()
+    usd = W.synth_state_dict(W.unet_shapes(ucfg), salt=5)
+    vsd = W.synth_state_dict(W.vae_decoder_shapes(vcfg), salt=2)
+    vsd.update(W.synth_state_dict(W.vae_encoder_shapes(vcfg), salt=2))
+    return B200Pix2PixPipeline(ops, usd, vsd, None, ucfg, vcfg, use_cuda_graph=use_cuda_graph), (usd, vsd, ucfg, vcfg)
+
+
+@pytest.mark.parametrize("n_steps", [1, 5])
+def test_pix2pix_pipeline_tiny_vs_oracle(ops, n_steps):
+    """StableDiffusionInstructPix2PixPipeline as controller/agent/sd_pix2pix_agent.py:52-60 calls it (guidance 0.0)."""
+    from oracle.pipeline import pix2pix_pipeline
+
+    pipe, (usd, vsd, ucfg, vcfg) = _tiny_pix2pix(ops)
+    _, ctx, cond = _unet_inputs(ucfg, 1, seed=21)
+    lat = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(2))
+    ref = pix2pix_pipeline(usd, vsd, ucfg, vcfg, cond.numpy(), ctx, lat, n_steps)
+    kw = dict(prompt_embeds=ctx, image=cond, num_inference_steps=n_steps, guidance_scale=0.0, latents=lat)
+    check(f"pix2pix latents after {n_steps} step(s)", pipe(output_type="latent", **kw).images, ref["latents"], LOOP_TOL)
+    check("pix2pix decoded image", pipe(output_type="pt", **kw).images, (ref["image"] / 2 + 0.5).clamp(0, 1), LOOP_TOL)
+    u8 = np.stack([np.asarray(im) for im in pipe(**kw)[0]])
+    diff = np.abs(u8.astype(np.int32) - ref["u8"].astype(np.int32))
+    print(f"pix2pix uint8 image: max |diff| {diff.max()}, exact {100.0 * (diff == 0).mean():.2f}%")
+    assert diff.max() <= 3 and (diff <= 1).mean() > 0.995
+
+
+def test_pix2pix_graph_matches_eager_and_rejects_guidance(ops):
+    pipe, (_, _, ucfg, _) = _tiny_pix2pix(ops)
+    _, ctx, cond = _unet_inputs(ucfg, 1, seed=22)
+    lat = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(2))
+    kw = dict(prompt_embeds=ctx.cuda().half(), num_inference_steps=3, guidance_scale=0.0, latents=lat, output_type="u8")
+    a = pipe(image=cond, **kw).images.cpu()
+    pipe.use_cuda_graph = True
+    b = pipe(image=cond, **kw).images.cpu().clone()
+    b2 = pipe(image=torch.flip(cond, dims=[1]), **kw).images.cpu().clone()
+    assert torch.equal(a, b) and not torch.equal(b, b2)
+    with pytest.raises(NotImplementedError):      # upstream: do_classifier_free_guidance (three-way batch)
+        pipe(prompt_embeds=ctx, image=cond, num_inference_steps=1, guidance_scale=7.5, image_guidance_scale=1.5)
+    with pytest.raises(ValueError):
+        pipe(prompt_embeds=ctx, image=None, num_inference_steps=1, guidance_scale=0.0)
+
+
+def test_pix2pix_agent_plugin_surface(ops):
+    """B200Pix2PixAgent(eval_cfg).infer(...) with the reference's six keywords (sd_pix2pix_agent.py:52-60)."""
+    from PIL import Image
+
+    from genima_b200.agents import B200Pix2PixAgent
+
+    agent = B200Pix2PixAgent(dict(synthetic_weights="tiny", image_resolution=128, device="cuda:0", use_cuda_graph=True,
+                                  synthetic_text_encoder=False), ops=ops)
+    g = torch.Generator().manual_seed(0)
+    tile = torch.randint(0, 256, (128, 128, 3), generator=g, dtype=torch.uint8).numpy()
+    ctx = torch.randn(1, 77, UNetConfig.tiny().cross_attention_dim, generator=g).half().cuda()
+    outs = []
+    for _ in range(2):
+        gen = torch.Generator(device="cuda").manual_seed(2)
+        out = agent.infer(images=[Image.fromarray(tile)], prompts=None, negative_prompts=None, prompt_embeds=ctx,
+                          num_inference_steps=2, guidance_scale=0.0, generator=[gen])
+        assert out[0][0].size == (128, 128)
+        outs.append(np.asarray(out[0][0]))
+    assert np.array_equal(outs[0], outs[1])        # same seed -> same image (graph replay)
+    assert agent.transform_to_half_resolution(out[0][0]).size == (64, 64)

@@ -86,3 +86,28 @@ def test_taesd_oracle_runs_and_is_bounded():
     z = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(0)) * 5.0
     img = sd_models.taesd_decode(sd, cfg, z)
     assert img.shape == (1, 3, 64, 64) and torch.isfinite(img).all()
+
+
+def test_vae_encoder_schema_and_oracle():
+    """AutoencoderKL encoder + quant_conv: 34,163,664 parameters; with the decoder + post_quant_conv the published
+    83,653,863 of the SD VAE.  The oracle's Downsample2D pads (0, 1, 0, 1): output is exactly H/8 and depends on the last
+    input row/column but the padding never shifts the image."""
+    import math
+
+    import torch
+
+    from genima_b200.configs import VAEConfig
+    from oracle import sd_models
+
+    n_enc = sum(math.prod(v) for v in W.vae_encoder_shapes(VAEConfig()).values())
+    n_dec = sum(math.prod(v) for v in W.vae_decoder_shapes(VAEConfig()).values())
+    assert n_enc == 34_163_664 and n_enc + n_dec == 83_653_863
+    cfg = VAEConfig.tiny()
+    sd = W.synth_state_dict(W.vae_encoder_shapes(cfg), salt=2)
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    z = sd_models.vae_encode_mean(sd, cfg, x)
+    assert z.shape == (1, 4, 8, 8) and torch.isfinite(z).all()
+    x2 = x.clone()
+    x2[..., -1, :] += 0.5                          # the last row is inside the receptive field (bottom padding only)
+    assert not torch.equal(sd_models.vae_encode_mean(sd, cfg, x2), z)
+    assert torch.equal(sd_models.vae_encode_mean(sd, cfg, x), z)
