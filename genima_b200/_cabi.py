@@ -90,6 +90,7 @@ SIGNATURES = {
     "gn_add": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "gn_timestep_embedding": (_i, [_vp, _f, _i, _vp, _vp]),
     "gn_euler_step": (_i, [_vp, _vp, _vp, _f, _f, _vp, _vp, _i64, _vp]),
+    "gn_euler_ancestral_step": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _i64, _vp]),
     "gn_scale": (_i, [_vp, _vp, _f, _vp, _i64, _vp]),
     "gn_tanh_clamp": (_i, [_vp, _vp, _f, _vp, _i64, _vp]),
     "gn_nchw_to_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _vp, _vp]),

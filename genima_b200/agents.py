@@ -7,6 +7,7 @@
                            `transform_to_half_resolution`; `.pipe` is a B200ControlNetPipeline.
   B200Pix2PixAgent         the same for `agent.SDPix2PixAgent` (controller/agent/sd_pix2pix_agent.py:11-60); `.pipe` is a
                            B200Pix2PixPipeline (InstructPix2Pix: VAE-encoded image latents, no ControlNet).
+  B200SDXLControlNetAgent  the same for `agent.SDXLControlNetAgent` (controller/agent/sdxl_controlnet_agent.py:11-75).
   B200GenimaACTPolicy      replacement for `GenimaACTPolicy` (controller/method/genima_act.py:142-214): forward(qpos, image,
                            actions=None, is_pad=None, task_emb=None) -> a_hat [B, 20, 8]; inference only.
   B200GenimaACT            the `act` / `encode_clip_text` surface of `GenimaACT` (genima_act.py:273-346) on the obs-dict
@@ -28,7 +29,7 @@ from . import weights as W
 from .act_policy import DeviceACT
 from .configs import ACTConfig, CLIPTextConfig, SchedulerConfig, TAESDConfig, UNetConfig, VAEConfig
 from .ops import Ops
-from .pipeline import B200ControlNetPipeline, B200Pix2PixPipeline
+from .pipeline import B200ControlNetPipeline, B200Pix2PixPipeline, B200SDXLControlNetPipeline
 from .text_encoder import DeviceCLIPText
 from .unet import tensor_key
 
@@ -187,6 +188,60 @@ class B200Pix2PixAgent(B200ControlNetAgent):
         self.pipe = B200Pix2PixPipeline(ops, loaded["unet"], loaded["vae"], loaded["text"], loaded["unet_cfg"],
                                         loaded["vae_cfg"], loaded["text_cfg"], loaded["scheduler_cfg"], tokenizer=tok,
                                         use_cuda_graph=graph)
+
+
+class B200SDXLControlNetAgent(B200ControlNetAgent):
+    """Drop-in for agent.SDXLControlNetAgent (controller/agent/sdxl_controlnet_agent.py:11-75): ControlNet from
+    `<diffusion_ckpt>/checkpoint-*/controlnet`, everything else from the SDXL snapshot in sd_ckpt (two text encoders,
+    Euler-ancestral scheduler for sdxl-turbo); `autoencoder` containing "taesdxl" selects AutoencoderTiny (:45-49).
+    `synthetic_weights`: 'sdxl' (full size) | 'sdxl-tiny'."""
+
+    def load_checkpoint(self):
+        cfg = self.eval_cfg
+        ops = self._ops or get_ops(_cfg_get(cfg, "device", "cuda"))
+        autoenc = _cfg_get(cfg, "autoencoder", "") or ""
+        taesd = "taesdxl" in autoenc
+        synth = _cfg_get(cfg, "synthetic_weights", None)
+        tok, tok2 = _cfg_get(cfg, "tokenizer", None), _cfg_get(cfg, "tokenizer_2", None)
+        graph = bool(_cfg_get(cfg, "use_cuda_graph", True))
+        if synth:
+            if synth == "sdxl-tiny":
+                ucfg, vcfg = UNetConfig.sdxl_tiny(), dataclasses.replace(VAEConfig.tiny(), scaling_factor=0.13025)
+                t1, t2 = CLIPTextConfig.tiny(), CLIPTextConfig.tiny(projection_dim=64)
+            elif synth == "sdxl":
+                ucfg, vcfg = UNetConfig.sdxl(), VAEConfig(scaling_factor=0.13025)
+                t1, t2 = CLIPTextConfig.sdxl_clip_l(), CLIPTextConfig.sdxl_open_clip_bigg()
+            else:
+                raise ValueError(f"unknown synthetic_weights preset {synth!r} for the SDXL agent (use 'sdxl' or 'sdxl-tiny')")
+            with_text = bool(_cfg_get(cfg, "synthetic_text_encoder", True))
+            if taesd:
+                vcfg = TAESDConfig.tiny() if synth == "sdxl-tiny" else TAESDConfig()
+            vae_sd = W.synth_state_dict(W.taesd_decoder_shapes(vcfg) if taesd else W.vae_decoder_shapes(vcfg), salt=2)
+            self.pipe = B200SDXLControlNetPipeline(
+                ops, W.synth_state_dict(W.unet_shapes(ucfg)), W.synth_state_dict(W.controlnet_shapes(ucfg), salt=1),
+                vae_sd, W.synth_state_dict(W.clip_text_shapes(t1)) if with_text else None,
+                W.synth_state_dict(W.clip_text_shapes(t2), salt=4) if with_text else None,
+                ucfg, vcfg, t1, t2, tokenizer=tok, tokenizer_2=tok2, use_cuda_graph=graph)
+            return
+        loaded = ckpt.load_sdxl(_cfg_get(cfg, "sd_ckpt"), _cfg_get(cfg, "diffusion_ckpt"))
+        if taesd:
+            loaded["vae"], loaded["vae_cfg"] = ckpt.load_taesd(autoenc)
+        self.pipe = B200SDXLControlNetPipeline(
+            ops, loaded["unet"], loaded["controlnet"], loaded["vae"], loaded["text"], loaded["text2"],
+            loaded["unet_cfg"], loaded["vae_cfg"], loaded["text_cfg"], loaded["text2_cfg"], loaded["scheduler_cfg"],
+            tokenizer=tok, tokenizer_2=tok2, use_cuda_graph=graph)
+
+    def infer(self, *args, **kwargs):
+        extra = ("latents", "prompt_embeds", "pooled_prompt_embeds", "output_type")
+        return self.pipe(
+            prompt=kwargs["prompts"],
+            image=kwargs["images"],
+            negative_prompt=kwargs["negative_prompts"],
+            num_inference_steps=kwargs["num_inference_steps"],
+            guidance_scale=kwargs["guidance_scale"],
+            generator=kwargs["generator"],
+            **{k: kwargs[k] for k in extra if k in kwargs},
+        )
 
 
 class B200GenimaACTPolicy:

@@ -69,10 +69,16 @@ def unet_config_from_json(cfg: dict) -> UNetConfig:
         raise NotImplementedError("use_linear_projection=False (conv proj_in/out, SD-1.x) is not implemented")
     if cfg.get("upcast_attention", False):
         raise NotImplementedError("upcast_attention=True (SD-2.1-768) is not implemented")
-    if cfg.get("class_embed_type") or cfg.get("addition_embed_type"):
-        raise NotImplementedError("class / additional embeddings (SDXL) are not implemented")
+    if cfg.get("class_embed_type") or cfg.get("addition_embed_type") not in (None, "text_time"):
+        raise NotImplementedError("class embeddings / addition_embed_type other than SDXL's 'text_time' are not implemented")
+    sdxl = cfg.get("addition_embed_type") == "text_time"
+    tl = cfg.get("transformer_layers_per_block", 1)
+    tl = () if tl == 1 else tuple((tl,) * len(boc) if isinstance(tl, int) else tl)
     ce = tuple(cfg.get("conditioning_embedding_out_channels", (16, 32, 96, 256)))
-    return UNetConfig(in_channels=cfg.get("in_channels", 4), out_channels=cfg.get("out_channels", 4),
+    return UNetConfig(transformer_layers=tl, addition_embed=sdxl,
+                      addition_time_embed_dim=cfg.get("addition_time_embed_dim") or 256,
+                      projection_input_dim=cfg.get("projection_class_embeddings_input_dim") or 2816,
+                      in_channels=cfg.get("in_channels", 4), out_channels=cfg.get("out_channels", 4),
                       block_out_channels=boc, layers_per_block=cfg.get("layers_per_block", 2),
                       num_heads=tuple(heads), attn_levels=tuple("CrossAttn" in t for t in down),
                       cross_attention_dim=cfg.get("cross_attention_dim", 1024),
@@ -122,6 +128,32 @@ def load_sd_pix2pix(sd_ckpt: str, diffusion_ckpt: str):
     return out
 
 
+def text_config_from_json(tj: dict) -> CLIPTextConfig:
+    return CLIPTextConfig(vocab_size=tj.get("vocab_size", 49408), hidden_size=tj.get("hidden_size", 1024),
+                          intermediate_size=tj.get("intermediate_size", 4096),
+                          num_layers=tj.get("num_hidden_layers", 23), num_heads=tj.get("num_attention_heads", 16),
+                          max_positions=tj.get("max_position_embeddings", 77),
+                          act="quick_gelu" if tj.get("hidden_act", "gelu") == "quick_gelu" else "gelu",
+                          eps=tj.get("layer_norm_eps", 1e-5),
+                          projection_dim=(tj.get("projection_dim", 0)
+                                          if "WithProjection" in str(tj.get("architectures", "")) else 0))
+
+
+def load_sdxl(sd_ckpt: str, diffusion_ckpt: str):
+    """load_sd_turbo for an SDXL snapshot (stabilityai/sdxl-turbo layout; controller/agent/sdxl_controlnet_agent.py:19-42):
+    adds text_encoder_2 (CLIPTextModelWithProjection) -> out["text2"], out["text2_cfg"]."""
+    out = load_sd_turbo(sd_ckpt, diffusion_ckpt)
+    if not out["unet_cfg"].addition_embed:
+        raise ValueError(f"{sd_ckpt} is not an SDXL snapshot (unet addition_embed_type != 'text_time')")
+    t2 = os.path.join(sd_ckpt, "text_encoder_2")
+    out["text2_cfg"] = text_config_from_json(_read_json(os.path.join(t2, "config.json")))
+    if not out["text2_cfg"].projection_dim:
+        raise ValueError("text_encoder_2 must be a CLIPTextModelWithProjection")
+    out["text2"] = load_safetensors_dir(t2)
+    check_schema(out["text2"], W.clip_text_shapes(out["text2_cfg"]), "text encoder 2")
+    return out
+
+
 def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: Optional[str]):
     """-> dict(unet=, controlnet=, vae=, text=, unet_cfg=, vae_cfg=, text_cfg=, scheduler_cfg=) from local directories
     (diffusion_ckpt None: the base components only, no ControlNet)."""
@@ -142,12 +174,7 @@ def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: Optional[str]):
                      layers_per_block=vj.get("layers_per_block", 2), norm_num_groups=vj.get("norm_num_groups", 32),
                      scaling_factor=vj.get("scaling_factor", 0.18215))
     tj = _read_json(os.path.join(sd_ckpt, "text_encoder", "config.json"))
-    tcfg = CLIPTextConfig(vocab_size=tj.get("vocab_size", 49408), hidden_size=tj.get("hidden_size", 1024),
-                          intermediate_size=tj.get("intermediate_size", 4096),
-                          num_layers=tj.get("num_hidden_layers", 23), num_heads=tj.get("num_attention_heads", 16),
-                          max_positions=tj.get("max_position_embeddings", 77),
-                          act="quick_gelu" if tj.get("hidden_act", "gelu") == "quick_gelu" else "gelu",
-                          eps=tj.get("layer_norm_eps", 1e-5))
+    tcfg = text_config_from_json(tj)
     scfg = scheduler_config_from_json(_read_json(os.path.join(sd_ckpt, "scheduler", "scheduler_config.json")))
     out = dict(unet=load_safetensors_dir(os.path.join(sd_ckpt, "unet")),
                controlnet=load_safetensors_dir(cn_dir) if cn_dir is not None else None,

@@ -29,6 +29,16 @@ class UNetConfig:
     norm_eps: float = 1e-5
     cond_embed_channels: Tuple[int, ...] = (16, 32, 96, 256)  # ControlNet conditioning embedding
     sample_size: int = 64
+    # BasicTransformerBlocks per Transformer2DModel at each level (diffusers transformer_layers_per_block; the mid block
+    # uses the last entry).  () = one everywhere (SD-2.x); SDXL: (1, 2, 10)
+    transformer_layers: Tuple[int, ...] = ()
+    # SDXL addition_embed_type="text_time": emb += add_embedding(cat(pooled text embeds, sinusoid(time_ids)))
+    addition_embed: bool = False
+    addition_time_embed_dim: int = 256
+    projection_input_dim: int = 2816          # pooled text embeds (1280) + 6 time ids x 256
+
+    def tf_layers(self, level: int) -> int:
+        return self.transformer_layers[level] if self.transformer_layers else 1
 
     @property
     def time_embed_dim(self) -> int:
@@ -38,6 +48,20 @@ class UNetConfig:
     def tiny() -> "UNetConfig":
         return UNetConfig(block_out_channels=(64, 128, 128, 128), num_heads=(1, 2, 2, 2), cross_attention_dim=128,
                           cond_embed_channels=(16, 32, 64, 64), sample_size=16)
+
+    @staticmethod
+    def sdxl() -> "UNetConfig":
+        """stabilityai/sdxl-turbo (and SDXL base) U-Net / ControlNet topology: three levels, no attention at level 0,
+        1 / 2 / 10 transformer blocks, 2048-wide context (two text encoders), text_time added conditioning."""
+        return UNetConfig(block_out_channels=(320, 640, 1280), num_heads=(5, 10, 20), attn_levels=(False, True, True),
+                          cross_attention_dim=2048, transformer_layers=(1, 2, 10), addition_embed=True, sample_size=64)
+
+    @staticmethod
+    def sdxl_tiny() -> "UNetConfig":
+        return UNetConfig(block_out_channels=(64, 128, 128), num_heads=(1, 2, 2), attn_levels=(False, True, True),
+                          cross_attention_dim=256, cond_embed_channels=(16, 32, 64, 64), transformer_layers=(1, 2, 3),
+                          addition_embed=True, addition_time_embed_dim=32, projection_input_dim=64 + 6 * 32,
+                          sample_size=16)
 
 
 @dataclass(frozen=True)
@@ -90,6 +114,17 @@ class CLIPTextConfig:
     @staticmethod
     def sd_turbo() -> "CLIPTextConfig":
         return CLIPTextConfig()
+
+    @staticmethod
+    def sdxl_clip_l() -> "CLIPTextConfig":
+        """SDXL text_encoder: OpenAI CLIP ViT-L/14 text tower (12 layers, d 768, quick_gelu)."""
+        return CLIPTextConfig(hidden_size=768, intermediate_size=3072, num_layers=12, num_heads=12, act="quick_gelu")
+
+    @staticmethod
+    def sdxl_open_clip_bigg() -> "CLIPTextConfig":
+        """SDXL text_encoder_2: OpenCLIP ViT-bigG/14 text tower with projection (32 layers, d 1280, GELU)."""
+        return CLIPTextConfig(hidden_size=1280, intermediate_size=5120, num_layers=32, num_heads=20, act="gelu",
+                              projection_dim=1280)
 
     @staticmethod
     def vit_b32() -> "CLIPTextConfig":

@@ -104,6 +104,20 @@ __global__ void euler_step_kernel(const __half* __restrict__ x, const __half* __
   }
 }
 
+__global__ void euler_ancestral_step_kernel(const __half* __restrict__ x, const __half* __restrict__ eps,
+                                            const __half* __restrict__ noise, float dsigma, float sigma_up,
+                                            float inv_scale_next, __half* __restrict__ x_next,
+                                            __half* __restrict__ x_scaled, int64_t n) {
+  GRID_STRIDE(i, n) {
+    // EulerAncestralDiscreteScheduler.step: fp32 update, noise drawn in the model dtype, result cast back to fp16
+    float xn = __half2float(x[i]) + dsigma * __half2float(eps[i]);
+    xn += __half2float(noise[i]) * sigma_up;
+    const __half h = __float2half_rn(xn);
+    x_next[i] = h;
+    if (x_scaled) x_scaled[i] = __float2half_rn(__half2float(h) * inv_scale_next);
+  }
+}
+
 struct Norm3 {
   float mean[3];
   float inv_std[3];
@@ -345,6 +359,20 @@ extern "C" int gn_euler_step(gn_handle* h, const void* x, const void* eps, float
   euler_step_kernel<<<grid_for(h, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(x), static_cast<const __half*>(eps), sigma_next - sigma, inv,
       static_cast<__half*>(x_next), static_cast<__half*>(x_scaled), n);
+  GN_CHECK_LAUNCH(h);
+  return GN_OK;
+}
+
+extern "C" int gn_euler_ancestral_step(gn_handle* h, const void* x, const void* eps, const void* noise, float sigma,
+                                       float sigma_down, float sigma_up, float sigma_next, void* x_next,
+                                       void* x_scaled, int64_t n, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  ProfScope prof(h, stream, GN_PROF_ELEMENTWISE, 0.0, 0.0);
+  GN_CHECK_ARG(h, x && eps && noise && x_next && n > 0, "gn_euler_ancestral_step: bad arguments");
+  const float inv = 1.0f / sqrtf(sigma_next * sigma_next + 1.0f);
+  euler_ancestral_step_kernel<<<grid_for(h, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(x), static_cast<const __half*>(eps), static_cast<const __half*>(noise),
+      sigma_down - sigma, sigma_up, inv, static_cast<__half*>(x_next), static_cast<__half*>(x_scaled), n);
   GN_CHECK_LAUNCH(h);
   return GN_OK;
 }

@@ -556,6 +556,23 @@ class Ops:
         self.handle.check(rc, "gn_euler_step")
         return x_next, x_scaled
 
+    def euler_ancestral_step(self, x: torch.Tensor, eps: torch.Tensor, noise: torch.Tensor, sigma: float,
+                             sigma_down: float, sigma_up: float, sigma_next: float,
+                             x_next: Optional[torch.Tensor] = None, x_scaled: Optional[torch.Tensor] = None):
+        """EulerAncestralDiscreteScheduler.step: x + (sigma_down - sigma) eps + sigma_up noise (+ next step's scaling)."""
+        _f16(x, "x")
+        _f16(eps, "eps")
+        _f16(noise, "noise")
+        if noise.shape != x.shape or not noise.is_contiguous():
+            raise ValueError("noise must be contiguous and shaped like x")
+        if x_next is None:
+            x_next = torch.empty_like(x)
+        rc = self.lib.gn_euler_ancestral_step(self.h, x.data_ptr(), eps.data_ptr(), noise.data_ptr(), float(sigma),
+                                              float(sigma_down), float(sigma_up), float(sigma_next),
+                                              x_next.data_ptr(), _ptr(x_scaled), x.numel(), self._stream())
+        self.handle.check(rc, "gn_euler_ancestral_step")
+        return x_next, x_scaled
+
     def nchw_to_nhwc(self, src: torch.Tensor, cpad: Optional[int] = None, mean=None, std=None) -> torch.Tensor:
         if not src.is_cuda or not src.is_contiguous() or src.dtype not in (torch.float16, torch.float32, torch.uint8):
             raise TypeError("nchw_to_nhwc: contiguous CUDA fp16/fp32/uint8 tensor expected")

@@ -114,6 +114,7 @@ class B200ControlNetPipeline:
         self._pinned: Dict[tuple, torch.Tensor] = {}
         self._tuned_shapes = set()
         self.progress_bar_disabled = True
+        self._added = None      # SDXL added conditioning of the current call (text_embeds, time_ids); None for SD-2.x
 
     def launch_count(self) -> int:
         """Kernels launched through this pipeline's handle(s) since creation."""
@@ -200,14 +201,20 @@ class B200ControlNetPipeline:
             self._kv_owner = ctx  # keep ctx alive so data_ptr cannot be recycled under the same key
         return self._kv_cache[key]
 
+    def _added_key(self) -> tuple:
+        a = getattr(self, "_added", None)
+        return () if a is None else tensor_key(a["text_embeds"]) + tuple(float(v) for v in a["time_ids"])
+
     def _time_rows(self, n_steps: int, batch: int):
-        key = (n_steps, batch)
+        key = (n_steps, batch) + self._added_key()
         if key not in self._temb_cache:
+            if len(self._temb_cache) > 16:
+                self._temb_cache.clear()
             ts, _ = self.schedule.set_timesteps(n_steps)
             per_step = []
             for t in ts:
-                su = self.unet_impl.time_embedding(float(t))
-                sc = self.controlnet_impl.time_embedding(float(t))
+                su = self.unet_impl.time_embedding(float(t), self._added)
+                sc = self.controlnet_impl.time_embedding(float(t), self._added)
                 per_step.append((self.unet_impl.temb_rows(self.unet_impl.resblocks(), su, batch),
                                  self.controlnet_impl.temb_rows(self.controlnet_impl.resblocks(), sc, batch)))
             self._temb_cache[key] = per_step
@@ -254,8 +261,23 @@ class B200ControlNetPipeline:
         return buf.numpy().copy()
 
     # ------------------------------------------------------------------ the device chain
+    def _scheduler_step(self, x: torch.Tensor, eps: torch.Tensor, i: int, noise: Optional[torch.Tensor]):
+        """scheduler.step + the next step's scale_model_input in one kernel -> (x_next, x_scaled_next)."""
+        sig = self.schedule.sigmas
+        x_next, xs_next = torch.empty_like(x), torch.empty_like(x)
+        if self.schedule.ancestral:
+            if noise is None:
+                raise RuntimeError("EulerAncestralDiscreteScheduler re-injects noise at every step: per-step noise "
+                                   "[n_steps, B, h, w, 8] is required (the public __call__ draws it from `generator`)")
+            up, down = self.schedule.ancestral_sigmas(i)
+            self.ops.euler_ancestral_step(x, eps, noise[i], float(sig[i]), down, up, float(sig[i + 1]),
+                                          x_next=x_next, x_scaled=xs_next)
+        else:
+            self.ops.euler_step(x, eps, float(sig[i]), float(sig[i + 1]), x_next=x_next, x_scaled=xs_next)
+        return x_next, xs_next
+
     def _denoise_and_decode(self, cond_u8: torch.Tensor, lat_in: torch.Tensor, kv, tk: int, n_steps: int,
-                            want_image: bool, cond_scale: float):
+                            want_image: bool, cond_scale: float, noise: Optional[torch.Tensor] = None):
         """cond_u8 [B, H, W, 3]; lat_in [B, h, w, 8] fp16 (unit-variance noise).  Returns (latents, image fp16|None)."""
         ops = self.ops
         B = lat_in.shape[0]
@@ -309,10 +331,7 @@ class B200ControlNetPipeline:
                 skips, mid = outs[:-1], outs[-1]
                 del cn_mid, cn_skips, outs
                 self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps)
-                x_next = torch.empty_like(x)
-                xs_next = torch.empty_like(x)
-                ops.euler_step(x, eps, float(sig[i]), float(sig[i + 1]), x_next=x_next, x_scaled=xs_next)
-                x, xs = x_next, xs_next
+                x, xs = self._scheduler_step(x, eps, i, noise)
                 continue
             if concurrent:
                 main = torch.cuda.current_stream()
@@ -329,10 +348,7 @@ class B200ControlNetPipeline:
                                                          ops=self.ops_zero if self.overlap_zero_convs else None)
             del cn_mid, cn_skips
             self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps)
-            x_next = torch.empty_like(x)
-            xs_next = torch.empty_like(x)
-            ops.euler_step(x, eps, float(sig[i]), float(sig[i + 1]), x_next=x_next, x_scaled=xs_next)
-            x, xs = x_next, xs_next
+            x, xs = self._scheduler_step(x, eps, i, noise)
         for o in self.all_ops():
             o.set_gn_max_ctas(0)
         img = None
@@ -341,34 +357,38 @@ class B200ControlNetPipeline:
             img = self.vae_impl.decode(z)
         return x, img
 
-    def _run(self, cond_u8, lat_in, kv, tk, n_steps, want_image, cond_scale):
+    def _run(self, cond_u8, lat_in, kv, tk, n_steps, want_image, cond_scale, noise=None):
         if not self.use_cuda_graph:
-            return self._denoise_and_decode(cond_u8, lat_in, kv, tk, n_steps, want_image, cond_scale)
-        key = (tuple(cond_u8.shape), tuple(lat_in.shape), id(kv), tk, n_steps, want_image, cond_scale)
+            return self._denoise_and_decode(cond_u8, lat_in, kv, tk, n_steps, want_image, cond_scale, noise)
+        key = (tuple(cond_u8.shape), tuple(lat_in.shape), id(kv), tk, n_steps, want_image, cond_scale,
+               noise is not None) + self._added_key()
         g = self._graphs.get(key)
         if g is None:
             static_cond = cond_u8.clone()
             static_lat = lat_in.clone()
+            static_noise = noise.clone() if noise is not None else None
             self._time_rows(n_steps, lat_in.shape[0])                 # hoisted work must exist before capture
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                             # warm-up: tensor maps, smem attributes, allocator
-                self._denoise_and_decode(static_cond, static_lat, kv, tk, n_steps, want_image, cond_scale)
+                self._denoise_and_decode(static_cond, static_lat, kv, tk, n_steps, want_image, cond_scale, static_noise)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             launches0 = ops_launches = self.launch_count()
             with torch.cuda.graph(graph):
                 out_lat, out_img = self._denoise_and_decode(static_cond, static_lat, kv, tk, n_steps, want_image,
-                                                            cond_scale)
+                                                            cond_scale, static_noise)
             ops_launches = self.launch_count() - launches0
-            g = dict(graph=graph, cond=static_cond, lat=static_lat, out_lat=out_lat, out_img=out_img, kv=kv,
-                     launches=ops_launches)
+            g = dict(graph=graph, cond=static_cond, lat=static_lat, noise=static_noise, out_lat=out_lat,
+                     out_img=out_img, kv=kv, launches=ops_launches)
             if len(self._graphs) > 4:
                 self._graphs.clear()
             self._graphs[key] = g
         g["cond"].copy_(cond_u8, non_blocking=True)
         g["lat"].copy_(lat_in, non_blocking=True)
+        if noise is not None:
+            g["noise"].copy_(noise, non_blocking=True)
         g["graph"].replay()
         self.last_graph_launches = g["launches"]
         return g["out_lat"], g["out_img"]
@@ -452,8 +472,24 @@ class B200ControlNetPipeline:
                 latents = latents.float()
         lat_in = ops.nchw_to_nhwc(latents.contiguous(), cpad=LATENT_CPAD)
 
-        self.schedule.set_timesteps(int(num_inference_steps))
-        x, img = self._run(cond_u8, lat_in, kv, tk, int(num_inference_steps), output_type != "latent", cond_scale)
+        n_steps = int(num_inference_steps)
+        self.schedule.set_timesteps(n_steps)
+        noise = None
+        if self.schedule.ancestral:
+            # EulerAncestralDiscreteScheduler.step draws randn_tensor(model_output.shape, dtype=model dtype,
+            # generator=generator) at EVERY step (also the last one, where sigma_up = 0): same draws, same order, so a
+            # generator shared across calls stays aligned with the reference's
+            gens = generator if isinstance(generator, (list, tuple)) else [generator] * B
+            if len(gens) != B:
+                raise ValueError(f"{len(gens)} generators for batch {B}")
+            draws = []
+            for _ in range(n_steps):
+                for g in gens:
+                    gdev = g.device if g is not None else ops.device
+                    draws.append(torch.randn((1, lc, h, w), generator=g, device=gdev, dtype=torch.float16).to(ops.device))
+            noise = ops.nchw_to_nhwc(torch.cat(draws, dim=0).contiguous(), cpad=LATENT_CPAD)
+            noise = noise.reshape(n_steps, B, h, w, LATENT_CPAD)
+        x, img = self._run(cond_u8, lat_in, kv, tk, n_steps, output_type != "latent", cond_scale, noise)
 
         if output_type == "latent":
             images = ops.nhwc_to_nchw(x, channels=lc)
@@ -472,6 +508,123 @@ class B200ControlNetPipeline:
         if not return_dict:
             return (images, None)
         return PipelineOutput(images=images, nsfw_content_detected=None)
+
+
+class B200SDXLControlNetPipeline(B200ControlNetPipeline):
+    """Drop-in for diffusers' StableDiffusionXLControlNetPipeline as controller/agent/sdxl_controlnet_agent.py:66-75 calls
+    it.  Same device chain as the SD-Turbo pipeline on the SDXL topology (UNetConfig.sdxl(): three levels, 1 / 2 / 10
+    transformer blocks, 2048-wide context) plus what SDXL adds [upstream, from memory: diffusers 0.29.0
+    pipelines/controlnet/pipeline_controlnet_sd_xl.py]:
+      * two text encoders: prompt_embeds = cat(hidden_states[-2] of CLIP-L, hidden_states[-2] of OpenCLIP-bigG),
+        pooled_prompt_embeds = text_encoder_2's projected EOT embedding;
+      * added conditioning of U-Net and ControlNet: emb += add_embedding(cat(pooled, sinusoid(time_ids))),
+        time_ids = original_size + crops_coords_top_left + target_size (hoisted: constant per call);
+      * sdxl-turbo's EulerAncestralDiscreteScheduler (per-step noise drawn from `generator`, gn_euler_ancestral_step).
+    The VAE runs in fp16 on the tensor cores (upstream upcasts an fp16 SDXL VAE to fp32 when config.force_upcast is set;
+    the reference trains with madebyollin/sdxl-vae-fp16-fix, diffusion/README.md:68, which does not need it)."""
+
+    def __init__(self, ops: Ops, unet_sd, controlnet_sd, vae_sd, text_sd=None, text2_sd=None,
+                 unet_cfg: UNetConfig = UNetConfig.sdxl(), vae_cfg: VAEConfig = VAEConfig(scaling_factor=0.13025),
+                 text_cfg: CLIPTextConfig = CLIPTextConfig.sdxl_clip_l(),
+                 text2_cfg: CLIPTextConfig = CLIPTextConfig.sdxl_open_clip_bigg(),
+                 scheduler_cfg: SchedulerConfig = SchedulerConfig(class_name="EulerAncestralDiscreteScheduler"),
+                 tokenizer=None, tokenizer_2=None, use_cuda_graph: bool = False, concurrent_controlnet: bool = True):
+        if not unet_cfg.addition_embed:
+            raise ValueError("the SDXL pipeline needs a U-Net with text_time added conditioning (UNetConfig.sdxl())")
+        super().__init__(ops, unet_sd, controlnet_sd, vae_sd, text_sd, unet_cfg, vae_cfg, text_cfg, scheduler_cfg,
+                         tokenizer=tokenizer, use_cuda_graph=use_cuda_graph, concurrent_controlnet=concurrent_controlnet)
+        self.text2_cfg = text2_cfg
+        self.text2_impl = DeviceCLIPText(ops, text2_sd, text2_cfg) if text2_sd is not None else None
+        self.text_encoder_2 = _ModuleShim(self.text2_impl)
+        self.tokenizer_2 = tokenizer_2 or tokenizer
+        self._pooled_cache: Dict = {}
+
+    def encode_prompt_sdxl(self, prompt=None, prompt_2=None, prompt_embeds=None, pooled_prompt_embeds=None):
+        """-> (prompt_embeds [B, 77, D1 + D2] fp16, pooled [B, P] fp16) on the device.  `prompt` / `prompt_2`: strings
+        (tokenizer / tokenizer_2) or token ids [B, 77] for the respective encoder; prompt_2 defaults to prompt."""
+        if prompt_embeds is not None:
+            if pooled_prompt_embeds is None:
+                raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+            ctx = self.encode_prompt(None, prompt_embeds)
+            key = ("pooled",) + tensor_key(pooled_prompt_embeds)
+            hit = self._pooled_cache.get(key)
+            if hit is None:
+                if len(self._pooled_cache) > 64:
+                    self._pooled_cache.clear()
+                hit = (pooled_prompt_embeds.to(self.ops.device, torch.float16).contiguous(), pooled_prompt_embeds)
+                self._pooled_cache[key] = hit
+            return ctx, hit[0]
+        if self.text_impl is None or self.text2_impl is None:
+            raise RuntimeError("pipeline was built without text encoders: pass prompt_embeds and pooled_prompt_embeds")
+        ids1 = self._prompt_ids(prompt)
+        tok = self.tokenizer
+        self.tokenizer = self.tokenizer_2
+        try:
+            ids2 = self._prompt_ids(prompt if prompt_2 is None else prompt_2)
+        finally:
+            self.tokenizer = tok
+        key = hashlib.sha1(ids1.cpu().numpy().tobytes() + b"|" + ids2.cpu().numpy().tobytes()).hexdigest()
+        if key not in self._ctx_cache:
+            if len(self._ctx_cache) > 64:
+                self._ctx_cache.clear()
+            h1, _ = self.text_impl(ids1.to(self.ops.device), penultimate=True)
+            h2, pooled = self.text2_impl(ids2.to(self.ops.device), penultimate=True)
+            self._ctx_cache[key] = (torch.cat([h1, h2], dim=-1).contiguous(), pooled.to(torch.float16))
+        return self._ctx_cache[key]
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, prompt_2=None, image=None, height: Optional[int] = None,
+                 width: Optional[int] = None, num_inference_steps: int = 50, denoising_end: Optional[float] = None,
+                 guidance_scale: float = 5.0, negative_prompt=None, negative_prompt_2=None,
+                 num_images_per_prompt: Optional[int] = 1, eta: float = 0.0, generator=None,
+                 latents: Optional[torch.Tensor] = None, prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 pooled_prompt_embeds: Optional[torch.Tensor] = None,
+                 negative_pooled_prompt_embeds: Optional[torch.Tensor] = None, ip_adapter_image=None,
+                 ip_adapter_image_embeds=None, output_type: Optional[str] = "pil", return_dict: bool = True,
+                 cross_attention_kwargs=None, controlnet_conditioning_scale: Union[float, List[float]] = 1.0,
+                 guess_mode: bool = False, control_guidance_start: Union[float, List[float]] = 0.0,
+                 control_guidance_end: Union[float, List[float]] = 1.0, original_size=None,
+                 crops_coords_top_left=(0, 0), target_size=None, negative_original_size=None,
+                 negative_crops_coords_top_left=(0, 0), negative_target_size=None, clip_skip: Optional[int] = None,
+                 callback_on_step_end=None, callback_on_step_end_tensor_inputs: List[str] = ["latents"], **kwargs):
+        if guidance_scale is not None and guidance_scale > 1.0:
+            raise NotImplementedError("classifier-free guidance (guidance_scale > 1) is not implemented; Genima runs 0.0")
+        if num_images_per_prompt not in (None, 1):
+            raise NotImplementedError("num_images_per_prompt != 1 is not implemented")
+        if guess_mode:
+            raise NotImplementedError("guess_mode is not implemented")
+        if denoising_end is not None:
+            raise NotImplementedError("denoising_end (base / refiner split) is not implemented")
+        if ip_adapter_image is not None or ip_adapter_image_embeds is not None:
+            raise NotImplementedError("ip-adapter inputs are not implemented")
+        if control_guidance_start != 0.0 or control_guidance_end != 1.0:
+            raise NotImplementedError("control_guidance_start/end windows are not implemented")
+        if isinstance(controlnet_conditioning_scale, (list, tuple)):
+            raise NotImplementedError("multi-ControlNet conditioning scales are not implemented")
+        if clip_skip is not None:
+            raise NotImplementedError("clip_skip is not implemented")
+        if cross_attention_kwargs:
+            raise NotImplementedError("cross_attention_kwargs are not implemented")
+        if callback_on_step_end is not None:
+            raise NotImplementedError("per-step callbacks would force a host sync inside the loop; not implemented")
+        if kwargs:
+            raise TypeError(f"unexpected arguments: {sorted(kwargs)}")
+        if output_type not in ("pil", "np", "pt", "latent", "u8"):
+            raise ValueError(f"output_type {output_type!r} is not supported")
+        if image is None:
+            raise ValueError("`image` (the ControlNet conditioning image) is required")
+        ctx, pooled = self.encode_prompt_sdxl(prompt, prompt_2, prompt_embeds, pooled_prompt_embeds)
+        if pooled.shape[0] != 1:
+            raise NotImplementedError("one prompt per call (it is broadcast over the batch of control images)")
+        cond_u8 = self._control_image_u8(image)
+        H, W = int(cond_u8.shape[1]), int(cond_u8.shape[2])
+        # _get_add_time_ids: original_size + crops_coords_top_left + target_size, each (height, width)
+        osz = tuple(original_size) if original_size is not None else (H, W)
+        tsz = tuple(target_size) if target_size is not None else (height or H, width or W)
+        self._added = dict(text_embeds=pooled, time_ids=[float(v) for v in (*osz, *crops_coords_top_left, *tsz)])
+        return self._generate(None, cond_u8, height, width, num_inference_steps, generator, latents, ctx,
+                              output_type, return_dict, float(controlnet_conditioning_scale))
 
 
 class B200Pix2PixPipeline(B200ControlNetPipeline):
@@ -513,6 +666,7 @@ class B200Pix2PixPipeline(B200ControlNetPipeline):
         self._ctx_cache, self._kv_cache, self._temb_cache, self._graphs, self._pinned = {}, {}, {}, {}, {}
         self._tuned_shapes = set()
         self.progress_bar_disabled = True
+        self._added = None
 
     def _context_kv(self, ctx: torch.Tensor) -> Dict[str, torch.Tensor]:
         key = tensor_key(ctx)
@@ -533,7 +687,7 @@ class B200Pix2PixPipeline(B200ControlNetPipeline):
         return self._temb_cache[key]
 
     def _denoise_and_decode(self, cond_u8: torch.Tensor, lat_in: torch.Tensor, kv, tk: int, n_steps: int,
-                            want_image: bool, cond_scale: float):
+                            want_image: bool, cond_scale: float, noise: Optional[torch.Tensor] = None):
         """cond_u8 [B, H, W, 3] (the image to edit); lat_in [B, h, w, 8] fp16 (unit-variance noise in channels 0..3)."""
         ops = self.ops
         temb = self._time_rows(n_steps, lat_in.shape[0])
@@ -549,9 +703,7 @@ class B200Pix2PixPipeline(B200ControlNetPipeline):
             xs[..., lc:] = img_lat[..., :lc]                                         # cat([scaled latents, image latents])
             mid, skips = self.unet_impl.encode(xs, temb[i], kv_u, tk)
             self.unet_impl.decode(mid, skips, temb[i], kv_u, tk, eps)
-            x_next, xs_next = torch.empty_like(x), torch.empty_like(x)
-            ops.euler_step(x, eps, float(sig[i]), float(sig[i + 1]), x_next=x_next, x_scaled=xs_next)
-            x, xs = x_next, xs_next
+            x, xs = self._scheduler_step(x, eps, i, noise)
         img = None
         if want_image:
             img = self.vae_impl.decode(ops.scale(x, 1.0 / self.vae_cfg.scaling_factor))

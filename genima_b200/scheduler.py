@@ -1,4 +1,5 @@
-"""Host-side scheduler tables for the denoise loop (diffusers EulerDiscreteScheduler as shipped by sd-turbo).
+"""Host-side scheduler tables for the denoise loop (diffusers EulerDiscreteScheduler as shipped by sd-turbo, and
+EulerAncestralDiscreteScheduler as shipped by sdxl-turbo).
 
 Only scalar, data-independent host logic lives here (timesteps, sigmas); the per-element update runs in
 gn_euler_step.  The reference keeps whatever scheduler `stabilityai/sd-turbo` ships (it never assigns pipe.scheduler on
@@ -16,8 +17,11 @@ from .configs import SchedulerConfig
 
 class EulerDiscreteSchedule:
     def __init__(self, cfg: SchedulerConfig = SchedulerConfig()):
-        if cfg.class_name != "EulerDiscreteScheduler":
-            raise NotImplementedError(f"scheduler {cfg.class_name!r} is not implemented (EulerDiscreteScheduler only)")
+        if cfg.class_name not in ("EulerDiscreteScheduler", "EulerAncestralDiscreteScheduler"):
+            raise NotImplementedError(f"scheduler {cfg.class_name!r} is not implemented (EulerDiscreteScheduler and "
+                                      "EulerAncestralDiscreteScheduler only)")
+        # stabilityai/sdxl-turbo ships the ancestral variant: same tables, but every step re-injects noise
+        self.ancestral = cfg.class_name == "EulerAncestralDiscreteScheduler"
         if cfg.prediction_type != "epsilon" or cfg.beta_schedule != "scaled_linear":
             raise NotImplementedError("only epsilon prediction with the scaled_linear beta schedule is implemented")
         self.cfg = cfg
@@ -54,3 +58,11 @@ class EulerDiscreteSchedule:
         if self.cfg.timestep_spacing in ("linspace", "trailing"):
             return m
         return float((m * m + 1.0) ** 0.5)
+
+    def ancestral_sigmas(self, i: int) -> Tuple[float, float]:
+        """(sigma_up, sigma_down) of step i (EulerAncestralDiscreteScheduler.step): the noise re-injected after the
+        deterministic move from sigmas[i] down to sigma_down.  The last step (sigma_to = 0) has sigma_up = 0."""
+        s_from, s_to = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        up = (s_to ** 2 * (s_from ** 2 - s_to ** 2) / s_from ** 2) ** 0.5
+        down = (s_to ** 2 - up ** 2) ** 0.5
+        return up, down

@@ -3,6 +3,8 @@
   * SD-Turbo text encoder (OpenCLIP-H text, 23 layers): diffusers `encode_prompt` inside pipe(...) —
     controller/agent/sd_controlnet_agent.py:67-76 — run once per distinct prompt and cached (the prompt is constant
     for a whole episode, controller/eval_genima.py:139,178);
+  * the two SDXL text encoders (CLIP ViT-L and OpenCLIP bigG with projection; penultimate hidden states + pooled
+    projection) for the SDXL-ControlNet sibling (controller/agent/sdxl_controlnet_agent.py);
   * OpenAI CLIP ViT-B/32 text tower of GenimaACT.encode_clip_text (controller/method/genima_act.py:314-346), likewise
     constant per episode.
 Token ids are the input: no CLIP BPE vocabulary exists offline, so string -> ids stays upstream.
@@ -40,14 +42,19 @@ class DeviceCLIPText:
         self.proj = P.f16("text_projection.weight") if cfg.projection_dim else None
         self.head_dim = cfg.hidden_size // cfg.num_heads
 
-    def __call__(self, ids: torch.Tensor) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-        """ids [B, T] int64 (device) -> (last_hidden_state [B, T, d] fp16, pooled projection [B, proj] fp32 or None)."""
+    def __call__(self, ids: torch.Tensor, penultimate: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """ids [B, T] int64 (device) -> (last_hidden_state [B, T, d] fp16, pooled projection [B, proj] fp32 or None).
+        penultimate=True: the first item is `hidden_states[-2]` (input of the last layer, no final LayerNorm), the
+        conditioning diffusers' SDXL encode_prompt uses."""
         ops, cfg = self.ops, self.cfg
         B, T = ids.shape
         d = cfg.hidden_size
         h = ops.embed_tokens(ids, self.tok, self.pos).reshape(B * T, d)
         act = "quick_gelu" if cfg.act == "quick_gelu" else "gelu"
-        for L in self.layers:
+        pen = None
+        for li, L in enumerate(self.layers):
+            if li == len(self.layers) - 1:
+                pen = h                                  # (every op below allocates its output: h is never overwritten)
             n = ops.layer_norm(h, *L["ln1"], eps=cfg.eps)
             qkv = ops.linear(n, L["wqkv"], bias=L["bqkv"])
             a = ops.attention_small(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], B, cfg.num_heads, self.head_dim, T, T,
@@ -62,4 +69,4 @@ class DeviceCLIPText:
             eot = ids.argmax(dim=-1)  # index arithmetic on token ids (plumbing): the EOT token has the largest id
             rows = h[torch.arange(B, device=ids.device), eot].contiguous()
             pooled = ops.linear(rows, self.proj, out_fp32=True)
-        return h, pooled
+        return (pen.reshape(B, T, d) if penultimate else h), pooled

@@ -117,35 +117,45 @@ class _ResBlock:
         return ops.conv2d(n2, self.w2, self.cout, bias=self.cb2, residual=x0, gn_stats=self.bucket)
 
 
-class _Transformer2D:
-    def __init__(self, P: _Params, prefix: str, c: int, heads: int, groups: int):
-        self.c, self.heads, self.groups = c, heads, groups
-        self.prefix = prefix
-        self.bucket = P.gn_bucket
-        t = f"{prefix}.transformer_blocks.0"
+class _TransformerBlock:
+    """One BasicTransformerBlock (self attention, cross attention, GEGLU feed-forward).  The three LayerNorms are folded
+    into the GEMMs that consume them (gn_epilogue.ln_*): gamma goes into the weights, beta into the bias, and
+    (mean, rstd) come from row statistics written by the producing GEMM's epilogue."""
+
+    def __init__(self, P: _Params, t: str):
         dev = P.device
-        self.gn_g, self.gn_b = P.f32(f"{prefix}.norm.weight"), P.f32(f"{prefix}.norm.bias")
-        self.w_in, self.b_in = P.f16(f"{prefix}.proj_in.weight"), P.f32(f"{prefix}.proj_in.bias")
-        self.w_out, self.b_out = P.f16(f"{prefix}.proj_out.weight"), P.f32(f"{prefix}.proj_out.bias")
-        # The three LayerNorms are folded into the GEMMs that consume them (gn_epilogue.ln_*): gamma goes into the
-        # weights, beta into the bias, and (mean, rstd) come from row statistics written by the producing GEMM's epilogue.
         ln = [(P.sd[f"{t}.norm{i}.weight"].to(dev).float(), P.sd[f"{t}.norm{i}.bias"].to(dev).float()) for i in (1, 2, 3)]
         w_qkv = torch.cat([P.host16(f"{t}.attn1.to_{n}.weight") for n in "qkv"], dim=0).to(dev)
         self.w_qkv, self.cs_qkv, self.b_qkv = fold_layer_norm(w_qkv, *ln[0])
         self.w_o1, self.b_o1 = P.f16(f"{t}.attn1.to_out.0.weight"), P.f32(f"{t}.attn1.to_out.0.bias")
         self.w_q2, self.cs_q2, self.b_q2 = fold_layer_norm(P.f16(f"{t}.attn2.to_q.weight"), *ln[1])
-        self.w_kv2 = torch.cat([P.host16(f"{t}.attn2.to_k.weight"), P.host16(f"{t}.attn2.to_v.weight")],
-                               dim=0).contiguous().to(dev)
+        self.w_kv2 = torch.cat([P.host16(f"{t}.attn2.to_k.weight"), P.host16(f"{t}.attn2.to_v.weight")], dim=0)
         self.w_o2, self.b_o2 = P.f16(f"{t}.attn2.to_out.0.weight"), P.f32(f"{t}.attn2.to_out.0.bias")
         wg, bg = pack_geglu_weight(P.host16(f"{t}.ff.net.0.proj.weight"), P.sd[f"{t}.ff.net.0.proj.bias"].float())
         self.w_ff1, self.cs_ff1, self.b_ff1 = fold_layer_norm(wg.to(dev), *ln[2], bias=bg.to(dev))
         self.w_ff2, self.b_ff2 = P.f16(f"{t}.ff.net.2.weight"), P.f32(f"{t}.ff.net.2.bias")
+
+
+class _Transformer2D:
+    def __init__(self, P: _Params, prefix: str, c: int, heads: int, groups: int, depth: int = 1):
+        self.c, self.heads, self.groups = c, heads, groups
+        self.prefix = prefix
+        self.bucket = P.gn_bucket
+        self.gn_g, self.gn_b = P.f32(f"{prefix}.norm.weight"), P.f32(f"{prefix}.norm.bias")
+        self.w_in, self.b_in = P.f16(f"{prefix}.proj_in.weight"), P.f32(f"{prefix}.proj_in.bias")
+        self.w_out, self.b_out = P.f16(f"{prefix}.proj_out.weight"), P.f32(f"{prefix}.proj_out.bias")
+        self.blocks = [_TransformerBlock(P, f"{prefix}.transformer_blocks.{k}") for k in range(depth)]
+        # the context K/V projections of all blocks as one GEMM: block k reads columns [2 C k, 2 C (k + 1))
+        self.w_kv2 = torch.cat([b.w_kv2 for b in self.blocks], dim=0).contiguous().to(P.device)
+        for b in self.blocks:
+            del b.w_kv2
         self.ln_eps = 1e-5
         self.scale = 64 ** -0.5
         assert c // heads == 64, "the tcgen05 attention kernel is specialised for head_dim 64"
 
     def project_context(self, ops: Ops, ctx: torch.Tensor) -> torch.Tensor:
-        """ctx [B, Tk, D] -> [B*Tk, 2C] = (K | V); constant per prompt, so computed once and cached by the caller."""
+        """ctx [B, Tk, D] -> [B*Tk, depth * 2C] = (K | V) per block; constant per prompt, so computed once and cached by
+        the caller."""
         return ops.linear(ctx.reshape(-1, ctx.shape[-1]), self.w_kv2)
 
     def __call__(self, ops: Ops, x: torch.Tensor, kv: torch.Tensor, tk: int) -> torch.Tensor:
@@ -154,19 +164,25 @@ class _Transformer2D:
         n = ops.group_norm(x, self.gn_g, self.gn_b, self.groups, 1e-6, silu=False)
         st = ops.new_row_stats(B * T, C)
         h = ops.linear(n.reshape(B * T, C), self.w_in, bias=self.b_in, row_stats=st)
-        # self attention (norm1 folded into the QKV projection)
-        qkv = ops.linear(h, self.w_qkv, bias=self.b_qkv, ln=(st, self.cs_qkv, self.ln_eps))
-        a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, self.heads, T, T, self.scale)
-        st = ops.new_row_stats(B * T, C)
-        h = ops.linear(a, self.w_o1, bias=self.b_o1, residual=h, row_stats=st)
-        # cross attention against the cached text K/V (norm2 folded into the Q projection)
-        q = ops.linear(h, self.w_q2, bias=self.b_q2, ln=(st, self.cs_q2, self.ln_eps))
-        a = ops.attention(q, kv[:, :C], kv[:, C:], B, self.heads, T, tk, self.scale)
-        st = ops.new_row_stats(B * T, C)
-        h = ops.linear(a, self.w_o2, bias=self.b_o2, residual=h, row_stats=st)
-        # GEGLU feed-forward (norm3 folded into the first projection)
-        g = ops.linear(h, self.w_ff1, bias=self.b_ff1, ln=(st, self.cs_ff1, self.ln_eps), geglu=True)
-        h = ops.linear(g, self.w_ff2, bias=self.b_ff2, residual=h)
+        for i, blk in enumerate(self.blocks):
+            k2 = kv[:, 2 * C * i:2 * C * (i + 1)]
+            # self attention (norm1 folded into the QKV projection)
+            qkv = ops.linear(h, blk.w_qkv, bias=blk.b_qkv, ln=(st, blk.cs_qkv, self.ln_eps))
+            a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, self.heads, T, T, self.scale)
+            st = ops.new_row_stats(B * T, C)
+            h = ops.linear(a, blk.w_o1, bias=blk.b_o1, residual=h, row_stats=st)
+            # cross attention against the cached text K/V (norm2 folded into the Q projection)
+            q = ops.linear(h, blk.w_q2, bias=blk.b_q2, ln=(st, blk.cs_q2, self.ln_eps))
+            a = ops.attention(q, k2[:, :C], k2[:, C:], B, self.heads, T, tk, self.scale)
+            st = ops.new_row_stats(B * T, C)
+            h = ops.linear(a, blk.w_o2, bias=blk.b_o2, residual=h, row_stats=st)
+            # GEGLU feed-forward (norm3 folded into the first projection)
+            g = ops.linear(h, blk.w_ff1, bias=blk.b_ff1, ln=(st, blk.cs_ff1, self.ln_eps), geglu=True)
+            if i + 1 < len(self.blocks):     # the next block's norm1 needs the row statistics of this output
+                st = ops.new_row_stats(B * T, C)
+                h = ops.linear(g, blk.w_ff2, bias=blk.b_ff2, residual=h, row_stats=st)
+            else:
+                h = ops.linear(g, blk.w_ff2, bias=blk.b_ff2, residual=h)
         out = ops.linear(h, self.w_out, bias=self.b_out, residual=x.reshape(B * T, C), rows_per_batch=T,
                          gn_stats=self.bucket)
         return ops.carry_stats(out.reshape(B, H, W, C), out)
@@ -208,19 +224,23 @@ class _Encoder:
         self.conv_in = _Conv(P, "conv_in", cin_layout=(cfg.in_channels, LATENT_CPAD), gn=True)
         self.te_w1, self.te_b1 = P.f16("time_embedding.linear_1.weight"), P.f32("time_embedding.linear_1.bias")
         self.te_w2, self.te_b2 = P.f16("time_embedding.linear_2.weight"), P.f32("time_embedding.linear_2.bias")
+        if cfg.addition_embed:   # SDXL text_time conditioning
+            self.ae_w1, self.ae_b1 = P.f16("add_embedding.linear_1.weight"), P.f32("add_embedding.linear_1.bias")
+            self.ae_w2, self.ae_b2 = P.f16("add_embedding.linear_2.weight"), P.f32("add_embedding.linear_2.bias")
         self.down: List[Tuple[List[_ResBlock], List[Optional[_Transformer2D]], Optional[_Conv]]] = []
         cin = ch[0]
         for i, cout in enumerate(ch):
             res, att = [], []
             for j in range(cfg.layers_per_block):
                 res.append(_ResBlock(P, f"down_blocks.{i}.resnets.{j}", (cin,), g, eps))
-                att.append(_Transformer2D(P, f"down_blocks.{i}.attentions.{j}", cout, cfg.num_heads[i], g)
-                           if cfg.attn_levels[i] else None)
+                att.append(_Transformer2D(P, f"down_blocks.{i}.attentions.{j}", cout, cfg.num_heads[i], g,
+                                          cfg.tf_layers(i)) if cfg.attn_levels[i] else None)
                 cin = cout
             ds = _Conv(P, f"down_blocks.{i}.downsamplers.0.conv", stride=2, gn=True) if i < len(ch) - 1 else None
             self.down.append((res, att, ds))
         self.mid_res0 = _ResBlock(P, "mid_block.resnets.0", (ch[-1],), g, eps)
-        self.mid_attn = _Transformer2D(P, "mid_block.attentions.0", ch[-1], cfg.num_heads[-1], g)
+        self.mid_attn = _Transformer2D(P, "mid_block.attentions.0", ch[-1], cfg.num_heads[-1], g,
+                                       cfg.tf_layers(len(ch) - 1))
         self.mid_res1 = _ResBlock(P, "mid_block.resnets.1", (ch[-1],), g, eps)
 
     # ---- hoisted, latent-independent work --------------------------------------------------------------------
@@ -236,13 +256,27 @@ class _Encoder:
             out += [a for a in att if a is not None]
         return out + [self.mid_attn]
 
-    def time_embedding(self, t: float) -> torch.Tensor:
-        """silu(temb) [1, 1280] fp16, temb = Linear(SiLU(Linear(sinusoid(t))))."""
+    def time_embedding(self, t: float, added: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        """silu(emb) [1, 1280] fp16, emb = Linear(SiLU(Linear(sinusoid(t)))) [+ add_embedding(cat(text_embeds,
+        sinusoid(time_ids))) for SDXL; added = dict(text_embeds [1, P] , time_ids: 6 floats)]."""
         ops = self.ops
         e = ops.timestep_embedding(t, self.cfg.block_out_channels[0])
         e = ops.linear(e, self.te_w1, bias=self.te_b1, act_pre="silu")
         # every consumer applies SiLU to temb first (ResnetBlock2D.nonlinearity), so fuse it here
-        return ops.linear(e, self.te_w2, bias=self.te_b2, act_pre="silu")
+        if not self.cfg.addition_embed:
+            return ops.linear(e, self.te_w2, bias=self.te_b2, act_pre="silu")
+        if added is None:
+            raise ValueError("this model needs added conditioning (text_embeds, time_ids)")
+        temb = ops.linear(e, self.te_w2, bias=self.te_b2)
+        d = self.cfg.addition_time_embed_dim
+        parts = [added["text_embeds"].reshape(1, -1).to(self.ops.device, torch.float16)]
+        parts += [ops.timestep_embedding(float(v), d) for v in added["time_ids"]]
+        a = torch.cat(parts, dim=1).contiguous()                       # (concatenation: data movement only)
+        if a.shape[1] != self.cfg.projection_input_dim:
+            raise ValueError(f"added conditioning has {a.shape[1]} features, the model expects "
+                             f"{self.cfg.projection_input_dim}")
+        a = ops.linear(a, self.ae_w1, bias=self.ae_b1, act_pre="silu")
+        return ops.linear(a, self.ae_w2, bias=self.ae_b2, residual=temb, act_post="silu")   # silu(temb + aug_emb)
 
     def temb_rows(self, blocks: Sequence[_ResBlock], silu_temb: torch.Tensor, batch: int) -> Dict[str, torch.Tensor]:
         rows = {}
@@ -294,8 +328,8 @@ class DeviceUNet(_Encoder):
             res, att = [], []
             for j in range(cfg.layers_per_block + 1):
                 res.append(_ResBlock(P, f"up_blocks.{i}.resnets.{j}", (prev, skips.pop()), g, eps))
-                att.append(_Transformer2D(P, f"up_blocks.{i}.attentions.{j}", cout, cfg.num_heads[level], g)
-                           if cfg.attn_levels[level] else None)
+                att.append(_Transformer2D(P, f"up_blocks.{i}.attentions.{j}", cout, cfg.num_heads[level], g,
+                                          cfg.tf_layers(level)) if cfg.attn_levels[level] else None)
                 prev = cout
             us = _Conv(P, f"up_blocks.{i}.upsamplers.0.conv", gn=True, upsample=True) if i < len(ch) - 1 else None
             self.up.append((res, att, us))

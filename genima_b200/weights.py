@@ -47,22 +47,23 @@ def _resnet(s, p, cin, cout, temb_dim):
         _conv(s, f"{p}.conv_shortcut", cout, cin, 1)
 
 
-def _transformer2d(s, p, c, ctx_dim):
+def _transformer2d(s, p, c, ctx_dim, depth=1):
     _norm(s, f"{p}.norm", c)
     _lin(s, f"{p}.proj_in", c, c)
-    t = f"{p}.transformer_blocks.0"
-    _norm(s, f"{t}.norm1", c)
-    for n in ("to_q", "to_k", "to_v"):
-        _lin(s, f"{t}.attn1.{n}", c, c, bias=False)
-    _lin(s, f"{t}.attn1.to_out.0", c, c)
-    _norm(s, f"{t}.norm2", c)
-    _lin(s, f"{t}.attn2.to_q", c, c, bias=False)
-    _lin(s, f"{t}.attn2.to_k", c, ctx_dim, bias=False)
-    _lin(s, f"{t}.attn2.to_v", c, ctx_dim, bias=False)
-    _lin(s, f"{t}.attn2.to_out.0", c, c)
-    _norm(s, f"{t}.norm3", c)
-    _lin(s, f"{t}.ff.net.0.proj", 8 * c, c)
-    _lin(s, f"{t}.ff.net.2", c, 4 * c)
+    for k in range(depth):
+        t = f"{p}.transformer_blocks.{k}"
+        _norm(s, f"{t}.norm1", c)
+        for n in ("to_q", "to_k", "to_v"):
+            _lin(s, f"{t}.attn1.{n}", c, c, bias=False)
+        _lin(s, f"{t}.attn1.to_out.0", c, c)
+        _norm(s, f"{t}.norm2", c)
+        _lin(s, f"{t}.attn2.to_q", c, c, bias=False)
+        _lin(s, f"{t}.attn2.to_k", c, ctx_dim, bias=False)
+        _lin(s, f"{t}.attn2.to_v", c, ctx_dim, bias=False)
+        _lin(s, f"{t}.attn2.to_out.0", c, c)
+        _norm(s, f"{t}.norm3", c)
+        _lin(s, f"{t}.ff.net.0.proj", 8 * c, c)
+        _lin(s, f"{t}.ff.net.2", c, 4 * c)
     _lin(s, f"{p}.proj_out", c, c)
 
 
@@ -72,17 +73,20 @@ def _unet_encoder(s, cfg: UNetConfig):
     _conv(s, "conv_in", ch[0], cfg.in_channels, 3)
     _lin(s, "time_embedding.linear_1", temb, ch[0])
     _lin(s, "time_embedding.linear_2", temb, temb)
+    if cfg.addition_embed:      # SDXL text_time conditioning (add_time_proj is a parameter-free sinusoid)
+        _lin(s, "add_embedding.linear_1", temb, cfg.projection_input_dim)
+        _lin(s, "add_embedding.linear_2", temb, temb)
     cin = ch[0]
     for i, cout in enumerate(ch):
         for j in range(cfg.layers_per_block):
             _resnet(s, f"down_blocks.{i}.resnets.{j}", cin, cout, temb)
             if cfg.attn_levels[i]:
-                _transformer2d(s, f"down_blocks.{i}.attentions.{j}", cout, cfg.cross_attention_dim)
+                _transformer2d(s, f"down_blocks.{i}.attentions.{j}", cout, cfg.cross_attention_dim, cfg.tf_layers(i))
             cin = cout
         if i < len(ch) - 1:
             _conv(s, f"down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
     _resnet(s, "mid_block.resnets.0", ch[-1], ch[-1], temb)
-    _transformer2d(s, "mid_block.attentions.0", ch[-1], cfg.cross_attention_dim)
+    _transformer2d(s, "mid_block.attentions.0", ch[-1], cfg.cross_attention_dim, cfg.tf_layers(len(ch) - 1))
     _resnet(s, "mid_block.resnets.1", ch[-1], ch[-1], temb)
 
 
@@ -112,7 +116,7 @@ def unet_shapes(cfg: UNetConfig) -> Shapes:
             skip = skips.pop()
             _resnet(s, f"up_blocks.{i}.resnets.{j}", prev + skip, cout, temb)
             if cfg.attn_levels[level]:
-                _transformer2d(s, f"up_blocks.{i}.attentions.{j}", cout, cfg.cross_attention_dim)
+                _transformer2d(s, f"up_blocks.{i}.attentions.{j}", cout, cfg.cross_attention_dim, cfg.tf_layers(level))
             prev = cout
         if i < len(ch) - 1:
             _conv(s, f"up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)

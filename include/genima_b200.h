@@ -235,6 +235,13 @@ int gn_timestep_embedding(gn_handle* h, float t, int dim, void* out, void* strea
  * x / eps / x_next / x_scaled: [n] fp16 element-wise; x_scaled may be NULL. */
 int gn_euler_step(gn_handle* h, const void* x, const void* eps, float sigma, float sigma_next, void* x_next,
                   void* x_scaled, int64_t n, void* stream);
+/* Euler-ancestral scheduler (diffusers EulerAncestralDiscreteScheduler.step, what stabilityai/sdxl-turbo ships; reached
+ * through controller/agent/sdxl_controlnet_agent.py:66-75), epsilon prediction:
+ *   x_next = x + (sigma_down - sigma) * eps + sigma_up * noise;   x_scaled = x_next / sqrt(sigma_next^2 + 1)
+ * with sigma_up / sigma_down the host scalars of the step and `noise` [n] fp16 drawn by the caller's generator. */
+int gn_euler_ancestral_step(gn_handle* h, const void* x, const void* eps, const void* noise, float sigma,
+                            float sigma_down, float sigma_up, float sigma_next, void* x_next, void* x_scaled,
+                            int64_t n, void* stream);
 /* y = x * s (fp16), used for scale_model_input at step 0 and latents / scaling_factor before the VAE. */
 int gn_scale(gn_handle* h, const void* x, float s, void* y, int64_t n, void* stream);
 /* y = tanh(x / mag) * mag (fp16, n elements): AutoencoderTiny's soft clamp of the latents before its decoder

@@ -17,15 +17,20 @@ import torch.nn.functional as F
 from genima_b200.configs import CLIPTextConfig
 
 
-def clip_text_forward(sd: Dict[str, torch.Tensor], cfg: CLIPTextConfig, ids: torch.Tensor):
-    """ids: [B, T] int64.  Returns (last_hidden_state [B, T, d], pooled-projected [B, proj] or None)."""
+def clip_text_forward(sd: Dict[str, torch.Tensor], cfg: CLIPTextConfig, ids: torch.Tensor, penultimate: bool = False):
+    """ids: [B, T] int64.  Returns (last_hidden_state [B, T, d], pooled-projected [B, proj] or None); with
+    penultimate=True the first item is transformers' `hidden_states[-2]` instead (the input of the last layer, no final
+    LayerNorm), which is what diffusers' SDXL encode_prompt feeds to the U-Net."""
     w = lambda k: sd[k].to(torch.float32)  # noqa: E731
     b, t = ids.shape
     d = cfg.hidden_size
     h = w("text_model.embeddings.token_embedding.weight")[ids] + w("text_model.embeddings.position_embedding.weight")[:t]
     mask = torch.full((t, t), float("-inf")).triu(1)
     hd = d // cfg.num_heads
+    pen = None
     for i in range(cfg.num_layers):
+        if i == cfg.num_layers - 1:
+            pen = h
         p = f"text_model.encoder.layers.{i}"
         n = F.layer_norm(h, (d,), w(f"{p}.layer_norm1.weight"), w(f"{p}.layer_norm1.bias"), cfg.eps)
         q = F.linear(n, w(f"{p}.self_attn.q_proj.weight"), w(f"{p}.self_attn.q_proj.bias"))
@@ -46,4 +51,4 @@ def clip_text_forward(sd: Dict[str, torch.Tensor], cfg: CLIPTextConfig, ids: tor
     if cfg.projection_dim:
         eot = ids.argmax(dim=-1)  # OpenAI CLIP: the EOT token has the largest id
         pooled = F.linear(h[torch.arange(b), eot], w("text_projection.weight"))
-    return h, pooled
+    return (pen if penultimate else h), pooled

@@ -5,6 +5,8 @@
                          controller/cfgs/eval_genima.yaml:31), control image in [0, 1] without normalisation, explicit
                          `latents` multiplied by init_noise_sigma, Euler-trailing loop with ControlNet residuals added to
                          the U-Net skips, VAE decode of latents / scaling_factor, postprocess to uint8.
+  sdxl_controlnet_pipeline()  the SDXL-ControlNet sibling (controller/agent/sdxl_controlnet_agent.py): two text encoders'
+                         penultimate states, text_time added conditioning, Euler-ancestral steps.
   pix2pix_pipeline()     the InstructPix2Pix sibling (controller/agent/sd_pix2pix_agent.py): VAE-encoded image latents
                          concatenated to the U-Net input, no ControlNet.
   agent_step()           controller/eval_genima.py:163-249 between `obs` and `actions`: tile_images -> pipeline ->
@@ -52,6 +54,36 @@ def controlnet_pipeline(unet_sd, cn_sd, vae_sd, ucfg: UNetConfig, vcfg: VAEConfi
     if return_intermediates:
         out["steps"] = inter
     return out
+
+
+def sdxl_controlnet_pipeline(unet_sd, cn_sd, vae_sd, ucfg: UNetConfig, vcfg: VAEConfig, cond_u8: np.ndarray,
+                             ctx: torch.Tensor, pooled: torch.Tensor, latents: torch.Tensor, step_noise, n_steps: int,
+                             conditioning_scale: float = 1.0):
+    """diffusers 0.29.0 StableDiffusionXLControlNetPipeline.__call__ as controller/agent/sdxl_controlnet_agent.py:66-75
+    exercises it (guidance 0.0 -> no CFG) [upstream, from memory]: ctx = cat of the two encoders' penultimate hidden
+    states [B, 77, 2048]; added_cond_kwargs = {text_embeds: pooled, time_ids: (H, W, 0, 0, H, W)} for both ControlNet
+    and U-Net; EulerAncestralDiscreteScheduler (sdxl-turbo) with the per-step noise passed in as step_noise[i]
+    [B, 4, h, w] (upstream draws it from `generator` inside scheduler.step)."""
+    from .scheduler import EulerAncestralOracle
+
+    sched = EulerAncestralOracle()
+    ts, sig = sched.set_timesteps(n_steps)
+    B, H, W, _ = cond_u8.shape
+    cond = torch.from_numpy(cond_u8.astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    added = dict(text_embeds=pooled.to(torch.float32).expand(B, -1),
+                 time_ids=torch.tensor([[H, W, 0, 0, H, W]], dtype=torch.float32).expand(B, -1))
+    x = latents.to(torch.float32) * sched.init_noise_sigma
+    for i, t in enumerate(ts):
+        xs = sched.scale_model_input(x, i)
+        tt = torch.tensor([float(t)])
+        down, mid = sd_models.controlnet_forward(cn_sd, ucfg, xs, tt, ctx, cond, conditioning_scale, added)
+        eps = sd_models.unet_forward(unet_sd, ucfg, xs, tt, ctx, down, mid, added)
+        x = sched.step(eps, i, x, step_noise[i])
+    decode = sd_models.taesd_decode if hasattr(vcfg, "num_blocks") else sd_models.vae_decode
+    img = decode(vae_sd, vcfg, x / vcfg.scaling_factor)
+    den = (img / 2 + 0.5).clamp(0, 1)
+    u8 = (den.permute(0, 2, 3, 1).numpy() * 255).round().astype(np.uint8)
+    return dict(latents=x, image=img, u8=u8)
 
 
 def pix2pix_pipeline(unet_sd, vae_sd, ucfg: UNetConfig, vcfg: VAEConfig, image_u8: np.ndarray, ctx: torch.Tensor,

@@ -53,3 +53,19 @@ class EulerDiscreteOracle:
         x0 = x - sigma * eps.to(torch.float32)
         d = (x - x0) / sigma
         return x + d * (sigma_next - sigma)
+
+
+class EulerAncestralOracle(EulerDiscreteOracle):
+    """diffusers 0.29.0 EulerAncestralDiscreteScheduler (schedulers/scheduling_euler_ancestral_discrete.py) as shipped
+    with stabilityai/sdxl-turbo: same sigma tables / scaling as EulerDiscrete; step() moves to sigma_down and adds
+    sigma_up * noise.  [upstream, from memory]  `noise` is passed in (upstream draws randn_tensor(model_output.shape,
+    dtype=model_output.dtype, generator=generator) inside step)."""
+
+    def step(self, eps: torch.Tensor, i: int, x: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+        sigma_from, sigma_to = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        x = x.to(torch.float32)
+        x0 = x - sigma_from * eps.to(torch.float32)
+        sigma_up = (sigma_to ** 2 * (sigma_from ** 2 - sigma_to ** 2) / sigma_from ** 2) ** 0.5
+        sigma_down = (sigma_to ** 2 - sigma_up ** 2) ** 0.5
+        d = (x - x0) / sigma_from
+        return x + d * (sigma_down - sigma_from) + noise.to(torch.float32) * sigma_up

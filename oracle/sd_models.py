@@ -40,12 +40,23 @@ def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     return torch.cat([torch.cos(emb), torch.sin(emb)], dim=-1)
 
 
-def time_embed(sd: SD, cfg: UNetConfig, t: torch.Tensor) -> torch.Tensor:
+def time_embed(sd: SD, cfg: UNetConfig, t: torch.Tensor, added: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+    """time_embedding(time_proj(t)) [+ SDXL get_aug_embed: add_embedding(cat([text_embeds, add_time_proj(time_ids)]))
+    when the model has addition_embed_type='text_time'; added = dict(text_embeds [B, P], time_ids [B, 6])]."""
     emb = timestep_embedding(t, cfg.block_out_channels[0])
     w1 = _w(sd, "time_embedding.linear_1.weight")
     emb = F.linear(emb.to(w1.dtype), w1, _w(sd, "time_embedding.linear_1.bias"))  # sinusoid in fp32, then model dtype
     emb = F.silu(emb)
-    return F.linear(emb, _w(sd, "time_embedding.linear_2.weight"), _w(sd, "time_embedding.linear_2.bias"))
+    emb = F.linear(emb, _w(sd, "time_embedding.linear_2.weight"), _w(sd, "time_embedding.linear_2.bias"))
+    if cfg.addition_embed:
+        if added is None:
+            raise ValueError("this model needs added_cond_kwargs (text_embeds, time_ids)")
+        ids = added["time_ids"].to(torch.float32)
+        tid = timestep_embedding(ids.flatten(), cfg.addition_time_embed_dim).reshape(ids.shape[0], -1)
+        a = torch.cat([added["text_embeds"].to(tid.dtype), tid], dim=-1).to(w1.dtype)
+        a = F.silu(F.linear(a, _w(sd, "add_embedding.linear_1.weight"), _w(sd, "add_embedding.linear_1.bias")))
+        emb = emb + F.linear(a, _w(sd, "add_embedding.linear_2.weight"), _w(sd, "add_embedding.linear_2.bias"))
+    return emb
 
 
 def resnet_block(sd: SD, p: str, x: torch.Tensor, temb: Optional[torch.Tensor], groups: int, eps: float):
@@ -81,22 +92,25 @@ def attention(sd: SD, p: str, x: torch.Tensor, ctx: torch.Tensor, heads: int) ->
 
 
 def transformer2d(sd: SD, p: str, x: torch.Tensor, ctx: torch.Tensor, heads: int, groups: int) -> torch.Tensor:
-    """Transformer2DModel with one BasicTransformerBlock, linear projections, GN eps 1e-6, LN eps 1e-5."""
+    """Transformer2DModel with its BasicTransformerBlocks (one for SD-2.x, `transformer_layers_per_block` for SDXL; the
+    count is read off the state dict), linear projections, GN eps 1e-6, LN eps 1e-5."""
     b, c, hh, ww = x.shape
     res = x
     h = F.group_norm(x, groups, _w(sd, f"{p}.norm.weight"), _w(sd, f"{p}.norm.bias"), 1e-6)
     h = h.permute(0, 2, 3, 1).reshape(b, hh * ww, c)
     h = F.linear(h, _w(sd, f"{p}.proj_in.weight"), _w(sd, f"{p}.proj_in.bias"))
-    t = f"{p}.transformer_blocks.0"
-    n = F.layer_norm(h, (c,), _w(sd, f"{t}.norm1.weight"), _w(sd, f"{t}.norm1.bias"), 1e-5)
-    h = h + attention(sd, f"{t}.attn1", n, n, heads)
-    n = F.layer_norm(h, (c,), _w(sd, f"{t}.norm2.weight"), _w(sd, f"{t}.norm2.bias"), 1e-5)
-    h = h + attention(sd, f"{t}.attn2", n, ctx, heads)
-    n = F.layer_norm(h, (c,), _w(sd, f"{t}.norm3.weight"), _w(sd, f"{t}.norm3.bias"), 1e-5)
-    proj = F.linear(n, _w(sd, f"{t}.ff.net.0.proj.weight"), _w(sd, f"{t}.ff.net.0.proj.bias"))
-    hidden, gate = proj.chunk(2, dim=-1)
-    ff = F.linear(hidden * F.gelu(gate), _w(sd, f"{t}.ff.net.2.weight"), _w(sd, f"{t}.ff.net.2.bias"))
-    h = h + ff
+    k = 0
+    while f"{p}.transformer_blocks.{k}.norm1.weight" in sd:
+        t = f"{p}.transformer_blocks.{k}"
+        n = F.layer_norm(h, (c,), _w(sd, f"{t}.norm1.weight"), _w(sd, f"{t}.norm1.bias"), 1e-5)
+        h = h + attention(sd, f"{t}.attn1", n, n, heads)
+        n = F.layer_norm(h, (c,), _w(sd, f"{t}.norm2.weight"), _w(sd, f"{t}.norm2.bias"), 1e-5)
+        h = h + attention(sd, f"{t}.attn2", n, ctx, heads)
+        n = F.layer_norm(h, (c,), _w(sd, f"{t}.norm3.weight"), _w(sd, f"{t}.norm3.bias"), 1e-5)
+        proj = F.linear(n, _w(sd, f"{t}.ff.net.0.proj.weight"), _w(sd, f"{t}.ff.net.0.proj.bias"))
+        hidden, gate = proj.chunk(2, dim=-1)
+        h = h + F.linear(hidden * F.gelu(gate), _w(sd, f"{t}.ff.net.2.weight"), _w(sd, f"{t}.ff.net.2.bias"))
+        k += 1
     h = F.linear(h, _w(sd, f"{p}.proj_out.weight"), _w(sd, f"{p}.proj_out.bias"))
     return h.reshape(b, hh, ww, c).permute(0, 3, 1, 2) + res
 
@@ -134,9 +148,9 @@ def cond_embedding(sd: SD, cfg: UNetConfig, cond: torch.Tensor) -> torch.Tensor:
 
 
 def controlnet_forward(sd: SD, cfg: UNetConfig, x: torch.Tensor, t: torch.Tensor, ctx: torch.Tensor,
-                       cond: torch.Tensor, conditioning_scale: float = 1.0):
+                       cond: torch.Tensor, conditioning_scale: float = 1.0, added=None):
     """ControlNetModel.forward(guess_mode=False) -> (12 down residuals, mid residual)."""
-    temb = time_embed(sd, cfg, t.expand(x.shape[0]))
+    temb = time_embed(sd, cfg, t.expand(x.shape[0]), added)
     h = F.conv2d(x, _w(sd, "conv_in.weight"), _w(sd, "conv_in.bias"), padding=1)
     h = h + cond_embedding(sd, cfg, cond)
     mid, skips = _encoder(sd, cfg, h, temb, ctx)
@@ -149,10 +163,11 @@ def controlnet_forward(sd: SD, cfg: UNetConfig, x: torch.Tensor, t: torch.Tensor
 
 
 def unet_forward(sd: SD, cfg: UNetConfig, x: torch.Tensor, t: torch.Tensor, ctx: torch.Tensor,
-                 down_residuals: Optional[List[torch.Tensor]] = None, mid_residual: Optional[torch.Tensor] = None):
+                 down_residuals: Optional[List[torch.Tensor]] = None, mid_residual: Optional[torch.Tensor] = None,
+                 added=None):
     """UNet2DConditionModel.forward with ControlNet residuals added to the skips and to the mid-block output."""
     g, eps = cfg.norm_num_groups, cfg.norm_eps
-    temb = time_embed(sd, cfg, t.expand(x.shape[0]))
+    temb = time_embed(sd, cfg, t.expand(x.shape[0]), added)
     h = F.conv2d(x, _w(sd, "conv_in.weight"), _w(sd, "conv_in.bias"), padding=1)
     h, skips = _encoder(sd, cfg, h, temb, ctx)
     if down_residuals is not None:

@@ -48,9 +48,9 @@ def test_schema_mismatch_fails_loudly(dirs):
     with pytest.raises(NotImplementedError):
         ckpt.unet_config_from_json({"use_linear_projection": False})
     with pytest.raises(NotImplementedError):
-        ckpt.scheduler_config_from_json({"_class_name": "EulerAncestralDiscreteScheduler"}) and None or \
+        ckpt.scheduler_config_from_json({"_class_name": "DPMSolverMultistepScheduler"}) and None or \
             __import__("genima_b200.scheduler", fromlist=["x"]).EulerDiscreteSchedule(
-                ckpt.scheduler_config_from_json({"_class_name": "EulerAncestralDiscreteScheduler"}))
+                ckpt.scheduler_config_from_json({"_class_name": "DPMSolverMultistepScheduler"}))
 
 
 def test_controller_snapshot_round_trip(dirs):

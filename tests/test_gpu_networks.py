@@ -475,3 +475,133 @@ def test_pix2pix_agent_plugin_surface(ops):
         outs.append(np.asarray(out[0][0]))
     assert np.array_equal(outs[0], outs[1])        # same seed -> same image (graph replay)
     assert agent.transform_to_half_resolution(out[0][0]).size == (64, 64)
+
+
+# --------------------------------------------------------------------------------------------------- SDXL-ControlNet sibling
+def _sdxl_added(ucfg, g, hw=128):
+    p = ucfg.projection_input_dim - 6 * ucfg.addition_time_embed_dim
+    pooled = torch.randn(1, p, generator=g).half().float()
+    return pooled, dict(text_embeds=pooled, time_ids=torch.tensor([[hw, hw, 0, 0, hw, hw]], dtype=torch.float32))
+
+
+def test_sdxl_unet_controlnet_tiny(ops):
+    """SDXL topology (no attention at level 0, 1 / 2 / 3 transformer blocks per Transformer2D, attention at the last
+    level, text_time added conditioning) through DeviceControlNet + DeviceUNet against the oracle."""
+    from genima_b200.unet import DeviceControlNet, DeviceUNet
+    from oracle import sd_models
+
+    cfg = UNetConfig.sdxl_tiny()
+    usd, csd = W.synth_state_dict(W.unet_shapes(cfg)), W.synth_state_dict(W.controlnet_shapes(cfg), salt=1)
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(1, 4, 16, 16, generator=g).half().float()
+    ctx = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).half().float()
+    cond = torch.randint(0, 256, (1, 128, 128, 3), generator=g, dtype=torch.uint8)
+    pooled, added = _sdxl_added(cfg, g)
+    t = torch.tensor([799.0])
+    down, mid = sd_models.controlnet_forward(csd, cfg, x, t, ctx, cond.float().permute(0, 3, 1, 2) / 255.0, 1.0, added)
+    ref = sd_models.unet_forward(usd, cfg, x, t, ctx, down, mid, added)
+
+    unet, cn = DeviceUNet(ops, usd, cfg), DeviceControlNet(ops, csd, cfg)
+    dadd = dict(text_embeds=pooled.cuda().half(), time_ids=[128.0, 128.0, 0.0, 0.0, 128.0, 128.0])
+    ctx_d = ctx.cuda().half()
+    kv_u = {tr.prefix: tr.project_context(ops, ctx_d) for tr in unet.transformers()}
+    kv_c = {tr.prefix: tr.project_context(ops, ctx_d) for tr in cn.transformers()}
+    tu = unet.temb_rows(unet.resblocks(), unet.time_embedding(799.0, dadd), 1)
+    tc = cn.temb_rows(cn.resblocks(), cn.time_embedding(799.0, dadd), 1)
+    ops.gn_stats_reset()
+    xs = _latent_pad(x)
+    cemb = cn.cond_embedding(ops.u8_to_nhwc(cond.cuda(), cpad=64))
+    cmid, cskips = cn.encode(xs, cemb, tc, kv_c, 77)
+    umid, uskips = unet.encode(xs, tu, kv_u, 77)
+    skips, mid_d = cn.zero_convs(cmid, cskips, uskips, umid, 1.0)
+    eps = torch.zeros_like(xs)
+    unet.decode(mid_d, skips, tu, kv_u, 77, eps)
+    check("SDXL-tiny ControlNet + U-Net eps", eps[..., :4], nhwc(ref), NET_TOL)
+    with pytest.raises(ValueError):
+        unet.time_embedding(799.0, None)             # an SDXL U-Net cannot run without its added conditioning
+
+
+def test_clip_text_penultimate_and_pooled(ops):
+    """hidden_states[-2] + projected EOT embedding in one pass (SDXL encode_prompt)."""
+    from genima_b200.text_encoder import DeviceCLIPText
+    from oracle.clip_text import clip_text_forward
+
+    cfg = CLIPTextConfig.tiny(projection_dim=64)
+    sd = W.synth_state_dict(W.clip_text_shapes(cfg), salt=4)
+    ids = torch.randint(1, 900, (2, 77), generator=torch.Generator().manual_seed(5))
+    ids[:, 0], ids[0, 9], ids[1, 30] = 998, 999, 999
+    ref_h, ref_p = clip_text_forward(sd, cfg, ids, penultimate=True)
+    last_h, _ = clip_text_forward(sd, cfg, ids)
+    assert not torch.allclose(ref_h, last_h)
+    h, p = DeviceCLIPText(ops, sd, cfg)(ids.cuda(), penultimate=True)
+    check("CLIP penultimate hidden state", h, ref_h, NET_TOL)
+    check("CLIP pooled projection", p, ref_p, NET_TOL)
+
+
+def _tiny_sdxl(ops, use_cuda_graph=False):
+    import dataclasses
+
+    from genima_b200.pipeline import B200SDXLControlNetPipeline
+
+    ucfg, vcfg = UNetConfig.sdxl_tiny(), dataclasses.replace(VAEConfig.tiny(), scaling_factor=0.13025)
+    usd = W.synth_state_dict(W.unet_shapes(ucfg))
+    csd = W.synth_state_dict(W.controlnet_shapes(ucfg), salt=1)
+    vsd = W.synth_state_dict(W.vae_decoder_shapes(vcfg), salt=2)
+    pipe = B200SDXLControlNetPipeline(ops, usd, csd, vsd, None, None, ucfg, vcfg, use_cuda_graph=use_cuda_graph)
+    return pipe, (usd, csd, vsd, ucfg, vcfg)
+
+
+@pytest.mark.parametrize("n_steps", [1, 4])
+def test_sdxl_pipeline_tiny_vs_oracle(ops, n_steps):
+    """StableDiffusionXLControlNetPipeline as controller/agent/sdxl_controlnet_agent.py:66-75 calls it: Euler-ancestral
+    steps whose noise comes from the caller's generator (same draws, same order as diffusers' scheduler.step)."""
+    from oracle.pipeline import sdxl_controlnet_pipeline
+
+    pipe, (usd, csd, vsd, ucfg, vcfg) = _tiny_sdxl(ops)
+    g = torch.Generator().manual_seed(41)
+    ctx = torch.randn(1, 77, ucfg.cross_attention_dim, generator=g).half().float()
+    cond = torch.randint(0, 256, (1, 128, 128, 3), generator=g, dtype=torch.uint8)
+    pooled, _ = _sdxl_added(ucfg, g)
+    # the draws the pipeline will make: latents first, then one noise tensor per step (fp16, on the generator's device)
+    gen = torch.Generator().manual_seed(2)
+    lat = torch.randn(1, 4, 16, 16, generator=gen, dtype=torch.float16)
+    noises = [torch.randn(1, 4, 16, 16, generator=gen, dtype=torch.float16).float() for _ in range(n_steps)]
+    ref = sdxl_controlnet_pipeline(usd, csd, vsd, ucfg, vcfg, cond.numpy(), ctx, pooled, lat.float(), noises, n_steps)
+    kw = dict(prompt_embeds=ctx, pooled_prompt_embeds=pooled, image=cond, num_inference_steps=n_steps, guidance_scale=0.0)
+    out = pipe(generator=torch.Generator().manual_seed(2), output_type="latent", **kw).images
+    check(f"SDXL latents after {n_steps} ancestral step(s)", out, ref["latents"], LOOP_TOL)
+    img = pipe(generator=[torch.Generator().manual_seed(2)], output_type="pt", **kw).images
+    check("SDXL decoded image", img, (ref["image"] / 2 + 0.5).clamp(0, 1), LOOP_TOL)
+    # CUDA graph replay == eager, and a second call on the same generator continues its stream (different image)
+    pipe.use_cuda_graph = True
+    gen2 = torch.Generator().manual_seed(2)
+    a = pipe(generator=gen2, output_type="u8", **kw).images.cpu().clone()
+    b = pipe(generator=gen2, output_type="u8", **kw).images.cpu().clone()
+    pipe.use_cuda_graph = False
+    c = pipe(generator=torch.Generator().manual_seed(2), output_type="u8", **kw).images.cpu()
+    assert torch.equal(a, c) and not torch.equal(a, b)
+    with pytest.raises(ValueError):
+        pipe(prompt_embeds=ctx, image=cond, num_inference_steps=1, guidance_scale=0.0)     # pooled embeds missing
+    with pytest.raises(NotImplementedError):
+        pipe(guidance_scale=5.0, **{k: v for k, v in kw.items() if k != "guidance_scale"})
+
+
+def test_sdxl_agent_plugin_surface(ops):
+    """B200SDXLControlNetAgent(eval_cfg).infer(...) with token ids for both tokenizers, TAESDXL decoder option."""
+    from PIL import Image
+
+    from genima_b200.agents import B200SDXLControlNetAgent
+
+    agent = B200SDXLControlNetAgent(dict(synthetic_weights="sdxl-tiny", autoencoder="madebyollin/taesdxl",
+                                         image_resolution=128, device="cuda:0", use_cuda_graph=True), ops=ops)
+    g = torch.Generator().manual_seed(0)
+    tile = torch.randint(0, 256, (128, 128, 3), generator=g, dtype=torch.uint8).numpy()
+    ids = torch.randint(1, 900, (1, 77), generator=g)
+    ids[0, 0], ids[0, 12] = 998, 999
+    outs = []
+    for _ in range(2):
+        out = agent.infer(images=[Image.fromarray(tile)], prompts=ids, negative_prompts=None, num_inference_steps=2,
+                          guidance_scale=0.0, generator=[torch.Generator(device="cuda").manual_seed(2)])
+        assert out[0][0].size == (128, 128)
+        outs.append(np.asarray(out[0][0]))
+    assert np.array_equal(outs[0], outs[1])

@@ -32,9 +32,30 @@ def test_sigma_max_and_init_noise_sigma():
 
 def test_unknown_scheduler_classes_fail_loudly():
     with pytest.raises(NotImplementedError):
-        EulerDiscreteSchedule(SchedulerConfig(class_name="EulerAncestralDiscreteScheduler"))
+        EulerDiscreteSchedule(SchedulerConfig(class_name="DPMSolverMultistepScheduler"))
     with pytest.raises(NotImplementedError):
         EulerDiscreteSchedule(SchedulerConfig(prediction_type="v_prediction"))
+
+
+def test_euler_ancestral_tables_and_step():
+    """EulerAncestralDiscreteScheduler (sdxl-turbo): sigma_up^2 + sigma_down^2 = sigma_to^2, no noise on the last step,
+    and with zero noise the step is the plain Euler move to sigma_down."""
+    from oracle.scheduler import EulerAncestralOracle
+
+    sch = EulerDiscreteSchedule(SchedulerConfig(class_name="EulerAncestralDiscreteScheduler"))
+    assert sch.ancestral
+    ts, sig = sch.set_timesteps(4)
+    o = EulerAncestralOracle()
+    ts_o, sig_o = o.set_timesteps(4)
+    assert np.array_equal(ts, ts_o) and np.array_equal(sig, sig_o) and sch.init_noise_sigma == o.init_noise_sigma
+    g = torch.Generator().manual_seed(0)
+    x, eps, noise = (torch.randn(1, 4, 8, 8, generator=g) for _ in range(3))
+    for i in range(4):
+        up, down = sch.ancestral_sigmas(i)
+        assert abs(up * up + down * down - float(sig[i + 1]) ** 2) < 1e-5 * max(1.0, float(sig[i + 1]) ** 2)
+        want = x + eps * (down - float(sig[i])) + noise * up
+        assert torch.allclose(o.step(eps, i, x, noise), want, rtol=1e-5, atol=1e-5)
+    assert sch.ancestral_sigmas(3) == (0.0, 0.0)
 
 
 def test_euler_step_equals_ddim_eta0_update():

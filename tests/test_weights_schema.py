@@ -111,3 +111,20 @@ def test_vae_encoder_schema_and_oracle():
     x2[..., -1, :] += 0.5                          # the last row is inside the receptive field (bottom padding only)
     assert not torch.equal(sd_models.vae_encode_mean(sd, cfg, x2), z)
     assert torch.equal(sd_models.vae_encode_mean(sd, cfg, x), z)
+
+
+def test_sdxl_schemas_match_published_sizes():
+    """SDXL U-Net 2,567,463,684 parameters (published), CLIP ViT-L text tower 123,060,480, OpenCLIP bigG text tower with
+    projection 694,659,840 — the topology restated from memory reproduces all three exactly."""
+    import math
+
+    from genima_b200.configs import CLIPTextConfig, UNetConfig
+
+    n = lambda shapes: sum(math.prod(v) for v in shapes.values())  # noqa: E731
+    assert n(W.unet_shapes(UNetConfig.sdxl())) == 2_567_463_684
+    assert n(W.clip_text_shapes(CLIPTextConfig.sdxl_clip_l())) == 123_060_480
+    assert n(W.clip_text_shapes(CLIPTextConfig.sdxl_open_clip_bigg())) == 694_659_840
+    cn = W.controlnet_shapes(UNetConfig.sdxl())
+    assert "add_embedding.linear_1.weight" in cn and cn["add_embedding.linear_1.weight"] == (1280, 2816)
+    assert "down_blocks.2.attentions.1.transformer_blocks.9.ff.net.2.weight" in cn
+    assert "down_blocks.0.attentions.0.norm.weight" not in cn          # level 0 is a plain DownBlock2D
