@@ -216,8 +216,11 @@ def load_controller_snapshot(path: str, cfg: ACTConfig = ACTConfig(), prefix: st
     return sd
 
 
-def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcfg: CLIPTextConfig, acfg: ACTConfig):
-    """Writes seeded synthetic weights in the reference's on-disk layouts (for loader tests and offline demos)."""
+def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcfg: CLIPTextConfig, acfg: ACTConfig,
+                               text2_cfg: Optional[CLIPTextConfig] = None):
+    """Writes seeded synthetic weights in the reference's on-disk layouts (for loader tests and offline demos).  With an
+    SDXL `ucfg` (addition_embed) and `text2_cfg` the snapshot has the stabilityai/sdxl-turbo layout: text_encoder_2/ and an
+    EulerAncestralDiscreteScheduler."""
     from safetensors.torch import save_file
 
     sd_ckpt = os.path.join(root, "sd-turbo")
@@ -230,6 +233,10 @@ def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcf
                  attention_head_dim=heads, down_block_types=down, cross_attention_dim=ucfg.cross_attention_dim,
                  norm_num_groups=ucfg.norm_num_groups, norm_eps=ucfg.norm_eps, use_linear_projection=True,
                  sample_size=ucfg.sample_size)
+    if ucfg.addition_embed:
+        ujson.update(addition_embed_type="text_time", addition_time_embed_dim=ucfg.addition_time_embed_dim,
+                     projection_class_embeddings_input_dim=ucfg.projection_input_dim,
+                     transformer_layers_per_block=list(ucfg.transformer_layers))
     parts = [
         (os.path.join(sd_ckpt, "unet"), "diffusion_pytorch_model.fp16.safetensors", W.unet_shapes(ucfg), 0, ujson),
         (os.path.join(sd_ckpt, "vae"), "diffusion_pytorch_model.fp16.safetensors",
@@ -247,6 +254,15 @@ def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcf
          W.controlnet_shapes(ucfg), 1,
          dict(ujson, _class_name="ControlNetModel",
               conditioning_embedding_out_channels=list(ucfg.cond_embed_channels))),
+    ]
+    if text2_cfg is not None:
+        parts.append((os.path.join(sd_ckpt, "text_encoder_2"), "model.fp16.safetensors", W.clip_text_shapes(text2_cfg), 4,
+                      dict(architectures=["CLIPTextModelWithProjection"], vocab_size=text2_cfg.vocab_size,
+                           hidden_size=text2_cfg.hidden_size, intermediate_size=text2_cfg.intermediate_size,
+                           num_hidden_layers=text2_cfg.num_layers, num_attention_heads=text2_cfg.num_heads,
+                           max_position_embeddings=text2_cfg.max_positions, hidden_act=text2_cfg.act,
+                           layer_norm_eps=text2_cfg.eps, projection_dim=text2_cfg.projection_dim)))
+    parts += [
         # InstructPix2Pix fine-tune (diffusion/train_instruct_pix2pix_genima.py output): 8-channel conv_in
         (os.path.join(root, "pix2pix_ckpt", "checkpoint-200", "unet"), "diffusion_pytorch_model.safetensors",
          W.unet_shapes(dataclasses.replace(ucfg, in_channels=2 * vcfg.latent_channels)), 5,
@@ -259,7 +275,8 @@ def save_synthetic_checkpoints(root: str, ucfg: UNetConfig, vcfg: VAEConfig, tcf
             json.dump(cfg, f)
     os.makedirs(os.path.join(sd_ckpt, "scheduler"), exist_ok=True)
     with open(os.path.join(sd_ckpt, "scheduler", "scheduler_config.json"), "w") as f:
-        json.dump(dict(_class_name="EulerDiscreteScheduler", num_train_timesteps=1000, beta_start=0.00085,
+        json.dump(dict(_class_name="EulerAncestralDiscreteScheduler" if text2_cfg is not None else "EulerDiscreteScheduler",
+                       num_train_timesteps=1000, beta_start=0.00085,
                        beta_end=0.012, beta_schedule="scaled_linear", timestep_spacing="trailing",
                        prediction_type="epsilon"), f)
     os.makedirs(ctl, exist_ok=True)

@@ -76,3 +76,23 @@ def test_pix2pix_checkpoint_round_trip(dirs):
     assert all(torch.equal(out["vae"][k], v) for k, v in enc.items())
     with pytest.raises(ValueError):               # a 4-channel U-Net is not an InstructPix2Pix U-Net
         ckpt.load_sd_pix2pix(dirs["sd_ckpt"], os.path.join(dirs["sd_ckpt"]))
+
+
+def test_sdxl_snapshot_round_trip(tmp_path):
+    """controller/agent/sdxl_controlnet_agent.py:19-42 layout: SDXL U-Net / ControlNet config fields, text_encoder_2 with
+    projection, Euler-ancestral scheduler."""
+    from genima_b200.scheduler import EulerDiscreteSchedule
+
+    ucfg, t2 = UNetConfig.sdxl_tiny(), CLIPTextConfig.tiny(projection_dim=64)
+    d = ckpt.save_synthetic_checkpoints(str(tmp_path), ucfg, VAEConfig.tiny(), CLIPTextConfig.tiny(), ACTConfig.tiny(),
+                                        text2_cfg=t2)
+    out = ckpt.load_sdxl(d["sd_ckpt"], d["diffusion_ckpt"])
+    assert out["unet_cfg"] == ucfg and out["text2_cfg"] == t2 and out["text_cfg"].projection_dim == 0
+    assert EulerDiscreteSchedule(out["scheduler_cfg"]).ancestral
+    want = W.synth_state_dict(W.clip_text_shapes(t2), salt=4)
+    assert all(torch.equal(out["text2"][k], v) for k, v in want.items())
+    assert "add_embedding.linear_1.weight" in out["controlnet"]
+    with pytest.raises(ValueError):                # an SD-2.x snapshot is not an SDXL snapshot
+        d2 = ckpt.save_synthetic_checkpoints(str(tmp_path / "sd2"), UNetConfig.tiny(), VAEConfig.tiny(),
+                                             CLIPTextConfig.tiny(), ACTConfig.tiny())
+        ckpt.load_sdxl(d2["sd_ckpt"], d2["diffusion_ckpt"])
