@@ -440,8 +440,25 @@ def make_roofline(classes, step_ms):
     g_fl = classes["linear"]["flops"] + classes["conv"]["flops"]
     tot_ms = sum(c["ms"] for c in classes.values())
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    # DRAM bytes the GEMM launches of one step really moved, from the committed ncu capture of the same step (the
+    # default workload only: other presets / autoencoders have no capture)
+    traffic = traffic_step = traffic_src = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1i_dram_traffic.json")) as f:
+            cap = json.load(f)
+        k = cap["kernels"]["gn::gemm_tc_kernel"]
+        if k["launches"] == classes["linear"]["calls"] + classes["conv"]["calls"]:
+            traffic = k["dram_bytes_per_launch"]
+            traffic_step = k["dram_read_bytes_per_step"] + k["dram_write_bytes_per_step"]
+            traffic_src = ("profiles/r1i_dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the "
+                           f"{k['launches']} gemm_tc_kernel launches of one agent step (ncu, cold cache per launch), "
+                           "average per launch; algorithmic bytes of the same launches: "
+                           f"{(classes['linear']['bytes'] + classes['conv']['bytes']) / 1e9:.2f} GB per step")
+    except Exception:
+        pass
     return {"bound": "tensor", "kernel": "gemm_tc_kernel (gn_conv2d implicit GEMM + gn_linear)", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": src,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_bytes_per_step": traffic_step, "traffic_source": traffic_src, "peak_source": src,
             # the same FLOPs over the kernel's proportional share of the graph-replayed step (PDL and the two-stream overlap
             # hide most of the ~5 us per launch that an event pair around a single eager launch includes)
             "achieved_graph_attributed": (g_fl / (step_ms * 1e-3 * g_ms / tot_ms) / 1e12) if g_ms > 0 and tot_ms else None,
