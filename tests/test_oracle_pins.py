@@ -1,5 +1,6 @@
 """Pins the CPU oracle (oracle/) against independent implementations that ARE available offline:
-  * CLIP text towers      vs transformers.CLIPTextModel (the class the reference's diffusers pipeline instantiates)
+  * CLIP text towers      vs transformers.CLIPTextModel (the class the reference's diffusers pipeline instantiates) and
+                          transformers.CLIPTextModelWithProjection (SDXL text_encoder_2: hidden_states[-2], text_embeds)
   * ResNet-18 trunk       vs torchvision.models.resnet18 with FrozenBatchNorm2d (FiLM projections zeroed -> identity)
   * multi-head attention  vs torch.nn.MultiheadAttention (what the DETR/ACT transformer layers wrap)
   * DETR encoder layer    vs torch.nn.TransformerEncoderLayer(norm_first=False) with zero positional input
@@ -45,6 +46,37 @@ def test_clip_text_oracle_matches_transformers(act):
         ref = hf(input_ids=ids).last_hidden_state
     out, _ = clip_text_forward(sd, cfg, ids)
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-5), float((out - ref).abs().max())
+
+
+def test_sdxl_text_conditioning_matches_transformers_with_projection():
+    """What diffusers' SDXL encode_prompt reads off text_encoder_2 (transformers.CLIPTextModelWithProjection with
+    output_hidden_states=True): hidden_states[-2] and text_embeds — the oracle's penultimate / pooled outputs."""
+    from transformers import CLIPTextConfig as HFConfig
+    from transformers import CLIPTextModelWithProjection
+
+    from oracle.clip_text import clip_text_forward
+
+    cfg = CLIPTextConfig(vocab_size=1000, hidden_size=128, intermediate_size=256, num_layers=4, num_heads=2, act="gelu",
+                         projection_dim=64)
+    sd = {k: v.float() for k, v in W.synth_state_dict(W.clip_text_shapes(cfg), salt=4).items()}
+    hf = CLIPTextModelWithProjection(HFConfig(
+        vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=4, num_attention_heads=2,
+        max_position_embeddings=77, hidden_act="gelu", projection_dim=64, eos_token_id=999, bos_token_id=998,
+        pad_token_id=0)).eval()
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in m for m in missing)
+    ids = torch.zeros(2, 77, dtype=torch.int64)
+    g = torch.Generator().manual_seed(6)
+    for b in range(2):
+        ids[b, 0] = 998
+        ids[b, 1:12 + b] = torch.randint(1, 990, (11 + b,), generator=g)
+        ids[b, 12 + b] = 999
+    with torch.no_grad():
+        ref = hf(input_ids=ids, output_hidden_states=True)
+    pen, pooled = clip_text_forward(sd, cfg, ids, penultimate=True)
+    assert torch.allclose(pen, ref.hidden_states[-2], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(pooled, ref.text_embeds, rtol=1e-4, atol=1e-5)
+    assert not torch.allclose(pen, ref.last_hidden_state, rtol=1e-2, atol=1e-3)
 
 
 def test_clip_pooled_projection_takes_eot_row():
