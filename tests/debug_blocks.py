@@ -1,5 +1,5 @@
 """GPU debugging aid: runs every block of the (tiny or full) ControlNet / U-Net in isolation, feeding each device block
-the oracle's input for that block, and prints the normalised error per block.  Usage: python tools/debug_blocks.py [full]"""
+the oracle's input for that block, and prints the normalised error per block.  Usage: python tests/debug_blocks.py [full]  (lives under tests/: it executes the oracle)"""
 import os
 import sys
 

@@ -66,8 +66,8 @@ class _HalfSD(dict):
         def __getattr__(self, n):
             return getattr(self.t, n)
 
-    def __init__(self, sd):
-        super().__init__({k: _HalfSD._T(v.to("cuda", torch.float16)) for k, v in sd.items()})
+    def __init__(self, sd, dtype=torch.float16):
+        super().__init__({k: _HalfSD._T(v.to("cuda", dtype)) for k, v in sd.items()})
 
 
 def _latent_pad(x_nchw, cpad=8):
@@ -519,6 +519,55 @@ def test_sdxl_unet_controlnet_tiny(ops):
     check("SDXL-tiny ControlNet + U-Net eps", eps[..., :4], nhwc(ref), NET_TOL)
     with pytest.raises(ValueError):
         unet.time_embedding(799.0, None)             # an SDXL U-Net cannot run without its added conditioning
+
+
+def test_sdxl_unet_controlnet_full_size_one_step(ops):
+    """The real SDXL topology (2.57 B + 1.25 B parameters, synthetic weights), one 512 x 512 tile, t = 999.  The fp32
+    oracle graph (oracle/sd_models.py) is executed ON THE GPU here (TF32 off): on the host cores one evaluation of this
+    model takes minutes.  Stock torch fp16 running the same graph is the yardstick, as in the other network tests."""
+    from genima_b200.unet import DeviceControlNet, DeviceUNet
+    from oracle import sd_models
+
+    cfg = UNetConfig.sdxl()
+    usd, csd = W.synth_state_dict(W.unet_shapes(cfg)), W.synth_state_dict(W.controlnet_shapes(cfg), salt=1)
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(1, 4, 64, 64, generator=g).half().float()
+    ctx = torch.randn(1, 77, cfg.cross_attention_dim, generator=g).half().float()
+    cond = torch.randint(0, 256, (1, 512, 512, 3), generator=g, dtype=torch.uint8)
+    pooled, _ = _sdxl_added(cfg, g, 512)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+
+    def graph_on_gpu(dtype):
+        added = dict(text_embeds=pooled.to("cuda", dtype),
+                     time_ids=torch.tensor([[512.0, 512, 0, 0, 512, 512]], device="cuda"))
+        u, c = _HalfSD(usd, dtype), _HalfSD(csd, dtype)
+        t = torch.tensor([999.0], device="cuda")
+        cc = (cond.float() / 255.0).permute(0, 3, 1, 2).to("cuda", dtype)
+        down, mid = sd_models.controlnet_forward(c, cfg, x.to("cuda", dtype), t, ctx.to("cuda", dtype), cc, 1.0, added)
+        return sd_models.unet_forward(u, cfg, x.to("cuda", dtype), t, ctx.to("cuda", dtype), down, mid, added).float().cpu()
+
+    try:
+        with torch.no_grad():
+            ref, stock = graph_on_gpu(torch.float32), graph_on_gpu(torch.float16)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    torch.cuda.empty_cache()
+    unet, cn = DeviceUNet(ops, usd, cfg), DeviceControlNet(ops, csd, cfg)
+    dadd = dict(text_embeds=pooled.cuda().half(), time_ids=[512.0, 512.0, 0.0, 0.0, 512.0, 512.0])
+    ctx_d = ctx.cuda().half()
+    kv_u = {tr.prefix: tr.project_context(ops, ctx_d) for tr in unet.transformers()}
+    kv_c = {tr.prefix: tr.project_context(ops, ctx_d) for tr in cn.transformers()}
+    tu = unet.temb_rows(unet.resblocks(), unet.time_embedding(999.0, dadd), 1)
+    tc = cn.temb_rows(cn.resblocks(), cn.time_embedding(999.0, dadd), 1)
+    ops.gn_stats_reset()
+    xs = _latent_pad(x)
+    cmid, cskips = cn.encode(xs, cn.cond_embedding(ops.u8_to_nhwc(cond.cuda(), cpad=64)), tc, kv_c, 77)
+    umid, uskips = unet.encode(xs, tu, kv_u, 77)
+    skips, mid_d = cn.zero_convs(cmid, cskips, uskips, umid, 1.0)
+    eps = torch.zeros_like(xs)
+    unet.decode(mid_d, skips, tu, kv_u, 77, eps)
+    check("full-size SDXL ControlNet + U-Net eps", eps[..., :4], nhwc(ref), NET_TOL, nhwc(stock))
 
 
 def test_clip_text_penultimate_and_pooled(ops):
