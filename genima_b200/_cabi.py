@@ -64,6 +64,7 @@ SIGNATURES = {
     "gn_set_staged_epilogue": (_i, [_vp, _i]),
     "gn_set_autotune": (_i, [_vp, _i]),
     "gn_set_gemm_occupancy": (_i, [_vp, _i]),
+    "gn_set_attention_kv_split": (_i, [_vp, _i]),
     "gn_set_gemm_multicast": (_i, [_vp, _i, _i]),
     "gn_set_conv_halo": (_i, [_vp, _i, _i]),
     "gn_set_gemm_trace": (_i, [_vp, _vp]),

@@ -176,6 +176,12 @@ int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm) {
   return GN_OK;
 }
 
+int gn_set_attention_kv_split(gn_handle* h, int mode) {
+  if (!h || mode < 0 || mode > 2) return GN_ERR_INVALID;
+  h->attn_kv_split = mode;
+  return GN_OK;
+}
+
 int gn_set_pdl(gn_handle* h, int enable) {
   if (!h) return GN_ERR_INVALID;
   h->pdl = enable != 0;

@@ -30,8 +30,12 @@ constexpr int AT_STAGES = 2;
 constexpr int AT_SM_WARPS = 8;
 constexpr int AT_THREADS = 64 + 32 * AT_SM_WARPS;
 constexpr int AT_TMEM_COLS = 512;
+// KV-split combine buffer (written by the peer CTA of a 2-CTA cluster through distributed shared memory): the partial
+// O tile as [16 float4 columns][128 rows] (conflict-free for one row per lane) + the row maxima and row sums
+constexpr int AT_COMB_BYTES = 128 * 64 * 4 + 2 * 128 * 4;
 constexpr int AT_SMEM_BYTES = AT_TILE_BYTES /*Q*/ + 2 * AT_P_BYTES /*P, double-buffered*/ +
-                             2 * AT_STAGES * AT_TILE_BYTES /*K, V*/ + 4 * 128 * 4 /*row exchange*/ + 256 + 1024;
+                             2 * AT_STAGES * AT_TILE_BYTES /*K, V*/ + AT_COMB_BYTES + 4 * 128 * 4 /*row exchange*/ +
+                             256 + 1024;
 constexpr float AT_RESCALE_LOG2 = 8.0f;
 
 struct AttnParams {
@@ -40,6 +44,10 @@ struct AttnParams {
   int64_t ldo;
   int Tq, Tk;
   float scale_log2;  // softmax scale * log2(e)
+  // 1 or 2.  2: the launch is a 2-CTA cluster along grid.z; CTA rank r handles KV blocks [r * nblk / 2, (r + 1) * nblk / 2)
+  // and rank 1 hands its partial (O, m, l) to rank 0 through distributed shared memory.  Fixes the wave quantisation of
+  // the level-0 self-attention (160 CTAs of 32 KV blocks on 148 SMs = 2 waves -> 320 CTAs of 16 blocks = 1.5 waves).
+  int kv_splits;
 };
 
 // 2^x for x <= ~8 without the SFU: n = round(x) through the 1.5 * 2^23 magic constant (its low mantissa bits then hold n),
@@ -55,6 +63,18 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
 }
 
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float a) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+
 __device__ __forceinline__ void at_bar_sync_softmax() {
   asm volatile("bar.sync 2, %0;" ::"n"(32 * AT_SM_WARPS) : "memory");
 }
@@ -67,7 +87,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
   uint8_t* sP = sQ + AT_TILE_BYTES;
   uint8_t* sK = sP + 2 * AT_P_BYTES;
   uint8_t* sV = sK + AT_STAGES * AT_TILE_BYTES;
-  float* s_xchg = reinterpret_cast<float*>(sV + AT_STAGES * AT_TILE_BYTES);  // [2 parities][2 halves][128 rows]
+  float* s_comb = reinterpret_cast<float*>(sV + AT_STAGES * AT_TILE_BYTES);  // KV-split partial of the peer CTA
+  float* s_xchg = s_comb + AT_COMB_BYTES / 4;                                // [2 parities][2 halves][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_xchg + 4 * 128);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;    // [2]
@@ -84,8 +105,15 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_BQ;
   const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int nblk = (p.Tk + AT_BKV - 1) / AT_BKV;
+  const int splits = p.kv_splits;
+  const int rank = splits > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int batch = blockIdx.z / splits;
+  const int nblk_all = (p.Tk + AT_BKV - 1) / AT_BKV;
+  const int kb0 = rank * nblk_all / splits;                  // first KV block of this CTA
+  const int nblk = (rank + 1) * nblk_all / splits - kb0;     // >= 1: the host only splits when nblk_all >= splits
+  // every CTA of the cluster must be running before its shared memory is written remotely: arrive now, wait just before
+  // the hand-over at the end
+  if (splits > 1) cluster_arrive();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -123,10 +151,10 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
         const uint32_t ph = ((i >> 1) & 1) ^ 1;
         mbar_wait(&k_empty[st], ph);
         mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
-        tma_load_2d(sK + st * AT_TILE_BYTES, &p.tmK, &k_full[st], head * AT_D, batch * p.Tk + i * AT_BKV);
+        tma_load_2d(sK + st * AT_TILE_BYTES, &p.tmK, &k_full[st], head * AT_D, batch * p.Tk + (kb0 + i) * AT_BKV);
         mbar_wait(&v_empty[st], ph);
         mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
-        tma_load_2d(sV + st * AT_TILE_BYTES, &p.tmV, &v_full[st], head * AT_D, batch * p.Tk + i * AT_BKV);
+        tma_load_2d(sV + st * AT_TILE_BYTES, &p.tmV, &v_full[st], head * AT_D, batch * p.Tk + (kb0 + i) * AT_BKV);
       }
     }
   } else if (warp == 1) {
@@ -199,7 +227,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
       }
       tc_fence_before();
       mbar_arrive(&s_free[st]);  // the scores are in registers: QK^T of block i+2 may overwrite this buffer
-      const int nvalid = p.Tk - i * AT_BKV - half * 64;  // valid columns of this half (may be <= 0)
+      const int nvalid = p.Tk - (kb0 + i) * AT_BKV - half * 64;  // valid columns of this half (may be <= 0)
       float mx = -INFINITY;
       if (nvalid >= 64) {  // (warp-uniform) every column is a real key: no masking
 #pragma unroll
@@ -279,14 +307,48 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
     float* xl = s_xchg + (nblk & 1) * 256;
     xl[half * 128 + row] = l_run;
     at_bar_sync_softmax();
-    const float l_tot = l_run + xl[(half ^ 1) * 128 + row];
+    float l_tot = l_run + xl[(half ^ 1) * 128 + row];
     mbar_wait(&pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
     tc_fence_after();
     uint32_t o[32];
     tmem_ld_x32(tmem_o + lane_sel + half * 32, o);
     tmem_ld_wait();
     tc_fence_before();
-    if (q0 + row < p.Tq) {
+    if (splits > 1) {
+      // ---- KV split: rank 1 -> rank 0 hand-over of (O, m, l) in the units of its own running maximum, then rank 0 merges
+      // in a fixed order (deterministic).  Buffer layout: float4 column q4 (0..15) of row r at (q4 * 128 + r) * 16 bytes.
+      cluster_wait();                                   // (phase 1) the peer CTA is running: its shared memory exists
+      if (rank == 1) {
+        const uint32_t base = mapa_cluster(smem_u32(s_comb), 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_cluster_v4(base + (((half * 8 + j) * 128 + row) << 4), __uint_as_float(o[4 * j]),
+                        __uint_as_float(o[4 * j + 1]), __uint_as_float(o[4 * j + 2]), __uint_as_float(o[4 * j + 3]));
+        if (half == 0) {
+          st_cluster_f32(base + 128 * 64 * 4 + row * 4, m_used);
+          st_cluster_f32(base + 128 * 64 * 4 + 512 + row * 4, l_tot);
+        }
+      }
+      cluster_arrive();                                 // (phase 2) release: the partial is written ...
+      cluster_wait();                                   // ... acquire: and visible to rank 0
+      if (rank == 0) {
+        const float m1 = s_comb[128 * 16 * 4 + row];
+        const float l1 = s_comb[128 * 16 * 4 + 128 + row];
+        const float m = fmaxf(m_used, m1);
+        const float a0 = ex2_approx((m_used - m) * c), a1 = ex2_approx((m1 - m) * c);   // -inf -> 0
+        const float4* pc = reinterpret_cast<const float4*>(s_comb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = pc[(half * 8 + j) * 128 + row];
+          o[4 * j] = __float_as_uint(__uint_as_float(o[4 * j]) * a0 + w.x * a1);
+          o[4 * j + 1] = __float_as_uint(__uint_as_float(o[4 * j + 1]) * a0 + w.y * a1);
+          o[4 * j + 2] = __float_as_uint(__uint_as_float(o[4 * j + 2]) * a0 + w.z * a1);
+          o[4 * j + 3] = __float_as_uint(__uint_as_float(o[4 * j + 3]) * a0 + w.w * a1);
+        }
+        l_tot = l_tot * a0 + l1 * a1;
+      }
+    }
+    if (rank == 0 && q0 + row < p.Tq) {
       const float inv = 1.0f / l_tot;
       __half* op = p.out + ((int64_t)batch * p.Tq + q0 + row) * p.ldo + head * AT_D + half * 32;
 #pragma unroll
@@ -299,6 +361,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
         *reinterpret_cast<uint4*>(op + j) = w;
       }
     }
+  }
+  if (splits > 1 && warp < 2) {  // the producer and MMA warps take part in both cluster barrier phases as well
+    __syncwarp();
+    cluster_wait();
+    cluster_arrive();
+    cluster_wait();
   }
   __syncthreads();
   if (warp == 1) {
@@ -414,13 +482,25 @@ extern "C" int gn_attention(gn_handle* h, const void* q, int64_t ldq, const void
   p.Tq = Tq;
   p.Tk = Tk;
   p.scale_log2 = scale * 1.4426950408889634f;
+  // KV split across a 2-CTA cluster when it shortens the critical path: cost in KV blocks = waves x blocks per CTA
+  // (+ half a block for the hand-over), and only for a clear (15 %) win: clusters schedule less freely than single CTAs
+  // (measured: 160 CTAs x 32 blocks 78 -> 68 us, 40 CTAs x 2 blocks 18 -> 14.5 us, 640 CTAs x 32 blocks 194 -> 202 us)
+  const int nblk = ceil_div(Tk, AT_BKV);
+  const int ctas = ceil_div(Tq, AT_BQ) * heads * B;
+  const int sms = h->num_sms > 0 ? h->num_sms : 148;
+  p.kv_splits = 1;
+  if (nblk >= 2 && h->attn_kv_split != 0) {
+    const double c1 = (double)ceil_div(ctas, sms) * nblk;
+    const double c2 = (double)ceil_div(2 * ctas, sms) * ceil_div(nblk, 2) + 0.5;
+    if (h->attn_kv_split == 2 || c2 < 0.85 * c1) p.kv_splits = 2;
+  }
   if (!h->attn_attr_set) {
     GN_CHECK_CUDA(h, cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
     h->attn_attr_set = true;
   }
-  dim3 grid(ceil_div(Tq, AT_BQ), heads, B);
+  dim3 grid(ceil_div(Tq, AT_BQ), heads, B * p.kv_splits);
   GN_CHECK_CUDA(h, launch_ex(h, attn_tc_kernel, grid, dim3(AT_THREADS, 1, 1), AT_SMEM_BYTES,
-                              static_cast<cudaStream_t>(stream), 1, p));
+                              static_cast<cudaStream_t>(stream), p.kv_splits, p));
   h->launches++;
   return GN_OK;
 }

@@ -49,6 +49,7 @@ struct gn_handle {
   void* stats_scratch = nullptr;  // GroupNorm: grid-barrier words (first 256 B, zero-initialised) + per-CTA partials
   int64_t stats_scratch_bytes = 0;
   bool attn_attr_set = false;
+  int attn_kv_split = 1;  // 0: never, 1: when it shortens the critical path (default), 2: whenever Tk spans >= 2 blocks
   bool gn_attr_set = false;
   bool gna_attr_set = false;
   int gn_max_ctas = 0;  // 0: one CTA per SM

@@ -104,6 +104,8 @@ class Ops:
             parts = [int(v) for v in mc.split(",")]
             self.handle.check(self.lib.gn_set_gemm_multicast(self.h, parts[0], parts[1] if len(parts) > 1 else 0),
                               "gn_set_gemm_multicast")
+        if os.environ.get("GENIMA_B200_ATTN_SPLIT", "1") != "1":   # A/B: 0 = no KV split, 2 = split whenever possible
+            self.set_attention_kv_split(int(os.environ["GENIMA_B200_ATTN_SPLIT"]))
         # GroupNorm statistics fused into the producing GEMM epilogues (A/B switch: GENIMA_B200_GNFUSE=0)
         self.gn_fuse = os.environ.get("GENIMA_B200_GNFUSE", "1") != "0"
         # nearest-upsample folded into the following convolution (four 2x2 phase kernels; A/B: GENIMA_B200_UPFOLD=0)
@@ -194,6 +196,10 @@ class Ops:
         if st is not None:
             view.gn_stats = st
         return view
+
+    def set_attention_kv_split(self, mode: int) -> None:
+        """0: never split the keys of gn_attention across a 2-CTA cluster, 1: when it pays (default), 2: whenever possible."""
+        self.handle.check(self.lib.gn_set_attention_kv_split(self.h, int(mode)), "gn_set_attention_kv_split")
 
     def set_gemm_tuning(self, block_n: int = 0, splits: int = 0) -> None:
         self.handle.check(self.lib.gn_set_gemm_tuning(self.h, block_n, splits), "gn_set_gemm_tuning")

@@ -128,6 +128,10 @@ int gn_set_gemm_multicast(gn_handle* h, int max_cluster, int force_cluster);
 int gn_set_conv_halo(gn_handle* h, int enable, int base_offset_field);
 /* Force the operand-ring sizing of the next GEMM-class calls for 1 or 2 resident CTAs per SM (0 = heuristic). */
 int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm);
+/* gn_attention KV split across a 2-CTA cluster (partials merged through distributed shared memory): 0 = never,
+ * 1 = when it shortens the critical path (default; e.g. 160 CTAs x 32 KV blocks on 148 SMs), 2 = whenever Tk spans at
+ * least two 128-key blocks (tests). */
+int gn_set_attention_kv_split(gn_handle* h, int mode);
 /* Debug aid: when dptr (device uint64[8]) is non-NULL, CTA (0,0,0) of every following GEMM-class launch writes
  * %globaltimer stamps of its phases: 0 start, 1 set-up done, 2 first TMA issued, 3 first operands landed, 4 all MMAs
  * issued, 5 accumulator complete, 6 epilogue done, 7 exit.  NULL switches it off. */

@@ -34,6 +34,29 @@ def test_attention_tc(ops, B, heads, Tq, Tk):
     report_close(f"attention B{B} h{heads} {Tq}x{Tk}", out, ref, rtol=1e-3, atol=1e-4 * float(v.abs().max()))
 
 
+@pytest.mark.parametrize("B,heads,Tq,Tk", [(1, 5, 4096, 4096), (1, 20, 256, 256), (2, 3, 200, 300), (1, 2, 130, 129),
+                                           (1, 1, 128, 1000), (3, 2, 64, 257)])
+def test_attention_tc_kv_split(ops, B, heads, Tq, Tk):
+    """Keys split across a 2-CTA cluster (partials merged through distributed shared memory), forced on for every shape
+    with at least two key blocks — ragged tails, a second CTA with a single valid key, batches — and compared both with
+    the fp32 reference and with the unsplit kernel."""
+    d = 64
+    q, k, v = _rand((B * Tq, heads * d), 11), _rand((B * Tk, heads * d), 12), _rand((B * Tk, heads * d), 13)
+    scale = d ** -0.5
+    ref = ops_ref.attention_ref(q, k, v, B, heads, d, Tq, Tk, scale)
+    try:
+        ops.set_attention_kv_split(2)
+        split = ops.attention(q.cuda(), k.cuda(), v.cuda(), B, heads, Tq, Tk, scale)
+        again = ops.attention(q.cuda(), k.cuda(), v.cuda(), B, heads, Tq, Tk, scale)
+        ops.set_attention_kv_split(0)
+        plain = ops.attention(q.cuda(), k.cuda(), v.cuda(), B, heads, Tq, Tk, scale)
+    finally:
+        ops.set_attention_kv_split(1)
+    assert torch.equal(split, again)                                  # fixed merge order: deterministic
+    report_close(f"attention kv-split B{B} h{heads} {Tq}x{Tk}", split, ref, rtol=1e-3, atol=1e-4 * float(v.abs().max()))
+    assert float((split.float() - plain.float()).abs().max()) <= 2e-3 * float(v.abs().max())
+
+
 def test_attention_tc_peaked_and_fused_qkv_layout(ops):
     # q/k/v are column slices of one [M, 3C] buffer (the fused QKV projection output); large logits (peaked softmax)
     B, heads, T, d = 1, 5, 512, 64
