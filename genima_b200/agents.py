@@ -125,9 +125,11 @@ class B200ControlNetAgent:
         loaded = ckpt.load_sd_turbo(_cfg_get(cfg, "sd_ckpt"), _cfg_get(cfg, "diffusion_ckpt"))
         if taesd:
             loaded["vae"], loaded["vae_cfg"] = ckpt.load_taesd(autoenc)
+        # string prompts: the snapshot's own tokenizer files (sd_ckpt/tokenizer), unless the caller supplied a callable
         self.pipe = B200ControlNetPipeline(ops, loaded["unet"], loaded["controlnet"], loaded["vae"], loaded["text"],
                                            loaded["unet_cfg"], loaded["vae_cfg"], loaded["text_cfg"],
-                                           loaded["scheduler_cfg"], tokenizer=tok, use_cuda_graph=graph)
+                                           loaded["scheduler_cfg"], tokenizer=tok or loaded["tokenizer"],
+                                           use_cuda_graph=graph)
 
     # ---- controller/agent/diffusion_agent.py:21-42 (the toggles are accepted; the kernels are always fused)
     def set_optimizations(self):
@@ -189,8 +191,8 @@ class B200Pix2PixAgent(B200ControlNetAgent):
             return
         loaded = ckpt.load_sd_pix2pix(_cfg_get(cfg, "sd_ckpt"), _cfg_get(cfg, "diffusion_ckpt"))
         self.pipe = B200Pix2PixPipeline(ops, loaded["unet"], loaded["vae"], loaded["text"], loaded["unet_cfg"],
-                                        loaded["vae_cfg"], loaded["text_cfg"], loaded["scheduler_cfg"], tokenizer=tok,
-                                        use_cuda_graph=graph)
+                                        loaded["vae_cfg"], loaded["text_cfg"], loaded["scheduler_cfg"],
+                                        tokenizer=tok or loaded["tokenizer"], use_cuda_graph=graph)
 
 
 class B200SDXLControlNetAgent(B200ControlNetAgent):
@@ -232,7 +234,7 @@ class B200SDXLControlNetAgent(B200ControlNetAgent):
         self.pipe = B200SDXLControlNetPipeline(
             ops, loaded["unet"], loaded["controlnet"], loaded["vae"], loaded["text"], loaded["text2"],
             loaded["unet_cfg"], loaded["vae_cfg"], loaded["text_cfg"], loaded["text2_cfg"], loaded["scheduler_cfg"],
-            tokenizer=tok, tokenizer_2=tok2, use_cuda_graph=graph)
+            tokenizer=tok or loaded["tokenizer"], tokenizer_2=tok2 or loaded["tokenizer_2"], use_cuda_graph=graph)
 
     def infer(self, *args, **kwargs):
         extra = ("latents", "prompt_embeds", "pooled_prompt_embeds", "output_type")

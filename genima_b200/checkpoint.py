@@ -128,6 +128,28 @@ def load_sd_pix2pix(sd_ckpt: str, diffusion_ckpt: str):
     return out
 
 
+def load_clip_tokenizer(path: str):
+    """`<sd_ckpt>/tokenizer` (vocab.json + merges.txt [+ tokenizer_config.json]) -> callable list[str] -> ids [B, 77] int64,
+    i.e. what diffusers' encode_prompt does with `self.tokenizer(prompt, padding="max_length", max_length=
+    tokenizer.model_max_length, truncation=True, return_tensors="pt").input_ids`.  Uses transformers' CLIPTokenizer on
+    local files only; returns None when the directory (or transformers) is missing — string prompts then need an explicit
+    `tokenizer=` callable (no CLIP vocabulary ships with this repository)."""
+    if not (os.path.isfile(os.path.join(path, "vocab.json")) and os.path.isfile(os.path.join(path, "merges.txt"))):
+        return None
+    try:
+        from transformers import CLIPTokenizer
+    except Exception:  # pragma: no cover
+        return None
+    tok = CLIPTokenizer.from_pretrained(path, local_files_only=True)
+    max_len = min(int(getattr(tok, "model_max_length", 77) or 77), 77)
+
+    def encode(prompts):
+        return tok(list(prompts), padding="max_length", max_length=max_len, truncation=True,
+                   return_tensors="pt").input_ids.to(torch.int64)
+
+    return encode
+
+
 def text_config_from_json(tj: dict) -> CLIPTextConfig:
     return CLIPTextConfig(vocab_size=tj.get("vocab_size", 49408), hidden_size=tj.get("hidden_size", 1024),
                           intermediate_size=tj.get("intermediate_size", 4096),
@@ -149,6 +171,7 @@ def load_sdxl(sd_ckpt: str, diffusion_ckpt: str):
     out["text2_cfg"] = text_config_from_json(_read_json(os.path.join(t2, "config.json")))
     if not out["text2_cfg"].projection_dim:
         raise ValueError("text_encoder_2 must be a CLIPTextModelWithProjection")
+    out["tokenizer_2"] = load_clip_tokenizer(os.path.join(sd_ckpt, "tokenizer_2"))
     out["text2"] = load_safetensors_dir(t2)
     check_schema(out["text2"], W.clip_text_shapes(out["text2_cfg"]), "text encoder 2")
     return out
@@ -176,7 +199,8 @@ def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: Optional[str]):
     tj = _read_json(os.path.join(sd_ckpt, "text_encoder", "config.json"))
     tcfg = text_config_from_json(tj)
     scfg = scheduler_config_from_json(_read_json(os.path.join(sd_ckpt, "scheduler", "scheduler_config.json")))
-    out = dict(unet=load_safetensors_dir(os.path.join(sd_ckpt, "unet")),
+    out = dict(tokenizer=load_clip_tokenizer(os.path.join(sd_ckpt, "tokenizer")),
+               unet=load_safetensors_dir(os.path.join(sd_ckpt, "unet")),
                controlnet=load_safetensors_dir(cn_dir) if cn_dir is not None else None,
                vae=load_safetensors_dir(os.path.join(sd_ckpt, "vae")),
                text=load_safetensors_dir(os.path.join(sd_ckpt, "text_encoder")),
