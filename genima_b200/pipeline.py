@@ -17,6 +17,12 @@ Execution (restated for the device):
                   Euler update (+ next step's input scaling) — all on one stream, no host sync inside the loop
   latents / 0.18215 -> VAE decoder -> (x / 2 + 0.5).clamp -> u8
 The whole post-upload chain can be captured once into a CUDA graph (`use_cuda_graph=True`) and replayed per call.
+
+Sibling pipelines on the same device graphs, further down in this file:
+  B200SDXLControlNetPipeline   diffusers StableDiffusionXLControlNetPipeline (controller/agent/sdxl_controlnet_agent.py)
+  B200Pix2PixPipeline          diffusers StableDiffusionInstructPix2PixPipeline (controller/agent/sd_pix2pix_agent.py)
+Both Euler schedulers the upstream snapshots ship are implemented (EulerDiscrete for sd-turbo, EulerAncestral for
+sdxl-turbo: its per-step noise is drawn from the caller's generator in diffusers' order before the graph is replayed).
 """
 from __future__ import annotations
 
