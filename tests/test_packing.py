@@ -76,3 +76,30 @@ def test_upsample_conv_phase_kernels_reproduce_the_3x3_convolution():
     eff_exact[:, :, 1, 1] = w[:, :, 1:, 1:].double().sum(dim=(2, 3))
     got00 = w4[0].double().reshape(cout, 2, 2, 64).permute(0, 3, 1, 2)
     assert float((got00 - eff_exact).abs().max()) < 4e-3
+
+
+def test_layer_norm_fold_is_the_same_affine_map():
+    """fold_layer_norm: LayerNorm(x) @ W^T + b == rstd * (x @ Wg^T - mean * colsum) + bias_f (the epilogue's formula,
+    gn_epilogue.ln_*), checked in fp64 with the fp16-rounded folded weight the tensor core would multiply."""
+    import torch
+
+    from genima_b200.packing import fold_layer_norm
+
+    g = torch.Generator().manual_seed(0)
+    K, N, M = 96, 40, 17
+    x = torch.randn(M, K, generator=g, dtype=torch.float64) * 3 + 0.5
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).half()
+    gamma, beta, bias = torch.randn(K, generator=g) * 0.3 + 1, torch.randn(K, generator=g) * 0.2, torch.randn(N, generator=g)
+    w_g, colsum, bias_f = fold_layer_norm(w, gamma, beta, bias)
+    assert w_g.dtype == torch.float16 and colsum.dtype == torch.float32 and bias_f.dtype == torch.float32
+    mean = x.mean(dim=1, keepdim=True)
+    rstd = (x.var(dim=1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    folded = rstd * (x @ w_g.double().T - mean * colsum.double()[None]) + bias_f.double()[None]
+    # reference with the same fp16-rounded (w * gamma): only the algebra is under test here
+    ln_rounded = (x - mean) * rstd
+    ref = ln_rounded @ w_g.double().T + (w.double() @ beta.double() + bias.double())[None]
+    assert torch.allclose(folded, ref, rtol=1e-9, atol=1e-9)
+    # and against the textbook LayerNorm with unrounded weights, to fp16 weight-rounding accuracy
+    ln = torch.nn.functional.layer_norm(x, (K,), gamma.double(), beta.double(), 1e-5)
+    full = ln @ w.double().T + bias.double()[None]
+    assert float((folded - full).abs().max()) < 5e-3 * float(full.abs().max())
