@@ -98,7 +98,7 @@ def test_layer_norm_fold_is_the_same_affine_map():
     # reference with the same fp16-rounded (w * gamma): only the algebra is under test here
     ln_rounded = (x - mean) * rstd
     ref = ln_rounded @ w_g.double().T + (w.double() @ beta.double() + bias.double())[None]
-    assert torch.allclose(folded, ref, rtol=1e-9, atol=1e-9)
+    assert torch.allclose(folded, ref, rtol=1e-5, atol=1e-5)      # (colsum / bias_f are stored in fp32)
     # and against the textbook LayerNorm with unrounded weights, to fp16 weight-rounding accuracy
     ln = torch.nn.functional.layer_norm(x, (K,), gamma.double(), beta.double(), 1e-5)
     full = ln @ w.double().T + bias.double()[None]
