@@ -91,8 +91,13 @@ def scheduler_config_from_json(cfg: dict) -> SchedulerConfig:
                            num_train_timesteps=cfg.get("num_train_timesteps", 1000),
                            beta_start=cfg.get("beta_start", 0.00085), beta_end=cfg.get("beta_end", 0.012),
                            beta_schedule=cfg.get("beta_schedule", "scaled_linear"),
-                           timestep_spacing=cfg.get("timestep_spacing", "trailing"),
-                           prediction_type=cfg.get("prediction_type", "epsilon"))
+                           timestep_spacing=cfg.get("timestep_spacing",
+                                                    "leading" if cfg.get("_class_name") == "DDIMScheduler" else "trailing"),
+                           prediction_type=cfg.get("prediction_type", "epsilon"),
+                           steps_offset=cfg.get("steps_offset", 0),
+                           set_alpha_to_one=cfg.get("set_alpha_to_one", True),
+                           # diffusers' DDIMScheduler clips the predicted x0 by default; SD snapshots switch it off
+                           clip_sample=bool(cfg.get("clip_sample", cfg.get("_class_name") == "DDIMScheduler")))
 
 
 def check_schema(sd: Dict[str, torch.Tensor], shapes, what: str, allow_extra: Tuple[str, ...] = ()) -> None:

@@ -171,3 +171,7 @@ class SchedulerConfig:
     beta_schedule: str = "scaled_linear"
     timestep_spacing: str = "trailing"
     prediction_type: str = "epsilon"
+    # DDIMScheduler only (diffusers defaults; Stable Diffusion snapshots ship clip_sample / set_alpha_to_one = false)
+    steps_offset: int = 0
+    set_alpha_to_one: bool = True
+    clip_sample: bool = False

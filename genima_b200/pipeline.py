@@ -282,7 +282,12 @@ class B200ControlNetPipeline:
         """scheduler.step + the next step's scale_model_input in one kernel -> (x_next, x_scaled_next)."""
         sig = self.schedule.sigmas
         x_next, xs_next = torch.empty_like(x), torch.empty_like(x)
-        if self.schedule.ancestral:
+        if self.schedule.ddim:
+            # DDIM (eta = 0): x' = a x + b eps, written as x + b eps + (a - 1) x on the ancestral-step kernel with the
+            # sample itself in the noise slot (sigmas are all zero here, so x_scaled = x')
+            a, b = self.schedule.ddim_coeffs(i)
+            self.ops.euler_ancestral_step(x, eps, x, 0.0, b, a - 1.0, 0.0, x_next=x_next, x_scaled=xs_next)
+        elif self.schedule.ancestral:
             if noise is None:
                 raise RuntimeError("EulerAncestralDiscreteScheduler re-injects noise at every step: per-step noise "
                                    "[n_steps, B, h, w, 8] is required (the public __call__ draws it from `generator`)")

@@ -29,10 +29,12 @@ from .scheduler import EulerDiscreteOracle
 
 def controlnet_pipeline(unet_sd, cn_sd, vae_sd, ucfg: UNetConfig, vcfg: VAEConfig, cond_u8: np.ndarray,
                         ctx: torch.Tensor, latents: torch.Tensor, n_steps: int, conditioning_scale: float = 1.0,
-                        return_intermediates: bool = False):
+                        return_intermediates: bool = False, scheduler=None):
     """cond_u8 [B, H, W, 3] uint8; ctx [B, 77, D] fp32 prompt embeddings; latents [B, 4, H/8, W/8] unit-variance noise.
+    `scheduler`: an oracle scheduler object (default: sd-turbo's EulerDiscrete; oracle.scheduler.DDIMOracle for
+    snapshots that ship DDIMScheduler).
     Returns dict(latents=final latents fp32, image=decoded image in [-1, 1] NCHW fp32, u8=[B, H, W, 3] uint8)."""
-    sched = EulerDiscreteOracle()
+    sched = scheduler if scheduler is not None else EulerDiscreteOracle()
     ts, sig = sched.set_timesteps(n_steps)
     cond = torch.from_numpy(cond_u8.astype(np.float32) / 255.0).permute(0, 3, 1, 2)      # VaeImageProcessor.preprocess
     x = latents.to(torch.float32) * sched.init_noise_sigma

@@ -374,6 +374,29 @@ def test_pipeline_tiny_vs_oracle(ops, n_steps):
     assert diff.max() <= 3 and (diff <= 1).mean() > 0.995
 
 
+def test_pipeline_ddim_scheduler_vs_oracle(ops):
+    """A snapshot whose scheduler_config.json names DDIMScheduler (the boundary reads the scheduler):
+    eta = 0 steps x' = a x + b eps on the device against the oracle restatement of diffusers' DDIMScheduler.step."""
+    from genima_b200.configs import SchedulerConfig
+    from genima_b200.pipeline import B200ControlNetPipeline
+    from oracle.pipeline import controlnet_pipeline
+    from oracle.scheduler import DDIMOracle
+
+    ucfg, vcfg = UNetConfig.tiny(), VAEConfig.tiny()
+    usd = W.synth_state_dict(W.unet_shapes(ucfg))
+    csd = W.synth_state_dict(W.controlnet_shapes(ucfg), salt=1)
+    vsd = W.synth_state_dict(W.vae_decoder_shapes(vcfg), salt=2)
+    _, ctx, cond = _unet_inputs(ucfg, 1, seed=13)
+    lat = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(2)).half().float()
+    kw = dict(timestep_spacing="leading", steps_offset=1, set_alpha_to_one=False)
+    ref = controlnet_pipeline(usd, csd, vsd, ucfg, vcfg, cond.numpy(), ctx, lat, 4, scheduler=DDIMOracle(**kw))
+    pipe = B200ControlNetPipeline(ops, usd, csd, vsd, None, ucfg, vcfg,
+                                  scheduler_cfg=SchedulerConfig(class_name="DDIMScheduler", **kw))
+    out = pipe(prompt_embeds=ctx, image=cond, num_inference_steps=4, guidance_scale=0.0, latents=lat,
+               output_type="latent").images
+    check("pipeline latents after 4 DDIM steps", out, ref["latents"], LOOP_TOL)
+
+
 def test_pipeline_cuda_graph_matches_eager(ops):
     """Same pipeline object (same handles, hence the same measured tile configurations): eager launches, CUDA-graph
     capture and graph replay on new inputs must agree bit for bit — every kernel is deterministic, including GroupNorm

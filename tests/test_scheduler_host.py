@@ -73,3 +73,46 @@ def test_euler_step_equals_ddim_eta0_update():
         y2 = math.sqrt(ab2) * (y - math.sqrt(1 - ab) * eps) / math.sqrt(ab) + math.sqrt(1 - ab2) * eps
         assert torch.allclose(x_next * math.sqrt(ab2), y2, rtol=1e-5, atol=1e-5)
         x = x_next
+
+
+@pytest.mark.parametrize("spacing,offset,alpha_one", [("leading", 1, False), ("trailing", 0, True), ("linspace", 0, False)])
+def test_ddim_tables_and_coefficients(spacing, offset, alpha_one):
+    """DDIMScheduler (eta = 0) as x' = a x + b eps: timesteps and per-step coefficients against the oracle restatement of
+    diffusers' step(); sigmas are all zero so that the Euler-form plumbing scales nothing; clip_sample raises."""
+    from oracle.scheduler import DDIMOracle
+
+    cfg = SchedulerConfig(class_name="DDIMScheduler", timestep_spacing=spacing, steps_offset=offset,
+                          set_alpha_to_one=alpha_one)
+    sch = EulerDiscreteSchedule(cfg)
+    assert sch.ddim and not sch.ancestral
+    ts, sig = sch.set_timesteps(5)
+    o = DDIMOracle(timestep_spacing=spacing, steps_offset=offset, set_alpha_to_one=alpha_one)
+    assert np.array_equal(ts, o.set_timesteps(5)[0])
+    assert sch.init_noise_sigma == 1.0 and not sig.any() and len(sig) == 6
+    g = torch.Generator().manual_seed(0)
+    x, eps = torch.randn(1, 4, 8, 8, generator=g), torch.randn(1, 4, 8, 8, generator=g)
+    for i in range(5):
+        a, b = sch.ddim_coeffs(i)
+        assert torch.allclose(a * x + b * eps, o.step(eps, i, x), rtol=1e-5, atol=1e-5)
+        x = o.step(eps, i, x)
+    with pytest.raises(NotImplementedError):
+        EulerDiscreteSchedule(SchedulerConfig(class_name="DDIMScheduler", clip_sample=True))
+
+
+def test_ddim_trailing_equals_euler_in_scaled_variable():
+    """SURVEY.md Appendix D, now through both schedule objects: with set_alpha_to_one the DDIM(eta = 0) trajectory of
+    y = x / sqrt(sigma^2 + 1) is the Euler trajectory of x on the same trailing timesteps."""
+    eu = EulerDiscreteSchedule(SchedulerConfig())
+    dd = EulerDiscreteSchedule(SchedulerConfig(class_name="DDIMScheduler"))
+    ts_e, sig = eu.set_timesteps(5)
+    ts_d, _ = dd.set_timesteps(5)
+    assert np.array_equal(ts_e, ts_d)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64) * float(sig[0])
+    y = x / math.sqrt(float(sig[0]) ** 2 + 1)
+    for i in range(5):
+        eps = torch.randn(1, 4, 8, 8, generator=g, dtype=torch.float64)
+        x = x + (float(sig[i + 1]) - float(sig[i])) * eps
+        a, b = dd.ddim_coeffs(i)
+        y = a * y + b * eps
+        assert torch.allclose(y, x / math.sqrt(float(sig[i + 1]) ** 2 + 1), rtol=1e-4, atol=1e-4)
