@@ -19,6 +19,7 @@ Same graph as oracle/act.py, different execution:
 from __future__ import annotations
 
 import math
+from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -125,8 +126,10 @@ class DeviceACT:
                 cin = cout
         self.film_w = torch.cat(film_w, 0).contiguous().to(dev)          # one GEMM for the eight FiLM projections
         self.film_b = torch.cat(film_b, 0).contiguous().to(dev)
-        self._film_key = None
-        self._film: List[List[Tuple[torch.Tensor, torch.Tensor]]] = []
+        # FiLM affines per task embedding: key -> (affines, the task tensor itself so its data_ptr cannot be recycled).
+        # A captured graph reads these buffers by raw pointer, so every graph entry also holds its list (see
+        # forward_graphed): evicting an entry here can never free memory a live graph still reads.
+        self._film: "OrderedDict[tuple, tuple]" = OrderedDict()
         d = cfg.hidden_dim
         self.proj_w = P.f16("encoder_model.input_proj.weight").reshape(d, -1).contiguous()
         self.proj_b = P.f32("encoder_model.input_proj.bias")
@@ -216,8 +219,10 @@ class DeviceACT:
         """task_emb [B, E] fp32 -> per sample, per BasicBlock (scale, shift) of bn2 with FiLM folded in.
         Constant per episode (the task text does not change): cached while the same tensor is passed."""
         key = tensor_key(task_emb)
-        if key == self._film_key:
-            return self._film
+        hit = self._film.get(key)
+        if hit is not None and hit[1] is task_emb:
+            self._film.move_to_end(key)
+            return hit[0]
         ops = self.ops
         te16 = ops.nchw_to_nhwc(task_emb.reshape(task_emb.shape[0], -1, 1, 1).contiguous())  # fp32 -> fp16 [B,1,1,E]
         film = ops.linear(te16.reshape(task_emb.shape[0], -1), self.film_w, bias=self.film_b, out_fp32=True)
@@ -229,7 +234,9 @@ class DeviceACT:
                 per_block.append(ops.film_fold(film[bidx, off:off + 2 * c], blk["c2"].scale, blk["c2"].shift))
                 off += 2 * c
             out.append(per_block)
-        self._film_key, self._film, self._film_owner = key, out, task_emb
+        self._film[key] = (out, task_emb)
+        while len(self._film) > 8:
+            self._film.popitem(last=False)
         return out
 
     # ------------------------------------------------------------------------------------------------ forward
@@ -311,7 +318,7 @@ class DeviceACT:
         g = self._graphs.get(key)
         if g is None:
             st = dict(qpos=qpos.clone(), image=image.clone(), task=task_emb)
-            self.film_affines(task_emb)
+            film = self.film_affines(task_emb)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):           # warm-up outside capture (autotuning, smem attributes, allocator)
@@ -323,7 +330,8 @@ class DeviceACT:
                 a_hat, is_pad = self.forward(st["qpos"], st["image"], st["task"])
             if len(self._graphs) > 4:
                 self._graphs.clear()
-            g = self._graphs[key] = dict(graph=graph, st=st, a_hat=a_hat, is_pad=is_pad)
+            # the entry owns everything the graph reads by pointer: static inputs, the task tensor, its FiLM affines
+            g = self._graphs[key] = dict(graph=graph, st=st, a_hat=a_hat, is_pad=is_pad, film=film)
         g["st"]["qpos"].copy_(qpos, non_blocking=True)
         g["st"]["image"].copy_(image, non_blocking=True)
         g["graph"].replay()

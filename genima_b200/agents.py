@@ -19,6 +19,7 @@ from __future__ import annotations
 import dataclasses
 import os
 import re
+from collections import OrderedDict
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -290,45 +291,240 @@ class B200GenimaACTPolicy:
     __call__ = forward
 
 
-class B200GenimaACT:
-    """`GenimaACT.act` / `.encode_clip_text` (controller/method/genima_act.py:273-346)."""
+def _hp(spec, name, default):
+    """Hyper-parameter `name` of a hydra `_partial_: true` node (functools.partial -> `.keywords`), a DictConfig / dict,
+    or None."""
+    if spec is None:
+        return default
+    kw = getattr(spec, "keywords", None)
+    if isinstance(kw, dict):
+        return kw.get(name, default)
+    return _cfg_get(spec, name, default)
 
-    def __init__(self, policy: B200GenimaACTPolicy, clip_state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                 clip_cfg: CLIPTextConfig = CLIPTextConfig.vit_b32()):
-        self.actor = policy
-        self.ops = policy.ops
-        self.clip = DeviceCLIPText(self.ops, clip_state_dict, clip_cfg) if clip_state_dict is not None else None
-        self._emb_cache: Dict[bytes, tuple] = {}
+
+def _space_get(space, key):
+    """gymnasium.spaces.Dict item (or a plain dict of objects with `.shape`)."""
+    try:
+        return space[key]
+    except Exception:
+        return getattr(space, "spaces", {}).get(key)
+
+
+def _space_keys(space):
+    if hasattr(space, "spaces"):
+        return list(space.spaces.keys())
+    return list(space.keys())
+
+
+class _IncompatibleKeys(tuple):
+    """torch.nn.modules.module._IncompatibleKeys look-alike returned by load_state_dict."""
+
+    def __new__(cls, missing_keys, unexpected_keys):
+        self = super().__new__(cls, (missing_keys, unexpected_keys))
+        self.missing_keys, self.unexpected_keys = missing_keys, unexpected_keys
+        return self
+
+
+class B200GenimaACT:
+    """Drop-in for `method.genima_act.GenimaACT` on the eval path (controller/method/genima_act.py:217-346 over RoboBase
+    `ActBCAgent`): hydra target of the checkpoint's `config.yaml` (`controller/cfgs/method/genima_act.yaml:4`),
+
+        hydra.utils.instantiate(train_cfg.method, device=, observation_space=, action_space=, num_train_envs=,
+                                replay_alpha=, replay_beta=, frame_stack_on_channel=)       # eval_genima.py:55-64
+
+    followed by `.train(False)` (:66), `.state_dict()` / `.load_state_dict(checkpoint["agent"], strict=False)`
+    (:91-103), `robobase_utils.eval_mode(agent)` (:200, reads `.training`, calls `.train(bool)`) and
+    `.act(obs, step=, eval_mode=True)` (:243-247).  The network hyper-parameters come from the same places the
+    reference reads them: `actor_model` / `encoder_model` (the yaml's `_partial_` nodes), the observation space
+    (state size, number of rgb views, image size: genima_act.py:227-231) and the action space.
+
+    State-dict keys are RoboBase's: the policy lives under `actor.` (`actor.encoder_model.*`, `actor.actor_model.*`,
+    train_act.py:262-279 saves them minus `clip_model.*`).  No weights exist until `load_state_dict` (the reference
+    starts from a random init it immediately overwrites); `act` before that raises.
+
+    The ViT-B/32 text tower the reference fetches with `clip.load` at the first `encode_clip_text` (genima_act.py:315-321)
+    comes from `clip_state_dict` (transformers / OpenAI naming) or `clip_ckpt` (a local `ViT-B-32.pt`, TorchScript
+    archive or state dict): hub downloads are impossible offline.
+
+    Training-side keywords (lr, weight_decay, replay_*, ...) are accepted and kept in `.hparams`; `update()` raises."""
+
+    def __init__(self, *args, device="cuda", observation_space=None, action_space=None, actor_model=None,
+                 encoder_model=None, policy: Optional[B200GenimaACTPolicy] = None,
+                 clip_state_dict: Optional[Dict[str, torch.Tensor]] = None, clip_ckpt: Optional[str] = None,
+                 clip_cfg: CLIPTextConfig = CLIPTextConfig.vit_b32(), act_cfg: Optional[ACTConfig] = None,
+                 ops: Optional[Ops] = None, use_cuda_graph: bool = True, **kwargs):
+        if args and isinstance(args[0], B200GenimaACTPolicy):     # round-1 signature: B200GenimaACT(policy, clip_sd, cfg)
+            policy, args = args[0], args[1:]
+            if args:
+                clip_state_dict, args = args[0], args[1:]
+            if args:
+                clip_cfg, args = args[0], args[1:]
+        if args:
+            raise TypeError(f"unexpected positional arguments: {args!r}")
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        self.observation_space, self.action_space = observation_space, action_space
+        self.hparams = dict(kwargs)
+        self.training = False
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._ops = ops if ops is not None else (policy.ops if policy is not None else None)
+        self._actor: Optional[B200GenimaACTPolicy] = policy
+        self._actor_sd: Optional[Dict[str, torch.Tensor]] = None        # loaded, not yet bound to the device
+        self.cfg = policy.cfg if policy is not None else (act_cfg or self._config_from_spaces(actor_model, encoder_model))
+        self._clip_sd, self._clip_ckpt, self.clip_cfg = clip_state_dict, clip_ckpt, clip_cfg
+        self.clip: Optional[DeviceCLIPText] = None
+        self._emb_cache: "OrderedDict[bytes, tuple]" = OrderedDict()     # token content -> (task_emb, last hidden)
+        self._ident_cache: "OrderedDict[tuple, tuple]" = OrderedDict()   # same tensor object -> the same, no D2H read
+
+    # ---- genima_act.py:221-249 (what build_actor derives from the spaces and the yaml)
+    def _config_from_spaces(self, actor_model, encoder_model) -> ACTConfig:
+        base = ACTConfig()
+        kw = dict(hidden_dim=int(_hp(actor_model, "hidden_dim", base.hidden_dim)),
+                  enc_layers=int(_hp(actor_model, "enc_layers", base.enc_layers)),
+                  dec_layers=int(_hp(actor_model, "dec_layers", base.dec_layers)),
+                  dim_feedforward=int(_hp(actor_model, "dim_feedforward", base.dim_feedforward)),
+                  nheads=int(_hp(actor_model, "nheads", base.nheads)),
+                  num_queries=int(_hp(actor_model, "num_queries", base.num_queries)),
+                  state_dim=int(_hp(actor_model, "state_dim", base.state_dim)),
+                  action_dim=int(_hp(actor_model, "action_dim", base.action_dim)))
+        if _hp(actor_model, "pre_norm", False):
+            raise NotImplementedError("pre_norm transformer layers are not implemented (genima_act.yaml: pre_norm false)")
+        bb = _hp(encoder_model, "backbone", "resnet18")
+        if bb != "resnet18":
+            raise NotImplementedError(f"backbone {bb!r} is not implemented (genima_act.yaml: resnet18)")
+        if _hp(encoder_model, "position_embedding", "sine") != "sine":
+            raise NotImplementedError("only the sine position embedding is implemented")
+        if encoder_model is not None and not _hp(encoder_model, "use_lang_cond", True):
+            raise NotImplementedError("use_lang_cond=False (no FiLM) is not implemented")
+        enc_hidden = _hp(encoder_model, "hidden_dim", kw["hidden_dim"])
+        if int(enc_hidden) != kw["hidden_dim"]:
+            raise ValueError("encoder_model.hidden_dim and actor_model.hidden_dim differ")
+        osp = self.observation_space
+        if osp is not None:
+            low = _space_get(osp, "low_dim_state")
+            if low is not None:
+                kw["state_dim"] = int(np.prod(low.shape))               # genima_act.py:228
+            rgb = [k for k in _space_keys(osp) if re.match(r"rgb.*", k) or "_rgb" in k]
+            if rgb:
+                shp = tuple(_space_get(osp, rgb[0]).shape)              # (T, 3, H, W) with the frame-stack wrapper
+                frames = int(shp[0]) if len(shp) == 4 else 1
+                kw["num_views"] = len(rgb) * frames
+                kw["image_size"] = int(shp[-1])
+        if self.action_space is not None:
+            kw["action_dim"] = int(self.action_space.shape[-1])         # genima_act.py:229
+        return dataclasses.replace(base, **kw)
+
+    # ---- torch.nn.Module surface the eval workspace touches
+    @property
+    def ops(self) -> Ops:
+        if self._ops is None:
+            self._ops = get_ops(self.device if self.device.type == "cuda" else "cuda")
+        return self._ops
+
+    @property
+    def actor(self) -> Optional[B200GenimaACTPolicy]:
+        """The policy (`self.actor` of the reference, genima_act.py:244-249), bound to the device on first use."""
+        if self._actor_sd is not None:
+            sd, self._actor_sd = self._actor_sd, None
+            if self._actor is None:
+                self._actor = B200GenimaACTPolicy(sd, self.cfg, ops=self.ops, use_cuda_graph=self.use_cuda_graph)
+            else:
+                self._actor.load_state_dict(sd)
+        return self._actor
+
+    def train(self, mode: bool = True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def to(self, *a, **k):
+        return self
+
+    def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        """`actor.*` keys of the RoboBase snapshot schema; shape-only (meta) tensors until weights are loaded."""
+        if self._actor_sd is not None:
+            return OrderedDict((f"actor.{k}", v) for k, v in self._actor_sd.items())
+        if self._actor is not None:
+            return OrderedDict((f"actor.{k}", v) for k, v in self._actor.state_dict().items())
+        return OrderedDict((f"actor.{k}", torch.empty(shape, device="meta"))
+                           for k, shape in W.act_shapes(self.cfg).items())
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """`checkpoint["agent"]` (eval_genima.py:102).  Binds the device policy to the `actor.*` tensors; other keys
+        (`clip_model.*`, optimiser-side duplicates RoboBase may register) are reported as unexpected, and with
+        strict=True raise like torch does.  A missing policy tensor always raises: nothing can run without it."""
+        want = W.act_shapes(self.cfg)
+        sd = {k[len("actor."):]: v for k, v in state_dict.items() if k.startswith("actor.")}
+        missing = [f"actor.{k}" for k in want if k not in sd]
+        unexpected = [k for k in state_dict if not (k.startswith("actor.") and k[len("actor."):] in want)]
+        if missing:
+            raise RuntimeError(f"Error(s) in loading state_dict for B200GenimaACT: missing keys {missing[:8]}"
+                               f"{' ...' if len(missing) > 8 else ''}")
+        if strict and unexpected:
+            raise RuntimeError(f"Error(s) in loading state_dict for B200GenimaACT: unexpected keys {unexpected[:8]}")
+        sd = {k: sd[k] for k in want}
+        ckpt.check_schema(sd, want, "ACT policy")
+        self._actor_sd = sd          # bound to the device (DeviceACT: packing, BN / FiLM folds) at the first act()
+        if any(k.startswith("clip_model.") for k in state_dict) and self._clip_sd is None and self._clip_ckpt is None:
+            self._clip_sd = {k[len("clip_model."):]: v for k, v in state_dict.items() if k.startswith("clip_model.")}
+            self.clip = None
+        return _IncompatibleKeys([], unexpected)
+
+    def update(self, *a, **k):
+        raise NotImplementedError("training (GenimaACT.update, genima_act.py:348-422) is out of scope: inference path only")
+
+    # ---- genima_act.py:314-346
+    def _ensure_clip(self) -> DeviceCLIPText:
+        if self.clip is None:
+            sd = self._clip_sd
+            if sd is None and self._clip_ckpt is not None:
+                sd = ckpt.load_openai_clip_text(self._clip_ckpt)
+            if sd is None:
+                raise RuntimeError(
+                    "no CLIP text tower bound: the reference downloads ViT-B/32 with clip.load (genima_act.py:315-321), "
+                    "which is impossible offline — pass clip_ckpt=<local ViT-B-32.pt> or clip_state_dict=, or supply "
+                    "task_emb to the policy yourself")
+            if "token_embedding.weight" in sd:                       # OpenAI naming -> transformers naming
+                sd = ckpt.openai_clip_text_to_hf(sd)
+            self.clip = DeviceCLIPText(self.ops, sd, self.clip_cfg)
+        return self.clip
+
+    @staticmethod
+    def _lru_put(cache: "OrderedDict", key, value, limit: int) -> None:
+        cache[key] = value
+        cache.move_to_end(key)
+        while len(cache) > limit:
+            cache.popitem(last=False)
 
     def encode_clip_text(self, tokens: torch.Tensor):
         """tokens [B, T, 77] int -> (task_emb [B, proj] fp32, last hidden [B*T, 77, d]).  The text is constant for an
-        episode (controller/env/rlbench_utils.py:156), so results are cached by token content."""
+        episode (controller/env/rlbench_utils.py:156), so results are cached by token content; both caches are small
+        LRUs (the eval loop hands over a fresh device tensor every step, eval_genima.py:237-240)."""
         shape = tokens.shape
-        # same tensor object, unmodified (data_ptr / shape / version): no device-to-host read of the ids at all
-        ident = ("id",) + tensor_key(tokens)
-        hit = self._emb_cache.get(ident)
-        if hit is not None:
+        ident = tensor_key(tokens)
+        hit = self._ident_cache.get(ident)
+        if hit is not None and hit[2] is tokens:      # the very same tensor object, unmodified: no device-to-host read
+            self._ident_cache.move_to_end(ident)
             return hit[0], hit[1]
         tks = tokens.reshape(-1, shape[-1])
-        key = tks.cpu().numpy().tobytes()
+        key = tks.cpu().numpy().tobytes() + repr(tuple(shape)).encode()
         hit = self._emb_cache.get(key)
-        if hit is not None:
-            self._emb_cache[ident] = (hit[0], hit[1], tokens)      # (keeps `tokens` alive: its data_ptr cannot be reused)
         if hit is None:
-            if self.clip is None:
-                raise RuntimeError("no CLIP text tower bound: pass clip_state_dict or supply task_emb yourself")
-            if len(self._emb_cache) > 64:
-                self._emb_cache.clear()
-            emb, pooled = self.clip(tks.to(self.ops.device, torch.int64))
+            clip = self._ensure_clip()
+            emb, pooled = clip(tks.to(self.ops.device, torch.int64))
             x = pooled.reshape(shape[0], shape[1], -1)[:, 0].contiguous()   # text does not change across frames
             hit = (x, emb)
-            self._emb_cache[key] = hit
-            self._emb_cache[ident] = (x, emb, tokens)
+        self._lru_put(self._emb_cache, key, hit, 16)
+        self._lru_put(self._ident_cache, ident, (hit[0], hit[1], tokens), 4)
         return hit
 
     @torch.no_grad()
     def act(self, obs: Dict[str, torch.Tensor], step: int = 0, eval_mode: bool = True) -> torch.Tensor:
         """obs: low_dim_state [B, T, S]; `*rgb*` [B, T, 3, H, W] (dict order = view order); lang_tokens [B, T, 77]."""
+        actor = self.actor
+        if actor is None:
+            raise RuntimeError("B200GenimaACT.act before load_state_dict: no controller weights are bound")
         low = obs["low_dim_state"]
         qpos = low.reshape(low.shape[0], -1).float()
         rgbs = [v for k, v in obs.items() if re.match(r"rgb.*", k) or "_rgb" in k]
@@ -337,4 +533,4 @@ class B200GenimaACT:
         if image.dtype != torch.uint8:
             image = image.float()                                     # genima_act.py:296 (`rgb.float()`)
         task_emb, _ = self.encode_clip_text(obs["lang_tokens"])
-        return self.actor(qpos, image, task_emb=task_emb)
+        return actor(qpos, image, task_emb=task_emb)

@@ -86,18 +86,34 @@ def unet_config_from_json(cfg: dict) -> UNetConfig:
                       cond_embed_channels=ce, sample_size=cfg.get("sample_size", 64))
 
 
+# scheduler_config.json keys that change the ODE and are NOT implemented: a non-default value raises instead of being
+# silently dropped (diffusers 0.29.0 defaults in the right column)
+_UNSUPPORTED_SCHEDULER_FLAGS = {
+    "use_karras_sigmas": False, "interpolation_type": "linear", "rescale_betas_zero_snr": False,
+    "timestep_type": "discrete", "final_sigmas_type": "zero", "sigma_min": None, "sigma_max": None,
+    "thresholding": False, "trained_betas": None,
+}
+
+
 def scheduler_config_from_json(cfg: dict) -> SchedulerConfig:
-    return SchedulerConfig(class_name=cfg.get("_class_name", "EulerDiscreteScheduler"),
+    cls = cfg.get("_class_name", "EulerDiscreteScheduler")
+    for k, default in _UNSUPPORTED_SCHEDULER_FLAGS.items():
+        if k in cfg and cfg[k] != default:
+            raise NotImplementedError(f"scheduler_config.json: {k}={cfg[k]!r} is not implemented (only {default!r})")
+    # diffusers' own defaults when the key is absent: DDIM 'leading'; EulerDiscrete / EulerAncestral 'linspace'
+    # (the sd-turbo / sdxl-turbo snapshots the reference loads say 'trailing' explicitly)
+    default_spacing = "leading" if cls == "DDIMScheduler" else "linspace"
+    return SchedulerConfig(class_name=cls,
                            num_train_timesteps=cfg.get("num_train_timesteps", 1000),
-                           beta_start=cfg.get("beta_start", 0.00085), beta_end=cfg.get("beta_end", 0.012),
+                           beta_start=cfg.get("beta_start", 0.00085),
+                           beta_end=cfg.get("beta_end", 0.012),
                            beta_schedule=cfg.get("beta_schedule", "scaled_linear"),
-                           timestep_spacing=cfg.get("timestep_spacing",
-                                                    "leading" if cfg.get("_class_name") == "DDIMScheduler" else "trailing"),
+                           timestep_spacing=cfg.get("timestep_spacing", default_spacing),
                            prediction_type=cfg.get("prediction_type", "epsilon"),
                            steps_offset=cfg.get("steps_offset", 0),
                            set_alpha_to_one=cfg.get("set_alpha_to_one", True),
                            # diffusers' DDIMScheduler clips the predicted x0 by default; SD snapshots switch it off
-                           clip_sample=bool(cfg.get("clip_sample", cfg.get("_class_name") == "DDIMScheduler")))
+                           clip_sample=bool(cfg.get("clip_sample", cls == "DDIMScheduler")))
 
 
 def check_schema(sd: Dict[str, torch.Tensor], shapes, what: str, allow_extra: Tuple[str, ...] = ()) -> None:
@@ -200,7 +216,10 @@ def load_sd_turbo(sd_ckpt: str, diffusion_ckpt: Optional[str]):
     vcfg = VAEConfig(latent_channels=vj.get("latent_channels", 4), out_channels=vj.get("out_channels", 3),
                      block_out_channels=tuple(vj.get("block_out_channels", (128, 256, 512, 512))),
                      layers_per_block=vj.get("layers_per_block", 2), norm_num_groups=vj.get("norm_num_groups", 32),
-                     scaling_factor=vj.get("scaling_factor", 0.18215))
+                     scaling_factor=vj.get("scaling_factor", 0.18215),
+                     force_upcast=bool(vj.get("force_upcast", False)) and ucfg.addition_embed)   # (SDXL VAEs only: the
+    #                SD-2.x VAE config also carries force_upcast=true by default but is fp16-safe and diffusers only
+    #                acts on the flag in the SDXL pipelines)
     tj = _read_json(os.path.join(sd_ckpt, "text_encoder", "config.json"))
     tcfg = text_config_from_json(tj)
     scfg = scheduler_config_from_json(_read_json(os.path.join(sd_ckpt, "scheduler", "scheduler_config.json")))
@@ -242,6 +261,54 @@ def load_controller_snapshot(path: str, cfg: ACTConfig = ACTConfig(), prefix: st
     agent = payload["agent"] if "agent" in payload else payload
     sd = {k[len(prefix):]: v for k, v in agent.items() if k.startswith(prefix)}
     check_schema(sd, W.act_shapes(cfg), f"controller snapshot {path}")
+    return sd
+
+
+def openai_clip_text_to_hf(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Text tower of an OpenAI CLIP state dict (`clip.load("ViT-B/32")`, controller/method/genima_act.py:315-321; names as
+    the reference reads them at :324-341: token_embedding, positional_embedding, transformer.resblocks, ln_final,
+    text_projection) -> the transformers CLIPTextModelWithProjection names DeviceCLIPText binds.  OpenAI's
+    `x @ text_projection` ([d, proj]) becomes `text_projection.weight` = its transpose ([proj, d])."""
+    out: Dict[str, torch.Tensor] = {}
+    out["text_model.embeddings.token_embedding.weight"] = sd["token_embedding.weight"]
+    out["text_model.embeddings.position_embedding.weight"] = sd["positional_embedding"]
+    i = 0
+    while f"transformer.resblocks.{i}.attn.in_proj_weight" in sd:
+        src, dst = f"transformer.resblocks.{i}", f"text_model.encoder.layers.{i}"
+        w, b = sd[f"{src}.attn.in_proj_weight"], sd[f"{src}.attn.in_proj_bias"]
+        d = w.shape[1]
+        for j, n in enumerate("qkv"):
+            out[f"{dst}.self_attn.{n}_proj.weight"] = w[j * d:(j + 1) * d]
+            out[f"{dst}.self_attn.{n}_proj.bias"] = b[j * d:(j + 1) * d]
+        for a, bname in (("attn.out_proj", "self_attn.out_proj"), ("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"),
+                         ("mlp.c_fc", "mlp.fc1"), ("mlp.c_proj", "mlp.fc2")):
+            out[f"{dst}.{bname}.weight"] = sd[f"{src}.{a}.weight"]
+            out[f"{dst}.{bname}.bias"] = sd[f"{src}.{a}.bias"]
+        i += 1
+    if i == 0:
+        raise ValueError("not an OpenAI CLIP state dict: no transformer.resblocks.* keys")
+    out["text_model.final_layer_norm.weight"] = sd["ln_final.weight"]
+    out["text_model.final_layer_norm.bias"] = sd["ln_final.bias"]
+    out["text_projection.weight"] = sd["text_projection"].t().contiguous()
+    return out
+
+
+def load_openai_clip_text(path: str, cfg: CLIPTextConfig = CLIPTextConfig.vit_b32()) -> Dict[str, torch.Tensor]:
+    """Local copy of the file `clip.load("ViT-B/32")` downloads (`~/.cache/clip/ViT-B-32.pt`: a TorchScript archive) or a
+    plain state dict saved with torch.save -> text-tower state dict in transformers naming, schema-checked."""
+    if not os.path.isfile(path):
+        raise FileNotFoundError(f"CLIP checkpoint {path!r} not found; hub downloads are impossible offline")
+    try:
+        sd = torch.jit.load(path, map_location="cpu").state_dict()
+    except RuntimeError:
+        sd = torch.load(path, map_location="cpu", weights_only=False)
+        if hasattr(sd, "state_dict"):
+            sd = sd.state_dict()
+    sd = {k: v for k, v in sd.items() if not k.startswith("visual.")}
+    if "token_embedding.weight" in sd:
+        sd = openai_clip_text_to_hf(sd)
+    sd = {k: v for k, v in sd.items() if k in W.clip_text_shapes(cfg)}
+    check_schema(sd, W.clip_text_shapes(cfg), f"CLIP text tower {path}")
     return sd
 
 

@@ -73,6 +73,10 @@ class VAEConfig:
     norm_num_groups: int = 32
     norm_eps: float = 1e-6
     scaling_factor: float = 0.18215
+    # AutoencoderKL config.json `force_upcast` (stabilityai/sdxl-turbo's VAE ships true: diffusers then decodes in fp32
+    # because that VAE overflows fp16).  The fp16 tensor-core decoder here checks its output for non-finite values when
+    # the flag is set (pipeline.py) instead of silently returning a black image.
+    force_upcast: bool = False
 
     @staticmethod
     def tiny() -> "VAEConfig":

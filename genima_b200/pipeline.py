@@ -196,16 +196,17 @@ class B200ControlNetPipeline:
 
     def _context_kv(self, ctx: torch.Tensor) -> Dict[str, torch.Tensor]:
         key = tensor_key(ctx)
-        if key not in self._kv_cache:
+        hit = self._kv_cache.get(key)
+        if hit is None or hit[1] is not ctx:
             if len(self._kv_cache) > 8:
-                self._kv_cache.clear()
+                self._kv_cache.clear()      # (graphs that captured an evicted K/V set hold their own reference to it)
             kv = {}
             for net in (self.unet_impl, self.controlnet_impl):
                 for tr in net.transformers():
                     kv[("u:" if net is self.unet_impl else "c:") + tr.prefix] = tr.project_context(self.ops, ctx)
-            self._kv_cache[key] = kv
-            self._kv_owner = ctx  # keep ctx alive so data_ptr cannot be recycled under the same key
-        return self._kv_cache[key]
+            kv["__ctx__"] = ctx             # the entry keeps its context alive: the data_ptr in `key` cannot be recycled
+            hit = self._kv_cache[key] = (kv, ctx)
+        return hit[0]
 
     def _added_key(self) -> tuple:
         a = getattr(self, "_added", None)
@@ -389,7 +390,7 @@ class B200ControlNetPipeline:
             static_cond = cond_u8.clone()
             static_lat = lat_in.clone()
             static_noise = noise.clone() if noise is not None else None
-            self._time_rows(n_steps, lat_in.shape[0])                 # hoisted work must exist before capture
+            temb = self._time_rows(n_steps, lat_in.shape[0])          # hoisted work must exist before capture
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                             # warm-up: tensor maps, smem attributes, allocator
@@ -402,8 +403,11 @@ class B200ControlNetPipeline:
                 out_lat, out_img = self._denoise_and_decode(static_cond, static_lat, kv, tk, n_steps, want_image,
                                                             cond_scale, static_noise)
             ops_launches = self.launch_count() - launches0
+            # the entry owns everything the graph reads by raw pointer: static inputs, the K/V set (which holds its
+            # context), the per-step time-embedding rows and the SDXL added conditioning -- clearing _temb_cache /
+            # _kv_cache / _ctx_cache later cannot free memory under a graph that is still cached
             g = dict(graph=graph, cond=static_cond, lat=static_lat, noise=static_noise, out_lat=out_lat,
-                     out_img=out_img, kv=kv, launches=ops_launches)
+                     out_img=out_img, kv=kv, temb=temb, added=self._added, launches=ops_launches)
             if len(self._graphs) > 4:
                 self._graphs.clear()
             self._graphs[key] = g
@@ -512,6 +516,14 @@ class B200ControlNetPipeline:
             noise = ops.nchw_to_nhwc(torch.cat(draws, dim=0).contiguous(), cpad=LATENT_CPAD)
             noise = noise.reshape(n_steps, B, h, w, LATENT_CPAD)
         x, img = self._run(cond_u8, lat_in, kv, tk, n_steps, output_type != "latent", cond_scale, noise)
+        if img is not None and getattr(self.vae_cfg, "force_upcast", False):
+            # this VAE asks for an fp32 decode upstream (config.json force_upcast: the stock SDXL VAE overflows fp16);
+            # the fp16 decoder ran anyway -- refuse to hand back a NaN / black image
+            if not bool(torch.isfinite(img).all()):
+                raise FloatingPointError(
+                    "the fp16 VAE decode produced non-finite values and the snapshot's VAE sets force_upcast=true: use an "
+                    "fp16-safe VAE (madebyollin/sdxl-vae-fp16-fix, which the reference trains with, or taesdxl via "
+                    "`autoencoder`)")
 
         if output_type == "latent":
             images = ops.nhwc_to_nchw(x, channels=lc)
@@ -542,8 +554,11 @@ class B200SDXLControlNetPipeline(B200ControlNetPipeline):
       * added conditioning of U-Net and ControlNet: emb += add_embedding(cat(pooled, sinusoid(time_ids))),
         time_ids = original_size + crops_coords_top_left + target_size (hoisted: constant per call);
       * sdxl-turbo's EulerAncestralDiscreteScheduler (per-step noise drawn from `generator`, gn_euler_ancestral_step).
-    The VAE runs in fp16 on the tensor cores (upstream upcasts an fp16 SDXL VAE to fp32 when config.force_upcast is set;
-    the reference trains with madebyollin/sdxl-vae-fp16-fix, diffusion/README.md:68, which does not need it)."""
+    The VAE runs in fp16 on the tensor cores.  Upstream upcasts an fp16 SDXL VAE to fp32 when its config.json sets
+    force_upcast (stabilityai/sdxl-turbo's does; madebyollin/sdxl-vae-fp16-fix, which the reference trains with,
+    diffusion/README.md:68, does not need it): checkpoint.load_sd_turbo carries the flag into VAEConfig.force_upcast, the
+    constructor warns, and every decode is then checked for non-finite values (FloatingPointError instead of a silent
+    black image)."""
 
     def __init__(self, ops: Ops, unet_sd, controlnet_sd, vae_sd, text_sd=None, text2_sd=None,
                  unet_cfg: UNetConfig = UNetConfig.sdxl(), vae_cfg: VAEConfig = VAEConfig(scaling_factor=0.13025),
@@ -555,6 +570,11 @@ class B200SDXLControlNetPipeline(B200ControlNetPipeline):
             raise ValueError("the SDXL pipeline needs a U-Net with text_time added conditioning (UNetConfig.sdxl())")
         super().__init__(ops, unet_sd, controlnet_sd, vae_sd, text_sd, unet_cfg, vae_cfg, text_cfg, scheduler_cfg,
                          tokenizer=tokenizer, use_cuda_graph=use_cuda_graph, concurrent_controlnet=concurrent_controlnet)
+        if getattr(vae_cfg, "force_upcast", False):
+            import warnings
+
+            warnings.warn("this SDXL snapshot's VAE sets force_upcast=true (diffusers would decode in fp32); decoding in "
+                          "fp16 with a non-finite check — prefer sdxl-vae-fp16-fix or taesdxl", RuntimeWarning)
         self.text2_cfg = text2_cfg
         self.text2_impl = DeviceCLIPText(ops, text2_sd, text2_cfg) if text2_sd is not None else None
         self.text_encoder_2 = _ModuleShim(self.text2_impl)
@@ -636,9 +656,20 @@ class B200SDXLControlNetPipeline(B200ControlNetPipeline):
             raise ValueError(f"output_type {output_type!r} is not supported")
         if image is None:
             raise ValueError("`image` (the ControlNet conditioning image) is required")
+        # the eval loop passes `frame_stack` copies of one prompt string, one per tiled image (eval_genima.py:176-183):
+        # identical rows collapse to one conditioning row that is broadcast over the batch of control images
+        if isinstance(prompt, (list, tuple)) and len(prompt) > 1 and all(isinstance(p, str) for p in prompt):
+            if len(set(prompt)) == 1 and (prompt_2 is None or isinstance(prompt_2, str) or len(set(prompt_2)) == 1):
+                prompt = [prompt[0]]
+                if isinstance(prompt_2, (list, tuple)):
+                    prompt_2 = [prompt_2[0]]
         ctx, pooled = self.encode_prompt_sdxl(prompt, prompt_2, prompt_embeds, pooled_prompt_embeds)
         if pooled.shape[0] != 1:
-            raise NotImplementedError("one prompt per call (it is broadcast over the batch of control images)")
+            if bool((pooled == pooled[:1]).all()) and bool((ctx == ctx[:1]).all()):
+                ctx, pooled = ctx[:1].contiguous(), pooled[:1].contiguous()
+            else:
+                raise NotImplementedError("different prompts within one call are not implemented for SDXL (the added "
+                                          "text_time conditioning is hoisted per call): pass one prompt, or identical rows")
         cond_u8 = self._control_image_u8(image)
         H, W = int(cond_u8.shape[1]), int(cond_u8.shape[2])
         # _get_add_time_ids: original_size + crops_coords_top_left + target_size, each (height, width)
@@ -692,13 +723,14 @@ class B200Pix2PixPipeline(B200ControlNetPipeline):
 
     def _context_kv(self, ctx: torch.Tensor) -> Dict[str, torch.Tensor]:
         key = tensor_key(ctx)
-        if key not in self._kv_cache:
+        hit = self._kv_cache.get(key)
+        if hit is None or hit[1] is not ctx:
             if len(self._kv_cache) > 8:
                 self._kv_cache.clear()
-            self._kv_cache[key] = {"u:" + tr.prefix: tr.project_context(self.ops, ctx)
-                                   for tr in self.unet_impl.transformers()}
-            self._kv_owner = ctx
-        return self._kv_cache[key]
+            kv = {"u:" + tr.prefix: tr.project_context(self.ops, ctx) for tr in self.unet_impl.transformers()}
+            kv["__ctx__"] = ctx
+            hit = self._kv_cache[key] = (kv, ctx)
+        return hit[0]
 
     def _time_rows(self, n_steps: int, batch: int):
         key = (n_steps, batch)

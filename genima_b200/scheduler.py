@@ -51,7 +51,8 @@ class EulerDiscreteSchedule:
         if sp == "trailing":
             ts = np.round(np.arange(T, 0, -T / n)).astype(np.float64) - 1
         elif sp == "leading":
-            ts = (np.arange(0, n) * (T // n)).round()[::-1].astype(np.float64)
+            # EulerDiscreteScheduler.set_timesteps: (arange(n) * (T // n)).round()[::-1] + steps_offset
+            ts = (np.arange(0, n) * (T // n)).round()[::-1].astype(np.float64) + self.cfg.steps_offset
         elif sp == "linspace":
             ts = np.linspace(0, T - 1, n, dtype=np.float64)[::-1].copy()
         else:

@@ -70,8 +70,8 @@ class GenimaStep:
         g = self._graphs.get(key)
         if g is None:
             st = dict(views=views_u8.clone(), lat=latents.clone(), qpos=qpos.to(torch.float32).clone(), task=task_emb)
-            pipe._time_rows(self.n_steps, B)
-            self.act.film_affines(task_emb)
+            temb = pipe._time_rows(self.n_steps, B)
+            film = self.act.film_affines(task_emb)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):   # warm-up outside capture: smem attributes, per-shape caches, allocator
@@ -82,7 +82,9 @@ class GenimaStep:
             l0 = pipe.launch_count()
             with torch.cuda.graph(graph):
                 a_hat, is_pad, gen_tile = self._chain(st["views"], st["lat"], st["qpos"], st["task"], kv, tk)
-            g = dict(graph=graph, st=st, a_hat=a_hat, is_pad=is_pad, tile=gen_tile, kv=kv,
+            # the entry owns every buffer the graph reads by raw pointer (static inputs, cross-attention K/V and their
+            # context, per-step time-embedding rows, FiLM affines): cache evictions elsewhere cannot free them
+            g = dict(graph=graph, st=st, a_hat=a_hat, is_pad=is_pad, tile=gen_tile, kv=kv, ctx=ctx, temb=temb, film=film,
                      launches=pipe.launch_count() - l0)
             if len(self._graphs) > 4:
                 self._graphs.clear()

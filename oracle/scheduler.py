@@ -10,8 +10,10 @@ import torch
 
 
 class EulerDiscreteOracle:
-    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, timestep_spacing="trailing"):
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, timestep_spacing="trailing",
+                 steps_offset=0):
         self.num_train_timesteps = num_train_timesteps
+        self.steps_offset = steps_offset
         betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
         self.train_sigmas = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
@@ -24,7 +26,8 @@ class EulerDiscreteOracle:
         if self.timestep_spacing == "trailing":
             ts = np.round(np.arange(T, 0, -T / n)).astype(np.float64) - 1
         elif self.timestep_spacing == "leading":
-            ts = (np.arange(0, n) * (T // n)).round()[::-1].astype(np.float64)
+            # upstream: timesteps = (arange(n) * step_ratio).round()[::-1]; timesteps += self.config.steps_offset
+            ts = (np.arange(0, n) * (T // n)).round()[::-1].astype(np.float64) + self.steps_offset
         elif self.timestep_spacing == "linspace":
             ts = np.linspace(0, T - 1, n, dtype=np.float64)[::-1].copy()
         else:

@@ -4,6 +4,8 @@ import os
 import pytest
 import torch
 
+from fake_workspace import write_tiny_clip_tokenizer
+
 from genima_b200 import checkpoint as ckpt
 from genima_b200 import weights as W
 from genima_b200.configs import ACTConfig, CLIPTextConfig, UNetConfig, VAEConfig
@@ -92,51 +94,26 @@ def test_sdxl_snapshot_round_trip(tmp_path):
     want = W.synth_state_dict(W.clip_text_shapes(t2), salt=4)
     assert all(torch.equal(out["text2"][k], v) for k, v in want.items())
     assert "add_embedding.linear_1.weight" in out["controlnet"]
+    # stabilityai/sdxl-turbo's VAE config says force_upcast: true (diffusers decodes it in fp32): the flag must survive
+    assert out["vae_cfg"].force_upcast is False
+    import json
+    vj = os.path.join(d["sd_ckpt"], "vae", "config.json")
+    with open(vj) as f:
+        j = json.load(f)
+    with open(vj, "w") as f:
+        json.dump(dict(j, force_upcast=True), f)
+    assert ckpt.load_sdxl(d["sd_ckpt"], d["diffusion_ckpt"])["vae_cfg"].force_upcast is True
     with pytest.raises(ValueError):                # an SD-2.x snapshot is not an SDXL snapshot
         d2 = ckpt.save_synthetic_checkpoints(str(tmp_path / "sd2"), UNetConfig.tiny(), VAEConfig.tiny(),
                                              CLIPTextConfig.tiny(), ACTConfig.tiny())
         ckpt.load_sdxl(d2["sd_ckpt"], d2["diffusion_ckpt"])
 
 
-def _write_tiny_clip_tokenizer(path):
-    """A syntactically complete CLIP BPE vocabulary (byte alphabet + a few merges): no real vocabulary exists offline."""
-    import json
-
-    bs = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAD)) + list(range(0xAE, 0x100))
-    cs, n = bs[:], 0
-    for b in range(256):
-        if b not in bs:
-            bs.append(b)
-            cs.append(256 + n)
-            n += 1
-    chars = [chr(c) for c in cs]
-    vocab = {}
-    for c in chars:
-        vocab[c] = len(vocab)
-    for c in chars:
-        vocab[c + "</w>"] = len(vocab)
-    merges = ["t h", "th e</w>", "o p", "op e", "ope n</w>", "b o", "bo x</w>"]
-    for m in merges:
-        a, b = m.split()
-        vocab.setdefault(a + b, len(vocab))
-    vocab["<|startoftext|>"] = len(vocab)
-    vocab["<|endoftext|>"] = len(vocab)
-    os.makedirs(path, exist_ok=True)
-    with open(os.path.join(path, "vocab.json"), "w") as f:
-        json.dump(vocab, f)
-    with open(os.path.join(path, "merges.txt"), "w") as f:
-        f.write("#version: 0.2\n" + "\n".join(merges) + "\n")
-    with open(os.path.join(path, "tokenizer_config.json"), "w") as f:
-        json.dump({"model_max_length": 77, "pad_token": "<|endoftext|>", "bos_token": "<|startoftext|>",
-                   "eos_token": "<|endoftext|>", "unk_token": "<|endoftext|>", "tokenizer_class": "CLIPTokenizer"}, f)
-    return vocab
-
-
 def test_snapshot_tokenizer_is_picked_up(dirs):
     """String prompts (what controller/eval_genima.py:178 passes) tokenize through the snapshot's own tokenizer files the
     way diffusers' encode_prompt does: BOS, BPE ids, EOS, padded to 77."""
     assert ckpt.load_sd_turbo(dirs["sd_ckpt"], dirs["diffusion_ckpt"])["tokenizer"] is None      # no tokenizer/ directory
-    vocab = _write_tiny_clip_tokenizer(os.path.join(dirs["sd_ckpt"], "tokenizer"))
+    vocab = write_tiny_clip_tokenizer(os.path.join(dirs["sd_ckpt"], "tokenizer"))
     tok = ckpt.load_sd_turbo(dirs["sd_ckpt"], dirs["diffusion_ckpt"])["tokenizer"]
     ids = tok(["open the box", "the box"])
     assert ids.shape == (2, 77) and ids.dtype == torch.int64

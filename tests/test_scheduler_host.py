@@ -116,3 +116,35 @@ def test_ddim_trailing_equals_euler_in_scaled_variable():
         a, b = dd.ddim_coeffs(i)
         y = a * y + b * eps
         assert torch.allclose(y, x / math.sqrt(float(sig[i + 1]) ** 2 + 1), rtol=1e-4, atol=1e-4)
+
+
+def test_euler_leading_adds_steps_offset():
+    """EulerDiscreteScheduler 'leading' spacing: (arange(n) * (T // n))[::-1] + steps_offset (sdxl-base / SD-1.x ship
+    leading spacing with steps_offset 1): n = 4 -> [751, 501, 251, 1]."""
+    from oracle.scheduler import EulerDiscreteOracle
+
+    s = EulerDiscreteSchedule(SchedulerConfig(timestep_spacing="leading", steps_offset=1))
+    ts, sig = s.set_timesteps(4)
+    assert ts.tolist() == [751.0, 501.0, 251.0, 1.0]
+    o = EulerDiscreteOracle(timestep_spacing="leading", steps_offset=1)
+    ots, osig = o.set_timesteps(4)
+    assert np.array_equal(ts, ots) and np.array_equal(sig, osig)
+    assert EulerDiscreteSchedule(SchedulerConfig(timestep_spacing="leading")).set_timesteps(4)[0].tolist() == [750.0, 500.0, 250.0, 0.0]
+
+
+def test_scheduler_json_defaults_and_unsupported_flags():
+    from genima_b200.checkpoint import scheduler_config_from_json
+
+    # diffusers' defaults when the key is missing: Euler / Euler-ancestral 'linspace', DDIM 'leading'
+    assert scheduler_config_from_json({"_class_name": "EulerDiscreteScheduler"}).timestep_spacing == "linspace"
+    assert scheduler_config_from_json({"_class_name": "EulerAncestralDiscreteScheduler"}).timestep_spacing == "linspace"
+    assert scheduler_config_from_json({"_class_name": "DDIMScheduler"}).timestep_spacing == "leading"
+    turbo = {"_class_name": "EulerDiscreteScheduler", "timestep_spacing": "trailing", "steps_offset": 1,
+             "use_karras_sigmas": False, "interpolation_type": "linear", "rescale_betas_zero_snr": False,
+             "timestep_type": "discrete", "final_sigmas_type": "zero", "sigma_min": None, "sigma_max": None}
+    cfg = scheduler_config_from_json(turbo)
+    assert cfg.timestep_spacing == "trailing" and cfg.steps_offset == 1
+    for k, v in (("use_karras_sigmas", True), ("interpolation_type", "log_linear"), ("rescale_betas_zero_snr", True),
+                 ("timestep_type", "continuous"), ("final_sigmas_type", "sigma_min"), ("thresholding", True)):
+        with pytest.raises(NotImplementedError, match=k):
+            scheduler_config_from_json(dict(turbo, **{k: v}))
