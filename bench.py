@@ -192,12 +192,104 @@ def workload_config(args, ucfg):
 
 
 # ------------------------------------------------------------------------------------------------ own arm
+def stub_tokenizer(prompts):
+    """Deterministic stand-in for the CLIP BPE tokenizer (no vocabulary exists offline): BOS 49406, one id
+    per whitespace-separated word (crc32 -> [1000, 41000)), EOS 49407, zero padding to 77 (the SD-2.x tokenizer pads
+    with id 0).  Lets the e2e leg hand the pipeline the STRING prompts the reference loop builds
+    (controller/eval_genima.py:178), so tokenisation, the prompt-cache lookup and its host-side hashing are timed."""
+    import zlib
+
+    ids = torch.zeros(len(prompts), 77, dtype=torch.int64)
+    for r, p in enumerate(prompts):
+        toks = [49406] + [1000 + zlib.crc32(w.encode()) % 40000 for w in p.split()][:75] + [49407]
+        ids[r, :len(toks)] = torch.tensor(toks)
+    return ids
+
+
+def graph_kernel_times(fn, reps: int = 3, groups=("gemm_tc_kernel", "attn_tc_kernel")):
+    """Per-kernel device intervals of `fn()` (a CUDA-graph replay) from CUPTI through torch.profiler: returns
+    {kernel name: dict(n=launches per call, sum_ms=sum of durations per call, busy_ms=length of the UNION of the kernel's
+    intervals per call)} plus "__span_ms__".  The union is the time during which at least one instance of the kernel is
+    executing: it can never exceed the step time, whatever overlaps on the other streams."""
+    from torch.profiler import ProfilerActivity, profile
+
+    fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+    by = {}
+    t_lo, t_hi = None, None
+    for ev in prof.events():
+        if ev.device_type is None or "cuda" not in str(ev.device_type).lower():
+            continue
+        name = ev.name.split("(")[0].replace("void ", "").strip()
+        tr = ev.time_range
+        by.setdefault(name, []).append((tr.start, tr.end))
+        t_lo = tr.start if t_lo is None else min(t_lo, tr.start)
+        t_hi = tr.end if t_hi is None else max(t_hi, tr.end)
+    def union(iv):
+        iv = sorted(iv)
+        busy, cur_s, cur_e = 0.0, None, None
+        for a, b in iv:
+            if cur_e is None or a > cur_e:
+                if cur_e is not None:
+                    busy += cur_e - cur_s
+                cur_s, cur_e = a, b
+            else:
+                cur_e = max(cur_e, b)
+        if cur_e is not None:
+            busy += cur_e - cur_s
+        return busy
+
+    out = {}
+    for name, iv in by.items():
+        out[name] = {"n": len(iv) / reps, "sum_ms": sum(b - a for a, b in iv) / reps / 1e3,
+                     "busy_ms": union(iv) / reps / 1e3}
+    for grp in groups:          # all template flavours of one kernel together
+        iv = [x for name, v in by.items() if grp in name for x in v]
+        out["__group__" + grp] = {"n": len(iv) / reps, "sum_ms": sum(b - a for a, b in iv) / reps / 1e3,
+                                  "busy_ms": union(iv) / reps / 1e3}
+    out["__span_ms__"] = (t_hi - t_lo) / reps / 1e3 if t_lo is not None else None
+    return out
+
+
+def gpu_baseline_leg(args):
+    """Stock PyTorch fp16 on the same GPU (what the reference's diffusers / RoboBase stack would run here if it were
+    installable: cuDNN / cuBLAS / SDPA library kernels on the oracle's restatement of the graph), in a subprocess:
+    eager and CUDA-graphed always; torch.compile in the reference's own mode (`reduce-overhead`,
+    controller/agent/sd_controlnet_agent.py:52-62) and `max-autotune` when asked for (--gpu-baseline all) or from the
+    committed capture of the same script (profiles/) otherwise.  A BASELINE leg like cpu_baseline: never the product."""
+    modes = {"eager": "eager,graph", "all": "eager,graph,compile-reduce-overhead,compile-max-autotune"}[args.gpu_baseline]
+    res = {}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "stock_torch_gpu_baseline.py"), "--modes", modes,
+                            "--denoise-steps", str(args.denoise_steps)], capture_output=True, text=True,
+                           timeout=3000 if args.gpu_baseline == "all" else 240)
+        last = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+        res = json.loads(last[-1]) if last else {"error": (r.stderr or "no output")[-400:]}
+    except Exception as ex:  # noqa: BLE001
+        res = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+    if args.gpu_baseline != "all":
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_gpu_baseline_compile.json")) as f:
+                cap = json.load(f)
+            res["committed_capture"] = {k: cap.get(k) for k in ("compile_reduce_overhead_ms", "compile_max_autotune_ms",
+                                                                "compile_reduce_overhead_error",
+                                                                "compile_max_autotune_error", "torch", "gpu")}
+            res["committed_capture"]["source"] = ("profiles/r2_gpu_baseline_compile.json: the same script run once with "
+                                                  "--modes all on a B200 of this pool (compilation takes minutes)")
+        except Exception:
+            pass
+    return res
+
+
 def run_ours(args):
     import torch.distributed as dist
 
     from genima_b200 import distributed as gd
-    from genima_b200.act_policy import DeviceACT
-    from genima_b200.agents import B200ControlNetAgent, B200GenimaACT, B200GenimaACTPolicy
+    from genima_b200.agents import B200ControlNetAgent, B200GenimaACT
     from genima_b200.host_glue import tile_images, untile_images
     from genima_b200.ops import Ops
     from genima_b200.pipeline import B200ControlNetPipeline
@@ -210,36 +302,76 @@ def run_ours(args):
         raise RuntimeError("bench.py (own arm) needs a B200: genima_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    comm_init_s = 0.0
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version at VERSION/INFO)
+        # NCCL's own INIT lines (communicator size, transports) are left visible: they prove how many ranks joined.
+        # They go to stdout BEFORE the JSON line, which is always the LAST line this program prints.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        t_c = time.perf_counter()
         dist.init_process_group("nccl", device_id=dev)
+        warm = torch.ones(1, device=dev)
+        dist.all_reduce(warm)                       # communicator bring-up (rings / NVLS set-up) happens here, once
+        torch.cuda.synchronize()
+        comm_init_s = time.perf_counter() - t_c
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
 
     ucfg, vcfg, acfg = presets(args.preset, args.autoencoder)
+    tiny = args.preset == "tiny"
+    tcfg = CLIPTextConfig.tiny() if tiny else CLIPTextConfig.sd_turbo()
+    ccfg = CLIPTextConfig.tiny(projection_dim=acfg.task_emb_dim) if tiny else CLIPTextConfig.vit_b32()
     shapes = model_shapes(ucfg, vcfg, acfg)
+    shapes["text"] = W.clip_text_shapes(tcfg)       # SD text encoder (prompt -> context, cached per episode)
+    shapes["clip"] = W.clip_text_shapes(ccfg)       # controller's CLIP ViT-B/32 text tower (task embedding, cached)
     # ---- weights: rank 0 synthesises, ONE broadcast of the packed arena, every rank binds views into its copy
     t_w = time.perf_counter()
-    sds_host = synth_all(shapes) if rank == 0 else None
-    sds, arena = gd.broadcast_weights(shapes, sds_host, src=0, device=dev)
-    torch.cuda.synchronize()
-    weight_s = time.perf_counter() - t_w
+    sds_host = None
+    if rank == 0:
+        sds_host = synth_all(model_shapes(ucfg, vcfg, acfg))
+        sds_host["text"] = W.synth_state_dict(shapes["text"], salt=6)
+        sds_host["clip"] = W.synth_state_dict(shapes["clip"], salt=7)
+    synth_s = time.perf_counter() - t_w
+    timings = {}
+    sds, arena = gd.broadcast_weights(shapes, sds_host, src=0, device=dev, timings=timings)
 
     ops = Ops(local)
-    pipe = B200ControlNetPipeline(ops, sds["unet"], sds["controlnet"], sds["vae"], None, ucfg, vcfg,
-                                  use_cuda_graph=True)
-    act = DeviceACT(ops, sds["act"], acfg)
-    step = GenimaStep(pipe, act, num_inference_steps=args.denoise_steps, use_cuda_graph=True)
-    views, qpos, task, ctx, lat = make_inputs(ucfg, acfg, seed=rank)
+    pipe = B200ControlNetPipeline(ops, sds["unet"], sds["controlnet"], sds["vae"], sds["text"], ucfg, vcfg, tcfg,
+                                  tokenizer=stub_tokenizer, use_cuda_graph=True)
+    # plugin point 2, built the way GenimaEvalWorkspace builds it (eval_genima.py:55-66, 91-103)
     S = acfg.image_size
+    cameras = ["wrist", "front", "right_shoulder", "left_shoulder"]
+    controller = B200GenimaACT(device=dev, observation_space=None, action_space=None, act_cfg=acfg, ops=ops,
+                               clip_state_dict=sds["clip"], clip_cfg=ccfg, num_train_envs=1)
+    controller.train(False)
+    controller.load_state_dict({f"actor.{k}": v for k, v in sds["act"].items()}, strict=False)
+    act = controller.actor.impl                                    # the DeviceACT both legs share
+    step = GenimaStep(pipe, act, num_inference_steps=args.denoise_steps, use_cuda_graph=True)
+
+    views, qpos, _task, _ctx, lat = make_inputs(ucfg, acfg, seed=rank)
+    goal = "open the box"
+    prompts = [f"tiled perspectives of a robot arm executing '{goal}'"]                  # eval_genima.py:178
+    negative_prompts = ["monochrome, lowres, bad anatomy, worst quality, low quality"]   # eval_genima.py:181-183
+    lang_np = stub_tokenizer([goal]).numpy().astype(np.int32)[:, None, :]                # obs["lang_tokens"] [T=1,77]->[1,1,77]
+    d_ctx = pipe.encode_prompt(prompts)                                                  # text encoder: once per episode
+    d_task = controller.encode_clip_text(torch.from_numpy(lang_np).to(dev))[0]           # CLIP text tower: once per episode
     d_views = views.permute(0, 2, 3, 1).contiguous()[None].to(dev)          # [1, 4, S, S, 3] u8
-    d_lat, d_qpos, d_task, d_ctx = lat.to(dev), qpos.to(dev), task.to(dev), ctx.to(dev)
+    d_lat, d_qpos = lat.to(dev), qpos.to(dev)
 
     def barrier():
         if world > 1:
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
+
+    # ---- tile configurations: rank 0 measures them on its first (eager) pass, every other rank adopts them, so all
+    # ranks launch identical kernels (bit-identical results wherever an episode is sharded)
+    tune_bytes = 0
+    if world > 1:
+        if rank == 0:
+            step(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx)
+        barrier()
+        tune_bytes = gd.sync_tune_caches(pipe.all_ops(), src=0)
 
     # ---- device-resident timed region
     for _ in range(max(args.warmup, 3)):
@@ -263,17 +395,18 @@ def run_ours(args):
     launches = step.launches_per_step * args.steps
     value = world * args.steps / (ms * 1e-3)
     a_hat = out["a_hat"].float().cpu()
+    tile_dev = out["tile_u8"].clone()
 
     # ---- U-Net + ControlNet only (sub-metric "U-Net ms/step"): 5-step loop to latents, graph replay
     for _ in range(3):
-        pipe(prompt_embeds=d_ctx, image=out["tile_u8"], num_inference_steps=args.denoise_steps, guidance_scale=0.0,
+        pipe(prompt_embeds=d_ctx, image=tile_dev, num_inference_steps=args.denoise_steps, guidance_scale=0.0,
              latents=d_lat, output_type="latent")
     torch.cuda.synchronize()
     u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nrep = max(5, min(args.steps, 30))
     u0.record()
     for _ in range(nrep):
-        pipe(prompt_embeds=d_ctx, image=out["tile_u8"], num_inference_steps=args.denoise_steps, guidance_scale=0.0,
+        pipe(prompt_embeds=d_ctx, image=tile_dev, num_inference_steps=args.denoise_steps, guidance_scale=0.0,
              latents=d_lat, output_type="latent")
     u1.record()
     torch.cuda.synchronize()
@@ -305,7 +438,7 @@ def run_ours(args):
                             "max_abs_diff_vs_batch_1": float((ba[0].cpu() - a_hat[0]).abs().max())})
         out = step(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx)   # back to the batch-1 graph / buffers
 
-    # ---- e2e through the reference-facing API with host buffers
+    # ---- e2e through the reference-facing API with host buffers: the loop body of controller/eval_genima.py:163-249
     from PIL import Image
 
     agent = B200ControlNetAgent.__new__(B200ControlNetAgent)       # bind the already-built pipeline (no second copy)
@@ -313,66 +446,64 @@ def run_ours(args):
     agent.pipe, agent._ops = pipe, ops
     agent.set_optimizations()
     agent.common_setup()
-    policy = B200GenimaACTPolicy.__new__(B200GenimaACTPolicy)
-    policy.cfg, policy.ops, policy._sd, policy.impl, policy.training = acfg, ops, sds["act"], act, False
-    controller = B200GenimaACT(policy)
-    lang_tokens = torch.zeros(1, 1, 77, dtype=torch.int32)
-    controller._emb_cache[lang_tokens.reshape(-1, 77).numpy().tobytes()] = (d_task, None)   # CLIP output cached per episode
-    cameras = ["wrist", "front", "right_shoulder", "left_shoulder"]
     obs_np = {f"{c}_rgb": views[i:i + 1].numpy() for i, c in enumerate(cameras)}             # [T=1, 3, S, S] u8
-    low_dim = qpos.numpy()[None]                                                             # [1, T=1, 8]
-    gen = [torch.Generator(device=dev).manual_seed(2)]
+    low_dim = qpos.numpy()                                                                   # [T=1, 8]
+    gen = [torch.Generator(device=dev).manual_seed(2)]                                       # eval_genima.py:129-135
     n_e2e = max(3, min(args.steps, args.e2e_steps))
     h2d = d2h = 0
 
-    # The hot path starts at tile_images, whose inputs are the cameras' PIL images: the env-side
-    # uint8 CHW -> PIL conversion of controller/eval_genima.py:166-172 is outside it and is done once, like the oracle arm
-    # starts from numpy views.
-    rgbs = [Image.fromarray(np.ascontiguousarray(np.transpose(obs_np[f"{c}_rgb"][0], (1, 2, 0)))) for c in cameras]
-
     def e2e_step():
         nonlocal h2d, d2h
+        # eval_genima.py:163-186: env observation (uint8 CHW numpy) -> PIL -> tile
+        rgbs = [Image.fromarray(np.transpose(obs_np[f"{c}_rgb"][0], (1, 2, 0))) for c in cameras]
         tiles = tile_images(rgbs, 1) if S == 256 else [Image.fromarray(
             np.concatenate([np.concatenate([np.asarray(rgbs[0]), np.asarray(rgbs[1])], 1),
                             np.concatenate([np.asarray(rgbs[2]), np.asarray(rgbs[3])], 1)], 0))]
-        target = agent.infer(images=tiles, prompts=None, negative_prompts=None, prompt_embeds=d_ctx,
+        # :199-210 (string prompts -> tokenizer -> prompt cache; CUDA generator shared across the batch)
+        target = agent.infer(images=tiles, prompts=prompts, negative_prompts=negative_prompts,
                              num_inference_steps=args.denoise_steps, guidance_scale=0.0, generator=gen * len(tiles))
+        # :224-234
         if S == 256:
             un = untile_images(target[0], cameras, agent.transform_to_half_resolution)
         else:
             g = np.asarray(target[0][0])
             quads = [g[:S, :S], g[:S, S:], g[S:, :S], g[S:, S:]]
-            un = {c: np.transpose(q, (2, 0, 1))[None] for c, q in zip(cameras, quads)}
+            un = {c: np.ascontiguousarray(np.transpose(q, (2, 0, 1))[None]) for c, q in zip(cameras, quads)}
         obs = {f"{c}_rgb": un[c] for c in cameras}
         obs["low_dim_state"] = low_dim
-        obs = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev).unsqueeze(0) for k, v in obs.items()}
-        obs["lang_tokens"] = lang_tokens
+        obs["lang_tokens"] = lang_np[0]
+        # :237-249
+        obs = {k: torch.from_numpy(v).to(dev).unsqueeze(0) for k, v in obs.items()}
         actions = controller.act(obs, step=0, eval_mode=True)[0]
         actions = actions.detach().cpu().numpy()
-        h2d = tiles[0].size[0] * tiles[0].size[1] * 3 + sum(v.nbytes for v in un.values()) + low_dim.nbytes
-        d2h = tiles[0].size[0] * tiles[0].size[1] * 3 + actions.nbytes
+        h2d = (tiles[0].size[0] * tiles[0].size[1] * 3 + sum(v.nbytes for v in un.values()) + low_dim.nbytes
+               + lang_np[0].nbytes)
+        d2h = tiles[0].size[0] * tiles[0].size[1] * 3 + actions.nbytes + lang_np[0].nbytes   # (token ids read back: cache key)
         return actions
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(n_e2e):
-        actions = e2e_step()
-    torch.cuda.synchronize()
+    with torch.inference_mode():                                                             # eval_genima.py:199
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(n_e2e):
+            actions = e2e_step()
+        torch.cuda.synchronize()
     e2e_ms = gd.reduce_max((time.perf_counter() - w0) * 1e3, device=dev)
     e2e_value = world * n_e2e / (e2e_ms * 1e-3)
 
-    # ---- kernel-class profile of ONE eager step (CUDA events around every C-ABI call, inside the library)
-    roofline, classes = None, None
-    if rank == 0:
+    # ---- roofline of the dominant kernel (gemm_tc_kernel: every convolution and linear layer)
+    #   FLOPs / bytes: counted by the library per gn_linear / gn_conv2d call during ONE eager step (gn_profile_*);
+    #   time: CUPTI intervals of the kernel's launches inside the REPLAYED graph (torch.profiler), as the length of their
+    #   union -- the time during which a gemm_tc_kernel is executing, <= the step time by construction.
+    roofline, classes, kernels = None, None, None
+    if rank == 0 and not args.no_roofline:
         eager = GenimaStep(pipe, act, num_inference_steps=args.denoise_steps, use_cuda_graph=False)
         eager(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx)
         torch.cuda.synchronize()
         for o in pipe.all_ops():
             o.profile_begin()
         eager(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx)
-        classes = None
         for o in pipe.all_ops():           # the ControlNet encoder runs through its own handle / stream
             part = o.profile_end()
             if classes is None:
@@ -381,24 +512,41 @@ def run_ours(args):
                 for k, v in part.items():
                     for f in v:
                         classes[k][f] += v[f]
-        roofline = make_roofline(classes, ms / args.steps)
+        try:
+            kernels = graph_kernel_times(lambda: step(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx))
+        except Exception as ex:  # noqa: BLE001
+            kernels = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        roofline = make_roofline(classes, kernels, ms / args.steps)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        if sds_host is None:
-            sds_host = synth_all(shapes)
-        cstep = cpu_agent_step_fn(ucfg, vcfg, acfg, sds_host, args.denoise_steps)
+        from oracle.pipeline import agent_step as oracle_agent_step
+
+        w32 = {m: {k: v.float().cpu() for k, v in sds[m].items()} for m in ("unet", "controlnet", "vae", "act")}
+        views_hwc = views.permute(0, 2, 3, 1).contiguous().numpy()
         c0 = time.perf_counter()
-        ref = cstep()
+        with torch.no_grad():
+            ref = oracle_agent_step(w32, ucfg, vcfg, acfg, views_hwc, d_ctx.float().cpu(), lat, qpos,
+                                    d_task.float().cpu(), args.denoise_steps)
         cdt = time.perf_counter() - c0
         err = float((a_hat - ref["a_hat"]).abs().max() / ref["a_hat"].abs().max())
+        dd = np.abs(tile_dev.cpu().numpy()[0].astype(np.int32) - ref["tile_u8"][0].astype(np.int32))
         cpu_baseline = {"value": 1.0 / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "1 full agent step (same inputs, same synthetic weights) of the fp32 PyTorch-CPU "
                                   "oracle, oracle/pipeline.py::agent_step, no warm-up",
-                        "a_hat_normalised_max_err_vs_device": err}
+                        "a_hat_normalised_max_err_vs_device": err, "tile_max_abs_diff_levels": int(dd.max()),
+                        "tile_frac_within_1_level": float((dd <= 1).mean())}
+        del w32
 
+    gpu_baseline = None
+    if rank == 0 and world == 1 and args.gpu_baseline != "none":
+        gpu_baseline = gpu_baseline_leg(args)
+
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -407,25 +555,28 @@ def run_ours(args):
             "unet_ms_per_step": unet_ms, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
-                    "api": "tile_images + B200ControlNetAgent.infer + untile_images + B200GenimaACT.act "
-                           "(PIL / numpy host buffers in, numpy actions out)"},
+                    "api": "the loop body of controller/eval_genima.py:163-249: uint8 CHW observations -> PIL -> tile_images "
+                           "-> B200ControlNetAgent.infer(string prompts through a stub tokenizer + prompt cache, CUDA "
+                           "generator) -> untile_images -> obs tensors .to(device) (fresh lang_tokens every step) -> "
+                           "B200GenimaACT.act -> .cpu().numpy(), under torch.inference_mode()"},
             "gpu_launches": int(launches), "launches_per_step": int(step.launches_per_step),
-            "roofline": roofline, "kernel_classes": classes, "cpu_baseline": cpu_baseline, "batched": batched,
-            "weights_broadcast_s": weight_s, "weights_gb": arena.numel() * 2 / 1e9,
+            "roofline": roofline, "kernel_classes": classes, "cpu_baseline": cpu_baseline, "gpu_baseline": gpu_baseline,
+            "batched": batched,
+            "weights": {"gb": arena.numel() * 2 / 1e9, "synthesis_s_rank0": synth_s, "pack_h2d_s": timings.get("pack_s"),
+                        "broadcast_s": timings.get("broadcast_s"), "comm_init_s": comm_init_s,
+                        "broadcast_gb_per_s": (arena.numel() * 2 / 1e9 / timings["broadcast_s"]
+                                               if timings.get("broadcast_s") else None),
+                        "tune_cache_bytes_broadcast": tune_bytes},
             "agent_step_tflop": (args.denoise_steps * FLOPS_DENOISE_ITER
                                  + (0.14e12 if "taesd" in (args.autoencoder or "") else FLOPS_VAE) + FLOPS_ACT) / 1e12
             if args.preset != "tiny" else None,
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier(device_ids=[local])
-        dist.destroy_process_group()
+        print(json.dumps(line), flush=True)          # ALWAYS the last line on stdout
     return 0
 
 
-def make_roofline(classes, step_ms):
-    """Dominant kernel = gemm_tc_kernel (gn_linear + gn_conv2d launches: every convolution and linear layer).
-    achieved = algorithmic FLOPs of those launches in one step / their summed CUDA-event durations."""
+def make_roofline(classes, kernels, step_ms):
+    """Dominant kernel = gemm_tc_kernel (gn_linear + gn_conv2d launches: every convolution and linear layer)."""
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -436,39 +587,47 @@ def make_roofline(classes, step_ms):
     src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); fp16 uses the same pipe"
     if not peak:
         peak, src = 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
-    g_ms = classes["linear"]["ms"] + classes["conv"]["ms"]
     g_fl = classes["linear"]["flops"] + classes["conv"]["flops"]
-    tot_ms = sum(c["ms"] for c in classes.values())
-    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
-    # DRAM bytes the GEMM launches of one step really moved, from the committed ncu capture of the same step (the
-    # default workload only: other presets / autoencoders have no capture)
+    g_by = classes["linear"]["bytes"] + classes["conv"]["bytes"]
+    g_calls = classes["linear"]["calls"] + classes["conv"]["calls"]
+    gk = (kernels or {}).get("__group__gemm_tc_kernel")
+    busy = sum_ms = n = None
+    if gk and gk["n"] > 0:
+        sum_ms, n, busy = gk["sum_ms"], gk["n"], gk["busy_ms"]     # union over ALL flavours of the kernel template
+    t_ms = busy if busy else step_ms
+    achieved = g_fl / (t_ms * 1e-3) / 1e12
+    # DRAM bytes the GEMM launches of one step really moved, from the committed ncu capture (default workload only)
     traffic = traffic_step = traffic_src = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1i_dram_traffic.json")) as f:
-            cap = json.load(f)
-        k = cap["kernels"]["gn::gemm_tc_kernel"]
-        if k["launches"] == classes["linear"]["calls"] + classes["conv"]["calls"]:
+    for cap_name in ("r2_dram_traffic.json", "r1i_dram_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", cap_name)) as f:
+                cap = json.load(f)
+            k = cap["kernels"]["gn::gemm_tc_kernel"]
             traffic = k["dram_bytes_per_launch"]
             traffic_step = k["dram_read_bytes_per_step"] + k["dram_write_bytes_per_step"]
-            traffic_src = ("profiles/r1i_dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of the "
-                           f"{k['launches']} gemm_tc_kernel launches of one agent step (ncu, cold cache per launch), "
-                           "average per launch; algorithmic bytes of the same launches: "
-                           f"{(classes['linear']['bytes'] + classes['conv']['bytes']) / 1e9:.2f} GB per step")
-    except Exception:
-        pass
+            traffic_src = (f"profiles/{cap_name}: dram__bytes_read.sum + dram__bytes_write.sum of the {k['launches']} "
+                           "gemm_tc_kernel launches of one agent step (ncu, cold cache per launch), average per launch"
+                           f"; this run launches {g_calls} per step; algorithmic bytes of these launches: "
+                           f"{g_by / 1e9:.2f} GB per step")
+            break
+        except Exception:
+            continue
     return {"bound": "tensor", "kernel": "gemm_tc_kernel (gn_conv2d implicit GEMM + gn_linear)", "achieved": achieved,
             "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_bytes_per_step": traffic_step, "traffic_source": traffic_src, "peak_source": src,
-            # the same FLOPs over the kernel's proportional share of the graph-replayed step (PDL and the two-stream overlap
-            # hide most of the ~5 us per launch that an event pair around a single eager launch includes)
-            "achieved_graph_attributed": (g_fl / (step_ms * 1e-3 * g_ms / tot_ms) / 1e12) if g_ms > 0 and tot_ms else None,
-            "frac_graph_attributed": (g_fl / (step_ms * 1e-3 * g_ms / tot_ms) / 1e12 / peak) if g_ms > 0 and tot_ms else None,
-            "launches_per_step": classes["linear"]["calls"] + classes["conv"]["calls"],
-            "kernel_ms_per_step": g_ms, "share_of_step_kernel_time": g_ms / tot_ms if tot_ms else None,
-            "algorithmic_tflop_per_step": g_fl / 1e12,
-            "how": "one eager (non-graph) agent step after the timed region, CUDA event pair recorded by the library "
-                   "around every gn_linear / gn_conv2d call on the launching stream; graph-replayed step takes "
-                   f"{step_ms:.3f} ms"}
+            "launches_per_step": g_calls, "graph_launches_per_step": n,
+            "kernel_ms_per_step": t_ms, "kernel_ms_sum_of_durations": sum_ms, "step_ms": step_ms,
+            "graph_span_ms": (kernels or {}).get("__span_ms__"),
+            "algorithmic_tflop_per_step": g_fl / 1e12, "algorithmic_gb_per_step": g_by / 1e9,
+            "hbm_frac_of_measured": (g_by / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None,
+            "eager_event_pair_ms": classes["linear"]["ms"] + classes["conv"]["ms"],
+            "kernels_in_graph": {k: v for k, v in sorted((kernels or {}).items(), key=lambda kv: -(kv[1]["busy_ms"] if isinstance(kv[1], dict) else 0))[:12]
+                                 if isinstance(v, dict)},
+            "how": "achieved = algorithmic FLOPs of the gn_linear / gn_conv2d calls of one agent step (counted by the "
+                   "library, 2*M*N*K_real) / kernel_ms_per_step; kernel_ms_per_step = length of the union of the "
+                   "gemm_tc_kernel intervals CUPTI records inside one REPLAYED step graph (torch.profiler on the graph "
+                   "replay, warm, on the streams the graph launches on): the time a gemm_tc_kernel is executing, <= the "
+                   f"step's {step_ms:.3f} ms"}
 
 
 def main():
@@ -483,6 +642,10 @@ def main():
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true", help="skip the tile_batch 2 / 4 throughput variant")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-class profile / CUPTI pass")
+    ap.add_argument("--gpu-baseline", default="eager", choices=["none", "eager", "all"],
+                    help="stock PyTorch fp16 on the same GPU: 'eager' = eager + CUDA graph (seconds); 'all' adds "
+                         "torch.compile reduce-overhead / max-autotune (minutes)")
     ap.add_argument("--autoencoder", default="", help="'taesd': decode with AutoencoderTiny (reference option "
                                                       "eval_cfg.autoencoder); default: the KL-VAE of the headline config")
     args = ap.parse_args()

@@ -63,6 +63,8 @@ SIGNATURES = {
     "gn_set_gn_max_ctas": (_i, [_vp, _i]),
     "gn_set_staged_epilogue": (_i, [_vp, _i]),
     "gn_set_autotune": (_i, [_vp, _i]),
+    "gn_tune_cache_export": (_i64, [_vp, C.c_char_p, _i64]),
+    "gn_tune_cache_import": (_i, [_vp, C.c_char_p, _i64, _i]),
     "gn_set_gemm_occupancy": (_i, [_vp, _i]),
     "gn_set_attention_kv_split": (_i, [_vp, _i]),
     "gn_set_gemm_multicast": (_i, [_vp, _i, _i]),

@@ -479,7 +479,7 @@ class B200GenimaACT:
         if self.clip is None:
             sd = self._clip_sd
             if sd is None and self._clip_ckpt is not None:
-                sd = ckpt.load_openai_clip_text(self._clip_ckpt)
+                sd = ckpt.load_openai_clip_text(self._clip_ckpt, self.clip_cfg)
             if sd is None:
                 raise RuntimeError(
                     "no CLIP text tower bound: the reference downloads ViT-B/32 with clip.load (genima_act.py:315-321), "

@@ -1,6 +1,8 @@
 // Handle lifecycle, error reporting and TMA descriptor construction for libgenima_b200.so.
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.h"
 
 namespace gn {
@@ -207,6 +209,54 @@ int gn_set_autotune(gn_handle* h, int enable) {
   if (!h) return GN_ERR_INVALID;
   h->autotune = enable != 0;
   if (enable < 0) h->tune_cache.clear();
+  return GN_OK;
+}
+
+// Measured tile configurations as text, one "key=block_n,splits,stages,packed" line per problem shape: lets rank 0 tune
+// once and every other rank / handle import the same choices, so that all ranks sum in the same order (sharding an
+// evaluation must not change an episode's result).  Returns the number of bytes the export needs (call with cap = 0
+// to size the buffer); negative on error.
+int64_t gn_tune_cache_export(const gn_handle* h, char* buf, int64_t cap) {
+  if (!h) return GN_ERR_INVALID;
+  std::vector<std::string> lines;
+  lines.reserve(h->tune_cache.size());
+  for (const auto& kv : h->tune_cache) {
+    char tmp[192];
+    snprintf(tmp, sizeof(tmp), "%s=%d,%d,%d,%d\n", kv.first.c_str(), kv.second[0], kv.second[1], kv.second[2],
+             kv.second[3]);
+    lines.emplace_back(tmp);
+  }
+  std::sort(lines.begin(), lines.end());
+  int64_t need = 0;
+  for (const auto& l : lines) need += (int64_t)l.size();
+  if (buf && cap >= need) {
+    char* p = buf;
+    for (const auto& l : lines) {
+      memcpy(p, l.data(), l.size());
+      p += l.size();
+    }
+  }
+  return need;
+}
+
+int gn_tune_cache_import(gn_handle* h, const char* buf, int64_t n, int replace) {
+  if (!h || (!buf && n > 0) || n < 0) return GN_ERR_INVALID;
+  if (replace) h->tune_cache.clear();
+  const char* p = buf;
+  const char* end = buf + n;
+  while (p < end) {
+    const char* nl = static_cast<const char*>(memchr(p, '\n', end - p));
+    const char* le = nl ? nl : end;
+    const char* eq = static_cast<const char*>(memchr(p, '=', le - p));
+    if (eq) {
+      int v[4];
+      std::string val(eq + 1, le);
+      if (sscanf(val.c_str(), "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) != 4)
+        return gn::set_error(h, GN_ERR_INVALID, "gn_tune_cache_import: malformed line");
+      h->tune_cache[std::string(p, eq)] = {v[0], v[1], v[2], v[3]};
+    }
+    p = le + 1;
+  }
   return GN_OK;
 }
 

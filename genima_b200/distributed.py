@@ -30,20 +30,40 @@ def arena_layout(shapes_by_model: "OrderedDict[str, OrderedDict[str, Tuple[int, 
     return index, off
 
 
-def broadcast_weights(shapes_by_model, state_dicts=None, src: int = 0, device="cpu"):
+def broadcast_weights(shapes_by_model, state_dicts=None, src: int = 0, device="cpu", timings: dict = None):
     """Rank `src` packs its fp16 state dicts into one flat arena; one broadcast; every rank returns state dicts whose
-    tensors are views into its copy of the arena (so the device graphs bind them without another copy)."""
+    tensors are views into its copy of the arena (so the device graphs bind them without another copy).
+    `timings` (optional dict) receives pack_s (host state dicts -> device arena on the source rank) and broadcast_s (the
+    collective alone, synchronised on both sides; the communicator must already be warm for this to be a bandwidth
+    figure)."""
+    import time
+
     index, total = arena_layout(shapes_by_model)
     arena = torch.empty(total, dtype=torch.float16, device=device)
     rank = dist.get_rank() if _is_dist() else 0
+    is_cuda = torch.device(device).type == "cuda"
+    t0 = time.perf_counter()
     if rank == src:
         if state_dicts is None:
             raise ValueError("the source rank must supply the state dicts")
         for (model, key), (off, shp) in index.items():
             t = state_dicts[model][key]
             arena[off:off + t.numel()].copy_(t.reshape(-1).to(torch.float16))
+    if is_cuda:
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
     if _is_dist() and dist.get_world_size() > 1:
+        dist.barrier()
+        if is_cuda:
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
         dist.broadcast(arena, src=src)
+        if is_cuda:
+            torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    if timings is not None:
+        timings["pack_s"] = t1 - t0 if rank == src else 0.0
+        timings["broadcast_s"] = (t2 - t1) if (_is_dist() and dist.get_world_size() > 1) else 0.0
     out = OrderedDict((m, OrderedDict()) for m in shapes_by_model)
     for (model, key), (off, shp) in index.items():
         n = 1
@@ -51,6 +71,21 @@ def broadcast_weights(shapes_by_model, state_dicts=None, src: int = 0, device="c
             n *= v
         out[model][key] = arena[off:off + n].view(shp)
     return out, arena
+
+
+def sync_tune_caches(ops_list, src: int = 0) -> int:
+    """Rank `src` has measured its GEMM tile configurations (gn_set_autotune); every other rank adopts them
+    (gn_tune_cache_export / gn_tune_cache_import) instead of timing its own, so that all ranks launch identical tile and
+    split-K configurations and every episode gives bit-identical results wherever it is sharded.  `ops_list`: the Ops
+    handles in the same order on every rank.  Returns the number of bytes exchanged."""
+    if not _is_dist() or dist.get_world_size() == 1:
+        return 0
+    payload = [[o.tune_cache_export() for o in ops_list] if dist.get_rank() == src else None]
+    dist.broadcast_object_list(payload, src=src)
+    if dist.get_rank() != src:
+        for o, blob in zip(ops_list, payload[0]):
+            o.tune_cache_import(blob, replace=True)
+    return sum(len(b) for b in payload[0])
 
 
 def shard_units(tasks: Sequence[str], episodes_per_task: int, rank: int, world: int) -> List[Tuple[str, int]]:

@@ -90,6 +90,7 @@ class Ops:
                           "gn_set_workspace")
         # tile configurations are measured once per problem shape (first eager call) and cached in the handle
         self.handle.check(self.lib.gn_set_autotune(self.h, 1 if autotune else 0), "gn_set_autotune")
+        self.autotune = bool(autotune)
         if os.environ.get("GENIMA_B200_PDL", "1") != "1":   # A/B: 0 = ordinary launches, 2 = PDL without weight prefetch
             self.handle.check(self.lib.gn_set_pdl(self.h, int(os.environ["GENIMA_B200_PDL"])), "gn_set_pdl")
         if os.environ.get("GENIMA_B200_STAGED", "1") == "0":   # A/B switch for the TMA-stored GEMM epilogue
@@ -203,6 +204,25 @@ class Ops:
 
     def set_gemm_tuning(self, block_n: int = 0, splits: int = 0) -> None:
         self.handle.check(self.lib.gn_set_gemm_tuning(self.h, block_n, splits), "gn_set_gemm_tuning")
+
+    def set_autotune(self, enable: bool) -> None:
+        self.handle.check(self.lib.gn_set_autotune(self.h, 1 if enable else 0), "gn_set_autotune")
+        self.autotune = bool(enable)
+
+    def tune_cache_export(self) -> bytes:
+        """Measured tile configurations of this handle as text (gn_tune_cache_export)."""
+        n = int(self.lib.gn_tune_cache_export(self.h, None, 0))
+        if n < 0:
+            self.handle.check(n, "gn_tune_cache_export")
+        buf = C.create_string_buffer(max(n, 1))
+        self.lib.gn_tune_cache_export(self.h, buf, n)
+        return buf.raw[:n]
+
+    def tune_cache_import(self, text: bytes, replace: bool = False) -> None:
+        """Adopt tile configurations measured elsewhere (another handle / rank 0): identical launches, identical
+        summation order, bit-identical results."""
+        self.handle.check(self.lib.gn_tune_cache_import(self.h, text, len(text), 1 if replace else 0),
+                          "gn_tune_cache_import")
 
     def last_gemm_config(self) -> Tuple[int, int, int, int]:
         out = (C.c_int32 * 4)()

@@ -89,10 +89,10 @@ class B200ControlNetPipeline:
         # on two streams (both are chains of small latency-bound kernels at batch 1).  The ControlNet gets its own
         # gn_handle so that the per-handle GroupNorm scratch / grid-barrier words are never shared between streams.
         self.concurrent_controlnet = bool(concurrent_controlnet)
-        self.ops_side = Ops(ops.device.index) if self.concurrent_controlnet else ops
+        self.ops_side = Ops(ops.device.index, autotune=ops.autotune) if self.concurrent_controlnet else ops
         # third handle / stream: the 13 zero-convs start as soon as both encoders have produced their skip tensor,
         # instead of running one after the other once the two encoders have joined
-        self.ops_zero = Ops(ops.device.index) if self.concurrent_controlnet else ops
+        self.ops_zero = Ops(ops.device.index, autotune=ops.autotune) if self.concurrent_controlnet else ops
         self.zero_stream = torch.cuda.Stream(device=ops.device) if self.concurrent_controlnet else None
         self.overlap_zero_convs = os.environ.get("GENIMA_B200_ZERO_OVERLAP", "1") != "0"
         self.side_stream = (torch.cuda.Stream(device=ops.device, priority=int(os.environ.get("GENIMA_B200_SIDE_PRIO", "0")))
@@ -128,6 +128,14 @@ class B200ControlNetPipeline:
 
     def all_ops(self):
         return [self.ops] if self.ops_side is self.ops else [self.ops, self.ops_side, self.ops_zero]
+
+    def tune_cache_export(self) -> List[bytes]:
+        """Measured GEMM tile configurations of this pipeline's handles (see genima_b200.distributed.sync_tune_caches)."""
+        return [o.tune_cache_export() for o in self.all_ops()]
+
+    def tune_cache_import(self, blobs: Sequence[bytes]) -> None:
+        for o, b in zip(self.all_ops(), blobs):
+            o.tune_cache_import(b, replace=True)
 
     # ------------------------------------------------------------------ diffusers API surface used by the reference
     def to(self, *args, **kwargs):

@@ -117,6 +117,13 @@ int gn_set_gn_max_ctas(gn_handle* h, int max_ctas);
  * fastest; later calls, and calls made while the stream is being captured into a CUDA graph, use the cache.
  * enable = 0 keeps the pure model; enable = -1 also clears the cache. */
 int gn_set_autotune(gn_handle* h, int enable);
+/* The measured tile configurations as text ("key=block_n,splits,stages,packed" lines, sorted).  Export returns the number
+ * of bytes needed (nothing is written unless cap is large enough; call with buf = NULL to size the buffer).  Import adds
+ * the lines to the handle's cache (replace != 0: clears it first).  Rank 0 of a multi-GPU evaluation tunes once and
+ * broadcasts the text with the weights, so every rank launches the same tile / split-K configurations and therefore sums
+ * in the same order: sharding the episodes of controller/eval_genima.py:115-142 over GPUs does not change any result. */
+int64_t gn_tune_cache_export(const gn_handle* h, char* buf, int64_t cap);
+int gn_tune_cache_import(gn_handle* h, const char* buf, int64_t n, int replace);
 /* W-tile TMA multicast: the CTAs computing the m-tiles of one n-tile form clusters of up to max_cluster (1, 2 or 4) CTAs
  * that fetch one slice of the weight tile each and multicast it to the others (less L2 traffic on shapes where many
  * m-tiles re-read the same weights).  force_cluster = 2 / 4 uses that size wherever it applies (tests, A/B); 0 = autotuned. */

@@ -33,6 +33,21 @@ def _worker(rank, world, port, q):
         ok = ok and all(t.data_ptr() % 16 == 0 for t in got["act"].values())        # TMA-aligned views of ONE arena
         units = gd.shard_units(["open_box", "close_box", "push_button"], 5, rank, world)
         recs = gd.gather_records([{"task": t, "episode": e, "rank": rank} for t, e in units])
+        # tile configurations measured on rank 0 are adopted by every other rank (bit-identical sharded results)
+        class FakeOps:
+            def __init__(self, blob):
+                self.blob = blob
+
+            def tune_cache_export(self):
+                return self.blob
+
+            def tune_cache_import(self, blob, replace=False):
+                assert replace
+                self.blob = blob
+
+        fake = [FakeOps(b"1:32:320:45=160,1,5,256\n" if rank == 0 else b"other\n"), FakeOps(b"" if rank == 0 else b"x")]
+        nbytes = gd.sync_tune_caches(fake, src=0)
+        ok = ok and nbytes == 24 and fake[0].blob == b"1:32:320:45=160,1,5,256\n" and fake[1].blob == b""
         mx = gd.reduce_max(10.0 + rank)
         sm = gd.reduce_sum(float(len(units)))
         q.put((rank, ok, len(units), sorted((r["task"], r["episode"]) for r in recs), mx, sm))

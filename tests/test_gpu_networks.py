@@ -18,8 +18,8 @@ from genima_b200.configs import ACTConfig, CLIPTextConfig, UNetConfig, VAEConfig
 
 pytestmark = pytest.mark.gpu
 
-NET_TOL = 4e-3        # one network pass (U-Net, ControlNet, VAE, CLIP, ACT)
-LOOP_TOL = 1e-2       # multi-step denoise loop + VAE decode
+NET_TOL = 2.5e-3      # one network pass (U-Net, ControlNet, VAE, CLIP, ACT): measured 1.0e-3 .. 1.8e-3
+LOOP_TOL = 4e-3       # multi-step denoise loop + VAE decode: measured 0.7e-3 .. 2.3e-3
 
 
 def rel_err(out, ref):
