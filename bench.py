@@ -285,39 +285,18 @@ def gpu_baseline_leg(args):
     return res
 
 
-def run_ours(args):
-    import torch.distributed as dist
+def build_world(args, rank: int = 0, local: int = 0):
+    """Weights (rank 0 synthesises, one arena broadcast), the pipeline, the hydra-style controller, the fused step and
+    the inputs of the workload: everything run_ours and the tools/ scripts share."""
+    from types import SimpleNamespace
 
     from genima_b200 import distributed as gd
-    from genima_b200.agents import B200ControlNetAgent, B200GenimaACT
-    from genima_b200.host_glue import tile_images, untile_images
+    from genima_b200.agents import B200GenimaACT
     from genima_b200.ops import Ops
     from genima_b200.pipeline import B200ControlNetPipeline
     from genima_b200.step import GenimaStep
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (own arm) needs a B200: genima_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    comm_init_s = 0.0
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL's own INIT lines (communicator size, transports) are left visible: they prove how many ranks joined.
-        # They go to stdout BEFORE the JSON line, which is always the LAST line this program prints.
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        t_c = time.perf_counter()
-        dist.init_process_group("nccl", device_id=dev)
-        warm = torch.ones(1, device=dev)
-        dist.all_reduce(warm)                       # communicator bring-up (rings / NVLS set-up) happens here, once
-        torch.cuda.synchronize()
-        comm_init_s = time.perf_counter() - t_c
-    if world != args.gpus and rank == 0:
-        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
-
     ucfg, vcfg, acfg = presets(args.preset, args.autoencoder)
     tiny = args.preset == "tiny"
     tcfg = CLIPTextConfig.tiny() if tiny else CLIPTextConfig.sd_turbo()
@@ -358,6 +337,111 @@ def run_ours(args):
     d_task = controller.encode_clip_text(torch.from_numpy(lang_np).to(dev))[0]           # CLIP text tower: once per episode
     d_views = views.permute(0, 2, 3, 1).contiguous()[None].to(dev)          # [1, 4, S, S, 3] u8
     d_lat, d_qpos = lat.to(dev), qpos.to(dev)
+
+    return SimpleNamespace(**{k: v for k, v in locals().items() if k not in ("args", "SimpleNamespace")})
+
+
+def make_e2e_step(pipe, ops, controller, views, qpos, prompts, negative_prompts, lang_np, acfg, denoise_steps, dev, local,
+                  tick=None):
+    """-> (e2e_step, bytes): `e2e_step()` is one iteration of the reference loop body (controller/eval_genima.py:163-249)
+    on host buffers; `bytes` = dict(h2d=, d2h=) filled by the first call.  tick(name, t0): optional phase timer hook."""
+    from PIL import Image
+
+    from genima_b200.agents import B200ControlNetAgent
+    from genima_b200.host_glue import tile_images, untile_images
+
+    S = acfg.image_size
+    cameras = ["wrist", "front", "right_shoulder", "left_shoulder"]
+    agent = B200ControlNetAgent.__new__(B200ControlNetAgent)       # bind the already-built pipeline (no second copy)
+    agent.eval_cfg = dict(image_resolution=2 * S, device=f"cuda:{local}")
+    agent.pipe, agent._ops = pipe, ops
+    agent.set_optimizations()
+    agent.common_setup()
+    obs_np = {f"{c}_rgb": views[i:i + 1].numpy() for i, c in enumerate(cameras)}             # [T=1, 3, S, S] u8
+    low_dim = qpos.numpy()                                                                   # [T=1, 8]
+    gen = [torch.Generator(device=dev).manual_seed(2)]                                       # eval_genima.py:129-135
+    nbytes = {"h2d": 0, "d2h": 0}
+    tick = tick or (lambda name, t0: None)
+
+    def e2e_step():
+        t0 = time.perf_counter()
+        # eval_genima.py:163-186: env observation (uint8 CHW numpy) -> PIL -> tile
+        rgbs = [Image.fromarray(np.transpose(obs_np[f"{c}_rgb"][0], (1, 2, 0))) for c in cameras]
+        tiles = tile_images(rgbs, 1) if S == 256 else [Image.fromarray(
+            np.concatenate([np.concatenate([np.asarray(rgbs[0]), np.asarray(rgbs[1])], 1),
+                            np.concatenate([np.asarray(rgbs[2]), np.asarray(rgbs[3])], 1)], 0))]
+        tick("obs -> PIL -> tile_images", t0)
+        t0 = time.perf_counter()
+        # :199-210 (string prompts -> tokenizer -> prompt cache; CUDA generator shared across the batch)
+        target = agent.infer(images=tiles, prompts=prompts, negative_prompts=negative_prompts,
+                             num_inference_steps=denoise_steps, guidance_scale=0.0, generator=gen * len(tiles))
+        tick("diffusion_agent.infer (incl. GPU)", t0)
+        t0 = time.perf_counter()
+        # :224-234
+        if S == 256:
+            un = untile_images(target[0], cameras, agent.transform_to_half_resolution)
+        else:
+            g = np.asarray(target[0][0])
+            quads = [g[:S, :S], g[:S, S:], g[S:, :S], g[S:, S:]]
+            un = {c: np.ascontiguousarray(np.transpose(q, (2, 0, 1))[None]) for c, q in zip(cameras, quads)}
+        obs = {f"{c}_rgb": un[c] for c in cameras}
+        obs["low_dim_state"] = low_dim
+        obs["lang_tokens"] = lang_np[0]
+        tick("untile_images", t0)
+        t0 = time.perf_counter()
+        # :237-249
+        obs = {k: torch.from_numpy(v).to(dev).unsqueeze(0) for k, v in obs.items()}
+        tick("obs -> device", t0)
+        t0 = time.perf_counter()
+        actions = controller.act(obs, step=0, eval_mode=True)[0]
+        actions = actions.detach().cpu().numpy()
+        tick("controller_agent.act (incl. GPU)", t0)
+        nbytes["h2d"] = (tiles[0].size[0] * tiles[0].size[1] * 3 + sum(v.nbytes for v in un.values()) + low_dim.nbytes
+                         + lang_np[0].nbytes)
+        nbytes["d2h"] = tiles[0].size[0] * tiles[0].size[1] * 3 + actions.nbytes + lang_np[0].nbytes  # (ids read back: cache key)
+        return actions
+
+    return e2e_step, nbytes
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from genima_b200 import distributed as gd
+    from genima_b200.agents import B200GenimaACT
+    from genima_b200.ops import Ops
+    from genima_b200.pipeline import B200ControlNetPipeline
+    from genima_b200.step import GenimaStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (own arm) needs a B200: genima_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm_init_s = 0.0
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL's own INIT lines (communicator size, transports) are left visible: they prove how many ranks joined.
+        # They go to stdout BEFORE the JSON line, which is always the LAST line this program prints.
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        t_c = time.perf_counter()
+        dist.init_process_group("nccl", device_id=dev)
+        warm = torch.ones(1, device=dev)
+        dist.all_reduce(warm)                       # communicator bring-up (rings / NVLS set-up) happens here, once
+        torch.cuda.synchronize()
+        comm_init_s = time.perf_counter() - t_c
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+
+    w = build_world(args, rank, local)
+    ucfg, vcfg, acfg, sds, arena, ops, pipe, controller, act, step = (w.ucfg, w.vcfg, w.acfg, w.sds, w.arena, w.ops,
+                                                                      w.pipe, w.controller, w.act, w.step)
+    views, qpos, lat, prompts, negative_prompts, lang_np = w.views, w.qpos, w.lat, w.prompts, w.negative_prompts, w.lang_np
+    d_ctx, d_task, d_views, d_lat, d_qpos, synth_s, timings = (w.d_ctx, w.d_task, w.d_views, w.d_lat, w.d_qpos, w.synth_s,
+                                                                w.timings)
 
     def barrier():
         if world > 1:
@@ -439,47 +523,9 @@ def run_ours(args):
         out = step(d_views, d_lat, d_qpos, d_task, prompt_embeds=d_ctx)   # back to the batch-1 graph / buffers
 
     # ---- e2e through the reference-facing API with host buffers: the loop body of controller/eval_genima.py:163-249
-    from PIL import Image
-
-    agent = B200ControlNetAgent.__new__(B200ControlNetAgent)       # bind the already-built pipeline (no second copy)
-    agent.eval_cfg = dict(image_resolution=2 * S, device=f"cuda:{local}")
-    agent.pipe, agent._ops = pipe, ops
-    agent.set_optimizations()
-    agent.common_setup()
-    obs_np = {f"{c}_rgb": views[i:i + 1].numpy() for i, c in enumerate(cameras)}             # [T=1, 3, S, S] u8
-    low_dim = qpos.numpy()                                                                   # [T=1, 8]
-    gen = [torch.Generator(device=dev).manual_seed(2)]                                       # eval_genima.py:129-135
+    e2e_step, e2e_bytes = make_e2e_step(pipe, ops, controller, views, qpos, prompts, negative_prompts, lang_np, acfg,
+                                        args.denoise_steps, dev, local)
     n_e2e = max(3, min(args.steps, args.e2e_steps))
-    h2d = d2h = 0
-
-    def e2e_step():
-        nonlocal h2d, d2h
-        # eval_genima.py:163-186: env observation (uint8 CHW numpy) -> PIL -> tile
-        rgbs = [Image.fromarray(np.transpose(obs_np[f"{c}_rgb"][0], (1, 2, 0))) for c in cameras]
-        tiles = tile_images(rgbs, 1) if S == 256 else [Image.fromarray(
-            np.concatenate([np.concatenate([np.asarray(rgbs[0]), np.asarray(rgbs[1])], 1),
-                            np.concatenate([np.asarray(rgbs[2]), np.asarray(rgbs[3])], 1)], 0))]
-        # :199-210 (string prompts -> tokenizer -> prompt cache; CUDA generator shared across the batch)
-        target = agent.infer(images=tiles, prompts=prompts, negative_prompts=negative_prompts,
-                             num_inference_steps=args.denoise_steps, guidance_scale=0.0, generator=gen * len(tiles))
-        # :224-234
-        if S == 256:
-            un = untile_images(target[0], cameras, agent.transform_to_half_resolution)
-        else:
-            g = np.asarray(target[0][0])
-            quads = [g[:S, :S], g[:S, S:], g[S:, :S], g[S:, S:]]
-            un = {c: np.ascontiguousarray(np.transpose(q, (2, 0, 1))[None]) for c, q in zip(cameras, quads)}
-        obs = {f"{c}_rgb": un[c] for c in cameras}
-        obs["low_dim_state"] = low_dim
-        obs["lang_tokens"] = lang_np[0]
-        # :237-249
-        obs = {k: torch.from_numpy(v).to(dev).unsqueeze(0) for k, v in obs.items()}
-        actions = controller.act(obs, step=0, eval_mode=True)[0]
-        actions = actions.detach().cpu().numpy()
-        h2d = (tiles[0].size[0] * tiles[0].size[1] * 3 + sum(v.nbytes for v in un.values()) + low_dim.nbytes
-               + lang_np[0].nbytes)
-        d2h = tiles[0].size[0] * tiles[0].size[1] * 3 + actions.nbytes + lang_np[0].nbytes   # (token ids read back: cache key)
-        return actions
 
     with torch.inference_mode():                                                             # eval_genima.py:199
         for _ in range(3):
@@ -553,7 +599,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16", "data": "synthetic", "config": workload_config(args, ucfg),
             "unet_ms_per_step": unet_ms, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_bytes["h2d"]), "d2h_bytes_per_step": int(e2e_bytes["d2h"]),
                     "steps": n_e2e, "ms_per_step": e2e_ms / n_e2e,
                     "api": "the loop body of controller/eval_genima.py:163-249: uint8 CHW observations -> PIL -> tile_images "
                            "-> B200ControlNetAgent.infer(string prompts through a stub tokenizer + prompt cache, CUDA "

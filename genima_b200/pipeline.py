@@ -95,6 +95,8 @@ class B200ControlNetPipeline:
         self.ops_zero = Ops(ops.device.index, autotune=ops.autotune) if self.concurrent_controlnet else ops
         self.zero_stream = torch.cuda.Stream(device=ops.device) if self.concurrent_controlnet else None
         self.overlap_zero_convs = os.environ.get("GENIMA_B200_ZERO_OVERLAP", "1") != "0"
+        # scheduler step + input scaling fused into conv_out / conv_in epilogues (A/B: GENIMA_B200_FUSE_SCHED=0)
+        self.fuse_scheduler = os.environ.get("GENIMA_B200_FUSE_SCHED", "1") != "0"
         self.side_stream = (torch.cuda.Stream(device=ops.device, priority=int(os.environ.get("GENIMA_B200_SIDE_PRIO", "0")))
                             if self.concurrent_controlnet else None)
         self.unet_impl = DeviceUNet(ops, unet_sd, unet_cfg)
@@ -232,6 +234,11 @@ class B200ControlNetPipeline:
                 sc = self.controlnet_impl.time_embedding(float(t), self._added)
                 per_step.append((self.unet_impl.temb_rows(self.unet_impl.resblocks(), su, batch),
                                  self.controlnet_impl.temb_rows(self.controlnet_impl.resblocks(), sc, batch)))
+            # scheduler.scale_model_input folded into the two conv_in epilogues: one constant fp32 vector per step
+            _, sig = self.schedule.set_timesteps(n_steps)
+            c0 = self.unet_cfg.block_out_channels[0]
+            per_step = [(tu, tc, torch.full((c0,), 1.0 / float(np.sqrt(float(sig[i]) ** 2 + 1.0)), dtype=torch.float32,
+                                            device=self.ops.device)) for i, (tu, tc) in enumerate(per_step)]
             self._temb_cache[key] = per_step
         return self._temb_cache[key]
 
@@ -323,8 +330,14 @@ class B200ControlNetPipeline:
         cond = ops.u8_to_nhwc(cond_u8, cpad=64)
         cond_emb = self.controlnet_impl.cond_embedding(cond)
         x = ops.scale(lat_in, self.schedule.init_noise_sigma)                       # latents * init_noise_sigma
-        xs = ops.scale(x, 1.0 / float(np.sqrt(float(sig[0]) ** 2 + 1.0)))           # scale_model_input, step 0
-        eps = torch.zeros_like(x)
+        # Euler / DDIM: the whole scheduler lives in epilogues -- scale_model_input in the two conv_in's (per-step scale
+        # vector), the update x' = a x + b eps in the U-Net's conv_out (alpha / beta of its residual add); the ancestral
+        # variant re-injects noise and keeps its own kernel
+        fused = self.fuse_scheduler and not self.schedule.ancestral and self.unet_impl.w_out8 is not None
+        xs = eps = None
+        if not fused:
+            xs = ops.scale(x, 1.0 / float(np.sqrt(float(sig[0]) ** 2 + 1.0)))       # scale_model_input, step 0
+            eps = torch.zeros_like(x)
         half_sms = max(1, ops.num_sms() // 2)
         # the first eager pass for a new shape runs the two encoders one after the other: that is when the GEMM tile
         # configurations are measured (gn_set_autotune), and a concurrent neighbour would disturb the timings
@@ -338,7 +351,17 @@ class B200ControlNetPipeline:
         for o in self.all_ops():
             o.set_gn_max_ctas(half_sms)
         for i in range(n_steps):
-            tu, tc = temb[i]
+            tu, tc, svec = temb[i]
+            if fused:
+                xs = x                                   # conv_in reads the unscaled sample, its epilogue scales
+                if self.schedule.ddim:
+                    svec, (sa, sb) = None, self.schedule.ddim_coeffs(i)
+                else:
+                    sa, sb = 1.0, float(sig[i + 1]) - float(sig[i])
+                eps = torch.empty_like(x)                # receives x' directly
+                sched = (x, sa, sb)
+            else:
+                svec, sched = None, None
             if concurrent and self.overlap_zero_convs:
                 main = torch.cuda.current_stream()
                 n_ev = len(self.controlnet_impl.zero_w) + 1
@@ -348,8 +371,9 @@ class B200ControlNetPipeline:
                 self.zero_stream.wait_stream(main)
                 with torch.cuda.stream(self.side_stream):
                     cn_mid, cn_skips = self.controlnet_impl.encode(
-                        xs, cond_emb, tc, kv_c, tk, on_skip=lambda j: ev_c[j].record(self.side_stream))
-                mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk, on_skip=lambda j: ev_u[j].record(main))
+                        xs, cond_emb, tc, kv_c, tk, on_skip=lambda j: ev_c[j].record(self.side_stream), in_scale=svec)
+                mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk, on_skip=lambda j: ev_u[j].record(main),
+                                                   in_scale=svec)
                 with torch.cuda.stream(self.zero_stream):
                     outs = []
                     for j in range(n_ev):
@@ -361,31 +385,34 @@ class B200ControlNetPipeline:
                 main.wait_stream(self.zero_stream)
                 skips, mid = outs[:-1], outs[-1]
                 del cn_mid, cn_skips, outs
-                self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps)
-                x, xs = self._scheduler_step(x, eps, i, noise)
+                self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps, step=sched)
+                x, xs = (eps, None) if fused else self._scheduler_step(x, eps, i, noise)
                 continue
             if concurrent:
                 main = torch.cuda.current_stream()
                 self.side_stream.wait_stream(main)
                 with torch.cuda.stream(self.side_stream):
-                    cn_mid, cn_skips = self.controlnet_impl.encode(xs, cond_emb, tc, kv_c, tk)
-                mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk)
+                    cn_mid, cn_skips = self.controlnet_impl.encode(xs, cond_emb, tc, kv_c, tk, in_scale=svec)
+                mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk, in_scale=svec)
                 main.wait_stream(self.side_stream)
             else:
-                mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk)
-                cn_mid, cn_skips = self.controlnet_impl.encode(xs, cond_emb, tc, kv_c, tk)
+                mid, skips = self.unet_impl.encode(xs, tu, kv_u, tk, in_scale=svec)
+                cn_mid, cn_skips = self.controlnet_impl.encode(xs, cond_emb, tc, kv_c, tk, in_scale=svec)
             # (same handle as the overlapped path, so that its tile configurations are the ones measured here)
             skips, mid = self.controlnet_impl.zero_convs(cn_mid, cn_skips, skips, mid, cond_scale,
                                                          ops=self.ops_zero if self.overlap_zero_convs else None)
             del cn_mid, cn_skips
-            self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps)
-            x, xs = self._scheduler_step(x, eps, i, noise)
+            self.unet_impl.decode(mid, skips, tu, kv_u, tk, eps, step=sched)
+            x, xs = (eps, None) if fused else self._scheduler_step(x, eps, i, noise)
         for o in self.all_ops():
             o.set_gn_max_ctas(0)
         img = None
         if want_image:
-            z = ops.scale(x, 1.0 / self.vae_cfg.scaling_factor)
-            img = self.vae_impl.decode(z)
+            if isinstance(self.vae_impl, DeviceVAEDecoder):
+                # `latents / scaling_factor` rides in post_quant_conv's epilogue
+                img = self.vae_impl.decode(x, in_scale=1.0 / self.vae_cfg.scaling_factor)
+            else:
+                img = self.vae_impl.decode(ops.scale(x, 1.0 / self.vae_cfg.scaling_factor))
         return x, img
 
     def _run(self, cond_u8, lat_in, kv, tk, n_steps, want_image, cond_scale, noise=None):
@@ -711,6 +738,7 @@ class B200Pix2PixPipeline(B200ControlNetPipeline):
         self.ops_side = self.ops_zero = ops
         self.side_stream = self.zero_stream = None
         self.overlap_zero_convs = False
+        self.fuse_scheduler = False          # the image latents ride in channels 4..7 of the scaled input: not foldable
         self.unet_impl = DeviceUNet(ops, unet_sd, unet_cfg)
         self.controlnet_impl = None
         self.vae_impl = DeviceVAEDecoder(ops, vae_sd, vae_cfg)

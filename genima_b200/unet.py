@@ -335,6 +335,16 @@ class DeviceUNet(_Encoder):
             self.up.append((res, att, us))
         self.out_g, self.out_b = P.f32("conv_norm_out.weight"), P.f32("conv_norm_out.bias")
         self.conv_out = _Conv(P, "conv_out")
+        # conv_out with its rows zero-padded to the 8-channel latent pixel: the scheduler step is fused into its epilogue
+        # (x' = a * x + b * (conv + bias) written straight into the next latent tensor, padding channels stay 0)
+        co = self.conv_out
+        if co.cout <= LATENT_CPAD:
+            self.w_out8 = torch.zeros(LATENT_CPAD, co.w.shape[1], dtype=torch.float16, device=P.device)
+            self.w_out8[:co.cout] = co.w
+            self.b_out8 = torch.zeros(LATENT_CPAD, dtype=torch.float32, device=P.device)
+            self.b_out8[:co.cout] = co.b
+        else:
+            self.w_out8 = None
 
     def resblocks(self) -> List[_ResBlock]:
         out = super().resblocks()
@@ -348,12 +358,17 @@ class DeviceUNet(_Encoder):
             out += [a for a in att if a is not None]
         return out
 
-    def encode(self, x: torch.Tensor, temb, kv, tk, on_skip=None):
-        h = self.conv_in(self.ops, x)
+    def encode(self, x: torch.Tensor, temb, kv, tk, on_skip=None, in_scale: Optional[torch.Tensor] = None):
+        """in_scale: fp32 [C0] vector s (all entries equal): the scheduler's scale_model_input folded into conv_in's
+        epilogue, conv_in(s * x) + b == s * conv(x) + b, so `x` is the UNSCALED sample."""
+        h = self.conv_in(self.ops, x, scale=in_scale) if in_scale is not None else self.conv_in(self.ops, x)
         return self.run(h, temb, kv, tk, on_skip)
 
-    def decode(self, h: torch.Tensor, skips: List[torch.Tensor], temb, kv, tk, eps_out: torch.Tensor) -> torch.Tensor:
-        """`skips` / `h` already include the ControlNet residuals.  Writes eps into eps_out [B, H, W, 8] (4 valid)."""
+    def decode(self, h: torch.Tensor, skips: List[torch.Tensor], temb, kv, tk, eps_out: torch.Tensor,
+               step: Optional[Tuple[torch.Tensor, float, float]] = None) -> torch.Tensor:
+        """`skips` / `h` already include the ControlNet residuals.  Writes eps into eps_out [B, H, W, 8] (4 valid).
+        step = (x, a, b): the scheduler update is fused into conv_out's epilogue instead -- eps_out receives
+        x' = a * x + b * eps (Euler: a = 1, b = sigma_next - sigma; DDIM: its (a, b)), eps itself is never stored."""
         ops = self.ops
         skips = list(skips)
         for res, att, us in self.up:
@@ -364,6 +379,13 @@ class DeviceUNet(_Encoder):
             if us is not None:
                 h = us.upsampled(ops, h)
         n = ops.group_norm(h, self.out_g, self.out_b, self.cfg.norm_num_groups, self.cfg.norm_eps, silu=True)
+        if step is not None:
+            x, a, b = step
+            if self.w_out8 is None:
+                raise ValueError("fused scheduler step needs out_channels <= 8")
+            co = self.conv_out
+            return ops.conv2d(n, self.w_out8, LATENT_CPAD, ksize=co.k, stride=1, pad=co.pad, bias=self.b_out8,
+                              residual=x, alpha=float(b), beta=float(a), out=eps_out)
         return self.conv_out(ops, n, out=eps_out)
 
 
@@ -394,10 +416,13 @@ class DeviceControlNet(_Encoder):
             e = conv(ops, e, act_pre="silu")
         return self.ce_out(ops, e)
 
-    def encode(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk, on_skip=None):
+    def encode(self, x: torch.Tensor, cond_emb: torch.Tensor, temb, kv, tk, on_skip=None,
+               in_scale: Optional[torch.Tensor] = None):
         """conv_in(x) + cond_emb -> encoder copy -> (mid, [S0..S11]) BEFORE the zero-convs.  Independent of the U-Net's own
-        encoder, so the pipeline runs it on a second stream concurrently with DeviceUNet.encode."""
-        h = self.conv_in(self.ops, x, residual=cond_emb)
+        encoder, so the pipeline runs it on a second stream concurrently with DeviceUNet.encode.  in_scale: see
+        DeviceUNet.encode."""
+        epi = dict(scale=in_scale) if in_scale is not None else {}
+        h = self.conv_in(self.ops, x, residual=cond_emb, **epi)
         return self.run(h, temb, kv, tk, on_skip)
 
     def zero_conv(self, i: int, s: torch.Tensor, us: torch.Tensor, conditioning_scale: float = 1.0,

@@ -88,12 +88,19 @@ class DeviceVAEDecoder:
     def _mid_attention(self, h: torch.Tensor) -> torch.Tensor:
         return self.mid_attn(self.ops, h)
 
-    def decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """z: [B, h, w, 8] fp16 latents already divided by scaling_factor -> [B, 8h, 8w, 8] fp16 (RGB in 0..2)."""
+    def decode(self, z: torch.Tensor, out: Optional[torch.Tensor] = None, in_scale: float = 1.0) -> torch.Tensor:
+        """z: [B, h, w, 8] fp16 latents -> [B, 8h, 8w, 8] fp16 (RGB in 0..2).  in_scale: `latents / scaling_factor` of
+        the pipeline folded into post_quant_conv's epilogue (W (s z) + b == s (W z) + b); 1.0 = z is already divided."""
         ops = self.ops
         B, hh, ww, _ = z.shape
         zq = torch.zeros_like(z)
-        ops.linear(z.reshape(-1, LATENT_CPAD), self.pq_w, bias=self.pq_b, out=zq.reshape(-1, LATENT_CPAD))
+        sc = None
+        if in_scale != 1.0:
+            if getattr(self, "_pq_scale_val", None) != in_scale:
+                self._pq_scale = torch.full((self.pq_w.shape[0],), float(in_scale), dtype=torch.float32, device=z.device)
+                self._pq_scale_val = in_scale
+            sc = self._pq_scale
+        ops.linear(z.reshape(-1, LATENT_CPAD), self.pq_w, bias=self.pq_b, scale=sc, out=zq.reshape(-1, LATENT_CPAD))
         h = self.conv_in(ops, zq)
         h = self.mid0(ops, h, None, None)
         h = self._mid_attention(h)

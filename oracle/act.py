@@ -19,10 +19,23 @@ from typing import Dict
 import torch
 import torch.nn.functional as F
 
-from genima_b200.configs import ACTConfig
+ACTConfig = object   # duck-typed: oracle.configs.act_from_dict(...) or any object with the same attributes
 
 IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+_CONSTANTS = {}
+
+
+def _imagenet_constants(device):
+    """(mean, std) broadcastable over [B, V, 3, H, W], created once per device (a host -> device copy cannot be captured
+    into a CUDA graph, which the stock-PyTorch GPU baseline does with this function)."""
+    key = str(device)
+    if key not in _CONSTANTS:
+        _CONSTANTS[key] = (torch.tensor(IMAGENET_MEAN, device=device)[None, None, :, None, None],
+                           torch.tensor(IMAGENET_STD, device=device)[None, None, :, None, None])
+    return _CONSTANTS[key]
 
 
 def position_embedding_sine(h: int, w: int, num_pos_feats: int, temperature: float = 10000.0) -> torch.Tensor:
@@ -110,8 +123,7 @@ def act_forward(sd: Dict[str, torch.Tensor], cfg: ACTConfig, qpos: torch.Tensor,
     Returns (a_hat [B, num_queries, action_dim], is_pad_hat [B, num_queries, 1])."""
     bsz, nv = image.shape[:2]
     d = cfg.hidden_dim
-    mean = torch.tensor(IMAGENET_MEAN)[None, None, :, None, None]
-    std = torch.tensor(IMAGENET_STD)[None, None, :, None, None]
+    mean, std = _imagenet_constants(image.device)
     img = (image.float() / 255.0 - mean) / std                     # genima_act.py:188
     feats, poss = [], []
     for v in range(nv):

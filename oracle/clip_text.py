@@ -14,7 +14,7 @@ from typing import Dict
 import torch
 import torch.nn.functional as F
 
-from genima_b200.configs import CLIPTextConfig
+CLIPTextConfig = object   # duck-typed: oracle.configs.text_from_json(...) or any object with the same attributes
 
 
 def clip_text_forward(sd: Dict[str, torch.Tensor], cfg: CLIPTextConfig, ids: torch.Tensor, penultimate: bool = False):

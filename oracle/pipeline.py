@@ -20,7 +20,7 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from genima_b200.configs import ACTConfig, UNetConfig, VAEConfig
+ACTConfig = UNetConfig = VAEConfig = object   # duck-typed configuration objects (oracle/configs.py)
 
 from . import act as act_oracle
 from . import sd_models, tiling

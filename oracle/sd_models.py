@@ -2,7 +2,7 @@
 
 diffusers is pinned by the reference (pyproject.toml:24, poetry.lock:595-596) but is not vendored and cannot be
 installed offline, so these functions restate its published architecture (SURVEY.md Appendices A-C), operating on the
-upstream state-dict key names (genima_b200/weights.py schemas).  PARITY UNPINNED: no upstream golden vector exists.
+upstream state-dict key names.  PARITY UNPINNED: no upstream golden vector exists.
 
 Upstream modules restated (file paths inside diffusers 0.29.0):
   models/embeddings.py            get_timestep_embedding, TimestepEmbedding
@@ -23,7 +23,9 @@ from typing import Dict, List, Optional, Tuple
 import torch
 import torch.nn.functional as F
 
-from genima_b200.configs import UNetConfig, VAEConfig
+from .configs import taesd_layer_plan
+
+UNetConfig = VAEConfig = object   # duck-typed configuration objects (oracle/configs.py)
 
 SD = Dict[str, torch.Tensor]
 
@@ -255,8 +257,6 @@ def taesd_decode(sd: SD, cfg, z: torch.Tensor) -> torch.Tensor:
     upsampling -> x * 2 - 1 (images in [-1, 1], like AutoencoderKL.decode).  Reached from
     controller/agent/sd_controlnet_agent.py:45-49 when eval_cfg.autoencoder names a TAESD checkpoint; the pipeline divides
     the latents by scaling_factor (1.0) first.  [upstream, from memory: diffusers 0.29.0 models/autoencoders/vae.py]"""
-    from genima_b200.weights import taesd_layer_plan
-
     h = torch.tanh(z / cfg.latent_magnitude) * cfg.latent_magnitude
     for kind, i in taesd_layer_plan(cfg):
         p = f"decoder.layers.{i}"

@@ -153,12 +153,12 @@ def main():
             try:
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
+                with torch.cuda.stream(side), torch.device("cuda"):
                     chain()
                 torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph), torch.device("cuda"):
                     chain()
                 ms_g, _ = timed(graph.replay, args.reps, 2)
                 out["cuda_graph_ms"] = round(ms_g, 2)

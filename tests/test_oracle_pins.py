@@ -185,3 +185,91 @@ def test_tile_untile_round_trip_property():
 
     v = np.random.RandomState(3).randint(0, 256, size=(4, 64, 64, 3), dtype=np.uint8)
     assert np.array_equal(tiling.untile_views(tiling.tile_views(v)), v)
+
+
+# ------------------------------------------------------------------------------------ the oracle's own architecture
+class _Recording(dict):
+    """State dict that records which keys the oracle graph reads."""
+
+    def __init__(self, sd):
+        super().__init__(sd)
+        self.touched = set()
+
+    def __getitem__(self, k):
+        self.touched.add(k)
+        return super().__getitem__(k)
+
+    def __contains__(self, k):
+        return super().__contains__(k)
+
+
+def test_oracle_configs_are_independent_literals_that_reproduce_the_published_counts():
+    """oracle/configs.py states the upstream config.json values itself and counts parameters in closed form (no key
+    table): the published model sizes come out exactly, and the product's schemas agree with them."""
+    from genima_b200.configs import CLIPTextConfig as PText
+    from genima_b200.configs import UNetConfig, VAEConfig
+    from oracle import configs as oc
+
+    ucfg, vcfg, tcfg = oc.sd_turbo()
+    assert oc.count_unet(ucfg) == 865_910_724                    # SD-2.1 UNet2DConditionModel
+    assert oc.count_controlnet(ucfg) == 364_228_240              # ControlNetModel.from_unet(SD-2.1)
+    assert oc.count_vae_decoder(vcfg) == 49_490_199              # AutoencoderKL decoder + post_quant_conv
+    assert oc.count_clip_text(tcfg) == 340_387_840               # OpenCLIP ViT-H/14 text tower, 23 layers
+    assert oc.count_clip_text(oc.text_from_json(oc.CLIP_VIT_B32_TEXT)) == 63_428_096      # CLIP ViT-B/32 text tower
+    assert oc.count_unet(oc.unet_from_json(oc.SDXL_UNET_JSON)) == 2_567_463_684            # SDXL U-Net
+    # the product's table-driven schemas (a different derivation) give the same totals ...
+    assert W.count_params(W.unet_shapes(UNetConfig())) == oc.count_unet(ucfg)
+    assert W.count_params(W.controlnet_shapes(UNetConfig())) == oc.count_controlnet(ucfg)
+    assert W.count_params(W.vae_decoder_shapes(VAEConfig())) == oc.count_vae_decoder(vcfg)
+    assert W.count_params(W.clip_text_shapes(PText.sd_turbo())) == oc.count_clip_text(tcfg)
+    assert W.count_params(W.unet_shapes(UNetConfig.sdxl())) == oc.count_unet(oc.unet_from_json(oc.SDXL_UNET_JSON))
+    # ... and field for field the same hyper-parameters
+    for name in ("in_channels", "out_channels", "block_out_channels", "layers_per_block", "num_heads", "attn_levels",
+                 "cross_attention_dim", "norm_num_groups", "norm_eps", "cond_embed_channels", "addition_embed"):
+        assert getattr(ucfg, name) == getattr(UNetConfig(), name), name
+    for name in ("latent_channels", "out_channels", "block_out_channels", "layers_per_block", "norm_num_groups",
+                 "norm_eps", "scaling_factor"):
+        assert getattr(vcfg, name) == getattr(VAEConfig(), name), name
+    acfg = oc.act_from_dict(oc.GENIMA_ACT)
+    for name in ("hidden_dim", "enc_layers", "dec_layers", "dim_feedforward", "nheads", "num_queries", "state_dim",
+                 "action_dim", "latent_dim", "num_views", "image_size", "task_emb_dim", "resnet_widths"):
+        assert getattr(acfg, name) == getattr(ACTConfig(), name), name
+
+
+def test_oracle_graphs_touch_exactly_the_published_parameters():
+    """Trace the oracle's U-Net / ControlNet / VAE / ACT graphs (built from oracle/configs.py, NOT the product's config
+    classes) with a recording state dict at a reduced width: every parameter of the schema is read, none is invented —
+    so the graph that defines parity uses exactly the tensors whose count equals the published model size."""
+    from oracle import act as act_oracle
+    from oracle import configs as oc
+    from oracle import sd_models
+
+    j = dict(oc.SD_TURBO_UNET_JSON, block_out_channels=[64, 128, 128, 128], attention_head_dim=[1, 2, 2, 2],
+             cross_attention_dim=128)
+    ucfg = oc.unet_from_json(j, cond_channels=[16, 32, 64, 64])
+    vcfg = oc.vae_from_json(dict(oc.SD_TURBO_VAE_JSON, block_out_channels=[64, 64, 128, 128]))
+    acfg = oc.act_from_dict(dict(oc.GENIMA_ACT, hidden_dim=64, enc_layers=1, dec_layers=2, dim_feedforward=128, nheads=2,
+                                 num_queries=4, image_size=64, task_emb_dim=64, resnet_widths=[64, 64, 64, 64]))
+    usd = _Recording({k: v.float() for k, v in W.synth_state_dict(W.unet_shapes(ucfg)).items()})
+    csd = _Recording({k: v.float() for k, v in W.synth_state_dict(W.controlnet_shapes(ucfg), 1).items()})
+    vsd = _Recording({k: v.float() for k, v in W.synth_state_dict(W.vae_decoder_shapes(vcfg), 2).items()})
+    asd = _Recording({k: v.float() for k, v in W.synth_state_dict(W.act_shapes(acfg), 3).items()})
+    assert sum(v.numel() for v in usd.values()) == oc.count_unet(ucfg)
+    assert sum(v.numel() for v in csd.values()) == oc.count_controlnet(ucfg)
+    assert sum(v.numel() for v in vsd.values()) == oc.count_vae_decoder(vcfg)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 4, 8, 8, generator=g)
+    ctx = torch.randn(1, 77, 128, generator=g)
+    cond = torch.rand(1, 3, 64, 64, generator=g)
+    t = torch.tensor([999.0])
+    with torch.no_grad():
+        down, mid = sd_models.controlnet_forward(csd, ucfg, x, t, ctx, cond, 1.0)
+        sd_models.unet_forward(usd, ucfg, x, t, ctx, down, mid)
+        sd_models.vae_decode(vsd, vcfg, x)
+        act_oracle.act_forward(asd, acfg, torch.randn(1, 8, generator=g),
+                               torch.rand(1, 4, 3, 64, 64, generator=g) * 255, torch.randn(1, 64, generator=g))
+    assert usd.touched == set(usd.keys())
+    assert csd.touched == set(csd.keys())
+    assert vsd.touched == set(vsd.keys())
+    # ACT: the inference branch never reads the CVAE encoder side; everything in the schema is inference-side
+    assert asd.touched == set(asd.keys())

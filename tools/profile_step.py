@@ -21,17 +21,10 @@ ap.add_argument("--eager", action="store_true")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--out", default="gpurun_out/kineto_step.txt")
 args = ap.parse_args()
-ucfg, vcfg, acfg = bench.presets("sd-turbo")
-shapes = bench.model_shapes(ucfg, vcfg, acfg)
-dev = torch.device("cuda", 0)
-sds, arena = gd.broadcast_weights(shapes, bench.synth_all(shapes), device=dev)
-ops = Ops(0)
-pipe = B200ControlNetPipeline(ops, sds["unet"], sds["controlnet"], sds["vae"], None, ucfg, vcfg)
-act = DeviceACT(ops, sds["act"], acfg)
+w = bench.build_world(argparse.Namespace(preset="sd-turbo", autoencoder="", denoise_steps=5))
+pipe, act = w.pipe, w.act
 step = GenimaStep(pipe, act, num_inference_steps=5, use_cuda_graph=not args.eager)
-views, qpos, task, ctx, lat = bench.make_inputs(ucfg, acfg)
-d = dict(views=views.permute(0, 2, 3, 1).contiguous()[None].to(dev), lat=lat.to(dev), qpos=qpos.to(dev),
-         task=task.to(dev), ctx=ctx.to(dev))
+d = dict(views=w.d_views, lat=w.d_lat, qpos=w.d_qpos, task=w.d_task, ctx=w.d_ctx)
 for _ in range(3):
     step(d["views"], d["lat"], d["qpos"], d["task"], prompt_embeds=d["ctx"])
 torch.cuda.synchronize()
