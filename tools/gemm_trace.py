@@ -11,7 +11,8 @@ ops = Ops(0, workspace_mb=256)
 tr = torch.zeros(16, dtype=torch.int64, device="cuda")
 names = ["start", "setup", "tma0", "ops0", "mma_issued", "acc_done", "epi_done", "exit", "chunks", "bar", "st_issued", "gn", "st_read"]
 for (M, N, K, res) in [(4096, 320, 320, True), (4096, 320, 1280, True), (4096, 960, 320, False), (1024, 640, 640, True),
-                       (256, 1280, 1280, True), (64, 1280, 1280, True), (4096, 512, 512, False)]:
+                       (256, 1280, 1280, True), (64, 1280, 1280, True), (4096, 512, 512, False), (64, 1280, 5120, True),
+                       (256, 1280, 5120, True), (64, 1280, 11520, False), (256, 1280, 11520, False)]:
     a = torch.randn(M, K, device="cuda").half()
     w = (torch.randn(N, K, device="cuda") * K ** -0.5).half()
     b = torch.randn(N, device="cuda")
