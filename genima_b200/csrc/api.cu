@@ -164,6 +164,15 @@ int gn_set_gemm_multicast(gn_handle* h, int max_cluster, int force_cluster) {
   return GN_OK;
 }
 
+int gn_set_gemm_pair(gn_handle* h, int mode) {
+  if (!h || mode < 0 || mode > 2) return GN_ERR_INVALID;
+  h->pair_mode = mode;
+  h->tune_cache.clear();
+  return GN_OK;
+}
+
+int gn_last_gemm_pair(const gn_handle* h) { return h ? h->last_pair : 0; }
+
 int gn_set_conv_halo(gn_handle* h, int enable, int base_offset_field) {
   if (!h) return GN_ERR_INVALID;
   h->halo_conv = enable != 0;

@@ -38,6 +38,8 @@ struct gn_handle {
   bool halo_base_offset = false;  // UMMA descriptor variant: B200 swizzles on absolute address bits, the field stays 0
   int force_mcast = 0;  // 0: autotuned; 2 / 4: W-tile multicast cluster size wherever applicable
   int mcast_max = 1;    // largest multicast cluster the tile search may try (1 = off: measured slower on B200)
+  int pair_mode = 1;    // CTA pairs (cta_group::2, M = 256 MMAs): 0 never, 1 a candidate of the tile search, 2 wherever possible
+  int last_pair = 0;    // the last GEMM-class launch used CTA pairs
   // measured tile configurations per problem shape (gn_set_autotune): key -> {block_n, splits, stages, tmem_cols}
   bool autotune = false;
   std::unordered_map<std::string, std::array<int, 4>> tune_cache;
@@ -139,12 +141,13 @@ inline cudaError_t launch_ex(const gn_handle* h, void (*kernel)(KArgs...), dim3 
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  // cluster_z: low byte = cluster size along grid.z, next byte = cluster size along grid.y (0 / 1 = none)
+  // cluster_z: low byte = cluster size along grid.z, next byte = along grid.y, third byte = along grid.x (0 / 1 = none)
   const int cz = (cluster_z & 0xff) > 1 ? (cluster_z & 0xff) : 1;
   const int cy = ((cluster_z >> 8) & 0xff) > 1 ? ((cluster_z >> 8) & 0xff) : 1;
-  if (cz > 1 || cy > 1) {
+  const int cx = ((cluster_z >> 16) & 0xff) > 1 ? ((cluster_z >> 16) & 0xff) : 1;
+  if (cz > 1 || cy > 1 || cx > 1) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.x = cx;
     attr[na].val.clusterDim.y = cy;
     attr[na].val.clusterDim.z = cz;
     ++na;

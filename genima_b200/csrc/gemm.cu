@@ -95,6 +95,8 @@ struct GemmParams {
   int w_prefetch;  // 1: W is a constant weight matrix -- the producer requests the first W tiles BEFORE griddepcontrol.wait,
                    // so weight streaming (cold in HBM at batch 1) overlaps the tail of the previous kernel
   int mcast;  // compact flavours: cluster size along grid.y whose CTAs share the W tile through TMA multicast (1 = off)
+  int pair;   // 1: CTA pairs (cta_group::2): two consecutive m-tiles run ONE M = 256 MMA, every CTA fetches its own A tile
+              // and HALF of the W tile (block_n / 2 rows) -- the weight bytes an SM has to ingest per output tile halve
   // ---- output staging (see epilogue_tail): the epilogue warps write the finished fp16 tile into shared memory in the
   // layout of a TMA box {io_w columns, 128 rows} per sub-tile (swizzle span = 2 * io_w bytes) and ONE thread stores it with
   // cp.async.bulk.tensor; the residual tile is prefetched into the same buffer by the producer warp while the MMAs run.
@@ -626,7 +628,7 @@ __device__ __forceinline__ void fast_epilogue_rows(const GemmParams& p, uint32_t
     sts128(a1, q1);
   }
   if (e.rs_out && valid) {
-    const int part = (int)blockIdx.x * EPI_COLSPLIT + cw;  // one partial per (n-tile, column share)
+    const int part = (int)(p.pair ? blockIdx.y : blockIdx.x) * EPI_COLSPLIT + cw;  // one partial per (n-tile, column share)
     e.rs_out[(int64_t)m * e.rs_parts + part] = make_float2(rs[0], rs[1]);
   }
 }
@@ -902,7 +904,7 @@ __device__ __forceinline__ void split_finish(const GemmParams& p, uint32_t taddr
     sts128(a1, q1);
   }
   if (e.rs_out && valid) {
-    const int part = ((int)blockIdx.x * S + rank) * EPI_COLSPLIT + cw;
+    const int part = ((int)(p.pair ? blockIdx.y : blockIdx.x) * S + rank) * EPI_COLSPLIT + cw;
     e.rs_out[(int64_t)m * e.rs_parts + part] = make_float2(rs[0], rs[1]);
   }
   // ---- store the owned chunks, GroupNorm statistics of the owned chunks
@@ -985,7 +987,9 @@ __device__ __forceinline__ void split_finish(const GemmParams& p, uint32_t taddr
   if (et == 0) tma_store_wait_read();
 }
 
-template <int KIND>
+// PAIR variants are separate kernels: a kernel that contains cta_group::2 instructions can only be launched as a cluster
+// of an even number of CTAs.
+template <int KIND, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -995,7 +999,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
   const int block_n = p.block_n;
-  const int b_stage_bytes = block_n * BLOCK_K * 2;
+  constexpr bool pair = PAIR;
+  const uint32_t crank = pair ? cluster_ctarank() : 0u;  // pair peers: cluster ranks 2j (leader) and 2j + 1
+  const int half = (int)(crank & 1u);
+  const int b_rows = pair ? (block_n >> 1) : block_n;  // W rows this CTA fetches per k-block
+  const int b_stage_bytes = b_rows * BLOCK_K * 2;
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + (p.halo ? HALO_STAGES * HALO_STAGE : stages * p.a_stage_bytes);
@@ -1015,7 +1023,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
   const uint32_t io_base = smem_u32(smem) + p.io_off;
 
-  const int n0 = blockIdx.x * block_n;
+  // pair kernels swap the grid axes: the two CTAs of a pair must be neighbours along grid.x (cluster dims (2, 1, S))
+  const int n0 = (int)(PAIR ? blockIdx.y : blockIdx.x) * block_n;
   const int n0_out = p.epi.geglu ? (n0 >> 1) : n0;
   const bool mcast_on = (KIND < K_GENERIC) && p.mcast > 1;
   if (threadIdx.x == 0) trace_stamp(p, 0);
@@ -1037,12 +1046,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 1) {
+    if (pair) tmem_alloc_pair(tmem_slot, p.tmem_cols);
+    else tmem_alloc(tmem_slot, p.tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   // peers multicast into this CTA's shared memory and arrive on its barriers: they must see them initialised
   if (mcast_on) cluster_arrive();
+  if (pair) {  // the peer's TMA loads complete on the leader's barriers, the leader's commits arrive on the peer's
+    cluster_arrive();
+    cluster_wait();
+  }
   // Everything above touched only this CTA's shared / tensor memory.  Let the next kernel's CTAs be scheduled, then wait
   // for the previous kernel in the stream before the first global-memory access (programmatic dependent launch).
   pdl_trigger();
@@ -1052,21 +1068,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     const int nit = min(p.num_kblocks, kb0 + p.kb_per_split) - kb0;
     w_pre = min(nit, stages);
     for (int it = 0; it < w_pre; ++it) {
-      mbar_expect_tx(&full_bar[it], b_stage_bytes);
-      tma_load_2d(smem_b + it * b_stage_bytes, &p.tmB, &full_bar[it], (kb0 + it) * BLOCK_K, n0);
+      if (pair) {
+        // (no expect_tx here: the leader announces the bytes of BOTH CTAs when it arrives for the k-block; a complete_tx
+        // that lands first only drives the transaction count negative while that arrival is still pending)
+        tma_load_2d_pair(smem_b + it * b_stage_bytes, &p.tmB, mapa_shared(smem_u32(&full_bar[it]), crank & ~1u),
+                         (kb0 + it) * BLOCK_K, n0 + half * b_rows);
+      } else {
+        mbar_expect_tx(&full_bar[it], b_stage_bytes);
+        tma_load_2d(smem_b + it * b_stage_bytes, &p.tmB, &full_bar[it], (kb0 + it) * BLOCK_K, n0);
+      }
     }
     // ... and the rest of this CTA's W slice is requested into the L2 right away: at batch 1 every weight byte is cold
     // in HBM, and the HBM -> L2 transfer then runs behind the predecessor's tail and the first k-blocks instead of
     // being paced by the depth of the operand ring
     if (p.w_prefetch > 1)
-      for (int it = w_pre; it < nit; ++it) tma_prefetch_l2_2d(&p.tmB, (kb0 + it) * BLOCK_K, n0);
+      for (int it = w_pre; it < nit; ++it) tma_prefetch_l2_2d(&p.tmB, (kb0 + it) * BLOCK_K, n0 + half * b_rows);
   }
   pdl_wait();
   if (mcast_on) cluster_wait();  // (arrived above: complete long before the previous kernel has drained)
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace_stamp(p, 1);
 
-  const int mt = blockIdx.y;
+  const int mt = PAIR ? blockIdx.x : blockIdx.y;
   int m0 = 0, x0 = 0, y0 = 0, b0 = 0;
   if (p.mode == 0) {
     m0 = mt * BLOCK_M;
@@ -1088,7 +1111,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       // ------------------------------------------------------------------ TMA producer
       if (KIND == K_SPLIT && p.res_tma) {
         // residual boxes ({16 columns, 128 rows}) of the chunks this rank will finish -> staging buffer
-        const int rank = (int)cg::this_cluster().block_rank();
+        const int rank = (int)blockIdx.z;  // K-split index (= cluster rank without CTA pairs, rank / 2 with)
         const int nchunks = block_n >> 4;
         int owned = 0;
         for (int ch = rank; ch < nchunks && n0 + (ch << 4) < p.epi.N; ch += p.splits) ++owned;
@@ -1159,6 +1182,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       }
       int cb = kb_begin - seg_start;
       const uint32_t tx_bytes = p.a_stage_bytes + b_stage_bytes;
+      if (pair) {
+        // ---- CTA pair: own A tile + own half of the W tile per k-block; every load completes on the LEADER's barrier,
+        // which the leader arms with the bytes of both CTAs.  Each CTA waits for its own copy of the empty barrier
+        // (the leader's commit arrives on both).
+        const uint32_t lead = crank & ~1u;
+        for (int it = 0; it < num_it; ++it) {
+          const int s = it % stages;
+          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
+          if (half == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * tx_bytes);
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), lead);
+          const int kb = kb_begin + it;
+          if (p.mode == 0) {
+            tma_load_2d_pair(smem_a + s * p.a_stage_bytes, &p.tmA[0], fb, kb * BLOCK_K, m0);
+          } else {
+            const KSeg sg = p.segs[seg];
+            tma_load_4d_pair(smem_a + s * p.a_stage_bytes, &p.tmA[sg.map], fb, cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy, b0);
+            if (++cb == sg.nblk) {
+              cb = 0;
+              ++seg;
+            }
+          }
+          if (it >= w_pre) tma_load_2d_pair(smem_b + s * b_stage_bytes, &p.tmB, fb, kb * BLOCK_K, n0 + half * b_rows);
+          if (it == 0) trace_stamp(p, 2);
+        }
+      } else
       for (int it = 0; it < num_it; ++it) {
         const int s = it % stages;
         const uint32_t ph = (it / stages) & 1;
@@ -1243,6 +1291,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
             ++ia;
           }
         }
+      } else if (pair) {
+        // ---- leader of a CTA pair: M = 256 MMAs over both CTAs' shared memory (same offsets in the peer), commits
+        // multicast to both CTAs' barriers; the peer's MMA thread has nothing to do
+        if (half == 0) {
+          const uint32_t idesc2 = umma_idesc_f16_m256(block_n);
+          const uint16_t pmask = static_cast<uint16_t>(3u << crank);
+          for (int it = 0; it < num_it; ++it) {
+            const int s = it % stages;
+            mbar_wait(&full_bar[s], (it / stages) & 1);
+            tc_fence_after();
+            if (it == 0) trace_stamp(p, 3);
+            const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * p.a_stage_bytes), 1024, 0);
+            const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * b_stage_bytes), 1024, 0);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k)
+              umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc2, (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(&empty_bar[s], pmask);
+          }
+          umma_commit_pair(tmem_full_bar, pmask);
+          trace_stamp(p, 4);
+        }
       } else
       for (int it = 0; it < num_it; ++it) {
         const int s = it % stages;
@@ -1260,8 +1329,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         if (mcast_on) umma_commit_mcast(&empty_bar[s], static_cast<uint16_t>((1u << p.mcast) - 1u));
         else umma_commit(&empty_bar[s]);
       }
-      umma_commit(tmem_full_bar);
-      trace_stamp(p, 4);
+      if (!pair) {
+        umma_commit(tmem_full_bar);
+        trace_stamp(p, 4);
+      }
     }
   } else {
     // -------------------------------------------------------------------- epilogue warps (2 .. 2 + 4 * EPI_COLSPLIT)
@@ -1297,8 +1368,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       if (threadIdx.x == 64) trace_stamp(p, 5);
-      split_dump(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16), cw, (int)cg::this_cluster().block_rank(), row,
-                 valid);
+      split_dump(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16), cw, (int)blockIdx.z, row, valid);
       tc_fence_before();
       if (threadIdx.x == 64) trace_stamp(p, 6);
     } else if constexpr (KIND != K_GENERIC) {
@@ -1382,7 +1452,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         m = (gb * p.Ho + gy) * p.Wo + gx;
       }
       const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
-      const int rank = (int)cluster.block_rank();
+      const int rank = (int)blockIdx.z;
       if (p.res_tma) {
         int owned = 0;
         for (int ch = rank; ch < (block_n >> 4) && n0 + (ch << 4) < p.epi.N; ch += p.splits) ++owned;
@@ -1424,9 +1494,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     cluster.sync();  // peers may still be reading this CTA's staging tile
   }
   __syncthreads();
+  if (pair) {
+    // both CTAs of a pair are done with the shared tensor-memory allocation (and no commit of the leader can still be
+    // on its way to the peer's barriers) before either releases it
+    cluster_arrive();
+    cluster_wait();
+  }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (pair) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
   if (mcast_on) {
     // no CTA may exit while a peer's tcgen05.commit can still arrive on its barriers
@@ -1441,6 +1518,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
 struct TileChoice {
   int block_n, splits, stages, tmem_cols;
   int mcast = 1;  // W-tile multicast cluster size along the M tiles (compact non-split flavours)
+  int pair = 0;   // 1: CTA pairs along the M tiles (cta_group::2, M = 256 MMAs; compact and compact split-K flavours)
 };
 
 // What the epilogue of this launch may do (decided per call from the tensors' alignment and the gn_epilogue request).
@@ -1460,6 +1538,7 @@ struct OutGeom {
   bool mcast_ok = false;    // a non-split launch can use a compact flavour (and therefore W-tile multicast)
   bool halo = false;        // halo-mode convolution: the A ring holds HALO_STAGES halo tiles
   bool res_late = false;    // (set per candidate) alias the residual staging buffer with the operand ring
+  int pair = 0;             // (set per candidate) CTA pairs: every CTA stages block_n / 2 rows of W per k-block
   int a_stage = A_STAGE_BYTES;  // bytes of one A stage (8 KiB when the A box carries 64 rows)
   bool strided = false;         // the output pixels are not contiguous: only staged (TMA-stored) configurations apply
   int img_rows = 0;       // rows of one image inside a 128-row tile (GroupNorm statistics); 0: layout unsupported
@@ -1480,8 +1559,9 @@ static int gn_rows_for(int bn_out, int img_rows) {
 static SmemLayout smem_layout(int block_n, int stages, int splits, const OutGeom& og) {
   SmemLayout L;
   const int bn_out = og.geglu ? block_n / 2 : block_n;
-  int ring = og.halo ? HALO_STAGES * HALO_STAGE + stages * block_n * BLOCK_K * 2
-                     : stages * (og.a_stage + block_n * BLOCK_K * 2);
+  const int b_rows = og.pair ? block_n / 2 : block_n;
+  int ring = og.halo ? HALO_STAGES * HALO_STAGE + stages * b_rows * BLOCK_K * 2
+                     : stages * (og.a_stage + b_rows * BLOCK_K * 2);
   const int stage_tile = block_n * BLOCK_M * 4;  // fp32 staging tile of the cluster split-K reduction (aliases the ring)
   const bool split_fast = splits > 1 && og.split_fast;
   if (splits > 1 && !split_fast && stage_tile > ring) ring = stage_tile;
@@ -1521,10 +1601,16 @@ struct Candidate {
 };
 
 static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblocks, bool geglu, bool allow_split,
-                          Candidate* out, int max_out, int rs_capacity, const OutGeom& og) {
+                          Candidate* out, int max_out, int rs_capacity, const OutGeom& og_in) {
   static const int kCand[] = {256, 224, 192, 160, 128, 96, 80, 64, 48, 32, 16};
   const int sms = h->num_sms;
   std::vector<Candidate> all;
+  // CTA pairs need an even number of m-tiles, full 128-row A boxes and a compact kernel flavour
+  const bool pair_possible = h->pair_mode != 0 && (tiles_m % 2) == 0 && !og_in.halo && og_in.a_stage == A_STAGE_BYTES;
+  for (int pr = 0; pr <= (pair_possible ? 1 : 0); ++pr) {
+  if (h->pair_mode == 2 && pair_possible && pr == 0) continue;  // forced (tests, A/B)
+  OutGeom og = og_in;
+  og.pair = pr;
   for (int bn : kCand) {
     if (geglu && (bn % 128) != 0) continue;
     if (h->force_block_n && bn != h->force_block_n) continue;
@@ -1536,9 +1622,11 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
       max_splits = num_kblocks / 4;  // keep >= 4 k-blocks per split
       if (max_splits < 1) max_splits = 1;
       if (max_splits > MAX_CLUSTER_SPLITS) max_splits = MAX_CLUSTER_SPLITS;
+      if (pr && max_splits > MAX_CLUSTER_SPLITS / 2) max_splits = MAX_CLUSTER_SPLITS / 2;  // cluster = 2 x splits CTAs
     }
     for (int sp = 1; sp <= max_splits; ++sp) {
       if (h->force_splits && sp != h->force_splits && !(h->force_splits > max_splits && sp == max_splits)) continue;
+      if (pr && !(sp == 1 ? og.mcast_ok : og.split_fast)) continue;  // pairs exist in the compact flavours only
       const int kb_per = gn::ceil_div(num_kblocks, sp);
       if ((sp - 1) * kb_per >= num_kblocks) continue;  // an empty split
       if (rs_capacity > 0 && tiles_n * sp * EPI_COLSPLIT > rs_capacity) continue;  // row-statistics partials must fit
@@ -1552,13 +1640,14 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
         if (h->force_occupancy == 2 && occ == 1 && occ2_fits) continue;  // forced 2 CTAs/SM, unless that cannot fit
         if (occ == 2 && !occ2_fits) continue;
         const double t_mma = 2.0 * bn;
-        const double t_ld = (128.0 + bn) * 128.0 / 46.0;
+        const double t_ld = (128.0 + (pr ? bn / 2 : bn)) * 128.0 / 46.0;
         const double t_kb = t_mma > t_ld ? t_mma : t_ld;
         const double per_sm = (double)((ctas + sms - 1) / sms);                // main loops an SM runs back to back
         const double rounds = (double)((ctas + occ * sms - 1) / (occ * sms));  // exposed per-CTA latencies
         double lat = 25.0 * bn + 3000.0;
         if (sp > 1) lat += 2500.0 + 8.0 * bn;   // two cluster barriers + DSMEM reduction
         if (sp == 5 || sp == 7) lat += 2000.0;  // cluster sizes that pack the 18-SM GPCs badly
+        if (pr) lat += 600.0;                   // two more cluster barriers
         const int st = stages_for(bn, sp, kb_per, occ == 2 ? SMEM_OCC2 : SMEM_OCC1, og);
         if (smem_bytes_for(bn, st, sp, og) > 227 * 1024) continue;
         double mainloop = per_sm * kb_per * t_kb;
@@ -1567,44 +1656,40 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
         c.tc.block_n = bn;
         c.tc.splits = sp;
         c.tc.stages = st;
+        c.tc.pair = pr;
         int tm = 32;
         while (tm < bn) tm <<= 1;
         c.tc.tmem_cols = tm;
         c.cost = mainloop + rounds * lat;
         bool dup = false;  // occupancy 1 / 2 sizing may give the same stage count
         for (const Candidate& o : all)
-          if (o.tc.block_n == bn && o.tc.splits == sp && o.tc.stages == st) dup = true;
+          if (o.tc.block_n == bn && o.tc.splits == sp && o.tc.stages == st && o.tc.pair == pr) dup = true;
         if (!dup) all.push_back(c);
         // W-tile multicast variants: the m-tiles of one n-tile form clusters of 2 / 4 CTAs (compact flavours only)
-        if (!dup && sp == 1 && og.mcast_ok && h->mcast_max > 1) {
-          bool forced_applied = false;
+        if (!dup && !pr && sp == 1 && og.mcast_ok && h->mcast_max > 1) {
           for (int mc = 2; mc <= h->mcast_max && mc <= 4; mc <<= 1) {
             if (h->force_mcast && mc != h->force_mcast) continue;
             if ((tiles_m % mc) != 0 || (bn % (8 * mc)) != 0) continue;
             Candidate m = c;
             m.tc.mcast = mc;
             m.cost = c.cost * (mc == 2 ? 0.97 : 0.95);
-            if (h->force_mcast) {
-              all.back() = m;  // forced: replaces the plain variant
-              forced_applied = true;
-            } else {
-              all.push_back(m);
-            }
+            if (h->force_mcast) all.back() = m;  // forced: replaces the plain variant
+            else all.push_back(m);
           }
-          (void)forced_applied;
         }
       }
     }
   }
+  }
   std::sort(all.begin(), all.end(), [](const Candidate& a, const Candidate& b) { return a.cost < b.cost; });
-  // best by the model first; keep the list diverse (at most 3 entries per tile width) so that a model error on one
-  // axis cannot hide the real optimum from the measurement
+  // best by the model first; keep the list diverse (at most 4 entries per tile width and pairing) so that a model error on
+  // one axis cannot hide the real optimum from the measurement
   int n_out = 0;
   for (const Candidate& c : all) {
     if (n_out >= max_out) break;
     int same_bn = 0;
-    for (int i = 0; i < n_out; ++i) same_bn += out[i].tc.block_n == c.tc.block_n;
-    if (same_bn >= 4) continue;
+    for (int i = 0; i < n_out; ++i) same_bn += out[i].tc.block_n == c.tc.block_n && out[i].tc.pair == c.tc.pair;
+    if (same_bn >= (h->pair_mode ? 3 : 4)) continue;
     out[n_out++] = c;
   }
   return n_out;
@@ -1719,7 +1804,9 @@ static int fill_out_geom(gn_handle* h, GemmParams& p, OutGeom& og, const gn_epil
 }
 
 static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int tiles_m, const void* W, int64_t ktot,
-                         const OutGeom& og, cudaStream_t stream) {
+                         const OutGeom& og_in, cudaStream_t stream) {
+  OutGeom og = og_in;
+  og.pair = tc.pair;
   const int N = p.epi.N;
   p.block_n = tc.block_n;
   p.splits = tc.splits;
@@ -1743,11 +1830,13 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ktot * 2};
-    uint32_t box[2] = {BLOCK_K, (uint32_t)(tc.block_n / tc.mcast)};  // with multicast every CTA fetches one slice
+    // with multicast every CTA fetches one slice, in a CTA pair each CTA fetches one half of the tile
+    uint32_t box[2] = {BLOCK_K, (uint32_t)(tc.pair ? tc.block_n / 2 : tc.block_n / tc.mcast)};
     int rc = make_tmap_f16(h, &p.tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }
   p.mcast = tc.mcast;
+  p.pair = tc.pair;
   p.a_stage_bytes = og.a_stage;
   // 2 (GENIMA_B200_DBG bit 32, off by default): also L2-prefetch the whole W slice of weight-heavy problems -- measured
   // 3 % SLOWER on the full step (the prefetch traffic competes with the kernels that are still running)
@@ -1792,13 +1881,16 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
   GN_CHECK_ARG(h, smem <= 227 * 1024, "GEMM tile configuration needs %d bytes of shared memory", smem);
   GN_CHECK_ARG(h, !og.strided || L.staged, "strided output needs a TMA-stored configuration");
   typedef void (*GemmKernel)(const GemmParams);
-  static const GemmKernel kKernels[K_SPLIT + 1] = {
-      gemm_tc_kernel<GN_ACT_NONE>,      gemm_tc_kernel<GN_ACT_SILU>, gemm_tc_kernel<GN_ACT_GELU>,
-      gemm_tc_kernel<GN_ACT_RELU>,      gemm_tc_kernel<GN_ACT_QUICKGELU>, gemm_tc_kernel<K_GEGLU>,
-      gemm_tc_kernel<K_GENERIC>,        gemm_tc_kernel<K_SPLIT>};
+  static const GemmKernel kKernels[2 * (K_SPLIT + 1)] = {
+      gemm_tc_kernel<GN_ACT_NONE, false>,      gemm_tc_kernel<GN_ACT_SILU, false>, gemm_tc_kernel<GN_ACT_GELU, false>,
+      gemm_tc_kernel<GN_ACT_RELU, false>,      gemm_tc_kernel<GN_ACT_QUICKGELU, false>, gemm_tc_kernel<K_GEGLU, false>,
+      gemm_tc_kernel<K_GENERIC, false>,        gemm_tc_kernel<K_SPLIT, false>,
+      gemm_tc_kernel<GN_ACT_NONE, true>,       gemm_tc_kernel<GN_ACT_SILU, true>, gemm_tc_kernel<GN_ACT_GELU, true>,
+      gemm_tc_kernel<GN_ACT_RELU, true>,       gemm_tc_kernel<GN_ACT_QUICKGELU, true>, gemm_tc_kernel<K_GEGLU, true>,
+      nullptr,                                 gemm_tc_kernel<K_SPLIT, true>};
   if (!h->gemm_attr_set) {
     for (GemmKernel k : kKernels)
-      GN_CHECK_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      if (k) GN_CHECK_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     h->gemm_attr_set = true;
   }
   // compact flavour when the whole epilogue can run from shared memory (see fast_epilogue_rows)
@@ -1809,15 +1901,20 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
                     e.act_pre >= GN_ACT_NONE && e.act_pre <= GN_ACT_QUICKGELU && !(e.geglu && e.act_pre != GN_ACT_NONE);
   const int kind = split_fast ? K_SPLIT : (!fast || tc.splits > 1) ? K_GENERIC : (e.geglu ? K_GEGLU : e.act_pre);
   dim3 grid(gn::ceil_div(N, tc.block_n), tiles_m, tc.splits);
+  if (tc.pair) grid = dim3(tiles_m, gn::ceil_div(N, tc.block_n), tc.splits);  // pairs are neighbours along grid.x
   // the K-splits of one output tile form a thread-block cluster (grid.z == cluster size)
   GN_CHECK_ARG(h, tc.mcast == 1 || (kind < K_GENERIC && tc.splits == 1 && (tiles_m % tc.mcast) == 0),
                "W multicast needs a compact non-split flavour and m-tiles divisible by the cluster size");
-  GN_CHECK_CUDA(h, launch_ex(h, kKernels[kind], grid, dim3(GEMM_THREADS, 1, 1), smem, stream,
-                              tc.splits | (tc.mcast << 8), p));
+  GN_CHECK_ARG(h, !tc.pair || (kind != K_GENERIC && tc.mcast == 1 && (tiles_m % 2) == 0 && 2 * tc.splits <= 8 &&
+                               !og.halo && og.a_stage == A_STAGE_BYTES),
+               "CTA pairs need a compact flavour, an even number of m-tiles and at most 4 K-splits");
+  GN_CHECK_CUDA(h, launch_ex(h, kKernels[kind + (tc.pair ? K_SPLIT + 1 : 0)], grid, dim3(GEMM_THREADS, 1, 1), smem, stream,
+                              tc.splits | (tc.pair ? (2 << 16) : (tc.mcast << 8)), p));
   h->last_cfg[0] = tc.block_n;
   h->last_cfg[1] = tc.splits;
   h->last_cfg[2] = tc.stages;
   h->last_cfg[3] = (int)(grid.x * grid.y * grid.z) * (tc.mcast > 1 ? -tc.mcast : 1);  // negative: x multicast size
+  h->last_pair = tc.pair;
   return GN_OK;
 }
 
@@ -1844,7 +1941,8 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
   if (!forced) {
     auto it = h->tune_cache.find(key);
     if (it != h->tune_cache.end()) {
-      TileChoice tc{it->second[0], it->second[1], it->second[2], it->second[3] & 0xffff, it->second[3] >> 16};
+      TileChoice tc{it->second[0], it->second[1], it->second[2], it->second[3] & 0xffff, (it->second[3] >> 16) & 0xff,
+                    (it->second[3] >> 24) & 1};
       if (tc.mcast < 1) tc.mcast = 1;
       int rc = launch_config(h, p, tc, tiles_m, W, ktot, og, stream);
       if (rc == GN_OK) h->launches++;
@@ -1854,8 +1952,9 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(stream, &cap);
   if (h->autotune && !forced && !h->profiling && cap == cudaStreamCaptureStatusNone) {
-    Candidate cand[10];
-    const int nc = candidate_list(h, tiles_m, N, p.num_kblocks, geglu, allow_split, cand, 10, rs_capacity, og);
+    Candidate cand[14];
+    const int nc = candidate_list(h, tiles_m, N, p.num_kblocks, geglu, allow_split, cand, h->pair_mode ? 14 : 10,
+                                  rs_capacity, og);
     if (nc > 1) {
       if (!h->tune_ev[0]) {
         GN_CHECK_CUDA(h, cudaEventCreate(&h->tune_ev[0]));
@@ -1891,7 +1990,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
         }
       }
       const TileChoice& tc = cand[best].tc;
-      h->tune_cache[key] = {tc.block_n, tc.splits, tc.stages, tc.tmem_cols | (tc.mcast << 16)};
+      h->tune_cache[key] = {tc.block_n, tc.splits, tc.stages, tc.tmem_cols | (tc.mcast << 16) | (tc.pair << 24)};
       // the timed launches accumulated into the caller's GroupNorm statistics as well: start them again from zero
       if (p.gn_out)
         GN_CHECK_CUDA(h, cudaMemsetAsync(p.gn_out, 0, (size_t)p.gn_stat_images * p.gn_nb * 16, stream));

@@ -105,6 +105,8 @@ class Ops:
             parts = [int(v) for v in mc.split(",")]
             self.handle.check(self.lib.gn_set_gemm_multicast(self.h, parts[0], parts[1] if len(parts) > 1 else 0),
                               "gn_set_gemm_multicast")
+        if os.environ.get("GENIMA_B200_PAIR", "1") != "1":   # A/B: 0 = no CTA pairs, 2 = pairs wherever possible
+            self.handle.check(self.lib.gn_set_gemm_pair(self.h, int(os.environ["GENIMA_B200_PAIR"])), "gn_set_gemm_pair")
         if os.environ.get("GENIMA_B200_ATTN_SPLIT", "1") != "1":   # A/B: 0 = no KV split, 2 = split whenever possible
             self.set_attention_kv_split(int(os.environ["GENIMA_B200_ATTN_SPLIT"]))
         # GroupNorm statistics fused into the producing GEMM epilogues (A/B switch: GENIMA_B200_GNFUSE=0)

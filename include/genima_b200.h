@@ -128,6 +128,13 @@ int gn_tune_cache_import(gn_handle* h, const char* buf, int64_t n, int replace);
  * that fetch one slice of the weight tile each and multicast it to the others (less L2 traffic on shapes where many
  * m-tiles re-read the same weights).  force_cluster = 2 / 4 uses that size wherever it applies (tests, A/B); 0 = autotuned. */
 int gn_set_gemm_multicast(gn_handle* h, int max_cluster, int force_cluster);
+/* CTA pairs (tcgen05 cta_group::2): two CTAs on neighbouring SMs compute two consecutive 128-row m-tiles with ONE M = 256
+ * MMA per k-step; each fetches its own A tile and half of the W tile, so the weight bytes an SM ingests per output tile
+ * halve (batch-1 GEMMs are bound by L2 -> SM operand traffic, not by the tensor pipe).  mode 0 = never, 1 = a candidate
+ * of the tile search (default), 2 = wherever the shape allows it (tests, A/B).  gn_last_gemm_pair reports whether the last
+ * gn_linear / gn_conv2d launch used pairs. */
+int gn_set_gemm_pair(gn_handle* h, int mode);
+int gn_last_gemm_pair(const gn_handle* h);
 /* Halo mode of gn_conv2d (3x3, stride 1, pad 1, C % 64 == 0, output width % 8 == 0): every CTA fetches, per
  * 64-channel block, three 8 x (16 + 2) pixel column strips (one per horizontal tap offset) and feeds the three vertical
  * taps of each to the tensor core as atom-aligned shared-memory windows of the strip, instead of fetching a 128-pixel

@@ -107,7 +107,7 @@ def main():
                 kw["out_fp32"] = True
             out = ops.linear(a, w, **kw)
             t = graph_time(lambda: ops.linear(a, w, out=out, **kw))
-            cfg = ops.last_gemm_config()
+            cfg = ops.last_gemm_config() + (("P",) if ops.lib.gn_last_gemm_pair(ops.h) else ())
             tb = graph_time(lambda: torch.matmul(a, w.t()))
             fl = 2.0 * M * N * K
             extra = ""
@@ -117,6 +117,13 @@ def main():
                     t2 = graph_time(lambda: ops.linear(a, w, out=out, **kw))
                     extra += f" | occ{occ} {t2:6.2f} {ops.last_gemm_config()}"
                 ops.lib.gn_set_gemm_occupancy(ops.h, 0)
+            if "--pair" in sys.argv:
+                for pm in (0, 2):
+                    ops.lib.gn_set_gemm_pair(ops.h, pm)
+                    ops.linear(a, w, out=out, **kw)   # re-tune among the allowed candidates
+                    t2 = graph_time(lambda: ops.linear(a, w, out=out, **kw))
+                    extra += f" | pair{pm} {t2:6.2f} {ops.last_gemm_config()}"
+                ops.lib.gn_set_gemm_pair(ops.h, 1)
             print(f"{M:5d} {N:6d} {K:5d} {mode:>9} | {t:7.2f} us {fl / t / 1e6:7.1f} TF/s {str(cfg):>22} | cuBLAS {tb:7.2f} us{extra}", flush=True)
     if which == "conv":
         import torch.nn.functional as F
@@ -132,7 +139,7 @@ def main():
             bias = torch.randn(Cout, device="cuda")
             out = ops.conv2d(x, wp, Cout, stride=s, bias=bias)
             t = graph_time(lambda: ops.conv2d(x, wp, Cout, stride=s, bias=bias, out=out), n=10)
-            cfg = ops.last_gemm_config()
+            cfg = ops.last_gemm_config() + (("P",) if ops.lib.gn_last_gemm_pair(ops.h) else ())
             xc = x.permute(0, 3, 1, 2)
             wc = w.cuda().to(memory_format=torch.channels_last)
             bh = bias.half()
@@ -145,6 +152,13 @@ def main():
                     t2 = graph_time(lambda: ops.conv2d(x, wp, Cout, stride=s, bias=bias, out=out), n=10)
                     extra += f" | occ{occ} {t2:6.2f} {ops.last_gemm_config()}"
                 ops.lib.gn_set_gemm_occupancy(ops.h, 0)
+            if "--pair" in sys.argv:
+                for pm in (0, 2):
+                    ops.lib.gn_set_gemm_pair(ops.h, pm)
+                    ops.conv2d(x, wp, Cout, stride=s, bias=bias, out=out)   # re-tune among the allowed candidates
+                    t2 = graph_time(lambda: ops.conv2d(x, wp, Cout, stride=s, bias=bias, out=out), n=10)
+                    extra += f" | pair{pm} {t2:6.2f} {ops.last_gemm_config()}"
+                ops.lib.gn_set_gemm_pair(ops.h, 1)
             print(f"conv {H:3d}^2 {Cin:4d}->{Cout:4d} s{s} | {t:7.2f} us {fl / t / 1e6:7.1f} TF/s {str(cfg):>22} | cuDNN {tb:7.2f} us{extra}", flush=True)
 
 
