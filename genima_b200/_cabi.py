@@ -67,10 +67,8 @@ SIGNATURES = {
     "gn_tune_cache_import": (_i, [_vp, C.c_char_p, _i64, _i]),
     "gn_set_gemm_occupancy": (_i, [_vp, _i]),
     "gn_set_attention_kv_split": (_i, [_vp, _i]),
-    "gn_set_gemm_multicast": (_i, [_vp, _i, _i]),
     "gn_set_gemm_pair": (_i, [_vp, _i]),
     "gn_last_gemm_pair": (_i, [_vp]),
-    "gn_set_conv_halo": (_i, [_vp, _i, _i]),
     "gn_set_gemm_trace": (_i, [_vp, _vp]),
     "gn_get_last_gemm_config": (_i, [_vp, C.POINTER(C.c_int32)]),
     "gn_get_last_rowstats_parts": (_i, [_vp]),

@@ -156,14 +156,6 @@ int gn_set_gemm_tuning(gn_handle* h, int block_n, int splits) {
   return GN_OK;
 }
 
-int gn_set_gemm_multicast(gn_handle* h, int max_cluster, int force_cluster) {
-  if (!h || max_cluster < 1 || max_cluster > 4 || force_cluster < 0 || force_cluster > 4) return GN_ERR_INVALID;
-  h->mcast_max = max_cluster;
-  h->force_mcast = force_cluster;
-  h->tune_cache.clear();
-  return GN_OK;
-}
-
 int gn_set_gemm_pair(gn_handle* h, int mode) {
   if (!h || mode < 0 || mode > 2) return GN_ERR_INVALID;
   h->pair_mode = mode;
@@ -172,14 +164,6 @@ int gn_set_gemm_pair(gn_handle* h, int mode) {
 }
 
 int gn_last_gemm_pair(const gn_handle* h) { return h ? h->last_pair : 0; }
-
-int gn_set_conv_halo(gn_handle* h, int enable, int base_offset_field) {
-  if (!h) return GN_ERR_INVALID;
-  h->halo_conv = enable != 0;
-  h->halo_base_offset = base_offset_field != 0;
-  h->tune_cache.clear();
-  return GN_OK;
-}
 
 int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm) {
   if (!h || ctas_per_sm < 0 || ctas_per_sm > 2) return GN_ERR_INVALID;

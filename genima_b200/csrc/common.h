@@ -34,10 +34,6 @@ struct gn_handle {
   int force_block_n = 0;
   int force_splits = 0;
   int force_occupancy = 0;
-  bool halo_conv = false;        // 3x3 stride-1 convolutions fetch column-strip halo tiles (gn_set_conv_halo); measured slower
-  bool halo_base_offset = false;  // UMMA descriptor variant: B200 swizzles on absolute address bits, the field stays 0
-  int force_mcast = 0;  // 0: autotuned; 2 / 4: W-tile multicast cluster size wherever applicable
-  int mcast_max = 1;    // largest multicast cluster the tile search may try (1 = off: measured slower on B200)
   int pair_mode = 1;    // CTA pairs (cta_group::2, M = 256 MMAs): 0 never, 1 a candidate of the tile search, 2 wherever possible
   int last_pair = 0;    // the last GEMM-class launch used CTA pairs
   // measured tile configurations per problem shape (gn_set_autotune): key -> {block_n, splits, stages, tmem_cols}

@@ -31,7 +31,9 @@ constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int MAX_SEGS = 52;
 constexpr int EPI_COLSPLIT = 2;                        // epilogue warps per TMEM lane quadrant
-constexpr int GEMM_THREADS = 64 + 128 * EPI_COLSPLIT;  // producer warp + MMA warp + epilogue warps
+constexpr int EPI_THREADS = 128 * EPI_COLSPLIT;
+constexpr int W_WARP = 2 + 4 * EPI_COLSPLIT;          // index of the W-producer warp (after the epilogue warps)
+constexpr int GEMM_THREADS = 64 + EPI_THREADS + 32;   // A-producer warp + MMA warp + epilogue warps + W-producer warp
 
 struct KSeg {
   int8_t map;  // index into tmA
@@ -81,20 +83,11 @@ struct GemmParams {
   int bw, bh, bb;
   int tiles_w, tiles_h;
   int block_n, stages, tmem_cols;
-  // ---- halo mode (3x3, stride 1, pad 1 convolutions): the A ring holds 8 x (16 + 2) pixel column strips of one
-  // 64-channel block, one per horizontal tap offset kx; the three vertical taps are the windows of the strip that start
-  // 0 / 8 / 16 rows (whole 1 KiB swizzle atoms) into it, so the input is fetched 3 times per channel block instead of 9.
-  // (A single (8 + 2) x (16 + 2) halo tile with nine windows at arbitrary row offsets also gives correct results -- the
-  // tensor core swizzles on absolute address bits -- but its MMAs measured ~3x slower: windows must stay atom-aligned.)
-  int halo;      // 1: halo mode (mode == 1 only)
-  int halo_ncb;  // 64-channel blocks of the main input; k-blocks [0, 9 * halo_ncb) are ((cb, kx), ky), ky fastest
-  int halo_bo;   // (unused) descriptor variant switch
   int a_stage_bytes;  // bytes of one A stage: 16 KiB, or 8 KiB when every m-tile has at most 64 real rows (8 x 8 images,
                       // M <= 64): the A box then carries 64 rows, the MMA still spans 128 (rows 64.. read whatever follows in
                       // shared memory; those accumulator rows are never stored), and the ring gets ~1.5x deeper
-  int w_prefetch;  // 1: W is a constant weight matrix -- the producer requests the first W tiles BEFORE griddepcontrol.wait,
-                   // so weight streaming (cold in HBM at batch 1) overlaps the tail of the previous kernel
-  int mcast;  // compact flavours: cluster size along grid.y whose CTAs share the W tile through TMA multicast (1 = off)
+  int w_prefetch;  // 1: W is a constant weight matrix -- its producer warp does not wait for the previous kernel
+                   // (griddepcontrol.wait), so weight streaming (cold in HBM at batch 1) overlaps that kernel's tail
   int pair;   // 1: CTA pairs (cta_group::2): two consecutive m-tiles run ONE M = 256 MMA, every CTA fetches its own A tile
               // and HALF of the W tile (block_n / 2 rows) -- the weight bytes an SM has to ingest per output tile halve
   // ---- output staging (see epilogue_tail): the epilogue warps write the finished fp16 tile into shared memory in the
@@ -116,17 +109,12 @@ struct GemmParams {
   int gn_stat_images;          // host-side: images covered by gn_out
   int w_dynamic;  // host-side: W is produced by an earlier kernel of the stream (no early prefetch)
   int dbg;    // experiment switches (GENIMA_B200_DBG): 1 skip scale/bias smem reads, 2 skip staging stores, 4 skip tmem_ld
-  float* ws;  // (unused) split-K workspace
+  float* ws;  // split-K workspace (L2-resident fp32 partials)
   int rs_capacity;            // host-side: capacity (partials per row) of epi.rs_out
   unsigned long long* trace;  // optional: %globaltimer stamps of CTA (0,0,0)'s phases (gn_set_gemm_trace)
   KSeg segs[MAX_SEGS];
 };
 
-constexpr int HALO_W = 8, HALO_H = 16;                 // output pixels per tile in halo mode
-constexpr int HALO_ROWS = HALO_W * (HALO_H + 2);        // one column strip: 8 x 18 pixel rows of 128 bytes
-constexpr int HALO_BYTES = HALO_ROWS * 128;             // 18 KiB per strip (a multiple of the 1 KiB swizzle repeat)
-constexpr int HALO_STAGE = HALO_BYTES;
-constexpr int HALO_STAGES = 4;
 constexpr float GN_FIXED_SCALE = 1048576.0f;  // 2^20: fixed-point scale of the GroupNorm (sum, sumsq) accumulators
 constexpr int TAIL_SCALE_FLOATS = 256;
 constexpr int TAIL_COL_FLOATS = 1024;  // column partials of the GroupNorm pass: row groups x out columns x 2 <= 1024
@@ -634,7 +622,7 @@ __device__ __forceinline__ void fast_epilogue_rows(const GemmParams& p, uint32_t
 }
 
 __device__ __forceinline__ void epi_bar_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(GEMM_THREADS - 64) : "memory");  // epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // epilogue warps only
 }
 
 // After every epilogue warp has staged its part of the tile (et = epilogue thread index 0 .. 255):
@@ -691,7 +679,7 @@ __device__ __forceinline__ void epilogue_tail(const GemmParams& p, uint32_t io_b
       const int nbt = (n0_out + ncv - 1) / bs - kb0 + 1;
       const int n_img = BLOCK_M / p.gn_img_rows;
       const int rg_per_img = p.gn_img_rows / R;
-      for (int idx = et; idx < nbt * n_img; idx += GEMM_THREADS - 64) {
+      for (int idx = et; idx < nbt * n_img; idx += EPI_THREADS) {
         const int k = kb0 + idx % nbt;
         const int i = idx / nbt;
         int bimg;
@@ -926,7 +914,7 @@ __device__ __forceinline__ void split_finish(const GemmParams& p, uint32_t taddr
   if (p.gn_out && owned > 0) {
     const int P = owned << 3;  // column pairs of the owned chunks
     int R = 16;
-    while ((BLOCK_M / R) * P > GEMM_THREADS - 64) R <<= 1;
+    while ((BLOCK_M / R) * P > EPI_THREADS) R <<= 1;
     const int rgs = BLOCK_M / R;
     const int pair = et % P;
     const int rg = et / P;
@@ -950,7 +938,7 @@ __device__ __forceinline__ void split_finish(const GemmParams& p, uint32_t taddr
     const int n_img = BLOCK_M / p.gn_img_rows;
     const int rg_per_img = p.gn_img_rows / R;
     // items: (owned chunk k, image i, t-th bucket touching the chunk); a chunk touches at most 9 buckets (bs >= 2)
-    for (int idx = et; idx < owned * n_img * 9; idx += GEMM_THREADS - 64) {
+    for (int idx = et; idx < owned * n_img * 9; idx += EPI_THREADS) {
       const int t = idx % 9;
       const int i = (idx / 9) % n_img;
       const int k = idx / (9 * n_img);
@@ -987,8 +975,19 @@ __device__ __forceinline__ void split_finish(const GemmParams& p, uint32_t taddr
   if (et == 0) tma_store_wait_read();
 }
 
+// Thread roles.  TMA issue is the scarce resource of a batch-1 main loop: one cp.async.bulk.tensor costs its issuing
+// thread ~145 cycles (plus ~100 for the mbarrier wait / arrive around it; tools/ingest_bench.cu), so a single producer
+// thread feeding A and W sustains at most one k-block per ~450 cycles -- less than the tensor pipe consumes with tiles
+// narrower than 224 columns, and far less than L2 delivers (> 75 B/clk per SM).  The A tiles and the W tiles therefore
+// have a producer warp each.
+//   warp 0       A producer (+ residual prefetch)
+//   warp 1       TMEM allocator + MMA issuer
+//   warps 2-9    epilogue
+//   warp 10      W producer: starts BEFORE griddepcontrol.wait when W is a constant weight matrix, so the weight stream
+//                (cold in HBM at batch 1) runs ahead of the dependency on the previous kernel
+//
 // PAIR variants are separate kernels: a kernel that contains cta_group::2 instructions can only be launched as a cluster
-// of an even number of CTAs.
+// of an even number of CTAs along grid.x.
 template <int KIND, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1006,9 +1005,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   const int b_stage_bytes = b_rows * BLOCK_K * 2;
 
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + (p.halo ? HALO_STAGES * HALO_STAGE : stages * p.a_stage_bytes);
+  uint8_t* smem_b = smem + stages * p.a_stage_bytes;
   // tail region (offsets computed by the host, see smem_layout): per-column scale / bias, GroupNorm column partials,
-  // mbarriers.  The fp32 staging tile of the split-K cluster reduction aliases the operand ring; the fp16 output staging
+  // mbarriers.  The fp32 staging tile of the cluster split-K reduction aliases the operand ring; the fp16 output staging
   // buffer aliases it too unless it must coexist with the main loop (residual prefetch) or with the split-K partials.
   float* s_scale = reinterpret_cast<float*>(smem + p.tail_off);
   float* s_bias = s_scale + TAIL_SCALE_FLOATS;
@@ -1018,34 +1017,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* tmem_full_bar = empty_bar + stages;
   uint64_t* res_full_bar = tmem_full_bar + 1;
-  uint64_t* afull_bar = res_full_bar + 1;   // halo mode: A ring (HALO_STAGES) full / empty
-  uint64_t* aempty_bar = afull_bar + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full_bar + 1);
   const uint32_t io_base = smem_u32(smem) + p.io_off;
 
   // pair kernels swap the grid axes: the two CTAs of a pair must be neighbours along grid.x (cluster dims (2, 1, S))
   const int n0 = (int)(PAIR ? blockIdx.y : blockIdx.x) * block_n;
   const int n0_out = p.epi.geglu ? (n0 >> 1) : n0;
-  const bool mcast_on = (KIND < K_GENERIC) && p.mcast > 1;
   if (threadIdx.x == 0) trace_stamp(p, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
-    tma_prefetch_desc(&p.tmB);
     if (p.staged) tma_prefetch_desc(&p.tmOut);
     if (p.res_tma) tma_prefetch_desc(&p.tmRes);
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      // with W multicast a stage is free only when the MMA warps of ALL CTAs of the cluster have consumed it
-      mbar_init(&empty_bar[s], mcast_on ? p.mcast : 1);
+      mbar_init(&full_bar[s], 2);  // one arrival (with its byte count) from each producer
+      mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
     mbar_init(res_full_bar, 1);
-    for (int s = 0; s < 4; ++s) {
-      mbar_init(&afull_bar[s], 1);
-      mbar_init(&aempty_bar[s], 1);
-    }
     fence_barrier_init();
   }
+  if (warp == W_WARP && lane == 0) tma_prefetch_desc(&p.tmB);
   if (warp == 1) {
     if (pair) tmem_alloc_pair(tmem_slot, p.tmem_cols);
     else tmem_alloc(tmem_slot, p.tmem_cols);
@@ -1053,39 +1044,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // peers multicast into this CTA's shared memory and arrive on its barriers: they must see them initialised
-  if (mcast_on) cluster_arrive();
   if (pair) {  // the peer's TMA loads complete on the leader's barriers, the leader's commits arrive on the peer's
     cluster_arrive();
     cluster_wait();
   }
   // Everything above touched only this CTA's shared / tensor memory.  Let the next kernel's CTAs be scheduled, then wait
-  // for the previous kernel in the stream before the first global-memory access (programmatic dependent launch).
+  // for the previous kernel in the stream before the first global-memory access (programmatic dependent launch) -- except
+  // the W producer of a constant weight matrix, which does not depend on the previous kernel at all.
   pdl_trigger();
-  int w_pre = 0;  // k-blocks whose W tile was requested ahead of the dependency wait (producer thread only)
-  if (p.w_prefetch && !mcast_on && !p.halo && warp == 0 && lane == 0) {
-    const int kb0 = blockIdx.z * p.kb_per_split;
-    const int nit = min(p.num_kblocks, kb0 + p.kb_per_split) - kb0;
-    w_pre = min(nit, stages);
-    for (int it = 0; it < w_pre; ++it) {
-      if (pair) {
-        // (no expect_tx here: the leader announces the bytes of BOTH CTAs when it arrives for the k-block; a complete_tx
-        // that lands first only drives the transaction count negative while that arrival is still pending)
-        tma_load_2d_pair(smem_b + it * b_stage_bytes, &p.tmB, mapa_shared(smem_u32(&full_bar[it]), crank & ~1u),
-                         (kb0 + it) * BLOCK_K, n0 + half * b_rows);
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
+  const int num_it = kb_end - kb_begin;
+  if (warp == W_WARP) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ W producer
+      if (!p.w_prefetch) pdl_wait();
+      int s = 0;
+      uint32_t ph = 1;
+      if constexpr (pair) {
+        const uint32_t fb0 = mapa_shared(smem_u32(full_bar), crank & ~1u);  // the LEADER's full barriers
+        for (int it = 0; it < num_it; ++it) {
+          mbar_wait(&empty_bar[s], ph);
+          if (half == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * b_stage_bytes);  // the W bytes of BOTH CTAs
+          tma_load_2d_pair(smem_b + s * b_stage_bytes, &p.tmB, fb0 + 8u * s, (kb_begin + it) * BLOCK_K, n0 + half * b_rows);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
       } else {
-        mbar_expect_tx(&full_bar[it], b_stage_bytes);
-        tma_load_2d(smem_b + it * b_stage_bytes, &p.tmB, &full_bar[it], (kb0 + it) * BLOCK_K, n0);
+        for (int it = 0; it < num_it; ++it) {
+          mbar_wait(&empty_bar[s], ph);
+          mbar_arrive_expect_tx(&full_bar[s], b_stage_bytes);
+          tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], (kb_begin + it) * BLOCK_K, n0);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
       }
     }
-    // ... and the rest of this CTA's W slice is requested into the L2 right away: at batch 1 every weight byte is cold
-    // in HBM, and the HBM -> L2 transfer then runs behind the predecessor's tail and the first k-blocks instead of
-    // being paced by the depth of the operand ring
-    if (p.w_prefetch > 1)
-      for (int it = w_pre; it < nit; ++it) tma_prefetch_l2_2d(&p.tmB, (kb0 + it) * BLOCK_K, n0 + half * b_rows);
+  } else {
+    pdl_wait();
   }
-  pdl_wait();
-  if (mcast_on) cluster_wait();  // (arrived above: complete long before the previous kernel has drained)
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace_stamp(p, 1);
 
@@ -1101,14 +1102,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     y0 = th * p.bh;
     b0 = tb * p.bb;
   }
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
-  const int num_it = kb_end - kb_begin;
   float ln_rstd = 1.f, ln_nmr = 0.f;  // folded LayerNorm of this thread's row (epilogue warps)
 
   if (warp == 0) {
     if (lane == 0) {
-      // ------------------------------------------------------------------ TMA producer
+      // ------------------------------------------------------------------ A producer
       if (KIND == K_SPLIT && p.res_tma) {
         // residual boxes ({16 columns, 128 rows}) of the chunks this rank will finish -> staging buffer
         const int rank = (int)blockIdx.z;  // K-split index (= cluster rank without CTA pairs, rank / 2 with)
@@ -1138,41 +1136,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
           else tma_load_4d(dst, &p.tmRes, res_full_bar, n0_out + s * w, x0, y0, b0);
         }
       }
-      if (p.halo) {
-        // ---- halo mode: one A load per group of k-blocks (the 9 taps of a channel block / one extra 1x1 block)
-        const int nk_halo = 9 * p.halo_ncb;
-        const int cp = p.halo_ncb * BLOCK_K;
-        int ia = 0;
-        for (int it = 0; it < num_it; ++it) {
-          const int kb = kb_begin + it;
-          const bool is_halo = kb < nk_halo;
-          const int grp = kb / 3, ky = kb - grp * 3;  // group = (cb, kx)
-          const int cbh = grp / 3, kx = grp - cbh * 3;
-          if (it == 0 || !is_halo || ky == 0) {
-            const int sa = ia % HALO_STAGES;
-            mbar_wait(&aempty_bar[sa], ((ia / HALO_STAGES) & 1) ^ 1);
-            if (is_halo) {
-              mbar_arrive_expect_tx(&afull_bar[sa], HALO_BYTES);
-              tma_load_4d(smem_a + sa * HALO_STAGE, &p.tmA[0], &afull_bar[sa], cbh * BLOCK_K, x0 - 1 + kx, y0 - 1, b0);
-            } else {
-              int e = kb - nk_halo, sg = 0;
-              while (e >= p.segs[sg].nblk) {
-                e -= p.segs[sg].nblk;
-                ++sg;
-              }
-              mbar_arrive_expect_tx(&afull_bar[sa], A_STAGE_BYTES);
-              tma_load_4d(smem_a + sa * HALO_STAGE, &p.tmA[p.segs[sg].map], &afull_bar[sa], e * BLOCK_K, x0, y0, b0);
-            }
-            ++ia;
-          }
-          const int s = it % stages;
-          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], b_stage_bytes);
-          const int wcol = is_halo ? ((ky * 3 + kx) * cp + cbh * BLOCK_K) : (9 * cp + (kb - nk_halo) * BLOCK_K);
-          tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], wcol, n0);
-          if (it == 0) trace_stamp(p, 2);
-        }
-      } else {
       int seg = 0, seg_start = 0;
       if (p.mode == 1) {
         while (kb_begin >= seg_start + p.segs[seg].nblk) {
@@ -1181,61 +1144,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         }
       }
       int cb = kb_begin - seg_start;
-      const uint32_t tx_bytes = p.a_stage_bytes + b_stage_bytes;
-      if (pair) {
-        // ---- CTA pair: own A tile + own half of the W tile per k-block; every load completes on the LEADER's barrier,
-        // which the leader arms with the bytes of both CTAs.  Each CTA waits for its own copy of the empty barrier
-        // (the leader's commit arrives on both).
-        const uint32_t lead = crank & ~1u;
+      KSeg sg = p.segs[seg];
+      const uint32_t a_bytes = p.a_stage_bytes;
+      int s = 0;
+      uint32_t ph = 1;
+      if constexpr (pair) {
+        // ---- CTA pair: every load completes on the LEADER's barrier, which the leader arms with the bytes of both CTAs;
+        // each CTA waits for its own copy of the empty barrier (the leader's commit arrives on both)
+        const uint32_t fb0 = mapa_shared(smem_u32(full_bar), crank & ~1u);
         for (int it = 0; it < num_it; ++it) {
-          const int s = it % stages;
-          mbar_wait(&empty_bar[s], ((it / stages) & 1) ^ 1);
-          if (half == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * tx_bytes);
-          const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), lead);
-          const int kb = kb_begin + it;
+          mbar_wait(&empty_bar[s], ph);
+          if (half == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * a_bytes);
           if (p.mode == 0) {
-            tma_load_2d_pair(smem_a + s * p.a_stage_bytes, &p.tmA[0], fb, kb * BLOCK_K, m0);
+            tma_load_2d_pair(smem_a + s * a_bytes, &p.tmA[0], fb0 + 8u * s, (kb_begin + it) * BLOCK_K, m0);
           } else {
-            const KSeg sg = p.segs[seg];
-            tma_load_4d_pair(smem_a + s * p.a_stage_bytes, &p.tmA[sg.map], fb, cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy, b0);
+            tma_load_4d_pair(smem_a + s * a_bytes, &p.tmA[sg.map], fb0 + 8u * s, cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy, b0);
             if (++cb == sg.nblk) {
               cb = 0;
-              ++seg;
+              sg = p.segs[++seg];
             }
           }
-          if (it >= w_pre) tma_load_2d_pair(smem_b + s * b_stage_bytes, &p.tmB, fb, kb * BLOCK_K, n0 + half * b_rows);
           if (it == 0) trace_stamp(p, 2);
-        }
-      } else
-      for (int it = 0; it < num_it; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], it < w_pre ? (uint32_t)p.a_stage_bytes : tx_bytes);
-        const int kb = kb_begin + it;
-        if (p.mode == 0) {
-          tma_load_2d(smem_a + s * p.a_stage_bytes, &p.tmA[0], &full_bar[s], kb * BLOCK_K, m0);
-        } else {
-          const KSeg sg = p.segs[seg];
-          tma_load_4d(smem_a + s * p.a_stage_bytes, &p.tmA[sg.map], &full_bar[s], cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy,
-                      b0);
-          if (++cb == sg.nblk) {
-            cb = 0;
-            ++seg;
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
           }
         }
-        if (mcast_on) {
-          // this CTA fetches its 1 / mcast slice of the W tile for every CTA of the cluster
-          const int slice_rows = block_n / p.mcast;
-          const int r = (int)cluster_ctarank();
-          tma_load_2d_mcast(smem_b + s * b_stage_bytes + r * slice_rows * (BLOCK_K * 2), &p.tmB, &full_bar[s],
-                            kb * BLOCK_K, n0 + r * slice_rows, static_cast<uint16_t>((1u << p.mcast) - 1u));
-        } else if (it >= w_pre) {
-          tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], kb * BLOCK_K, n0);
+      } else {
+        for (int it = 0; it < num_it; ++it) {
+          mbar_wait(&empty_bar[s], ph);
+          mbar_arrive_expect_tx(&full_bar[s], a_bytes);
+          if (p.mode == 0) {
+            tma_load_2d(smem_a + s * a_bytes, &p.tmA[0], &full_bar[s], (kb_begin + it) * BLOCK_K, m0);
+          } else {
+            tma_load_4d(smem_a + s * a_bytes, &p.tmA[sg.map], &full_bar[s], cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy, b0);
+            if (++cb == sg.nblk) {
+              cb = 0;
+              sg = p.segs[++seg];
+            }
+          }
+          if (it == 0) trace_stamp(p, 2);
+          if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+          }
         }
-        if (it == 0) trace_stamp(p, 2);
       }
-      }  // !halo
       if (KIND != K_SPLIT && p.res_tma && p.res_late) {
         // late residual prefetch: the staging buffer lies over the first operand stages; wait until the MMAs that read
         // them last have completed (same wait the producer would do before refilling them), then fetch the residual tile
@@ -1243,13 +1197,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         const int bn_out = p.epi.geglu ? (block_n >> 1) : block_n;
         const int n_out_total = p.epi.geglu ? (p.epi.N >> 1) : p.epi.N;
         const int io_bytes = bn_out * BLOCK_M * 2;
-        const int a_bytes = p.halo ? HALO_STAGES * HALO_STAGE : stages * p.a_stage_bytes;
-        int need = (io_bytes <= a_bytes && !p.halo) ? (io_bytes + p.a_stage_bytes - 1) / p.a_stage_bytes : stages;
+        const int a_ring = stages * p.a_stage_bytes;
+        int need = io_bytes <= a_ring ? (io_bytes + p.a_stage_bytes - 1) / p.a_stage_bytes : stages;
         if (need > stages) need = stages;
-        for (int s = 0; s < need; ++s) {
-          int itv = num_it - (num_it % stages) + s;  // first virtual iteration >= num_it that would reuse stage s
+        for (int sl = 0; sl < need; ++sl) {
+          int itv = num_it - (num_it % stages) + sl;  // first virtual iteration >= num_it that would reuse stage sl
           if (itv < num_it) itv += stages;
-          mbar_wait(&empty_bar[s], ((itv / stages) & 1) ^ 1);
+          mbar_wait(&empty_bar[sl], ((itv / stages) & 1) ^ 1);
         }
         int nsub = 0;
         for (int sidx = 0; sidx * w < bn_out && n0_out + sidx * w < n_out_total; ++sidx) ++nsub;
@@ -1262,79 +1216,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
-      const uint32_t idesc = umma_idesc_f16(block_n, 0, 0);
-      if (p.halo) {
-        const int nk_halo = 9 * p.halo_ncb;
-        int ia = 0;
-        for (int it = 0; it < num_it; ++it) {
-          const int kb = kb_begin + it;
-          const bool is_halo = kb < nk_halo;
-          const int ky = kb % 3;
-          const int sa = ia % HALO_STAGES;
-          if (it == 0 || !is_halo || ky == 0) mbar_wait(&afull_bar[sa], (ia / HALO_STAGES) & 1);
-          const int s = it % stages;
-          mbar_wait(&full_bar[s], (it / stages) & 1);
-          tc_fence_after();
-          if (it == 0) trace_stamp(p, 3);
-          // vertical tap ky = the window that starts ky image rows (ky whole swizzle atoms) into the strip
-          const uint64_t a_desc =
-              umma_desc_sw128(smem_u32(smem_a + sa * HALO_STAGE) + (is_halo ? ky * (HALO_W * 128) : 0), 1024, 0);
-          const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * b_stage_bytes), 1024, 0);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
-          if (it == num_it - 1 || !is_halo || ky == 2) {
-            umma_commit(&aempty_bar[sa]);
-            ++ia;
-          }
-        }
-      } else if (pair) {
-        // ---- leader of a CTA pair: M = 256 MMAs over both CTAs' shared memory (same offsets in the peer), commits
-        // multicast to both CTAs' barriers; the peer's MMA thread has nothing to do
-        if (half == 0) {
-          const uint32_t idesc2 = umma_idesc_f16_m256(block_n);
-          const uint16_t pmask = static_cast<uint16_t>(3u << crank);
-          for (int it = 0; it < num_it; ++it) {
-            const int s = it % stages;
-            mbar_wait(&full_bar[s], (it / stages) & 1);
-            tc_fence_after();
-            if (it == 0) trace_stamp(p, 3);
-            const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * p.a_stage_bytes), 1024, 0);
-            const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * b_stage_bytes), 1024, 0);
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k)
-              umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc2, (it > 0 || k > 0) ? 1u : 0u);
-            umma_commit_pair(&empty_bar[s], pmask);
-          }
-          umma_commit_pair(tmem_full_bar, pmask);
-          trace_stamp(p, 4);
-        }
-      } else
+    if (lane == 0 && half == 0) {
+      // ------------------------------------------------------------------ MMA issuer (the leader's, for a CTA pair: M = 256
+      // MMAs over both CTAs' shared memory -- same offsets in the peer --, commits multicast to both CTAs' barriers)
+      const uint32_t idesc = pair ? umma_idesc_f16_m256(block_n) : umma_idesc_f16(block_n, 0, 0);
+      const uint16_t pmask = static_cast<uint16_t>(3u << crank);
+      const uint32_t a0 = smem_u32(smem_a), bb0 = smem_u32(smem_b);
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < num_it; ++it) {
-        const int s = it % stages;
-        const uint32_t ph = (it / stages) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         if (it == 0) trace_stamp(p, 3);
-        const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * p.a_stage_bytes), 1024, 0);
-        const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * b_stage_bytes), 1024, 0);
+        const uint64_t a_desc = umma_desc_sw128(a0 + s * p.a_stage_bytes, 1024, 0);
+        const uint64_t b_desc = umma_desc_sw128(bb0 + s * b_stage_bytes, 1024, 0);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 16; ++k) {
           // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if constexpr (pair) umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          else umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        if (mcast_on) umma_commit_mcast(&empty_bar[s], static_cast<uint16_t>((1u << p.mcast) - 1u));
+        if constexpr (pair) umma_commit_pair(&empty_bar[s], pmask);
         else umma_commit(&empty_bar[s]);
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
       }
-      if (!pair) {
-        umma_commit(tmem_full_bar);
-        trace_stamp(p, 4);
-      }
+      if constexpr (pair) umma_commit_pair(tmem_full_bar, pmask);
+      else umma_commit(tmem_full_bar);
+      trace_stamp(p, 4);
     }
-  } else {
+  } else if (warp < W_WARP) {
     // -------------------------------------------------------------------- epilogue warps (2 .. 2 + 4 * EPI_COLSPLIT)
     const int q = warp & 3;                // TMEM lane quadrant this warp may access
     const int cw = (warp - 2) >> 2;        // which share of the column chunks
@@ -1355,7 +1268,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     }
     const int b = (p.epi.rowvec && valid) ? (m / p.epi.rows_per_batch) : 0;
     if constexpr (KIND == K_SPLIT) {
-      for (int i = et; i < block_n; i += GEMM_THREADS - 64) {
+      for (int i = et; i < block_n; i += EPI_THREADS) {
         const int n = n0 + i;
         const bool in = n < p.epi.N;
         const bool ln = p.epi.ln_stats != nullptr;
@@ -1373,7 +1286,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       if (threadIdx.x == 64) trace_stamp(p, 6);
     } else if constexpr (KIND != K_GENERIC) {
       // ---- compact flavour: staged fp16 output, compile-time activation, no split-K
-      for (int i = et; i < block_n; i += GEMM_THREADS - 64) {
+      for (int i = et; i < block_n; i += EPI_THREADS) {
         const int n = n0 + i;
         const bool in = n < p.epi.N;
         const bool ln = p.epi.ln_stats != nullptr;  // the "scale" slot then carries the folded LayerNorm's column sums
@@ -1395,7 +1308,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       if (threadIdx.x == 64) trace_stamp(p, 6);
     } else {
     // stage the tile's per-column scale / bias once (identity when absent) — read back as broadcast float4s
-    for (int i = et; i < block_n; i += GEMM_THREADS - 64) {
+    for (int i = et; i < block_n; i += EPI_THREADS) {
       const int n = n0 + i;
       s_scale[i] = (p.epi.scale && n < p.epi.N) ? __ldg(p.epi.scale + n) : 1.0f;
       s_bias[i] = (p.epi.bias && n < p.epi.N) ? __ldg(p.epi.bias + n) : 0.0f;
@@ -1404,7 +1317,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       // split-K + GroupNorm statistics: every CTA of the cluster finishes only some chunks of the tile; the others must
       // read as zeros in its (dedicated) staging buffer
       const int io_bytes = block_n * BLOCK_M * 2;
-      for (int i = et * 16; i < io_bytes; i += (GEMM_THREADS - 64) * 16) sts128(io_base + i, make_uint4(0, 0, 0, 0));
+      for (int i = et * 16; i < io_bytes; i += (EPI_THREADS) * 16) sts128(io_base + i, make_uint4(0, 0, 0, 0));
     }
     epi_bar_sync();
     // folded LayerNorm: (rstd, -mean * rstd) of this row from the producer's partials, fetched while the MMAs run
@@ -1434,7 +1347,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();  // every CTA's partial is in the workspace (barrier.cluster: release / acquire over global memory)
     if (threadIdx.x == 64) trace_stamp(p, 8);
-    if (warp >= 2) {
+    if (warp >= 2 && warp < W_WARP) {
       const int q = warp & 3;
       const int cw = (warp - 2) >> 2;
       const int row = q * 32 + lane;
@@ -1469,7 +1382,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     // ---- split-K reduction across the cluster (gridDim.z == cluster size): no workspace, no second kernel
     cg::cluster_group cluster = cg::this_cluster();
     cluster.sync();
-    if (warp >= 2) {
+    if (warp >= 2 && warp < W_WARP) {
       const int q = warp & 3;
       const int cw = (warp - 2) >> 2;
       const int row = q * 32 + lane;
@@ -1505,11 +1418,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
     if (pair) tmem_dealloc_pair(tmem_base, p.tmem_cols);
     else tmem_dealloc(tmem_base, p.tmem_cols);
   }
-  if (mcast_on) {
-    // no CTA may exit while a peer's tcgen05.commit can still arrive on its barriers
-    cluster_arrive();
-    cluster_wait();
-  }
   if (threadIdx.x == 0) trace_stamp(p, 7);
 }
 
@@ -1517,7 +1425,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
 
 struct TileChoice {
   int block_n, splits, stages, tmem_cols;
-  int mcast = 1;  // W-tile multicast cluster size along the M tiles (compact non-split flavours)
   int pair = 0;   // 1: CTA pairs along the M tiles (cta_group::2, M = 256 MMAs; compact and compact split-K flavours)
 };
 
@@ -1535,8 +1442,7 @@ struct OutGeom {
   bool gn = false;        // GroupNorm statistics requested
   bool geglu = false;
   bool split_fast = false;  // a split-K launch of this problem can use the compact K_SPLIT flavour
-  bool mcast_ok = false;    // a non-split launch can use a compact flavour (and therefore W-tile multicast)
-  bool halo = false;        // halo-mode convolution: the A ring holds HALO_STAGES halo tiles
+  bool compact_ok = false;  // a non-split launch can use a compact flavour
   bool res_late = false;    // (set per candidate) alias the residual staging buffer with the operand ring
   int pair = 0;             // (set per candidate) CTA pairs: every CTA stages block_n / 2 rows of W per k-block
   int a_stage = A_STAGE_BYTES;  // bytes of one A stage (8 KiB when the A box carries 64 rows)
@@ -1552,7 +1458,7 @@ struct SmemLayout {
 // rows per row group of the GroupNorm column pass for a bn_out-wide output tile, 0 if the tile cannot be handled
 static int gn_rows_for(int bn_out, int img_rows) {
   for (int R = 16; R <= BLOCK_M; R <<= 1)
-    if ((BLOCK_M / R) * (bn_out / 2) <= GEMM_THREADS - 64 && R <= img_rows) return R;
+    if ((BLOCK_M / R) * (bn_out / 2) <= EPI_THREADS && R <= img_rows) return R;
   return 0;
 }
 
@@ -1560,8 +1466,7 @@ static SmemLayout smem_layout(int block_n, int stages, int splits, const OutGeom
   SmemLayout L;
   const int bn_out = og.geglu ? block_n / 2 : block_n;
   const int b_rows = og.pair ? block_n / 2 : block_n;
-  int ring = og.halo ? HALO_STAGES * HALO_STAGE + stages * b_rows * BLOCK_K * 2
-                     : stages * (og.a_stage + b_rows * BLOCK_K * 2);
+  int ring = stages * (og.a_stage + b_rows * BLOCK_K * 2);
   const int stage_tile = block_n * BLOCK_M * 4;  // fp32 staging tile of the cluster split-K reduction (aliases the ring)
   const bool split_fast = splits > 1 && og.split_fast;
   if (splits > 1 && !split_fast && stage_tile > ring) ring = stage_tile;
@@ -1570,7 +1475,7 @@ static SmemLayout smem_layout(int block_n, int stages, int splits, const OutGeom
   L.io_needed = L.staged || og.gn;
   // residual prefetch: a dedicated staging buffer lets it run during the whole main loop, but costs operand stages; the
   // caller asks for the aliased ("late") variant when the ring would otherwise get shallower than the K loop can use
-  L.res_late = L.res_tma && og.res_late && splits == 1 && !og.halo;
+  L.res_late = L.res_tma && og.res_late && splits == 1;
   const bool dedicated = (L.res_tma && !L.res_late) || (og.gn && splits > 1 && !split_fast);
   const int io_bytes = L.io_needed ? bn_out * BLOCK_M * 2 : 0;
   L.io_off = dedicated ? ring : 0;
@@ -1589,7 +1494,7 @@ constexpr int SMEM_OCC1 = 200 * 1024;  // one CTA per SM: deep operand ring
 constexpr int SMEM_OCC2 = 112 * 1024;  // two CTAs per SM: one CTA's epilogue / set-up overlaps the other's main loop
 
 static int stages_for(int block_n, int splits, int kb_per, int budget, const OutGeom& og) {
-  int st = (og.halo || og.a_stage < A_STAGE_BYTES) ? 12 : 8;
+  int st = og.a_stage < A_STAGE_BYTES ? 12 : 8;
   while (st > 2 && smem_bytes_for(block_n, st, splits, og) > budget) --st;
   if (st > kb_per) st = kb_per < 2 ? 2 : kb_per;
   return st;
@@ -1606,7 +1511,7 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
   const int sms = h->num_sms;
   std::vector<Candidate> all;
   // CTA pairs need an even number of m-tiles, full 128-row A boxes and a compact kernel flavour
-  const bool pair_possible = h->pair_mode != 0 && (tiles_m % 2) == 0 && !og_in.halo && og_in.a_stage == A_STAGE_BYTES;
+  const bool pair_possible = h->pair_mode != 0 && (tiles_m % 2) == 0 && og_in.a_stage == A_STAGE_BYTES;
   for (int pr = 0; pr <= (pair_possible ? 1 : 0); ++pr) {
   if (h->pair_mode == 2 && pair_possible && pr == 0) continue;  // forced (tests, A/B)
   OutGeom og = og_in;
@@ -1626,7 +1531,7 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
     }
     for (int sp = 1; sp <= max_splits; ++sp) {
       if (h->force_splits && sp != h->force_splits && !(h->force_splits > max_splits && sp == max_splits)) continue;
-      if (pr && !(sp == 1 ? og.mcast_ok : og.split_fast)) continue;  // pairs exist in the compact flavours only
+      if (pr && !(sp == 1 ? og.compact_ok : og.split_fast)) continue;  // pairs exist in the compact flavours only
       const int kb_per = gn::ceil_div(num_kblocks, sp);
       if ((sp - 1) * kb_per >= num_kblocks) continue;  // an empty split
       if (rs_capacity > 0 && tiles_n * sp * EPI_COLSPLIT > rs_capacity) continue;  // row-statistics partials must fit
@@ -1665,18 +1570,6 @@ static int candidate_list(const gn_handle* h, int tiles_m, int N, int num_kblock
         for (const Candidate& o : all)
           if (o.tc.block_n == bn && o.tc.splits == sp && o.tc.stages == st && o.tc.pair == pr) dup = true;
         if (!dup) all.push_back(c);
-        // W-tile multicast variants: the m-tiles of one n-tile form clusters of 2 / 4 CTAs (compact flavours only)
-        if (!dup && !pr && sp == 1 && og.mcast_ok && h->mcast_max > 1) {
-          for (int mc = 2; mc <= h->mcast_max && mc <= 4; mc <<= 1) {
-            if (h->force_mcast && mc != h->force_mcast) continue;
-            if ((tiles_m % mc) != 0 || (bn % (8 * mc)) != 0) continue;
-            Candidate m = c;
-            m.tc.mcast = mc;
-            m.cost = c.cost * (mc == 2 ? 0.97 : 0.95);
-            if (h->force_mcast) all.back() = m;  // forced: replaces the plain variant
-            else all.push_back(m);
-          }
-        }
       }
     }
   }
@@ -1770,7 +1663,7 @@ static int fill_out_geom(gn_handle* h, GemmParams& p, OutGeom& og, const gn_epil
   og.split_fast = h->fast_epilogue && h->workspace && h->workspace_bytes >= (64 << 20) && og.stage_ok && (!e.residual || og.res_ok) && e.act_post == GN_ACT_NONE && !e.geglu &&
                   (e.act_pre == GN_ACT_NONE || e.act_pre == GN_ACT_SILU || e.act_pre == GN_ACT_RELU) &&
                   (!e.rowvec || ((e.N % 4) == 0 && (reinterpret_cast<uintptr_t>(e.rowvec) & 15) == 0));
-  og.mcast_ok = h->fast_epilogue && og.stage_ok && (!e.residual || og.res_ok) &&
+  og.compact_ok = h->fast_epilogue && og.stage_ok && (!e.residual || og.res_ok) &&
                 (e.act_post == GN_ACT_NONE || (e.act_post == GN_ACT_RELU && !e.geglu)) &&
                 (!e.rowvec || ((e.N % 4) == 0 && (reinterpret_cast<uintptr_t>(e.rowvec) & 15) == 0)) &&
                 e.act_pre >= GN_ACT_NONE && e.act_pre <= GN_ACT_QUICKGELU && !(e.geglu && e.act_pre != GN_ACT_NONE);
@@ -1830,17 +1723,13 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ktot * 2};
-    // with multicast every CTA fetches one slice, in a CTA pair each CTA fetches one half of the tile
-    uint32_t box[2] = {BLOCK_K, (uint32_t)(tc.pair ? tc.block_n / 2 : tc.block_n / tc.mcast)};
+    uint32_t box[2] = {BLOCK_K, (uint32_t)(tc.pair ? tc.block_n / 2 : tc.block_n)};  // a CTA of a pair fetches one half
     int rc = make_tmap_f16(h, &p.tmB, W, 2, dims, strides, box);
     if (rc) return rc;
   }
-  p.mcast = tc.mcast;
   p.pair = tc.pair;
   p.a_stage_bytes = og.a_stage;
-  // 2 (GENIMA_B200_DBG bit 32, off by default): also L2-prefetch the whole W slice of weight-heavy problems -- measured
-  // 3 % SLOWER on the full step (the prefetch traffic competes with the kernels that are still running)
-  p.w_prefetch = (h->w_prefetch && !p.w_dynamic) ? (((double)N * (double)ktot * 2.0 >= 2.0e6 && (p.dbg & 32)) ? 2 : 1) : 0;
+  p.w_prefetch = (h->w_prefetch && !p.w_dynamic) ? 1 : 0;
   // epilogue staging: layout, sub-tile width and the output / residual tensor maps
   const SmemLayout L = smem_layout(tc.block_n, tc.stages, tc.splits, og);
   const int bn_out = og.geglu ? tc.block_n / 2 : tc.block_n;
@@ -1903,17 +1792,15 @@ static int launch_config(gn_handle* h, GemmParams& p, const TileChoice& tc, int 
   dim3 grid(gn::ceil_div(N, tc.block_n), tiles_m, tc.splits);
   if (tc.pair) grid = dim3(tiles_m, gn::ceil_div(N, tc.block_n), tc.splits);  // pairs are neighbours along grid.x
   // the K-splits of one output tile form a thread-block cluster (grid.z == cluster size)
-  GN_CHECK_ARG(h, tc.mcast == 1 || (kind < K_GENERIC && tc.splits == 1 && (tiles_m % tc.mcast) == 0),
-               "W multicast needs a compact non-split flavour and m-tiles divisible by the cluster size");
-  GN_CHECK_ARG(h, !tc.pair || (kind != K_GENERIC && tc.mcast == 1 && (tiles_m % 2) == 0 && 2 * tc.splits <= 8 &&
-                               !og.halo && og.a_stage == A_STAGE_BYTES),
+  GN_CHECK_ARG(h, !tc.pair || (kind != K_GENERIC && (tiles_m % 2) == 0 && 2 * tc.splits <= 8 &&
+                               og.a_stage == A_STAGE_BYTES),
                "CTA pairs need a compact flavour, an even number of m-tiles and at most 4 K-splits");
   GN_CHECK_CUDA(h, launch_ex(h, kKernels[kind + (tc.pair ? K_SPLIT + 1 : 0)], grid, dim3(GEMM_THREADS, 1, 1), smem, stream,
-                              tc.splits | (tc.pair ? (2 << 16) : (tc.mcast << 8)), p));
+                              tc.splits | (tc.pair ? (2 << 16) : 0), p));
   h->last_cfg[0] = tc.block_n;
   h->last_cfg[1] = tc.splits;
   h->last_cfg[2] = tc.stages;
-  h->last_cfg[3] = (int)(grid.x * grid.y * grid.z) * (tc.mcast > 1 ? -tc.mcast : 1);  // negative: x multicast size
+  h->last_cfg[3] = (int)(grid.x * grid.y * grid.z);
   h->last_pair = tc.pair;
   return GN_OK;
 }
@@ -1935,15 +1822,13 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
   p.rs_capacity = rs_capacity;
   snprintf(keybuf, sizeof(keybuf), "%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d", p.mode, tiles_m, N, p.num_kblocks,
            geglu ? 1 : 0, p.epi.out32 ? 1 : 0, p.epi.residual ? 1 : 0, p.epi.ln_stats ? 1 : 0, rs_capacity,
-           og.stage_ok ? 1 : 0, og.res_ok ? 1 : 0, (og.gn ? og.img_rows : 0) + (og.halo ? 1000 : 0) + (og.a_stage != A_STAGE_BYTES ? 2000 : 0) +
+           og.stage_ok ? 1 : 0, og.res_ok ? 1 : 0, (og.gn ? og.img_rows : 0) + (og.a_stage != A_STAGE_BYTES ? 2000 : 0) +
                (og.strided ? 4000 : 0));
   const std::string key(keybuf);
   if (!forced) {
     auto it = h->tune_cache.find(key);
     if (it != h->tune_cache.end()) {
-      TileChoice tc{it->second[0], it->second[1], it->second[2], it->second[3] & 0xffff, (it->second[3] >> 16) & 0xff,
-                    (it->second[3] >> 24) & 1};
-      if (tc.mcast < 1) tc.mcast = 1;
+      TileChoice tc{it->second[0], it->second[1], it->second[2], it->second[3] & 0xffff, (it->second[3] >> 24) & 1};
       int rc = launch_config(h, p, tc, tiles_m, W, ktot, og, stream);
       if (rc == GN_OK) h->launches++;
       return rc;
@@ -1990,7 +1875,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
         }
       }
       const TileChoice& tc = cand[best].tc;
-      h->tune_cache[key] = {tc.block_n, tc.splits, tc.stages, tc.tmem_cols | (tc.mcast << 16) | (tc.pair << 24)};
+      h->tune_cache[key] = {tc.block_n, tc.splits, tc.stages, tc.tmem_cols | (tc.pair << 24)};
       // the timed launches accumulated into the caller's GroupNorm statistics as well: start them again from zero
       if (p.gn_out)
         GN_CHECK_CUDA(h, cudaMemsetAsync(p.gn_out, 0, (size_t)p.gn_stat_images * p.gn_nb * 16, stream));
@@ -2098,18 +1983,10 @@ static int conv_impl(gn_handle* h, const void* x, int B, int H, int W, int C, co
   int bh = pow2_ceil(Ho);
   if (bh > 128 / bw) bh = 128 / bw;
   int bb = 128 / (bw * bh);
-  // halo mode: 3x3 / stride 1 / pad 1 over whole 64-channel blocks and image widths that tile by 8
-  const bool halo = h->halo_conv && !view && KH == 3 && KW == 3 && stride == 1 && pad == 1 && (C % BLOCK_K) == 0 &&
-                    (Wo % HALO_W) == 0 && Ho >= 8;
-  if (halo) {
-    bw = HALO_W;
-    bh = HALO_H;
-    bb = 1;
-  }
   // images per A box: when the whole batch fills exactly 64 of the tile's 128 rows (one 8 x 8 image), the A box carries
   // just those rows (8 KiB stages, see GemmParams::a_stage_bytes)
   int bb_box = bb;
-  if (!halo && h->half_a_box && B < bb && bw * bh * B == 64) bb_box = B;
+  if (h->half_a_box && B < bb && bw * bh * B == 64) bb_box = B;
   p.bw = bw;
   p.bh = bh;
   p.bb = bb;
@@ -2122,18 +1999,7 @@ static int conv_impl(gn_handle* h, const void* x, int B, int H, int W, int C, co
   const int cblk = Cp / BLOCK_K;
   int nseg = 0;
   int nmaps = 0;
-  if (halo) {
-    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    uint32_t box[4] = {BLOCK_K, HALO_W, HALO_H + 2, 1};
-    rc = make_tmap_f16(h, &p.tmA[0], x, 4, dims, strides, box);
-    if (rc) return rc;
-    nmaps = 1;
-    p.halo = 1;
-    p.halo_ncb = cblk;
-    p.halo_bo = h->halo_base_offset ? 1 : 0;
-    nseg = 0;  // the segment table lists the extra 1x1 sources only
-  } else if (stride == 1) {
+  if (stride == 1) {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
     uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb_box};
@@ -2197,7 +2063,6 @@ static int conv_impl(gn_handle* h, const void* x, int B, int H, int W, int C, co
   OutGeom og;
   rc = fill_out_geom(h, p, og, epi, out);
   if (rc) return rc;
-  og.halo = halo;
   og.a_stage = bb_box != bb ? A_STAGE_BYTES / 2 : A_STAGE_BYTES;
   og.rank = 4;
   og.dims[1] = (uint64_t)Wo;

@@ -95,16 +95,6 @@ class Ops:
             self.handle.check(self.lib.gn_set_pdl(self.h, int(os.environ["GENIMA_B200_PDL"])), "gn_set_pdl")
         if os.environ.get("GENIMA_B200_STAGED", "1") == "0":   # A/B switch for the TMA-stored GEMM epilogue
             self.handle.check(self.lib.gn_set_staged_epilogue(self.h, 0), "gn_set_staged_epilogue")
-        halo = os.environ.get("GENIMA_B200_HALO")   # "enable[,base_offset_field]": halo-mode convolutions (A/B)
-        if halo:
-            parts = [int(v) for v in halo.split(",")]
-            self.handle.check(self.lib.gn_set_conv_halo(self.h, parts[0], parts[1] if len(parts) > 1 else 1),
-                              "gn_set_conv_halo")
-        mc = os.environ.get("GENIMA_B200_MCAST")   # "max[,force]": W-tile multicast cluster sizes (A/B)
-        if mc:
-            parts = [int(v) for v in mc.split(",")]
-            self.handle.check(self.lib.gn_set_gemm_multicast(self.h, parts[0], parts[1] if len(parts) > 1 else 0),
-                              "gn_set_gemm_multicast")
         if os.environ.get("GENIMA_B200_PAIR", "1") != "1":   # A/B: 0 = no CTA pairs, 2 = pairs wherever possible
             self.handle.check(self.lib.gn_set_gemm_pair(self.h, int(os.environ["GENIMA_B200_PAIR"])), "gn_set_gemm_pair")
         if os.environ.get("GENIMA_B200_ATTN_SPLIT", "1") != "1":   # A/B: 0 = no KV split, 2 = split whenever possible

@@ -124,10 +124,6 @@ int gn_set_autotune(gn_handle* h, int enable);
  * in the same order: sharding the episodes of controller/eval_genima.py:115-142 over GPUs does not change any result. */
 int64_t gn_tune_cache_export(const gn_handle* h, char* buf, int64_t cap);
 int gn_tune_cache_import(gn_handle* h, const char* buf, int64_t n, int replace);
-/* W-tile TMA multicast: the CTAs computing the m-tiles of one n-tile form clusters of up to max_cluster (1, 2 or 4) CTAs
- * that fetch one slice of the weight tile each and multicast it to the others (less L2 traffic on shapes where many
- * m-tiles re-read the same weights).  force_cluster = 2 / 4 uses that size wherever it applies (tests, A/B); 0 = autotuned. */
-int gn_set_gemm_multicast(gn_handle* h, int max_cluster, int force_cluster);
 /* CTA pairs (tcgen05 cta_group::2): two CTAs on neighbouring SMs compute two consecutive 128-row m-tiles with ONE M = 256
  * MMA per k-step; each fetches its own A tile and half of the W tile, so the weight bytes an SM ingests per output tile
  * halve (batch-1 GEMMs are bound by L2 -> SM operand traffic, not by the tensor pipe).  mode 0 = never, 1 = a candidate
@@ -135,11 +131,6 @@ int gn_set_gemm_multicast(gn_handle* h, int max_cluster, int force_cluster);
  * gn_linear / gn_conv2d launch used pairs. */
 int gn_set_gemm_pair(gn_handle* h, int mode);
 int gn_last_gemm_pair(const gn_handle* h);
-/* Halo mode of gn_conv2d (3x3, stride 1, pad 1, C % 64 == 0, output width % 8 == 0): every CTA fetches, per
- * 64-channel block, three 8 x (16 + 2) pixel column strips (one per horizontal tap offset) and feeds the three vertical
- * taps of each to the tensor core as atom-aligned shared-memory windows of the strip, instead of fetching a 128-pixel
- * tile for each of the nine taps (3x less activation traffic into the SM).  enable = 0 restores per-tap loads (A/B). */
-int gn_set_conv_halo(gn_handle* h, int enable, int base_offset_field);
 /* Force the operand-ring sizing of the next GEMM-class calls for 1 or 2 resident CTAs per SM (0 = heuristic). */
 int gn_set_gemm_occupancy(gn_handle* h, int ctas_per_sm);
 /* gn_attention KV split across a 2-CTA cluster (partials merged through distributed shared memory): 0 = never,

@@ -224,26 +224,3 @@ def test_linear_strided_output_and_residual(ops):
     ops.linear(a.cuda(), w.cuda(), residual=big_res[:, N:], out=big_out[:, N:2 * N])
     report_close("linear strided", big_out[:, N:2 * N], ops_ref.linear_ref(a, w, residual=big_res[:, N:].cpu()))
     assert float(big_out[:, :N].abs().max()) == 0.0 and float(big_out[:, 2 * N:].abs().max()) == 0.0
-
-
-@pytest.mark.parametrize("mc", [2, 4])
-@pytest.mark.parametrize("M,N,K,residual", [(4096, 320, 320, True), (1024, 1920, 640, False), (512, 256, 1024, True)])
-def test_linear_w_multicast(ops, mc, M, N, K, residual):
-    """W-tile TMA multicast across clusters of m-tiles (gn_set_gemm_multicast) must not change the result."""
-    a = _rand((M, K), 40)
-    w = _rand((N, K), 41, K ** -0.5)
-    bias = torch.randn(N) * 0.1
-    kw = dict(bias=bias.cuda())
-    if residual:
-        kw["residual"] = _rand((M, N), 42).cuda()
-    ops.handle.check(ops.lib.gn_set_gemm_multicast(ops.h, 4, mc), "gn_set_gemm_multicast")
-    ops.set_gemm_tuning(64, 1)
-    try:
-        out = ops.linear(a.cuda(), w.cuda(), **kw)
-        cfg = ops.last_gemm_config()
-    finally:
-        ops.handle.check(ops.lib.gn_set_gemm_multicast(ops.h, 4, 0), "gn_set_gemm_multicast")
-        ops.set_gemm_tuning(0, 0)
-    assert cfg[3] < 0 and -cfg[3] % mc == 0, f"multicast not applied: cfg={cfg}"
-    report_close(f"linear multicast x{mc} {M}x{N}x{K}", out,
-                 ops_ref.linear_ref(a, w, bias=bias, residual=kw.get("residual")))

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,memory.total,clocks.sm,clocks.max.sm --format=csv > 
 for f in $FILES; do
   name=$(basename $f .py)
   echo "=== $f"
-  timeout 600 python -m pytest $f -m gpu -q --tb=short -s -p no:cacheprovider > gpurun_out/$name.log 2>&1
+  timeout ${GPU_TEST_TIMEOUT:-300} python -m pytest $f -m gpu -q --tb=short -s -p no:cacheprovider > gpurun_out/$name.log 2>&1
   echo "exit $?" >> gpurun_out/$name.log
   tail -5 gpurun_out/$name.log
 done
