@@ -621,6 +621,138 @@ __device__ __forceinline__ void fast_epilogue_rows(const GemmParams& p, uint32_t
   }
 }
 
+// Lean variant of the compact epilogue for the plain activations (KIND 0 .. 4).  The per-column constants are folded at
+// staging time (s_add = bias [+ the tile's time-embedding row]) and the arithmetic form is a compile-time MODE:
+//   0: v = acc + add        1: v = acc * mul + add        2 (folded LayerNorm): v = acc * rstd + (nmr * colsum + add)
+// The tensor-memory load of the next chunk is issued as soon as the accumulators of this one have been consumed, so its
+// latency hides behind the activation / residual / packing of the current chunk (two warps per scheduler cannot hide it).
+template <int KIND, int MODE>
+__device__ __forceinline__ void lean_epilogue_rows(const GemmParams& p, uint32_t taddr, int n0, int m, int b, bool valid,
+                                                   int cw, const float* s_mul, const float* s_add, const float* s_cs,
+                                                   int row, float ln_rstd, float ln_nmr, uint32_t io_base,
+                                                   bool rowvec_per_row) {
+  const EpiParams& e = p.epi;
+  const int nchunks = min(p.block_n, e.N - n0 + 15) >> 4;  // chunks that hold at least one real column
+  const int lw = p.io_lw;
+  const bool unit = e.alpha == 1.0f && e.beta == 1.0f;
+  // staging address of the chunk's first 16-byte unit (see io_offset): the row term and the swizzle XOR (address bits
+  // [7, 10) come from the row only) are loop invariants; the second unit is its neighbour, bit 4 flipped
+  const uint32_t row_base = io_base + (static_cast<uint32_t>(row) << (1 + lw));
+  const uint32_t swz = ((static_cast<uint32_t>(row) << (1 + lw) >> 7) & ((1u << (lw - 3)) - 1u)) << 4;
+  const int wmask = (1 << lw) - 1;
+  float rs[2] = {0.f, 0.f};
+  uint32_t r[16];
+  if (cw < nchunks) tmem_ld_x16(taddr + (cw << 4), r);
+#pragma unroll 1
+  for (int ch = cw; ch < nchunks; ch += EPI_COLSPLIT) {
+    const int c = ch << 4;
+    float v[16];
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 ad = *reinterpret_cast<const float4*>(s_add + c + j);
+      if constexpr (MODE == 0) {
+        v[j] = __uint_as_float(r[j]) + ad.x;
+        v[j + 1] = __uint_as_float(r[j + 1]) + ad.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + ad.z;
+        v[j + 3] = __uint_as_float(r[j + 3]) + ad.w;
+      } else if constexpr (MODE == 1) {
+        const float4 mu = *reinterpret_cast<const float4*>(s_mul + c + j);
+        v[j] = fmaf(__uint_as_float(r[j]), mu.x, ad.x);
+        v[j + 1] = fmaf(__uint_as_float(r[j + 1]), mu.y, ad.y);
+        v[j + 2] = fmaf(__uint_as_float(r[j + 2]), mu.z, ad.z);
+        v[j + 3] = fmaf(__uint_as_float(r[j + 3]), mu.w, ad.w);
+      } else {
+        const float4 cs = *reinterpret_cast<const float4*>(s_cs + c + j);
+        v[j] = fmaf(__uint_as_float(r[j]), ln_rstd, fmaf(ln_nmr, cs.x, ad.x));
+        v[j + 1] = fmaf(__uint_as_float(r[j + 1]), ln_rstd, fmaf(ln_nmr, cs.y, ad.y));
+        v[j + 2] = fmaf(__uint_as_float(r[j + 2]), ln_rstd, fmaf(ln_nmr, cs.z, ad.z));
+        v[j + 3] = fmaf(__uint_as_float(r[j + 3]), ln_rstd, fmaf(ln_nmr, cs.w, ad.w));
+      }
+    }
+    if (ch + EPI_COLSPLIT < nchunks) tmem_ld_x16(taddr + ((ch + EPI_COLSPLIT) << 4), r);  // r[] is dead: refill it
+    if (rowvec_per_row) {  // a tile that spans several images: the time-embedding row differs per output row
+      const float4* rv = reinterpret_cast<const float4*>(e.rowvec + (int64_t)b * e.N + n0 + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldg(rv + j);
+        v[4 * j] += t.x;
+        v[4 * j + 1] += t.y;
+        v[4 * j + 2] += t.z;
+        v[4 * j + 3] += t.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = act_ct<KIND>(v[j]);
+    const uint32_t a0 = row_base + (static_cast<uint32_t>(c >> lw) << (8 + lw)) + ((static_cast<uint32_t>(c & wmask) << 1) ^ swz);
+    const uint32_t a1 = a0 ^ 16u;
+    if (p.res_tma) {
+      const uint4 q0 = lds128(a0), q1 = lds128(a1);
+      const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+      if (unit) {
+        const uint32_t w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // fp32 accumulator + fp16 residual in one instruction each
+          v[2 * t] = add_f32_f16_lo(w0[t], v[2 * t]);
+          v[2 * t + 1] = add_f32_f16_hi(w0[t], v[2 * t + 1]);
+          v[8 + 2 * t] = add_f32_f16_lo(w1[t], v[8 + 2 * t]);
+          v[8 + 2 * t + 1] = add_f32_f16_hi(w1[t], v[8 + 2 * t + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 f = __half22float2(h0[t]);
+          const float2 g = __half22float2(h1[t]);
+          v[2 * t] = fmaf(e.alpha, v[2 * t], e.beta * f.x);
+          v[2 * t + 1] = fmaf(e.alpha, v[2 * t + 1], e.beta * f.y);
+          v[8 + 2 * t] = fmaf(e.alpha, v[8 + 2 * t], e.beta * g.x);
+          v[8 + 2 * t + 1] = fmaf(e.alpha, v[8 + 2 * t + 1], e.beta * g.y);
+        }
+      }
+    } else if (e.alpha != 1.0f) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= e.alpha;
+    }
+    if (e.act_post == GN_ACT_RELU) {  // ReLU after the residual add (torchvision BasicBlock, AutoencoderTinyBlock.fuse)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    const int nout = n0 + c;
+    if (!valid || nout + 16 > e.N) {  // zeros outside the tensor (TMA clips them; the GroupNorm pass sums them)
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (!valid || nout + j >= e.N) v[j] = 0.f;
+    }
+    uint4 q0, q1;
+    q0.x = pack_half2(v[0], v[1]);
+    q0.y = pack_half2(v[2], v[3]);
+    q0.z = pack_half2(v[4], v[5]);
+    q0.w = pack_half2(v[6], v[7]);
+    q1.x = pack_half2(v[8], v[9]);
+    q1.y = pack_half2(v[10], v[11]);
+    q1.z = pack_half2(v[12], v[13]);
+    q1.w = pack_half2(v[14], v[15]);
+    if (e.rs_out) {
+      const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(h0[t]);
+        const float2 g = __half22float2(h1[t]);
+        rs[0] += (f.x + f.y) + (g.x + g.y);
+        rs[1] = fmaf(f.x, f.x, fmaf(f.y, f.y, fmaf(g.x, g.x, fmaf(g.y, g.y, rs[1]))));
+      }
+    }
+    sts128(a0, q0);
+    sts128(a1, q1);
+  }
+  if (e.rs_out && valid) {
+    const int part = (int)(p.pair ? blockIdx.y : blockIdx.x) * EPI_COLSPLIT + cw;  // one partial per (n-tile, column share)
+    e.rs_out[(int64_t)m * e.rs_parts + part] = make_float2(rs[0], rs[1]);
+  }
+}
+
 __device__ __forceinline__ void epi_bar_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // epilogue warps only
 }
@@ -640,16 +772,20 @@ __device__ __forceinline__ void epilogue_tail(const GemmParams& p, uint32_t io_b
   fence_proxy_async_smem();  // staged tile (generic-proxy writes) -> visible to the TMA unit (async proxy)
   epi_bar_sync();
   if (et == 0) trace_stamp(p, 9);
-  if (p.staged && et == 0) {
+  // the sub-tiles are stored by lane 0 of the epilogue warps in turn: a TMA instruction costs its issuing thread ~150
+  // cycles, eight threads issue in parallel
+  const bool storer = p.staged && (et & 31) == 0;
+  if (storer) {
     const int w = 1 << p.io_lw;
-    for (int s = 0; s * w < bn_out && n0_out + s * w < n_out_total; ++s) {
+    for (int s = et >> 5; s * w < bn_out && n0_out + s * w < n_out_total; s += EPI_THREADS / 32) {
       const uint32_t src = io_base + (static_cast<uint32_t>(s) << (8 + p.io_lw));
       if (p.mode == 0) tma_store_2d(&p.tmOut, src, n0_out + s * w, m0);
       else tma_store_4d(&p.tmOut, src, n0_out + s * w, x0, y0, b0);
     }
     tma_store_commit();
-    trace_stamp(p, 10);
+    if (et == 0) trace_stamp(p, 10);
   }
+  __syncwarp();  // the barriers below are warp-aligned: the storing lane must have rejoined its warp
   if (p.gn_out) {
     const int ncv = min(bn_out, n_out_total - n0_out);  // valid out columns of this tile (even)
     const int P = bn_out >> 1;                           // column pairs the tile can hold
@@ -711,7 +847,7 @@ __device__ __forceinline__ void epilogue_tail(const GemmParams& p, uint32_t io_b
     }
   }
   if (et == 0) trace_stamp(p, 11);
-  if (p.staged && et == 0) tma_store_wait_read();  // the TMA unit has read the tile: shared memory may be released
+  if (storer) tma_store_wait_read();  // the TMA unit has read the tile: shared memory may be released
   if (et == 0) trace_stamp(p, 12);
 }
 
@@ -901,16 +1037,18 @@ __device__ __forceinline__ void split_finish(const GemmParams& p, uint32_t taddr
   for (int ch = rank; ch < nchunks && n0 + (ch << 4) < e.N; ch += S) ++owned;
   fence_proxy_async_smem();
   epi_bar_sync();
-  if (et == 0) {
-    for (int k = 0; k < owned; ++k) {
+  const bool storer = (et & 31) == 0;
+  if (storer) {
+    for (int k = et >> 5; k < owned; k += EPI_THREADS / 32) {
       const int ch = rank + S * k;
       const uint32_t src = io_base + (static_cast<uint32_t>(ch) << 12);
       if (p.mode == 0) tma_store_2d(&p.tmOut, src, n0 + (ch << 4), m0);
       else tma_store_4d(&p.tmOut, src, n0 + (ch << 4), x0, y0, b0);
     }
     tma_store_commit();
-    trace_stamp(p, 10);
+    if (et == 0) trace_stamp(p, 10);
   }
+  __syncwarp();  // the barriers below are warp-aligned: the storing lane must have rejoined its warp
   if (p.gn_out && owned > 0) {
     const int P = owned << 3;  // column pairs of the owned chunks
     int R = 16;
@@ -972,7 +1110,7 @@ __device__ __forceinline__ void split_finish(const GemmParams& p, uint32_t taddr
       if (f2 != 0) atomicAdd(dst + 1, static_cast<unsigned long long>(f2));
     }
   }
-  if (et == 0) tma_store_wait_read();
+  if (storer) tma_store_wait_read();
 }
 
 // Thread roles.  TMA issue is the scarce resource of a batch-1 main loop: one cp.async.bulk.tensor costs its issuing
@@ -1056,31 +1194,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
   const int num_it = kb_end - kb_begin;
   if (warp == W_WARP) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ W producer
-      if (!p.w_prefetch) pdl_wait();
-      int s = 0;
-      uint32_t ph = 1;
-      if constexpr (pair) {
-        const uint32_t fb0 = mapa_shared(smem_u32(full_bar), crank & ~1u);  // the LEADER's full barriers
-        for (int it = 0; it < num_it; ++it) {
-          mbar_wait(&empty_bar[s], ph);
+    // ------------------------------------------------------------------ W producer (whole warp, one elected lane issues)
+    if (!p.w_prefetch) pdl_wait();
+    int s = 0;
+    uint32_t ph = 1;
+    if constexpr (pair) {
+      const uint32_t fb0 = mapa_shared(smem_u32(full_bar), crank & ~1u);  // the LEADER's full barriers
+      for (int it = 0; it < num_it; ++it) {
+        mbar_wait(&empty_bar[s], ph);
+        if (elect_one()) {
           if (half == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * b_stage_bytes);  // the W bytes of BOTH CTAs
           tma_load_2d_pair(smem_b + s * b_stage_bytes, &p.tmB, fb0 + 8u * s, (kb_begin + it) * BLOCK_K, n0 + half * b_rows);
-          if (++s == stages) {
-            s = 0;
-            ph ^= 1;
-          }
         }
-      } else {
-        for (int it = 0; it < num_it; ++it) {
-          mbar_wait(&empty_bar[s], ph);
+        __syncwarp();
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    } else {
+      for (int it = 0; it < num_it; ++it) {
+        mbar_wait(&empty_bar[s], ph);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[s], b_stage_bytes);
           tma_load_2d(smem_b + s * b_stage_bytes, &p.tmB, &full_bar[s], (kb_begin + it) * BLOCK_K, n0);
-          if (++s == stages) {
-            s = 0;
-            ph ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++s == stages) {
+          s = 0;
+          ph ^= 1;
         }
       }
     }
@@ -1105,37 +1247,44 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   float ln_rstd = 1.f, ln_nmr = 0.f;  // folded LayerNorm of this thread's row (epilogue warps)
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ A producer
-      if (KIND == K_SPLIT && p.res_tma) {
-        // residual boxes ({16 columns, 128 rows}) of the chunks this rank will finish -> staging buffer
-        const int rank = (int)blockIdx.z;  // K-split index (= cluster rank without CTA pairs, rank / 2 with)
-        const int nchunks = block_n >> 4;
-        int owned = 0;
-        for (int ch = rank; ch < nchunks && n0 + (ch << 4) < p.epi.N; ch += p.splits) ++owned;
-        if (owned > 0) {
-          mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(owned) << 12);
-          for (int k = 0; k < owned; ++k) {
-            const int ch = rank + p.splits * k;
-            uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(ch) << 12);
-            if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0 + (ch << 4), m0);
-            else tma_load_4d(dst, &p.tmRes, res_full_bar, n0 + (ch << 4), x0, y0, b0);
+    {
+      // ------------------------------------------------------------------ A producer (whole warp, one elected lane issues)
+      // The residual tile is only needed by the epilogue: it is requested after the first ring-full of A tiles, so that
+      // the first MMA is not delayed by the issue cost of those loads.
+      auto issue_residual = [&]() {
+        if (KIND == K_SPLIT && p.res_tma) {
+          // residual boxes ({16 columns, 128 rows}) of the chunks this rank will finish -> staging buffer
+          const int rank = (int)blockIdx.z;  // K-split index (= cluster rank without CTA pairs, rank / 2 with)
+          const int nchunks = block_n >> 4;
+          int owned = 0;
+          for (int ch = rank; ch < nchunks && n0 + (ch << 4) < p.epi.N; ch += p.splits) ++owned;
+          if (owned > 0) {
+            mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(owned) << 12);
+            for (int k = 0; k < owned; ++k) {
+              const int ch = rank + p.splits * k;
+              uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(ch) << 12);
+              if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0 + (ch << 4), m0);
+              else tma_load_4d(dst, &p.tmRes, res_full_bar, n0 + (ch << 4), x0, y0, b0);
+            }
+          }
+        } else if (p.res_tma && !p.res_late) {
+          // residual tile -> staging buffer, in flight while the main loop runs
+          const int w = 1 << p.io_lw;
+          const int bn_out = p.epi.geglu ? (block_n >> 1) : block_n;
+          const int n_out_total = p.epi.geglu ? (p.epi.N >> 1) : p.epi.N;
+          int nsub = 0;
+          for (int sb = 0; sb * w < bn_out && n0_out + sb * w < n_out_total; ++sb) ++nsub;
+          mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(nsub) << (8 + p.io_lw));
+          for (int sb = 0; sb < nsub; ++sb) {
+            uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(sb) << (8 + p.io_lw));
+            if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0_out + sb * w, m0);
+            else tma_load_4d(dst, &p.tmRes, res_full_bar, n0_out + sb * w, x0, y0, b0);
           }
         }
-      } else if (p.res_tma && !p.res_late) {
-        // residual tile -> staging buffer, in flight while the main loop runs
-        const int w = 1 << p.io_lw;
-        const int bn_out = p.epi.geglu ? (block_n >> 1) : block_n;
-        const int n_out_total = p.epi.geglu ? (p.epi.N >> 1) : p.epi.N;
-        int nsub = 0;
-        for (int s = 0; s * w < bn_out && n0_out + s * w < n_out_total; ++s) ++nsub;
-        mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(nsub) << (8 + p.io_lw));
-        for (int s = 0; s < nsub; ++s) {
-          uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(s) << (8 + p.io_lw));
-          if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0_out + s * w, m0);
-          else tma_load_4d(dst, &p.tmRes, res_full_bar, n0_out + s * w, x0, y0, b0);
-        }
-      }
+      };
+      const int res_after = min(stages, num_it) - 1;  // iteration after which the residual is requested
+      if (res_after < 0 && elect_one()) issue_residual();
+      __syncwarp();
       int seg = 0, seg_start = 0;
       if (p.mode == 1) {
         while (kb_begin >= seg_start + p.segs[seg].nblk) {
@@ -1154,17 +1303,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         const uint32_t fb0 = mapa_shared(smem_u32(full_bar), crank & ~1u);
         for (int it = 0; it < num_it; ++it) {
           mbar_wait(&empty_bar[s], ph);
-          if (half == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * a_bytes);
-          if (p.mode == 0) {
-            tma_load_2d_pair(smem_a + s * a_bytes, &p.tmA[0], fb0 + 8u * s, (kb_begin + it) * BLOCK_K, m0);
-          } else {
-            tma_load_4d_pair(smem_a + s * a_bytes, &p.tmA[sg.map], fb0 + 8u * s, cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy, b0);
-            if (++cb == sg.nblk) {
-              cb = 0;
-              sg = p.segs[++seg];
-            }
+          if (elect_one()) {
+            if (half == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * a_bytes);
+            if (p.mode == 0)
+              tma_load_2d_pair(smem_a + s * a_bytes, &p.tmA[0], fb0 + 8u * s, (kb_begin + it) * BLOCK_K, m0);
+            else
+              tma_load_4d_pair(smem_a + s * a_bytes, &p.tmA[sg.map], fb0 + 8u * s, cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy, b0);
+            if (it == 0) trace_stamp(p, 2);
+            if (it == res_after) issue_residual();
           }
-          if (it == 0) trace_stamp(p, 2);
+          __syncwarp();
+          if (p.mode != 0 && ++cb == sg.nblk) {
+            cb = 0;
+            sg = p.segs[++seg];
+          }
           if (++s == stages) {
             s = 0;
             ph ^= 1;
@@ -1173,17 +1325,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       } else {
         for (int it = 0; it < num_it; ++it) {
           mbar_wait(&empty_bar[s], ph);
-          mbar_arrive_expect_tx(&full_bar[s], a_bytes);
-          if (p.mode == 0) {
-            tma_load_2d(smem_a + s * a_bytes, &p.tmA[0], &full_bar[s], (kb_begin + it) * BLOCK_K, m0);
-          } else {
-            tma_load_4d(smem_a + s * a_bytes, &p.tmA[sg.map], &full_bar[s], cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy, b0);
-            if (++cb == sg.nblk) {
-              cb = 0;
-              sg = p.segs[++seg];
-            }
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[s], a_bytes);
+            if (p.mode == 0)
+              tma_load_2d(smem_a + s * a_bytes, &p.tmA[0], &full_bar[s], (kb_begin + it) * BLOCK_K, m0);
+            else
+              tma_load_4d(smem_a + s * a_bytes, &p.tmA[sg.map], &full_bar[s], cb * BLOCK_K, x0 + sg.dx, y0 + sg.dy, b0);
+            if (it == 0) trace_stamp(p, 2);
+            if (it == res_after) issue_residual();
           }
-          if (it == 0) trace_stamp(p, 2);
+          __syncwarp();
+          if (p.mode != 0 && ++cb == sg.nblk) {
+            cb = 0;
+            sg = p.segs[++seg];
+          }
           if (++s == stages) {
             s = 0;
             ph ^= 1;
@@ -1207,16 +1362,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         }
         int nsub = 0;
         for (int sidx = 0; sidx * w < bn_out && n0_out + sidx * w < n_out_total; ++sidx) ++nsub;
-        mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(nsub) << (8 + p.io_lw));
-        for (int sidx = 0; sidx < nsub; ++sidx) {
-          uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(sidx) << (8 + p.io_lw));
-          if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0_out + sidx * w, m0);
-          else tma_load_4d(dst, &p.tmRes, res_full_bar, n0_out + sidx * w, x0, y0, b0);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(res_full_bar, static_cast<uint32_t>(nsub) << (8 + p.io_lw));
+          for (int sidx = 0; sidx < nsub; ++sidx) {
+            uint8_t* dst = smem + p.io_off + (static_cast<uint32_t>(sidx) << (8 + p.io_lw));
+            if (p.mode == 0) tma_load_2d(dst, &p.tmRes, res_full_bar, n0_out + sidx * w, m0);
+            else tma_load_4d(dst, &p.tmRes, res_full_bar, n0_out + sidx * w, x0, y0, b0);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && half == 0) {
+    if (half == 0) {
       // ------------------------------------------------------------------ MMA issuer (the leader's, for a CTA pair: M = 256
       // MMAs over both CTAs' shared memory -- same offsets in the peer --, commits multicast to both CTAs' barriers)
       const uint32_t idesc = pair ? umma_idesc_f16_m256(block_n) : umma_idesc_f16(block_n, 0, 0);
@@ -1227,25 +1385,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       for (int it = 0; it < num_it; ++it) {
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (it == 0) trace_stamp(p, 3);
-        const uint64_t a_desc = umma_desc_sw128(a0 + s * p.a_stage_bytes, 1024, 0);
-        const uint64_t b_desc = umma_desc_sw128(bb0 + s * b_stage_bytes, 1024, 0);
+        if (elect_one()) {
+          if (it == 0) trace_stamp(p, 3);
+          const uint64_t a_desc = umma_desc_sw128(a0 + s * p.a_stage_bytes, 1024, 0);
+          const uint64_t b_desc = umma_desc_sw128(bb0 + s * b_stage_bytes, 1024, 0);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          if constexpr (pair) umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          else umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            if constexpr (pair) umma_f16_ss_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          if constexpr (pair) umma_commit_pair(&empty_bar[s], pmask);
+          else umma_commit(&empty_bar[s]);
         }
-        if constexpr (pair) umma_commit_pair(&empty_bar[s], pmask);
-        else umma_commit(&empty_bar[s]);
+        __syncwarp();
         if (++s == stages) {
           s = 0;
           ph ^= 1;
         }
       }
-      if constexpr (pair) umma_commit_pair(tmem_full_bar, pmask);
-      else umma_commit(tmem_full_bar);
-      trace_stamp(p, 4);
+      if (elect_one()) {
+        if constexpr (pair) umma_commit_pair(tmem_full_bar, pmask);
+        else umma_commit(tmem_full_bar);
+        trace_stamp(p, 4);
+      }
+      __syncwarp();
     }
   } else if (warp < W_WARP) {
     // -------------------------------------------------------------------- epilogue warps (2 .. 2 + 4 * EPI_COLSPLIT)
@@ -1286,12 +1450,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       if (threadIdx.x == 64) trace_stamp(p, 6);
     } else if constexpr (KIND != K_GENERIC) {
       // ---- compact flavour: staged fp16 output, compile-time activation, no split-K
+      // the image every row of this tile belongs to, or -1 when the tile spans several images: in the first case the
+      // time-embedding row (rowvec) is one more per-column constant and folds into the staged bias
+      int tile_b = -1;
+      if (KIND != K_GEGLU && p.epi.rowvec) {
+        if (p.mode == 0) {
+          const int last = min(m0 + BLOCK_M, p.epi.M) - 1;
+          if (m0 / p.epi.rows_per_batch == last / p.epi.rows_per_batch) tile_b = m0 / p.epi.rows_per_batch;
+        } else if (p.bb == 1) {
+          tile_b = b0;
+        }
+      }
       for (int i = et; i < block_n; i += EPI_THREADS) {
         const int n = n0 + i;
         const bool in = n < p.epi.N;
         const bool ln = p.epi.ln_stats != nullptr;  // the "scale" slot then carries the folded LayerNorm's column sums
         s_scale[i] = (p.epi.scale && !ln && in) ? __ldg(p.epi.scale + n) : 1.0f;
-        s_bias[i] = (p.epi.bias && in) ? __ldg(p.epi.bias + n) : 0.0f;
+        float add = (p.epi.bias && in) ? __ldg(p.epi.bias + n) : 0.0f;
+        if (tile_b >= 0 && in) add += __ldg(p.epi.rowvec + (int64_t)tile_b * p.epi.N + n);
+        s_bias[i] = add;
         s_cs[i] = (ln && in) ? __ldg(p.epi.scale + n) : 0.0f;
       }
       epi_bar_sync();
@@ -1301,8 +1478,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
       tc_fence_after();
       if (threadIdx.x == 64) trace_stamp(p, 5);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      fast_epilogue_rows<KIND>(p, taddr, n0, n0_out, m, b, valid, cw, s_scale, s_bias, s_cs, row, ln_rstd, ln_nmr,
-                               io_base);
+      if constexpr (KIND == K_GEGLU) {
+        fast_epilogue_rows<KIND>(p, taddr, n0, n0_out, m, b, valid, cw, s_scale, s_bias, s_cs, row, ln_rstd, ln_nmr,
+                                 io_base);
+      } else {
+        const bool rv_row = p.epi.rowvec != nullptr && tile_b < 0;
+        if (p.epi.ln_stats)
+          lean_epilogue_rows<KIND, 2>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, s_cs, row, ln_rstd, ln_nmr, io_base,
+                                      rv_row);
+        else if (p.epi.scale)
+          lean_epilogue_rows<KIND, 1>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, s_cs, row, ln_rstd, ln_nmr, io_base,
+                                      rv_row);
+        else
+          lean_epilogue_rows<KIND, 0>(p, taddr, n0, m, b, valid, cw, s_scale, s_bias, s_cs, row, ln_rstd, ln_nmr, io_base,
+                                      rv_row);
+      }
       epilogue_tail(p, io_base, s_col, et, n0_out, m0, x0, y0, b0);
       tc_fence_before();
       if (threadIdx.x == 64) trace_stamp(p, 6);
@@ -1851,7 +2041,13 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
       const bool cold = (double)N * (double)ktot * 2.0 >= 4.0e6 && h->workspace && h->workspace_bytes >= (140 << 20);
       int best = 0;
       float best_ms = 1e30f;
+      static const bool tune_verbose = getenv("GENIMA_B200_TUNE_VERBOSE") != nullptr;
       for (int i = 0; i < nc; ++i) {
+        if (tune_verbose) {
+          fprintf(stderr, "[tune %s] candidate %d/%d: block_n %d splits %d stages %d pair %d\n", key.c_str(), i, nc,
+                  cand[i].tc.block_n, cand[i].tc.splits, cand[i].tc.stages, cand[i].tc.pair);
+          fflush(stderr);
+        }
         int rc = launch_config(h, p, cand[i].tc, tiles_m, W, ktot, og, stream);  // warm-up (tensor maps, smem carve-out)
         if (rc) return rc;
         float total = 1e30f;  // the fastest of `reps` timing rounds: robust against a neighbour kernel / clock hiccup

@@ -52,6 +52,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a converged warp.  Role loops run with the WHOLE warp on warp-uniform values and issue their TMA / MMA /
+// mbarrier-arrive instructions under this predicate: the operands then live in uniform registers.  A loop run by
+// `if (lane == 0)` instead makes every operand thread-varying, and each tensor-core / TMA instruction is preceded by a
+// register-to-uniform-register waterfall (~10 dependent instructions per issue).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- programmatic dependent launch
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
 // stream is still running; pdl_wait() blocks until that predecessor has completed and its writes are visible, so
@@ -368,6 +382,19 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return fmaf(hx, erf_fast(x * 0.70710678118654752f), hx);
 }
 __device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+
+// Mixed-precision add / fma (PTX ISA 8.6, sm_100): one instruction instead of a conversion plus an fp32 operation.
+// lo / hi select the half of a packed fp16 pair.
+__device__ __forceinline__ float add_f32_f16_lo(uint32_t h2, float c) {
+  float d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, lo, %2;\n\t}" : "=f"(d) : "r"(h2), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float add_f32_f16_hi(uint32_t h2, float c) {
+  float d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, hi, %2;\n\t}" : "=f"(d) : "r"(h2), "f"(c));
+  return d;
+}
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);

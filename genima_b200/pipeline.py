@@ -88,7 +88,7 @@ class B200ControlNetPipeline:
         # The ControlNet encoder and the U-Net encoder are independent until the zero-conv adds: they run concurrently
         # on two streams (both are chains of small latency-bound kernels at batch 1).  The ControlNet gets its own
         # gn_handle so that the per-handle GroupNorm scratch / grid-barrier words are never shared between streams.
-        self.concurrent_controlnet = bool(concurrent_controlnet)
+        self.concurrent_controlnet = bool(concurrent_controlnet) and os.environ.get("GENIMA_B200_CONCURRENT", "1") != "0"   # A/B
         self.ops_side = Ops(ops.device.index, autotune=ops.autotune) if self.concurrent_controlnet else ops
         # third handle / stream: the 13 zero-convs start as soon as both encoders have produced their skip tensor,
         # instead of running one after the other once the two encoders have joined

@@ -32,7 +32,8 @@ for (M, N, K, res) in [(4096, 320, 320, True), (4096, 320, 1280, True), (4096, 9
         e1.record()
         torch.cuda.synchronize()
         ops.lib.gn_set_gemm_trace(ops.h, None)
-        t = tr.cpu().tolist()[:len(names)]
+        full = tr.cpu().tolist()
+        t = full[:len(names)]
         rel = [(x - t[0]) / 1e3 if x else float("nan") for x in t]
         tr.zero_()
         print(f"M{M} N{N} K{K} cfg{ops.last_gemm_config()} {'cold' if cold else 'warm'} events {e0.elapsed_time(e1) * 1e3:.1f} us | "
