@@ -149,47 +149,62 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
   const uint32_t tmem_o = tmem_base + 256;  // 64 fp32 columns; S buffers: tmem_base + 0 and + 128
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
+    // ---------------------------------------------------------------- TMA producer (whole warp, one elected lane issues:
+    // operands stay in uniform registers)
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
       tma_load_2d(sQ, &p.tmQ, q_full, head * AT_D, batch * p.Tq + q0);
-      for (int i = 0; i < nblk; ++i) {
-        const int st = i & 1;
-        const uint32_t ph = ((i >> 1) & 1) ^ 1;
-        mbar_wait(&k_empty[st], ph);
+    }
+    __syncwarp();
+    for (int i = 0; i < nblk; ++i) {
+      const int st = i & 1;
+      const uint32_t ph = ((i >> 1) & 1) ^ 1;
+      mbar_wait(&k_empty[st], ph);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
         tma_load_2d(sK + st * AT_TILE_BYTES, &p.tmK, &k_full[st], head * AT_D, batch * p.Tk + (kb0 + i) * AT_BKV);
-        mbar_wait(&v_empty[st], ph);
+      }
+      __syncwarp();
+      mbar_wait(&v_empty[st], ph);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
         tma_load_2d(sV + st * AT_TILE_BYTES, &p.tmV, &v_full[st], head * AT_D, batch * p.Tk + (kb0 + i) * AT_BKV);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      const uint32_t idesc_qk = umma_idesc_f16(AT_BKV, 0, 0);  // N = 128 keys, both operands K-major
-      const uint32_t idesc_pv = umma_idesc_f16(AT_D, 0, 1);    // N = 64 dims, B (= V) MN-major
-      const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ), 1024, 0);
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
-        if (j >= 2) mbar_wait(&s_free[st], ((j >> 1) - 1) & 1);  // softmax of block j-2 has read this S buffer
-        tc_fence_after();
+    // ---------------------------------------------------------------- MMA issuer (whole warp waits, one elected lane issues)
+    const uint32_t idesc_qk = umma_idesc_f16(AT_BKV, 0, 0);  // N = 128 keys, both operands K-major
+    const uint32_t idesc_pv = umma_idesc_f16(AT_D, 0, 1);    // N = 64 dims, B (= V) MN-major
+    const uint64_t q_desc = umma_desc_sw128(smem_u32(sQ), 1024, 0);
+    // The scores run TWO blocks ahead of the softmax (three S buffers): the softmax warps fetch block i + 1 into a second
+    // register set while they exponentiate block i, so S(i + 1) must be complete when block i starts and S(i + 2) is
+    // computed behind it.
+    auto issue_qk = [&](int j) {
+      const int st = j & 1;
+      const int sb = st;
+      mbar_wait(&k_full[st], (j >> 1) & 1);
+      if (j >= 2) mbar_wait(&s_free[st], ((j >> 1) - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
         const uint64_t k_desc = umma_desc_sw128(smem_u32(sK + st * AT_TILE_BYTES), 1024, 0);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_f16_ss(tmem_base + st * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0);
-        umma_commit(&s_full[st]);
+          umma_f16_ss(tmem_base + sb * 128, q_desc + 2 * k, k_desc + 2 * k, idesc_qk, k > 0);
+        umma_commit(&s_full[sb]);
         umma_commit(&k_empty[st]);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int i = 0; i < nblk; ++i) {
-        if (i + 1 < nblk) issue_qk(i + 1);  // next scores while the softmax warps work on block i
-        const int st = i & 1;
-        mbar_wait(&p_full[st], (i >> 1) & 1);
-        mbar_wait(&v_full[st], (i >> 1) & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int i = 0; i < nblk; ++i) {
+      if (i + 1 < nblk) issue_qk(i + 1);
+      const int st = i & 1;
+      mbar_wait(&p_full[st], (i >> 1) & 1);
+      mbar_wait(&v_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
 #pragma unroll
         for (int j = 0; j < AT_BKV / 16; ++j) {
           // A: P buffer i & 1, [128 rows][16 k] slice j: 64-column sub-tile j/4, 32-byte step j%4 inside the swizzle row
@@ -202,6 +217,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
         umma_commit(&pv_done[st]);
         umma_commit(&v_empty[st]);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ softmax / output warps (2..9)
