@@ -83,6 +83,8 @@ SIGNATURES = {
                             C.POINTER(GnEpilogue), _vp]),
     "gn_conv2d_up2x": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i64, C.POINTER(GnEpilogue), _vp]),
     "gn_attention": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _vp]),
+    "gn_attention_qproj": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _f, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i,
+                                _f, _vp]),
     "gn_attention_small": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "gn_group_norm": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
     "gn_group_norm_apply": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp]),

@@ -55,7 +55,21 @@ struct AttnParams {
   // and rank 1 hands its partial (O, m, l) to rank 0 through distributed shared memory.  Fixes the wave quantisation of
   // the level-0 self-attention (160 CTAs of 32 KV blocks on 148 SMs = 2 waves -> 320 CTAs of 16 blocks = 1.5 waves).
   int kv_splits;
+  // ---- fused query projection (gn_attention_qproj): Q = LayerNorm-folded(X W_q^T) is computed by the kernel itself.
+  // X [B * Tq][C] is the un-normalised hidden state, W_q [heads * 64][C] carries the LayerNorm gamma; the CTA of head h
+  // multiplies its 128 rows of X with rows [64 h, 64 h + 64) of W_q over C / 64 k-blocks (accumulator = the O columns of
+  // tensor memory, free until the first P V), applies rstd * acc - mean * rstd * colsum + bias and writes the fp16 tile
+  // into the Q buffer in the swizzled layout the QK^T MMA reads.  One launch and one round trip of Q through L2 less
+  // per cross-attention.
+  CUtensorMap tmX, tmWq;
+  int qp_kblocks;          // C / 64 (0: Q comes from memory through tmQ)
+  const float2* ln_stats;  // [B * Tq][ln_parts] (sum, sumsq) partials of each row of X (NULL: no LayerNorm, rstd = 1)
+  int ln_parts, ln_dim;
+  float ln_eps;
+  const float* qp_colsum;  // [heads * 64] sum_k gamma[k] W_q[n, k]  (ignored without ln_stats)
+  const float* qp_bias;    // [heads * 64] bias[n] + sum_k beta[k] W_q[n, k]  (may be NULL)
 };
+constexpr int AT_QP_STAGE = AT_TILE_BYTES + 64 * 64 * 2;  // one projection k-block: X tile 16 KiB + W_q tile 8 KiB
 
 // 2^x for x <= ~8 without the SFU: n = round(x) through the 1.5 * 2^23 magic constant (its low mantissa bits then hold n),
 // 2^(x - n) by a degree-4 polynomial on [-0.5, 0.5], n added to the exponent field with an integer shift / add.
@@ -106,7 +120,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
   uint64_t* s_free = bars + 11;   // [2]
   uint64_t* p_full = bars + 13;   // [2]
   uint64_t* pv_done = bars + 15;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* xp_full = bars + 17;   // [2]  query projection operand ring (lives in the P buffers)
+  uint64_t* xp_empty = bars + 19;  // [2]
+  uint64_t* qp_done = bars + 21;   // projection accumulator complete
+  uint64_t* q_ready = bars + 22;   // fp16 Q tile written to shared memory by the softmax warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -127,6 +145,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
+    mbar_init(qp_done, 1);
+    mbar_init(q_ready, 32 * AT_SM_WARPS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&xp_full[s], 1);
+      mbar_init(&xp_empty[s], 1);
+    }
     for (int s = 0; s < AT_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
@@ -151,11 +175,25 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (whole warp, one elected lane issues:
     // operands stay in uniform registers)
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
-      tma_load_2d(sQ, &p.tmQ, q_full, head * AT_D, batch * p.Tq + q0);
+    if (p.qp_kblocks > 0) {
+      for (int kb = 0; kb < p.qp_kblocks; ++kb) {
+        const int st = kb & 1;
+        mbar_wait(&xp_empty[st], ((kb >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          uint8_t* dst = sP + st * AT_QP_STAGE;
+          mbar_arrive_expect_tx(&xp_full[st], AT_QP_STAGE);
+          tma_load_2d(dst, &p.tmX, &xp_full[st], kb * 64, batch * p.Tq + q0);
+          tma_load_2d(dst + AT_TILE_BYTES, &p.tmWq, &xp_full[st], kb * 64, head * AT_D);
+        }
+        __syncwarp();
+      }
+    } else {
+      if (elect_one()) {
+        mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
+        tma_load_2d(sQ, &p.tmQ, q_full, head * AT_D, batch * p.Tq + q0);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     for (int i = 0; i < nblk; ++i) {
       const int st = i & 1;
       const uint32_t ph = ((i >> 1) & 1) ^ 1;
@@ -196,7 +234,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
+    if (p.qp_kblocks > 0) {
+      const uint32_t idesc_qp = umma_idesc_f16(AT_D, 0, 0);  // N = 64 (this head's columns of W_q), both operands K-major
+      for (int kb = 0; kb < p.qp_kblocks; ++kb) {
+        const int st = kb & 1;
+        mbar_wait(&xp_full[st], (kb >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t x_desc = umma_desc_sw128(smem_u32(sP + st * AT_QP_STAGE), 1024, 0);
+          const uint64_t w_desc = umma_desc_sw128(smem_u32(sP + st * AT_QP_STAGE + AT_TILE_BYTES), 1024, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_o, x_desc + 2 * k, w_desc + 2 * k, idesc_qp, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&xp_empty[st]);
+          if (kb == p.qp_kblocks - 1) umma_commit(qp_done);
+        }
+        __syncwarp();
+      }
+      mbar_wait(q_ready, 0);  // the softmax warps have turned the accumulator into the fp16 Q tile
+      tc_fence_after();
+    } else {
+      mbar_wait(q_full, 0);
+    }
     issue_qk(0);
     for (int i = 0; i < nblk; ++i) {
       if (i + 1 < nblk) issue_qk(i + 1);
@@ -230,6 +288,53 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_kernel(const __grid_con
     const uint32_t p_row0 = smem_u32(sP) + half * AT_TILE_BYTES + row * 128;
     const uint32_t swz = static_cast<uint32_t>(row & 7);
     const float c = p.scale_log2;
+
+    if (p.qp_kblocks > 0) {
+      // ---- query projection epilogue: folded LayerNorm + bias, fp16, into the Q buffer (SWIZZLE_128B, K-major)
+      float rstd = 1.f, nmr = 0.f;
+      const int grow = batch * p.Tq + q0 + row;
+      if (p.ln_stats && q0 + row < p.Tq) {  // row statistics from the producer's partials, summed in index order
+        const float2* sp = p.ln_stats + (int64_t)grow * p.ln_parts;
+        float s1 = 0.f, s2 = 0.f;
+        for (int t = 0; t < p.ln_parts; ++t) {
+          const float2 v2 = __ldg(sp + t);
+          s1 += v2.x;
+          s2 += v2.y;
+        }
+        const float inv = 1.0f / (float)p.ln_dim;
+        const float mean = s1 * inv;
+        const float var = fmaxf(s2 * inv - mean * mean, 0.f);
+        rstd = rsqrtf(var + p.ln_eps);
+        nmr = -mean * rstd;
+      }
+      const int n0c = head * AT_D + half * 32;  // first of this thread's 32 output columns
+      mbar_wait(qp_done, 0);
+      tc_fence_after();
+      uint32_t a[32];
+      tmem_ld_x32(tmem_o + lane_sel + half * 32, a);
+      tmem_ld_wait();
+      tc_fence_before();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int j = 8 * u + 2 * t;
+          const float cs0 = p.ln_stats ? __ldg(p.qp_colsum + n0c + j) : 0.f;
+          const float cs1 = p.ln_stats ? __ldg(p.qp_colsum + n0c + j + 1) : 0.f;
+          const float b0 = p.qp_bias ? __ldg(p.qp_bias + n0c + j) : 0.f;
+          const float b1 = p.qp_bias ? __ldg(p.qp_bias + n0c + j + 1) : 0.f;
+          const float v0 = fmaf(__uint_as_float(a[j]), rstd, fmaf(nmr, cs0, b0));
+          const float v1 = fmaf(__uint_as_float(a[j + 1]), rstd, fmaf(nmr, cs1, b1));
+          pk[t] = pack_half2(v0, v1);
+        }
+        const uint32_t addr = smem_u32(sQ) + row * 128 + ((static_cast<uint32_t>(half * 4 + u) ^ swz) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(q_ready);
+    }
 
     for (int i = 0; i < nblk; ++i) {
       const int st = i & 1;
@@ -477,6 +582,50 @@ __global__ void __launch_bounds__(128) attn_small_kernel(const __half* __restric
 
 using namespace gn;
 
+static int attention_launch(gn_handle* h, AttnParams& p, int B, int heads, int Tq, int Tk, float scale, void* out,
+                            int64_t ldo, cudaStream_t stream) {
+  p.out = static_cast<__half*>(out);
+  p.ldo = ldo;
+  p.Tq = Tq;
+  p.Tk = Tk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  // KV split across a 2-CTA cluster when it shortens the critical path: cost in KV blocks = waves x blocks per CTA
+  // (+ half a block for the hand-over), and only for a clear (15 %) win: clusters schedule less freely than single CTAs
+  // (measured: 160 CTAs x 32 blocks 78 -> 68 us, 40 CTAs x 2 blocks 18 -> 14.5 us, 640 CTAs x 32 blocks 194 -> 202 us)
+  const int nblk = ceil_div(Tk, AT_BKV);
+  const int ctas = ceil_div(Tq, AT_BQ) * heads * B;
+  const int sms = h->num_sms > 0 ? h->num_sms : 148;
+  p.kv_splits = 1;
+  if (nblk >= 2 && h->attn_kv_split != 0 && p.qp_kblocks == 0) {
+    const double c1 = (double)ceil_div(ctas, sms) * nblk;
+    const double c2 = (double)ceil_div(2 * ctas, sms) * ceil_div(nblk, 2) + 0.5;
+    if (h->attn_kv_split == 2 || c2 < 0.85 * c1) p.kv_splits = 2;
+  }
+  if (!h->attn_attr_set) {
+    GN_CHECK_CUDA(h, cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
+    h->attn_attr_set = true;
+  }
+  dim3 grid(ceil_div(Tq, AT_BQ), heads, B * p.kv_splits);
+  GN_CHECK_CUDA(h, launch_ex(h, attn_tc_kernel, grid, dim3(AT_THREADS, 1, 1), AT_SMEM_BYTES, stream, p.kv_splits, p));
+  h->launches++;
+  return GN_OK;
+}
+
+static int attention_kv_maps(gn_handle* h, AttnParams& p, const void* k, int64_t ldk, const void* v, int64_t ldv, int B,
+                             int heads, int Tk) {
+  const void* ptrs[2] = {k, v};
+  const int64_t lds[2] = {ldk, ldv};
+  CUtensorMap* maps[2] = {&p.tmK, &p.tmV};
+  for (int i = 0; i < 2; ++i) {
+    uint64_t dims[2] = {(uint64_t)heads * AT_D, (uint64_t)B * Tk};
+    uint64_t strides[1] = {(uint64_t)lds[i] * 2};
+    uint32_t box[2] = {AT_D, 128};
+    int rc = make_tmap_f16(h, maps[i], ptrs[i], 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  return GN_OK;
+}
+
 extern "C" int gn_attention(gn_handle* h, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                             int64_t ldv, void* out, int64_t ldo, int B, int heads, int Tq, int Tk, float scale,
                             void* stream) {
@@ -494,43 +643,61 @@ extern "C" int gn_attention(gn_handle* h, const void* q, int64_t ldq, const void
                  2.0 * B * heads * AT_D * (2.0 * Tq + 2.0 * Tk));
   static thread_local AttnParams p;
   memset(&p, 0, sizeof(p));
-  const void* ptrs[3] = {q, k, v};
-  const int64_t lds[3] = {ldq, ldk, ldv};
-  const int rows[3] = {B * Tq, B * Tk, B * Tk};
-  CUtensorMap* maps[3] = {&p.tmQ, &p.tmK, &p.tmV};
-  for (int i = 0; i < 3; ++i) {
-    uint64_t dims[2] = {(uint64_t)heads * AT_D, (uint64_t)rows[i]};
-    uint64_t strides[1] = {(uint64_t)lds[i] * 2};
+  {
+    uint64_t dims[2] = {(uint64_t)heads * AT_D, (uint64_t)B * Tq};
+    uint64_t strides[1] = {(uint64_t)ldq * 2};
     uint32_t box[2] = {AT_D, 128};
-    int rc = make_tmap_f16(h, maps[i], ptrs[i], 2, dims, strides, box);
+    int rc = make_tmap_f16(h, &p.tmQ, q, 2, dims, strides, box);
     if (rc) return rc;
   }
-  p.out = static_cast<__half*>(out);
-  p.ldo = ldo;
-  p.Tq = Tq;
-  p.Tk = Tk;
-  p.scale_log2 = scale * 1.4426950408889634f;
-  // KV split across a 2-CTA cluster when it shortens the critical path: cost in KV blocks = waves x blocks per CTA
-  // (+ half a block for the hand-over), and only for a clear (15 %) win: clusters schedule less freely than single CTAs
-  // (measured: 160 CTAs x 32 blocks 78 -> 68 us, 40 CTAs x 2 blocks 18 -> 14.5 us, 640 CTAs x 32 blocks 194 -> 202 us)
-  const int nblk = ceil_div(Tk, AT_BKV);
-  const int ctas = ceil_div(Tq, AT_BQ) * heads * B;
-  const int sms = h->num_sms > 0 ? h->num_sms : 148;
-  p.kv_splits = 1;
-  if (nblk >= 2 && h->attn_kv_split != 0) {
-    const double c1 = (double)ceil_div(ctas, sms) * nblk;
-    const double c2 = (double)ceil_div(2 * ctas, sms) * ceil_div(nblk, 2) + 0.5;
-    if (h->attn_kv_split == 2 || c2 < 0.85 * c1) p.kv_splits = 2;
+  int rc = attention_kv_maps(h, p, k, ldk, v, ldv, B, heads, Tk);
+  if (rc) return rc;
+  return attention_launch(h, p, B, heads, Tq, Tk, scale, out, ldo, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gn_attention_qproj(gn_handle* h, const void* x, int64_t ldx, int C, const void* wq, const float* bias,
+                                  const void* ln_stats, int ln_parts, float ln_eps, const float* ln_colsum, const void* k,
+                                  int64_t ldk, const void* v, int64_t ldv, void* out, int64_t ldo, int B, int heads, int Tq,
+                                  int Tk, float scale, void* stream) {
+  if (!h) return GN_ERR_INVALID;
+  GN_CHECK_ARG(h, x && wq && k && v && out, "gn_attention_qproj: null pointer");
+  {
+    static const char* skip_env = getenv("GENIMA_B200_SKIP");
+    if (skip_env && (atoi(skip_env) & 2)) return GN_OK;
   }
-  if (!h->attn_attr_set) {
-    GN_CHECK_CUDA(h, cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES));
-    h->attn_attr_set = true;
+  GN_CHECK_ARG(h, B > 0 && heads > 0 && Tq > 0 && Tk > 0, "gn_attention_qproj: bad shape");
+  GN_CHECK_ARG(h, C > 0 && (C % 64) == 0, "gn_attention_qproj: C (%d) must be a multiple of 64", C);
+  GN_CHECK_ARG(h, (ldx % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0 && (ldo % 8) == 0,
+               "gn_attention_qproj: row strides must be multiples of 8 elements");
+  GN_CHECK_ARG(h, !ln_stats || (ln_colsum && ln_parts > 0), "gn_attention_qproj: folded LayerNorm needs ln_colsum and ln_parts");
+  ProfScope prof(h, stream, GN_PROF_ATTENTION,
+                 4.0 * B * heads * (double)Tq * Tk * AT_D + 2.0 * B * (double)Tq * heads * AT_D * C,
+                 2.0 * B * heads * AT_D * (2.0 * Tq + 2.0 * Tk) + 2.0 * B * (double)Tq * C);
+  static thread_local AttnParams p;
+  memset(&p, 0, sizeof(p));
+  {
+    uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * Tq};
+    uint64_t strides[1] = {(uint64_t)ldx * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap_f16(h, &p.tmX, x, 2, dims, strides, box);
+    if (rc) return rc;
+    uint64_t wdims[2] = {(uint64_t)C, (uint64_t)heads * AT_D};
+    uint64_t wstr[1] = {(uint64_t)C * 2};
+    uint32_t wbox[2] = {64, 64};
+    rc = make_tmap_f16(h, &p.tmWq, wq, 2, wdims, wstr, wbox);
+    if (rc) return rc;
+    p.tmQ = p.tmX;  // (unused: keeps the descriptor prefetch valid)
   }
-  dim3 grid(ceil_div(Tq, AT_BQ), heads, B * p.kv_splits);
-  GN_CHECK_CUDA(h, launch_ex(h, attn_tc_kernel, grid, dim3(AT_THREADS, 1, 1), AT_SMEM_BYTES,
-                              static_cast<cudaStream_t>(stream), p.kv_splits, p));
-  h->launches++;
-  return GN_OK;
+  int rc = attention_kv_maps(h, p, k, ldk, v, ldv, B, heads, Tk);
+  if (rc) return rc;
+  p.qp_kblocks = C / 64;
+  p.ln_stats = static_cast<const float2*>(ln_stats);
+  p.ln_parts = ln_parts;
+  p.ln_dim = C;
+  p.ln_eps = ln_eps;
+  p.qp_colsum = ln_colsum;
+  p.qp_bias = bias;
+  return attention_launch(h, p, B, heads, Tq, Tk, scale, out, ldo, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int gn_attention_small(gn_handle* h, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

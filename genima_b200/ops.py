@@ -97,10 +97,15 @@ class Ops:
             self.handle.check(self.lib.gn_set_staged_epilogue(self.h, 0), "gn_set_staged_epilogue")
         if os.environ.get("GENIMA_B200_PAIR", "1") != "1":   # A/B: 0 = no CTA pairs, 2 = pairs wherever possible
             self.handle.check(self.lib.gn_set_gemm_pair(self.h, int(os.environ["GENIMA_B200_PAIR"])), "gn_set_gemm_pair")
+        if os.environ.get("GENIMA_B200_OCC"):   # A/B: operand-ring sizing for 1 or 2 resident CTAs per SM everywhere
+            self.handle.check(self.lib.gn_set_gemm_occupancy(self.h, int(os.environ["GENIMA_B200_OCC"])),
+                              "gn_set_gemm_occupancy")
         if os.environ.get("GENIMA_B200_ATTN_SPLIT", "1") != "1":   # A/B: 0 = no KV split, 2 = split whenever possible
             self.set_attention_kv_split(int(os.environ["GENIMA_B200_ATTN_SPLIT"]))
         # GroupNorm statistics fused into the producing GEMM epilogues (A/B switch: GENIMA_B200_GNFUSE=0)
         self.gn_fuse = os.environ.get("GENIMA_B200_GNFUSE", "1") != "0"
+        # cross-attention query projection inside the attention kernel (A/B: GENIMA_B200_QPROJ=0)
+        self.fuse_qproj = os.environ.get("GENIMA_B200_QPROJ", "1") != "0"
         # nearest-upsample folded into the following convolution (four 2x2 phase kernels; A/B: GENIMA_B200_UPFOLD=0)
         self.fold_upsample = os.environ.get("GENIMA_B200_UPFOLD", "1") != "0"
         self._gn_arena = torch.zeros(self.GN_ARENA_WORDS, dtype=torch.int64, device=self.device)
@@ -421,6 +426,38 @@ class Ops:
                                    v.stride(0), out.data_ptr(), out.stride(0), B, heads, Tq, Tk, float(scale),
                                    self._stream())
         self.handle.check(rc, "gn_attention")
+        return out
+
+    def attention_qproj(self, x: torch.Tensor, wq: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int,
+                        Tq: int, Tk: int, scale: float, bias: Optional[torch.Tensor] = None, ln=None,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """softmax(scale (x Wq^T + bias) K^T) V with the query projection inside the attention kernel (cross-attention:
+        K / V are cached per prompt).  x [B*Tq, C] fp16, wq [heads*64, C] fp16; ln = (RowStats of x, colsum, eps) folds a
+        LayerNorm of x into the projection exactly as `linear(..., ln=)` does."""
+        _f16(x, "x")
+        _f16(wq, "wq")
+        C = x.shape[1]
+        if x.dim() != 2 or x.stride(1) != 1 or x.shape[0] != B * Tq:
+            raise ValueError("x must be a [B*Tq, C] view with unit-stride columns")
+        if tuple(wq.shape) != (heads * 64, C) or not wq.is_contiguous():
+            raise ValueError(f"wq must be a contiguous [{heads * 64}, {C}] matrix")
+        for name, t in (("k", k), ("v", v)):
+            _f16(t, name)
+            if t.dim() != 2 or t.stride(1) != 1 or t.shape[1] != heads * 64 or t.shape[0] != B * Tk:
+                raise ValueError(f"{name} must be a [B*Tk, {heads * 64}] view with unit-stride columns")
+        if out is None:
+            out = torch.empty(B * Tq, heads * 64, dtype=torch.float16, device=x.device)
+        st_ptr, parts, eps, cs_ptr = None, 0, 0.0, None
+        if ln is not None:
+            stats, colsum, eps = ln
+            if stats.buf.shape[0] != B * Tq or colsum.numel() != heads * 64:
+                raise ValueError("folded LayerNorm: row statistics / colsum do not match the projection")
+            st_ptr, parts, cs_ptr = stats.buf.data_ptr(), stats.parts, _f32(colsum, "ln colsum").data_ptr()
+        rc = self.lib.gn_attention_qproj(self.h, x.data_ptr(), x.stride(0), C, wq.data_ptr(), _ptr(_f32(bias, "bias")),
+                                         st_ptr, parts, float(eps), cs_ptr, k.data_ptr(), k.stride(0), v.data_ptr(),
+                                         v.stride(0), out.data_ptr(), out.stride(0), B, heads, Tq, Tk, float(scale),
+                                         self._stream())
+        self.handle.check(rc, "gn_attention_qproj")
         return out
 
     def attention_small(self, q, k, v, B: int, heads: int, head_dim: int, Tq: int, Tk: int, scale: float,

@@ -172,8 +172,12 @@ class _Transformer2D:
             st = ops.new_row_stats(B * T, C)
             h = ops.linear(a, blk.w_o1, bias=blk.b_o1, residual=h, row_stats=st)
             # cross attention against the cached text K/V (norm2 folded into the Q projection)
-            q = ops.linear(h, blk.w_q2, bias=blk.b_q2, ln=(st, blk.cs_q2, self.ln_eps))
-            a = ops.attention(q, k2[:, :C], k2[:, C:], B, self.heads, T, tk, self.scale)
+            if ops.fuse_qproj:   # ... inside the attention kernel: one launch, no trip of Q through memory
+                a = ops.attention_qproj(h, blk.w_q2, k2[:, :C], k2[:, C:], B, self.heads, T, tk, self.scale,
+                                        bias=blk.b_q2, ln=(st, blk.cs_q2, self.ln_eps))
+            else:
+                q = ops.linear(h, blk.w_q2, bias=blk.b_q2, ln=(st, blk.cs_q2, self.ln_eps))
+                a = ops.attention(q, k2[:, :C], k2[:, C:], B, self.heads, T, tk, self.scale)
             st = ops.new_row_stats(B * T, C)
             h = ops.linear(a, blk.w_o2, bias=blk.b_o2, residual=h, row_stats=st)
             # GEGLU feed-forward (norm3 folded into the first projection)

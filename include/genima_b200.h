@@ -205,6 +205,14 @@ int gn_attention(gn_handle* h, const void* q, int64_t ldq, const void* k, int64_
                  void* out, int64_t ldo, int B, int heads, int Tq, int Tk, float scale, void* stream);
 /* Generic SIMT attention for small problems (ACT transformer: head_dim 32; any Tk); fp16 in/out, fp32 math.
  * Optional causal mask (CLIP text towers).  Replaces nn.MultiheadAttention's SDPA core. */
+/* Cross-attention with the query projection inside the kernel (diffusers Attention.to_q + scaled_dot_product_attention of
+ * BasicTransformerBlock.attn2, with norm2 folded): q = LayerNorm-folded(x W_q^T + bias) is computed per (128 queries, head)
+ * CTA from x [B * Tq][C] (row stride ldx) and W_q [heads * 64][C]; ln_stats / ln_parts / ln_colsum as in gn_epilogue
+ * (NULL ln_stats: plain projection).  k, v, out as in gn_attention.  One launch and one trip of Q through memory less. */
+int gn_attention_qproj(gn_handle* h, const void* x, int64_t ldx, int C, const void* wq, const float* bias,
+                       const void* ln_stats, int ln_parts, float ln_eps, const float* ln_colsum, const void* k, int64_t ldk,
+                       const void* v, int64_t ldv, void* out, int64_t ldo, int B, int heads, int Tq, int Tk, float scale,
+                       void* stream);
 int gn_attention_small(gn_handle* h, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                        int64_t ldv, void* out, int64_t ldo, int B, int heads, int head_dim, int Tq, int Tk,
                        float scale, int causal, void* stream);

@@ -81,3 +81,49 @@ def test_attention_small(ops, B, heads, d, Tq, Tk, causal):
     out = ops.attention_small(q.cuda(), k.cuda(), v.cuda(), B, heads, d, Tq, Tk, scale, causal=causal)
     ref = ops_ref.attention_ref(q, k, v, B, heads, d, Tq, Tk, scale, causal=causal)
     report_close(f"attention_small B{B} h{heads} d{d} {Tq}x{Tk} causal={causal}", out, ref)
+
+
+@pytest.mark.parametrize("B,heads,Tq,Tk,use_ln", [(1, 5, 4096, 77, True), (1, 10, 1024, 77, True), (1, 20, 256, 77, True),
+                                                  (1, 20, 64, 77, True), (2, 3, 200, 77, True), (1, 2, 130, 300, False),
+                                                  (1, 5, 4096, 77, False)])
+def test_attention_qproj_fused(ops, B, heads, Tq, Tk, use_ln):
+    """gn_attention_qproj: the cross-attention query projection (with the block's LayerNorm folded, as BasicTransformerBlock
+    norm2 -> attn2.to_q) runs inside the attention kernel.  Checked against (i) the fp32 reference of LayerNorm -> Linear
+    -> attention and (ii) the two-launch device path (gn_linear with ln= followed by gn_attention): the fused kernel rounds
+    Q to fp16 at the same point, so the two device paths agree to the last bit or two."""
+    import torch.nn.functional as F
+
+    from genima_b200.packing import fold_layer_norm
+
+    d = 64
+    C = heads * d
+    g = torch.Generator().manual_seed(B * 1000 + Tq + heads)
+    a = torch.randn(B * Tq, C, generator=g).to(torch.float16)
+    w0 = (torch.randn(C, C, generator=g) * C ** -0.5).to(torch.float16)
+    res = (torch.randn(B * Tq, C, generator=g) + 0.5).to(torch.float16)          # non-zero row means
+    gamma = 1.0 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    wq = (torch.randn(C, C, generator=g) * C ** -0.5).to(torch.float16)
+    bq = torch.randn(C, generator=g) * 0.1
+    k = _rand((B * Tk, C), 21)
+    v = _rand((B * Tk, C), 22)
+    scale = d ** -0.5
+    # x = the output of a producing GEMM (that is where the row statistics of a folded LayerNorm come from)
+    st = ops.new_row_stats(B * Tq, C)
+    x = ops.linear(a.cuda(), w0.cuda(), residual=res.cuda(), row_stats=st)
+    xf = x.cpu().float()
+    if use_ln:
+        q_ref = F.linear(F.layer_norm(xf, (C,), gamma, beta, 1e-5), wq.float(), bq)
+        wg, colsum, bias_f = fold_layer_norm(wq.cuda(), gamma.cuda(), beta.cuda(), bias=bq.cuda())
+        ln = (st, colsum, 1e-5)
+    else:
+        q_ref = F.linear(xf, wq.float(), bq)
+        wg, bias_f, ln = wq.cuda(), bq.cuda(), None
+    ref = ops_ref.attention_ref(q_ref.to(torch.float16), k, v, B, heads, d, Tq, Tk, scale)
+    fused = ops.attention_qproj(x, wg, k.cuda(), v.cuda(), B, heads, Tq, Tk, scale, bias=bias_f, ln=ln)
+    q_dev = ops.linear(x, wg, bias=bias_f, ln=ln)
+    two = ops.attention(q_dev, k.cuda(), v.cuda(), B, heads, Tq, Tk, scale)
+    tol = float(v.abs().max())
+    print(f"qproj fused vs two-launch: max |diff| {float((fused.float() - two.float()).abs().max()):.3e}")
+    assert float((fused.float() - two.float()).abs().max()) <= 2e-3 * tol
+    report_close(f"attention+qproj B{B} h{heads} {Tq}x{Tk} ln={use_ln}", fused, ref, rtol=2e-3, atol=3e-4 * tol)
