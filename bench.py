@@ -694,7 +694,18 @@ def main():
                          "torch.compile reduce-overhead / max-autotune (minutes)")
     ap.add_argument("--autoencoder", default="", help="'taesd': decode with AutoencoderTiny (reference option "
                                                       "eval_cfg.autoencoder); default: the KL-VAE of the headline config")
+    ap.add_argument("--replay", default="", metavar="TASKSxEPISODES[xIN_FLIGHT]",
+                    help="BASELINE configs[3]/[4] instead of the step benchmark: the episode-parallel evaluation replay "
+                         "(genima_b200.eval_replay) sharded over the launched ranks, e.g. 25x25x4 under torchrun "
+                         "--nproc-per-node 8; prints its summary as the JSON line")
     args = ap.parse_args()
+    if args.replay:
+        from genima_b200 import eval_replay
+
+        parts = [int(v) for v in args.replay.lower().split("x")]
+        argv = ["--tasks", str(parts[0]), "--episodes", str(parts[1]), "--preset", args.preset, "--denoise-steps",
+                str(args.denoise_steps), "--episodes-in-flight", str(parts[2] if len(parts) > 2 else 1)]
+        return eval_replay.main(argv)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

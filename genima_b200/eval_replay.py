@@ -107,6 +107,96 @@ def run_units_batched(units: Sequence[Tuple[str, int]],
     return records
 
 
+def run_units_async(units: Sequence[Tuple[str, int]],
+                    agent_step: Callable[[np.ndarray, np.ndarray, int, Sequence[bool]], np.ndarray], in_flight: int,
+                    size: int = 256, episode_length: int = 200, diffusion_seed: int = 2,
+                    reseed: Callable[[int, int], None] = lambda slot, seed: None, sim_delay: Callable[[int], float] = None,
+                    gather_window_s: float = 2e-4) -> List[dict]:
+    """Asynchronous variant of run_units_batched: `in_flight` simulator workers (threads; one episode each at a time, the
+    next unit of the shard when it finishes) post their observations to a request queue, and ONE server loop batches
+    whatever is ready (waiting at most `gather_window_s` for stragglers once a request is there) into a single agent-step
+    call.  A slow simulator step therefore delays only its own episode, never the batch (the lock-step loop waits for the
+    slowest env every step).  Worker i always uses batch slot i and the generator of that slot, re-seeded when a new
+    episode starts there, so an episode's noise stream does not depend on what its neighbours do.  `sim_delay(slot)`:
+    optional extra seconds per env.step (tests / what-if runs)."""
+    import queue
+    import threading
+
+    todo = list(units)
+    todo_lock = threading.Lock()
+    requests: "queue.Queue" = queue.Queue()
+    replies = [queue.Queue(maxsize=1) for _ in range(in_flight)]
+    records: List[dict] = []
+    rec_lock = threading.Lock()
+    live = [in_flight]
+
+    def worker(slot: int):
+        while True:
+            with todo_lock:
+                unit = todo.pop(0) if todo else None
+            if unit is None:
+                break
+            task, ep = unit
+            env = StubEnv(task, ep, size=size, episode_length=episode_length)
+            steps, done, actions, t_wait = 0, False, None, 0.0
+            first = True
+            while not done:
+                views, qpos = env.observe()
+                t0 = time.perf_counter()
+                requests.put((slot, views, qpos, first))
+                actions = replies[slot].get()
+                t_wait += time.perf_counter() - t0
+                first = False
+                if sim_delay is not None:
+                    time.sleep(sim_delay(slot))
+                done = env.step(actions)
+                steps += 1
+            with rec_lock:
+                records.append({"task": task, "episode": ep, "agent_steps": steps, "sim_steps": env.t,
+                                "mean_step_time": t_wait / max(steps, 1), "checksum": float(np.abs(actions).sum())})
+        requests.put((slot, None, None, False))      # this worker is done
+
+    threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(in_flight)]
+    for t in threads:
+        t.start()
+    last_views, last_qpos = None, None
+    k = 0
+    while live[0] > 0:
+        batch = [requests.get()]
+        deadline = time.perf_counter() + gather_window_s
+        while len(batch) < live[0]:
+            try:
+                batch.append(requests.get(timeout=max(0.0, deadline - time.perf_counter())))
+            except queue.Empty:
+                break
+        work = []
+        for slot, views, qpos, first in batch:
+            if views is None:
+                live[0] -= 1
+            else:
+                if first:
+                    reseed(slot, diffusion_seed)
+                work.append((slot, views, qpos))
+        if not work:
+            continue
+        if last_views is None:
+            last_views, last_qpos = work[0][1], work[0][2]
+        v = [last_views] * in_flight
+        q = [last_qpos] * in_flight
+        active = [False] * in_flight
+        for slot, views, qpos in work:
+            v[slot], q[slot], active[slot] = views, qpos, True
+        actions = agent_step(np.stack(v), np.stack(q), k, active)
+        k += 1
+        for slot, _, _ in work:
+            replies[slot].put(np.array(actions[slot]))
+    for t in threads:
+        t.join()
+    order = {u: i for i, u in enumerate(units)}
+    records.sort(key=lambda r: order[(r["task"], r["episode"])])
+    return records
+
+
 def summarize(records: List[dict], wall_s: float, world: int) -> dict:
     steps = sum(r["agent_steps"] for r in records)
     return {"episodes": len(records), "agent_steps": steps, "wall_s": wall_s, "n_gpus": world,
@@ -133,6 +223,9 @@ def main(argv=None):
     ap.add_argument("--out", default="")
     ap.add_argument("--episodes-in-flight", type=int, default=1,
                     help="independent episodes batched into one agent-step call per GPU (1 = the reference's serial loop)")
+    ap.add_argument("--async-sim", action="store_true",
+                    help="simulator worker threads feed a batching GPU server (run_units_async) instead of advancing the "
+                         "episodes in flight in lock-step")
     args = ap.parse_args(argv)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,7 +233,9 @@ def main(argv=None):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL's INIT lines (communicator size) stay visible: they prove how many ranks joined; the JSON line is printed last
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     tiny = args.preset == "tiny"
     ucfg, vcfg, acfg = (UNetConfig.tiny(), VAEConfig.tiny(), ACTConfig.tiny()) if tiny else (UNetConfig(), VAEConfig(), ACTConfig())
@@ -163,11 +258,15 @@ def main(argv=None):
     pin_q = torch.empty(E, acfg.state_dim, dtype=torch.float32).pin_memory()
     ctx_e, task_e = ctx.repeat(E, 1, 1), task_emb.repeat(E, 1)
 
-    def agent_step_batched(views, qpos, _k, _active):
+    zero_lat = torch.zeros((1, 4, S // 4, S // 4), device=dev, dtype=torch.float16)
+
+    def agent_step_batched(views, qpos, _k, active):
         pin_v.copy_(torch.from_numpy(views))
         pin_q.copy_(torch.from_numpy(qpos).reshape(E, -1))
-        # diffusers prepare_latents, one generator per episode: every episode sees the noise it would see on its own
-        lat = torch.cat([torch.randn((1, 4, S // 4, S // 4), generator=g, device=dev, dtype=torch.float16) for g in gens])
+        # diffusers prepare_latents, one generator per episode: every episode sees the noise it would see on its own (an
+        # idle slot draws nothing, so its generator does not move while its simulator is busy)
+        lat = torch.cat([torch.randn((1, 4, S // 4, S // 4), generator=g, device=dev, dtype=torch.float16) if on else zero_lat
+                         for g, on in zip(gens, active)])
         out = step(pin_v.to(dev, non_blocking=True), lat, pin_q.to(dev, non_blocking=True), task_e, prompt_embeds=ctx_e)
         return out["a_hat"].float().cpu().numpy()                                                    # the step's sync point
 
@@ -176,6 +275,13 @@ def main(argv=None):
 
     units = gd.shard_units(RLBENCH_25[:args.tasks], args.episodes, rank, world)
     w_views, w_qpos = StubEnv("warm", 0, S).observe()
+    if world > 1:
+        # rank 0 measures the GEMM tile configurations on its first pass, every other rank adopts them BEFORE it captures
+        # its graph: all ranks then launch identical kernels and an episode gives the same bits wherever it is sharded
+        if rank == 0:
+            agent_step_batched(np.stack([w_views] * E), np.stack([w_qpos] * E), 0, [True] * E)
+        dist.barrier(device_ids=[local])
+        gd.sync_tune_caches(pipe.all_ops(), src=0)
     agent_step_batched(np.stack([w_views] * E), np.stack([w_qpos] * E), 0, [True] * E)   # graph capture, untimed
     if world > 1:
         dist.barrier(device_ids=[local])
@@ -183,6 +289,9 @@ def main(argv=None):
     if E == 1:
         recs = run_units(units, agent_step, size=S, episode_length=args.episode_length,
                          reseed=lambda s: gens[0].manual_seed(s))
+    elif args.async_sim:
+        recs = run_units_async(units, agent_step_batched, E, size=S, episode_length=args.episode_length,
+                               reseed=lambda slot, s: gens[slot].manual_seed(s))
     else:
         recs = run_units_batched(units, agent_step_batched, E, size=S, episode_length=args.episode_length,
                                  reseed=lambda slot, s: gens[slot].manual_seed(s))
@@ -192,6 +301,7 @@ def main(argv=None):
     if rank == 0:
         out = summarize(allrecs, wall, world)
         out["episodes_in_flight_per_gpu"] = E
+        out["scheduling"] = "serial" if E == 1 else ("async sim workers -> batching server" if args.async_sim else "lock-step")
         print(json.dumps(out), flush=True)
         if args.out:
             with open(args.out, "w") as f:

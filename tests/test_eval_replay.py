@@ -65,3 +65,34 @@ def test_batched_episode_loop_matches_the_serial_one():
     assert seeds == [(0, 2), (1, 2), (0, 2)]
     assert [(r["task"], r["episode"], r["agent_steps"], r["sim_steps"], r["checksum"]) for r in serial] == \
            [(r["task"], r["episode"], r["agent_steps"], r["sim_steps"], r["checksum"]) for r in batched]
+
+
+def test_async_sim_workers_give_the_serial_records():
+    """Simulator worker threads + batching server (run_units_async): every episode sees its own observations in order,
+    finishes with the serial loop's step counts and checksums, and is re-seeded when it starts in a slot -- also when one
+    simulator is much slower than the others (its episode lags, the others are not held back)."""
+    from genima_b200.eval_replay import run_units_async
+
+    units = [("open_box", 0), ("open_box", 1), ("push_button", 0), ("push_button", 1), ("close_jar", 0)]
+    seeds, batch_sizes = [], []
+
+    def fake_serial(views, qpos, k):
+        return np.full((20, 8), float(views[0, 0, 0, 0]), dtype=np.float32)
+
+    def fake_batched(views, qpos, k, active):
+        assert views.shape == (3, 4, 64, 64, 3) and qpos.shape == (3, 1, 8) and len(active) == 3 and any(active)
+        batch_sizes.append(sum(active))
+        return np.stack([np.full((20, 8), float(v[0, 0, 0, 0]), dtype=np.float32) for v in views])
+
+    serial = run_units(units, fake_serial, size=64, episode_length=200)
+    key = lambda r: (r["task"], r["episode"], r["agent_steps"], r["sim_steps"], r["checksum"])   # noqa: E731
+    for delay in (None, lambda slot: 0.004 if slot == 0 else 0.0):
+        seeds.clear()
+        batch_sizes.clear()
+        recs = run_units_async(units, fake_batched, 3, size=64, episode_length=200,
+                               reseed=lambda slot, s: seeds.append((slot, s)), sim_delay=delay)
+        assert [key(r) for r in recs] == [key(r) for r in serial]
+        assert len(seeds) == len(units) and all(s == 2 for _, s in seeds)
+        assert sum(batch_sizes) == sum(r["agent_steps"] for r in serial)
+    # with one slow simulator the server did not wait for it: some calls ran with fewer than all slots active
+    assert min(batch_sizes) < 3

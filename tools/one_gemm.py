@@ -1,7 +1,8 @@
 """Runs one op a few times; the LAST call sits between cudaProfilerStart/Stop so that
 `ncu --profile-from-start off --set full ...` captures the tuned configuration, not an autotuning candidate.
 Usage: python tools/one_gemm.py linear M N K [geglu|fp32out|bias_res|plain]   |   conv B H Cin Cout [stride]
-       |   attn Tq Tk heads   |   gnapply hw C bucket   |   gn hw C"""
+       |   attn Tq Tk heads   |   xattn Tq Tk heads (query projection inside)   |   gnapply hw C bucket   |   gn hw C
+       |   ln rows C   |   softmax rows cols   |   u8 (uint8 image -> NHWC fp16 and back)   |   tile (tile / untile views)"""
 import os
 import sys
 
@@ -35,6 +36,30 @@ elif kind == "attn":
     k = torch.randn(tk, c, device="cuda").half()
     v = torch.randn(tk, c, device="cuda").half()
     fn = lambda: ops.attention(q, k, v, 1, heads, tq, tk, 0.125)
+elif kind == "xattn":
+    tq, tk, heads = (int(v) for v in sys.argv[2:5])
+    c = heads * 64
+    x = torch.randn(tq, c, device="cuda").half()
+    wq = (torch.randn(c, c, device="cuda") * c ** -0.5).half()
+    k = torch.randn(tk, c, device="cuda").half()
+    v = torch.randn(tk, c, device="cuda").half()
+    bq = torch.randn(c, device="cuda")
+    fn = lambda: ops.attention_qproj(x, wq, k, v, 1, heads, tq, tk, 0.125, bias=bq)
+elif kind == "ln":
+    rows, c = int(sys.argv[2]), int(sys.argv[3])
+    x = torch.randn(rows, c, device="cuda").half()
+    g, b = torch.ones(c, device="cuda"), torch.zeros(c, device="cuda")
+    fn = lambda: ops.layer_norm(x, g, b)
+elif kind == "softmax":
+    rows, cols = int(sys.argv[2]), int(sys.argv[3])
+    x = torch.randn(rows, cols, device="cuda")
+    fn = lambda: ops.softmax_rows(x, 0.044)
+elif kind == "u8":
+    img = torch.randint(0, 255, (1, 512, 512, 3), dtype=torch.uint8, device="cuda")
+    fn = lambda: ops.nhwc_to_u8(ops.u8_to_nhwc(img, cpad=8)[..., :8].contiguous())
+elif kind == "tile":
+    views = torch.randint(0, 255, (1, 4, 256, 256, 3), dtype=torch.uint8, device="cuda")
+    fn = lambda: ops.untile_views(ops.tile_views(views))
 elif kind == "gnapply":
     # GroupNorm from statistics accumulated by the producing GEMM epilogue: `gnapply hw C bucket`
     hw, c, bucket = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
