@@ -111,11 +111,12 @@ def run_units_async(units: Sequence[Tuple[str, int]],
                     agent_step: Callable[[np.ndarray, np.ndarray, int, Sequence[bool]], np.ndarray], in_flight: int,
                     size: int = 256, episode_length: int = 200, diffusion_seed: int = 2,
                     reseed: Callable[[int, int], None] = lambda slot, seed: None, sim_delay: Callable[[int], float] = None,
-                    gather_window_s: float = 2e-4) -> List[dict]:
+                    gather_window_s: float = None) -> List[dict]:
     """Asynchronous variant of run_units_batched: `in_flight` simulator workers (threads; one episode each at a time, the
     next unit of the shard when it finishes) post their observations to a request queue, and ONE server loop batches
-    whatever is ready (waiting at most `gather_window_s` for stragglers once a request is there) into a single agent-step
-    call.  A slow simulator step therefore delays only its own episode, never the batch (the lock-step loop waits for the
+    whatever is ready (waiting at most `gather_window_s` for stragglers once a request is there; default: 30 % of the
+    running mean of the agent-step time, so a full batch is preferred as long as waiting for it is cheap) into a single
+    agent-step call.  A slow simulator step therefore delays only its own episode, never the batch (the lock-step loop waits for the
     slowest env every step).  Worker i always uses batch slot i and the generator of that slot, re-seeded when a new
     episode starts there, so an episode's noise stream does not depend on what its neighbours do.  `sim_delay(slot)`:
     optional extra seconds per env.step (tests / what-if runs)."""
@@ -161,9 +162,10 @@ def run_units_async(units: Sequence[Tuple[str, int]],
         t.start()
     last_views, last_qpos = None, None
     k = 0
+    step_ema = 0.015
     while live[0] > 0:
         batch = [requests.get()]
-        deadline = time.perf_counter() + gather_window_s
+        deadline = time.perf_counter() + (gather_window_s if gather_window_s is not None else 0.3 * step_ema)
         while len(batch) < live[0]:
             try:
                 batch.append(requests.get(timeout=max(0.0, deadline - time.perf_counter())))
@@ -186,7 +188,9 @@ def run_units_async(units: Sequence[Tuple[str, int]],
         active = [False] * in_flight
         for slot, views, qpos in work:
             v[slot], q[slot], active[slot] = views, qpos, True
+        t0 = time.perf_counter()
         actions = agent_step(np.stack(v), np.stack(q), k, active)
+        step_ema = 0.8 * step_ema + 0.2 * (time.perf_counter() - t0)
         k += 1
         for slot, _, _ in work:
             replies[slot].put(np.array(actions[slot]))
@@ -298,8 +302,13 @@ def main(argv=None):
     torch.cuda.synchronize()
     wall = gd.reduce_max(time.perf_counter() - t0, device=dev)
     allrecs = gd.gather_records(recs)
+    # which physical GPUs took part (one distinct UUID per rank proves the sharding really used `world` devices)
+    uuids = gd.gather_records([{"rank": rank, "gpu_uuid": str(torch.cuda.get_device_properties(local).uuid),
+                                "episodes": len(recs)}])
     if rank == 0:
         out = summarize(allrecs, wall, world)
+        out["gpus_active"] = len({u["gpu_uuid"] for u in uuids})
+        out["episodes_per_rank"] = [u["episodes"] for u in sorted(uuids, key=lambda u: u["rank"])]
         out["episodes_in_flight_per_gpu"] = E
         out["scheduling"] = "serial" if E == 1 else ("async sim workers -> batching server" if args.async_sim else "lock-step")
         print(json.dumps(out), flush=True)
