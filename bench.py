@@ -425,8 +425,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's own INIT lines (communicator size, transports) are left visible: they prove how many ranks joined.
         # They go to stdout BEFORE the JSON line, which is always the LAST line this program prints.
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):   # (the image presets VERSION)
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         t_c = time.perf_counter()
         dist.init_process_group("nccl", device_id=dev)
         warm = torch.ones(1, device=dev)

@@ -238,8 +238,9 @@ def main(argv=None):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL's INIT lines (communicator size) stay visible: they prove how many ranks joined; the JSON line is printed last
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):   # (the image presets VERSION)
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     tiny = args.preset == "tiny"
     ucfg, vcfg, acfg = (UNetConfig.tiny(), VAEConfig.tiny(), ACTConfig.tiny()) if tiny else (UNetConfig(), VAEConfig(), ACTConfig())
