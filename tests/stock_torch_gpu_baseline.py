@@ -99,6 +99,10 @@ def make_chain(n_steps: int, inputs=None):
     def chain():
         x = lat * sched.init_noise_sigma
         for i in range(n_steps):
+            if nets.get("compiled"):
+                # CUDA-graph trees of torch.compile (reduce-overhead / max-autotune): a new denoise iteration may reuse
+                # the memory of the previous iteration's graph outputs (eps and the residuals were consumed eagerly)
+                torch.compiler.cudagraph_mark_step_begin()
             xs = sched.scale_model_input(x, i)
             down, mid = nets["controlnet"](xs, tts[i])
             eps = nets["unet"](xs, tts[i], down, mid)
@@ -176,6 +180,7 @@ def main():
                 t0 = time.time()
                 nets["controlnet"] = torch.compile(controlnet, mode=mode, fullgraph=False)
                 nets["unet"] = torch.compile(unet, mode=mode, fullgraph=False)
+                nets["compiled"] = True
                 ms_c, got = timed(chain, args.reps, 3)
                 out[key + "_ms"] = round(ms_c, 2)
                 out[key + "_steps_per_s"] = round(1e3 / ms_c, 2)
@@ -187,6 +192,7 @@ def main():
                 out[key + "_error"] = f"{type(ex).__name__}: {str(ex)[:300]}"
             finally:
                 nets["controlnet"], nets["unet"] = controlnet, unet
+                nets["compiled"] = False
     print(json.dumps(out), flush=True)
 
 
