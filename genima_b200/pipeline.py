@@ -567,7 +567,12 @@ class B200ControlNetPipeline:
         elif output_type == "pt":
             images = (ops.nhwc_to_nchw(img, channels=3, fp32=True) / 2 + 0.5).clamp(0, 1)
         else:
-            u8 = self._to_host_u8(ops.nhwc_to_u8(img))
+            # persistent device buffer: a fresh allocation here would sit behind the replayed graph in the allocator
+            key = ("u8dev", tuple(img.shape[:3]))
+            dbuf = self._pinned.get(key)
+            if dbuf is None:
+                dbuf = self._pinned[key] = torch.empty(tuple(img.shape[:3]) + (3,), dtype=torch.uint8, device=img.device)
+            u8 = self._to_host_u8(ops.nhwc_to_u8(img, out=dbuf))
             if output_type == "np":
                 images = u8.astype(np.float32) / 255.0
             else:

@@ -50,5 +50,9 @@ with torch.inference_mode():
         e2e_step()
     pr.disable()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(30)
+st = pstats.Stats(pr, stream=s)
+st.sort_stats("tottime").print_stats(30)
 print("\n".join(s.getvalue().splitlines()[:60]))
+s2 = io.StringIO()
+pstats.Stats(pr, stream=s2).print_callers("torch.empty")   # who allocates on the timed path
+print("\n".join(s2.getvalue().splitlines()[:30]))
