@@ -90,6 +90,9 @@ class B200ControlNetPipeline:
         # gn_handle so that the per-handle GroupNorm scratch / grid-barrier words are never shared between streams.
         self.concurrent_controlnet = bool(concurrent_controlnet) and os.environ.get("GENIMA_B200_CONCURRENT", "1") != "0"   # A/B
         self.ops_side = Ops(ops.device.index, autotune=ops.autotune) if self.concurrent_controlnet else ops
+        if self.concurrent_controlnet and os.environ.get("GENIMA_B200_SIDE_OCC"):   # A/B: ring sizing of the ControlNet's kernels
+            self.ops_side.handle.check(self.ops_side.lib.gn_set_gemm_occupancy(
+                self.ops_side.h, int(os.environ["GENIMA_B200_SIDE_OCC"])), "gn_set_gemm_occupancy")
         # third handle / stream: the 13 zero-convs start as soon as both encoders have produced their skip tensor,
         # instead of running one after the other once the two encoders have joined
         self.ops_zero = Ops(ops.device.index, autotune=ops.autotune) if self.concurrent_controlnet else ops
