@@ -2,18 +2,25 @@
 //
 //   out[M, N] = epilogue( sum_k A[m, k] * W[n, k] )        fp16 operands, fp32 accumulation in TMEM
 //
-// One CTA computes a 128 x block_n output tile (block_n chosen per problem, multiple of 16, <= 256):
-//   warp 0      TMA producer: A tile [128 rows][64 fp16] and W tile [block_n rows][64 fp16] per k-block,
-//               SWIZZLE_128B, multi-stage ring guarded by full/empty mbarriers
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 MMAs per k-block),
-//               tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-5   epilogue: tcgen05.ld (one TMEM lane = one output row per thread) -> fused
-//               scale/bias/time-embedding/activation/residual/GEGLU -> fp16 stores
+// One CTA computes a 128 x block_n output tile (block_n chosen per problem, multiple of 16, <= 256); the PAIR variants
+// (tcgen05 cta_group::2) compute two consecutive m-tiles with one M = 256 MMA per k-step, each CTA staging its own A tile
+// and half of the W tile.  352 threads:
+//   warp 0      A producer: [128 rows][64 fp16] tile per k-block, SWIZZLE_128B, multi-stage ring guarded by full / empty
+//               mbarriers (+ the residual tile prefetch once the first ring-full of A tiles is on its way)
+//   warp 10     W producer: [block_n rows][64 fp16] tile per k-block; starts BEFORE griddepcontrol.wait when W is a
+//               constant weight matrix (the weight stream does not depend on the previous kernel)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (4 x K=16 MMAs per k-block), tcgen05.commit releases the smem
+//               stage / publishes the accumulator
+//   warps 2-9   epilogue: tcgen05.ld (one TMEM lane = one output row per thread) -> fused scale / bias / time-embedding
+//               row / folded LayerNorm / activation / residual / GEGLU -> fp16 -> swizzled staging tile -> TMA stores,
+//               plus the GroupNorm / LayerNorm statistics of the output for its consumer
+// Every role loop runs its whole warp on warp-uniform values and issues under elect.sync (operands in uniform registers).
 //
 // The A operand is either a plain row-major matrix (2D tensor map) or an NHWC image addressed through 4D tensor
 // maps: k-blocks walk a table of "segments" (tap (dy, dx) x 64-channel blocks); TMA's zero OOB fill implements the
 // convolution padding, per-phase tensor maps implement stride 2, and extra 1x1 segments fuse ResnetBlock2D's
-// conv_shortcut into the same accumulation.  Split-K (gridDim.z) covers the weight-streaming-bound 8x8/16x16 levels.
+// conv_shortcut into the same accumulation.  Split-K (a thread-block cluster along grid.z, partials exchanged through an
+// L2-resident workspace, deterministic rank-ordered sums) covers the shapes with too few output tiles for 148 SMs.
 #include <cooperative_groups.h>
 
 #include <algorithm>
