@@ -2058,7 +2058,7 @@ static int launch_gemm(gn_handle* h, GemmParams& p, int tiles_m, const void* W, 
         int rc = launch_config(h, p, cand[i].tc, tiles_m, W, ktot, og, stream);  // warm-up (tensor maps, smem carve-out)
         if (rc) return rc;
         float total = 1e30f;  // the fastest of `reps` timing rounds: robust against a neighbour kernel / clock hiccup
-        const int reps = cold ? 3 : 3;
+        const int reps = cold ? 3 : 5;
         for (int r = 0; r < reps; ++r) {
           if (cold) GN_CHECK_CUDA(h, cudaMemsetAsync(h->workspace, r, (size_t)h->workspace_bytes, stream));
           GN_CHECK_CUDA(h, cudaEventRecord(h->tune_ev[0], stream));
