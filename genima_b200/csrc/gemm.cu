@@ -1200,6 +1200,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.num_kblocks, kb_begin + p.kb_per_split);
   const int num_it = kb_end - kb_begin;
+  // short-K matrix problems: the two producer warps share the A tiles (even k-blocks: warp 0, odd: the W warp)
+  const bool share_a = p.mode == 0 && num_it <= stages && num_it >= 2;
   if (warp == W_WARP) {
     // ------------------------------------------------------------------ W producer (whole warp, one elected lane issues)
     if (!p.w_prefetch) pdl_wait();
@@ -1230,6 +1232,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         if (++s == stages) {
           s = 0;
           ph ^= 1;
+        }
+      }
+    }
+    if (share_a) {
+      // short-K matrix problem (every k-block has its own ring slot, so nothing above had to wait): this warp is free
+      // and takes the odd A tiles -- the A tiles are issued at twice the rate of a single thread
+      if (p.w_prefetch) pdl_wait();  // A is an activation of the previous kernel
+      const int am0 = (int)(PAIR ? blockIdx.x : blockIdx.y) * BLOCK_M;
+      if constexpr (pair) {
+        const uint32_t fb0 = mapa_shared(smem_u32(full_bar), crank & ~1u);
+        for (int it = 1; it < num_it; it += 2) {
+          if (elect_one()) {
+            if (half == 0) mbar_arrive_expect_tx(&full_bar[it], 2u * (uint32_t)p.a_stage_bytes);
+            tma_load_2d_pair(smem_a + it * p.a_stage_bytes, &p.tmA[0], fb0 + 8u * it, (kb_begin + it) * BLOCK_K, am0);
+          }
+          __syncwarp();
+        }
+      } else {
+        for (int it = 1; it < num_it; it += 2) {
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[it], (uint32_t)p.a_stage_bytes);
+            tma_load_2d(smem_a + it * p.a_stage_bytes, &p.tmA[0], &full_bar[it], (kb_begin + it) * BLOCK_K, am0);
+          }
+          __syncwarp();
         }
       }
     }
@@ -1289,7 +1315,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
           }
         }
       };
-      const int res_after = min(stages, num_it) - 1;  // iteration after which the residual is requested
+      // iteration after which the residual is requested (with shared A tiles: this warp's last, even, k-block)
+      const int res_after = share_a ? ((num_it - 1) & ~1) : min(stages, num_it) - 1;
+      const int a_step = share_a ? 2 : 1;
       if (res_after < 0 && elect_one()) issue_residual();
       __syncwarp();
       int seg = 0, seg_start = 0;
@@ -1308,7 +1336,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
         // ---- CTA pair: every load completes on the LEADER's barrier, which the leader arms with the bytes of both CTAs;
         // each CTA waits for its own copy of the empty barrier (the leader's commit arrives on both)
         const uint32_t fb0 = mapa_shared(smem_u32(full_bar), crank & ~1u);
-        for (int it = 0; it < num_it; ++it) {
+        for (int it = 0; it < num_it; it += a_step) {
+          if (share_a) s = it;  // (one ring slot per k-block, first use: no wait needed, parity 1 passes at once)
           mbar_wait(&empty_bar[s], ph);
           if (elect_one()) {
             if (half == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * a_bytes);
@@ -1330,7 +1359,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const __grid_c
           }
         }
       } else {
-        for (int it = 0; it < num_it; ++it) {
+        for (int it = 0; it < num_it; it += a_step) {
+          if (share_a) s = it;
           mbar_wait(&empty_bar[s], ph);
           if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[s], a_bytes);
