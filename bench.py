@@ -428,6 +428,8 @@ def run_ours(args):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):   # (the image presets VERSION)
             os.environ["NCCL_DEBUG"] = "INFO"
             os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            # ... on stderr: NCCL also logs at teardown, and the JSON line must stay the last line of stdout
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         t_c = time.perf_counter()
         dist.init_process_group("nccl", device_id=dev)
         warm = torch.ones(1, device=dev)

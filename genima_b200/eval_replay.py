@@ -241,6 +241,8 @@ def main(argv=None):
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):   # (the image presets VERSION)
             os.environ["NCCL_DEBUG"] = "INFO"
             os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+            # ... on stderr: NCCL also logs at teardown, and the JSON line must stay the last line of stdout
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     tiny = args.preset == "tiny"
     ucfg, vcfg, acfg = (UNetConfig.tiny(), VAEConfig.tiny(), ACTConfig.tiny()) if tiny else (UNetConfig(), VAEConfig(), ACTConfig())
